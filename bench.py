@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the recursive-CV hot path on B200.
+
+One "step" = one optimisation iteration of optimize.py:104-132 for method
+cv_ps on synthetic data: state rotation + majorant, correlated two-state
+render (theta_{i-1}, theta_i), film develop, recursive CV / Welford update,
+L1 loss + image gradient, volpathsimple path-replay adjoint (pass 1 + pass 2)
+scatter-adding into the sigma_t/albedo gradient grid, [all-reduce at N>1],
+Adam + clamp.  Metric: Mpaths/s (paths = lanes traced by the three passes)
+and ms per iteration.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N > 1 is launched by torchrun (one rank per GPU, NCCL): every rank renders a
+disjoint range of the samples of each pixel (global PCG32 lane indices), the
+film accumulators and the gradient grid are all-reduced before the CV update
+and the Adam step.  Weak scaling: 64 spp per GPU.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+METRIC = "Mpaths/s (two-state CV render + adjoint)"
+UNIT = "Mpaths/s"
+# BASELINE.json configs[1]: 256^3 grid, 512x512, 64 spp, cv_ps (environment-lit variant)
+WORKLOAD = dict(grid=256, width=512, height=512, spp_per_gpu=64, kind="cube")
+SEED0 = 17   # the reference discards iterations 0..16 when benchmarking (optimize.py:105)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", type=int, default=WORKLOAD["grid"])
+    ap.add_argument("--res", type=int, default=WORKLOAD["width"])
+    ap.add_argument("--spp", type=int, default=WORKLOAD["spp_per_gpu"], help="samples per pixel per GPU")
+    ap.add_argument("--kind", default=WORKLOAD["kind"])
+    ap.add_argument("--tracer", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-sample-spp", type=int, default=0, help="spp range of the CPU sample (0 = auto)")
+    return ap.parse_args()
+
+
+def workload_name(a, n_gpus):
+    return (f"synthetic {a.kind} {a.grid}^3 sigma_t+albedo two-state grid, {a.res}x{a.res}, {a.spp * n_gpus} spp "
+            f"({a.spp}/GPU), cv_ps, constant environment emitter, box filter, max_depth=rr_depth=64")
+
+
+# ----------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md): SM clock + throttle reasons during the timed region
+# ----------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------
+# CPU arm: the oracle (CPU restatement of the reference path) on the host cores
+# ----------------------------------------------------------------------------
+def cpu_iteration_sample(a, n_gpus, sample_spp, threads):
+    """Times one bounded sample of the step on the CPU: samples [0, sample_spp) of every pixel
+    for the two-state render and for both adjoint passes, on the same grids/film/seeds."""
+    import oracle as O
+    from recursive_control_variates_b200.runtime import tea32
+    from recursive_control_variates_b200.scene import SceneConfig
+    from recursive_control_variates_b200.synthetic import make_medium
+    O.build()
+    desc = SceneConfig(width=a.res, height=a.res).to_desc()
+    old, new = make_medium(a.grid, a.kind, 0.0), make_medium(a.grid, a.kind, 5e-3)
+    mo, mn = O.OracleMedium(desc, *old), O.OracleMedium(desc, *new)
+    spp = a.spp * n_gpus
+    npix = a.res * a.res
+    seed = SEED0
+    seed_grad = tea32(seed, 1)[0]
+    grad_img = np.full((a.res, a.res, 3), 1.0 / (npix * 3), np.float32)
+    film_w = np.full((a.res, a.res), float(spp), np.float32)
+    t0 = time.perf_counter()
+    O.render_twostates_accum(desc, mo, mn, seed, spp, 0, sample_spp, threads=threads)
+    t1 = time.perf_counter()
+    O.vps_backward(desc, mn, seed_grad, spp, grad_img, 0, sample_spp, threads=threads, film_w=film_w)
+    t2 = time.perf_counter()
+    paths = npix * sample_spp * 3
+    return paths, t2 - t0, t1 - t0, t2 - t1
+
+
+def run_reference(a):
+    """--impl reference: the reference cannot be installed (no Mitsuba 3 / Dr.Jit wheel);
+    its CPU restatement (oracle/, kind 'port') is timed on all host cores instead."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_gpus = a.gpus
+    import oracle as O
+    threads = O.default_threads()
+    sample_spp = a.cpu_sample_spp or 1
+    for _ in range(min(a.warmup, 1)):
+        cpu_iteration_sample(a, n_gpus, 1, threads)
+    times, paths = [], 0
+    for _ in range(a.steps):
+        paths, t, _, _ = cpu_iteration_sample(a, n_gpus, sample_spp, threads)
+        times.append(t)
+    t = float(np.mean(times))
+    v = paths / t / 1e6
+    sample = f"samples [0,{sample_spp}) of {a.spp * n_gpus} spp of every pixel, all three passes, same grids/film/seeds"
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps,
+           "warmup": a.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": workload_name(a, n_gpus), "note": "CPU restatement of the reference (oracle/), "
+                      "bounded sample per step; ms_per_step is for the sample"},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+# ----------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from recursive_control_variates_b200 import _abi
+    from recursive_control_variates_b200.runtime import Context, tea32
+    from recursive_control_variates_b200.scene import SceneConfig
+    from recursive_control_variates_b200.synthetic import make_medium
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_gpus = world
+    dev = torch.device("cuda", local)
+
+    W = H = a.res
+    spp_total = a.spp * n_gpus
+    spp_b, spp_e = rank * a.spp, (rank + 1) * a.spp
+    desc = SceneConfig(width=W, height=H).to_desc()
+    ctx = Context(local)
+    ctx.set_scene(desc)
+    ctx.set_tracer(a.tracer)
+
+    # synthetic theta_{i-1}, theta_i and a target (generated on the host once; resident in HBM before timing)
+    old, new = make_medium(a.grid, a.kind, 0.0), make_medium(a.grid, a.kind, 5e-3)
+    tgt = make_medium(a.grid, a.kind, 5e-2)
+    sigma = torch.from_numpy(new[0]).to(dev); albedo = torch.from_numpy(new[1]).to(dev)
+    ctx.rotate(torch.from_numpy(tgt[0]).to(dev), torch.from_numpy(tgt[1]).to(dev))
+    ref = ctx.develop(ctx.render_primal_accum(1, 17843, min(spp_total, 64)))   # utils.py:98-111 reference render
+    ctx.rotate(torch.from_numpy(old[0]).to(dev), torch.from_numpy(old[1]).to(dev))
+    m_s, v_s = torch.zeros_like(sigma), torch.zeros_like(sigma)
+    m_a, v_a = torch.zeros_like(albedo), torch.zeros_like(albedo)
+    acc = (torch.zeros(H, W, 4, device=dev), torch.zeros(H, W, 4, device=dev))
+    Himg, Fimg = torch.zeros(H, W, 3, device=dev), torch.zeros(H, W, 3, device=dev)
+    cv = ctx.new_cv_state()
+    state = {"it": 0, "stats_n": 0, "t": 0}
+    npix = W * H
+    paths_per_step = npix * a.spp * 3 * n_gpus     # primal + adjoint pass 1 + adjoint pass 2, all ranks
+
+    def step(i):
+        seed = SEED0 + i
+        seed_grad = tea32(seed, 1)[0]
+        ctx.rotate(sigma, albedo)                                            # scene_params.update(opt)
+        acc[0].zero_(); acc[1].zero_()
+        ctx.render_twostates_accum(seed, spp_total, spp_b, spp_e, out=acc)   # mi.render -> render_twostates
+        if world > 1:
+            dist.all_reduce(acc[0]); dist.all_reduce(acc[1])
+        ctx.develop(acc[0], Himg); ctx.develop(acc[1], Fimg)
+        ctx.cv_update(Himg, Fimg, cv, state["it"], 1, state["stats_n"], 0.9, 0.999)
+        state["stats_n"] += state["it"] > 0
+        state["it"] += 1
+        loss, g = ctx.loss_grad(_abi.RCV_LOSS_L1, cv["img"], ref)           # l1_loss + dr.backward seed
+        ctx.grad_zero()
+        ctx.render_backward(seed_grad, spp_total, g, spp_b, spp_e)           # adjoint_integrator.render_backward
+        if world > 1:
+            dist.all_reduce(ctx.grad_packed())
+        state["t"] += 1
+        ctx.adam_step(sigma, albedo, m_s, v_s, m_a, v_a, state["t"], 5e-3, 1e-2)   # opt.step() + clamp
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(a.warmup):
+        step(i)
+    barrier()
+    ctx.counters(True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(a.steps):
+        loss = step(a.warmup + i)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    cnt = ctx.counters(True)
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / a.steps
+    value = paths_per_step / (ms_per_step * 1e-3) / 1e6
+
+    # ---- per-kernel timing (CUDA events on the launching stream) + roofline of the dominant kernel
+    peak, peak_src = measured_peaks()
+
+    def time_kernel(fn, reps=3):
+        fn(); torch.cuda.synchronize(); ctx.counters(True)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(reps):
+            fn()
+        a1.record(); torch.cuda.synchronize()
+        c = ctx.counters(True).astype(np.float64) / reps
+        return a0.elapsed_time(a1) / reps, c
+
+    g_img = torch.full((H, W, 3), 1.0 / (npix * 3), device=dev)
+    k1_ms, k1_c = time_kernel(lambda: ctx.render_twostates_accum(SEED0, spp_total, spp_b, spp_e, out=acc))
+    k6_ms, k6_c = time_kernel(lambda: ctx.render_backward(tea32(SEED0, 1)[0], spp_total, g_img, spp_b, spp_e))
+    lanes = npix * a.spp
+    # algorithmic bytes (SURVEY.md §8d / DESIGN.md §5)
+    k1_bytes = k1_c[0] * 64 + k1_c[1] * 192 + lanes * (16 + 32)
+    k6_bytes = k6_c[2] * 32 + k6_c[3] * (96 + 32) + k6_c[4] * 32 + k6_c[5] * 96 + lanes * 2 * 16
+    kernels = {
+        "twostate_primal": {"ms": k1_ms, "algorithmic_gb": k1_bytes / 1e9, "gbs": k1_bytes / k1_ms / 1e6,
+                            "collisions": k1_c[0], "scatters": k1_c[1], "mpaths_s": lanes / k1_ms / 1e3},
+        "volpathsimple_adjoint": {"ms": k6_ms, "algorithmic_gb": k6_bytes / 1e9, "gbs": k6_bytes / k6_ms / 1e6,
+                                  "collisions": k6_c[2], "scatters": k6_c[3], "grad_sites": k6_c[4] + k6_c[5],
+                                  "mpaths_s": 2 * lanes / k6_ms / 1e3},
+    }
+    dom = max(kernels, key=lambda k: kernels[k]["ms"])
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": kernels[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "share_of_step": kernels[dom]["ms"] / ms_per_step}
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host memory, copies inside the timed region)
+    e2e = None
+    if not a.no_e2e and world == 1:
+        pin = lambda t_: t_.detach().cpu().contiguous().pin_memory()
+        hs, ha, href = pin(sigma), pin(albedo), pin(ref)
+        himg, hloss = torch.zeros(H, W, 3).pin_memory(), torch.zeros(1).pin_memory()
+        hgs, hga = torch.zeros_like(hs).pin_memory(), torch.zeros_like(ha).pin_memory()
+
+        def e2e_step(i, reset=False):
+            seed = SEED0 + i
+            ctx.cv_iteration_host(hs, ha, href, seed, spp_total, tea32(seed, 1)[0], spp_total, himg, hloss, hgs, hga, reset=reset)
+
+        e2e_step(0, reset=True); e2e_step(1)
+        torch.cuda.synchronize()
+        n_e2e = max(2, min(a.steps, 3))
+        t0 = time.perf_counter()
+        for i in range(n_e2e):
+            e2e_step(2 + i)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / n_e2e
+        h2d = (hs.numel() + ha.numel() + href.numel()) * 4
+        d2h = (himg.numel() + 1 + hgs.numel() + hga.numel()) * 4
+        e2e = {"value": npix * a.spp * 3 / dt / 1e6, "unit": UNIT, "ms_per_step": dt * 1e3, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "api": "rcv_cv_iteration_host (render_twostates + cv update + loss + adjoint; "
+               "host-side optimiser)"}
+
+    # ---- CPU baseline (rank 0, N = 1 only): the oracle on the host cores, bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        import oracle as O
+        threads = O.default_threads()
+        sample_spp = a.cpu_sample_spp or 1
+        paths, tt, t_primal, t_adj = cpu_iteration_sample(a, n_gpus, sample_spp, threads)
+        cpu = {"value": paths / tt / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"samples [0,{sample_spp}) of {spp_total} spp of every pixel ({paths} paths): two-state render "
+                         f"{t_primal:.2f}s + volpathsimple adjoint {t_adj:.2f}s",
+               "seconds": tt}
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps, "warmup": a.warmup,
+               "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f32", "data": "synthetic",
+               "config": {"workload": workload_name(a, n_gpus), "grid": a.grid, "film": [W, H], "spp_total": spp_total,
+                          "spp_per_gpu": a.spp, "paths_per_step": paths_per_step, "parallelism": f"spp-shard x{n_gpus}",
+                          "l2": "inputs larger than L2 (two-state grids %d MiB)" % (a.grid ** 3 * 40 // 2 ** 20),
+                          "tracer": "persistent" if a.tracer == 0 else "simple", "loss_last": float(loss.item())},
+               "clocks": clocks, "gpu_launches": int(cnt[7]), "roofline": roofline, "kernels": kernels,
+               "e2e": e2e, "cpu_baseline": cpu}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

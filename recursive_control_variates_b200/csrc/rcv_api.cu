@@ -1,0 +1,507 @@
+// rcv_api.cu — the C-ABI of librcv_b200.so (include/rcv_b200.h): context,
+// packed medium state, and the entry points the reference's plugin classes
+// call in place of their Dr.Jit code.  No torch types, no hidden host syncs
+// except in the *_host functions.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/rcv_b200.h"
+#include "rcv_internal.h"
+
+using namespace rcv;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+int fail_cuda(cudaError_t e, const char *what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return RCV_ERR_CUDA;
+}
+#define CK(expr)                                              \
+    do {                                                      \
+        cudaError_t _e = (expr);                              \
+        if (_e != cudaSuccess) return fail_cuda(_e, #expr);   \
+    } while (0)
+
+}  // namespace
+
+struct rcv_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    int tracer = RCV_TRACER_WAVEFRONT;
+    bool has_scene = false;
+    rcv_scene_desc desc{};
+    SceneK S{};
+    // packed medium state
+    int nx = 0, ny = 0, nz = 0;
+    size_t nvox = 0;
+    float2 *sig2 = nullptr;
+    float *sig1 = nullptr;
+    float4 *alb2 = nullptr;
+    float4 *grad = nullptr;
+    float *majorants = nullptr;
+    float *block_max = nullptr;
+    int n_rot_blocks = 0;
+    // scratch
+    Counters *counters = nullptr;
+    unsigned long long *work = nullptr;
+    uint64_t launches = 0;
+    float *film_w = nullptr;
+    size_t film_w_pix = 0;
+    double *loss_partial = nullptr;
+    int n_partial = 0;
+    // state of rcv_cv_iteration_host
+    struct {
+        size_t nvox = 0, npix = 0;
+        float *sigma = nullptr, *albedo = nullptr, *ref = nullptr;
+        float *acc = nullptr;      // 2 x (H,W,4)
+        float *HF = nullptr;       // 2 x (H,W,3)
+        float *cv = nullptr;       // 8 x (H,W,3): img v_n w_s mean_x mean_y var_x var_y cov
+        float *grad_img = nullptr, *loss = nullptr;
+        float *g_sigma = nullptr, *g_albedo = nullptr;
+        int it = 0, stats_n = 0;
+    } e2e;
+
+    LaunchCfg cfg() {
+        LaunchCfg c;
+        c.stream = stream; c.sm_count = sm_count; c.tracer = tracer;
+        c.counters = counters; c.work_counter = work; c.launches = &launches;
+        return c;
+    }
+    GridK gridk() const {
+        GridK g;
+        g.sig2 = sig2; g.sig1 = sig1; g.alb2 = alb2; g.nx = nx; g.ny = ny; g.nz = nz; g.majorants = majorants;
+        return g;
+    }
+};
+
+namespace {
+
+int use_device(rcv_ctx *ctx) {
+    if (!ctx) return fail(RCV_ERR_ARG, "null context");
+    CK(cudaSetDevice(ctx->device));
+    return RCV_OK;
+}
+
+void free_medium(rcv_ctx *c) {
+    cudaFree(c->sig2); cudaFree(c->sig1); cudaFree(c->alb2); cudaFree(c->grad); cudaFree(c->block_max);
+    c->sig2 = nullptr; c->sig1 = nullptr; c->alb2 = nullptr; c->grad = nullptr; c->block_max = nullptr;
+    c->nvox = 0; c->nx = c->ny = c->nz = 0;
+}
+
+// nearest x2 upsample of the previous `new` state into the `new` slot of
+// freshly allocated packed grids, so that the following rotation moves it to
+// the `old` slot (the reference keeps theta_{i-1} at the coarse
+// resolution for the single iteration after utils.py:177-192 upsample()).
+__global__ void k_upsample_state(const float2 *sig2_lo, const float4 *alb2_lo, int nz, int ny, int nx, float2 *sig2_hi,
+                                 float4 *alb2_hi) {
+    size_t n_hi = (size_t) 8 * nz * ny * nx;
+    for (size_t v = (size_t) blockIdx.x * blockDim.x + threadIdx.x; v < n_hi; v += (size_t) gridDim.x * blockDim.x) {
+        size_t r = v;
+        int x = (int) (r % (2 * nx)); r /= (2 * nx);
+        int y = (int) (r % (2 * ny)); r /= (2 * ny);
+        int z = (int) r;
+        size_t lo = ((size_t) (z >> 1) * ny + (y >> 1)) * nx + (x >> 1);
+        sig2_hi[v] = make_float2(0.f, sig2_lo[lo].y);
+        alb2_hi[2 * v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        alb2_hi[2 * v + 1] = alb2_lo[2 * lo + 1];
+    }
+}
+
+float one_minus_pow(float beta, int n) { return (float) (1.0 - std::pow((double) beta, (double) n)); }
+float adam_lr_t(float lr, float beta1, float beta2, int t) {
+    double s = std::sqrt(1.0 - std::pow((double) beta2, (double) t)) / (1.0 - std::pow((double) beta1, (double) t));
+    return (float) ((double) lr * s);
+}
+
+// seed of volpathsimple's secondary sampler (plugins/volpathsimple.py:112-120):
+// lane 0's fourth float reinterpreted as uint32, scrambled by TEA — a pure
+// function of seed_grad, so no device->host read is needed.
+uint32_t alt_seed_for(uint32_t seed_grad) {
+    Pcg r;
+    sampler_seed(r, seed_grad, 0u);
+    pcg_u32(r); pcg_u32(r); pcg_u32(r);
+    uint32_t bits = (pcg_u32(r) >> 9) | 0x3f800000u;
+    float f;
+    std::memcpy(&f, &bits, 4);
+    f = f - 1.f;
+    uint32_t fb;
+    std::memcpy(&fb, &f, 4);
+    uint32_t v0, v1;
+    tea4(fb, 1u, v0, v1);
+    return v0;
+}
+
+int ensure_film_w(rcv_ctx *c) {
+    size_t npix = (size_t) c->S.W * c->S.H;
+    if (c->film_w_pix != npix) {
+        cudaFree(c->film_w); c->film_w = nullptr;
+        CK(cudaMalloc(&c->film_w, npix * sizeof(float)));
+        c->film_w_pix = npix;
+    }
+    return RCV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *rcv_last_error(void) { return g_err.c_str(); }
+int rcv_abi_version(void) { return RCV_ABI_VERSION; }
+int rcv_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return n;
+}
+
+int rcv_ctx_create(int device, void *stream, rcv_ctx **out) {
+    if (!out) return fail(RCV_ERR_ARG, "out is null");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(RCV_ERR_CUDA, "no CUDA device available (librcv_b200 has no CPU fallback)");
+    }
+    if (device < 0 || device >= n) return fail(RCV_ERR_ARG, "invalid device index");
+    CK(cudaSetDevice(device));
+    rcv_ctx *c = new rcv_ctx();
+    c->device = device;
+    c->stream = (cudaStream_t) stream;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    CK(cudaMalloc(&c->counters, sizeof(Counters)));
+    CK(cudaMemset(c->counters, 0, sizeof(Counters)));
+    CK(cudaMalloc(&c->work, sizeof(unsigned long long)));
+    CK(cudaMalloc(&c->majorants, 2 * sizeof(float)));
+    CK(cudaMemset(c->majorants, 0, 2 * sizeof(float)));
+    c->n_partial = c->sm_count * 4;
+    CK(cudaMalloc(&c->loss_partial, c->n_partial * sizeof(double)));
+    *out = c;
+    return RCV_OK;
+}
+
+int rcv_ctx_destroy(rcv_ctx *c) {
+    if (!c) return RCV_OK;
+    cudaSetDevice(c->device);
+    free_medium(c);
+    cudaFree(c->counters); cudaFree(c->work); cudaFree(c->majorants); cudaFree(c->film_w); cudaFree(c->loss_partial);
+    auto &E = c->e2e;
+    cudaFree(E.sigma); cudaFree(E.albedo); cudaFree(E.ref); cudaFree(E.acc); cudaFree(E.HF); cudaFree(E.cv);
+    cudaFree(E.grad_img); cudaFree(E.loss); cudaFree(E.g_sigma); cudaFree(E.g_albedo);
+    delete c;
+    return RCV_OK;
+}
+
+int rcv_ctx_set_stream(rcv_ctx *c, void *stream) {
+    if (!c) return fail(RCV_ERR_ARG, "null context");
+    c->stream = (cudaStream_t) stream;
+    return RCV_OK;
+}
+int rcv_ctx_set_tracer(rcv_ctx *c, int kind) {
+    if (!c) return fail(RCV_ERR_ARG, "null context");
+    if (kind != RCV_TRACER_WAVEFRONT && kind != RCV_TRACER_SIMPLE) return fail(RCV_ERR_ARG, "unknown tracer kind");
+    c->tracer = kind;
+    return RCV_OK;
+}
+
+int rcv_scene_set(rcv_ctx *c, const rcv_scene_desc *d) {
+    if (!c || !d) return fail(RCV_ERR_ARG, "null argument");
+    if (d->struct_size != sizeof(rcv_scene_desc)) return fail(RCV_ERR_ARG, "rcv_scene_desc size mismatch (ABI)");
+    if (d->film_width == 0 || d->film_height == 0) return fail(RCV_ERR_ARG, "empty film");
+    if (d->phase_type != RCV_PHASE_ISOTROPIC && d->phase_type != RCV_PHASE_HG) return fail(RCV_ERR_ARG, "unknown phase function");
+    for (int a = 0; a < 3; ++a)
+        if (!(d->bbox_max[a] > d->bbox_min[a])) return fail(RCV_ERR_ARG, "degenerate medium bounding box");
+    c->desc = *d;
+    SceneK &S = c->S;
+    S.W = d->film_width; S.H = d->film_height;
+    S.rcpW = 1.f / (float) S.W; S.rcpH = 1.f / (float) S.H;
+    for (int i = 0; i < 3; ++i) {
+        S.cam_o[i] = d->cam_origin[i];
+        S.bmin[i] = d->bbox_min[i]; S.bmax[i] = d->bbox_max[i];
+        S.inv_ext[i] = 1.f / (d->bbox_max[i] - d->bbox_min[i]);
+        S.env[i] = d->env_radiance[i];
+    }
+    for (int i = 0; i < 9; ++i) S.cam_axes[i] = d->cam_axes[i];
+    S.tan_x = d->cam_tan_x; S.tan_y = d->cam_tan_y; S.near_clip = d->cam_near_clip;
+    S.scale = d->sigma_t_scale; S.phase = d->phase_type; S.g = d->phase_g;
+    S.sample_emitters = d->sample_emitters; S.env_dist = d->env_dist;
+    S.max_depth = d->max_depth; S.rr_depth = d->rr_depth; S.hide_emitters = d->hide_emitters; S.use_nee = d->use_nee;
+    c->has_scene = true;
+    return RCV_OK;
+}
+
+int rcv_medium_rotate(rcv_ctx *c, const float *sigma_t_in, const float *albedo_in, int nz, int ny, int nx) {
+    if (int r = use_device(c)) return r;
+    if (!c->has_scene) return fail(RCV_ERR_STATE, "rcv_scene_set must be called before rcv_medium_rotate");
+    if (!sigma_t_in || !albedo_in || nz <= 0 || ny <= 0 || nx <= 0) return fail(RCV_ERR_ARG, "invalid grid");
+    size_t nvox = (size_t) nz * ny * nx;
+    LaunchCfg cfg = c->cfg();
+    if (nz != c->nz || ny != c->ny || nx != c->nx) {
+        float2 *sig2; float *sig1; float4 *alb2, *grad; float *bm;
+        CK(cudaMalloc(&sig2, nvox * sizeof(float2)));
+        CK(cudaMalloc(&sig1, nvox * sizeof(float)));
+        CK(cudaMalloc(&alb2, 2 * nvox * sizeof(float4)));
+        CK(cudaMalloc(&grad, nvox * sizeof(float4)));
+        uint64_t want = (nvox + 255) / 256, cap = (uint64_t) c->sm_count * 8;
+        int nb = (int) (want < cap ? want : cap);
+        CK(cudaMalloc(&bm, nb * sizeof(float)));
+        if (c->sig2 && nz == 2 * c->nz && ny == 2 * c->ny && nx == 2 * c->nx) {
+            k_upsample_state<<<c->sm_count * 8, 256, 0, c->stream>>>(c->sig2, c->alb2, c->nz, c->ny, c->nx, sig2, alb2);
+            c->launches++;
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(c->stream));
+        } else {
+            CK(cudaMemsetAsync(sig2, 0, nvox * sizeof(float2), c->stream));
+            CK(cudaMemsetAsync(alb2, 0, 2 * nvox * sizeof(float4), c->stream));
+            CK(cudaMemsetAsync(c->majorants, 0, 2 * sizeof(float), c->stream));
+        }
+        CK(cudaMemsetAsync(grad, 0, nvox * sizeof(float4), c->stream));
+        free_medium(c);
+        c->sig2 = sig2; c->sig1 = sig1; c->alb2 = alb2; c->grad = grad; c->block_max = bm; c->n_rot_blocks = nb;
+        c->nz = nz; c->ny = ny; c->nx = nx; c->nvox = nvox;
+    }
+    CK(launch_rotate(cfg, sigma_t_in, albedo_in, nvox, c->S.scale, c->sig2, c->sig1, c->alb2, c->block_max, c->n_rot_blocks,
+                     c->majorants));
+    return RCV_OK;
+}
+
+int rcv_medium_majorants_host(rcv_ctx *c, float out[2]) {
+    if (int r = use_device(c)) return r;
+    CK(cudaMemcpyAsync(out, c->majorants, 2 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return RCV_OK;
+}
+
+int rcv_medium_read(rcv_ctx *c, int state, float *sigma_t_out, float *albedo_out) {
+    if (int r = use_device(c)) return r;
+    if (!c->sig2) return fail(RCV_ERR_STATE, "no medium state");
+    if (state != 0 && state != 1) return fail(RCV_ERR_ARG, "state must be 0 (old) or 1 (new)");
+    CK(launch_medium_read(c->cfg(), c->sig2, c->alb2, c->nvox, state, sigma_t_out, albedo_out));
+    return RCV_OK;
+}
+
+static int check_render(rcv_ctx *c, uint32_t spp, uint32_t b, uint32_t e) {
+    if (int r = use_device(c)) return r;
+    if (!c->has_scene) return fail(RCV_ERR_STATE, "no scene set");
+    if (!c->sig2) return fail(RCV_ERR_STATE, "no medium state (call rcv_medium_rotate)");
+    if (spp == 0 || b > e || e > spp) return fail(RCV_ERR_ARG, "invalid sample range");
+    if ((uint64_t) c->S.W * c->S.H * spp > 0xffffffffull) return fail(RCV_ERR_ARG, "wavefront exceeds 2^32 lanes");
+    return RCV_OK;
+}
+
+int rcv_render_twostates(rcv_ctx *c, uint32_t seed, uint32_t spp, uint32_t spp_begin, uint32_t spp_end, float *accum_old,
+                         float *accum_new) {
+    if (int r = check_render(c, spp, spp_begin, spp_end)) return r;
+    if (!accum_old || !accum_new) return fail(RCV_ERR_ARG, "null accumulator");
+    CK(launch_twostates(c->cfg(), c->S, c->gridk(), 0, seed, spp, spp_begin, spp_end, (float4 *) accum_old, (float4 *) accum_new));
+    return RCV_OK;
+}
+
+int rcv_render_primal(rcv_ctx *c, int state, uint32_t seed, uint32_t spp, uint32_t spp_begin, uint32_t spp_end, float *accum) {
+    if (int r = check_render(c, spp, spp_begin, spp_end)) return r;
+    if (!accum) return fail(RCV_ERR_ARG, "null accumulator");
+    if (state != 0 && state != 1) return fail(RCV_ERR_ARG, "state must be 0 (old) or 1 (new)");
+    CK(launch_twostates(c->cfg(), c->S, c->gridk(), state == 0 ? 1 : 2, seed, spp, spp_begin, spp_end, (float4 *) accum,
+                        (float4 *) accum));
+    return RCV_OK;
+}
+
+int rcv_develop(rcv_ctx *c, const float *accum, float *img) {
+    if (int r = use_device(c)) return r;
+    if (!c->has_scene) return fail(RCV_ERR_STATE, "no scene set");
+    if (!accum || !img) return fail(RCV_ERR_ARG, "null pointer");
+    CK(launch_develop(c->cfg(), (const float4 *) accum, img, (size_t) c->S.W * c->S.H));
+    return RCV_OK;
+}
+
+int rcv_cv_update(rcv_ctx *c, const float *H, const float *F, float *img, float *v_n, float *w_s, float *mean_x, float *mean_y,
+                  float *var_x, float *var_y, float *cov, uint64_t n, int32_t it, int32_t warmup, int32_t stats_n, float beta1,
+                  float beta2, int32_t pre_update) {
+    if (int r = use_device(c)) return r;
+    if (!H || !F || !img || !v_n || !w_s || !mean_x || !mean_y || !var_x || !var_y || !cov) return fail(RCV_ERR_ARG, "null pointer");
+    if (n == 0) return RCV_OK;
+    CvArgs a;
+    a.H = H; a.F = F; a.img = img; a.v_n = v_n; a.w_s = w_s; a.mean_x = mean_x; a.mean_y = mean_y;
+    a.var_x = var_x; a.var_y = var_y; a.cov = cov; a.n = n;
+    a.do_weights = it > warmup; a.do_update = it > 0; a.pre_update = pre_update != 0;
+    a.stats_n_is_zero = stats_n == 0;
+    a.c1a = one_minus_pow(beta1, stats_n); a.c1b = one_minus_pow(beta1, stats_n + 1);
+    int n_get = stats_n + ((a.do_update && a.pre_update) ? 1 : 0);
+    a.c2 = one_minus_pow(beta2, n_get);
+    a.beta1 = beta1; a.beta2 = beta2;
+    CK(launch_cv_update(c->cfg(), a));
+    return RCV_OK;
+}
+
+int rcv_loss_grad(rcv_ctx *c, int kind, const float *img, const float *ref, uint64_t n, float *loss_out, float *grad_img) {
+    if (int r = use_device(c)) return r;
+    if (kind != RCV_LOSS_L1 && kind != RCV_LOSS_L2) return fail(RCV_ERR_ARG, "unknown loss");
+    if (!img || !ref || !loss_out || n == 0) return fail(RCV_ERR_ARG, "invalid argument");
+    CK(launch_loss_grad(c->cfg(), kind, img, ref, n, c->loss_partial, c->n_partial, loss_out, grad_img));
+    return RCV_OK;
+}
+
+int rcv_render_backward(rcv_ctx *c, int adjoint_kind, uint32_t seed_grad, uint32_t spp_grad, uint32_t spp_begin, uint32_t spp_end,
+                        const float *grad_img) {
+    if (int r = check_render(c, spp_grad, spp_begin, spp_end)) return r;
+    if (adjoint_kind != RCV_ADJOINT_VOLPATHSIMPLE) return fail(RCV_ERR_ARG, "unknown adjoint integrator");
+    if (!grad_img) return fail(RCV_ERR_ARG, "null grad_img");
+    if (int r = ensure_film_w(c)) return r;
+    LaunchCfg cfg = c->cfg();
+    CK(launch_film_weights(cfg, c->S, seed_grad, spp_grad, c->film_w));
+    GradK D; D.grad = c->grad;
+    CK(launch_vps_backward(cfg, c->S, c->gridk(), D, seed_grad, spp_grad, spp_begin, spp_end, alt_seed_for(seed_grad), grad_img,
+                           c->film_w));
+    return RCV_OK;
+}
+
+int rcv_render_adjoint_primal(rcv_ctx *c, int adjoint_kind, uint32_t seed, uint32_t spp, uint32_t spp_begin, uint32_t spp_end,
+                              float *accum) {
+    if (int r = check_render(c, spp, spp_begin, spp_end)) return r;
+    if (adjoint_kind != RCV_ADJOINT_VOLPATHSIMPLE) return fail(RCV_ERR_ARG, "unknown adjoint integrator");
+    if (!accum) return fail(RCV_ERR_ARG, "null accumulator");
+    CK(launch_vps_primal(c->cfg(), c->S, c->gridk(), seed, spp, spp_begin, spp_end, (float4 *) accum));
+    return RCV_OK;
+}
+
+int rcv_grad_zero(rcv_ctx *c) {
+    if (int r = use_device(c)) return r;
+    if (!c->grad) return fail(RCV_ERR_STATE, "no medium state");
+    CK(cudaMemsetAsync(c->grad, 0, c->nvox * sizeof(float4), c->stream));
+    return RCV_OK;
+}
+int rcv_grad_buffer(rcv_ctx *c, float **ptr, uint64_t *n_floats) {
+    if (!c || !ptr || !n_floats) return fail(RCV_ERR_ARG, "null argument");
+    if (!c->grad) return fail(RCV_ERR_STATE, "no medium state");
+    *ptr = (float *) c->grad; *n_floats = 4 * (uint64_t) c->nvox;
+    return RCV_OK;
+}
+int rcv_grad_read(rcv_ctx *c, float *grad_sigma_t, float *grad_albedo) {
+    if (int r = use_device(c)) return r;
+    if (!c->grad) return fail(RCV_ERR_STATE, "no medium state");
+    CK(launch_grad_unpack(c->cfg(), c->grad, c->nvox, grad_sigma_t, grad_albedo));
+    return RCV_OK;
+}
+
+int rcv_adam_step(rcv_ctx *c, float *sigma_t, float *albedo, float *m_sigma_t, float *v_sigma_t, float *m_albedo, float *v_albedo,
+                  int32_t t, float lr_sigma_t, float lr_albedo, float beta1, float beta2, float eps, float slo, float shi,
+                  float alo, float ahi) {
+    if (int r = use_device(c)) return r;
+    if (!c->grad) return fail(RCV_ERR_STATE, "no medium state");
+    if (t < 1) return fail(RCV_ERR_ARG, "t must be >= 1");
+    if (!sigma_t || !albedo || !m_sigma_t || !v_sigma_t || !m_albedo || !v_albedo) return fail(RCV_ERR_ARG, "null pointer");
+    CK(launch_adam_packed(c->cfg(), c->grad, c->nvox, sigma_t, albedo, m_sigma_t, v_sigma_t, m_albedo, v_albedo,
+                          adam_lr_t(lr_sigma_t, beta1, beta2, t), adam_lr_t(lr_albedo, beta1, beta2, t), beta1, beta2, eps, slo,
+                          shi, alo, ahi));
+    return RCV_OK;
+}
+int rcv_adam_flat(rcv_ctx *c, float *p, const float *g, float *m, float *v, uint64_t n, int32_t t, float lr, float beta1,
+                  float beta2, float eps) {
+    if (int r = use_device(c)) return r;
+    if (t < 1) return fail(RCV_ERR_ARG, "t must be >= 1");
+    if (!p || !g || !m || !v) return fail(RCV_ERR_ARG, "null pointer");
+    if (n == 0) return RCV_OK;
+    CK(launch_adam_flat(c->cfg(), p, g, m, v, n, adam_lr_t(lr, beta1, beta2, t), beta1, beta2, eps));
+    return RCV_OK;
+}
+int rcv_clamp(rcv_ctx *c, float *p, uint64_t n, float lo, float hi) {
+    if (int r = use_device(c)) return r;
+    if (!p) return fail(RCV_ERR_ARG, "null pointer");
+    if (n == 0) return RCV_OK;
+    CK(launch_clamp(c->cfg(), p, n, lo, hi));
+    return RCV_OK;
+}
+int rcv_upsample2x(rcv_ctx *c, const float *in, float *out, int nz, int ny, int nx, int ch) {
+    if (int r = use_device(c)) return r;
+    if (!in || !out || nz <= 0 || ny <= 0 || nx <= 0 || ch <= 0) return fail(RCV_ERR_ARG, "invalid argument");
+    CK(launch_upsample2x(c->cfg(), in, out, nz, ny, nx, ch));
+    return RCV_OK;
+}
+
+int rcv_counters_host(rcv_ctx *c, uint64_t out[8], int reset) {
+    if (int r = use_device(c)) return r;
+    Counters h;
+    CK(cudaMemcpyAsync(&h, c->counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < 8; ++i) out[i] = h.c[i];
+    out[7] = c->launches;
+    if (reset) {
+        CK(cudaMemsetAsync(c->counters, 0, sizeof(Counters), c->stream));
+        c->launches = 0;
+    }
+    return RCV_OK;
+}
+
+int rcv_cv_iteration_host(rcv_ctx *c, const rcv_iter_host_args *a) {
+    if (int r = use_device(c)) return r;
+    if (!a || a->struct_size != sizeof(rcv_iter_host_args)) return fail(RCV_ERR_ARG, "rcv_iter_host_args size mismatch (ABI)");
+    if (!c->has_scene) return fail(RCV_ERR_STATE, "no scene set");
+    if (!a->sigma_t_in || !a->albedo_in || !a->ref || !a->img_out || !a->loss_out) return fail(RCV_ERR_ARG, "null host buffer");
+    auto &E = c->e2e;
+    size_t nvox = (size_t) a->nz * a->ny * a->nx, npix = (size_t) c->S.W * c->S.H;
+    if (E.nvox != nvox) {
+        cudaFree(E.sigma); cudaFree(E.albedo); cudaFree(E.g_sigma); cudaFree(E.g_albedo);
+        CK(cudaMalloc(&E.sigma, nvox * sizeof(float)));
+        CK(cudaMalloc(&E.albedo, 3 * nvox * sizeof(float)));
+        CK(cudaMalloc(&E.g_sigma, nvox * sizeof(float)));
+        CK(cudaMalloc(&E.g_albedo, 3 * nvox * sizeof(float)));
+        E.nvox = nvox;
+    }
+    if (E.npix != npix || a->reset) {
+        if (E.npix != npix) {
+            cudaFree(E.ref); cudaFree(E.acc); cudaFree(E.HF); cudaFree(E.cv); cudaFree(E.grad_img); cudaFree(E.loss);
+            CK(cudaMalloc(&E.ref, 3 * npix * sizeof(float)));
+            CK(cudaMalloc(&E.acc, 8 * npix * sizeof(float)));
+            CK(cudaMalloc(&E.HF, 6 * npix * sizeof(float)));
+            CK(cudaMalloc(&E.cv, 24 * npix * sizeof(float)));
+            CK(cudaMalloc(&E.grad_img, 3 * npix * sizeof(float)));
+            CK(cudaMalloc(&E.loss, sizeof(float)));
+            E.npix = npix;
+        }
+        CK(cudaMemsetAsync(E.cv, 0, 24 * npix * sizeof(float), c->stream));   // integrator.reset() (cv_integrator.py:29-43)
+        E.it = 0; E.stats_n = 0;
+    }
+    cudaStream_t st = c->stream;
+    const uint64_t n3 = 3 * npix;
+    // host -> device: this iteration's parameters and the reference image
+    CK(cudaMemcpyAsync(E.sigma, a->sigma_t_in, nvox * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(E.albedo, a->albedo_in, 3 * nvox * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(E.ref, a->ref, n3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (int r = rcv_medium_rotate(c, E.sigma, E.albedo, a->nz, a->ny, a->nx)) return r;      // optimize.py:107
+    CK(cudaMemsetAsync(E.acc, 0, 8 * npix * sizeof(float), st));
+    float *acc_old = E.acc, *acc_new = E.acc + 4 * npix, *H = E.HF, *F = E.HF + n3;
+    if (int r = rcv_render_twostates(c, a->seed, a->spp, 0, a->spp, acc_old, acc_new)) return r;   // optimize.py:108
+    if (int r = rcv_develop(c, acc_old, H)) return r;
+    if (int r = rcv_develop(c, acc_new, F)) return r;
+    float *cv = E.cv;
+    if (int r = rcv_cv_update(c, H, F, cv, cv + n3, cv + 2 * n3, cv + 3 * n3, cv + 4 * n3, cv + 5 * n3, cv + 6 * n3, cv + 7 * n3,
+                              n3, E.it, a->warmup, E.stats_n, a->beta1, a->beta2, 0)) return r;
+    if (E.it > 0) E.stats_n += 1;
+    E.it += 1;
+    if (int r = rcv_loss_grad(c, a->loss_kind, cv, E.ref, n3, E.loss, E.grad_img)) return r;   // optimize.py:110-122
+    if (int r = rcv_grad_zero(c)) return r;
+    if (int r = rcv_render_backward(c, RCV_ADJOINT_VOLPATHSIMPLE, a->seed_grad, a->spp_grad, 0, a->spp_grad, E.grad_img)) return r;
+    // device -> host: image, loss, gradients
+    CK(cudaMemcpyAsync(a->img_out, cv, n3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(a->loss_out, E.loss, sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (a->grad_sigma_t_out || a->grad_albedo_out) {
+        if (int r = rcv_grad_read(c, a->grad_sigma_t_out ? E.g_sigma : nullptr, a->grad_albedo_out ? E.g_albedo : nullptr)) return r;
+        if (a->grad_sigma_t_out)
+            CK(cudaMemcpyAsync(a->grad_sigma_t_out, E.g_sigma, nvox * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (a->grad_albedo_out)
+            CK(cudaMemcpyAsync(a->grad_albedo_out, E.g_albedo, 3 * nvox * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    return RCV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,458 @@
+// rcv_device.cuh — device-side building blocks shared by the tracing kernels:
+// RNG (TEA-4 + PCG32), the fixed-order float32 elementary functions, the box
+// geometry, the packed two-state grid and its trilinear lookups.
+//
+// Numerical contract: every value that can influence a path
+// decision is IEEE binary32 with a fixed evaluation order.  This translation
+// unit is compiled with -fmad=false, so a*b+c is never contracted; where the
+// specification wants a fused multiply-add it is written as __fmaf_rn.
+// Divisions and square roots are the IEEE-rounded ones (-prec-div/-prec-sqrt
+// defaults).  log and sincos are the Cephes single-precision polynomials
+// spelled out here (not the libdevice versions), so that a lane's random walk
+// is reproducible bit for bit against the CPU restatement used in the tests.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace rcv {
+
+// ----------------------------------------------------------------------------
+// kernel-side scene / medium parameter blocks (passed by value)
+// ----------------------------------------------------------------------------
+struct SceneK {
+    uint32_t W, H;
+    float rcpW, rcpH;
+    float cam_o[3];
+    float cam_axes[9];
+    float tan_x, tan_y, near_clip;
+    float bmin[3], bmax[3], inv_ext[3];
+    float scale;              // sigma_t scale
+    int phase;                // RCV_PHASE_*
+    float g;
+    int sample_emitters;
+    float env[3];
+    float env_dist;
+    int max_depth, rr_depth, hide_emitters, use_nee;
+};
+
+// Packed medium state in HBM:
+//   sig2[v]      = (sigma_t_old, sigma_t_new) of voxel v         (8 B / voxel)
+//   sig1[v]      = sigma_t_new                                   (4 B / voxel)
+//   alb2[2v + s] = (albedo rgb of state s, 0)                    (32 B / voxel)
+// v = (z * ny + y) * nx + x, x fastest (the reference's (Z,Y,X,C) layout).
+struct GridK {
+    const float2 *sig2;
+    const float *sig1;
+    const float4 *alb2;
+    int nx, ny, nz;
+    const float *majorants;   // device: [0] = old, [1] = new  (scale * max)
+};
+
+// packed gradient grid: float4 per voxel = (d sigma_t, d albedo r, g, b)
+struct GradK {
+    float4 *grad;
+};
+
+struct Counters {
+    unsigned long long c[8];
+};
+
+// ----------------------------------------------------------------------------
+// float helpers with oracle-identical NaN behaviour
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ float fmin_(float a, float b) { return (b < a) ? b : a; }
+__device__ __forceinline__ float fmax_(float a, float b) { return (b > a) ? b : a; }
+__device__ __forceinline__ float inf_() { return __int_as_float(0x7f800000); }
+#define RCV_LARGEST 3.402823466e+38f
+#define RCV_RAY_EPS (1500.f * 5.9604644775390625e-8f)
+#define RCV_SHADOW_EPS (10.f * RCV_RAY_EPS)
+#define RCV_INV_FOURPI 0.07957747154594766788f
+#define RCV_TWO_PI 6.28318530717958647692f
+
+struct V3 {
+    float x, y, z;
+};
+__device__ __forceinline__ V3 mk3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 operator*(V3 a, V3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ V3 operator/(V3 a, V3 b) { return mk3(a.x / b.x, a.y / b.y, a.z / b.z); }
+__device__ __forceinline__ V3 operator*(V3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ V3 splat3(float s) { return mk3(s, s, s); }
+__device__ __forceinline__ float max3(V3 a) { return fmax_(fmax_(a.x, a.y), a.z); }
+__device__ __forceinline__ V3 vmax3(V3 a, V3 b) { return mk3(fmax_(a.x, b.x), fmax_(a.y, b.y), fmax_(a.z, b.z)); }
+__device__ __forceinline__ bool any_nz(V3 a) { return a.x != 0.f || a.y != 0.f || a.z != 0.f; }
+__device__ __forceinline__ V3 ray_at(V3 o, V3 d, float t) {
+    return mk3(__fmaf_rn(d.x, t, o.x), __fmaf_rn(d.y, t, o.y), __fmaf_rn(d.z, t, o.z));
+}
+__device__ __forceinline__ float dot3(V3 a, V3 b) { return __fmaf_rn(a.x, b.x, __fmaf_rn(a.y, b.y, a.z * b.z)); }
+
+// ----------------------------------------------------------------------------
+// RNG: mi.sample_tea_32 (4 rounds) + drjit PCG32 (independent sampler)
+// ----------------------------------------------------------------------------
+__host__ __device__ __forceinline__ void tea4(uint32_t v0, uint32_t v1, uint32_t &o0, uint32_t &o1) {
+    uint32_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        sum += 0x9e3779b9u;
+        v0 += ((v1 << 4) + 0xa341316cu) ^ (v1 + sum) ^ ((v1 >> 5) + 0xc8013ea4u);
+        v1 += ((v0 << 4) + 0xad90777du) ^ (v0 + sum) ^ ((v0 >> 5) + 0x7e95761eu);
+    }
+    o0 = v0; o1 = v1;
+}
+
+struct Pcg {
+    uint64_t state, inc;
+};
+__host__ __device__ __forceinline__ uint32_t pcg_u32(Pcg &r) {
+    uint64_t old = r.state;
+    r.state = old * 0x5851f42d4c957f2dULL + r.inc;
+    uint32_t xs = (uint32_t) (((old >> 18u) ^ old) >> 27u);
+    uint32_t rot = (uint32_t) (old >> 59u);
+    return (xs >> rot) | (xs << ((0u - rot) & 31u));
+}
+__host__ __device__ __forceinline__ void pcg_seed(Pcg &r, uint64_t initstate, uint64_t initseq) {
+    r.state = 0;
+    r.inc = (initseq << 1u) | 1u;
+    pcg_u32(r);
+    r.state += initstate;
+    pcg_u32(r);
+}
+__device__ __forceinline__ float pcg_f32(Pcg &r) {
+    return __uint_as_float((pcg_u32(r) >> 9) | 0x3f800000u) - 1.f;
+}
+__host__ __device__ __forceinline__ void sampler_seed(Pcg &r, uint32_t seed, uint32_t idx) {
+    uint32_t v0, v1;
+    tea4(seed, idx, v0, v1);
+    pcg_seed(r, (uint64_t) v0, (uint64_t) v1);
+}
+
+// ----------------------------------------------------------------------------
+// elementary functions, fixed operation order (Cephes logf / sinf / cosf)
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ float spec_log(float x) {
+    uint32_t u = __float_as_uint(x);
+    int e = (int) (u >> 23) - 126;
+    float m = __uint_as_float((u & 0x007fffffu) | 0x3f000000u);
+    if (m < 0.707106781186547524f) { e -= 1; m = (m + m) - 1.f; }
+    else { m = m - 1.f; }
+    float z = m * m;
+    float y = 7.0376836292e-2f;
+    y = __fmaf_rn(y, m, -1.1514610310e-1f);
+    y = __fmaf_rn(y, m, 1.1676998740e-1f);
+    y = __fmaf_rn(y, m, -1.2420140846e-1f);
+    y = __fmaf_rn(y, m, 1.4249322787e-1f);
+    y = __fmaf_rn(y, m, -1.6668057665e-1f);
+    y = __fmaf_rn(y, m, 2.0000714765e-1f);
+    y = __fmaf_rn(y, m, -2.4999993993e-1f);
+    y = __fmaf_rn(y, m, 3.3333331174e-1f);
+    y = (y * m) * z;
+    float fe = (float) e;
+    y = __fmaf_rn(fe, -2.12194440e-4f, y);
+    y = __fmaf_rn(-0.5f, z, y);
+    float r = m + y;
+    r = __fmaf_rn(fe, 0.693359375f, r);
+    return r;
+}
+
+__device__ __forceinline__ void spec_sincos(float x, float &s_out, float &c_out) {
+    int j = (int) (x * 1.27323954473516f);
+    j = j + (j & 1);
+    float y = (float) j;
+    float r = __fmaf_rn(y, -0.78515625f, x);
+    r = __fmaf_rn(y, -2.4187564849853515625e-4f, r);
+    r = __fmaf_rn(y, -3.77489497744594108e-8f, r);
+    float z = r * r;
+    float ps = -1.9515295891e-4f;
+    ps = __fmaf_rn(ps, z, 8.3321608736e-3f);
+    ps = __fmaf_rn(ps, z, -1.6666654611e-1f);
+    ps = __fmaf_rn(ps * z, r, r);
+    float pc = 2.443315711809948e-5f;
+    pc = __fmaf_rn(pc, z, -1.388731625493765e-3f);
+    pc = __fmaf_rn(pc, z, 4.166664568298827e-2f);
+    pc = __fmaf_rn(pc * z, z, __fmaf_rn(-0.5f, z, 1.f));
+    int q = (j >> 1) & 3;
+    float s = (q & 1) ? pc : ps;
+    float c = (q & 1) ? ps : pc;
+    if (q & 2) s = -s;
+    if ((q + 1) & 2) c = -c;
+    s_out = s; c_out = c;
+}
+
+__device__ __forceinline__ V3 uniform_sphere(float sx, float sy) {
+    float z = __fmaf_rn(-2.f, sy, 1.f);
+    float r2 = __fmaf_rn(-z, z, 1.f);
+    float r = sqrtf(fmax_(r2, 0.f));
+    float s, c;
+    spec_sincos(RCV_TWO_PI * sx, s, c);
+    return mk3(r * c, r * s, z);
+}
+
+__device__ __forceinline__ float mis_weight(float pdf_a, float pdf_b) {
+    float a2 = pdf_a * pdf_a, b2 = pdf_b * pdf_b;
+    float w = a2 / (a2 + b2);
+    return isfinite(w) ? w : 0.f;
+}
+
+// ----------------------------------------------------------------------------
+// phase functions
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ float phase_eval(const SceneK &S, V3 wi, V3 wo) {
+    if (S.phase == 0) return RCV_INV_FOURPI;
+    float g = S.g;
+    float cos_theta = dot3(wi, wo);
+    float temp = 1.f + g * g + 2.f * g * cos_theta;
+    return RCV_INV_FOURPI * (1.f - g * g) / (temp * sqrtf(temp));
+}
+__device__ __forceinline__ V3 phase_sample(const SceneK &S, V3 wi, float s2x, float s2y, float &pdf) {
+    if (S.phase == 0) {
+        pdf = RCV_INV_FOURPI;
+        return uniform_sphere(s2x, s2y);
+    }
+    float g = S.g;
+    float sqr_term = (1.f - g * g) / (1.f - g + 2.f * g * s2x);
+    float cos_theta = (1.f + g * g - sqr_term * sqr_term) / (2.f * g);
+    if (fabsf(g) < 1.1920929e-7f) cos_theta = 1.f - 2.f * s2x;
+    float sin_theta = sqrtf(fmax_(__fmaf_rn(-cos_theta, cos_theta, 1.f), 0.f));
+    float sp, cp;
+    spec_sincos(RCV_TWO_PI * s2y, sp, cp);
+    V3 l = mk3(sin_theta * cp, sin_theta * sp, -cos_theta);
+    float sign = copysignf(1.f, wi.z);
+    float a = -1.f / (sign + wi.z);
+    float b = wi.x * wi.y * a;
+    V3 s = mk3(__fmaf_rn(wi.x * wi.x, a * sign, 1.f), b * sign, -wi.x * sign);
+    V3 t = mk3(b, __fmaf_rn(wi.y * wi.y, a, sign), -wi.y);
+    V3 wo = mk3(__fmaf_rn(s.x, l.x, __fmaf_rn(t.x, l.y, wi.x * l.z)),
+                __fmaf_rn(s.y, l.x, __fmaf_rn(t.y, l.y, wi.y * l.z)),
+                __fmaf_rn(s.z, l.x, __fmaf_rn(t.z, l.y, wi.z * l.z)));
+    float temp = 1.f + g * g - 2.f * g * cos_theta;
+    pdf = RCV_INV_FOURPI * (1.f - g * g) / (temp * sqrtf(temp));
+    return wo;
+}
+
+// ----------------------------------------------------------------------------
+// geometry: the medium's box (null-BSDF boundary)
+// ----------------------------------------------------------------------------
+struct Hit {
+    bool valid;
+    float t;
+    V3 p, n;
+};
+
+// slab intervals of all three axes; returns tn (entry), tf (exit) and the axes
+__device__ __forceinline__ void slabs(const SceneK &S, V3 o, V3 d, float &tn, float &tf, int &an, int &af) {
+    float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+    tn = -inf_(); tf = inf_(); an = 0; af = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float rcp = 1.f / dd[a];
+        float t1 = (S.bmin[a] - oo[a]) * rcp, t2 = (S.bmax[a] - oo[a]) * rcp;
+        float t1p = fmin_(t1, t2), t2p = fmax_(t1, t2);
+        if (t1p > tn) { tn = t1p; an = a; }
+        if (t2p < tf) { tf = t2p; af = a; }
+    }
+}
+
+// Medium::prepare_interaction_sampling: [mint, maxt] of the ray inside the box
+__device__ __forceinline__ bool medium_interval(const SceneK &S, V3 o, V3 d, float ray_maxt, float &mint, float &maxt) {
+    float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+    bool active = true;
+    float tn = -inf_(), tf = inf_();
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        active = active && (dd[a] != 0.f || oo[a] > S.bmin[a] || oo[a] < S.bmax[a]);
+        float rcp = 1.f / dd[a];
+        float t1 = (S.bmin[a] - oo[a]) * rcp, t2 = (S.bmax[a] - oo[a]) * rcp;
+        tn = fmax_(tn, fmin_(t1, t2));
+        tf = fmin_(tf, fmax_(t1, t2));
+    }
+    active = active && (tf >= tn);
+    active = active && (isfinite(tn) || isfinite(tf));
+    if (!active) { tn = 0.f; tf = inf_(); }
+    mint = fmax_(0.f, tn);
+    maxt = fmin_(ray_maxt, tf);
+    return active;
+}
+
+// nearest boundary hit with 0 < t <= maxt
+__device__ __forceinline__ Hit box_hit(const SceneK &S, V3 o, V3 d, float maxt) {
+    Hit h; h.valid = false; h.t = inf_(); h.p = mk3(0, 0, 0); h.n = mk3(0, 0, 0);
+    float tn, tf; int an, af;
+    slabs(S, o, d, tn, tf, an, af);
+    if (!(tf >= tn)) return h;
+    float t; int axis;
+    bool entering = tn > 0.f;
+    if (entering) { t = tn; axis = an; }
+    else if (tf > 0.f) { t = tf; axis = af; }
+    else return h;
+    if (!(t <= maxt) || !isfinite(t)) return h;
+    float dd = (axis == 0) ? d.x : ((axis == 1) ? d.y : d.z);
+    bool positive_face = entering ? (dd < 0.f) : (dd > 0.f);
+    float nsign = positive_face ? 1.f : -1.f;
+    V3 p = ray_at(o, d, t);
+    float plane;
+    if (axis == 0) { plane = positive_face ? S.bmax[0] : S.bmin[0]; p.x = plane; h.n = mk3(nsign, 0, 0); }
+    else if (axis == 1) { plane = positive_face ? S.bmax[1] : S.bmin[1]; p.y = plane; h.n = mk3(0, nsign, 0); }
+    else { plane = positive_face ? S.bmax[2] : S.bmin[2]; p.z = plane; h.n = mk3(0, 0, nsign); }
+    h.valid = true; h.t = t; h.p = p;
+    return h;
+}
+
+// Interaction::spawn_ray origin: p offset along n towards the side d points to
+__device__ __forceinline__ V3 offset_p(V3 p, V3 n, V3 d) {
+    float mag = (1.f + fmax_(fmax_(fabsf(p.x), fabsf(p.y)), fabsf(p.z))) * RCV_RAY_EPS;
+    float dn = dot3(n, d);
+    if (dn < 0.f) mag = -mag;
+    return mk3(__fmaf_rn(mag, n.x, p.x), __fmaf_rn(mag, n.y, p.y), __fmaf_rn(mag, n.z, p.z));
+}
+
+// ----------------------------------------------------------------------------
+// trilinear lookups on the packed grids
+// ----------------------------------------------------------------------------
+struct Tri {
+    bool inside;
+    int x0, x1, y0, y1, z0, z1;
+    float wx0, wx1, wy0, wy1, wz0, wz1;
+};
+
+__device__ __forceinline__ void tri_axis(float p, float bmin, float inv_ext, int res, bool &inside, int &i0, int &i1,
+                                         float &w0, float &w1) {
+    float pl = (p - bmin) * inv_ext;
+    inside = inside && (pl >= 0.f) && (pl <= 1.f);
+    float pos = __fmaf_rn(pl, (float) res, -0.5f);
+    float fl = floorf(pos);
+    int i = (int) fl;
+    w1 = pos - fl;
+    w0 = 1.f - w1;
+    i0 = min(max(i, 0), res - 1);
+    i1 = min(max(i + 1, 0), res - 1);
+}
+__device__ __forceinline__ Tri tri_setup(const SceneK &S, const GridK &G, V3 p) {
+    Tri T; T.inside = true;
+    tri_axis(p.x, S.bmin[0], S.inv_ext[0], G.nx, T.inside, T.x0, T.x1, T.wx0, T.wx1);
+    tri_axis(p.y, S.bmin[1], S.inv_ext[1], G.ny, T.inside, T.y0, T.y1, T.wy0, T.wy1);
+    tri_axis(p.z, S.bmin[2], S.inv_ext[2], G.nz, T.inside, T.z0, T.z1, T.wz0, T.wz1);
+    return T;
+}
+// v[k], k = 4*zbit + 2*ybit + xbit
+__device__ __forceinline__ float tri_lerp(const Tri &T, float v0_, float v1_, float v2_, float v3_, float v4_, float v5_,
+                                          float v6_, float v7_) {
+    float a0 = __fmaf_rn(T.wx0, v0_, T.wx1 * v1_);
+    float a1 = __fmaf_rn(T.wx0, v2_, T.wx1 * v3_);
+    float a2 = __fmaf_rn(T.wx0, v4_, T.wx1 * v5_);
+    float a3 = __fmaf_rn(T.wx0, v6_, T.wx1 * v7_);
+    float b0 = __fmaf_rn(T.wy0, a0, T.wy1 * a1);
+    float b1 = __fmaf_rn(T.wy0, a2, T.wy1 * a3);
+    return __fmaf_rn(T.wz0, b0, T.wz1 * b1);
+}
+__device__ __forceinline__ void tri_rows(const GridK &G, const Tri &T, size_t r[4]) {
+    r[0] = ((size_t) T.z0 * G.ny + T.y0) * G.nx;
+    r[1] = ((size_t) T.z0 * G.ny + T.y1) * G.nx;
+    r[2] = ((size_t) T.z1 * G.ny + T.y0) * G.nx;
+    r[3] = ((size_t) T.z1 * G.ny + T.y1) * G.nx;
+}
+__device__ __forceinline__ float tri_weight(const Tri &T, int k) {
+    float wx = (k & 1) ? T.wx1 : T.wx0;
+    float wy = (k & 2) ? T.wy1 : T.wy0;
+    float wz = (k & 4) ? T.wz1 : T.wz0;
+    return (wz * wy) * wx;
+}
+__device__ __forceinline__ size_t tri_voxel(const GridK &G, const Tri &T, int k) {
+    int x = (k & 1) ? T.x1 : T.x0;
+    int y = (k & 2) ? T.y1 : T.y0;
+    int z = (k & 4) ? T.z1 : T.z0;
+    return ((size_t) z * G.ny + y) * G.nx + x;
+}
+
+// both states' sigma_t (scale * grid) with one gather of 8 float2
+__device__ __forceinline__ void lookup_sigma2(const SceneK &S, const GridK &G, const Tri &T, float &s_old, float &s_new) {
+    if (!T.inside) { s_old = 0.f; s_new = 0.f; return; }
+    size_t r[4];
+    tri_rows(G, T, r);
+    float2 v[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        v[2 * k] = __ldg(G.sig2 + r[k] + T.x0);
+        v[2 * k + 1] = __ldg(G.sig2 + r[k] + T.x1);
+    }
+    s_old = S.scale * tri_lerp(T, v[0].x, v[1].x, v[2].x, v[3].x, v[4].x, v[5].x, v[6].x, v[7].x);
+    s_new = S.scale * tri_lerp(T, v[0].y, v[1].y, v[2].y, v[3].y, v[4].y, v[5].y, v[6].y, v[7].y);
+}
+// state `new` only
+__device__ __forceinline__ float lookup_sigma1(const SceneK &S, const GridK &G, const Tri &T) {
+    if (!T.inside) return 0.f;
+    size_t r[4];
+    tri_rows(G, T, r);
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        v[2 * k] = __ldg(G.sig1 + r[k] + T.x0);
+        v[2 * k + 1] = __ldg(G.sig1 + r[k] + T.x1);
+    }
+    return S.scale * tri_lerp(T, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+}
+// albedo of state s (0 = old, 1 = new)
+__device__ __forceinline__ V3 lookup_albedo(const GridK &G, const Tri &T, int s) {
+    if (!T.inside) return mk3(0, 0, 0);
+    size_t r[4];
+    tri_rows(G, T, r);
+    float4 v[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        v[2 * k] = __ldg(G.alb2 + 2 * (r[k] + T.x0) + s);
+        v[2 * k + 1] = __ldg(G.alb2 + 2 * (r[k] + T.x1) + s);
+    }
+    return mk3(tri_lerp(T, v[0].x, v[1].x, v[2].x, v[3].x, v[4].x, v[5].x, v[6].x, v[7].x),
+               tri_lerp(T, v[0].y, v[1].y, v[2].y, v[3].y, v[4].y, v[5].y, v[6].y, v[7].y),
+               tri_lerp(T, v[0].z, v[1].z, v[2].z, v[3].z, v[4].z, v[5].z, v[6].z, v[7].z));
+}
+
+// ----------------------------------------------------------------------------
+// sensor: lane -> (rng, camera ray, film pixel)
+// ----------------------------------------------------------------------------
+struct Lane {
+    Pcg rng;
+    V3 o, d;
+    int pix;   // -1: the sample fell outside the film
+};
+__device__ __forceinline__ Lane lane_setup(const SceneK &S, uint32_t seed, uint32_t spp, uint64_t idx) {
+    Lane L;
+    sampler_seed(L.rng, seed, (uint32_t) idx);
+    uint32_t pixel = (uint32_t) (idx / spp);
+    uint32_t py = pixel / S.W, px = pixel - S.W * py;
+    float u1 = pcg_f32(L.rng), u2 = pcg_f32(L.rng);
+    float pfx = (float) px + u1, pfy = (float) py + u2;
+    int ix = (int) floorf(pfx), iy = (int) floorf(pfy);
+    L.pix = (ix >= 0 && ix < (int) S.W && iy >= 0 && iy < (int) S.H) ? iy * (int) S.W + ix : -1;
+    float sx = pfx * S.rcpW, sy = pfy * S.rcpH;
+    float nx = __fmaf_rn(sx, -2.f * S.tan_x, S.tan_x);
+    float ny = __fmaf_rn(sy, -2.f * S.tan_y, S.tan_y);
+    float len2 = __fmaf_rn(nx, nx, __fmaf_rn(ny, ny, 1.f));
+    float inv = 1.f / sqrtf(len2);
+    float dx = nx * inv, dy = ny * inv, dz = inv;
+    const float *A = S.cam_axes;
+    L.d = mk3(__fmaf_rn(A[0], dx, __fmaf_rn(A[1], dy, A[2] * dz)),
+              __fmaf_rn(A[3], dx, __fmaf_rn(A[4], dy, A[5] * dz)),
+              __fmaf_rn(A[6], dx, __fmaf_rn(A[7], dy, A[8] * dz)));
+    float near_t = S.near_clip / dz;
+    L.o = ray_at(mk3(S.cam_o[0], S.cam_o[1], S.cam_o[2]), L.d, near_t);
+    return L;
+}
+
+// ----------------------------------------------------------------------------
+// vector reductions into global memory (sm_90+: red.global.add.v4.f32)
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void red_add_v4(float4 *addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red_add_f32(float *addr, float a) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
+}
+
+// warp-aggregated counter flush
+__device__ __forceinline__ void counter_flush(Counters *C, int slot, unsigned v) {
+    unsigned s = __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(&C->c[slot], (unsigned long long) s);
+}
+
+}  // namespace rcv

@@ -1,0 +1,233 @@
+// rcv_volpathsimple.cuh — per-lane restatement of VolpathSimpleIntegrator
+// (plugins/volpathsimple.py) in Primal and Backward mode, use_drt = False:
+// sample (:51-303), reach_medium (:305-332), sample_real_interaction
+// (:336-390), sample_emitter_for_nee / sample_emitter / estimate_transmittance
+// (:393-517), backpropagate_transmittance (:597-620).
+//
+// Backward mode replays the identical main random stream and turns the AD of
+// the trilinear gathers into reductions on the packed gradient grid
+// (float4 per voxel = d sigma_t, d albedo rgb): one red.global.add.v4.f32 per
+// corner at scattering vertices, one red.global.add.f32 per corner for the
+// sigma_t-only terms.
+#pragma once
+#include "rcv_device.cuh"
+
+namespace rcv {
+
+struct VpsCounts {
+    unsigned coll, scat, g_sig, g_alb;
+};
+
+struct Mei1 {
+    float t;      // inf when invalid
+    V3 p;
+    float st;     // sigma_t(p) (0 when invalid)
+    bool valid;
+};
+
+// Medium::sample_interaction of state `new` with a global majorant
+__device__ __forceinline__ void sample_interaction1(const SceneK &S, const GridK &G, float mu, V3 o, V3 d, float ray_maxt,
+                                                    float u, Mei1 &m, VpsCounts &cnt) {
+    float mint, maxt;
+    bool active = medium_interval(S, o, d, ray_maxt, mint, maxt);
+    float tau = -spec_log(1.f - u);
+    float t = mint + (tau / mu);
+    m.valid = active && (t <= maxt);
+    m.t = m.valid ? t : inf_();
+    m.p = ray_at(o, d, t);
+    m.st = 0.f;
+    if (m.valid) {
+        Tri T = tri_setup(S, G, m.p);
+        m.st = lookup_sigma1(S, G, T);
+        cnt.coll++;
+    }
+}
+
+// AD of sigma_t(p) = scale * trilinear(grid): scatter w_corner * scale * g
+__device__ __forceinline__ void scatter_sigma_t(const SceneK &S, const GridK &G, const GradK &D, V3 p, float g, VpsCounts &cnt) {
+    Tri T = tri_setup(S, G, p);
+    if (!T.inside) return;
+    float sg = S.scale * g;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        red_add_f32(&D.grad[tri_voxel(G, T, k)].x, tri_weight(T, k) * sg);
+    cnt.g_sig++;
+}
+
+// volpathsimple.py:449-517, ratio tracking from o along d over [0, tmax]
+template <bool ADJ>
+__device__ __forceinline__ float estimate_transmittance(const SceneK &S, const GridK &G, const GradK &D, float mu, Pcg &rng,
+                                                        V3 o, V3 d, float tmax, bool active, V3 adjoint, VpsCounts &cnt) {
+    o = ray_at(o, d, 0.f);                                            // :467 (tmin = 0)
+    float tr_acc = active ? 1.f : 0.f;                                // :472
+    while (active) {                                                  // :478
+        float u = pcg_f32(rng);
+        Mei1 m;
+        sample_interaction1(S, G, mu, o, d, tmax, u, m, cnt);         // :482
+        float sn = m.valid ? (mu - m.st) : 0.f;
+        float ce = m.valid ? mu : 0.f;
+        float tr = (ce != 0.f) ? (sn / ce) : sn;                      // :486-489
+        if (m.t > tmax) m.t = inf_();                                 // :493
+        if (!(m.t < inf_())) break;                                   // :494
+        if (ADJ) {                                                    // :496-505
+            float g = 0.f;
+            if (tr > 0.f) {
+                float k = (-1.f / ce) / tr;
+                g += adjoint.x * k; g += adjoint.y * k; g += adjoint.z * k;
+            }
+            scatter_sigma_t(S, G, D, m.p, g, cnt);
+        }
+        tr_acc = tr_acc * tr;                                         // :508
+        o = m.p;                                                      // :510
+        tmax = tmax - m.t;
+        if (!(tr_acc != 0.f)) break;                                  // :515
+    }
+    return tr_acc;
+}
+
+// volpathsimple.py:419-446; returns the scalar transmittance, the sampled direction in `dir`
+template <bool ADJ>
+__device__ __forceinline__ float vps_sample_emitter(const SceneK &S, const GridK &G, const GradK &D, float mu, Pcg &rng, V3 ref_p,
+                                                    V3 adjoint, V3 &dir, VpsCounts &cnt) {
+    float s2x = pcg_f32(rng), s2y = pcg_f32(rng);                     // :431
+    V3 d = uniform_sphere(s2x, s2y);
+    Hit si = box_hit(S, ref_p, d, RCV_LARGEST);                       // :440-441
+    dir = d;
+    return estimate_transmittance<ADJ>(S, G, D, mu, rng, ref_p, d, si.t, si.valid, adjoint, cnt);   // :443
+}
+
+template <bool ADJ>
+__device__ __forceinline__ void vps_trace(const SceneK &S, const GridK &G, const GradK &D, Pcg &rng, Pcg &alt, V3 o, V3 d, V3 dL,
+                                          V3 state_in, V3 &result, VpsCounts &cnt) {
+    const float mu = __ldg(G.majorants + 1);       // state `new` (twostatemedium.py:125-136)
+    const V3 env = mk3(S.env[0], S.env[1], S.env[2]);
+    result = ADJ ? state_in : mk3(0, 0, 0);                           // :68
+    V3 thr = mk3(1, 1, 1);
+    int depth = 0;
+    (void) pcg_f32(rng);                                              // :84
+    // reach_medium (:305-332)
+    Hit si = box_hit(S, o, d, RCV_LARGEST);                           // :311
+    bool escaped = !si.valid, active = si.valid;
+    float ray_maxt = RCV_LARGEST;
+    if (active) {
+        o = offset_p(si.p, si.n, d);                                  // :319
+        Hit si2 = box_hit(S, o, d, RCV_LARGEST);                      // :320
+        active = si2.valid;                                           // :323
+        if (active) { ray_maxt = isfinite(si2.t) ? si2.t : RCV_LARGEST; si = si2; }   // :329-330
+    }
+    bool has_scattered = false;
+    float last_pdf = 1.f;
+    if (active) (void) pcg_f32(rng);                                  // :112 alt_seed_rnd
+
+    while (active) {                                                  // :127
+        float q = fmin_(max3(thr), 0.99f);                            // :130
+        bool perform_rr = depth > S.rr_depth;
+        float rr = pcg_f32(rng);                                      // :133
+        if (!(any_nz(thr) && (!perform_rr || (rr < q)))) break;
+        if (perform_rr) thr = thr * (1.f / q);                        // :134
+
+        // ---- sample_real_interaction (:336-390): delta tracking to the next real collision
+        V3 ro = o; float rmaxt = ray_maxt, running_t = 0.f, mei_t;
+        bool did_scatter;
+        while (true) {                                                // :360
+            float u = pcg_f32(rng);
+            Mei1 m;
+            sample_interaction1(S, G, mu, ro, d, rmaxt, u, m, cnt);   // :361
+            mei_t = m.t + running_t;                                  // :364
+            if (!m.valid) { did_scatter = false; break; }             // :371
+            float r = (mu != 0.f) ? (m.st / mu) : 0.f;                // :367
+            float xi = pcg_f32(rng);                                  // :372
+            if (!(xi >= r)) { did_scatter = true; break; }
+            ro = ro + d * m.t;                                        // :378-380
+            rmaxt = rmaxt - m.t;
+            running_t = running_t + m.t;
+        }
+        bool did_escape = !did_scatter;
+        has_scattered = has_scattered || did_scatter;                 // :150
+        V3 mei_p = mk3(0, 0, 0), albedo = mk3(1, 1, 1);
+        float st = 0.f;
+        Tri T;
+        if (did_scatter) {
+            mei_p = ray_at(o, d, mei_t);                              // :384
+            T = tri_setup(S, G, mei_p);
+            if (ADJ) st = lookup_sigma1(S, G, T);                     // :386-388 (value only used by the adjoint)
+            albedo = lookup_albedo(G, T, 1);                          // :154
+            cnt.scat++;
+        }
+        if (ADJ) {
+            if (did_scatter) {
+                // scattering term (:165-185): backward_from(dL * (sigma_t * albedo) * Li * inv_pdf)
+                V3 inv_pdf = splat3(1.f / st);                        // :175
+                V3 Li = result / vmax3(splat3(1e-8f), albedo);        // :180
+                V3 c = (dL * Li) * inv_pdf;
+                float g_st = (c.x * albedo.x + c.y * albedo.y) + c.z * albedo.z;
+                V3 g_al = c * splat3(st);
+                if (T.inside) {
+                    float sg = S.scale * g_st;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        float w = tri_weight(T, k);
+                        red_add_v4(&D.grad[tri_voxel(G, T, k)], w * sg, w * g_al.x, w * g_al.y, w * g_al.z);
+                    }
+                    cnt.g_sig++; cnt.g_alb++;
+                }
+            }
+            // transmittance term (:194-202, :597-620): 4 uniform points on the last segment
+            V3 aw = dL * result;                                      // :198
+            float interval = did_escape ? si.t : mei_t;               // :601
+            float inv_pdf = interval / 4.f;                           // :617
+            float g = -((aw.x * inv_pdf) + (aw.y * inv_pdf) + (aw.z * inv_pdf));
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j) {
+                float t = pcg_f32(alt) * interval;                    // :608
+                scatter_sigma_t(S, G, D, ray_at(o, d, t), g, cnt);    // :609-613
+            }
+        }
+        thr = thr * albedo;                                           // :206
+        if (did_scatter) depth += 1;                                  // :212
+        active = did_scatter && (depth < S.max_depth);                // :213
+
+        V3 wi = mk3(-d.x, -d.y, -d.z);
+        if (S.use_nee && did_scatter && active) {                     // :219-228, :393-416
+            Pcg nee_rng = rng;                                        // :396 sampler.clone()
+            V3 dir;
+            float tr = vps_sample_emitter<false>(S, G, D, mu, rng, mei_p, mk3(0, 0, 0), dir, cnt);
+            V3 emitted = mk3(env.x / RCV_INV_FOURPI, env.y / RCV_INV_FOURPI, env.z / RCV_INV_FOURPI) * splat3(tr);
+            float phase_val = phase_eval(S, wi, dir);                 // :401
+            V3 nee = ((thr * phase_val) * mis_weight(RCV_INV_FOURPI, phase_val)) * emitted;   // :404
+            if (ADJ) {
+                V3 dir2;
+                (void) vps_sample_emitter<true>(S, G, D, mu, nee_rng, mei_p, dL * nee, dir2, cnt);   // :412-414
+                result = result - nee;                                // :227
+            } else {
+                result = result + nee;                                // :225
+            }
+        }
+        if (did_scatter) {                                            // :234-243
+            (void) pcg_f32(rng);
+            float s2x = pcg_f32(rng), s2y = pcg_f32(rng);
+            float pdf;
+            V3 wo = phase_sample(S, wi, s2x, s2y, pdf);
+            o = mei_p; d = wo; ray_maxt = RCV_LARGEST;
+            last_pdf = pdf;
+        }
+        si = box_hit(S, o, d, ray_maxt);                              // :246-248 (needs_update is always true here)
+        ray_maxt = isfinite(si.t) ? si.t : RCV_LARGEST;
+        if (did_scatter && !si.valid) active = false;                 // :253-254
+        if (did_escape) {                                             // :257-258
+            o = offset_p(si.p, si.n, d);
+            ray_maxt = RCV_LARGEST;
+            escaped = true;
+        }
+    }
+    if (!ADJ) {                                                       // :276-300
+        if (escaped && si.valid) si = box_hit(S, o, d, ray_maxt);     // :277-278
+        if (escaped && !si.valid && !((depth <= 0) && S.hide_emitters)) {
+            float w = 1.f;
+            if (S.use_nee) w = mis_weight(last_pdf, has_scattered ? RCV_INV_FOURPI : 0.f);   // :286-291
+            result = result + (thr * w) * env;                        // :298
+        }
+    }
+}
+
+}  // namespace rcv

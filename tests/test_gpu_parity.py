@@ -1,0 +1,168 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle
+on identical seeded inputs.  Per-lane radiance is bit-exact by construction
+(DESIGN.md §2), so spp=1 accumulators must be *equal*; images with several
+samples per pixel and gradients differ only by float summation order
+(tolerances of BASELINE.json: 1e-4 rel. L2 for images, 1e-3 for gradients)."""
+import numpy as np
+import pytest
+
+from helpers import gpu_set_states, media, rel_l2, small_scene, to_cuda
+
+pytestmark = pytest.mark.gpu
+
+IMG_TOL = 1e-4    # BASELINE.json north_star: primal and CV images
+GRAD_TOL = 1e-3   # BASELINE.json north_star: grid gradient
+
+
+@pytest.fixture(scope="module")
+def setup(oracle, gpu_ctx):
+    cfg = small_scene()
+    desc = cfg.to_desc()
+    old, new = media(24)
+    mo, mn = oracle.OracleMedium(desc, *old), oracle.OracleMedium(desc, *new)
+    gpu_ctx.set_scene(desc)
+    gpu_set_states(gpu_ctx, old, new)
+    return dict(cfg=cfg, desc=desc, old=old, new=new, mo=mo, mn=mn)
+
+
+@pytest.mark.parametrize("tracer", [0, 1])
+def test_twostates_per_lane_bit_exact(oracle, gpu_ctx, setup, tracer):
+    gpu_ctx.set_tracer(tracer)
+    d = setup["desc"]
+    oracle.counters(True); gpu_ctx.counters(True)
+    ao, an = oracle.render_twostates_accum(d, setup["mo"], setup["mn"], seed=3, spp=1)
+    go, gn = gpu_ctx.render_twostates_accum(seed=3, spp=1)
+    oc, gc = oracle.counters(True), gpu_ctx.counters(True)
+    assert np.array_equal(go.cpu().numpy(), ao), "old-state radiance differs from the oracle"
+    assert np.array_equal(gn.cpu().numpy(), an), "new-state radiance differs from the oracle"
+    assert int(oc[0]) == int(gc[0]) and int(oc[1]) == int(gc[1]), (oc, gc)
+    assert int(gc[6]) == d.film_width * d.film_height
+    gpu_ctx.set_tracer(0)
+
+
+def test_majorants(oracle, gpu_ctx, setup):
+    m_old, m_new = gpu_ctx.majorants()
+    assert m_old == setup["mo"].majorant and m_new == setup["mn"].majorant
+
+
+def test_twostates_image(oracle, gpu_ctx, setup):
+    d = setup["desc"]
+    H, F = oracle.render_twostates(d, setup["mo"], setup["mn"], seed=7, spp=16)
+    gH, gF = gpu_ctx.render_twostates(seed=7, spp=16)
+    assert rel_l2(gH.cpu().numpy(), H) < IMG_TOL
+    assert rel_l2(gF.cpu().numpy(), F) < IMG_TOL
+    assert rel_l2(gH.cpu().numpy(), H) < 1e-6   # only summation order differs
+
+
+def test_identity_H_equals_F(gpu_ctx, setup):
+    gpu_set_states(gpu_ctx, setup["new"], setup["new"])
+    H, F = gpu_ctx.render_twostates(seed=11, spp=4)
+    assert np.array_equal(H.cpu().numpy(), F.cpu().numpy())
+    gpu_set_states(gpu_ctx, setup["old"], setup["new"])
+
+
+def test_single_state_primal(oracle, gpu_ctx, setup):
+    d = setup["desc"]
+    for state, m in ((0, setup["mo"]), (1, setup["mn"])):
+        a, _ = oracle.render_twostates_accum(d, m, m, seed=5, spp=1)
+        g = gpu_ctx.render_primal_accum(state, seed=5, spp=1)
+        assert np.array_equal(g.cpu().numpy(), a)
+
+
+def test_spp_sharding_invariance(gpu_ctx, setup):
+    full_o, full_n = gpu_ctx.render_twostates_accum(seed=9, spp=8)
+    acc = None
+    for b, e in ((0, 3), (3, 8)):
+        acc = gpu_ctx.render_twostates_accum(seed=9, spp=8, spp_begin=b, spp_end=e, out=acc)
+    assert rel_l2(acc[0].cpu().numpy(), full_o.cpu().numpy()) < 1e-6
+    assert rel_l2(acc[1].cpu().numpy(), full_n.cpu().numpy()) < 1e-6
+    assert np.array_equal(acc[0][..., 3].cpu().numpy(), full_o[..., 3].cpu().numpy())
+
+
+@pytest.mark.parametrize("tracer", [0, 1])
+def test_volpathsimple_primal_bit_exact(oracle, gpu_ctx, setup, tracer):
+    gpu_ctx.set_tracer(tracer)
+    d = setup["desc"]
+    oracle.counters(True); gpu_ctx.counters(True)
+    a = oracle.vps_render_accum(d, setup["mn"], seed=13, spp=1)
+    g = gpu_ctx.render_adjoint_primal_accum(seed=13, spp=1)
+    oc, gc = oracle.counters(True), gpu_ctx.counters(True)
+    assert np.array_equal(g.cpu().numpy(), a)
+    assert int(oc[2]) == int(gc[2]) and int(oc[3]) == int(gc[3]), (oc, gc)
+    gpu_ctx.set_tracer(0)
+
+
+def test_volpathsimple_backward(oracle, gpu_ctx, setup):
+    d = setup["desc"]
+    rng = np.random.default_rng(0)
+    grad_img = (rng.standard_normal((d.film_height, d.film_width, 3)) / (d.film_height * d.film_width * 3)).astype(np.float32)
+    seed_grad, spp_grad = 0x5D8714D7, 4
+    oracle.counters(True); gpu_ctx.counters(True)
+    gs, ga = oracle.vps_backward(d, setup["mn"], seed_grad, spp_grad, grad_img, threads=1)
+    gpu_ctx.grad_zero()
+    gpu_ctx.render_backward(seed_grad, spp_grad, to_cuda(grad_img))
+    ggs, gga = gpu_ctx.grad_read()
+    oc, gc = oracle.counters(True), gpu_ctx.counters(True)
+    assert [int(v) for v in oc[2:6]] == [int(v) for v in gc[2:6]], (oc, gc)
+    assert rel_l2(ggs.cpu().numpy(), gs) < GRAD_TOL
+    assert rel_l2(gga.cpu().numpy(), ga) < GRAD_TOL
+    assert rel_l2(ggs.cpu().numpy(), gs) < 1e-4    # float atomics vs double accumulation
+
+
+def test_backward_sharding(gpu_ctx, setup):
+    d = setup["desc"]
+    g = to_cuda(np.full((d.film_height, d.film_width, 3), 1e-4, np.float32))
+    gpu_ctx.grad_zero(); gpu_ctx.render_backward(77, 4, g)
+    full_s, full_a = gpu_ctx.grad_read()
+    gpu_ctx.grad_zero()
+    gpu_ctx.render_backward(77, 4, g, 0, 1); gpu_ctx.render_backward(77, 4, g, 1, 4)
+    s, a = gpu_ctx.grad_read()
+    assert rel_l2(s.cpu().numpy(), full_s.cpu().numpy()) < 1e-4
+    assert rel_l2(a.cpu().numpy(), full_a.cpu().numpy()) < 1e-4
+
+
+def test_cv_update_matches_oracle(oracle, gpu_ctx):
+    rng = np.random.default_rng(1)
+    shape = (20, 28, 3)
+    st_o = {k: np.zeros(shape, np.float32) for k in ("img", "v_n", "w_s", "mean_x", "mean_y", "var_x", "var_y", "cov")}
+    st_g = {k: to_cuda(v) for k, v in st_o.items()}
+    stats_n = 0
+    for pre_update in (False, True):
+        for it in range(8):
+            base = rng.random(shape).astype(np.float32)
+            H = (base + 0.05 * rng.standard_normal(shape)).astype(np.float32)
+            F = (base + 0.05 * rng.standard_normal(shape)).astype(np.float32)
+            oracle.cv_update(H, F, st_o, it, 1, stats_n, 0.9, 0.999, pre_update)
+            gpu_ctx.cv_update(to_cuda(H), to_cuda(F), st_g, it, 1, stats_n, 0.9, 0.999, pre_update)
+            if it > 0:
+                stats_n += 1
+            for k in st_o:
+                assert np.array_equal(st_g[k].cpu().numpy(), st_o[k], equal_nan=True), (k, it, pre_update)
+
+
+def test_loss_adam_clamp_upsample(oracle, gpu_ctx):
+    rng = np.random.default_rng(2)
+    img = rng.random((16, 16, 3)).astype(np.float32); ref = rng.random((16, 16, 3)).astype(np.float32)
+    for kind in (0, 1):
+        lo, go = oracle.loss_grad(kind, img, ref)
+        lg, gg = gpu_ctx.loss_grad(kind, to_cuda(img), to_cuda(ref))
+        assert abs(float(lg.item()) - lo) < 1e-6 * max(1.0, abs(lo))
+        assert np.array_equal(gg.cpu().numpy(), go)
+    p = rng.random(1000).astype(np.float32); g = rng.standard_normal(1000).astype(np.float32)
+    m = np.zeros(1000, np.float32); v = np.zeros(1000, np.float32)
+    gp, gm, gv = to_cuda(p), to_cuda(m), to_cuda(v)
+    for t in range(1, 4):
+        oracle.adam(p, g, m, v, t, 5e-3)
+        gpu_ctx.adam_flat(gp, to_cuda(g), gm, gv, t, 5e-3)
+        assert np.array_equal(gp.cpu().numpy(), p) and np.array_equal(gm.cpu().numpy(), m) and np.array_equal(gv.cpu().numpy(), v)
+    oracle.clamp(p, 0.2, 0.7); gpu_ctx.clamp(gp, 0.2, 0.7)
+    assert np.array_equal(gp.cpu().numpy(), p)
+    a = rng.random((3, 4, 5, 3)).astype(np.float32)
+    assert np.array_equal(gpu_ctx.upsample2x(to_cuda(a)).cpu().numpy(), oracle.upsample2x(a))
+
+
+def test_rotation_semantics(gpu_ctx, setup):
+    s_old, a_old = gpu_ctx.medium_read(0)
+    s_new, a_new = gpu_ctx.medium_read(1)
+    assert np.array_equal(s_old.cpu().numpy(), setup["old"][0]) and np.array_equal(a_new.cpu().numpy(), setup["new"][1])
+    assert np.array_equal(s_new.cpu().numpy(), setup["new"][0]) and np.array_equal(a_old.cpu().numpy(), setup["old"][1])
