@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librcv_b200.so")
+# RCV_B200_LIB selects an alternative build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("RCV_B200_LIB") or os.path.join(_HERE, "librcv_b200.so")
 
 RCV_PHASE_ISOTROPIC, RCV_PHASE_HG = 0, 1
 RCV_ADJOINT_VOLPATHSIMPLE = 0

@@ -9,6 +9,7 @@
 
 #include "../../include/rcv_b200.h"
 #include "rcv_internal.h"
+#include "rcv_scene.h"
 
 using namespace rcv;
 
@@ -208,7 +209,7 @@ int rcv_ctx_set_stream(rcv_ctx *c, void *stream) {
 }
 int rcv_ctx_set_tracer(rcv_ctx *c, int kind) {
     if (!c) return fail(RCV_ERR_ARG, "null context");
-    if (kind != RCV_TRACER_WAVEFRONT && kind != RCV_TRACER_SIMPLE) return fail(RCV_ERR_ARG, "unknown tracer kind");
+    if (kind < 0 || kind > 2) return fail(RCV_ERR_ARG, "unknown tracer kind");
     c->tracer = kind;
     return RCV_OK;
 }
@@ -221,20 +222,7 @@ int rcv_scene_set(rcv_ctx *c, const rcv_scene_desc *d) {
     for (int a = 0; a < 3; ++a)
         if (!(d->bbox_max[a] > d->bbox_min[a])) return fail(RCV_ERR_ARG, "degenerate medium bounding box");
     c->desc = *d;
-    SceneK &S = c->S;
-    S.W = d->film_width; S.H = d->film_height;
-    S.rcpW = 1.f / (float) S.W; S.rcpH = 1.f / (float) S.H;
-    for (int i = 0; i < 3; ++i) {
-        S.cam_o[i] = d->cam_origin[i];
-        S.bmin[i] = d->bbox_min[i]; S.bmax[i] = d->bbox_max[i];
-        S.inv_ext[i] = 1.f / (d->bbox_max[i] - d->bbox_min[i]);
-        S.env[i] = d->env_radiance[i];
-    }
-    for (int i = 0; i < 9; ++i) S.cam_axes[i] = d->cam_axes[i];
-    S.tan_x = d->cam_tan_x; S.tan_y = d->cam_tan_y; S.near_clip = d->cam_near_clip;
-    S.scale = d->sigma_t_scale; S.phase = d->phase_type; S.g = d->phase_g;
-    S.sample_emitters = d->sample_emitters; S.env_dist = d->env_dist;
-    S.max_depth = d->max_depth; S.rr_depth = d->rr_depth; S.hide_emitters = d->hide_emitters; S.use_nee = d->use_nee;
+    scene_from_desc(*d, c->S);
     c->has_scene = true;
     return RCV_OK;
 }

@@ -14,6 +14,27 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+// ----------------------------------------------------------------------------
+// RCV_HOST_EMU: the per-lane device code of this directory also compiles with
+// a plain host C++ compiler so that tests/ can single-step the lane state
+// machines on the CPU and compare them with the oracle without a GPU
+// (tests/host_emu).  It is a test harness only: the library (librcv_b200.so)
+// is never built this way and has no CPU path.
+// ----------------------------------------------------------------------------
+#if defined(RCV_HOST_EMU)
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#ifndef __CUDACC__
+static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
+template <typename T> static inline T __ldg(const T *p) { return *p; }
+using std::isfinite; using std::isnan; using std::isinf; using std::max; using std::min;
+#endif
+#endif
+
 namespace rcv {
 
 // ----------------------------------------------------------------------------
@@ -442,6 +463,12 @@ __device__ __forceinline__ Lane lane_setup(const SceneK &S, uint32_t seed, uint3
 // ----------------------------------------------------------------------------
 // vector reductions into global memory (sm_90+: red.global.add.v4.f32)
 // ----------------------------------------------------------------------------
+#if defined(RCV_HOST_EMU) && !defined(__CUDACC__)
+static inline void red_add_v4(float4 *addr, float a, float b, float c, float d) {
+    addr->x += a; addr->y += b; addr->z += c; addr->w += d;
+}
+static inline void red_add_f32(float *addr, float a) { *addr += a; }
+#else
 __device__ __forceinline__ void red_add_v4(float4 *addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -454,5 +481,6 @@ __device__ __forceinline__ void counter_flush(Counters *C, int slot, unsigned v)
     unsigned s = __reduce_add_sync(0xffffffffu, v);
     if ((threadIdx.x & 31) == 0 && s) atomicAdd(&C->c[slot], (unsigned long long) s);
 }
+#endif
 
 }  // namespace rcv

@@ -1,0 +1,226 @@
+// rcv_twostate_wf.cuh — the two-state path tracer as a per-lane event machine.
+//
+// Same estimator and same random-number stream as rcv_twostate.cuh (and as
+// plugins/twostatevolpath.py:141-479), but cut into three event handlers so
+// that a persistent warp can run every handler with (nearly) all of its lanes
+// and refill finished lanes from a work queue:
+//
+//   EV_INIT    start a new path: sampler seed, camera ray, first loop head,
+//              boundary crossing into the medium (or direct environment hit)
+//   EV_COLL    ONE tentative collision on the lane's current segment — the
+//              main path (delta tracking, :180-266) or the shadow ray of next
+//              event estimation (ratio tracking, :408-477): loop head, free
+//              flight, one two-state sigma_t gather, null/real/escape decision
+//   EV_SCAT    a real scattering vertex: two-state albedo gather, throughput
+//              weights, phase sampling, emitter direction sample (:259-344)
+//
+// The handlers contain no warp intrinsics; they also compile for the host
+// (RCV_HOST_EMU) where tests single-step them against the oracle.
+#pragma once
+#include "rcv_twostate.cuh"
+
+namespace rcv {
+
+enum : int { EV_INIT = 0, EV_COLL = 1, EV_SCAT = 2 };
+enum : uint32_t { F_NEEDS_ISECT = 1u, F_SPECULAR = 2u, F_IN_NEE = 4u, F_SI_VALID = 8u };
+
+struct TsLane {
+    int ev;
+    int pix;                // film pixel of the path (-1: outside the film)
+    Pcg rng;
+    V3 o, d;                // main-path ray
+    V3 thr_old, thr_new, L_old, L_new;
+    float si_t;             // distance to the boundary along the current segment
+    float last_pdf;
+    int depth;
+    uint32_t flags;
+    // shadow ray of next event estimation (valid while F_IN_NEE); tr_old/tr_new
+    // double as the stash for (sigma_t old, new) between EV_COLL and EV_SCAT
+    V3 no, nd;
+    float total, tr_old, tr_new, phase_val, ratio;
+};
+
+struct TsSink {
+    float4 *acc_old, *acc_new;
+    unsigned n_coll, n_scat, n_paths;
+};
+
+template <int MODE>
+__device__ __forceinline__ void ts_finish(TsLane &ln, TsSink &sk) {
+    if (ln.pix >= 0) {
+        if (MODE != 2) red_add_v4(sk.acc_old + ln.pix, ln.L_old.x, ln.L_old.y, ln.L_old.z, 1.f);
+        if (MODE != 1) red_add_v4(sk.acc_new + ln.pix, ln.L_new.x, ln.L_new.y, ln.L_new.z, 1.f);
+    }
+    sk.n_paths++;
+    ln.ev = EV_INIT;
+}
+
+// environment "hit" of the main path (:288-308)
+__device__ __forceinline__ void ts_env_hit(const SceneK &S, TsLane &ln) {
+    if ((ln.depth == 0) && S.hide_emitters) return;
+    const V3 env = mk3(S.env[0], S.env[1], S.env[2]);
+    bool count_direct = (ln.depth == 0) || (ln.flags & F_SPECULAR);
+    if (count_direct) {
+        ln.L_new = ln.L_new + ln.thr_new * env;
+        ln.L_old = ln.L_old + ln.thr_old * env;
+    } else {
+        float mis_bsdf = mis_weight(ln.last_pdf, S.use_nee ? RCV_INV_FOURPI : 0.f);
+        ln.L_new = ln.L_new + (ln.thr_new * mis_bsdf) * env;
+        ln.L_old = ln.L_old + (ln.thr_old * mis_bsdf) * env;
+    }
+}
+
+// loop head of the main path (:182-188); false = the path ends here
+__device__ __forceinline__ bool ts_loop_head(const SceneK &S, TsLane &ln) {
+    if (!(any_nz(ln.thr_new) || any_nz(ln.thr_old))) return false;
+    float q = fmin_(max3(vmax3(ln.thr_new, ln.thr_old)), 0.99f);
+    bool perform_rr = ln.depth > S.rr_depth;
+    float rr = pcg_f32(ln.rng);
+    if (perform_rr) {
+        if (!(rr < q)) return false;
+        float rq = 1.f / q;
+        ln.thr_new = ln.thr_new * rq; ln.thr_old = ln.thr_old * rq;
+    }
+    return true;
+}
+
+// surface iterations of a path that is outside the medium (:283-380 with the
+// null BSDF): ends in the environment, or crosses the boundary into the medium
+template <int MODE>
+__device__ __forceinline__ void ts_outside(const SceneK &S, TsLane &ln, TsSink &sk) {
+    while (true) {
+        if (!ts_loop_head(S, ln)) { ts_finish<MODE>(ln, sk); return; }
+        Hit h = box_hit(S, ln.o, ln.d, RCV_LARGEST);
+        if (!h.valid) { ts_env_hit(S, ln); ts_finish<MODE>(ln, sk); return; }
+        (void) pcg_f32(ln.rng); (void) pcg_f32(ln.rng); (void) pcg_f32(ln.rng);   // :347-348
+        ln.o = offset_p(h.p, h.n, ln.d);
+        ln.flags |= F_NEEDS_ISECT;
+        if (!(dot3(h.n, ln.d) > 0.f)) { ln.ev = EV_COLL; return; }   // :378-379 entered the medium
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void ts_init(const SceneK &S, TsLane &ln, TsSink &sk, uint32_t seed, uint32_t spp, uint64_t idx) {
+    Lane L = lane_setup(S, seed, spp, idx);
+    ln.rng = L.rng; ln.o = L.o; ln.d = L.d; ln.pix = L.pix;
+    ln.depth = 0;
+    ln.L_old = mk3(0, 0, 0); ln.L_new = mk3(0, 0, 0);
+    ln.thr_old = mk3(1, 1, 1); ln.thr_new = mk3(1, 1, 1);
+    ln.si_t = 0.f; ln.last_pdf = 1.f;
+    ln.flags = F_NEEDS_ISECT | F_SPECULAR;
+    (void) pcg_f32(ln.rng);                                           // :173 channel draw
+    ts_outside<MODE>(S, ln, sk);
+}
+
+// end of the shadow ray: add the emitter-sampling contribution (:336-344),
+// then the phase ratio of the old state (:360-361); the main path resumes
+__device__ __forceinline__ void ts_nee_finish(const SceneK &S, TsLane &ln) {
+    const V3 env = mk3(S.env[0], S.env[1], S.env[2]);
+    V3 emitter_val = mk3(env.x / RCV_INV_FOURPI, env.y / RCV_INV_FOURPI, env.z / RCV_INV_FOURPI);
+    float mis_em = mis_weight(RCV_INV_FOURPI, ln.phase_val);
+    ln.L_new = ln.L_new + ((ln.thr_new * ln.phase_val) * mis_em) * (emitter_val * splat3(ln.tr_new));
+    ln.L_old = ln.L_old + ((ln.thr_old * ln.phase_val) * mis_em) * (emitter_val * splat3(ln.tr_old));
+    ln.thr_old = ln.thr_old * ln.ratio;
+    ln.flags = (ln.flags & ~F_IN_NEE) | F_NEEDS_ISECT;
+}
+
+template <int MODE>
+__device__ __forceinline__ void ts_collide(const SceneK &S, const GridK &G, float mu, TsLane &ln, TsSink &sk) {
+    const bool nee = (ln.flags & F_IN_NEE) != 0;
+    V3 so, sd; float maxt;
+    if (!nee) {
+        if (!ts_loop_head(S, ln)) { ts_finish<MODE>(ln, sk); return; }
+        so = ln.o; sd = ln.d; maxt = RCV_LARGEST;
+    } else {
+        float remaining = S.env_dist * (1.f - RCV_SHADOW_EPS) - ln.total;   // :409
+        if (!(remaining > 0.f)) { ts_nee_finish(S, ln); return; }           // :411
+        so = ln.no; sd = ln.nd; maxt = remaining;
+    }
+    float u = pcg_f32(ln.rng);                                        // :194 / :422
+    Mei2 m; Tri T;
+    sample_interaction2<MODE>(S, G, mu, so, sd, maxt, u, m, T, sk.n_coll);
+    if (ln.flags & F_NEEDS_ISECT) {                                   // :200-204 / :414-416
+        Hit h = box_hit(S, so, sd, maxt);
+        ln.si_t = h.t;
+        ln.flags = (ln.flags & ~(F_NEEDS_ISECT | F_SI_VALID)) | (h.valid ? F_SI_VALID : 0u);
+    }
+    if (ln.si_t < m.t) m.t = inf_();                                  // :205-206 / :423-424
+    if (m.t < inf_()) {
+        if (nee) {                                                    // :444-452, :472-473
+            ln.no = m.p;
+            ln.si_t = ln.si_t - m.t;
+            float sn_o = mu - m.so, sn_n = mu - m.sn;
+            ln.tr_old = ln.tr_old * ((mu != 0.f) ? (sn_o / mu) : sn_o);
+            ln.tr_new = ln.tr_new * ((mu != 0.f) ? (sn_n / mu) : sn_n);
+            if (!(ln.tr_new != 0.f || ln.tr_old != 0.f)) { ts_nee_finish(S, ln); return; }
+            ln.total += m.t;
+            return;
+        }
+        float sp_new = m.sn / mu, sp_old = m.so / mu;                 // :223-225
+        float prob = (mu != 0.f) ? (sp_new + sp_old) * 0.5f : 0.f;
+        float xi = pcg_f32(ln.rng);                                   // :227
+        if (xi >= prob) {                                             // null collision
+            float sn_n = mu - m.sn, sn_o = mu - m.so;
+            float den = sn_n + sn_o;
+            float w_new = (sn_n * 2.f) / den, w_old = (sn_o * 2.f) / den;
+            ln.o = m.p;
+            ln.si_t = ln.si_t - m.t;
+            ln.thr_new = ln.thr_new * w_new; ln.thr_old = ln.thr_old * w_old;
+            return;
+        }
+        ln.depth += 1;                                                // :249
+        if (!(ln.depth < S.max_depth)) { ts_finish<MODE>(ln, sk); return; }   // :253
+        ln.o = m.p;                                                   // the vertex; the new direction is chosen in EV_SCAT
+        ln.tr_old = m.so; ln.tr_new = m.sn;
+        ln.ev = EV_SCAT;
+        return;
+    }
+    // the segment left the medium
+    if (nee) { ts_nee_finish(S, ln); return; }                        // nothing attenuates the shadow ray outside the box
+    if (!(ln.flags & F_SI_VALID)) { ts_env_hit(S, ln); ts_finish<MODE>(ln, sk); return; }
+    // null-BSDF boundary crossing (:346-379), then one more loop head and the environment
+    (void) pcg_f32(ln.rng); (void) pcg_f32(ln.rng); (void) pcg_f32(ln.rng);
+    if (ts_loop_head(S, ln)) ts_env_hit(S, ln);
+    ts_finish<MODE>(ln, sk);
+}
+
+template <int MODE>
+__device__ __forceinline__ void ts_scatter(const SceneK &S, const GridK &G, TsLane &ln, TsSink &sk) {
+    sk.n_scat++;
+    const float st_old = ln.tr_old, st_new = ln.tr_new;
+    Tri T = tri_setup(S, G, ln.o);
+    V3 a_new = (MODE == 1) ? lookup_albedo(G, T, 0) : lookup_albedo(G, T, 1);
+    V3 a_old = (MODE == 0) ? lookup_albedo(G, T, 0) : a_new;
+    V3 ss_new = splat3(st_new) * a_new, ss_old = splat3(st_old) * a_old;
+    float den = st_new + st_old;                                      // :259-260
+    ln.thr_new = ln.thr_new * ((ss_new * 2.f) / splat3(den));
+    ln.thr_old = ln.thr_old * ((ss_old * 2.f) / splat3(den));
+    (void) pcg_f32(ln.rng);                                           // :275
+    float s2x = pcg_f32(ln.rng), s2y = pcg_f32(ln.rng);
+    V3 wi = mk3(-ln.d.x, -ln.d.y, -ln.d.z);
+    float pdf;
+    V3 wo = phase_sample(S, wi, s2x, s2y, pdf);
+    // pdf > 0 always holds for the isotropic and HG phase functions (:276)
+    ln.d = wo;
+    ln.flags |= F_NEEDS_ISECT;
+    ln.last_pdf = pdf;
+    float ratio = phase_eval(S, wi, wo) / pdf;                        // :360-361
+    ln.ev = EV_COLL;
+    if (S.use_nee) {                                                  // :315-325
+        ln.flags &= ~F_SPECULAR;
+        if (!S.sample_emitters) ln.flags |= F_SPECULAR;
+        if (S.sample_emitters) {
+            float e2x = pcg_f32(ln.rng), e2y = pcg_f32(ln.rng);       // :393
+            ln.nd = uniform_sphere(e2x, e2y);
+            ln.no = ln.o;
+            ln.total = 0.f; ln.tr_old = 1.f; ln.tr_new = 1.f;
+            ln.phase_val = phase_eval(S, wi, ln.nd);
+            ln.ratio = ratio;
+            ln.flags |= F_IN_NEE | F_NEEDS_ISECT;
+            return;
+        }
+    }
+    ln.thr_old = ln.thr_old * ratio;
+}
+
+}  // namespace rcv

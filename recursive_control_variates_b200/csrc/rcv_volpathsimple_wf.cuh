@@ -1,0 +1,300 @@
+// rcv_volpathsimple_wf.cuh — VolpathSimpleIntegrator (plugins/volpathsimple.py,
+// use_drt = False) as a per-lane event machine, for the persistent-warp
+// scheduler.  Same estimator, same random streams and the same arithmetic as
+// rcv_volpathsimple.cuh; cut into
+//
+//   EV_INIT   begin a path (pass 1, primal) or resume it as pass 2 (adjoint
+//             replay of the identical stream, RBIntegrator.render_backward)
+//   EV_COLL   ONE tentative collision: a delta-tracking step of
+//             sample_real_interaction (:360-380) or a ratio-tracking step of
+//             estimate_transmittance (:478-515) — in the adjoint's NEE replay
+//             (:406-414) with the sigma_t gradient scatter of :496-505
+//   EV_SCAT   a path vertex (real collision or medium exit): coefficient
+//             gathers, the adjoint's scattering (:165-185) and transmittance
+//             (:194-202, :597-620) gradient scatters, NEE set-up (:393-446)
+//
+// The handlers contain no warp intrinsics and also compile for the host
+// (RCV_HOST_EMU) where tests single-step them against the oracle.
+#pragma once
+#include "rcv_twostate_wf.cuh"
+#include "rcv_volpathsimple.cuh"
+
+namespace rcv {
+
+enum : uint32_t {
+    VF_ADJ = 1u,          // this is pass 2 (adjoint)
+    VF_HAS_SCAT = 2u,
+    VF_ESCAPED = 4u,
+    VF_IN_NEE = 8u,
+    VF_REPLAY = 16u,      // NEE transmittance replay with gradients
+    VF_HEAD = 32u,        // next main-path collision starts with the loop head (:129-134)
+    VF_DID_SCATTER = 64u,
+    VF_PASS2 = 128u       // pass 1 finished, EV_INIT must resume the lane as pass 2
+};
+
+struct VpLane {
+    int ev, pix, depth;
+    uint32_t idx, flags;
+    Pcg rng, alt;
+    uint64_t saved;         // main sampler state parked during the NEE / its replay
+    V3 o, d;                // current ray (origin = last vertex)
+    float ray_maxt;         // distance to the boundary along it (== si.t)
+    V3 thr, result, dL;
+    float last_pdf;
+    V3 ro;                  // running origin: delta tracking, or the shadow ray
+    float rmaxt, running_t, mei_t;
+    V3 nd;                  // shadow-ray direction
+    float tr_acc;
+    V3 nee;                 // NEE contribution of this vertex (needed after the replay)
+};
+
+struct VpSink {
+    float4 *accum;          // primal render target (H,W,4) or null
+    GradK D;                // packed gradient grid (adjoint)
+    const float *grad_img, *film_w;
+    uint32_t seed, spp, alt_seed;
+    VpsCounts cnt;
+    unsigned n_paths;
+};
+
+template <bool BW>
+__device__ __forceinline__ void vp_end_pass(const SceneK &S, VpLane &ln, VpSink &sk) {
+    sk.n_paths++;
+    if (ln.flags & VF_ADJ) { ln.flags = 0; ln.ev = EV_INIT; return; }
+    // primal pass: environment contribution of escaped lanes (:276-300)
+    if ((ln.flags & VF_ESCAPED) && !((ln.depth <= 0) && S.hide_emitters)) {
+        const V3 env = mk3(S.env[0], S.env[1], S.env[2]);
+        float w = 1.f;
+        if (S.use_nee) w = mis_weight(ln.last_pdf, (ln.flags & VF_HAS_SCAT) ? RCV_INV_FOURPI : 0.f);
+        ln.result = ln.result + (ln.thr * w) * env;
+    }
+    ln.ev = EV_INIT;
+    if (!BW) {
+        if (ln.pix >= 0) red_add_v4(sk.accum + ln.pix, ln.result.x, ln.result.y, ln.result.z, 1.f);
+        ln.flags = 0;
+        return;
+    }
+    // dL = d(develop o put)/dL * grad_in: box filter -> grad_in[pixel] / W[pixel]
+    ln.dL = mk3(0, 0, 0);
+    if (ln.pix >= 0) {
+        float w = __ldg(sk.film_w + ln.pix);
+        float dv = (w == 0.f) ? 1.f : w;
+        ln.dL = mk3(__ldg(sk.grad_img + 3 * ln.pix) / dv, __ldg(sk.grad_img + 3 * ln.pix + 1) / dv,
+                    __ldg(sk.grad_img + 3 * ln.pix + 2) / dv);
+    }
+    ln.flags = VF_PASS2;
+}
+
+// start pass 1 (adj = false) or pass 2 (adj = true) of lane ln.idx: camera ray,
+// dummy channel draw (:84), reach_medium (:305-332), alt_seed_rnd draw (:112)
+template <bool BW>
+__device__ __forceinline__ void vp_start_pass(const SceneK &S, VpLane &ln, VpSink &sk, bool adj) {
+    Lane L = lane_setup(S, sk.seed, sk.spp, (uint64_t) ln.idx);
+    ln.rng = L.rng; ln.o = L.o; ln.d = L.d; ln.pix = L.pix;
+    if (adj) sampler_seed(ln.alt, sk.alt_seed, ln.idx);              // :119-120
+    else ln.result = mk3(0, 0, 0);                                    // :68 (pass 2 starts from state_in = pass-1 result)
+    ln.thr = mk3(1, 1, 1);
+    ln.depth = 0;
+    ln.last_pdf = 1.f;
+    ln.flags = adj ? VF_ADJ : 0u;
+    (void) pcg_f32(ln.rng);                                           // :84
+    Hit si = box_hit(S, ln.o, ln.d, RCV_LARGEST);                     // :311
+    bool active = si.valid;
+    if (!si.valid) ln.flags |= VF_ESCAPED;
+    ln.ray_maxt = RCV_LARGEST;
+    if (active) {
+        ln.o = offset_p(si.p, si.n, ln.d);                            // :319
+        Hit si2 = box_hit(S, ln.o, ln.d, RCV_LARGEST);                // :320
+        active = si2.valid;                                           // :323
+        if (active) ln.ray_maxt = isfinite(si2.t) ? si2.t : RCV_LARGEST;   // :329
+    }
+    if (!active) { vp_end_pass<BW>(S, ln, sk); return; }
+    (void) pcg_f32(ln.rng);                                           // :112 alt_seed_rnd
+    ln.flags |= VF_HEAD;
+    ln.ev = EV_COLL;
+}
+
+template <bool BW>
+__device__ __forceinline__ void vp_begin(const SceneK &S, VpLane &ln, VpSink &sk, uint64_t idx) {
+    ln.idx = (uint32_t) idx;
+    vp_start_pass<BW>(S, ln, sk, false);
+}
+template <bool BW>
+__device__ __forceinline__ void vp_resume(const SceneK &S, VpLane &ln, VpSink &sk) {
+    vp_start_pass<BW>(S, ln, sk, true);
+}
+
+// after the vertex (and its NEE): phase sampling, new ray, boundary distance (:234-258)
+template <bool BW>
+__device__ __forceinline__ void vp_post_vertex(const SceneK &S, VpLane &ln, VpSink &sk, bool active) {
+    const bool did_scatter = (ln.flags & VF_DID_SCATTER) != 0;
+    if (!did_scatter) {                                               // did_escape (:257-258)
+        ln.flags |= VF_ESCAPED;
+        vp_end_pass<BW>(S, ln, sk);
+        return;
+    }
+    V3 mei_p = ray_at(ln.o, ln.d, ln.mei_t);
+    V3 wi = mk3(-ln.d.x, -ln.d.y, -ln.d.z);
+    (void) pcg_f32(ln.rng);                                           // :235
+    float s2x = pcg_f32(ln.rng), s2y = pcg_f32(ln.rng);
+    float pdf;
+    V3 wo = phase_sample(S, wi, s2x, s2y, pdf);
+    ln.o = mei_p; ln.d = wo;
+    ln.last_pdf = pdf;
+    Hit si = box_hit(S, ln.o, ln.d, RCV_LARGEST);                     // :247
+    ln.ray_maxt = isfinite(si.t) ? si.t : RCV_LARGEST;                // :248
+    if (!si.valid) active = false;                                    // :253-254
+    if (!active) { vp_end_pass<BW>(S, ln, sk); return; }
+    ln.flags |= VF_HEAD;
+    ln.ev = EV_COLL;
+}
+
+// (re)start the shadow ray at the current vertex; false when it has no extent
+__device__ __forceinline__ bool vp_nee_start(const SceneK &S, VpLane &ln) {
+    V3 mei_p = ray_at(ln.o, ln.d, ln.mei_t);
+    Hit si = box_hit(S, mei_p, ln.nd, RCV_LARGEST);                   // :440-441
+    ln.ro = ray_at(mei_p, ln.nd, 0.f);                                // :467 (tmin = 0)
+    ln.rmaxt = si.t;
+    ln.tr_acc = si.valid ? 1.f : 0.f;                                 // :472
+    return si.valid;
+}
+
+// the shadow ray (or its replay) ended
+template <bool BW>
+__device__ __forceinline__ void vp_nee_done(const SceneK &S, VpLane &ln, VpSink &sk) {
+    while (true) {
+        if (!(ln.flags & VF_REPLAY)) {
+            const V3 env = mk3(S.env[0], S.env[1], S.env[2]);
+            V3 wi = mk3(-ln.d.x, -ln.d.y, -ln.d.z);
+            V3 emitted = mk3(env.x / RCV_INV_FOURPI, env.y / RCV_INV_FOURPI, env.z / RCV_INV_FOURPI) * splat3(ln.tr_acc);
+            float phase_val = phase_eval(S, wi, ln.nd);               // :401
+            ln.nee = ((ln.thr * phase_val) * mis_weight(RCV_INV_FOURPI, phase_val)) * emitted;   // :404
+            if (BW && (ln.flags & VF_ADJ)) {
+                // replay with the cloned sampler (:396, :412-414): park the advanced state
+                uint64_t after = ln.rng.state;
+                ln.rng.state = ln.saved;
+                ln.saved = after;
+                (void) pcg_u32(ln.rng); (void) pcg_u32(ln.rng);       // the direction sample (:431), same values
+                ln.flags |= VF_REPLAY;
+                if (vp_nee_start(S, ln)) return;                      // EV_COLL continues in replay mode
+                continue;                                             // no extent: replay ends immediately
+            }
+            ln.result = ln.result + ln.nee;                           // :225
+        } else {
+            ln.rng.state = ln.saved;                                  // back to the main sampler
+            ln.result = ln.result - ln.nee;                           // :227
+        }
+        ln.flags &= ~(VF_IN_NEE | VF_REPLAY);
+        vp_post_vertex<BW>(S, ln, sk, true);
+        return;
+    }
+}
+
+template <bool BW>
+__device__ __forceinline__ void vp_collide(const SceneK &S, const GridK &G, float mu, VpLane &ln, VpSink &sk) {
+    if (ln.flags & VF_IN_NEE) {
+        // estimate_transmittance step (:478-515)
+        float u = pcg_f32(ln.rng);
+        Mei1 m;
+        sample_interaction1(S, G, mu, ln.ro, ln.nd, ln.rmaxt, u, m, sk.cnt);   // :482
+        float sn = m.valid ? (mu - m.st) : 0.f;
+        float ce = m.valid ? mu : 0.f;
+        float tr = (ce != 0.f) ? (sn / ce) : sn;                      // :486-489
+        if (m.t > ln.rmaxt) m.t = inf_();                             // :493
+        if (!(m.t < inf_())) { vp_nee_done<BW>(S, ln, sk); return; }  // :494
+        if (BW && (ln.flags & VF_REPLAY)) {                           // :496-505
+            V3 adjoint = ln.dL * ln.nee;                              // :412
+            float g = 0.f;
+            if (tr > 0.f) {
+                float k = (-1.f / ce) / tr;
+                g += adjoint.x * k; g += adjoint.y * k; g += adjoint.z * k;
+            }
+            scatter_sigma_t(S, G, sk.D, m.p, g, sk.cnt);
+        }
+        ln.tr_acc = ln.tr_acc * tr;                                   // :508
+        ln.ro = m.p;                                                  // :510
+        ln.rmaxt = ln.rmaxt - m.t;
+        if (!(ln.tr_acc != 0.f)) vp_nee_done<BW>(S, ln, sk);          // :515
+        return;
+    }
+    if (ln.flags & VF_HEAD) {                                         // loop head (:129-134)
+        float q = fmin_(max3(ln.thr), 0.99f);
+        bool perform_rr = ln.depth > S.rr_depth;
+        float rr = pcg_f32(ln.rng);
+        if (!(any_nz(ln.thr) && (!perform_rr || (rr < q)))) { vp_end_pass<BW>(S, ln, sk); return; }
+        if (perform_rr) ln.thr = ln.thr * (1.f / q);
+        ln.ro = ln.o; ln.rmaxt = ln.ray_maxt; ln.running_t = 0.f;     // :349-351
+        ln.flags &= ~VF_HEAD;
+    }
+    float u = pcg_f32(ln.rng);                                        // :361
+    Mei1 m;
+    sample_interaction1(S, G, mu, ln.ro, ln.d, ln.rmaxt, u, m, sk.cnt);
+    ln.mei_t = m.t + ln.running_t;                                    // :364
+    if (!m.valid) { ln.flags &= ~VF_DID_SCATTER; ln.ev = EV_SCAT; return; }   // :371 escape
+    float r = (mu != 0.f) ? (m.st / mu) : 0.f;                        // :367
+    float xi = pcg_f32(ln.rng);                                       // :372
+    if (!(xi >= r)) { ln.flags |= VF_DID_SCATTER; ln.ev = EV_SCAT; return; }
+    ln.ro = ln.ro + ln.d * m.t;                                       // :378-380
+    ln.rmaxt = ln.rmaxt - m.t;
+    ln.running_t = ln.running_t + m.t;
+}
+
+template <bool BW>
+__device__ __forceinline__ void vp_vertex(const SceneK &S, const GridK &G, float mu, VpLane &ln, VpSink &sk) {
+    const bool did_scatter = (ln.flags & VF_DID_SCATTER) != 0;
+    const bool adj = BW && (ln.flags & VF_ADJ);
+    if (did_scatter) ln.flags |= VF_HAS_SCAT;                         // :150
+    V3 mei_p = mk3(0, 0, 0), albedo = mk3(1, 1, 1);
+    float st = 0.f;
+    Tri T;
+    if (did_scatter) {
+        mei_p = ray_at(ln.o, ln.d, ln.mei_t);                         // :384
+        T = tri_setup(S, G, mei_p);
+        if (adj) st = lookup_sigma1(S, G, T);                         // :386-388
+        albedo = lookup_albedo(G, T, 1);                              // :154
+        sk.cnt.scat++;
+    }
+    if (adj) {
+        if (did_scatter) {                                            // scattering term (:165-185)
+            V3 inv_pdf = splat3(1.f / st);
+            V3 Li = ln.result / vmax3(splat3(1e-8f), albedo);
+            V3 c = (ln.dL * Li) * inv_pdf;
+            float g_st = (c.x * albedo.x + c.y * albedo.y) + c.z * albedo.z;
+            V3 g_al = c * splat3(st);
+            if (T.inside) {
+                float sg = S.scale * g_st;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    float w = tri_weight(T, k);
+                    red_add_v4(&sk.D.grad[tri_voxel(G, T, k)], w * sg, w * g_al.x, w * g_al.y, w * g_al.z);
+                }
+                sk.cnt.g_sig++; sk.cnt.g_alb++;
+            }
+        }
+        // transmittance term (:194-202, :597-620)
+        V3 aw = ln.dL * ln.result;
+        float interval = did_scatter ? ln.mei_t : ln.ray_maxt;        // :601 (si.t == ray.maxt)
+        float inv_pdf = interval / 4.f;
+        float g = -((aw.x * inv_pdf) + (aw.y * inv_pdf) + (aw.z * inv_pdf));
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+            float t = pcg_f32(ln.alt) * interval;                     // :608
+            scatter_sigma_t(S, G, sk.D, ray_at(ln.o, ln.d, t), g, sk.cnt);
+        }
+    }
+    ln.thr = ln.thr * albedo;                                         // :206
+    if (did_scatter) ln.depth += 1;                                   // :212
+    bool active = did_scatter && (ln.depth < S.max_depth);            // :213
+    if (S.use_nee && did_scatter && active) {                         // :219-228 -> :393-446
+        ln.saved = ln.rng.state;                                      // :396 sampler.clone()
+        float s2x = pcg_f32(ln.rng), s2y = pcg_f32(ln.rng);           // :431
+        ln.nd = uniform_sphere(s2x, s2y);
+        ln.flags |= VF_IN_NEE;
+        ln.ev = EV_COLL;
+        if (!vp_nee_start(S, ln)) vp_nee_done<BW>(S, ln, sk);
+        return;
+    }
+    vp_post_vertex<BW>(S, ln, sk, active);
+}
+
+}  // namespace rcv

@@ -1,0 +1,110 @@
+// emu.cpp — TEST HARNESS: compiles the per-lane event machines of
+// recursive_control_variates_b200/csrc for the host (RCV_HOST_EMU) and
+// single-steps them lane by lane, so that their logic and arithmetic can be
+// compared with the oracle without a GPU.  Never part of the product.
+#define RCV_HOST_EMU 1
+#include <cstdint>
+#include <cstdlib>
+#include <vector>
+
+#include "../../recursive_control_variates_b200/csrc/rcv_scene.h"
+#include "../../recursive_control_variates_b200/csrc/rcv_twostate_wf.cuh"
+#include "../../recursive_control_variates_b200/csrc/rcv_volpathsimple_wf.cuh"
+
+using namespace rcv;
+
+namespace {
+
+struct Packed {
+    std::vector<float2> sig2;
+    std::vector<float> sig1;
+    std::vector<float4> alb2;
+    float maj[2];
+    GridK G;
+};
+
+void pack(const rcv_scene_desc &d, const float *so, const float *ao, const float *sn, const float *an, int nz, int ny, int nx,
+          Packed &P) {
+    size_t n = (size_t) nz * ny * nx;
+    P.sig2.resize(n); P.sig1.resize(n); P.alb2.resize(2 * n);
+    float mo = so[0], mn = sn[0];
+    for (size_t v = 0; v < n; ++v) {
+        P.sig2[v] = make_float2(so[v], sn[v]);
+        P.sig1[v] = sn[v];
+        P.alb2[2 * v] = make_float4(ao[3 * v], ao[3 * v + 1], ao[3 * v + 2], 0.f);
+        P.alb2[2 * v + 1] = make_float4(an[3 * v], an[3 * v + 1], an[3 * v + 2], 0.f);
+        mo = fmax_(mo, so[v]); mn = fmax_(mn, sn[v]);
+    }
+    P.maj[0] = d.sigma_t_scale * mo; P.maj[1] = d.sigma_t_scale * mn;
+    P.G.sig2 = P.sig2.data(); P.G.sig1 = P.sig1.data(); P.G.alb2 = P.alb2.data();
+    P.G.nx = nx; P.G.ny = ny; P.G.nz = nz; P.G.majorants = P.maj;
+}
+
+template <int MODE>
+void run_twostates(const SceneK &S, const GridK &G, uint32_t seed, uint32_t spp, float4 *acc_old, float4 *acc_new, uint64_t *cnt) {
+    const float mu = combined_majorant<MODE>(G);
+    TsSink sk; sk.acc_old = acc_old; sk.acc_new = acc_new; sk.n_coll = sk.n_scat = sk.n_paths = 0;
+    uint64_t n = (uint64_t) S.W * S.H * spp;
+    for (uint64_t idx = 0; idx < n; ++idx) {
+        TsLane ln;
+        ts_init<MODE>(S, ln, sk, seed, spp, idx);
+        while (ln.ev != EV_INIT) {
+            if (ln.ev == EV_COLL) ts_collide<MODE>(S, G, mu, ln, sk);
+            else ts_scatter<MODE>(S, G, ln, sk);
+        }
+        cnt[0] += sk.n_coll; cnt[1] += sk.n_scat; cnt[6] += sk.n_paths;
+        sk.n_coll = sk.n_scat = sk.n_paths = 0;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int emu_twostates(const rcv_scene_desc *d, const float *so, const float *ao, const float *sn, const float *an, int nz, int ny,
+                  int nx, uint32_t seed, uint32_t spp, int mode, float *acc_old, float *acc_new, uint64_t *counters) {
+    SceneK S; scene_from_desc(*d, S);
+    Packed P; pack(*d, so, ao, sn, an, nz, ny, nx, P);
+    for (int i = 0; i < 8; ++i) counters[i] = 0;
+    if (mode == 0) run_twostates<0>(S, P.G, seed, spp, (float4 *) acc_old, (float4 *) acc_new, counters);
+    else if (mode == 1) run_twostates<1>(S, P.G, seed, spp, (float4 *) acc_old, (float4 *) acc_new, counters);
+    else run_twostates<2>(S, P.G, seed, spp, (float4 *) acc_old, (float4 *) acc_new, counters);
+    return 0;
+}
+
+// volpathsimple: primal render (backward == 0) or the two-pass adjoint; the
+// gradient grid is the packed float4 layout of the library
+int emu_vps(const rcv_scene_desc *d, const float *sn, const float *an, int nz, int ny, int nx, uint32_t seed, uint32_t spp,
+            int backward, uint32_t alt_seed, const float *grad_img, const float *film_w, float *accum, float *grad4,
+            uint64_t *counters) {
+    SceneK S; scene_from_desc(*d, S);
+    Packed P; pack(*d, sn, an, sn, an, nz, ny, nx, P);
+    for (int i = 0; i < 8; ++i) counters[i] = 0;
+    VpSink sk; sk.accum = (float4 *) accum; sk.D.grad = (float4 *) grad4; sk.grad_img = grad_img; sk.film_w = film_w;
+    sk.seed = seed; sk.spp = spp; sk.alt_seed = alt_seed;
+    sk.cnt.coll = sk.cnt.scat = sk.cnt.g_sig = sk.cnt.g_alb = 0; sk.n_paths = 0;
+    const float mu = P.maj[1];
+    uint64_t n = (uint64_t) S.W * S.H * spp;
+    for (uint64_t idx = 0; idx < n; ++idx) {
+        VpLane ln;
+        ln.flags = 0;
+        if (backward) vp_begin<true>(S, ln, sk, idx); else vp_begin<false>(S, ln, sk, idx);
+        while (true) {
+            if (ln.ev == EV_INIT) {
+                if (!(ln.flags & VF_PASS2)) break;
+                vp_resume<true>(S, ln, sk);
+            } else if (backward) {
+                if (ln.ev == EV_COLL) vp_collide<true>(S, P.G, mu, ln, sk);
+                else vp_vertex<true>(S, P.G, mu, ln, sk);
+            } else {
+                if (ln.ev == EV_COLL) vp_collide<false>(S, P.G, mu, ln, sk);
+                else vp_vertex<false>(S, P.G, mu, ln, sk);
+            }
+        }
+    }
+    counters[2] = sk.cnt.coll; counters[3] = sk.cnt.scat; counters[4] = sk.cnt.g_sig; counters[5] = sk.cnt.g_alb;
+    counters[6] = sk.n_paths;
+    return 0;
+}
+
+}  // extern "C"

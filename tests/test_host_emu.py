@@ -1,0 +1,108 @@
+"""CPU check of the CUDA lane event machines (csrc/rcv_*_wf.cuh) compiled for the
+host (tests/host_emu): every lane is single-stepped through its EV_INIT /
+EV_COLL / EV_SCAT handlers and must reproduce the oracle bit for bit (spp = 1
+accumulators, event counters) — the same comparison the GPU tests make, but
+runnable without a GPU.  The harness is test infrastructure, not a CPU path of
+the product."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import media, rel_l2, small_scene
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU_DIR = os.path.join(HERE, "host_emu")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.run(["make", "-C", EMU_DIR], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+    lib = C.CDLL(os.path.join(EMU_DIR, "librcv_emu.so"))
+    f32 = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+    u64 = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
+    lib.emu_twostates.argtypes = [C.c_void_p, f32, f32, f32, f32, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int,
+                                  f32, f32, u64]
+    lib.emu_vps.argtypes = [C.c_void_p, f32, f32, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32,
+                            C.c_void_p, C.c_void_p, f32, f32, u64]
+    return lib
+
+
+@pytest.fixture(scope="module")
+def setup(oracle):
+    cfg = small_scene(40, 36)
+    desc = cfg.to_desc()
+    old, new = media(20)
+    return dict(desc=desc, old=old, new=new, mo=oracle.OracleMedium(desc, *old), mn=oracle.OracleMedium(desc, *new))
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_twostate_event_machine_matches_oracle(oracle, emu, setup, mode):
+    d = setup["desc"]
+    (so, ao), (sn, an) = setup["old"], setup["new"]
+    H, W = d.film_height, d.film_width
+    acc_o = np.zeros((H, W, 4), np.float32); acc_n = np.zeros((H, W, 4), np.float32)
+    cnt = np.zeros(8, np.uint64)
+    emu.emu_twostates(C.addressof(d), so, ao, sn, an, *so.shape[:3], 21, 1, mode, acc_o, acc_n, cnt)
+    oracle.counters(True)
+    mo, mn = setup["mo"], setup["mn"]
+    if mode == 1:
+        mn = mo
+    elif mode == 2:
+        mo = mn
+    ref_o, ref_n = oracle.render_twostates_accum(d, mo, mn, 21, 1)
+    oc = oracle.counters(True)
+    if mode != 2:
+        assert np.array_equal(acc_o, ref_o)
+    if mode != 1:
+        assert np.array_equal(acc_n, ref_n)
+    assert int(cnt[0]) == int(oc[0]) and int(cnt[1]) == int(oc[1])
+    assert int(cnt[6]) == H * W
+
+
+def test_twostate_event_machine_multi_spp(oracle, emu, setup):
+    d = setup["desc"]
+    (so, ao), (sn, an) = setup["old"], setup["new"]
+    H, W = d.film_height, d.film_width
+    acc_o = np.zeros((H, W, 4), np.float32); acc_n = np.zeros((H, W, 4), np.float32)
+    cnt = np.zeros(8, np.uint64)
+    emu.emu_twostates(C.addressof(d), so, ao, sn, an, *so.shape[:3], 5, 4, 0, acc_o, acc_n, cnt)
+    ref_o, ref_n = oracle.render_twostates_accum(d, setup["mo"], setup["mn"], 5, 4)
+    # the harness and the oracle both splat in lane order: identical sums
+    assert np.array_equal(acc_o, ref_o) and np.array_equal(acc_n, ref_n)
+
+
+def test_volpathsimple_event_machine_primal(oracle, emu, setup):
+    d = setup["desc"]
+    sn, an = setup["new"]
+    H, W = d.film_height, d.film_width
+    acc = np.zeros((H, W, 4), np.float32); g4 = np.zeros((*sn.shape[:3], 4), np.float32)
+    cnt = np.zeros(8, np.uint64)
+    emu.emu_vps(C.addressof(d), sn, an, *sn.shape[:3], 33, 1, 0, 0, None, None, acc, g4, cnt)
+    oracle.counters(True)
+    ref = oracle.vps_render_accum(d, setup["mn"], 33, 1)
+    oc = oracle.counters(True)
+    assert np.array_equal(acc, ref)
+    assert [int(v) for v in cnt[2:4]] == [int(v) for v in oc[2:4]]
+
+
+def test_volpathsimple_event_machine_backward(oracle, emu, setup):
+    d = setup["desc"]
+    sn, an = setup["new"]
+    H, W = d.film_height, d.film_width
+    rng = np.random.default_rng(3)
+    grad_img = (rng.standard_normal((H, W, 3)) / (H * W * 3)).astype(np.float32)
+    seed_grad, spp = 0xC09848F2, 2
+    film_w = oracle.film_weights(d, seed_grad, spp)
+    acc = np.zeros((H, W, 4), np.float32); g4 = np.zeros((*sn.shape[:3], 4), np.float32)
+    cnt = np.zeros(8, np.uint64)
+    emu.emu_vps(C.addressof(d), sn, an, *sn.shape[:3], seed_grad, spp, 1, oracle.alt_seed(seed_grad),
+                grad_img.ctypes.data, film_w.ctypes.data, acc, g4, cnt)
+    oracle.counters(True)
+    gs, ga = oracle.vps_backward(d, setup["mn"], seed_grad, spp, grad_img, threads=1, film_w=film_w)
+    oc = oracle.counters(True)
+    assert [int(v) for v in cnt[2:7]] == [int(v) for v in oc[2:7]]
+    assert rel_l2(g4[..., 0:1], gs) < 1e-5       # float vs double accumulation
+    assert rel_l2(g4[..., 1:4], ga) < 1e-5
