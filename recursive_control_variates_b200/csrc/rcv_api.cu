@@ -47,7 +47,8 @@ struct rcv_ctx {
     float2 *sig2 = nullptr;
     float *sig1 = nullptr;
     float4 *alb2 = nullptr;
-    float4 *grad = nullptr;
+    float *grad = nullptr;       // [pad4(nvox) floats d sigma_t][nvox float4 d albedo]
+    size_t grad_floats = 0;
     float *majorants = nullptr;
     float *block_max = nullptr;
     int n_rot_blocks = 0;
@@ -76,6 +77,11 @@ struct rcv_ctx {
         c.stream = stream; c.sm_count = sm_count; c.tracer = tracer;
         c.counters = counters; c.work_counter = work; c.launches = &launches;
         return c;
+    }
+    GradK gradk() const {
+        GradK g;
+        g.gsig = grad; g.galb = (float4 *) (grad + ((nvox + 3) / 4) * 4);
+        return g;
     }
     GridK gridk() const {
         GridK g;
@@ -234,11 +240,12 @@ int rcv_medium_rotate(rcv_ctx *c, const float *sigma_t_in, const float *albedo_i
     size_t nvox = (size_t) nz * ny * nx;
     LaunchCfg cfg = c->cfg();
     if (nz != c->nz || ny != c->ny || nx != c->nx) {
-        float2 *sig2; float *sig1; float4 *alb2, *grad; float *bm;
+        float2 *sig2; float *sig1; float4 *alb2; float *grad; float *bm;
+        size_t grad_floats = ((nvox + 3) / 4) * 4 + 4 * nvox;
         CK(cudaMalloc(&sig2, nvox * sizeof(float2)));
         CK(cudaMalloc(&sig1, nvox * sizeof(float)));
         CK(cudaMalloc(&alb2, 2 * nvox * sizeof(float4)));
-        CK(cudaMalloc(&grad, nvox * sizeof(float4)));
+        CK(cudaMalloc(&grad, grad_floats * sizeof(float)));
         uint64_t want = (nvox + 255) / 256, cap = (uint64_t) c->sm_count * 8;
         int nb = (int) (want < cap ? want : cap);
         CK(cudaMalloc(&bm, nb * sizeof(float)));
@@ -252,10 +259,10 @@ int rcv_medium_rotate(rcv_ctx *c, const float *sigma_t_in, const float *albedo_i
             CK(cudaMemsetAsync(alb2, 0, 2 * nvox * sizeof(float4), c->stream));
             CK(cudaMemsetAsync(c->majorants, 0, 2 * sizeof(float), c->stream));
         }
-        CK(cudaMemsetAsync(grad, 0, nvox * sizeof(float4), c->stream));
+        CK(cudaMemsetAsync(grad, 0, grad_floats * sizeof(float), c->stream));
         free_medium(c);
         c->sig2 = sig2; c->sig1 = sig1; c->alb2 = alb2; c->grad = grad; c->block_max = bm; c->n_rot_blocks = nb;
-        c->nz = nz; c->ny = ny; c->nx = nx; c->nvox = nvox;
+        c->nz = nz; c->ny = ny; c->nx = nx; c->nvox = nvox; c->grad_floats = grad_floats;
     }
     CK(launch_rotate(cfg, sigma_t_in, albedo_in, nvox, c->S.scale, c->sig2, c->sig1, c->alb2, c->block_max, c->n_rot_blocks,
                      c->majorants));
@@ -346,7 +353,7 @@ int rcv_render_backward(rcv_ctx *c, int adjoint_kind, uint32_t seed_grad, uint32
     if (int r = ensure_film_w(c)) return r;
     LaunchCfg cfg = c->cfg();
     CK(launch_film_weights(cfg, c->S, seed_grad, spp_grad, c->film_w));
-    GradK D; D.grad = c->grad;
+    GradK D = c->gradk();
     CK(launch_vps_backward(cfg, c->S, c->gridk(), D, seed_grad, spp_grad, spp_begin, spp_end, alt_seed_for(seed_grad), grad_img,
                            c->film_w));
     return RCV_OK;
@@ -364,19 +371,19 @@ int rcv_render_adjoint_primal(rcv_ctx *c, int adjoint_kind, uint32_t seed, uint3
 int rcv_grad_zero(rcv_ctx *c) {
     if (int r = use_device(c)) return r;
     if (!c->grad) return fail(RCV_ERR_STATE, "no medium state");
-    CK(cudaMemsetAsync(c->grad, 0, c->nvox * sizeof(float4), c->stream));
+    CK(cudaMemsetAsync(c->grad, 0, c->grad_floats * sizeof(float), c->stream));
     return RCV_OK;
 }
 int rcv_grad_buffer(rcv_ctx *c, float **ptr, uint64_t *n_floats) {
     if (!c || !ptr || !n_floats) return fail(RCV_ERR_ARG, "null argument");
     if (!c->grad) return fail(RCV_ERR_STATE, "no medium state");
-    *ptr = (float *) c->grad; *n_floats = 4 * (uint64_t) c->nvox;
+    *ptr = c->grad; *n_floats = (uint64_t) c->grad_floats;
     return RCV_OK;
 }
 int rcv_grad_read(rcv_ctx *c, float *grad_sigma_t, float *grad_albedo) {
     if (int r = use_device(c)) return r;
     if (!c->grad) return fail(RCV_ERR_STATE, "no medium state");
-    CK(launch_grad_unpack(c->cfg(), c->grad, c->nvox, grad_sigma_t, grad_albedo));
+    CK(launch_grad_unpack(c->cfg(), c->gradk(), c->nvox, grad_sigma_t, grad_albedo));
     return RCV_OK;
 }
 
@@ -387,7 +394,7 @@ int rcv_adam_step(rcv_ctx *c, float *sigma_t, float *albedo, float *m_sigma_t, f
     if (!c->grad) return fail(RCV_ERR_STATE, "no medium state");
     if (t < 1) return fail(RCV_ERR_ARG, "t must be >= 1");
     if (!sigma_t || !albedo || !m_sigma_t || !v_sigma_t || !m_albedo || !v_albedo) return fail(RCV_ERR_ARG, "null pointer");
-    CK(launch_adam_packed(c->cfg(), c->grad, c->nvox, sigma_t, albedo, m_sigma_t, v_sigma_t, m_albedo, v_albedo,
+    CK(launch_adam_packed(c->cfg(), c->gradk(), c->nvox, sigma_t, albedo, m_sigma_t, v_sigma_t, m_albedo, v_albedo,
                           adam_lr_t(lr_sigma_t, beta1, beta2, t), adam_lr_t(lr_albedo, beta1, beta2, t), beta1, beta2, eps, slo,
                           shi, alo, ahi));
     return RCV_OK;

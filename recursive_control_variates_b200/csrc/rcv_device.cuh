@@ -69,9 +69,14 @@ struct GridK {
     const float *majorants;   // device: [0] = old, [1] = new  (scale * max)
 };
 
-// packed gradient grid: float4 per voxel = (d sigma_t, d albedo r, g, b)
+// gradient grids: d sigma_t as one float per voxel — dense, so the
+// sigma_t-only scatters (transmittance term, NEE replay: ~94 % of all scatter
+// sites) hit an array that fits in L2 at 256^3 — and d albedo as float4 per
+// voxel (rgb + one unused lane) so a scattering vertex needs one
+// red.global.add.v4.f32 per corner.
 struct GradK {
-    float4 *grad;
+    float *gsig;
+    float4 *galb;
 };
 
 struct Counters {

@@ -227,15 +227,18 @@ cudaError_t launch_loss_grad(const LaunchCfg &cfg, int kind, const float *img, c
 // ---------------------------------------------------------------------------
 // gradient grid unpack, Adam (+ clamp), clamp, upsample
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_grad_unpack(const float4 *__restrict__ grad, size_t nvox, float *g_sigma, float *g_albedo) {
+__global__ void __launch_bounds__(kBlock) k_grad_unpack(const float *__restrict__ gsig, const float4 *__restrict__ galb, size_t nvox,
+                                                        float *g_sigma, float *g_albedo) {
     for (size_t v = (size_t) blockIdx.x * kBlock + threadIdx.x; v < nvox; v += (size_t) gridDim.x * kBlock) {
-        float4 g = __ldg(grad + v);
-        if (g_sigma) g_sigma[v] = g.x;
-        if (g_albedo) { g_albedo[3 * v] = g.y; g_albedo[3 * v + 1] = g.z; g_albedo[3 * v + 2] = g.w; }
+        if (g_sigma) g_sigma[v] = __ldg(gsig + v);
+        if (g_albedo) {
+            float4 g = __ldg(galb + v);
+            g_albedo[3 * v] = g.x; g_albedo[3 * v + 1] = g.y; g_albedo[3 * v + 2] = g.z;
+        }
     }
 }
-cudaError_t launch_grad_unpack(const LaunchCfg &cfg, const float4 *grad, size_t nvox, float *g_sigma, float *g_albedo) {
-    k_grad_unpack<<<grid_for(cfg, nvox), kBlock, 0, cfg.stream>>>(grad, nvox, g_sigma, g_albedo);
+cudaError_t launch_grad_unpack(const LaunchCfg &cfg, const GradK &D, size_t nvox, float *g_sigma, float *g_albedo) {
+    k_grad_unpack<<<grid_for(cfg, nvox), kBlock, 0, cfg.stream>>>(D.gsig, D.galb, nvox, g_sigma, g_albedo);
     (*cfg.launches)++;
     return cudaGetLastError();
 }
@@ -247,16 +250,17 @@ __device__ __forceinline__ float adam_elem(float p, float g, float &m, float &v,
     m = m_t; v = v_t;
     return __fmaf_rn(-lr_t / (sqrtf(v_t) + eps), m_t, p);
 }
-__global__ void __launch_bounds__(kBlock) k_adam_packed(const float4 *__restrict__ grad, size_t nvox, float *sigma, float *albedo,
+__global__ void __launch_bounds__(kBlock) k_adam_packed(const float *__restrict__ gsig, const float4 *__restrict__ galb, size_t nvox,
+                                                        float *sigma, float *albedo,
                                                         float *m_s, float *v_s, float *m_a, float *v_a, float lr_t_s, float lr_t_a,
                                                         float b1, float b2, float eps, float slo, float shi, float alo, float ahi) {
     for (size_t v = (size_t) blockIdx.x * kBlock + threadIdx.x; v < nvox; v += (size_t) gridDim.x * kBlock) {
-        float4 g = __ldg(grad + v);
+        float4 g = __ldg(galb + v);
         float ms = m_s[v], vs = v_s[v];
-        float s = adam_elem(sigma[v], g.x, ms, vs, lr_t_s, b1, b2, eps);
+        float s = adam_elem(sigma[v], __ldg(gsig + v), ms, vs, lr_t_s, b1, b2, eps);
         m_s[v] = ms; v_s[v] = vs;
         sigma[v] = fmin_(fmax_(s, slo), shi);                          // utils.py:172-175
-        float gg[3] = {g.y, g.z, g.w};
+        float gg[3] = {g.x, g.y, g.z};
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             float ma = m_a[3 * v + c], va = v_a[3 * v + c];
@@ -266,10 +270,10 @@ __global__ void __launch_bounds__(kBlock) k_adam_packed(const float4 *__restrict
         }
     }
 }
-cudaError_t launch_adam_packed(const LaunchCfg &cfg, const float4 *grad, size_t nvox, float *sigma, float *albedo, float *m_s,
+cudaError_t launch_adam_packed(const LaunchCfg &cfg, const GradK &D, size_t nvox, float *sigma, float *albedo, float *m_s,
                                float *v_s, float *m_a, float *v_a, float lr_t_s, float lr_t_a, float beta1, float beta2,
                                float eps, float slo, float shi, float alo, float ahi) {
-    k_adam_packed<<<grid_for(cfg, nvox), kBlock, 0, cfg.stream>>>(grad, nvox, sigma, albedo, m_s, v_s, m_a, v_a, lr_t_s, lr_t_a,
+    k_adam_packed<<<grid_for(cfg, nvox), kBlock, 0, cfg.stream>>>(D.gsig, D.galb, nvox, sigma, albedo, m_s, v_s, m_a, v_a, lr_t_s, lr_t_a,
                                                                    beta1, beta2, eps, slo, shi, alo, ahi);
     (*cfg.launches)++;
     return cudaGetLastError();

@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(kBlock) k_twostates_persistent(const __grid_co
 #define RCV_WF_MINBLOCKS 2
 #endif
 #ifndef RCV_COLL_THRESHOLD
-#define RCV_COLL_THRESHOLD 24
+#define RCV_COLL_THRESHOLD 16
 #endif
 static constexpr int kWfBlock = RCV_WF_BLOCK;
 static constexpr int kWfMinBlocks = RCV_WF_MINBLOCKS;
@@ -376,7 +376,7 @@ static cudaError_t launch_vps(const LaunchCfg &cfg, const SceneK &S, const GridK
 
 cudaError_t launch_vps_primal(const LaunchCfg &cfg, const SceneK &S, const GridK &G, uint32_t seed, uint32_t spp,
                               uint32_t spp_begin, uint32_t spp_end, float4 *accum) {
-    GradK D; D.grad = nullptr;
+    GradK D; D.gsig = nullptr; D.galb = nullptr;
     return launch_vps<false>(cfg, S, G, D, seed, spp, spp_begin, spp_end, 0u, nullptr, nullptr, accum);
 }
 

@@ -5,10 +5,10 @@
 // (:393-517), backpropagate_transmittance (:597-620).
 //
 // Backward mode replays the identical main random stream and turns the AD of
-// the trilinear gathers into reductions on the packed gradient grid
-// (float4 per voxel = d sigma_t, d albedo rgb): one red.global.add.v4.f32 per
-// corner at scattering vertices, one red.global.add.f32 per corner for the
-// sigma_t-only terms.
+// the trilinear gathers into reductions on the
+// gradient grids (d sigma_t: float per voxel, d albedo: float4 per voxel): one
+// red.global.add.f32 per corner for every sigma_t term, plus one
+// red.global.add.v4.f32 per corner for the albedo at scattering vertices.
 #pragma once
 #include "rcv_device.cuh"
 
@@ -50,7 +50,7 @@ __device__ __forceinline__ void scatter_sigma_t(const SceneK &S, const GridK &G,
     float sg = S.scale * g;
 #pragma unroll
     for (int k = 0; k < 8; ++k)
-        red_add_f32(&D.grad[tri_voxel(G, T, k)].x, tri_weight(T, k) * sg);
+        red_add_f32(D.gsig + tri_voxel(G, T, k), tri_weight(T, k) * sg);
     cnt.g_sig++;
 }
 
@@ -167,7 +167,9 @@ __device__ __forceinline__ void vps_trace(const SceneK &S, const GridK &G, const
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         float w = tri_weight(T, k);
-                        red_add_v4(&D.grad[tri_voxel(G, T, k)], w * sg, w * g_al.x, w * g_al.y, w * g_al.z);
+                        size_t v = tri_voxel(G, T, k);
+                        red_add_f32(D.gsig + v, w * sg);
+                        red_add_v4(D.galb + v, w * g_al.x, w * g_al.y, w * g_al.z, 0.f);
                     }
                     cnt.g_sig++; cnt.g_alb++;
                 }

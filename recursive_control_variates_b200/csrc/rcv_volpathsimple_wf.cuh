@@ -266,7 +266,9 @@ __device__ __forceinline__ void vp_vertex(const SceneK &S, const GridK &G, float
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     float w = tri_weight(T, k);
-                    red_add_v4(&sk.D.grad[tri_voxel(G, T, k)], w * sg, w * g_al.x, w * g_al.y, w * g_al.z);
+                    size_t v = tri_voxel(G, T, k);
+                    red_add_f32(sk.D.gsig + v, w * sg);
+                    red_add_v4(sk.D.galb + v, w * g_al.x, w * g_al.y, w * g_al.z, 0.f);
                 }
                 sk.cnt.g_sig++; sk.cnt.g_alb++;
             }

@@ -175,10 +175,10 @@ class Context:
                                            spp_begin, spp_end, _ptr(grad_img)))
 
     def grad_packed(self) -> torch.Tensor:
-        """View of the packed gradient grid (nvox, 4) for in-place all-reduce."""
+        """Flat view of the library's gradient grids (d sigma_t, d albedo) for an in-place all-reduce."""
         p, n = C.c_void_p(), C.c_uint64()
         check(self.lib.rcv_grad_buffer(self._h, C.byref(p), C.byref(n)))
-        return _as_tensor(p.value, int(n.value), self.torch_device).view(-1, 4)
+        return _as_tensor(p.value, int(n.value), self.torch_device)
 
     def grad_read(self):
         nz, ny, nx = self.grid_shape

@@ -73,14 +73,14 @@ int emu_twostates(const rcv_scene_desc *d, const float *so, const float *ao, con
 }
 
 // volpathsimple: primal render (backward == 0) or the two-pass adjoint; the
-// gradient grid is the packed float4 layout of the library
+// gradient grids use the library's layout (float + float4 per voxel)
 int emu_vps(const rcv_scene_desc *d, const float *sn, const float *an, int nz, int ny, int nx, uint32_t seed, uint32_t spp,
-            int backward, uint32_t alt_seed, const float *grad_img, const float *film_w, float *accum, float *grad4,
-            uint64_t *counters) {
+            int backward, uint32_t alt_seed, const float *grad_img, const float *film_w, float *accum, float *gsig,
+            float *galb4, uint64_t *counters) {
     SceneK S; scene_from_desc(*d, S);
     Packed P; pack(*d, sn, an, sn, an, nz, ny, nx, P);
     for (int i = 0; i < 8; ++i) counters[i] = 0;
-    VpSink sk; sk.accum = (float4 *) accum; sk.D.grad = (float4 *) grad4; sk.grad_img = grad_img; sk.film_w = film_w;
+    VpSink sk; sk.accum = (float4 *) accum; sk.D.gsig = gsig; sk.D.galb = (float4 *) galb4; sk.grad_img = grad_img; sk.film_w = film_w;
     sk.seed = seed; sk.spp = spp; sk.alt_seed = alt_seed;
     sk.cnt.coll = sk.cnt.scat = sk.cnt.g_sig = sk.cnt.g_alb = 0; sk.n_paths = 0;
     const float mu = P.maj[1];

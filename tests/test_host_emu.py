@@ -26,7 +26,7 @@ def emu():
     lib.emu_twostates.argtypes = [C.c_void_p, f32, f32, f32, f32, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int,
                                   f32, f32, u64]
     lib.emu_vps.argtypes = [C.c_void_p, f32, f32, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32,
-                            C.c_void_p, C.c_void_p, f32, f32, u64]
+                            C.c_void_p, C.c_void_p, f32, f32, f32, u64]
     return lib
 
 
@@ -78,9 +78,9 @@ def test_volpathsimple_event_machine_primal(oracle, emu, setup):
     d = setup["desc"]
     sn, an = setup["new"]
     H, W = d.film_height, d.film_width
-    acc = np.zeros((H, W, 4), np.float32); g4 = np.zeros((*sn.shape[:3], 4), np.float32)
+    acc = np.zeros((H, W, 4), np.float32); g1 = np.zeros((*sn.shape[:3], 1), np.float32); g4 = np.zeros((*sn.shape[:3], 4), np.float32)
     cnt = np.zeros(8, np.uint64)
-    emu.emu_vps(C.addressof(d), sn, an, *sn.shape[:3], 33, 1, 0, 0, None, None, acc, g4, cnt)
+    emu.emu_vps(C.addressof(d), sn, an, *sn.shape[:3], 33, 1, 0, 0, None, None, acc, g1, g4, cnt)
     oracle.counters(True)
     ref = oracle.vps_render_accum(d, setup["mn"], 33, 1)
     oc = oracle.counters(True)
@@ -96,13 +96,13 @@ def test_volpathsimple_event_machine_backward(oracle, emu, setup):
     grad_img = (rng.standard_normal((H, W, 3)) / (H * W * 3)).astype(np.float32)
     seed_grad, spp = 0xC09848F2, 2
     film_w = oracle.film_weights(d, seed_grad, spp)
-    acc = np.zeros((H, W, 4), np.float32); g4 = np.zeros((*sn.shape[:3], 4), np.float32)
+    acc = np.zeros((H, W, 4), np.float32); g1 = np.zeros((*sn.shape[:3], 1), np.float32); g4 = np.zeros((*sn.shape[:3], 4), np.float32)
     cnt = np.zeros(8, np.uint64)
     emu.emu_vps(C.addressof(d), sn, an, *sn.shape[:3], seed_grad, spp, 1, oracle.alt_seed(seed_grad),
-                grad_img.ctypes.data, film_w.ctypes.data, acc, g4, cnt)
+                grad_img.ctypes.data, film_w.ctypes.data, acc, g1, g4, cnt)
     oracle.counters(True)
     gs, ga = oracle.vps_backward(d, setup["mn"], seed_grad, spp, grad_img, threads=1, film_w=film_w)
     oc = oracle.counters(True)
     assert [int(v) for v in cnt[2:7]] == [int(v) for v in oc[2:7]]
-    assert rel_l2(g4[..., 0:1], gs) < 1e-5       # float vs double accumulation
-    assert rel_l2(g4[..., 1:4], ga) < 1e-5
+    assert rel_l2(g1, gs) < 1e-5       # float vs double accumulation
+    assert rel_l2(g4[..., 0:3], ga) < 1e-5
