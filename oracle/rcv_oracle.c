@@ -469,7 +469,8 @@ static void sample_interaction_twostates(const rcv_scene_desc *S, const orc_medi
     /* single majorant for the whole volume (:71-78); majorant supergrid (:25-70) is a "next" row */
     float combined_extinction = fmaxf_(Mo->majorant, Mn->majorant);            /* :73-75 */
     float m = combined_extinction;                                             /* :76, channel 0 */
-    float sampled_t = mint + (desired_tau / m);                                /* :78 */
+    float inv_m = 1.f / m;                                                     /* [SPEC] x / majorant == x * (1 / majorant) */
+    float sampled_t = mint + (desired_tau * inv_m);                            /* :78 */
     int valid_mi = active && (sampled_t <= maxt);                              /* :80 */
     mei_t mn;
     mn.t = valid_mi ? sampled_t : ORC_INF;                                     /* :88 */
@@ -543,8 +544,10 @@ static void sample_emitter_twostates(const rcv_scene_desc *S, const orc_medium *
             si.t = si.t - mn.t;                                                /* :446 */
             float ce = mn.combined_extinction;
             v3 cev = V3(ce, ce, ce);
-            m_old = (ce != 0.f) ? vmul(m_old, vdiv(mo.sigma_n, cev)) : vmul(m_old, mo.sigma_n);   /* :447-449 */
-            m_new = (ce != 0.f) ? vmul(m_new, vdiv(mn.sigma_n, cev)) : vmul(m_new, mn.sigma_n);   /* :450-452 */
+            float inv_ce = 1.f / ce;                                           /* [SPEC] reciprocal majorant */
+            (void) cev;
+            m_old = (ce != 0.f) ? vmul(m_old, vscale(mo.sigma_n, inv_ce)) : vmul(m_old, mo.sigma_n);   /* :447-449 */
+            m_new = (ce != 0.f) ? vmul(m_new, vscale(mn.sigma_n, inv_ce)) : vmul(m_new, mn.sigma_n);   /* :450-452 */
         }
         active_surface = active_surface || escaped_medium;                     /* :455 */
         active_surface = active_surface && si.valid && !active_medium;
@@ -617,15 +620,17 @@ static void sample_twostates(const rcv_scene_desc *S, const orc_medium *Mo, cons
         active_medium = active_medium && mei_valid(&mn);
         /* handle_null_scattering branch (:219-231); heterogeneous media always take it (:99) */
         float majorant = mn.combined_extinction;
-        float sp_new = mn.sigma_t.x / majorant, sp_old = mo.sigma_t.x / majorant;
+        float inv_maj = 1.f / majorant;                                        /* [SPEC] reciprocal majorant */
+        float sp_new = mn.sigma_t.x * inv_maj, sp_old = mo.sigma_t.x * inv_maj;
         float scatter_prob = (majorant != 0.f) ? (sp_new + sp_old) * 0.5f : 0.f;   /* :225 */
         float xi = next_1d(rng, active_medium);                                /* :227 */
         int act_null_scatter = (xi >= scatter_prob) && active_medium;
         int act_medium_scatter = !act_null_scatter && active_medium;
         if (act_null_scatter) {                                                /* :230-231 */
             v3 den = vadd(mn.sigma_n, mo.sigma_n);
-            weight_new = vmul(weight_new, vdiv(vscale(mn.sigma_n, 2.f), den));
-            weight_old = vmul(weight_old, vdiv(vscale(mo.sigma_n, 2.f), den));
+            v3 rden = vdiv(V3(1, 1, 1), den);                                  /* [SPEC] a / den == a * (1 / den) */
+            weight_new = vmul(weight_new, vmul(vscale(mn.sigma_n, 2.f), rden));
+            weight_old = vmul(weight_old, vmul(vscale(mo.sigma_n, 2.f), rden));
         }
         if (act_medium_scatter) { depth += 1; last_scatter_p = mn.p; }         /* :249-250 */
         active = active && (depth < S->max_depth);                             /* :253 */
@@ -636,8 +641,9 @@ static void sample_twostates(const rcv_scene_desc *S, const orc_medium *Mo, cons
         }
         if (act_medium_scatter) {                                              /* :259-260 */
             v3 den = vadd(mn.sigma_t, mo.sigma_t);
-            weight_new = vmul(weight_new, vdiv(vscale(mn.sigma_s, 2.f), den));
-            weight_old = vmul(weight_old, vdiv(vscale(mo.sigma_s, 2.f), den));
+            v3 rden = vdiv(V3(1, 1, 1), den);                                  /* [SPEC] reciprocal */
+            weight_new = vmul(weight_new, vmul(vscale(mn.sigma_s, 2.f), rden));
+            weight_old = vmul(weight_old, vmul(vscale(mo.sigma_s, 2.f), rden));
             cnt->c[1]++;
         }
         if (active_medium) {                                                   /* :265-266 */
@@ -936,7 +942,8 @@ static void sample_interaction(const rcv_scene_desc *S, const orc_medium *M, con
     active = prepare_interaction_sampling(S, ray, active, &mint, &maxt);
     float desired_tau = -orc_logf(1.f - sample);
     float m = M->majorant;
-    float sampled_t = mint + (desired_tau / m);
+    float inv_m = 1.f / m;                           /* [SPEC] reciprocal majorant */
+    float sampled_t = mint + (desired_tau * inv_m);
     int valid = active && (sampled_t <= maxt);
     mei->t = valid ? sampled_t : ORC_INF;
     mei->p = ray_at(ray->o, ray->d, sampled_t);
@@ -970,7 +977,7 @@ static void sample_real_interaction(const rcv_scene_desc *S, const orc_medium *M
         *mei = mei_next;                                                       /* :363 */
         mei->t = mei->t + running_t;                                           /* :364 */
         float majorant = mei_next.combined_extinction;                         /* :366 */
-        float r = (majorant != 0.f) ? mei_next.sigma_t.x / majorant : 0.f;     /* :367 */
+        float r = (majorant != 0.f) ? mei_next.sigma_t.x * (1.f / majorant) : 0.f;   /* :367 [SPEC] reciprocal */
         active = active && mei_valid(&mei_next);                               /* :371 */
         float xi = next_1d(rng, active);                                       /* :372 */
         int did_null_scatter = active && (xi >= r);
@@ -1011,15 +1018,16 @@ static v3 estimate_transmittance(const rcv_scene_desc *S, const orc_medium *M, c
         float u = next_1d(rng, active);
         sample_interaction(S, M, &ray, u, active, &mei, cnt);                  /* :482 */
         float ce = mei.combined_extinction;
-        v3 tr = (ce != 0.f) ? vdiv(mei.sigma_n, V3(ce, ce, ce)) : mei.sigma_n; /* :486-489 */
+        float inv_ce = 1.f / ce;                                               /* [SPEC] reciprocal majorant */
+        v3 tr = (ce != 0.f) ? vscale(mei.sigma_n, inv_ce) : mei.sigma_n;       /* :486-489 */
         if (active && (mei.t > tmax)) mei.t = ORC_INF;                         /* :493 */
         active = active && mei_valid(&mei);
         if (adjoint && active) {                                               /* :496-505 */
             /* d/d sigma_t of adjoint * tr / detach(tr), tr = (mu - sigma_t)/mu, summed over channels */
             float g = 0.f;
-            if (tr.x > 0.f) g += adjoint->x * ((-1.f / ce) / tr.x);
-            if (tr.y > 0.f) g += adjoint->y * ((-1.f / ce) / tr.y);
-            if (tr.z > 0.f) g += adjoint->z * ((-1.f / ce) / tr.z);
+            if (tr.x > 0.f) g += adjoint->x * ((-inv_ce) / tr.x);
+            if (tr.y > 0.f) g += adjoint->y * ((-inv_ce) / tr.y);
+            if (tr.z > 0.f) g += adjoint->z * ((-inv_ce) / tr.z);
             scatter_sigma_t(S, M, G, mei.p, g, cnt);
         }
         if (active) {

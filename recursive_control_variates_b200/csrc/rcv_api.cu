@@ -58,6 +58,8 @@ struct rcv_ctx {
     uint64_t launches = 0;
     float *film_w = nullptr;
     size_t film_w_pix = 0;
+    PathQueue queue{nullptr, nullptr, nullptr, nullptr};
+    size_t queue_cap = 0;
     double *loss_partial = nullptr;
     int n_partial = 0;
     // state of rcv_cv_iteration_host
@@ -75,7 +77,7 @@ struct rcv_ctx {
     LaunchCfg cfg() {
         LaunchCfg c;
         c.stream = stream; c.sm_count = sm_count; c.tracer = tracer;
-        c.counters = counters; c.work_counter = work; c.launches = &launches;
+        c.counters = counters; c.work_counter = work; c.launches = &launches; c.queue = queue;
         return c;
     }
     GradK gradk() const {
@@ -147,6 +149,21 @@ uint32_t alt_seed_for(uint32_t seed_grad) {
     return v0;
 }
 
+// record queue of the wavefront schedule: 48 B per lane of the largest launch so far
+int ensure_queue(rcv_ctx *c, uint32_t spp_begin, uint32_t spp_end) {
+    size_t n = (size_t) c->S.W * c->S.H * (spp_end - spp_begin);
+    if (!c->queue.count) CK(cudaMalloc(&c->queue.count, sizeof(unsigned long long)));
+    if (n > c->queue_cap) {
+        cudaFree(c->queue.r0); cudaFree(c->queue.r1); cudaFree(c->queue.r2);
+        c->queue.r0 = c->queue.r1 = c->queue.r2 = nullptr; c->queue_cap = 0;
+        CK(cudaMalloc(&c->queue.r0, n * sizeof(float4)));
+        CK(cudaMalloc(&c->queue.r1, n * sizeof(float4)));
+        CK(cudaMalloc(&c->queue.r2, n * sizeof(float4)));
+        c->queue_cap = n;
+    }
+    return RCV_OK;
+}
+
 int ensure_film_w(rcv_ctx *c) {
     size_t npix = (size_t) c->S.W * c->S.H;
     if (c->film_w_pix != npix) {
@@ -201,6 +218,7 @@ int rcv_ctx_destroy(rcv_ctx *c) {
     cudaSetDevice(c->device);
     free_medium(c);
     cudaFree(c->counters); cudaFree(c->work); cudaFree(c->majorants); cudaFree(c->film_w); cudaFree(c->loss_partial);
+    cudaFree(c->queue.r0); cudaFree(c->queue.r1); cudaFree(c->queue.r2); cudaFree(c->queue.count);
     auto &E = c->e2e;
     cudaFree(E.sigma); cudaFree(E.albedo); cudaFree(E.ref); cudaFree(E.acc); cudaFree(E.HF); cudaFree(E.cv);
     cudaFree(E.grad_img); cudaFree(E.loss); cudaFree(E.g_sigma); cudaFree(E.g_albedo);
@@ -227,6 +245,7 @@ int rcv_scene_set(rcv_ctx *c, const rcv_scene_desc *d) {
     if (d->phase_type != RCV_PHASE_ISOTROPIC && d->phase_type != RCV_PHASE_HG) return fail(RCV_ERR_ARG, "unknown phase function");
     for (int a = 0; a < 3; ++a)
         if (!(d->bbox_max[a] > d->bbox_min[a])) return fail(RCV_ERR_ARG, "degenerate medium bounding box");
+    if (d->rr_depth < 0 || d->max_depth < 1) return fail(RCV_ERR_ARG, "rr_depth must be >= 0 and max_depth >= 1");
     c->desc = *d;
     scene_from_desc(*d, c->S);
     c->has_scene = true;
@@ -290,6 +309,8 @@ static int check_render(rcv_ctx *c, uint32_t spp, uint32_t b, uint32_t e) {
     if (!c->sig2) return fail(RCV_ERR_STATE, "no medium state (call rcv_medium_rotate)");
     if (spp == 0 || b > e || e > spp) return fail(RCV_ERR_ARG, "invalid sample range");
     if ((uint64_t) c->S.W * c->S.H * spp > 0xffffffffull) return fail(RCV_ERR_ARG, "wavefront exceeds 2^32 lanes");
+    if (c->tracer == RCV_TRACER_WAVEFRONT)
+        if (int r = ensure_queue(c, b, e)) return r;
     return RCV_OK;
 }
 

@@ -83,6 +83,15 @@ struct Counters {
     unsigned long long c[8];
 };
 
+// path record queue (structure of arrays, one float4 triple per path)
+//   r0 = (rng.state lo, rng.state hi, rng stream v1, film pixel)   [bit patterns]
+//   r1 = (o.x, o.y, o.z, aux)        aux: boundary distance (volpathsimple)
+//   r2 = (d.x, d.y, d.z, lane id)    lane id: global PCG32 lane index (bit pattern)
+struct PathQueue {
+    float4 *r0, *r1, *r2;
+    unsigned long long *count;   // number of records appended by the ray-generation kernel
+};
+
 // ----------------------------------------------------------------------------
 // float helpers with oracle-identical NaN behaviour
 // ----------------------------------------------------------------------------
@@ -265,13 +274,17 @@ struct Hit {
     V3 p, n;
 };
 
+// reciprocal direction of a ray (IEEE divisions); computed once per ray and
+// reused by every slab test along it — bit-identical to recomputing it
+__device__ __forceinline__ V3 rcp3(V3 d) { return mk3(1.f / d.x, 1.f / d.y, 1.f / d.z); }
+
 // slab intervals of all three axes; returns tn (entry), tf (exit) and the axes
-__device__ __forceinline__ void slabs(const SceneK &S, V3 o, V3 d, float &tn, float &tf, int &an, int &af) {
-    float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+__device__ __forceinline__ void slabs(const SceneK &S, V3 o, V3 id, float &tn, float &tf, int &an, int &af) {
+    float oo[3] = {o.x, o.y, o.z}, ii[3] = {id.x, id.y, id.z};
     tn = -inf_(); tf = inf_(); an = 0; af = 0;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        float rcp = 1.f / dd[a];
+        float rcp = ii[a];
         float t1 = (S.bmin[a] - oo[a]) * rcp, t2 = (S.bmax[a] - oo[a]) * rcp;
         float t1p = fmin_(t1, t2), t2p = fmax_(t1, t2);
         if (t1p > tn) { tn = t1p; an = a; }
@@ -280,14 +293,14 @@ __device__ __forceinline__ void slabs(const SceneK &S, V3 o, V3 d, float &tn, fl
 }
 
 // Medium::prepare_interaction_sampling: [mint, maxt] of the ray inside the box
-__device__ __forceinline__ bool medium_interval(const SceneK &S, V3 o, V3 d, float ray_maxt, float &mint, float &maxt) {
-    float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+__device__ __forceinline__ bool medium_interval(const SceneK &S, V3 o, V3 d, V3 id, float ray_maxt, float &mint, float &maxt) {
+    float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z}, ii[3] = {id.x, id.y, id.z};
     bool active = true;
     float tn = -inf_(), tf = inf_();
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         active = active && (dd[a] != 0.f || oo[a] > S.bmin[a] || oo[a] < S.bmax[a]);
-        float rcp = 1.f / dd[a];
+        float rcp = ii[a];
         float t1 = (S.bmin[a] - oo[a]) * rcp, t2 = (S.bmax[a] - oo[a]) * rcp;
         tn = fmax_(tn, fmin_(t1, t2));
         tf = fmin_(tf, fmax_(t1, t2));
@@ -301,10 +314,10 @@ __device__ __forceinline__ bool medium_interval(const SceneK &S, V3 o, V3 d, flo
 }
 
 // nearest boundary hit with 0 < t <= maxt
-__device__ __forceinline__ Hit box_hit(const SceneK &S, V3 o, V3 d, float maxt) {
+__device__ __forceinline__ Hit box_hit(const SceneK &S, V3 o, V3 d, V3 id, float maxt) {
     Hit h; h.valid = false; h.t = inf_(); h.p = mk3(0, 0, 0); h.n = mk3(0, 0, 0);
     float tn, tf; int an, af;
-    slabs(S, o, d, tn, tf, an, af);
+    slabs(S, o, id, tn, tf, an, af);
     if (!(tf >= tn)) return h;
     float t; int axis;
     bool entering = tn > 0.f;

@@ -13,6 +13,7 @@ struct LaunchCfg {
     int tracer;        // RCV_TRACER_*
     Counters *counters;   // device
     unsigned long long *work_counter;   // device, persistent-kernel work queue head
+    PathQueue queue;                    // device, path records of the wavefront schedule
     uint64_t *launches;   // host-side launch counter
 };
 

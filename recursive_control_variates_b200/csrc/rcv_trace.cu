@@ -1,11 +1,16 @@
 // rcv_trace.cu — tracing kernels: two-state primal (K1), volpathsimple primal
 // (K5) and the fused pass-1 + pass-2 adjoint (K5+K6).
 //
-// Two schedules of the same per-lane code (rcv_twostate.cuh, rcv_volpathsimple.cuh):
-//   * SIMPLE     one thread per lane; a warp runs until its longest path ends.
-//   * WAVEFRONT  persistent warps, one resident grid sized to the SM count;
-//                every warp pulls 32-lane batches from a global work counter
-//                until the lane range is exhausted (no tail of idle CTAs).
+// Three schedules of the same per-lane estimators:
+//   * WAVEFRONT (default)  a fully convergent ray-generation kernel writes one
+//       48-byte record per path that enters the medium; persistent warps then
+//       run the per-lane event machines (rcv_*_wf.cuh): every round a warp
+//       refills its finished lanes from the record queue and executes ONE event
+//       handler — the tentative-collision step (the only place with a grid
+//       gather) or the vertex step — with the lanes waiting for it.  The
+//       adjoint's gradient scatters are executed cooperatively by the warp.
+//   * SIMPLE   one thread per lane, nested loops (A/B baseline).
+//   * BATCH    persistent warps pulling 32-lane batches, nested loops (A/B baseline).
 // Results are schedule-independent: each lane owns its PCG32 stream, indexed
 // by the global lane id pixel*spp + k.
 #include "rcv_internal.h"
@@ -24,9 +29,9 @@ __device__ __forceinline__ uint64_t global_lane(uint64_t j, uint32_t spp, uint32
     return pixel * spp + k;
 }
 
-// ---------------------------------------------------------------------------
-// K1: two-state primal
-// ---------------------------------------------------------------------------
+// ===========================================================================
+// SIMPLE / BATCH schedules
+// ===========================================================================
 template <int MODE>
 __device__ __forceinline__ void twostates_lane(const SceneK &S, const GridK &G, uint32_t seed, uint32_t spp, uint64_t idx,
                                                float4 *acc_old, float4 *acc_new, unsigned &nc, unsigned &nsct) {
@@ -43,166 +48,35 @@ __device__ __forceinline__ void twostates_lane(const SceneK &S, const GridK &G, 
 template <int MODE>
 __global__ void __launch_bounds__(kBlock) k_twostates_simple(const __grid_constant__ SceneK S, const __grid_constant__ GridK G,
                                                              uint32_t seed, uint32_t spp, uint32_t spp_begin, uint32_t ns,
-                                                             uint64_t n_local, float4 *acc_old, float4 *acc_new, Counters *C) {
-    uint64_t j = (uint64_t) blockIdx.x * kBlock + threadIdx.x;
+                                                             uint64_t n_local, float4 *acc_old, float4 *acc_new, Counters *C,
+                                                             unsigned long long *work, int persistent) {
     unsigned nc = 0, nsct = 0, np = 0;
-    if (j < n_local) {
-        twostates_lane<MODE>(S, G, seed, spp, global_lane(j, spp, spp_begin, ns), acc_old, acc_new, nc, nsct);
-        np = 1;
-    }
-    counter_flush(C, MODE == 0 ? 0 : 2, nc);
-    counter_flush(C, MODE == 0 ? 1 : 3, nsct);
-    counter_flush(C, 6, np);
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(kBlock) k_twostates_persistent(const __grid_constant__ SceneK S, const __grid_constant__ GridK G,
-                                                                 uint32_t seed, uint32_t spp, uint32_t spp_begin, uint32_t ns,
-                                                                 uint64_t n_local, float4 *acc_old, float4 *acc_new, Counters *C,
-                                                                 unsigned long long *work) {
-    unsigned nc = 0, nsct = 0, np = 0;
-    const unsigned lane = threadIdx.x & 31;
-    while (true) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(work, 32ull);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n_local) break;
-        uint64_t j = base + lane;
+    if (!persistent) {
+        uint64_t j = (uint64_t) blockIdx.x * kBlock + threadIdx.x;
         if (j < n_local) {
             twostates_lane<MODE>(S, G, seed, spp, global_lane(j, spp, spp_begin, ns), acc_old, acc_new, nc, nsct);
-            np++;
+            np = 1;
         }
-        __syncwarp();
+    } else {
+        const unsigned lane = threadIdx.x & 31;
+        while (true) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(work, 32ull);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= n_local) break;
+            uint64_t j = base + lane;
+            if (j < n_local) {
+                twostates_lane<MODE>(S, G, seed, spp, global_lane(j, spp, spp_begin, ns), acc_old, acc_new, nc, nsct);
+                np++;
+            }
+            __syncwarp();
+        }
     }
     counter_flush(C, MODE == 0 ? 0 : 2, nc);
     counter_flush(C, MODE == 0 ? 1 : 3, nsct);
     counter_flush(C, 6, np);
 }
 
-// ---------------------------------------------------------------------------
-// Warp scheduler of the event machines (rcv_twostate_wf.cuh).
-// Every warp is persistent.  Each round it counts the lanes waiting for each
-// event class and runs ONE handler: the tentative-collision step whenever at
-// least kCollThreshold lanes are ready for it (it contains the grid gather, the
-// only expensive memory access), otherwise the larger of the scatter / init
-// queues.  Finished lanes are refilled from a warp-private chunk of lane
-// indices taken from the global work counter (one atomic per kChunk paths).
-// ---------------------------------------------------------------------------
-#ifndef RCV_WF_BLOCK
-#define RCV_WF_BLOCK 256
-#endif
-#ifndef RCV_WF_MINBLOCKS
-#define RCV_WF_MINBLOCKS 2
-#endif
-#ifndef RCV_COLL_THRESHOLD
-#define RCV_COLL_THRESHOLD 16
-#endif
-static constexpr int kWfBlock = RCV_WF_BLOCK;
-static constexpr int kWfMinBlocks = RCV_WF_MINBLOCKS;
-static constexpr int kCollThreshold = RCV_COLL_THRESHOLD;
-static constexpr unsigned long long kChunk = 512;
-
-template <int MODE>
-__global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_twostates_wavefront(const __grid_constant__ SceneK S, const __grid_constant__ GridK G,
-                                                                      uint32_t seed, uint32_t spp, uint32_t spp_begin, uint32_t ns,
-                                                                      uint64_t n_local, float4 *acc_old, float4 *acc_new, Counters *C,
-                                                                      unsigned long long *work) {
-    const unsigned lane = threadIdx.x & 31;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const float mu = combined_majorant<MODE>(G);
-    TsLane ln;
-    ln.ev = EV_INIT;
-    TsSink sk; sk.acc_old = acc_old; sk.acc_new = acc_new; sk.n_coll = sk.n_scat = sk.n_paths = 0;
-    unsigned long long chunk_next = 0, chunk_end = 0;
-    bool more = true;
-    while (true) {
-        unsigned m_init = __ballot_sync(0xffffffffu, ln.ev == EV_INIT);
-        unsigned m_coll = __ballot_sync(0xffffffffu, ln.ev == EV_COLL);
-        unsigned m_scat = __ballot_sync(0xffffffffu, ln.ev == EV_SCAT);
-        int n_init = more ? __popc(m_init) : 0, n_coll = __popc(m_coll), n_scat = __popc(m_scat);
-        if (n_coll == 0 && n_scat == 0 && n_init == 0) break;
-        int sel;
-        if (n_coll >= kCollThreshold || (n_scat == 0 && n_init == 0)) sel = EV_COLL;
-        else if (n_scat >= n_init) sel = EV_SCAT;
-        else sel = EV_INIT;
-        if (sel == EV_COLL) {
-            if (ln.ev == EV_COLL) ts_collide<MODE>(S, G, mu, ln, sk);
-        } else if (sel == EV_SCAT) {
-            if (ln.ev == EV_SCAT) ts_scatter<MODE>(S, G, ln, sk);
-        } else {
-            if (chunk_next >= chunk_end) {
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(work, kChunk);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (base >= n_local) { more = false; continue; }
-                chunk_next = base;
-                chunk_end = (base + kChunk < n_local) ? base + kChunk : n_local;
-            }
-            unsigned long long avail = chunk_end - chunk_next;
-            unsigned rank = __popc(m_init & lt_mask);
-            if (ln.ev == EV_INIT && rank < avail)
-                ts_init<MODE>(S, ln, sk, seed, spp, global_lane(chunk_next + rank, spp, spp_begin, ns));
-            unsigned long long take = (unsigned long long) n_init < avail ? (unsigned long long) n_init : avail;
-            chunk_next += take;
-        }
-        __syncwarp();
-    }
-    counter_flush(C, MODE == 0 ? 0 : 2, sk.n_coll);
-    counter_flush(C, MODE == 0 ? 1 : 3, sk.n_scat);
-    counter_flush(C, 6, sk.n_paths);
-}
-
-template <int MODE>
-static cudaError_t launch_twostates_mode(const LaunchCfg &cfg, const SceneK &S, const GridK &G, uint32_t seed, uint32_t spp,
-                                         uint32_t spp_begin, uint32_t ns, uint64_t n_local, float4 *acc_old, float4 *acc_new) {
-    if (cfg.tracer == 1) {
-        uint64_t blocks = (n_local + kBlock - 1) / kBlock;
-        k_twostates_simple<MODE><<<(unsigned) blocks, kBlock, 0, cfg.stream>>>(S, G, seed, spp, spp_begin, ns, n_local, acc_old,
-                                                                                acc_new, cfg.counters);
-    } else if (cfg.tracer == 0) {
-        cudaError_t e = cudaMemsetAsync(cfg.work_counter, 0, sizeof(unsigned long long), cfg.stream);
-        if (e != cudaSuccess) return e;
-        int per_sm = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_twostates_wavefront<MODE>, kWfBlock, 0);
-        if (e != cudaSuccess) return e;
-        if (per_sm < 1) per_sm = 1;
-        uint64_t want = (n_local + kWfBlock - 1) / kWfBlock;
-        uint64_t blocks = (uint64_t) per_sm * cfg.sm_count;
-        if (blocks > want) blocks = want;
-        k_twostates_wavefront<MODE><<<(unsigned) blocks, kWfBlock, 0, cfg.stream>>>(S, G, seed, spp, spp_begin, ns, n_local, acc_old,
-                                                                                     acc_new, cfg.counters, cfg.work_counter);
-    } else {
-        cudaError_t e = cudaMemsetAsync(cfg.work_counter, 0, sizeof(unsigned long long), cfg.stream);
-        if (e != cudaSuccess) return e;
-        int per_sm = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_twostates_persistent<MODE>, kBlock, 0);
-        if (e != cudaSuccess) return e;
-        if (per_sm < 1) per_sm = 1;
-        uint64_t want = (n_local + kBlock - 1) / kBlock;
-        uint64_t blocks = (uint64_t) per_sm * cfg.sm_count;
-        if (blocks > want) blocks = want;
-        k_twostates_persistent<MODE><<<(unsigned) blocks, kBlock, 0, cfg.stream>>>(S, G, seed, spp, spp_begin, ns, n_local, acc_old,
-                                                                                    acc_new, cfg.counters, cfg.work_counter);
-    }
-    (*cfg.launches)++;
-    return cudaGetLastError();
-}
-
-cudaError_t launch_twostates(const LaunchCfg &cfg, const SceneK &S, const GridK &G, int mode, uint32_t seed, uint32_t spp,
-                             uint32_t spp_begin, uint32_t spp_end, float4 *acc_old, float4 *acc_new) {
-    uint32_t ns = spp_end - spp_begin;
-    uint64_t n_local = (uint64_t) S.W * S.H * ns;
-    if (n_local == 0) return cudaSuccess;
-    switch (mode) {
-        case 0: return launch_twostates_mode<0>(cfg, S, G, seed, spp, spp_begin, ns, n_local, acc_old, acc_new);
-        case 1: return launch_twostates_mode<1>(cfg, S, G, seed, spp, spp_begin, ns, n_local, acc_old, acc_new);
-        default: return launch_twostates_mode<2>(cfg, S, G, seed, spp, spp_begin, ns, n_local, acc_old, acc_new);
-    }
-}
-
-// ---------------------------------------------------------------------------
-// K5 / K6: volpathsimple primal render and the fused two-pass adjoint
-// ---------------------------------------------------------------------------
 template <bool BACKWARD>
 __device__ __forceinline__ void vps_lane(const SceneK &S, const GridK &G, const GradK &D, uint32_t seed, uint32_t spp, uint64_t idx,
                                          uint32_t alt_seed, const float *grad_img, const float *film_w, float4 *accum,
@@ -229,10 +103,10 @@ __device__ __forceinline__ void vps_lane(const SceneK &S, const GridK &G, const 
 }
 
 template <bool BACKWARD>
-__global__ void __launch_bounds__(kBlock) k_vps(const __grid_constant__ SceneK S, const __grid_constant__ GridK G, GradK D,
-                                                uint32_t seed, uint32_t spp, uint32_t spp_begin, uint32_t ns, uint64_t n_local,
-                                                uint32_t alt_seed, const float *grad_img, const float *film_w, float4 *accum,
-                                                Counters *C, unsigned long long *work, int persistent) {
+__global__ void __launch_bounds__(kBlock) k_vps_simple(const __grid_constant__ SceneK S, const __grid_constant__ GridK G, GradK D,
+                                                       uint32_t seed, uint32_t spp, uint32_t spp_begin, uint32_t ns, uint64_t n_local,
+                                                       uint32_t alt_seed, const float *grad_img, const float *film_w, float4 *accum,
+                                                       Counters *C, unsigned long long *work, int persistent) {
     VpsCounts cnt; cnt.coll = cnt.scat = cnt.g_sig = cnt.g_alb = 0;
     unsigned np = 0;
     if (!persistent) {
@@ -263,66 +137,230 @@ __global__ void __launch_bounds__(kBlock) k_vps(const __grid_constant__ SceneK S
     counter_flush(C, 6, np);
 }
 
-// wavefront schedule of the volpathsimple event machine (rcv_volpathsimple_wf.cuh);
-// same warp scheduler as k_twostates_wavefront, plus the "resume as pass 2" flavour of EV_INIT
-template <bool BACKWARD>
-__global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_vps_wavefront(const __grid_constant__ SceneK S, const __grid_constant__ GridK G, GradK D,
-                                                                uint32_t seed, uint32_t spp, uint32_t spp_begin, uint32_t ns,
-                                                                uint64_t n_local, uint32_t alt_seed, const float *grad_img,
-                                                                const float *film_w, float4 *accum, Counters *C,
-                                                                unsigned long long *work) {
+// ===========================================================================
+// WAVEFRONT schedule
+// ===========================================================================
+#ifndef RCV_WF_BLOCK
+#define RCV_WF_BLOCK 256
+#endif
+#ifndef RCV_WF_MINBLOCKS
+#define RCV_WF_MINBLOCKS 2
+#endif
+#ifndef RCV_SCAT_BATCH
+#define RCV_SCAT_BATCH 8
+#endif
+static constexpr int kWfBlock = RCV_WF_BLOCK;
+static constexpr int kWfMinBlocks = RCV_WF_MINBLOCKS;
+static constexpr int kScatBatch = RCV_SCAT_BATCH;      // run the vertex step once this many lanes wait for it
+static constexpr unsigned long long kChunk = 256;      // records a warp takes from the queue per atomic
+
+// warp-aggregated append to the record queue
+__device__ __forceinline__ unsigned long long queue_slot(unsigned long long *count, bool want) {
+    unsigned m = __ballot_sync(0xffffffffu, want);
+    if (m == 0) return 0;
     const unsigned lane = threadIdx.x & 31;
-    const unsigned lt_mask = (1u << lane) - 1u;
+    const int leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if ((int) lane == leader) base = atomicAdd(count, (unsigned long long) __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + __popc(m & ((1u << lane) - 1u));
+}
+
+// --- ray generation: one thread per lane, no divergence to speak of -----------
+template <int MODE>
+__global__ void __launch_bounds__(kBlock) k_twostates_raygen(const __grid_constant__ SceneK S, uint32_t seed, uint32_t spp,
+                                                             uint32_t spp_begin, uint32_t ns, uint64_t n_local, float4 *acc_old,
+                                                             float4 *acc_new, PathQueue Q, Counters *C) {
+    uint64_t j = (uint64_t) blockIdx.x * kBlock + threadIdx.x;
+    TsLane ln; ln.ev = EV_INIT;
+    TsSink sk; sk.acc_old = acc_old; sk.acc_new = acc_new; sk.n_coll = sk.n_scat = sk.n_paths = 0;
+    if (j < n_local) ts_raygen<MODE>(S, ln, sk, seed, spp, global_lane(j, spp, spp_begin, ns));
+    bool enter = (j < n_local) && ln.ev == EV_COLL;
+    unsigned long long pos = queue_slot(Q.count, enter);
+    if (enter) ts_store(ln, Q, pos);
+    counter_flush(C, 6, sk.n_paths);
+}
+
+template <bool BACKWARD>
+__global__ void __launch_bounds__(kBlock) k_vps_raygen(const __grid_constant__ SceneK S, uint32_t seed, uint32_t spp, uint32_t spp_begin,
+                                                       uint32_t ns, uint64_t n_local, float4 *accum, PathQueue Q, Counters *C) {
+    uint64_t j = (uint64_t) blockIdx.x * kBlock + threadIdx.x;
+    VpLane ln; ln.ev = EV_INIT; ln.flags = 0;
+    VpSink sk; sk.accum = accum; sk.D.gsig = nullptr; sk.D.galb = nullptr; sk.grad_img = nullptr; sk.film_w = nullptr;
+    sk.seed = seed; sk.spp = spp; sk.alt_seed = 0;
+    sk.cnt.coll = sk.cnt.scat = sk.cnt.g_sig = sk.cnt.g_alb = 0; sk.n_paths = 0;
+    if (j < n_local) vp_raygen<BACKWARD>(S, ln, sk, global_lane(j, spp, spp_begin, ns));
+    bool enter = (j < n_local) && ln.ev == EV_COLL;
+    unsigned long long pos = queue_slot(Q.count, enter);
+    if (enter) vp_store(ln, Q, pos);
+    counter_flush(C, 6, sk.n_paths);
+}
+
+// warp-private chunk of queue positions
+struct ChunkCursor {
+    unsigned long long next, end;
+    bool more;
+};
+// all lanes call; the lanes of m_need receive distinct queue positions while work lasts, the others ~0
+__device__ __forceinline__ unsigned long long take_positions(ChunkCursor &cc, unsigned long long *work, unsigned long long n_total,
+                                                             unsigned m_need) {
+    const unsigned lane = threadIdx.x & 31;
+    unsigned long long mine = ~0ull;
+    while (m_need && cc.more) {
+        if (cc.next >= cc.end) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(work, kChunk);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= n_total) { cc.more = false; break; }
+            cc.next = base;
+            cc.end = (base + kChunk < n_total) ? base + kChunk : n_total;
+        }
+        unsigned long long avail = cc.end - cc.next;
+        unsigned rank = __popc(m_need & ((1u << lane) - 1u));
+        bool need = (m_need >> lane) & 1u;
+        bool got = need && rank < avail;
+        if (got) mine = cc.next + rank;
+        unsigned n_need = __popc(m_need);
+        cc.next += (n_need < avail) ? n_need : avail;
+        m_need &= ~__ballot_sync(0xffffffffu, got);
+    }
+    return mine;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_twostates_wavefront(const __grid_constant__ SceneK S,
+                                                                                 const __grid_constant__ GridK G, float4 *acc_old,
+                                                                                 float4 *acc_new, PathQueue Q, Counters *C,
+                                                                                 unsigned long long *work) {
+    const float mu = combined_majorant<MODE>(G);
+    const float inv_mu = 1.f / mu;
+    const unsigned long long n_total = *Q.count;
+    TsLane ln;
+    ln.ev = EV_INIT;
+    TsSink sk; sk.acc_old = acc_old; sk.acc_new = acc_new; sk.n_coll = sk.n_scat = sk.n_paths = 0;
+    ChunkCursor cc; cc.next = 0; cc.end = 0; cc.more = true;
+    while (true) {
+        // refill finished lanes from the record queue
+        unsigned m_init = __ballot_sync(0xffffffffu, ln.ev == EV_INIT);
+        if (m_init && cc.more) {
+            unsigned long long pos = take_positions(cc, work, n_total, m_init);
+            if (pos != ~0ull) ts_load(ln, Q, pos);
+        }
+        unsigned m_coll = __ballot_sync(0xffffffffu, ln.ev == EV_COLL);
+        unsigned m_scat = __ballot_sync(0xffffffffu, ln.ev == EV_SCAT);
+        if (m_coll == 0 && m_scat == 0) break;
+        if (__popc(m_scat) >= kScatBatch || m_coll == 0) {
+            if (ln.ev == EV_SCAT) ts_scatter<MODE>(S, G, ln, sk);
+        } else {
+            if (ln.ev == EV_COLL) ts_collide<MODE>(S, G, mu, inv_mu, ln, sk);
+        }
+        __syncwarp();
+    }
+    counter_flush(C, MODE == 0 ? 0 : 2, sk.n_coll);
+    counter_flush(C, MODE == 0 ? 1 : 3, sk.n_scat);
+    counter_flush(C, 6, sk.n_paths);
+}
+
+// --- cooperative gradient scatter ---------------------------------------------
+// One corner per lane.  The addends are computed with exactly the expressions
+// of vp_req_point (tri_weight(T,k) * sg), so only the order of the float
+// reductions differs from the serial version.
+__device__ __forceinline__ void coop_corner(const SceneK &S, const GridK &G, V3 p, int k, bool &inside, size_t &v, float &w) {
+    Tri T = tri_setup(S, G, p);
+    inside = T.inside;
+    v = tri_voxel(G, T, k);
+    w = tri_weight(T, k);
+}
+
+__device__ __forceinline__ void vp_req_flush_coop(const SceneK &S, const GridK &G, const GradK &D, const VpLane &ln, const VpReq &rq,
+                                                  VpsCounts &cnt) {
+    const unsigned lane = threadIdx.x & 31;
+    const int k = (int) (lane & 7u);
+    const int grp = (int) (lane >> 3);
+    // transmittance segments: 4 points x 8 corners = the 32 lanes, one requesting lane at a time
+    unsigned m = __ballot_sync(0xffffffffu, rq.has_seg);
+    while (m) {
+        int src = __ffs(m) - 1;
+        m &= m - 1;
+        V3 o = mk3(__shfl_sync(0xffffffffu, ln.o.x, src), __shfl_sync(0xffffffffu, ln.o.y, src), __shfl_sync(0xffffffffu, ln.o.z, src));
+        V3 d = mk3(__shfl_sync(0xffffffffu, ln.d.x, src), __shfl_sync(0xffffffffu, ln.d.y, src), __shfl_sync(0xffffffffu, ln.d.z, src));
+        float interval = __shfl_sync(0xffffffffu, rq.interval, src);
+        float sg = __shfl_sync(0xffffffffu, rq.sg_seg, src);
+        float u0 = __shfl_sync(0xffffffffu, rq.u[0], src), u1 = __shfl_sync(0xffffffffu, rq.u[1], src);
+        float u2 = __shfl_sync(0xffffffffu, rq.u[2], src), u3 = __shfl_sync(0xffffffffu, rq.u[3], src);
+        float u = (grp == 0) ? u0 : ((grp == 1) ? u1 : ((grp == 2) ? u2 : u3));
+        bool inside; size_t v; float w;
+        coop_corner(S, G, ray_at(o, d, u * interval), k, inside, v, w);
+        if (inside) {
+            red_add_f32(D.gsig + v, w * sg);
+            if (k == 0) cnt.g_sig++;
+        }
+    }
+    // single points: four requesting lanes at a time, 8 corners each
+    m = __ballot_sync(0xffffffffu, rq.has_pt);
+    while (m) {
+        unsigned src = __fns(m, 0, grp + 1);          // grp-th requesting lane, 0xffffffff if there is none
+        bool valid = src != 0xffffffffu;
+        int s = valid ? (int) src : 0;
+        V3 p = mk3(__shfl_sync(0xffffffffu, rq.p.x, s), __shfl_sync(0xffffffffu, rq.p.y, s), __shfl_sync(0xffffffffu, rq.p.z, s));
+        float sg = __shfl_sync(0xffffffffu, rq.sg, s);
+        int has_alb = __shfl_sync(0xffffffffu, (int) rq.has_alb, s);
+        V3 gal = mk3(__shfl_sync(0xffffffffu, rq.gal.x, s), __shfl_sync(0xffffffffu, rq.gal.y, s), __shfl_sync(0xffffffffu, rq.gal.z, s));
+        if (valid) {
+            bool inside; size_t v; float w;
+            coop_corner(S, G, p, k, inside, v, w);
+            if (inside) {
+                red_add_f32(D.gsig + v, w * sg);
+                if (has_alb) red_add_v4(D.galb + v, w * gal.x, w * gal.y, w * gal.z, 0.f);
+                if (k == 0) { cnt.g_sig++; if (has_alb) cnt.g_alb++; }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) m &= m - 1;       // clears the four lowest set bits (0 stays 0)
+    }
+}
+
+template <bool BACKWARD>
+__global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_vps_wavefront(const __grid_constant__ SceneK S,
+                                                                           const __grid_constant__ GridK G, GradK D, uint32_t seed,
+                                                                           uint32_t spp, uint32_t alt_seed, const float *grad_img,
+                                                                           const float *film_w, float4 *accum, PathQueue Q,
+                                                                           Counters *C, unsigned long long *work) {
     const float mu = __ldg(G.majorants + 1);
+    const float inv_mu = 1.f / mu;
+    const unsigned long long n_total = *Q.count;
     VpLane ln;
     ln.ev = EV_INIT; ln.flags = 0;
     VpSink sk;
     sk.accum = accum; sk.D = D; sk.grad_img = grad_img; sk.film_w = film_w;
     sk.seed = seed; sk.spp = spp; sk.alt_seed = alt_seed;
     sk.cnt.coll = sk.cnt.scat = sk.cnt.g_sig = sk.cnt.g_alb = 0; sk.n_paths = 0;
-    unsigned long long chunk_next = 0, chunk_end = 0;
-    bool more = true;
+    ChunkCursor cc; cc.next = 0; cc.end = 0; cc.more = true;
     while (true) {
+        // resume lanes that finished pass 1 as pass 2; refill the finished ones
         const bool is_init = ln.ev == EV_INIT;
         const bool resume = BACKWARD && is_init && (ln.flags & VF_PASS2);
+        if (resume) vp_load(ln, sk, Q, ln.qpos, true);
         unsigned m_new = __ballot_sync(0xffffffffu, is_init && !resume);
-        unsigned m_res = __ballot_sync(0xffffffffu, resume);
+        if (m_new && cc.more) {
+            unsigned long long pos = take_positions(cc, work, n_total, m_new);
+            if (pos != ~0ull) vp_load(ln, sk, Q, pos, false);
+        }
         unsigned m_coll = __ballot_sync(0xffffffffu, ln.ev == EV_COLL);
         unsigned m_scat = __ballot_sync(0xffffffffu, ln.ev == EV_SCAT);
-        int n_new = more ? __popc(m_new) : 0;
-        int n_init = n_new + __popc(m_res), n_coll = __popc(m_coll), n_scat = __popc(m_scat);
-        if (n_coll == 0 && n_scat == 0 && n_init == 0) break;
-        int sel;
-        if (n_coll >= kCollThreshold || (n_scat == 0 && n_init == 0)) sel = EV_COLL;
-        else if (n_scat >= n_init) sel = EV_SCAT;
-        else sel = EV_INIT;
-        if (sel == EV_COLL) {
-            if (ln.ev == EV_COLL) vp_collide<BACKWARD>(S, G, mu, ln, sk);
-        } else if (sel == EV_SCAT) {
-            if (ln.ev == EV_SCAT) vp_vertex<BACKWARD>(S, G, mu, ln, sk);
+        if (m_coll == 0 && m_scat == 0) break;
+        VpReq rq;
+        vp_req_clear(rq);
+        rq.p = mk3(0, 0, 0); rq.gal = mk3(0, 0, 0); rq.sg = 0.f; rq.interval = 0.f; rq.sg_seg = 0.f;
+        rq.u[0] = rq.u[1] = rq.u[2] = rq.u[3] = 0.f;
+        if (__popc(m_scat) >= kScatBatch || m_coll == 0) {
+            const bool mine = ln.ev == EV_SCAT;
+            if (mine) vp_vertex_a<BACKWARD>(S, G, ln, sk, rq);
+            if (BACKWARD) vp_req_flush_coop(S, G, D, ln, rq, sk.cnt);
+            if (mine) vp_vertex_b<BACKWARD>(S, ln, sk);
         } else {
-            bool have = true;
-            if (n_new > 0 && chunk_next >= chunk_end) {
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(work, kChunk);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (base >= n_local) { more = false; have = false; }
-                else {
-                    chunk_next = base;
-                    chunk_end = (base + kChunk < n_local) ? base + kChunk : n_local;
-                }
-            }
-            if (resume) {
-                vp_resume<BACKWARD>(S, ln, sk);
-            } else if (is_init && have && n_new > 0) {
-                unsigned long long avail = chunk_end - chunk_next;
-                unsigned rank = __popc(m_new & lt_mask);
-                if (rank < avail) vp_begin<BACKWARD>(S, ln, sk, global_lane(chunk_next + rank, spp, spp_begin, ns));
-            }
-            if (have && n_new > 0) {
-                unsigned long long avail = chunk_end - chunk_next;
-                chunk_next += ((unsigned long long) n_new < avail) ? (unsigned long long) n_new : avail;
-            }
+            if (ln.ev == EV_COLL) vp_collide<BACKWARD>(S, G, mu, inv_mu, ln, sk, rq);
+            if (BACKWARD) vp_req_flush_coop(S, G, D, ln, rq, sk.cnt);
         }
         __syncwarp();
     }
@@ -333,6 +371,62 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_vps_wavefront(const 
     counter_flush(C, 6, sk.n_paths);
 }
 
+// ===========================================================================
+// launchers
+// ===========================================================================
+template <typename K>
+static cudaError_t persistent_grid(const LaunchCfg &cfg, K kernel, int block, uint64_t n_items, unsigned &blocks) {
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    uint64_t want = (n_items + block - 1) / block;
+    uint64_t b = (uint64_t) per_sm * cfg.sm_count;
+    if (b > want) b = want;
+    blocks = (unsigned) (b < 1 ? 1 : b);
+    return cudaSuccess;
+}
+
+template <int MODE>
+static cudaError_t launch_twostates_mode(const LaunchCfg &cfg, const SceneK &S, const GridK &G, uint32_t seed, uint32_t spp,
+                                         uint32_t spp_begin, uint32_t ns, uint64_t n_local, float4 *acc_old, float4 *acc_new) {
+    cudaError_t e;
+    if (cfg.tracer == 0) {
+        if ((e = cudaMemsetAsync(cfg.work_counter, 0, sizeof(unsigned long long), cfg.stream)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(cfg.queue.count, 0, sizeof(unsigned long long), cfg.stream)) != cudaSuccess) return e;
+        k_twostates_raygen<MODE><<<(unsigned) ((n_local + kBlock - 1) / kBlock), kBlock, 0, cfg.stream>>>(
+            S, seed, spp, spp_begin, ns, n_local, acc_old, acc_new, cfg.queue, cfg.counters);
+        unsigned blocks;
+        if ((e = persistent_grid(cfg, k_twostates_wavefront<MODE>, kWfBlock, n_local, blocks)) != cudaSuccess) return e;
+        k_twostates_wavefront<MODE><<<blocks, kWfBlock, 0, cfg.stream>>>(S, G, acc_old, acc_new, cfg.queue, cfg.counters,
+                                                                         cfg.work_counter);
+        (*cfg.launches) += 2;
+    } else {
+        int persistent = cfg.tracer == 2;
+        unsigned blocks = (unsigned) ((n_local + kBlock - 1) / kBlock);
+        if (persistent) {
+            if ((e = cudaMemsetAsync(cfg.work_counter, 0, sizeof(unsigned long long), cfg.stream)) != cudaSuccess) return e;
+            if ((e = persistent_grid(cfg, k_twostates_simple<MODE>, kBlock, n_local, blocks)) != cudaSuccess) return e;
+        }
+        k_twostates_simple<MODE><<<blocks, kBlock, 0, cfg.stream>>>(S, G, seed, spp, spp_begin, ns, n_local, acc_old, acc_new,
+                                                                    cfg.counters, cfg.work_counter, persistent);
+        (*cfg.launches)++;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_twostates(const LaunchCfg &cfg, const SceneK &S, const GridK &G, int mode, uint32_t seed, uint32_t spp,
+                             uint32_t spp_begin, uint32_t spp_end, float4 *acc_old, float4 *acc_new) {
+    uint32_t ns = spp_end - spp_begin;
+    uint64_t n_local = (uint64_t) S.W * S.H * ns;
+    if (n_local == 0) return cudaSuccess;
+    switch (mode) {
+        case 0: return launch_twostates_mode<0>(cfg, S, G, seed, spp, spp_begin, ns, n_local, acc_old, acc_new);
+        case 1: return launch_twostates_mode<1>(cfg, S, G, seed, spp, spp_begin, ns, n_local, acc_old, acc_new);
+        default: return launch_twostates_mode<2>(cfg, S, G, seed, spp, spp_begin, ns, n_local, acc_old, acc_new);
+    }
+}
+
 template <bool BACKWARD>
 static cudaError_t launch_vps(const LaunchCfg &cfg, const SceneK &S, const GridK &G, const GradK &D, uint32_t seed, uint32_t spp,
                               uint32_t spp_begin, uint32_t spp_end, uint32_t alt_seed, const float *grad_img, const float *film_w,
@@ -340,37 +434,28 @@ static cudaError_t launch_vps(const LaunchCfg &cfg, const SceneK &S, const GridK
     uint32_t ns = spp_end - spp_begin;
     uint64_t n_local = (uint64_t) S.W * S.H * ns;
     if (n_local == 0) return cudaSuccess;
+    cudaError_t e;
     if (cfg.tracer == 0) {
-        cudaError_t e = cudaMemsetAsync(cfg.work_counter, 0, sizeof(unsigned long long), cfg.stream);
-        if (e != cudaSuccess) return e;
-        int per_sm = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vps_wavefront<BACKWARD>, kWfBlock, 0);
-        if (e != cudaSuccess) return e;
-        if (per_sm < 1) per_sm = 1;
-        uint64_t want = (n_local + kWfBlock - 1) / kWfBlock;
-        uint64_t blocks = (uint64_t) per_sm * cfg.sm_count;
-        if (blocks > want) blocks = want;
-        k_vps_wavefront<BACKWARD><<<(unsigned) blocks, kWfBlock, 0, cfg.stream>>>(S, G, D, seed, spp, spp_begin, ns, n_local, alt_seed,
-                                                                                   grad_img, film_w, accum, cfg.counters,
-                                                                                   cfg.work_counter);
+        if ((e = cudaMemsetAsync(cfg.work_counter, 0, sizeof(unsigned long long), cfg.stream)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(cfg.queue.count, 0, sizeof(unsigned long long), cfg.stream)) != cudaSuccess) return e;
+        k_vps_raygen<BACKWARD><<<(unsigned) ((n_local + kBlock - 1) / kBlock), kBlock, 0, cfg.stream>>>(
+            S, seed, spp, spp_begin, ns, n_local, accum, cfg.queue, cfg.counters);
+        unsigned blocks;
+        if ((e = persistent_grid(cfg, k_vps_wavefront<BACKWARD>, kWfBlock, n_local, blocks)) != cudaSuccess) return e;
+        k_vps_wavefront<BACKWARD><<<blocks, kWfBlock, 0, cfg.stream>>>(S, G, D, seed, spp, alt_seed, grad_img, film_w, accum, cfg.queue,
+                                                                       cfg.counters, cfg.work_counter);
+        (*cfg.launches) += 2;
     } else {
-        uint64_t want = (n_local + kBlock - 1) / kBlock;
-        uint64_t blocks = want;
-        int persistent = cfg.tracer != 1;
+        int persistent = cfg.tracer == 2;
+        unsigned blocks = (unsigned) ((n_local + kBlock - 1) / kBlock);
         if (persistent) {
-            cudaError_t e = cudaMemsetAsync(cfg.work_counter, 0, sizeof(unsigned long long), cfg.stream);
-            if (e != cudaSuccess) return e;
-            int per_sm = 0;
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vps<BACKWARD>, kBlock, 0);
-            if (e != cudaSuccess) return e;
-            if (per_sm < 1) per_sm = 1;
-            blocks = (uint64_t) per_sm * cfg.sm_count;
-            if (blocks > want) blocks = want;
+            if ((e = cudaMemsetAsync(cfg.work_counter, 0, sizeof(unsigned long long), cfg.stream)) != cudaSuccess) return e;
+            if ((e = persistent_grid(cfg, k_vps_simple<BACKWARD>, kBlock, n_local, blocks)) != cudaSuccess) return e;
         }
-        k_vps<BACKWARD><<<(unsigned) blocks, kBlock, 0, cfg.stream>>>(S, G, D, seed, spp, spp_begin, ns, n_local, alt_seed, grad_img,
-                                                                       film_w, accum, cfg.counters, cfg.work_counter, persistent);
+        k_vps_simple<BACKWARD><<<blocks, kBlock, 0, cfg.stream>>>(S, G, D, seed, spp, spp_begin, ns, n_local, alt_seed, grad_img, film_w,
+                                                                  accum, cfg.counters, cfg.work_counter, persistent);
+        (*cfg.launches)++;
     }
-    (*cfg.launches)++;
     return cudaGetLastError();
 }
 
@@ -393,8 +478,14 @@ __global__ void __launch_bounds__(kBlock) k_film_weights(const __grid_constant__
                                                          uint64_t n_lanes, float *film_w) {
     uint64_t idx = (uint64_t) blockIdx.x * kBlock + threadIdx.x;
     if (idx >= n_lanes) return;
-    Lane L = lane_setup(S, seed, spp, idx);
-    if (L.pix >= 0) red_add_f32(film_w + L.pix, 1.f);
+    // only the film position of lane_setup is needed here
+    Pcg rng;
+    sampler_seed(rng, seed, (uint32_t) idx);
+    uint32_t pixel = (uint32_t) (idx / spp);
+    uint32_t py = pixel / S.W, px = pixel - S.W * py;
+    float u1 = pcg_f32(rng), u2 = pcg_f32(rng);
+    int ix = (int) floorf((float) px + u1), iy = (int) floorf((float) py + u2);
+    if (ix >= 0 && ix < (int) S.W && iy >= 0 && iy < (int) S.H) red_add_f32(film_w + (iy * (int) S.W + ix), 1.f);
 }
 
 cudaError_t launch_film_weights(const LaunchCfg &cfg, const SceneK &S, uint32_t seed, uint32_t spp, float *film_w) {

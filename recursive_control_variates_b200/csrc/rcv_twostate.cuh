@@ -1,4 +1,5 @@
-// rcv_twostate.cuh — per-lane two-state volumetric path tracer (device code).
+// rcv_twostate.cuh — per-lane two-state volumetric path tracer (device code),
+// straight-line version used by the SIMPLE / BATCH schedules.
 //
 // Restates, for one lane and with the Dr.Jit masks resolved into control
 // flow, TwoStatePRBVolpathIntegrator.sample_twostates
@@ -12,6 +13,11 @@
 // MODE 0: two states (sig2.x = theta_{i-1}, sig2.y = theta_i), shared stream.
 // MODE 1/2: both "states" are the old/new one -> the estimator reduces to the
 // ordinary single-state null-scattering path tracer (baseline `prbvolpath`).
+//
+// Arithmetic forms fixed by this build (mirrored by the oracle):
+// divisions by the majorant are multiplications by its IEEE reciprocal, the
+// two weights that share a denominator use one IEEE reciprocal, and 1/d of a
+// ray is computed once per ray.
 #pragma once
 #include "rcv_device.cuh"
 
@@ -34,12 +40,12 @@ __device__ __forceinline__ float combined_majorant(const GridK &G) {
 // here; sigma_s (albedo) is needed at real scatters only and fetched there —
 // the results are identical to fetching it at every tentative collision.
 template <int MODE>
-__device__ __forceinline__ void sample_interaction2(const SceneK &S, const GridK &G, float mu, V3 o, V3 d, float ray_maxt,
-                                                    float u, Mei2 &m, Tri &T, unsigned &n_coll) {
+__device__ __forceinline__ void sample_interaction2(const SceneK &S, const GridK &G, float inv_mu, V3 o, V3 d, V3 id,
+                                                    float ray_maxt, float u, Mei2 &m, Tri &T, unsigned &n_coll) {
     float mint, maxt;
-    bool active = medium_interval(S, o, d, ray_maxt, mint, maxt);    // :22
+    bool active = medium_interval(S, o, d, id, ray_maxt, mint, maxt);   // :22
     float tau = -spec_log(1.f - u);                                   // :24
-    float t = mint + (tau / mu);                                      // :78
+    float t = mint + (tau * inv_mu);                                  // :78
     bool valid = active && (t <= maxt);                               // :80
     m.t = valid ? t : inf_();                                         // :88
     m.p = ray_at(o, d, t);                                            // :89
@@ -57,10 +63,11 @@ __device__ __forceinline__ void sample_interaction2(const SceneK &S, const GridK
 // tracking towards it.  Transmittances are scalars: all three channels carry
 // the same value because sigma_t is monochromatic.
 template <int MODE>
-__device__ __forceinline__ void nee_twostates(const SceneK &S, const GridK &G, float mu, Pcg &rng, V3 ref_p, float &tr_old,
-                                              float &tr_new, V3 &dir, unsigned &n_coll) {
+__device__ __forceinline__ void nee_twostates(const SceneK &S, const GridK &G, float mu, float inv_mu, Pcg &rng, V3 ref_p,
+                                              float &tr_old, float &tr_new, V3 &dir, unsigned &n_coll) {
     float s2x = pcg_f32(rng), s2y = pcg_f32(rng);                     // :393
     V3 d = uniform_sphere(s2x, s2y);
+    V3 id = rcp3(d);
     V3 o = ref_p;                                                     // :399 (n = 0: no offset)
     float total_dist = 0.f;
     Hit si; si.valid = false; si.t = 0.f; si.p = mk3(0, 0, 0); si.n = mk3(0, 0, 0);
@@ -69,18 +76,18 @@ __device__ __forceinline__ void nee_twostates(const SceneK &S, const GridK &G, f
     while (true) {                                                    // :408
         float remaining = S.env_dist * (1.f - RCV_SHADOW_EPS) - total_dist;   // :409
         if (!(remaining > 0.f)) break;                                // :411
-        if (needs_isect) { si = box_hit(S, o, d, remaining); needs_isect = false; }   // :414-416
+        if (needs_isect) { si = box_hit(S, o, d, id, remaining); needs_isect = false; }   // :414-416
         if (in_medium) {
             float u = pcg_f32(rng);                                   // :422
             Mei2 m; Tri T;
-            sample_interaction2<MODE>(S, G, mu, o, d, remaining, u, m, T, n_coll);
+            sample_interaction2<MODE>(S, G, inv_mu, o, d, id, remaining, u, m, T, n_coll);
             if (si.t < m.t) m.t = inf_();                             // :423-424
             if (m.t < inf_()) {                                       // :444
                 o = m.p;                                              // :445
                 si.t = si.t - m.t;                                    // :446
                 float sn_o = mu - m.so, sn_n = mu - m.sn;
-                tr_old = tr_old * ((mu != 0.f) ? (sn_o / mu) : sn_o); // :447-452, :462-463
-                tr_new = tr_new * ((mu != 0.f) ? (sn_n / mu) : sn_n);
+                tr_old = tr_old * ((mu != 0.f) ? (sn_o * inv_mu) : sn_o); // :447-452, :462-463
+                tr_new = tr_new * ((mu != 0.f) ? (sn_n * inv_mu) : sn_n);
                 if (!(tr_new != 0.f || tr_old != 0.f)) break;         // :472
                 total_dist += m.t;                                    // :473
                 continue;
@@ -101,6 +108,7 @@ template <int MODE>
 __device__ __forceinline__ void trace_twostates(const SceneK &S, const GridK &G, Pcg &rng, V3 o, V3 d, V3 &L_old, V3 &L_new,
                                                 unsigned &n_coll, unsigned &n_scat) {
     const float mu = combined_majorant<MODE>(G);
+    const float inv_mu = 1.f / mu;
     const V3 env = mk3(S.env[0], S.env[1], S.env[2]);
     int depth = 0;
     L_old = mk3(0, 0, 0); L_new = mk3(0, 0, 0);
@@ -108,6 +116,7 @@ __device__ __forceinline__ void trace_twostates(const SceneK &S, const GridK &G,
     Hit si; si.valid = false; si.t = 0.f; si.p = mk3(0, 0, 0); si.n = mk3(0, 0, 0);
     bool needs_isect = true, in_medium = false, specular_chain = true;
     float last_pdf = 1.f;
+    V3 id = rcp3(d);
     (void) pcg_f32(rng);                                              // :173 channel draw
 
     while (true) {                                                    // :180
@@ -123,18 +132,18 @@ __device__ __forceinline__ void trace_twostates(const SceneK &S, const GridK &G,
         if (in_medium) {
             float u = pcg_f32(rng);                                   // :194
             Mei2 m; Tri T;
-            sample_interaction2<MODE>(S, G, mu, o, d, RCV_LARGEST, u, m, T, n_coll);   // :196
-            if (needs_isect) { si = box_hit(S, o, d, RCV_LARGEST); needs_isect = false; }   // :200-204
+            sample_interaction2<MODE>(S, G, inv_mu, o, d, id, RCV_LARGEST, u, m, T, n_coll);   // :196
+            if (needs_isect) { si = box_hit(S, o, d, id, RCV_LARGEST); needs_isect = false; }   // :200-204
             if (si.t < m.t) m.t = inf_();                             // :205-206
             if (m.t < inf_()) {                                       // :217
-                float sp_new = m.sn / mu, sp_old = m.so / mu;         // :223-224
+                float sp_new = m.sn * inv_mu, sp_old = m.so * inv_mu; // :223-224
                 float prob = (mu != 0.f) ? (sp_new + sp_old) * 0.5f : 0.f;   // :225
                 float xi = pcg_f32(rng);                              // :227
                 if (xi >= prob) {
                     // null collision (:230-231, :256-257, :265-266)
                     float sn_n = mu - m.sn, sn_o = mu - m.so;
-                    float den = sn_n + sn_o;
-                    float w_new = (sn_n * 2.f) / den, w_old = (sn_o * 2.f) / den;
+                    float rden = 1.f / (sn_n + sn_o);
+                    float w_new = (sn_n * 2.f) * rden, w_old = (sn_o * 2.f) * rden;
                     o = m.p;
                     si.t = si.t - m.t;
                     thr_new = thr_new * w_new; thr_old = thr_old * w_old;
@@ -147,9 +156,9 @@ __device__ __forceinline__ void trace_twostates(const SceneK &S, const GridK &G,
                 V3 a_new = (MODE == 1) ? lookup_albedo(G, T, 0) : lookup_albedo(G, T, 1);
                 V3 a_old = (MODE == 0) ? lookup_albedo(G, T, 0) : a_new;
                 V3 ss_new = splat3(m.sn) * a_new, ss_old = splat3(m.so) * a_old;
-                float den = m.sn + m.so;                              // :259-260
-                thr_new = thr_new * ((ss_new * 2.f) / splat3(den));
-                thr_old = thr_old * ((ss_old * 2.f) / splat3(den));
+                float rden = 1.f / (m.sn + m.so);                     // :259-260
+                thr_new = thr_new * ((ss_new * 2.f) * rden);
+                thr_old = thr_old * ((ss_old * 2.f) * rden);
                 (void) pcg_f32(rng);                                  // :275 sample1
                 float s2x = pcg_f32(rng), s2y = pcg_f32(rng);
                 V3 wi = mk3(-d.x, -d.y, -d.z);
@@ -157,7 +166,7 @@ __device__ __forceinline__ void trace_twostates(const SceneK &S, const GridK &G,
                 V3 wo = phase_sample(S, wi, s2x, s2y, pdf);
                 bool scattered = pdf > 0.f;                           // :276
                 if (scattered) {                                      // :278-281
-                    o = m.p; d = wo;
+                    o = m.p; d = wo; id = rcp3(d);
                     needs_isect = true;
                     last_pdf = pdf;
                 }
@@ -166,7 +175,7 @@ __device__ __forceinline__ void trace_twostates(const SceneK &S, const GridK &G,
                     specular_chain = specular_chain || (scattered && !S.sample_emitters);
                     if (scattered && S.sample_emitters) {
                         float tr_old, tr_new; V3 dir;
-                        nee_twostates<MODE>(S, G, mu, rng, m.p, tr_old, tr_new, dir, n_coll);
+                        nee_twostates<MODE>(S, G, mu, inv_mu, rng, m.p, tr_old, tr_new, dir, n_coll);
                         V3 emitter_val = mk3(env.x / RCV_INV_FOURPI, env.y / RCV_INV_FOURPI, env.z / RCV_INV_FOURPI);
                         float phase_val = phase_eval(S, wi, dir);     // :333-334
                         float mis_em = mis_weight(RCV_INV_FOURPI, phase_val);   // :341
@@ -182,7 +191,7 @@ __device__ __forceinline__ void trace_twostates(const SceneK &S, const GridK &G,
             }
             // escaped the medium: continue with the surface part using the stored si
         } else if (needs_isect) {                                     // :285-286
-            si = box_hit(S, o, d, RCV_LARGEST);
+            si = box_hit(S, o, d, id, RCV_LARGEST);
             needs_isect = false;
         }
         // ---- emitter hit (:288-308): the environment is "hit" when nothing else is

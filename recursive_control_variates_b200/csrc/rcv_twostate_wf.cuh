@@ -1,12 +1,14 @@
 // rcv_twostate_wf.cuh — the two-state path tracer as a per-lane event machine.
 //
 // Same estimator and same random-number stream as rcv_twostate.cuh (and as
-// plugins/twostatevolpath.py:141-479), but cut into three event handlers so
-// that a persistent warp can run every handler with (nearly) all of its lanes
-// and refill finished lanes from a work queue:
+// plugins/twostatevolpath.py:141-479), cut into pieces that a persistent warp
+// can run with (nearly) all of its lanes:
 //
-//   EV_INIT    start a new path: sampler seed, camera ray, first loop head,
-//              boundary crossing into the medium (or direct environment hit)
+//   ts_raygen  (its own, fully convergent kernel) start of every path:
+//              sampler seed, camera ray, first loop head, boundary crossing.
+//              Paths that miss the medium are finished here; the others are
+//              appended as 48-byte path records to a queue in HBM.
+//   ts_load    a finished lane picks up the next record (three float4 loads)
 //   EV_COLL    ONE tentative collision on the lane's current segment — the
 //              main path (delta tracking, :180-266) or the shadow ray of next
 //              event estimation (ratio tracking, :408-477): loop head, free
@@ -29,6 +31,7 @@ struct TsLane {
     int pix;                // film pixel of the path (-1: outside the film)
     Pcg rng;
     V3 o, d;                // main-path ray
+    V3 id;                  // 1/d of the CURRENT segment (main ray, or the shadow ray during NEE)
     V3 thr_old, thr_new, L_old, L_new;
     float si_t;             // distance to the boundary along the current segment
     float last_pdf;
@@ -84,32 +87,52 @@ __device__ __forceinline__ bool ts_loop_head(const SceneK &S, TsLane &ln) {
     return true;
 }
 
-// surface iterations of a path that is outside the medium (:283-380 with the
-// null BSDF): ends in the environment, or crosses the boundary into the medium
+// Start of a path (:150-173) and its surface iterations outside the medium
+// (:283-380 with the null BSDF): the path ends in the environment (ev = EV_INIT,
+// already splatted) or crosses the boundary into the medium (ev = EV_COLL).
 template <int MODE>
-__device__ __forceinline__ void ts_outside(const SceneK &S, TsLane &ln, TsSink &sk) {
-    while (true) {
-        if (!ts_loop_head(S, ln)) { ts_finish<MODE>(ln, sk); return; }
-        Hit h = box_hit(S, ln.o, ln.d, RCV_LARGEST);
-        if (!h.valid) { ts_env_hit(S, ln); ts_finish<MODE>(ln, sk); return; }
-        (void) pcg_f32(ln.rng); (void) pcg_f32(ln.rng); (void) pcg_f32(ln.rng);   // :347-348
-        ln.o = offset_p(h.p, h.n, ln.d);
-        ln.flags |= F_NEEDS_ISECT;
-        if (!(dot3(h.n, ln.d) > 0.f)) { ln.ev = EV_COLL; return; }   // :378-379 entered the medium
-    }
-}
-
-template <int MODE>
-__device__ __forceinline__ void ts_init(const SceneK &S, TsLane &ln, TsSink &sk, uint32_t seed, uint32_t spp, uint64_t idx) {
+__device__ __forceinline__ void ts_raygen(const SceneK &S, TsLane &ln, TsSink &sk, uint32_t seed, uint32_t spp, uint64_t idx) {
     Lane L = lane_setup(S, seed, spp, idx);
     ln.rng = L.rng; ln.o = L.o; ln.d = L.d; ln.pix = L.pix;
+    ln.id = rcp3(ln.d);
     ln.depth = 0;
     ln.L_old = mk3(0, 0, 0); ln.L_new = mk3(0, 0, 0);
     ln.thr_old = mk3(1, 1, 1); ln.thr_new = mk3(1, 1, 1);
     ln.si_t = 0.f; ln.last_pdf = 1.f;
     ln.flags = F_NEEDS_ISECT | F_SPECULAR;
     (void) pcg_f32(ln.rng);                                           // :173 channel draw
-    ts_outside<MODE>(S, ln, sk);
+    while (true) {
+        if (!ts_loop_head(S, ln)) { ts_finish<MODE>(ln, sk); return; }
+        Hit h = box_hit(S, ln.o, ln.d, ln.id, RCV_LARGEST);
+        if (!h.valid) { ts_env_hit(S, ln); ts_finish<MODE>(ln, sk); return; }
+        (void) pcg_f32(ln.rng); (void) pcg_f32(ln.rng); (void) pcg_f32(ln.rng);   // :347-348
+        ln.o = offset_p(h.p, h.n, ln.d);
+        if (!(dot3(h.n, ln.d) > 0.f)) { ln.ev = EV_COLL; return; }   // :378-379 entered the medium
+    }
+}
+
+// path record <-> lane.  A record is written when the path enters the medium
+// with depth 0, unit throughput and no radiance yet (rcv_scene_set rejects
+// rr_depth < 0, the only way the first loop heads could rescale throughput).
+__device__ __forceinline__ void ts_store(const TsLane &ln, const PathQueue &Q, unsigned long long pos) {
+    Q.r0[pos] = make_float4(__uint_as_float((uint32_t) ln.rng.state), __uint_as_float((uint32_t) (ln.rng.state >> 32)),
+                            __uint_as_float((uint32_t) (ln.rng.inc >> 1)), __int_as_float(ln.pix));
+    Q.r1[pos] = make_float4(ln.o.x, ln.o.y, ln.o.z, 0.f);
+    Q.r2[pos] = make_float4(ln.d.x, ln.d.y, ln.d.z, 0.f);
+}
+__device__ __forceinline__ void ts_load(TsLane &ln, const PathQueue &Q, unsigned long long pos) {
+    float4 a = __ldg(Q.r0 + pos), b = __ldg(Q.r1 + pos), c = __ldg(Q.r2 + pos);
+    ln.rng.state = (uint64_t) __float_as_uint(a.x) | ((uint64_t) __float_as_uint(a.y) << 32);
+    ln.rng.inc = ((uint64_t) __float_as_uint(a.z) << 1) | 1u;
+    ln.pix = (int) __float_as_uint(a.w);
+    ln.o = mk3(b.x, b.y, b.z); ln.d = mk3(c.x, c.y, c.z);
+    ln.id = rcp3(ln.d);
+    ln.depth = 0;
+    ln.L_old = mk3(0, 0, 0); ln.L_new = mk3(0, 0, 0);
+    ln.thr_old = mk3(1, 1, 1); ln.thr_new = mk3(1, 1, 1);
+    ln.si_t = 0.f; ln.last_pdf = 1.f;
+    ln.flags = F_NEEDS_ISECT | F_SPECULAR;
+    ln.ev = EV_COLL;
 }
 
 // end of the shadow ray: add the emitter-sampling contribution (:336-344),
@@ -122,10 +145,11 @@ __device__ __forceinline__ void ts_nee_finish(const SceneK &S, TsLane &ln) {
     ln.L_old = ln.L_old + ((ln.thr_old * ln.phase_val) * mis_em) * (emitter_val * splat3(ln.tr_old));
     ln.thr_old = ln.thr_old * ln.ratio;
     ln.flags = (ln.flags & ~F_IN_NEE) | F_NEEDS_ISECT;
+    ln.id = rcp3(ln.d);
 }
 
 template <int MODE>
-__device__ __forceinline__ void ts_collide(const SceneK &S, const GridK &G, float mu, TsLane &ln, TsSink &sk) {
+__device__ __forceinline__ void ts_collide(const SceneK &S, const GridK &G, float mu, float inv_mu, TsLane &ln, TsSink &sk) {
     const bool nee = (ln.flags & F_IN_NEE) != 0;
     V3 so, sd; float maxt;
     if (!nee) {
@@ -138,9 +162,9 @@ __device__ __forceinline__ void ts_collide(const SceneK &S, const GridK &G, floa
     }
     float u = pcg_f32(ln.rng);                                        // :194 / :422
     Mei2 m; Tri T;
-    sample_interaction2<MODE>(S, G, mu, so, sd, maxt, u, m, T, sk.n_coll);
+    sample_interaction2<MODE>(S, G, inv_mu, so, sd, ln.id, maxt, u, m, T, sk.n_coll);
     if (ln.flags & F_NEEDS_ISECT) {                                   // :200-204 / :414-416
-        Hit h = box_hit(S, so, sd, maxt);
+        Hit h = box_hit(S, so, sd, ln.id, maxt);
         ln.si_t = h.t;
         ln.flags = (ln.flags & ~(F_NEEDS_ISECT | F_SI_VALID)) | (h.valid ? F_SI_VALID : 0u);
     }
@@ -150,19 +174,19 @@ __device__ __forceinline__ void ts_collide(const SceneK &S, const GridK &G, floa
             ln.no = m.p;
             ln.si_t = ln.si_t - m.t;
             float sn_o = mu - m.so, sn_n = mu - m.sn;
-            ln.tr_old = ln.tr_old * ((mu != 0.f) ? (sn_o / mu) : sn_o);
-            ln.tr_new = ln.tr_new * ((mu != 0.f) ? (sn_n / mu) : sn_n);
+            ln.tr_old = ln.tr_old * ((mu != 0.f) ? (sn_o * inv_mu) : sn_o);
+            ln.tr_new = ln.tr_new * ((mu != 0.f) ? (sn_n * inv_mu) : sn_n);
             if (!(ln.tr_new != 0.f || ln.tr_old != 0.f)) { ts_nee_finish(S, ln); return; }
             ln.total += m.t;
             return;
         }
-        float sp_new = m.sn / mu, sp_old = m.so / mu;                 // :223-225
+        float sp_new = m.sn * inv_mu, sp_old = m.so * inv_mu;         // :223-225
         float prob = (mu != 0.f) ? (sp_new + sp_old) * 0.5f : 0.f;
         float xi = pcg_f32(ln.rng);                                   // :227
         if (xi >= prob) {                                             // null collision
             float sn_n = mu - m.sn, sn_o = mu - m.so;
-            float den = sn_n + sn_o;
-            float w_new = (sn_n * 2.f) / den, w_old = (sn_o * 2.f) / den;
+            float rden = 1.f / (sn_n + sn_o);
+            float w_new = (sn_n * 2.f) * rden, w_old = (sn_o * 2.f) * rden;
             ln.o = m.p;
             ln.si_t = ln.si_t - m.t;
             ln.thr_new = ln.thr_new * w_new; ln.thr_old = ln.thr_old * w_old;
@@ -192,9 +216,9 @@ __device__ __forceinline__ void ts_scatter(const SceneK &S, const GridK &G, TsLa
     V3 a_new = (MODE == 1) ? lookup_albedo(G, T, 0) : lookup_albedo(G, T, 1);
     V3 a_old = (MODE == 0) ? lookup_albedo(G, T, 0) : a_new;
     V3 ss_new = splat3(st_new) * a_new, ss_old = splat3(st_old) * a_old;
-    float den = st_new + st_old;                                      // :259-260
-    ln.thr_new = ln.thr_new * ((ss_new * 2.f) / splat3(den));
-    ln.thr_old = ln.thr_old * ((ss_old * 2.f) / splat3(den));
+    float rden = 1.f / (st_new + st_old);                             // :259-260
+    ln.thr_new = ln.thr_new * ((ss_new * 2.f) * rden);
+    ln.thr_old = ln.thr_old * ((ss_old * 2.f) * rden);
     (void) pcg_f32(ln.rng);                                           // :275
     float s2x = pcg_f32(ln.rng), s2y = pcg_f32(ln.rng);
     V3 wi = mk3(-ln.d.x, -ln.d.y, -ln.d.z);
@@ -212,6 +236,7 @@ __device__ __forceinline__ void ts_scatter(const SceneK &S, const GridK &G, TsLa
         if (S.sample_emitters) {
             float e2x = pcg_f32(ln.rng), e2y = pcg_f32(ln.rng);       // :393
             ln.nd = uniform_sphere(e2x, e2y);
+            ln.id = rcp3(ln.nd);
             ln.no = ln.o;
             ln.total = 0.f; ln.tr_old = 1.f; ln.tr_new = 1.f;
             ln.phase_val = phase_eval(S, wi, ln.nd);
@@ -221,6 +246,7 @@ __device__ __forceinline__ void ts_scatter(const SceneK &S, const GridK &G, TsLa
         }
     }
     ln.thr_old = ln.thr_old * ratio;
+    ln.id = rcp3(ln.d);
 }
 
 }  // namespace rcv

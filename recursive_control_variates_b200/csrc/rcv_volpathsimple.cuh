@@ -26,12 +26,12 @@ struct Mei1 {
 };
 
 // Medium::sample_interaction of state `new` with a global majorant
-__device__ __forceinline__ void sample_interaction1(const SceneK &S, const GridK &G, float mu, V3 o, V3 d, float ray_maxt,
-                                                    float u, Mei1 &m, VpsCounts &cnt) {
+__device__ __forceinline__ void sample_interaction1(const SceneK &S, const GridK &G, float inv_mu, V3 o, V3 d, V3 id,
+                                                    float ray_maxt, float u, Mei1 &m, VpsCounts &cnt) {
     float mint, maxt;
-    bool active = medium_interval(S, o, d, ray_maxt, mint, maxt);
+    bool active = medium_interval(S, o, d, id, ray_maxt, mint, maxt);
     float tau = -spec_log(1.f - u);
-    float t = mint + (tau / mu);
+    float t = mint + (tau * inv_mu);
     m.valid = active && (t <= maxt);
     m.t = m.valid ? t : inf_();
     m.p = ray_at(o, d, t);
@@ -56,23 +56,24 @@ __device__ __forceinline__ void scatter_sigma_t(const SceneK &S, const GridK &G,
 
 // volpathsimple.py:449-517, ratio tracking from o along d over [0, tmax]
 template <bool ADJ>
-__device__ __forceinline__ float estimate_transmittance(const SceneK &S, const GridK &G, const GradK &D, float mu, Pcg &rng,
-                                                        V3 o, V3 d, float tmax, bool active, V3 adjoint, VpsCounts &cnt) {
+__device__ __forceinline__ float estimate_transmittance(const SceneK &S, const GridK &G, const GradK &D, float mu, float inv_mu,
+                                                        Pcg &rng, V3 o, V3 d, V3 id, float tmax, bool active, V3 adjoint,
+                                                        VpsCounts &cnt) {
     o = ray_at(o, d, 0.f);                                            // :467 (tmin = 0)
     float tr_acc = active ? 1.f : 0.f;                                // :472
     while (active) {                                                  // :478
         float u = pcg_f32(rng);
         Mei1 m;
-        sample_interaction1(S, G, mu, o, d, tmax, u, m, cnt);         // :482
+        sample_interaction1(S, G, inv_mu, o, d, id, tmax, u, m, cnt); // :482
         float sn = m.valid ? (mu - m.st) : 0.f;
         float ce = m.valid ? mu : 0.f;
-        float tr = (ce != 0.f) ? (sn / ce) : sn;                      // :486-489
+        float tr = (ce != 0.f) ? (sn * inv_mu) : sn;                  // :486-489
         if (m.t > tmax) m.t = inf_();                                 // :493
         if (!(m.t < inf_())) break;                                   // :494
         if (ADJ) {                                                    // :496-505
             float g = 0.f;
             if (tr > 0.f) {
-                float k = (-1.f / ce) / tr;
+                float k = (-inv_mu) / tr;
                 g += adjoint.x * k; g += adjoint.y * k; g += adjoint.z * k;
             }
             scatter_sigma_t(S, G, D, m.p, g, cnt);
@@ -87,31 +88,34 @@ __device__ __forceinline__ float estimate_transmittance(const SceneK &S, const G
 
 // volpathsimple.py:419-446; returns the scalar transmittance, the sampled direction in `dir`
 template <bool ADJ>
-__device__ __forceinline__ float vps_sample_emitter(const SceneK &S, const GridK &G, const GradK &D, float mu, Pcg &rng, V3 ref_p,
-                                                    V3 adjoint, V3 &dir, VpsCounts &cnt) {
+__device__ __forceinline__ float vps_sample_emitter(const SceneK &S, const GridK &G, const GradK &D, float mu, float inv_mu,
+                                                    Pcg &rng, V3 ref_p, V3 adjoint, V3 &dir, VpsCounts &cnt) {
     float s2x = pcg_f32(rng), s2y = pcg_f32(rng);                     // :431
     V3 d = uniform_sphere(s2x, s2y);
-    Hit si = box_hit(S, ref_p, d, RCV_LARGEST);                       // :440-441
+    V3 id = rcp3(d);
+    Hit si = box_hit(S, ref_p, d, id, RCV_LARGEST);                   // :440-441
     dir = d;
-    return estimate_transmittance<ADJ>(S, G, D, mu, rng, ref_p, d, si.t, si.valid, adjoint, cnt);   // :443
+    return estimate_transmittance<ADJ>(S, G, D, mu, inv_mu, rng, ref_p, d, id, si.t, si.valid, adjoint, cnt);   // :443
 }
 
 template <bool ADJ>
 __device__ __forceinline__ void vps_trace(const SceneK &S, const GridK &G, const GradK &D, Pcg &rng, Pcg &alt, V3 o, V3 d, V3 dL,
                                           V3 state_in, V3 &result, VpsCounts &cnt) {
     const float mu = __ldg(G.majorants + 1);       // state `new` (twostatemedium.py:125-136)
+    const float inv_mu = 1.f / mu;
+    V3 id = rcp3(d);
     const V3 env = mk3(S.env[0], S.env[1], S.env[2]);
     result = ADJ ? state_in : mk3(0, 0, 0);                           // :68
     V3 thr = mk3(1, 1, 1);
     int depth = 0;
     (void) pcg_f32(rng);                                              // :84
     // reach_medium (:305-332)
-    Hit si = box_hit(S, o, d, RCV_LARGEST);                           // :311
+    Hit si = box_hit(S, o, d, id, RCV_LARGEST);                       // :311
     bool escaped = !si.valid, active = si.valid;
     float ray_maxt = RCV_LARGEST;
     if (active) {
         o = offset_p(si.p, si.n, d);                                  // :319
-        Hit si2 = box_hit(S, o, d, RCV_LARGEST);                      // :320
+        Hit si2 = box_hit(S, o, d, id, RCV_LARGEST);                  // :320
         active = si2.valid;                                           // :323
         if (active) { ray_maxt = isfinite(si2.t) ? si2.t : RCV_LARGEST; si = si2; }   // :329-330
     }
@@ -132,10 +136,10 @@ __device__ __forceinline__ void vps_trace(const SceneK &S, const GridK &G, const
         while (true) {                                                // :360
             float u = pcg_f32(rng);
             Mei1 m;
-            sample_interaction1(S, G, mu, ro, d, rmaxt, u, m, cnt);   // :361
+            sample_interaction1(S, G, inv_mu, ro, d, id, rmaxt, u, m, cnt);   // :361
             mei_t = m.t + running_t;                                  // :364
             if (!m.valid) { did_scatter = false; break; }             // :371
-            float r = (mu != 0.f) ? (m.st / mu) : 0.f;                // :367
+            float r = (mu != 0.f) ? (m.st * inv_mu) : 0.f;            // :367
             float xi = pcg_f32(rng);                                  // :372
             if (!(xi >= r)) { did_scatter = true; break; }
             ro = ro + d * m.t;                                        // :378-380
@@ -193,13 +197,13 @@ __device__ __forceinline__ void vps_trace(const SceneK &S, const GridK &G, const
         if (S.use_nee && did_scatter && active) {                     // :219-228, :393-416
             Pcg nee_rng = rng;                                        // :396 sampler.clone()
             V3 dir;
-            float tr = vps_sample_emitter<false>(S, G, D, mu, rng, mei_p, mk3(0, 0, 0), dir, cnt);
+            float tr = vps_sample_emitter<false>(S, G, D, mu, inv_mu, rng, mei_p, mk3(0, 0, 0), dir, cnt);
             V3 emitted = mk3(env.x / RCV_INV_FOURPI, env.y / RCV_INV_FOURPI, env.z / RCV_INV_FOURPI) * splat3(tr);
             float phase_val = phase_eval(S, wi, dir);                 // :401
             V3 nee = ((thr * phase_val) * mis_weight(RCV_INV_FOURPI, phase_val)) * emitted;   // :404
             if (ADJ) {
                 V3 dir2;
-                (void) vps_sample_emitter<true>(S, G, D, mu, nee_rng, mei_p, dL * nee, dir2, cnt);   // :412-414
+                (void) vps_sample_emitter<true>(S, G, D, mu, inv_mu, nee_rng, mei_p, dL * nee, dir2, cnt);   // :412-414
                 result = result - nee;                                // :227
             } else {
                 result = result + nee;                                // :225
@@ -210,10 +214,10 @@ __device__ __forceinline__ void vps_trace(const SceneK &S, const GridK &G, const
             float s2x = pcg_f32(rng), s2y = pcg_f32(rng);
             float pdf;
             V3 wo = phase_sample(S, wi, s2x, s2y, pdf);
-            o = mei_p; d = wo; ray_maxt = RCV_LARGEST;
+            o = mei_p; d = wo; id = rcp3(d); ray_maxt = RCV_LARGEST;
             last_pdf = pdf;
         }
-        si = box_hit(S, o, d, ray_maxt);                              // :246-248 (needs_update is always true here)
+        si = box_hit(S, o, d, id, ray_maxt);                          // :246-248 (needs_update is always true here)
         ray_maxt = isfinite(si.t) ? si.t : RCV_LARGEST;
         if (did_scatter && !si.valid) active = false;                 // :253-254
         if (did_escape) {                                             // :257-258
@@ -223,7 +227,7 @@ __device__ __forceinline__ void vps_trace(const SceneK &S, const GridK &G, const
         }
     }
     if (!ADJ) {                                                       // :276-300
-        if (escaped && si.valid) si = box_hit(S, o, d, ray_maxt);     // :277-278
+        if (escaped && si.valid) si = box_hit(S, o, d, id, ray_maxt); // :277-278
         if (escaped && !si.valid && !((depth <= 0) && S.hide_emitters)) {
             float w = 1.f;
             if (S.use_nee) w = mis_weight(last_pdf, has_scattered ? RCV_INV_FOURPI : 0.f);   // :286-291

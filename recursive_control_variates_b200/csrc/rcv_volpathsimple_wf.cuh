@@ -3,16 +3,26 @@
 // scheduler.  Same estimator, same random streams and the same arithmetic as
 // rcv_volpathsimple.cuh; cut into
 //
-//   EV_INIT   begin a path (pass 1, primal) or resume it as pass 2 (adjoint
-//             replay of the identical stream, RBIntegrator.render_backward)
-//   EV_COLL   ONE tentative collision: a delta-tracking step of
-//             sample_real_interaction (:360-380) or a ratio-tracking step of
-//             estimate_transmittance (:478-515) — in the adjoint's NEE replay
-//             (:406-414) with the sigma_t gradient scatter of :496-505
-//   EV_SCAT   a path vertex (real collision or medium exit): coefficient
-//             gathers, the adjoint's scattering (:165-185) and transmittance
-//             (:194-202, :597-620) gradient scatters, NEE set-up (:393-446)
+//   vp_raygen  (its own, fully convergent kernel) camera ray, dummy channel
+//              draw (:84), reach_medium (:305-332), alt_seed_rnd draw (:112);
+//              paths that never enter the medium end here, the others become
+//              48-byte path records in HBM
+//   vp_load    a lane picks up a record: to begin pass 1 (primal) or to resume
+//              the same path as pass 2 (adjoint replay of the identical stream,
+//              RBIntegrator.render_backward)
+//   EV_COLL    ONE tentative collision: a delta-tracking step of
+//              sample_real_interaction (:360-380) or a ratio-tracking step of
+//              estimate_transmittance (:478-515) — in the adjoint's NEE replay
+//              (:406-414) it emits the sigma_t gradient request of :496-505
+//   EV_SCAT    a path vertex (real collision or medium exit), in two halves:
+//              vp_vertex_a  coefficient gathers, the adjoint's scattering
+//                           (:165-185) and transmittance (:194-202, :597-620)
+//                           gradient requests
+//              vp_vertex_b  NEE set-up (:393-446) or phase sampling (:234-258)
 //
+// Gradient scatters are not executed by the handlers: they are returned as a
+// VpReq and flushed between the two vertex halves — cooperatively by the whole
+// warp on the GPU (rcv_trace.cu), serially in the host harness.
 // The handlers contain no warp intrinsics and also compile for the host
 // (RCV_HOST_EMU) where tests single-step them against the oracle.
 #pragma once
@@ -29,16 +39,19 @@ enum : uint32_t {
     VF_REPLAY = 16u,      // NEE transmittance replay with gradients
     VF_HEAD = 32u,        // next main-path collision starts with the loop head (:129-134)
     VF_DID_SCATTER = 64u,
-    VF_PASS2 = 128u       // pass 1 finished, EV_INIT must resume the lane as pass 2
+    VF_PASS2 = 128u,      // pass 1 finished, the lane must reload its record as pass 2
+    VF_ACTIVE = 256u      // `active` after :213, carried from vertex_a to vertex_b
 };
 
 struct VpLane {
     int ev, pix, depth;
     uint32_t idx, flags;
+    uint32_t qpos;          // position of the path's record in the queue
     Pcg rng, alt;
     uint64_t saved;         // main sampler state parked during the NEE / its replay
     V3 o, d;                // current ray (origin = last vertex)
-    float ray_maxt;         // distance to the boundary along it (== si.t)
+    V3 id;                  // 1/direction of the current segment (ray, or shadow ray during NEE)
+    float ray_maxt;         // distance to the boundary along the ray (== si.t)
     V3 thr, result, dL;
     float last_pdf;
     V3 ro;                  // running origin: delta tracking, or the shadow ray
@@ -48,14 +61,51 @@ struct VpLane {
     V3 nee;                 // NEE contribution of this vertex (needed after the replay)
 };
 
+// gradient scatter requests of one handler invocation
+struct VpReq {
+    bool has_pt;            // one point: d sigma_t (+ d albedo at scattering vertices)
+    bool has_alb;
+    V3 p;
+    float sg;               // scale * g: weight of the sigma_t gradient
+    V3 gal;                 // albedo gradient
+    bool has_seg;           // transmittance term: 4 points u_j * interval along (ln.o, ln.d)
+    float interval, sg_seg;
+    float u[4];
+};
+__device__ __forceinline__ void vp_req_clear(VpReq &rq) { rq.has_pt = false; rq.has_alb = false; rq.has_seg = false; }
+
 struct VpSink {
     float4 *accum;          // primal render target (H,W,4) or null
-    GradK D;                // packed gradient grid (adjoint)
+    GradK D;                // gradient grids (adjoint)
     const float *grad_img, *film_w;
     uint32_t seed, spp, alt_seed;
     VpsCounts cnt;
     unsigned n_paths;
 };
+
+// serial execution of a request (host harness; the GPU kernels use the
+// cooperative version in rcv_trace.cu, which produces the same addends)
+__device__ __forceinline__ void vp_req_point(const SceneK &S, const GridK &G, const GradK &D, V3 p, float sg, bool has_alb, V3 gal,
+                                             VpsCounts &cnt) {
+    Tri T = tri_setup(S, G, p);
+    if (!T.inside) return;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        float w = tri_weight(T, k);
+        size_t v = tri_voxel(G, T, k);
+        red_add_f32(D.gsig + v, w * sg);
+        if (has_alb) red_add_v4(D.galb + v, w * gal.x, w * gal.y, w * gal.z, 0.f);
+    }
+    cnt.g_sig++;
+    if (has_alb) cnt.g_alb++;
+}
+__device__ __forceinline__ void vp_req_flush_serial(const SceneK &S, const GridK &G, const GradK &D, const VpLane &ln, const VpReq &rq,
+                                                    VpsCounts &cnt) {
+    if (rq.has_pt) vp_req_point(S, G, D, rq.p, rq.sg, rq.has_alb, rq.gal, cnt);
+    if (rq.has_seg)
+        for (int j = 0; j < 4; ++j)
+            vp_req_point(S, G, D, ray_at(ln.o, ln.d, rq.u[j] * rq.interval), rq.sg_seg, false, mk3(0, 0, 0), cnt);
+}
 
 template <bool BW>
 __device__ __forceinline__ void vp_end_pass(const SceneK &S, VpLane &ln, VpSink &sk) {
@@ -85,43 +135,78 @@ __device__ __forceinline__ void vp_end_pass(const SceneK &S, VpLane &ln, VpSink 
     ln.flags = VF_PASS2;
 }
 
-// start pass 1 (adj = false) or pass 2 (adj = true) of lane ln.idx: camera ray,
-// dummy channel draw (:84), reach_medium (:305-332), alt_seed_rnd draw (:112)
+// Start of a path up to the first loop iteration: camera ray, dummy channel
+// draw (:84), reach_medium (:305-332), alt_seed_rnd draw (:112).  Paths that do
+// not enter the medium are complete: their primal value is splatted here when
+// rendering (BW = false); they carry no gradient.  ev = EV_COLL: record it.
 template <bool BW>
-__device__ __forceinline__ void vp_start_pass(const SceneK &S, VpLane &ln, VpSink &sk, bool adj) {
-    Lane L = lane_setup(S, sk.seed, sk.spp, (uint64_t) ln.idx);
+__device__ __forceinline__ void vp_raygen(const SceneK &S, VpLane &ln, VpSink &sk, uint64_t idx) {
+    Lane L = lane_setup(S, sk.seed, sk.spp, idx);
+    ln.idx = (uint32_t) idx;
     ln.rng = L.rng; ln.o = L.o; ln.d = L.d; ln.pix = L.pix;
-    if (adj) sampler_seed(ln.alt, sk.alt_seed, ln.idx);              // :119-120
-    else ln.result = mk3(0, 0, 0);                                    // :68 (pass 2 starts from state_in = pass-1 result)
+    ln.id = rcp3(ln.d);
+    ln.result = mk3(0, 0, 0);
     ln.thr = mk3(1, 1, 1);
     ln.depth = 0;
     ln.last_pdf = 1.f;
-    ln.flags = adj ? VF_ADJ : 0u;
+    ln.flags = 0;
     (void) pcg_f32(ln.rng);                                           // :84
-    Hit si = box_hit(S, ln.o, ln.d, RCV_LARGEST);                     // :311
+    Hit si = box_hit(S, ln.o, ln.d, ln.id, RCV_LARGEST);              // :311
     bool active = si.valid;
     if (!si.valid) ln.flags |= VF_ESCAPED;
     ln.ray_maxt = RCV_LARGEST;
     if (active) {
         ln.o = offset_p(si.p, si.n, ln.d);                            // :319
-        Hit si2 = box_hit(S, ln.o, ln.d, RCV_LARGEST);                // :320
+        Hit si2 = box_hit(S, ln.o, ln.d, ln.id, RCV_LARGEST);         // :320
         active = si2.valid;                                           // :323
         if (active) ln.ray_maxt = isfinite(si2.t) ? si2.t : RCV_LARGEST;   // :329
     }
-    if (!active) { vp_end_pass<BW>(S, ln, sk); return; }
+    if (!active) {
+        if (BW) {
+            sk.n_paths += 2;                    // nothing to differentiate: both passes are complete
+            ln.flags = 0; ln.ev = EV_INIT;
+        } else {
+            vp_end_pass<false>(S, ln, sk);      // environment contribution (:276-300) + splat
+        }
+        return;
+    }
     (void) pcg_f32(ln.rng);                                           // :112 alt_seed_rnd
-    ln.flags |= VF_HEAD;
     ln.ev = EV_COLL;
 }
 
-template <bool BW>
-__device__ __forceinline__ void vp_begin(const SceneK &S, VpLane &ln, VpSink &sk, uint64_t idx) {
-    ln.idx = (uint32_t) idx;
-    vp_start_pass<BW>(S, ln, sk, false);
+__device__ __forceinline__ void vp_store(const VpLane &ln, const PathQueue &Q, unsigned long long pos) {
+    Q.r0[pos] = make_float4(__uint_as_float((uint32_t) ln.rng.state), __uint_as_float((uint32_t) (ln.rng.state >> 32)),
+                            __uint_as_float((uint32_t) (ln.rng.inc >> 1)), __int_as_float(ln.pix));
+    Q.r1[pos] = make_float4(ln.o.x, ln.o.y, ln.o.z, ln.ray_maxt);
+    Q.r2[pos] = make_float4(ln.d.x, ln.d.y, ln.d.z, __uint_as_float(ln.idx));
 }
-template <bool BW>
-__device__ __forceinline__ void vp_resume(const SceneK &S, VpLane &ln, VpSink &sk) {
-    vp_start_pass<BW>(S, ln, sk, true);
+// begin pass 1 (adj = false) or pass 2 (adj = true) of the path recorded at pos
+__device__ __forceinline__ void vp_load(VpLane &ln, const VpSink &sk, const PathQueue &Q, unsigned long long pos, bool adj) {
+    float4 a = __ldg(Q.r0 + pos), b = __ldg(Q.r1 + pos), c = __ldg(Q.r2 + pos);
+    ln.qpos = (uint32_t) pos;
+    ln.rng.state = (uint64_t) __float_as_uint(a.x) | ((uint64_t) __float_as_uint(a.y) << 32);
+    ln.rng.inc = ((uint64_t) __float_as_uint(a.z) << 1) | 1u;
+    ln.pix = (int) __float_as_uint(a.w);
+    ln.o = mk3(b.x, b.y, b.z); ln.ray_maxt = b.w;
+    ln.d = mk3(c.x, c.y, c.z); ln.idx = __float_as_uint(c.w);
+    ln.id = rcp3(ln.d);
+    if (adj) sampler_seed(ln.alt, sk.alt_seed, ln.idx);               // :119-120
+    else ln.result = mk3(0, 0, 0);                                    // :68 (pass 2 starts from state_in = pass-1 result)
+    ln.thr = mk3(1, 1, 1);
+    ln.depth = 0;
+    ln.last_pdf = 1.f;
+    ln.flags = (adj ? VF_ADJ : 0u) | VF_HEAD;
+    ln.ev = EV_COLL;
+}
+
+// (re)start the shadow ray at the current vertex; false when it has no extent
+__device__ __forceinline__ bool vp_nee_start(const SceneK &S, VpLane &ln) {
+    V3 mei_p = ray_at(ln.o, ln.d, ln.mei_t);
+    Hit si = box_hit(S, mei_p, ln.nd, ln.id, RCV_LARGEST);            // :440-441
+    ln.ro = ray_at(mei_p, ln.nd, 0.f);                                // :467 (tmin = 0)
+    ln.rmaxt = si.t;
+    ln.tr_acc = si.valid ? 1.f : 0.f;                                 // :472
+    return si.valid;
 }
 
 // after the vertex (and its NEE): phase sampling, new ray, boundary distance (:234-258)
@@ -139,24 +224,14 @@ __device__ __forceinline__ void vp_post_vertex(const SceneK &S, VpLane &ln, VpSi
     float s2x = pcg_f32(ln.rng), s2y = pcg_f32(ln.rng);
     float pdf;
     V3 wo = phase_sample(S, wi, s2x, s2y, pdf);
-    ln.o = mei_p; ln.d = wo;
+    ln.o = mei_p; ln.d = wo; ln.id = rcp3(wo);
     ln.last_pdf = pdf;
-    Hit si = box_hit(S, ln.o, ln.d, RCV_LARGEST);                     // :247
+    Hit si = box_hit(S, ln.o, ln.d, ln.id, RCV_LARGEST);              // :247
     ln.ray_maxt = isfinite(si.t) ? si.t : RCV_LARGEST;                // :248
     if (!si.valid) active = false;                                    // :253-254
     if (!active) { vp_end_pass<BW>(S, ln, sk); return; }
     ln.flags |= VF_HEAD;
     ln.ev = EV_COLL;
-}
-
-// (re)start the shadow ray at the current vertex; false when it has no extent
-__device__ __forceinline__ bool vp_nee_start(const SceneK &S, VpLane &ln) {
-    V3 mei_p = ray_at(ln.o, ln.d, ln.mei_t);
-    Hit si = box_hit(S, mei_p, ln.nd, RCV_LARGEST);                   // :440-441
-    ln.ro = ray_at(mei_p, ln.nd, 0.f);                                // :467 (tmin = 0)
-    ln.rmaxt = si.t;
-    ln.tr_acc = si.valid ? 1.f : 0.f;                                 // :472
-    return si.valid;
 }
 
 // the shadow ray (or its replay) ended
@@ -191,25 +266,26 @@ __device__ __forceinline__ void vp_nee_done(const SceneK &S, VpLane &ln, VpSink 
 }
 
 template <bool BW>
-__device__ __forceinline__ void vp_collide(const SceneK &S, const GridK &G, float mu, VpLane &ln, VpSink &sk) {
+__device__ __forceinline__ void vp_collide(const SceneK &S, const GridK &G, float mu, float inv_mu, VpLane &ln, VpSink &sk,
+                                           VpReq &rq) {
     if (ln.flags & VF_IN_NEE) {
         // estimate_transmittance step (:478-515)
         float u = pcg_f32(ln.rng);
         Mei1 m;
-        sample_interaction1(S, G, mu, ln.ro, ln.nd, ln.rmaxt, u, m, sk.cnt);   // :482
+        sample_interaction1(S, G, inv_mu, ln.ro, ln.nd, ln.id, ln.rmaxt, u, m, sk.cnt);   // :482
         float sn = m.valid ? (mu - m.st) : 0.f;
         float ce = m.valid ? mu : 0.f;
-        float tr = (ce != 0.f) ? (sn / ce) : sn;                      // :486-489
+        float tr = (ce != 0.f) ? (sn * inv_mu) : sn;                  // :486-489
         if (m.t > ln.rmaxt) m.t = inf_();                             // :493
         if (!(m.t < inf_())) { vp_nee_done<BW>(S, ln, sk); return; }  // :494
         if (BW && (ln.flags & VF_REPLAY)) {                           // :496-505
             V3 adjoint = ln.dL * ln.nee;                              // :412
             float g = 0.f;
             if (tr > 0.f) {
-                float k = (-1.f / ce) / tr;
+                float k = (-inv_mu) / tr;
                 g += adjoint.x * k; g += adjoint.y * k; g += adjoint.z * k;
             }
-            scatter_sigma_t(S, G, sk.D, m.p, g, sk.cnt);
+            rq.has_pt = true; rq.has_alb = false; rq.p = m.p; rq.sg = S.scale * g; rq.gal = mk3(0, 0, 0);
         }
         ln.tr_acc = ln.tr_acc * tr;                                   // :508
         ln.ro = m.p;                                                  // :510
@@ -228,10 +304,10 @@ __device__ __forceinline__ void vp_collide(const SceneK &S, const GridK &G, floa
     }
     float u = pcg_f32(ln.rng);                                        // :361
     Mei1 m;
-    sample_interaction1(S, G, mu, ln.ro, ln.d, ln.rmaxt, u, m, sk.cnt);
+    sample_interaction1(S, G, inv_mu, ln.ro, ln.d, ln.id, ln.rmaxt, u, m, sk.cnt);
     ln.mei_t = m.t + ln.running_t;                                    // :364
     if (!m.valid) { ln.flags &= ~VF_DID_SCATTER; ln.ev = EV_SCAT; return; }   // :371 escape
-    float r = (mu != 0.f) ? (m.st / mu) : 0.f;                        // :367
+    float r = (mu != 0.f) ? (m.st * inv_mu) : 0.f;                    // :367
     float xi = pcg_f32(ln.rng);                                       // :372
     if (!(xi >= r)) { ln.flags |= VF_DID_SCATTER; ln.ev = EV_SCAT; return; }
     ln.ro = ln.ro + ln.d * m.t;                                       // :378-380
@@ -239,17 +315,17 @@ __device__ __forceinline__ void vp_collide(const SceneK &S, const GridK &G, floa
     ln.running_t = ln.running_t + m.t;
 }
 
+// first half of a vertex: gathers, gradient requests, throughput/depth update
 template <bool BW>
-__device__ __forceinline__ void vp_vertex(const SceneK &S, const GridK &G, float mu, VpLane &ln, VpSink &sk) {
+__device__ __forceinline__ void vp_vertex_a(const SceneK &S, const GridK &G, VpLane &ln, VpSink &sk, VpReq &rq) {
     const bool did_scatter = (ln.flags & VF_DID_SCATTER) != 0;
     const bool adj = BW && (ln.flags & VF_ADJ);
     if (did_scatter) ln.flags |= VF_HAS_SCAT;                         // :150
     V3 mei_p = mk3(0, 0, 0), albedo = mk3(1, 1, 1);
     float st = 0.f;
-    Tri T;
     if (did_scatter) {
         mei_p = ray_at(ln.o, ln.d, ln.mei_t);                         // :384
-        T = tri_setup(S, G, mei_p);
+        Tri T = tri_setup(S, G, mei_p);
         if (adj) st = lookup_sigma1(S, G, T);                         // :386-388
         albedo = lookup_albedo(G, T, 1);                              // :154
         sk.cnt.scat++;
@@ -260,37 +336,33 @@ __device__ __forceinline__ void vp_vertex(const SceneK &S, const GridK &G, float
             V3 Li = ln.result / vmax3(splat3(1e-8f), albedo);
             V3 c = (ln.dL * Li) * inv_pdf;
             float g_st = (c.x * albedo.x + c.y * albedo.y) + c.z * albedo.z;
-            V3 g_al = c * splat3(st);
-            if (T.inside) {
-                float sg = S.scale * g_st;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    float w = tri_weight(T, k);
-                    size_t v = tri_voxel(G, T, k);
-                    red_add_f32(sk.D.gsig + v, w * sg);
-                    red_add_v4(sk.D.galb + v, w * g_al.x, w * g_al.y, w * g_al.z, 0.f);
-                }
-                sk.cnt.g_sig++; sk.cnt.g_alb++;
-            }
+            rq.has_pt = true; rq.has_alb = true; rq.p = mei_p; rq.sg = S.scale * g_st; rq.gal = c * splat3(st);
         }
         // transmittance term (:194-202, :597-620)
         V3 aw = ln.dL * ln.result;
         float interval = did_scatter ? ln.mei_t : ln.ray_maxt;        // :601 (si.t == ray.maxt)
         float inv_pdf = interval / 4.f;
         float g = -((aw.x * inv_pdf) + (aw.y * inv_pdf) + (aw.z * inv_pdf));
-#pragma unroll 1
-        for (int j = 0; j < 4; ++j) {
-            float t = pcg_f32(ln.alt) * interval;                     // :608
-            scatter_sigma_t(S, G, sk.D, ray_at(ln.o, ln.d, t), g, sk.cnt);
-        }
+        rq.has_seg = true; rq.interval = interval; rq.sg_seg = S.scale * g;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rq.u[j] = pcg_f32(ln.alt);        // :608
     }
     ln.thr = ln.thr * albedo;                                         // :206
     if (did_scatter) ln.depth += 1;                                   // :212
     bool active = did_scatter && (ln.depth < S.max_depth);            // :213
+    ln.flags = active ? (ln.flags | VF_ACTIVE) : (ln.flags & ~VF_ACTIVE);
+}
+
+// second half: NEE set-up or the continuation of the path
+template <bool BW>
+__device__ __forceinline__ void vp_vertex_b(const SceneK &S, VpLane &ln, VpSink &sk) {
+    const bool did_scatter = (ln.flags & VF_DID_SCATTER) != 0;
+    const bool active = (ln.flags & VF_ACTIVE) != 0;
     if (S.use_nee && did_scatter && active) {                         // :219-228 -> :393-446
         ln.saved = ln.rng.state;                                      // :396 sampler.clone()
         float s2x = pcg_f32(ln.rng), s2y = pcg_f32(ln.rng);           // :431
         ln.nd = uniform_sphere(s2x, s2y);
+        ln.id = rcp3(ln.nd);
         ln.flags |= VF_IN_NEE;
         ln.ev = EV_COLL;
         if (!vp_nee_start(S, ln)) vp_nee_done<BW>(S, ln, sk);

@@ -40,20 +40,68 @@ void pack(const rcv_scene_desc &d, const float *so, const float *ao, const float
     P.G.nx = nx; P.G.ny = ny; P.G.nz = nz; P.G.majorants = P.maj;
 }
 
+struct HostQueue {
+    std::vector<float4> r0, r1, r2;
+    unsigned long long count;
+    PathQueue Q;
+    explicit HostQueue(size_t n) : r0(n), r1(n), r2(n), count(0) { Q.r0 = r0.data(); Q.r1 = r1.data(); Q.r2 = r2.data(); Q.count = &count; }
+};
+
+// raygen for all lanes (as the GPU's ray-generation kernel), then the event
+// machines record by record
 template <int MODE>
 void run_twostates(const SceneK &S, const GridK &G, uint32_t seed, uint32_t spp, float4 *acc_old, float4 *acc_new, uint64_t *cnt) {
     const float mu = combined_majorant<MODE>(G);
+    const float inv_mu = 1.f / mu;
     TsSink sk; sk.acc_old = acc_old; sk.acc_new = acc_new; sk.n_coll = sk.n_scat = sk.n_paths = 0;
     uint64_t n = (uint64_t) S.W * S.H * spp;
+    HostQueue hq(n);
     for (uint64_t idx = 0; idx < n; ++idx) {
+        TsLane ln; ln.ev = EV_INIT;
+        ts_raygen<MODE>(S, ln, sk, seed, spp, idx);
+        if (ln.ev == EV_COLL) ts_store(ln, hq.Q, hq.count++);
+    }
+    for (unsigned long long pos = 0; pos < hq.count; ++pos) {
         TsLane ln;
-        ts_init<MODE>(S, ln, sk, seed, spp, idx);
+        ts_load(ln, hq.Q, pos);
         while (ln.ev != EV_INIT) {
-            if (ln.ev == EV_COLL) ts_collide<MODE>(S, G, mu, ln, sk);
+            if (ln.ev == EV_COLL) ts_collide<MODE>(S, G, mu, inv_mu, ln, sk);
             else ts_scatter<MODE>(S, G, ln, sk);
         }
-        cnt[0] += sk.n_coll; cnt[1] += sk.n_scat; cnt[6] += sk.n_paths;
-        sk.n_coll = sk.n_scat = sk.n_paths = 0;
+    }
+    cnt[0] += sk.n_coll; cnt[1] += sk.n_scat; cnt[6] += sk.n_paths;
+}
+
+template <bool BW>
+void run_vps(const SceneK &S, const GridK &G, VpSink &sk) {
+    const float mu = G.majorants[1];
+    const float inv_mu = 1.f / mu;
+    uint64_t n = (uint64_t) S.W * S.H * sk.spp;
+    HostQueue hq(n);
+    for (uint64_t idx = 0; idx < n; ++idx) {
+        VpLane ln; ln.ev = EV_INIT; ln.flags = 0;
+        vp_raygen<BW>(S, ln, sk, idx);
+        if (ln.ev == EV_COLL) vp_store(ln, hq.Q, hq.count++);
+    }
+    for (unsigned long long pos = 0; pos < hq.count; ++pos) {
+        VpLane ln; ln.flags = 0;
+        vp_load(ln, sk, hq.Q, pos, false);
+        while (true) {
+            if (ln.ev == EV_INIT) {
+                if (!(BW && (ln.flags & VF_PASS2))) break;
+                vp_load(ln, sk, hq.Q, ln.qpos, true);
+                continue;
+            }
+            VpReq rq; vp_req_clear(rq);
+            if (ln.ev == EV_COLL) {
+                vp_collide<BW>(S, G, mu, inv_mu, ln, sk, rq);
+                if (BW) vp_req_flush_serial(S, G, sk.D, ln, rq, sk.cnt);
+            } else {
+                vp_vertex_a<BW>(S, G, ln, sk, rq);
+                if (BW) vp_req_flush_serial(S, G, sk.D, ln, rq, sk.cnt);
+                vp_vertex_b<BW>(S, ln, sk);
+            }
+        }
     }
 }
 
@@ -83,25 +131,7 @@ int emu_vps(const rcv_scene_desc *d, const float *sn, const float *an, int nz, i
     VpSink sk; sk.accum = (float4 *) accum; sk.D.gsig = gsig; sk.D.galb = (float4 *) galb4; sk.grad_img = grad_img; sk.film_w = film_w;
     sk.seed = seed; sk.spp = spp; sk.alt_seed = alt_seed;
     sk.cnt.coll = sk.cnt.scat = sk.cnt.g_sig = sk.cnt.g_alb = 0; sk.n_paths = 0;
-    const float mu = P.maj[1];
-    uint64_t n = (uint64_t) S.W * S.H * spp;
-    for (uint64_t idx = 0; idx < n; ++idx) {
-        VpLane ln;
-        ln.flags = 0;
-        if (backward) vp_begin<true>(S, ln, sk, idx); else vp_begin<false>(S, ln, sk, idx);
-        while (true) {
-            if (ln.ev == EV_INIT) {
-                if (!(ln.flags & VF_PASS2)) break;
-                vp_resume<true>(S, ln, sk);
-            } else if (backward) {
-                if (ln.ev == EV_COLL) vp_collide<true>(S, P.G, mu, ln, sk);
-                else vp_vertex<true>(S, P.G, mu, ln, sk);
-            } else {
-                if (ln.ev == EV_COLL) vp_collide<false>(S, P.G, mu, ln, sk);
-                else vp_vertex<false>(S, P.G, mu, ln, sk);
-            }
-        }
-    }
+    if (backward) run_vps<true>(S, P.G, sk); else run_vps<false>(S, P.G, sk);
     counters[2] = sk.cnt.coll; counters[3] = sk.cnt.scat; counters[4] = sk.cnt.g_sig; counters[5] = sk.cnt.g_alb;
     counters[6] = sk.n_paths;
     return 0;
