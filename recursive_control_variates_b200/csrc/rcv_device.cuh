@@ -52,6 +52,7 @@ struct SceneK {
     float g;
     int sample_emitters;
     float env[3];
+    float env_over_pdf[3];    // env[c] / (1 / 4 pi): constant.cpp sample_direction value (radiance / pdf)
     float env_dist;
     int max_depth, rr_depth, hide_emitters, use_nee;
 };

@@ -13,6 +13,7 @@ inline void scene_from_desc(const rcv_scene_desc &d, SceneK &S) {
         S.bmin[i] = d.bbox_min[i]; S.bmax[i] = d.bbox_max[i];
         S.inv_ext[i] = 1.f / (d.bbox_max[i] - d.bbox_min[i]);
         S.env[i] = d.env_radiance[i];
+        S.env_over_pdf[i] = d.env_radiance[i] / RCV_INV_FOURPI;
     }
     for (int i = 0; i < 9; ++i) S.cam_axes[i] = d.cam_axes[i];
     S.tan_x = d.cam_tan_x; S.tan_y = d.cam_tan_y; S.near_clip = d.cam_near_clip;

@@ -146,12 +146,12 @@ __global__ void __launch_bounds__(kBlock) k_vps_simple(const __grid_constant__ S
 #ifndef RCV_WF_MINBLOCKS
 #define RCV_WF_MINBLOCKS 2
 #endif
-#ifndef RCV_SCAT_BATCH
-#define RCV_SCAT_BATCH 8
+#ifndef RCV_EVENT_BATCH
+#define RCV_EVENT_BATCH 8
 #endif
 static constexpr int kWfBlock = RCV_WF_BLOCK;
 static constexpr int kWfMinBlocks = RCV_WF_MINBLOCKS;
-static constexpr int kScatBatch = RCV_SCAT_BATCH;      // run the vertex step once this many lanes wait for it
+static constexpr int kEventBatch = RCV_EVENT_BATCH;    // run the vertex / slow step once this many lanes wait for it
 static constexpr unsigned long long kChunk = 256;      // records a warp takes from the queue per atomic
 
 // warp-aggregated append to the record queue
@@ -194,6 +194,15 @@ __global__ void __launch_bounds__(kBlock) k_vps_raygen(const __grid_constant__ S
     unsigned long long pos = queue_slot(Q.count, enter);
     if (enter) vp_store(ln, Q, pos);
     counter_flush(C, 6, sk.n_paths);
+}
+
+// Which handler a warp runs this round.  The collision step is the common case;
+// the vertex step and the slow step run once kEventBatch lanes wait for them (or
+// when no lane is ready to collide), so that they too execute with many lanes.
+__device__ __forceinline__ int pick_event(int n_coll, int n_scat, int n_slow) {
+    if (n_slow >= kEventBatch || n_scat >= kEventBatch) return (n_slow >= n_scat) ? EV_SLOW : EV_SCAT;
+    if (n_coll > 0) return EV_COLL;
+    return (n_slow >= n_scat) ? EV_SLOW : EV_SCAT;
 }
 
 // warp-private chunk of queue positions
@@ -240,19 +249,24 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_twostates_wavefront(
     TsSink sk; sk.acc_old = acc_old; sk.acc_new = acc_new; sk.n_coll = sk.n_scat = sk.n_paths = 0;
     ChunkCursor cc; cc.next = 0; cc.end = 0; cc.more = true;
     while (true) {
-        // refill finished lanes from the record queue
-        unsigned m_init = __ballot_sync(0xffffffffu, ln.ev == EV_INIT);
-        if (m_init && cc.more) {
-            unsigned long long pos = take_positions(cc, work, n_total, m_init);
-            if (pos != ~0ull) ts_load(ln, Q, pos);
-        }
-        unsigned m_coll = __ballot_sync(0xffffffffu, ln.ev == EV_COLL);
-        unsigned m_scat = __ballot_sync(0xffffffffu, ln.ev == EV_SCAT);
-        if (m_coll == 0 && m_scat == 0) break;
-        if (__popc(m_scat) >= kScatBatch || m_coll == 0) {
+        const int n_coll = __popc(__ballot_sync(0xffffffffu, ln.ev == EV_COLL));
+        const int n_scat = __popc(__ballot_sync(0xffffffffu, ln.ev == EV_SCAT));
+        // lanes waiting for the slow step: parked work, or empty lanes while records remain
+        const int n_slow = __popc(__ballot_sync(0xffffffffu, ln.ev == EV_SLOW || (ln.ev == EV_INIT && cc.more)));
+        if (n_coll == 0 && n_scat == 0 && n_slow == 0) break;
+        const int sel = pick_event(n_coll, n_scat, n_slow);
+        if (sel == EV_COLL) {
+            if (ln.ev == EV_COLL) ts_collide<MODE>(S, G, mu, inv_mu, ln, sk);
+        } else if (sel == EV_SCAT) {
             if (ln.ev == EV_SCAT) ts_scatter<MODE>(S, G, ln, sk);
         } else {
-            if (ln.ev == EV_COLL) ts_collide<MODE>(S, G, mu, inv_mu, ln, sk);
+            if (ln.ev == EV_SLOW) ts_slow<MODE>(S, ln, sk);
+            // refill finished lanes from the record queue
+            unsigned m_init = __ballot_sync(0xffffffffu, ln.ev == EV_INIT);
+            if (m_init && cc.more) {
+                unsigned long long pos = take_positions(cc, work, n_total, m_init);
+                if (pos != ~0ull) ts_load(ln, Q, pos);
+            }
         }
         __syncwarp();
     }
@@ -337,30 +351,36 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_vps_wavefront(const 
     sk.cnt.coll = sk.cnt.scat = sk.cnt.g_sig = sk.cnt.g_alb = 0; sk.n_paths = 0;
     ChunkCursor cc; cc.next = 0; cc.end = 0; cc.more = true;
     while (true) {
-        // resume lanes that finished pass 1 as pass 2; refill the finished ones
-        const bool is_init = ln.ev == EV_INIT;
-        const bool resume = BACKWARD && is_init && (ln.flags & VF_PASS2);
-        if (resume) vp_load(ln, sk, Q, ln.qpos, true);
-        unsigned m_new = __ballot_sync(0xffffffffu, is_init && !resume);
-        if (m_new && cc.more) {
-            unsigned long long pos = take_positions(cc, work, n_total, m_new);
-            if (pos != ~0ull) vp_load(ln, sk, Q, pos, false);
-        }
-        unsigned m_coll = __ballot_sync(0xffffffffu, ln.ev == EV_COLL);
-        unsigned m_scat = __ballot_sync(0xffffffffu, ln.ev == EV_SCAT);
-        if (m_coll == 0 && m_scat == 0) break;
+        const int n_coll = __popc(__ballot_sync(0xffffffffu, ln.ev == EV_COLL));
+        const int n_scat = __popc(__ballot_sync(0xffffffffu, ln.ev == EV_SCAT));
+        // lanes waiting for the slow step: parked work, lanes to resume as pass 2, empty lanes while records remain
+        const int n_slow = __popc(__ballot_sync(
+            0xffffffffu, ln.ev == EV_SLOW || (ln.ev == EV_INIT && ((BACKWARD && (ln.flags & VF_PASS2)) || cc.more))));
+        if (n_coll == 0 && n_scat == 0 && n_slow == 0) break;
+        const int sel = pick_event(n_coll, n_scat, n_slow);
         VpReq rq;
         vp_req_clear(rq);
         rq.p = mk3(0, 0, 0); rq.gal = mk3(0, 0, 0); rq.sg = 0.f; rq.interval = 0.f; rq.sg_seg = 0.f;
         rq.u[0] = rq.u[1] = rq.u[2] = rq.u[3] = 0.f;
-        if (__popc(m_scat) >= kScatBatch || m_coll == 0) {
+        if (sel == EV_COLL) {
+            if (ln.ev == EV_COLL) vp_collide<BACKWARD>(S, G, mu, inv_mu, ln, sk, rq);
+            if (BACKWARD) vp_req_flush_coop(S, G, D, ln, rq, sk.cnt);
+        } else if (sel == EV_SCAT) {
             const bool mine = ln.ev == EV_SCAT;
             if (mine) vp_vertex_a<BACKWARD>(S, G, ln, sk, rq);
             if (BACKWARD) vp_req_flush_coop(S, G, D, ln, rq, sk.cnt);
             if (mine) vp_vertex_b<BACKWARD>(S, ln, sk);
         } else {
-            if (ln.ev == EV_COLL) vp_collide<BACKWARD>(S, G, mu, inv_mu, ln, sk, rq);
-            if (BACKWARD) vp_req_flush_coop(S, G, D, ln, rq, sk.cnt);
+            if (ln.ev == EV_SLOW) vp_slow<BACKWARD>(S, ln, sk);
+            // resume lanes that finished pass 1 as pass 2; refill the finished ones
+            const bool is_init = ln.ev == EV_INIT;
+            const bool resume = BACKWARD && is_init && (ln.flags & VF_PASS2);
+            if (resume) vp_load(ln, sk, Q, ln.qpos, true);
+            unsigned m_new = __ballot_sync(0xffffffffu, is_init && !resume);
+            if (m_new && cc.more) {
+                unsigned long long pos = take_positions(cc, work, n_total, m_new);
+                if (pos != ~0ull) vp_load(ln, sk, Q, pos, false);
+            }
         }
         __syncwarp();
     }

@@ -176,7 +176,7 @@ __device__ __forceinline__ void trace_twostates(const SceneK &S, const GridK &G,
                     if (scattered && S.sample_emitters) {
                         float tr_old, tr_new; V3 dir;
                         nee_twostates<MODE>(S, G, mu, inv_mu, rng, m.p, tr_old, tr_new, dir, n_coll);
-                        V3 emitter_val = mk3(env.x / RCV_INV_FOURPI, env.y / RCV_INV_FOURPI, env.z / RCV_INV_FOURPI);
+                        V3 emitter_val = mk3(S.env_over_pdf[0], S.env_over_pdf[1], S.env_over_pdf[2]);
                         float phase_val = phase_eval(S, wi, dir);     // :333-334
                         float mis_em = mis_weight(RCV_INV_FOURPI, phase_val);   // :341
                         L_new = L_new + ((thr_new * phase_val) * mis_em) * (emitter_val * splat3(tr_new));   // :343

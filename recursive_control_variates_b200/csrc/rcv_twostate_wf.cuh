@@ -15,6 +15,10 @@
 //              flight, one two-state sigma_t gather, null/real/escape decision
 //   EV_SCAT    a real scattering vertex: two-state albedo gather, throughput
 //              weights, phase sampling, emitter direction sample (:259-344)
+//   EV_SLOW    everything that happens once per path or per shadow ray and
+//              would otherwise run with one or two lanes: end of the shadow
+//              ray (:336-344, :360-361), boundary crossing + environment hit
+//              of an escaping path (:346-379, :288-308), the film splat
 //
 // The handlers contain no warp intrinsics; they also compile for the host
 // (RCV_HOST_EMU) where tests single-step them against the oracle.
@@ -23,8 +27,14 @@
 
 namespace rcv {
 
-enum : int { EV_INIT = 0, EV_COLL = 1, EV_SCAT = 2 };
-enum : uint32_t { F_NEEDS_ISECT = 1u, F_SPECULAR = 2u, F_IN_NEE = 4u, F_SI_VALID = 8u };
+enum : int { EV_INIT = 0, EV_COLL = 1, EV_SCAT = 2, EV_SLOW = 3 };
+enum : uint32_t {
+    F_NEEDS_ISECT = 1u, F_SPECULAR = 2u, F_IN_NEE = 4u, F_SI_VALID = 8u,
+    // work parked for the batched EV_SLOW step
+    F_POST_NEE = 16u,      // the shadow ray ended: add its contribution, resume the main path
+    F_FIN = 32u,           // the path ended: splat it
+    F_FIN_ESCAPE = 64u     // ... after leaving the medium through the boundary (:346-379, :288-308)
+};
 
 struct TsLane {
     int ev;
@@ -139,7 +149,7 @@ __device__ __forceinline__ void ts_load(TsLane &ln, const PathQueue &Q, unsigned
 // then the phase ratio of the old state (:360-361); the main path resumes
 __device__ __forceinline__ void ts_nee_finish(const SceneK &S, TsLane &ln) {
     const V3 env = mk3(S.env[0], S.env[1], S.env[2]);
-    V3 emitter_val = mk3(env.x / RCV_INV_FOURPI, env.y / RCV_INV_FOURPI, env.z / RCV_INV_FOURPI);
+    V3 emitter_val = mk3(S.env_over_pdf[0], S.env_over_pdf[1], S.env_over_pdf[2]);
     float mis_em = mis_weight(RCV_INV_FOURPI, ln.phase_val);
     ln.L_new = ln.L_new + ((ln.thr_new * ln.phase_val) * mis_em) * (emitter_val * splat3(ln.tr_new));
     ln.L_old = ln.L_old + ((ln.thr_old * ln.phase_val) * mis_em) * (emitter_val * splat3(ln.tr_old));
@@ -148,16 +158,37 @@ __device__ __forceinline__ void ts_nee_finish(const SceneK &S, TsLane &ln) {
     ln.id = rcp3(ln.d);
 }
 
+// the batched slow step (see the header comment)
+template <int MODE>
+__device__ __forceinline__ void ts_slow(const SceneK &S, TsLane &ln, TsSink &sk) {
+    if (ln.flags & F_POST_NEE) {
+        ln.flags &= ~F_POST_NEE;
+        ts_nee_finish(S, ln);
+        ln.ev = EV_COLL;
+        return;
+    }
+    if (ln.flags & F_FIN_ESCAPE) {
+        if (!(ln.flags & F_SI_VALID)) {
+            ts_env_hit(S, ln);
+        } else {
+            // null-BSDF boundary crossing (:346-379), then one more loop head and the environment
+            (void) pcg_f32(ln.rng); (void) pcg_f32(ln.rng); (void) pcg_f32(ln.rng);
+            if (ts_loop_head(S, ln)) ts_env_hit(S, ln);
+        }
+    }
+    ts_finish<MODE>(ln, sk);
+}
+
 template <int MODE>
 __device__ __forceinline__ void ts_collide(const SceneK &S, const GridK &G, float mu, float inv_mu, TsLane &ln, TsSink &sk) {
     const bool nee = (ln.flags & F_IN_NEE) != 0;
     V3 so, sd; float maxt;
     if (!nee) {
-        if (!ts_loop_head(S, ln)) { ts_finish<MODE>(ln, sk); return; }
+        if (!ts_loop_head(S, ln)) { ln.flags |= F_FIN; ln.ev = EV_SLOW; return; }
         so = ln.o; sd = ln.d; maxt = RCV_LARGEST;
     } else {
         float remaining = S.env_dist * (1.f - RCV_SHADOW_EPS) - ln.total;   // :409
-        if (!(remaining > 0.f)) { ts_nee_finish(S, ln); return; }           // :411
+        if (!(remaining > 0.f)) { ln.flags |= F_POST_NEE; ln.ev = EV_SLOW; return; }   // :411
         so = ln.no; sd = ln.nd; maxt = remaining;
     }
     float u = pcg_f32(ln.rng);                                        // :194 / :422
@@ -176,7 +207,7 @@ __device__ __forceinline__ void ts_collide(const SceneK &S, const GridK &G, floa
             float sn_o = mu - m.so, sn_n = mu - m.sn;
             ln.tr_old = ln.tr_old * ((mu != 0.f) ? (sn_o * inv_mu) : sn_o);
             ln.tr_new = ln.tr_new * ((mu != 0.f) ? (sn_n * inv_mu) : sn_n);
-            if (!(ln.tr_new != 0.f || ln.tr_old != 0.f)) { ts_nee_finish(S, ln); return; }
+            if (!(ln.tr_new != 0.f || ln.tr_old != 0.f)) { ln.flags |= F_POST_NEE; ln.ev = EV_SLOW; return; }
             ln.total += m.t;
             return;
         }
@@ -193,19 +224,16 @@ __device__ __forceinline__ void ts_collide(const SceneK &S, const GridK &G, floa
             return;
         }
         ln.depth += 1;                                                // :249
-        if (!(ln.depth < S.max_depth)) { ts_finish<MODE>(ln, sk); return; }   // :253
+        if (!(ln.depth < S.max_depth)) { ln.flags |= F_FIN; ln.ev = EV_SLOW; return; }   // :253
         ln.o = m.p;                                                   // the vertex; the new direction is chosen in EV_SCAT
         ln.tr_old = m.so; ln.tr_new = m.sn;
         ln.ev = EV_SCAT;
         return;
     }
     // the segment left the medium
-    if (nee) { ts_nee_finish(S, ln); return; }                        // nothing attenuates the shadow ray outside the box
-    if (!(ln.flags & F_SI_VALID)) { ts_env_hit(S, ln); ts_finish<MODE>(ln, sk); return; }
-    // null-BSDF boundary crossing (:346-379), then one more loop head and the environment
-    (void) pcg_f32(ln.rng); (void) pcg_f32(ln.rng); (void) pcg_f32(ln.rng);
-    if (ts_loop_head(S, ln)) ts_env_hit(S, ln);
-    ts_finish<MODE>(ln, sk);
+    if (nee) { ln.flags |= F_POST_NEE; ln.ev = EV_SLOW; return; }     // nothing attenuates the shadow ray outside the box
+    ln.flags |= F_FIN | F_FIN_ESCAPE;
+    ln.ev = EV_SLOW;
 }
 
 template <int MODE>

@@ -198,7 +198,7 @@ __device__ __forceinline__ void vps_trace(const SceneK &S, const GridK &G, const
             Pcg nee_rng = rng;                                        // :396 sampler.clone()
             V3 dir;
             float tr = vps_sample_emitter<false>(S, G, D, mu, inv_mu, rng, mei_p, mk3(0, 0, 0), dir, cnt);
-            V3 emitted = mk3(env.x / RCV_INV_FOURPI, env.y / RCV_INV_FOURPI, env.z / RCV_INV_FOURPI) * splat3(tr);
+            V3 emitted = mk3(S.env_over_pdf[0], S.env_over_pdf[1], S.env_over_pdf[2]) * splat3(tr);
             float phase_val = phase_eval(S, wi, dir);                 // :401
             V3 nee = ((thr * phase_val) * mis_weight(RCV_INV_FOURPI, phase_val)) * emitted;   // :404
             if (ADJ) {

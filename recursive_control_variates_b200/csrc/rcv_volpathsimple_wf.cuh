@@ -19,6 +19,10 @@
 //                           (:165-185) and transmittance (:194-202, :597-620)
 //                           gradient requests
 //              vp_vertex_b  NEE set-up (:393-446) or phase sampling (:234-258)
+//   EV_SLOW    once-per-shadow-ray / once-per-pass work that would otherwise run
+//              with one or two lanes: end of the shadow ray, start of its
+//              adjoint replay, phase sampling after it, end of a pass; the
+//              scheduler also reloads / refills lanes in this step
 //
 // Gradient scatters are not executed by the handlers: they are returned as a
 // VpReq and flushed between the two vertex halves — cooperatively by the whole
@@ -40,7 +44,10 @@ enum : uint32_t {
     VF_HEAD = 32u,        // next main-path collision starts with the loop head (:129-134)
     VF_DID_SCATTER = 64u,
     VF_PASS2 = 128u,      // pass 1 finished, the lane must reload its record as pass 2
-    VF_ACTIVE = 256u      // `active` after :213, carried from vertex_a to vertex_b
+    VF_ACTIVE = 256u,     // `active` after :213, carried from vertex_a to vertex_b
+    // work parked for the batched EV_SLOW step
+    VF_POSTNEE = 512u,    // the shadow ray (or its replay) ended
+    VF_END = 1024u        // the pass ended at a loop head (:132-133)
 };
 
 struct VpLane {
@@ -241,7 +248,7 @@ __device__ __forceinline__ void vp_nee_done(const SceneK &S, VpLane &ln, VpSink 
         if (!(ln.flags & VF_REPLAY)) {
             const V3 env = mk3(S.env[0], S.env[1], S.env[2]);
             V3 wi = mk3(-ln.d.x, -ln.d.y, -ln.d.z);
-            V3 emitted = mk3(env.x / RCV_INV_FOURPI, env.y / RCV_INV_FOURPI, env.z / RCV_INV_FOURPI) * splat3(ln.tr_acc);
+            V3 emitted = mk3(S.env_over_pdf[0], S.env_over_pdf[1], S.env_over_pdf[2]) * splat3(ln.tr_acc);
             float phase_val = phase_eval(S, wi, ln.nd);               // :401
             ln.nee = ((ln.thr * phase_val) * mis_weight(RCV_INV_FOURPI, phase_val)) * emitted;   // :404
             if (BW && (ln.flags & VF_ADJ)) {
@@ -277,7 +284,7 @@ __device__ __forceinline__ void vp_collide(const SceneK &S, const GridK &G, floa
         float ce = m.valid ? mu : 0.f;
         float tr = (ce != 0.f) ? (sn * inv_mu) : sn;                  // :486-489
         if (m.t > ln.rmaxt) m.t = inf_();                             // :493
-        if (!(m.t < inf_())) { vp_nee_done<BW>(S, ln, sk); return; }  // :494
+        if (!(m.t < inf_())) { ln.flags |= VF_POSTNEE; ln.ev = EV_SLOW; return; }  // :494
         if (BW && (ln.flags & VF_REPLAY)) {                           // :496-505
             V3 adjoint = ln.dL * ln.nee;                              // :412
             float g = 0.f;
@@ -290,14 +297,14 @@ __device__ __forceinline__ void vp_collide(const SceneK &S, const GridK &G, floa
         ln.tr_acc = ln.tr_acc * tr;                                   // :508
         ln.ro = m.p;                                                  // :510
         ln.rmaxt = ln.rmaxt - m.t;
-        if (!(ln.tr_acc != 0.f)) vp_nee_done<BW>(S, ln, sk);          // :515
+        if (!(ln.tr_acc != 0.f)) { ln.flags |= VF_POSTNEE; ln.ev = EV_SLOW; }   // :515
         return;
     }
     if (ln.flags & VF_HEAD) {                                         // loop head (:129-134)
         float q = fmin_(max3(ln.thr), 0.99f);
         bool perform_rr = ln.depth > S.rr_depth;
         float rr = pcg_f32(ln.rng);
-        if (!(any_nz(ln.thr) && (!perform_rr || (rr < q)))) { vp_end_pass<BW>(S, ln, sk); return; }
+        if (!(any_nz(ln.thr) && (!perform_rr || (rr < q)))) { ln.flags |= VF_END; ln.ev = EV_SLOW; return; }
         if (perform_rr) ln.thr = ln.thr * (1.f / q);
         ln.ro = ln.o; ln.rmaxt = ln.ray_maxt; ln.running_t = 0.f;     // :349-351
         ln.flags &= ~VF_HEAD;
@@ -313,6 +320,19 @@ __device__ __forceinline__ void vp_collide(const SceneK &S, const GridK &G, floa
     ln.ro = ln.ro + ln.d * m.t;                                       // :378-380
     ln.rmaxt = ln.rmaxt - m.t;
     ln.running_t = ln.running_t + m.t;
+}
+
+// the batched slow step (see the header comment)
+template <bool BW>
+__device__ __forceinline__ void vp_slow(const SceneK &S, VpLane &ln, VpSink &sk) {
+    if (ln.flags & VF_POSTNEE) {
+        ln.flags &= ~VF_POSTNEE;
+        ln.ev = EV_COLL;
+        vp_nee_done<BW>(S, ln, sk);
+    } else {
+        ln.flags &= ~VF_END;
+        vp_end_pass<BW>(S, ln, sk);
+    }
 }
 
 // first half of a vertex: gathers, gradient requests, throughput/depth update

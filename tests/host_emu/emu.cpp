@@ -66,7 +66,8 @@ void run_twostates(const SceneK &S, const GridK &G, uint32_t seed, uint32_t spp,
         ts_load(ln, hq.Q, pos);
         while (ln.ev != EV_INIT) {
             if (ln.ev == EV_COLL) ts_collide<MODE>(S, G, mu, inv_mu, ln, sk);
-            else ts_scatter<MODE>(S, G, ln, sk);
+            else if (ln.ev == EV_SCAT) ts_scatter<MODE>(S, G, ln, sk);
+            else ts_slow<MODE>(S, ln, sk);
         }
     }
     cnt[0] += sk.n_coll; cnt[1] += sk.n_scat; cnt[6] += sk.n_paths;
@@ -96,10 +97,12 @@ void run_vps(const SceneK &S, const GridK &G, VpSink &sk) {
             if (ln.ev == EV_COLL) {
                 vp_collide<BW>(S, G, mu, inv_mu, ln, sk, rq);
                 if (BW) vp_req_flush_serial(S, G, sk.D, ln, rq, sk.cnt);
-            } else {
+            } else if (ln.ev == EV_SCAT) {
                 vp_vertex_a<BW>(S, G, ln, sk, rq);
                 if (BW) vp_req_flush_serial(S, G, sk.D, ln, rq, sk.cnt);
                 vp_vertex_b<BW>(S, ln, sk);
+            } else {
+                vp_slow<BW>(S, ln, sk);
             }
         }
     }
