@@ -141,13 +141,13 @@ __global__ void __launch_bounds__(kBlock) k_vps_simple(const __grid_constant__ S
 // WAVEFRONT schedule
 // ===========================================================================
 #ifndef RCV_WF_BLOCK
-#define RCV_WF_BLOCK 256
+#define RCV_WF_BLOCK 128
 #endif
 #ifndef RCV_WF_MINBLOCKS
-#define RCV_WF_MINBLOCKS 2
+#define RCV_WF_MINBLOCKS 5
 #endif
 #ifndef RCV_EVENT_BATCH
-#define RCV_EVENT_BATCH 8
+#define RCV_EVENT_BATCH 12
 #endif
 static constexpr int kWfBlock = RCV_WF_BLOCK;
 static constexpr int kWfMinBlocks = RCV_WF_MINBLOCKS;

@@ -275,11 +275,25 @@ __device__ __forceinline__ void vp_nee_done(const SceneK &S, VpLane &ln, VpSink 
 template <bool BW>
 __device__ __forceinline__ void vp_collide(const SceneK &S, const GridK &G, float mu, float inv_mu, VpLane &ln, VpSink &sk,
                                            VpReq &rq) {
-    if (ln.flags & VF_IN_NEE) {
+    const bool nee = (ln.flags & VF_IN_NEE) != 0;
+    if (!nee && (ln.flags & VF_HEAD)) {                               // loop head (:129-134)
+        float q = fmin_(max3(ln.thr), 0.99f);
+        bool perform_rr = ln.depth > S.rr_depth;
+        float rr = pcg_f32(ln.rng);
+        if (!(any_nz(ln.thr) && (!perform_rr || (rr < q)))) { ln.flags |= VF_END; ln.ev = EV_SLOW; return; }
+        if (perform_rr) ln.thr = ln.thr * (1.f / q);
+        ln.ro = ln.o; ln.rmaxt = ln.ray_maxt; ln.running_t = 0.f;     // :349-351
+        ln.flags &= ~VF_HEAD;
+    }
+    // one free-flight sample + sigma_t gather on the current segment, shared by
+    // delta tracking (:361) and ratio tracking (:482) so that all lanes of the
+    // warp execute the gather together
+    const V3 sd = nee ? ln.nd : ln.d;
+    float u = pcg_f32(ln.rng);
+    Mei1 m;
+    sample_interaction1(S, G, inv_mu, ln.ro, sd, ln.id, ln.rmaxt, u, m, sk.cnt);
+    if (nee) {
         // estimate_transmittance step (:478-515)
-        float u = pcg_f32(ln.rng);
-        Mei1 m;
-        sample_interaction1(S, G, inv_mu, ln.ro, ln.nd, ln.id, ln.rmaxt, u, m, sk.cnt);   // :482
         float sn = m.valid ? (mu - m.st) : 0.f;
         float ce = m.valid ? mu : 0.f;
         float tr = (ce != 0.f) ? (sn * inv_mu) : sn;                  // :486-489
@@ -300,18 +314,7 @@ __device__ __forceinline__ void vp_collide(const SceneK &S, const GridK &G, floa
         if (!(ln.tr_acc != 0.f)) { ln.flags |= VF_POSTNEE; ln.ev = EV_SLOW; }   // :515
         return;
     }
-    if (ln.flags & VF_HEAD) {                                         // loop head (:129-134)
-        float q = fmin_(max3(ln.thr), 0.99f);
-        bool perform_rr = ln.depth > S.rr_depth;
-        float rr = pcg_f32(ln.rng);
-        if (!(any_nz(ln.thr) && (!perform_rr || (rr < q)))) { ln.flags |= VF_END; ln.ev = EV_SLOW; return; }
-        if (perform_rr) ln.thr = ln.thr * (1.f / q);
-        ln.ro = ln.o; ln.rmaxt = ln.ray_maxt; ln.running_t = 0.f;     // :349-351
-        ln.flags &= ~VF_HEAD;
-    }
-    float u = pcg_f32(ln.rng);                                        // :361
-    Mei1 m;
-    sample_interaction1(S, G, inv_mu, ln.ro, ln.d, ln.id, ln.rmaxt, u, m, sk.cnt);
+    // sample_real_interaction step (:360-380)
     ln.mei_t = m.t + ln.running_t;                                    // :364
     if (!m.valid) { ln.flags &= ~VF_DID_SCATTER; ln.ev = EV_SCAT; return; }   // :371 escape
     float r = (mu != 0.f) ? (m.st * inv_mu) : 0.f;                    // :367
