@@ -1,0 +1,390 @@
+"""Minimal stand-in for the parts of the Mitsuba 3 Python API that the reference's
+hot path is driven through (`mi.load_dict`, `mi.traverse`, `mi.render`,
+`mi.register_integrator`, `mi.ad.Adam`), so that the plugin classes of
+`plugins/` keep the reference's names, constructor properties and call shapes
+ without a Mitsuba install.
+
+Only the scene class of the volumetric experiments is understood
+(experiments.py:20-133): a perspective sensor with an hdrfilm (box filter), one
+box shape with a `null` BSDF whose interior is a `heterogeneous` grid medium
+(optionally wrapped in a `twostatemedium`), and a `constant` emitter.
+
+Tensors are torch CUDA tensors; differentiation goes through torch autograd:
+`render()` returns an image whose backward calls the integrator's
+`render_backward`, exactly like Mitsuba's `_RenderOp`.
+"""
+from __future__ import annotations
+
+from typing import Any, Callable, Dict, Optional
+
+import numpy as np
+import torch
+
+from .runtime import Context, tea32
+from .scene import SceneConfig, look_at
+
+_INTEGRATORS: Dict[str, Callable] = {}
+_MEDIA: Dict[str, Callable] = {}
+
+
+def register_integrator(name: str, ctor: Callable) -> None:
+    """mi.register_integrator (plugins/__init__.py:11-15)."""
+    _INTEGRATORS[name] = ctor
+
+
+def register_medium(name: str, ctor: Callable) -> None:
+    """mi.register_medium (plugins/__init__.py:17)."""
+    _MEDIA[name] = ctor
+
+
+class Properties(dict):
+    """mi.Properties: `props.get(name, default)` / `props[name]`."""
+
+    def get(self, key, default=None):  # noqa: A003 - mirrors Mitsuba
+        return super().get(key, default)
+
+
+def _as_tensor(data, channels: int) -> torch.Tensor:
+    t = data if isinstance(data, torch.Tensor) else torch.as_tensor(np.asarray(data, dtype=np.float32))
+    t = t.detach().to(dtype=torch.float32)
+    assert t.dim() == 4 and t.shape[-1] == channels, f"expected a (Z,Y,X,{channels}) grid, got {tuple(t.shape)}"
+    return t.contiguous()
+
+
+class GridVolume:
+    """`gridvolume` with an in-memory tensor (Z, Y, X, C) (experiments.py:104-112)."""
+
+    def __init__(self, props: Properties, channels: int):
+        if "data" in props:
+            self.data = _as_tensor(props["data"], channels)
+        elif "value" in props:
+            res = props.get("resolution", (16, 16, 16))
+            self.data = torch.full((*res, channels), float(props["value"]), dtype=torch.float32)
+        else:
+            raise ValueError("gridvolume needs `data` (tensor) or `value`: volume files are not supported")
+
+
+class HeterogeneousMedium:
+    """`heterogeneous` medium (experiments.py:52-71): sigma_t = scale * grid, albedo grid, phase."""
+
+    def __init__(self, props: Properties):
+        self.sigma_t = GridVolume(Properties(props["sigma_t"]), 1)
+        self.albedo = GridVolume(Properties(props["albedo"]), 3)
+        self.scale = float(props.get("scale", 1.0))
+        self.sample_emitters = bool(props.get("sample_emitters", True))
+        phase = props.get("phase", {"type": "isotropic"})
+        self.phase = phase.get("type", "isotropic")
+        self.phase_g = float(phase.get("g", 0.0))
+        if props.get("has_spectral_extinction", False):
+            raise ValueError("spectrally varying extinction is not supported (utils.py:66)")
+        if props.get("majorant_resolution_factor", 0):
+            raise ValueError("majorant supergrids are not supported yet (SURVEY.md §8f)")
+
+    def is_twostate(self) -> bool:
+        return False
+
+    def parameters(self) -> Dict[str, torch.Tensor]:
+        return {"sigma_t.data": self.sigma_t.data, "albedo.data": self.albedo.data}
+
+    def set_parameter(self, key: str, value: torch.Tensor):
+        vol = self.sigma_t if key.startswith("sigma_t") else self.albedo
+        vol.data = _as_tensor(value, vol.data.shape[-1])
+
+    # what the renderer reads after a parameter update
+    def incoming_medium(self) -> "HeterogeneousMedium":
+        return self
+
+    def parameters_changed(self, keys=None):
+        pass
+
+
+def _make_medium(d: dict):
+    kind = d.get("type")
+    if kind == "heterogeneous":
+        return HeterogeneousMedium(Properties(d))
+    if kind in _MEDIA:
+        props = Properties({k: (_make_medium(v) if isinstance(v, dict) and "type" in v else v) for k, v in d.items()})
+        return _MEDIA[kind](props)
+    raise ValueError(f"unsupported medium type {kind!r}")
+
+
+class Film:
+    def __init__(self, width: int, height: int):
+        self.width, self.height = int(width), int(height)
+
+    def size(self):
+        return (self.width, self.height)
+
+
+class Sensor:
+    def __init__(self, d: dict):
+        if d.get("type") != "perspective":
+            raise ValueError("only `perspective` sensors are supported (batch sensors: SURVEY.md §8f)")
+        film = d.get("film", {})
+        if film.get("rfilter", {"type": "box"}).get("type", "box") != "box":
+            raise ValueError("only the box reconstruction filter is supported (SURVEY.md §8f)")
+        self._film = Film(film.get("width", 768), film.get("height", 576))
+        self.fov = float(d.get("fov", 45.0))
+        self.to_world = np.asarray(d.get("to_world", look_at([0.5, 0.5, -2.0], [0.5, 0.5, 0.5], [0, 1, 0])), dtype=np.float64)
+        self.near_clip = float(d.get("near_clip", 1e-2))
+
+    def film(self) -> Film:
+        return self._film
+
+
+class Shape:
+    def __init__(self, d: dict):
+        if d.get("type") not in ("cube", "obj", "box"):
+            raise ValueError("the medium container must be a box (`cube`)")
+        if d.get("bsdf", {"type": "null"}).get("type") != "null":
+            raise ValueError("the medium boundary must use a `null` BSDF (volpathsimple.py:24-30)")
+        self.bbox_min = tuple(float(v) for v in d.get("bbox_min", (0.0, 0.0, 0.0)))
+        self.bbox_max = tuple(float(v) for v in d.get("bbox_max", (1.0, 1.0, 1.0)))
+        self._interior = _make_medium(d["interior"]) if "interior" in d else None
+
+    def interior_medium(self):
+        return self._interior
+
+    def exterior_medium(self):
+        return None
+
+
+class Scene:
+    """The result of `load_dict({'type': 'scene', ...})`."""
+
+    def __init__(self, d: dict):
+        self._shapes, self._sensors, self.env_radiance = [], [], None
+        self.shape_key = None
+        for key, v in d.items():
+            if not isinstance(v, dict):
+                continue
+            t = v.get("type")
+            if t in ("cube", "obj", "box"):
+                self._shapes.append(Shape(v)); self.shape_key = key
+            elif t == "perspective":
+                self._sensors.append(Sensor(v))
+            elif t == "constant":
+                rad = v.get("radiance", 1.0)
+                if isinstance(rad, dict):
+                    rad = rad.get("value", 1.0)
+                self.env_radiance = tuple(float(x) for x in (rad if np.ndim(rad) else (rad, rad, rad)))
+            elif t in ("envmap", "area"):
+                raise ValueError(f"emitter `{t}` is not supported yet (SURVEY.md §8f); use `constant`")
+        if len(self._shapes) != 1 or self._shapes[0].interior_medium() is None:
+            raise ValueError("expected a single shape with an interior medium (volpathsimple.py:16-19)")
+        if len(self._sensors) != 1:
+            raise ValueError("only scenes with a single sensor are supported (optimize.py:36)")
+        if self.env_radiance is None:
+            raise ValueError("the scene needs a `constant` emitter")
+        self._ctx: Optional[Context] = None
+        self._ctx_key = None
+        self._medium_dirty = True
+
+    def shapes(self):
+        return self._shapes
+
+    def sensors(self):
+        return self._sensors
+
+    def medium(self):
+        return self._shapes[0].interior_medium()
+
+    # ---- device state -------------------------------------------------------
+    def scene_config(self, max_depth: int, rr_depth: int, hide_emitters: bool = False, use_nee: bool = True) -> SceneConfig:
+        s, sh, m = self._sensors[0], self._shapes[0], self.medium().incoming_medium()
+        return SceneConfig(width=s.film().width, height=s.film().height, fov=s.fov, to_world=s.to_world, near_clip=s.near_clip,
+                           bbox_min=sh.bbox_min, bbox_max=sh.bbox_max, sigma_t_scale=m.scale, phase=m.phase, phase_g=m.phase_g,
+                           sample_emitters=m.sample_emitters, env_radiance=self.env_radiance, max_depth=max_depth,
+                           rr_depth=rr_depth, hide_emitters=hide_emitters, use_nee=use_nee)
+
+    def context(self, max_depth: int, rr_depth: int, hide_emitters: bool = False, use_nee: bool = True) -> Context:
+        """The rcv_ctx of this scene, configured for the calling integrator."""
+        if self._ctx is None:
+            self._ctx = Context()
+        s = self._sensors[0]
+        key = (max_depth, rr_depth, hide_emitters, use_nee, s.film().width, s.film().height)
+        if key != self._ctx_key:
+            self._ctx.set_scene(self.scene_config(max_depth, rr_depth, hide_emitters, use_nee))
+            self._ctx_key = key
+        if self._medium_dirty:
+            self.push_medium()
+        return self._ctx
+
+    def push_medium(self):
+        """Upload the incoming parameters as the new state: TwoStateMedium.parameters_changed
+        (old <- new, new <- incoming) is one rcv_medium_rotate."""
+        if self._ctx is None or self._ctx_key is None:
+            self._medium_dirty = True
+            return
+        m = self.medium().incoming_medium()
+        dev = self._ctx.torch_device
+        m.sigma_t.data = m.sigma_t.data.to(dev)
+        m.albedo.data = m.albedo.data.to(dev)
+        self._ctx.rotate(m.sigma_t.data, m.albedo.data)
+        self._medium_dirty = False
+
+
+def load_dict(d: dict):
+    """mi.load_dict for the supported plugin types."""
+    t = d.get("type")
+    if t == "scene":
+        return Scene(d)
+    if t in _INTEGRATORS:
+        props = Properties({k: (load_dict(v) if isinstance(v, dict) and v.get("type") in _INTEGRATORS else v) for k, v in d.items()})
+        return _INTEGRATORS[t](props)
+    if t in ("heterogeneous",) or t in _MEDIA:
+        return _make_medium(d)
+    raise ValueError(f"load_dict: unsupported plugin type {t!r}")
+
+
+class SceneParameters(dict):
+    """mi.traverse(scene): differentiable parameters by key, e.g.
+    'object.interior_medium.sigma_t.data' (experiments.py:104-112)."""
+
+    def __init__(self, scene: Scene):
+        super().__init__()
+        self.scene = scene
+        self.prefix = f"{scene.shape_key}.interior_medium."
+        for k, v in scene.medium().incoming_medium().parameters().items():
+            super().__setitem__(self.prefix + k, v)
+        self._dirty = set()
+
+    def __setitem__(self, key, value):
+        if key not in self:
+            raise KeyError(key)
+        super().__setitem__(key, value)
+        self._dirty.add(key)
+
+    def update(self, values: Optional[dict] = None):
+        """SceneParameters.update: assign, then notify the medium (plugins/twostatemedium.py:189-200)."""
+        if values is not None:
+            for k, v in values.items():
+                if k in self:
+                    self[k] = v
+        med = self.scene.medium()
+        inc = med.incoming_medium()
+        for k in sorted(self._dirty):
+            inc.set_parameter(k[len(self.prefix):], self[k])
+        keys, self._dirty = list(self._dirty), set()
+        med.parameters_changed(keys)
+        self.scene.push_medium()
+        return keys
+
+
+def traverse(obj) -> SceneParameters:
+    if isinstance(obj, Scene):
+        return SceneParameters(obj)
+    raise TypeError("traverse() expects a Scene")
+
+
+# ----------------------------------------------------------------------------
+# mi.render with the _RenderOp AD boundary
+# ----------------------------------------------------------------------------
+class _RenderOp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, scene, integrator, params, keys, sensor, seed, spp, seed_grad, spp_grad, *tensors):
+        ctx.args = (scene, integrator, params, keys, sensor, seed_grad, spp_grad)
+        with torch.no_grad():
+            return integrator.render(scene, sensor, seed, spp)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        scene, integrator, params, keys, sensor, seed_grad, spp_grad = ctx.args
+        grads = integrator.render_backward(scene, params, grad_out.contiguous(), sensor, seed_grad, spp_grad)
+        out = [None] * 9
+        for k in keys:
+            out.append(grads.get(k) if grads else None)
+        return tuple(out)
+
+
+def render(scene: Scene, params: Optional[SceneParameters] = None, sensor: int = 0, integrator=None, seed: int = 0,
+           seed_grad: int = 0, spp: int = 0, spp_grad: int = 0) -> torch.Tensor:
+    """mi.render: primal image now, adjoint on `.backward()` (optimize.py:108,122).
+    seed_grad defaults to sample_tea_32(seed, 1)[0], spp_grad to spp."""
+    assert integrator is not None, "pass integrator=..."
+    if spp_grad == 0:
+        spp_grad = spp
+    if seed_grad == 0:
+        seed_grad = tea32(seed, 1)[0]
+    keys, tensors = [], []
+    if params is not None:
+        for k, v in params.items():
+            if isinstance(v, torch.Tensor) and v.requires_grad:
+                keys.append(k); tensors.append(v)
+    if not tensors:
+        with torch.no_grad():
+            return integrator.render(scene, sensor, seed, spp)
+    return _RenderOp.apply(scene, integrator, params, keys, sensor, seed, spp, seed_grad, spp_grad, *tensors)
+
+
+# ----------------------------------------------------------------------------
+# mi.ad.Adam
+# ----------------------------------------------------------------------------
+class Adam:
+    """mi.ad.Adam (optimize.py:90,127): dict of variables, per-key learning rates,
+    state reset when a variable changes shape (after utils.upsample)."""
+
+    def __init__(self, lr: float, beta_1: float = 0.9, beta_2: float = 0.999, epsilon: float = 1e-8):
+        self.lr_default, self.beta_1, self.beta_2, self.epsilon = float(lr), beta_1, beta_2, epsilon
+        self.lr: Dict[str, float] = {}
+        self.variables: Dict[str, torch.Tensor] = {}
+        self.state: Dict[str, Any] = {}
+        self.t: Dict[str, int] = {}
+
+    def __contains__(self, key):
+        return key in self.variables
+
+    def __getitem__(self, key) -> torch.Tensor:
+        return self.variables[key]
+
+    def __setitem__(self, key, value: torch.Tensor):
+        v = value.detach().clone().contiguous().float()
+        if torch.cuda.is_available():
+            v = v.cuda()
+        v.requires_grad_(True)
+        if key not in self.variables or self.variables[key].shape != v.shape:
+            self.reset(key, v)
+        self.variables[key] = v
+
+    def keys(self):
+        return self.variables.keys()
+
+    def items(self):
+        return self.variables.items()
+
+    def reset(self, key, like=None):
+        like = self.variables[key] if like is None else like
+        self.state[key] = (torch.zeros_like(like, requires_grad=False), torch.zeros_like(like, requires_grad=False))
+        self.t[key] = 0
+
+    def set_learning_rate(self, lr):
+        if isinstance(lr, dict):
+            self.lr.update({k: float(v) for k, v in lr.items()})
+        else:
+            self.lr_default = float(lr)
+            self.lr = {}          # mi.ad.Adam.set_learning_rate(float) sets the default for all keys
+
+    def learning_rate(self, key) -> float:
+        return self.lr.get(key, self.lr_default)
+
+    def step(self, ctx: Optional[Context] = None):
+        for k, p in self.variables.items():
+            g = p.grad
+            if g is None:
+                continue
+            self.t[k] += 1
+            m, v = self.state[k]
+            c = ctx or _any_context()
+            with torch.no_grad():
+                c.adam_flat(p.data, g.contiguous(), m, v, self.t[k], self.learning_rate(k), self.beta_1, self.beta_2, self.epsilon)
+            p.grad = None
+
+
+_CTX_FALLBACK: Optional[Context] = None
+
+
+def _any_context() -> Context:
+    global _CTX_FALLBACK
+    if _CTX_FALLBACK is None:
+        _CTX_FALLBACK = Context()
+    return _CTX_FALLBACK

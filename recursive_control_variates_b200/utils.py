@@ -1,0 +1,125 @@
+"""utils.py of the reference (loss functions, parameter initialisation, clamp, upsample,
+reference render, checkpoint metrics) on top of the B200 kernels.  File formats of the
+reference (EXR images, Mitsuba .vol grids) are outside the hot path: metrics and final
+parameters are returned / saved as .npz instead."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from . import _abi
+from . import mitsuba_compat as mi
+from .plugins.volpathsimple import get_single_medium  # noqa: F401  (utils.py:4 re-export)
+
+
+class _LossOp(torch.autograd.Function):
+    """loss value + d loss / d img in one kernel (rcv_loss_grad); utils.py:21-25, optimize.py:110-122."""
+
+    @staticmethod
+    def forward(ctx, x, y, kind):
+        c = mi._any_context()
+        loss, grad = c.loss_grad(kind, x.contiguous(), y.contiguous(), True)
+        ctx.save_for_backward(grad)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None, None
+
+
+def l2_loss(x, y):
+    return _LossOp.apply(x, y, _abi.RCV_LOSS_L2)
+
+
+def l1_loss(x, y):
+    return _LossOp.apply(x, y, _abi.RCV_LOSS_L1)
+
+
+class Stopwatch:
+    """Replacement of utils.runtime() (sum of Dr.Jit kernel times, utils.py:16-19): CUDA-event
+    time of everything enqueued on the current stream since start(), in milliseconds."""
+
+    def __init__(self):
+        self.e0 = torch.cuda.Event(enable_timing=True)
+        self.e1 = torch.cuda.Event(enable_timing=True)
+
+    def start(self):
+        self.e0.record()
+
+    def stop(self) -> float:
+        self.e1.record()
+        self.e1.synchronize()
+        return self.e0.elapsed_time(self.e1)
+
+
+def initialize_parameters(params, opt, scene, scene_params):
+    """utils.py:62-87.  Runs twice for cv_ps so that old == new == init."""
+    for _ in range(2 if params["method"] == "cv_ps" else 1):
+        for key, param in params["variables"].items():
+            init_state = param["init"]
+            if "sigma_t" in key:
+                assert init_state.shape[-1] == 1
+                if params.get("use_majorant_supergrid", False):
+                    raise NotImplementedError("majorant supergrids are not supported yet (SURVEY.md §8f)")
+            opt[key] = init_state
+            scene_params[key] = opt[key]
+            if "lr_factor" in param:
+                opt.set_learning_rate({key: params.get("lr", 1e-2) * param["lr_factor"]})
+        scene_params.update()
+
+
+def render_reference(params, scene, integrator):
+    """utils.py:98-111 without the on-disk cache."""
+    ref_passes = params.get("ref_passes", 1)
+    spp_ref = params.get("spp_ref", params.get("spp", 1))
+    img_ref = None
+    for j in range(ref_passes):
+        img = mi.render(scene, seed=17843 + j, integrator=integrator, spp=spp_ref) / ref_passes
+        img_ref = img if img_ref is None else img_ref + img
+    return img_ref
+
+
+def checkpoint(scene, params, i, integrator, loss_func, img, img_ref, result_dict):
+    """utils.py:129-165: loss / variance against a higher-spp render every recomp_freq iterations."""
+    recomp_freq = params.get("recomp_freq", 10)
+    spp_inf = params.get("spp_inf", 64)
+    if i % recomp_freq == 0:
+        with torch.no_grad():
+            img_inf = mi.render(scene, integrator=integrator.integrator, seed=i + 1, spp=spp_inf)
+            result_dict["loss"][i // recomp_freq] = float(loss_func(img_ref, img_inf))
+            result_dict["var"][i // recomp_freq] = float(torch.mean((img_inf - img.detach()) ** 2))
+
+
+def precondition(params, opt):
+    for _, param in params["variables"].items():
+        if "largesteps" in param:
+            raise NotImplementedError("large-steps preconditioning is outside the hot path (SURVEY.md §2.1 #14)")
+
+
+def clamp(params, opt):
+    """utils.py:172-175."""
+    ctx = mi._any_context()
+    for key, param in params["variables"].items():
+        if "clamp" in param:
+            ctx.clamp(opt[key].data, float(param["clamp"][0]), float(param["clamp"][1]))
+
+
+def upsample(scene, params, opt, integrator):
+    """utils.py:177-192: nearest x2 upsampling of every grid, then integrator.reset()."""
+    ctx = mi._any_context()
+    for key in params["variables"]:
+        old = opt[key]
+        if old.dim() != 4:
+            raise ValueError(f"Upsampling expects a 4D tensor. Got {old.dim()}.")
+        opt[key] = ctx.upsample2x(old.data.contiguous())
+    integrator.reset()
+
+
+def save_final_state(params, opt, output_dir):
+    """utils.py:45-60; .npz instead of .vol / .exr."""
+    os.makedirs(output_dir, exist_ok=True)
+    np.savez(os.path.join(output_dir, "final_state.npz"),
+             **{k.replace(".", "_"): opt[k].detach().cpu().numpy() for k in params["variables"]})

@@ -1,0 +1,121 @@
+"""GPU tests of the reference-facing plugin layer: the reference's class / plugin names,
+properties, the render -> loss -> backward -> Adam loop of optimize.py, checked against
+the oracle where it computes something."""
+import numpy as np
+import pytest
+
+from helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mi():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from recursive_control_variates_b200 import mitsuba_compat, plugins  # noqa: F401
+    return mitsuba_compat
+
+
+def _params(method, **kw):
+    from recursive_control_variates_b200 import experiments
+    return experiments.scene_synthetic(method, None, grid=16, init_grid=8, film=(32, 24), spp=4, n_steps=6, upsample=(0.5,), **kw)
+
+
+def test_plugin_names_and_errors(mi):
+    from recursive_control_variates_b200 import plugins
+    for name in ("volpathsimple", "meta", "cv", "twostateprbvolpath", "prbvolpath", "twostatevolpath", "cv_ps"):
+        assert name in mi._INTEGRATORS
+    with pytest.raises(ValueError):                       # cv_integrator.py:19-20
+        mi.load_dict({"type": "cv", "integrator": {"type": "volpathsimple"}})
+    inner = mi.load_dict({"type": "twostateprbvolpath", "max_depth": 8, "rr_depth": 8})
+    assert isinstance(inner, plugins.TwoStatePRBVolpathIntegrator) and inner.max_depth == 8
+    p = _params("baseline")                               # plain heterogeneous medium: no TwoStateMedium
+    with pytest.raises(RuntimeError):                     # twostatevolpath.py:77-78
+        inner.render_twostates(p["scene"], 0, 0, 1)
+
+
+def test_cv_integrator_matches_oracle(mi, oracle):
+    """`cv` around `twostateprbvolpath`: H, F and the recursive CV image over a few iterations of
+    changing parameters, against oracle two-state renders + oracle cv_update."""
+    import torch
+    from recursive_control_variates_b200.synthetic import make_medium
+    p = _params("cv_ps")
+    scene = p["scene"]
+    integ = mi.load_dict({"type": "cv", "integrator": {"type": "twostateprbvolpath", "max_depth": 64, "rr_depth": 64},
+                          "adjoint_integrator": {"type": "volpathsimple", "max_depth": 64, "rr_depth": 64}})
+    sp = mi.traverse(scene)
+    ks, ka = "object.interior_medium.sigma_t.data", "object.interior_medium.albedo.data"
+    states = [make_medium(12, "cube", a) for a in (0.0, 0.0, 4e-3, 8e-3, 1.2e-2)]
+    desc = None
+    st_o = None
+    n = 0
+    prev = None
+    for it, (sig, alb) in enumerate(states):
+        sp[ks] = torch.from_numpy(sig).cuda(); sp[ka] = torch.from_numpy(alb).cuda()
+        sp.update()
+        if it == 0:
+            prev = (sig, alb)
+            continue                                       # first update only fills `new`; second makes old == new
+        img = integ.render(scene, 0, seed=it, spp=4)
+        ctx = integ.integrator._ctx(scene)
+        desc = ctx.desc
+        mo, mn = oracle.OracleMedium(desc, *prev), oracle.OracleMedium(desc, sig, alb)
+        H, F = oracle.render_twostates(desc, mo, mn, it, 4)
+        assert rel_l2(integ.H.cpu().numpy(), H) < 1e-4 and rel_l2(integ.F.cpu().numpy(), F) < 1e-4
+        if st_o is None:
+            st_o = {k: np.zeros_like(H) for k in ("img", "v_n", "w_s", "mean_x", "mean_y", "var_x", "var_y", "cov")}
+        oracle.cv_update(H, F, st_o, it - 1, 1, n, 0.9, 0.999)
+        n += (it - 1) > 0
+        assert rel_l2(img.cpu().numpy(), st_o["img"]) < 1e-4
+        prev = (sig, alb)
+    assert integ.it == 4 and integ.stats.n == 3
+
+
+@pytest.mark.parametrize("method", ["cv_ps", "baseline"])
+def test_run_opt_loop(mi, method):
+    """optimize.run_opt end to end (render, L1 loss, backward through volpathsimple, Adam, clamp,
+    upsample with CV reset): finite, parameters move, loss does not blow up."""
+    import torch
+    from recursive_control_variates_b200.optimize import run_opt
+    p = _params(method)
+    init_s = p["variables"]["object.interior_medium.sigma_t.data"]["init"].clone()
+    res = run_opt(p)
+    opt = res["opt"]
+    s = opt["object.interior_medium.sigma_t.data"]
+    a = opt["object.interior_medium.albedo.data"]
+    assert s.shape == (16, 16, 16, 1) and a.shape == (16, 16, 16, 3)          # one x2 upsample happened
+    assert torch.isfinite(s).all() and torch.isfinite(a).all()
+    assert float(s.min()) >= 0.0 and float(a.min()) >= 0.0 and float(a.max()) <= 1.0
+    assert float((s - 0.04).abs().max()) > 0, "sigma_t did not move"
+    assert np.isfinite(res["loss"]).all()
+
+
+def test_gradient_through_render_op(mi, oracle):
+    """mi.render(...).backward() == volpathsimple adjoint of d loss / d img (RenderOp boundary)."""
+    import torch
+    from recursive_control_variates_b200.utils import l1_loss
+    p = _params("cv_ps")
+    scene = p["scene"]
+    integ = mi.load_dict({"type": "meta", "method": "cv_ps", "integrator": p["integrator"],
+                          "adjoint_integrator": p["adjoint_integrator"]})
+    opt = mi.Adam(lr=5e-3)
+    sp = mi.traverse(scene)
+    from recursive_control_variates_b200.synthetic import make_medium
+    sig, alb = make_medium(10, "cube", 0.0)
+    ks, ka = "object.interior_medium.sigma_t.data", "object.interior_medium.albedo.data"
+    for _ in range(2):
+        opt[ks] = torch.from_numpy(sig); opt[ka] = torch.from_numpy(alb)
+        sp.update(opt)
+    img = mi.render(scene, sp, integrator=integ, seed=3, spp=4, spp_grad=2)
+    ref = torch.zeros_like(img)
+    loss = l1_loss(img, ref)
+    loss.backward()
+    gs, ga = opt[ks].grad.cpu().numpy(), opt[ka].grad.cpu().numpy()
+    desc = integ.integrator._ctx(scene).desc
+    from recursive_control_variates_b200.runtime import tea32
+    _, gimg = oracle.loss_grad(0, img.detach().cpu().numpy(), ref.cpu().numpy())
+    m = oracle.OracleMedium(desc, sig, alb)
+    ogs, oga = oracle.vps_backward(desc, m, tea32(3, 1)[0], 2, gimg)
+    assert rel_l2(gs, ogs) < 1e-3 and rel_l2(ga, oga) < 1e-3
