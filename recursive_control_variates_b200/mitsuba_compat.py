@@ -178,7 +178,10 @@ class Scene:
             raise ValueError("the scene needs a `constant` emitter")
         self._ctx: Optional[Context] = None
         self._ctx_key = None
-        self._medium_dirty = True
+        # rotations requested before the device context exists; the scene file loads the same
+        # volume into old, new and incoming (experiments.py:89-95), i.e. two rotations of it
+        m = self.medium().incoming_medium()
+        self._pending = [(m.sigma_t.data, m.albedo.data)] * 2
 
     def shapes(self):
         return self._shapes
@@ -206,22 +209,24 @@ class Scene:
         if key != self._ctx_key:
             self._ctx.set_scene(self.scene_config(max_depth, rr_depth, hide_emitters, use_nee))
             self._ctx_key = key
-        if self._medium_dirty:
-            self.push_medium()
+        if self._pending:
+            pending, self._pending = self._pending[-2:], []      # only the last two states can matter
+            for sig, alb in pending:
+                self._rotate(sig, alb)
         return self._ctx
 
-    def push_medium(self):
-        """Upload the incoming parameters as the new state: TwoStateMedium.parameters_changed
-        (old <- new, new <- incoming) is one rcv_medium_rotate."""
-        if self._ctx is None or self._ctx_key is None:
-            self._medium_dirty = True
-            return
-        m = self.medium().incoming_medium()
+    def _rotate(self, sig: torch.Tensor, alb: torch.Tensor):
         dev = self._ctx.torch_device
-        m.sigma_t.data = m.sigma_t.data.to(dev)
-        m.albedo.data = m.albedo.data.to(dev)
-        self._ctx.rotate(m.sigma_t.data, m.albedo.data)
-        self._medium_dirty = False
+        self._ctx.rotate(sig.detach().to(dev).contiguous(), alb.detach().to(dev).contiguous())
+
+    def push_medium(self):
+        """The incoming parameters become the new state: TwoStateMedium.parameters_changed
+        (old <- new, new <- incoming) is one rcv_medium_rotate."""
+        m = self.medium().incoming_medium()
+        if self._ctx is None or self._ctx_key is None:
+            self._pending.append((m.sigma_t.data, m.albedo.data))
+            return
+        self._rotate(m.sigma_t.data, m.albedo.data)
 
 
 def load_dict(d: dict):
