@@ -64,11 +64,17 @@ def test_cv_integrator_matches_oracle(mi, oracle):
         mo, mn = oracle.OracleMedium(desc, *prev), oracle.OracleMedium(desc, sig, alb)
         H, F = oracle.render_twostates(desc, mo, mn, it, 4)
         assert rel_l2(integ.H.cpu().numpy(), H) < 1e-4 and rel_l2(integ.F.cpu().numpy(), F) < 1e-4
+        # The recursion itself is compared on identical inputs (the GPU's H and F): the first
+        # weights after the warm-up are ratios of rounding residues (welford.py:68: x - mean/(1-beta)
+        # with mean == (1-beta) x), so float-level differences between two renderers' H/F are
+        # amplified to O(1) weight differences there — in the reference as much as here.
+        gH, gF = integ.H.cpu().numpy(), integ.F.cpu().numpy()
         if st_o is None:
-            st_o = {k: np.zeros_like(H) for k in ("img", "v_n", "w_s", "mean_x", "mean_y", "var_x", "var_y", "cov")}
-        oracle.cv_update(H, F, st_o, it - 1, 1, n, 0.9, 0.999)
+            st_o = {k: np.zeros_like(gH) for k in ("img", "v_n", "w_s", "mean_x", "mean_y", "var_x", "var_y", "cov")}
+        oracle.cv_update(gH, gF, st_o, it - 1, 1, n, 0.9, 0.999)
         n += (it - 1) > 0
-        assert rel_l2(img.cpu().numpy(), st_o["img"]) < 1e-4
+        assert np.array_equal(img.cpu().numpy(), st_o["img"], equal_nan=True)
+        assert np.array_equal(integ.w_s.cpu().numpy(), st_o["w_s"], equal_nan=True)
         prev = (sig, alb)
     assert integ.it == 4 and integ.stats.n == 3
 
