@@ -1,0 +1,65 @@
+"""The C-ABI library loads without a GPU, exports every symbol include/rcv_b200.h declares,
+and its compute entry points fail loudly (no CPU fallback) when no device is present."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "rcv_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    g.build()
+    from recursive_control_variates_b200 import _abi
+    return _abi.load_library()
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rcv_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(lib):
+    from recursive_control_variates_b200 import _abi
+    names = declared_functions()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/rcv_b200.h but not exported"
+    assert set(names) == set(_abi.EXPORTED_SYMBOLS), set(names) ^ set(_abi.EXPORTED_SYMBOLS)
+
+
+def test_struct_layouts_match_header(lib):
+    from recursive_control_variates_b200 import _abi
+    # 4 + 2*4 + 3*4 + 9*4 + 3*4 + 6*4 + 4 + 4 + 4 + 4 + 3*4 + 4 + 4*4 = 144
+    assert C.sizeof(_abi.SceneDesc) == 144
+    assert lib.rcv_abi_version() == 1
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    assert lib.rcv_device_count() <= 0
+    h = C.c_void_p()
+    rc = lib.rcv_ctx_create(0, None, C.byref(h))
+    assert rc == 2 and b"no CPU fallback" in lib.rcv_last_error()          # RCV_ERR_CUDA
+    from recursive_control_variates_b200 import _abi
+    from recursive_control_variates_b200.runtime import Context
+    with pytest.raises(_abi.RcvError):
+        Context()
+
+
+def test_product_does_not_import_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may touch oracle/."""
+    pkg = os.path.join(ROOT, "recursive_control_variates_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", text, flags=re.M), f
+                assert "rcv_oracle" not in text, f
