@@ -50,7 +50,8 @@ def parse():
     ap.add_argument("--tracer", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cpu-sample-spp", type=int, default=0, help="spp range of the CPU sample (0 = auto)")
+    ap.add_argument("--cpu-sample-spp", type=int, default=0, help="spp range of the CPU sample (0 = auto: ~15 s of CPU work)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target duration of one CPU sample")
     return ap.parse_args()
 
 
@@ -144,6 +145,14 @@ def cpu_iteration_sample(a, n_gpus, sample_spp, threads):
     return paths, t2 - t0, t1 - t0, t2 - t1
 
 
+def calibrated_sample_spp(a, n_gpus, threads, budget_s):
+    """Size the CPU sample: time samples [0,1) of every pixel, then pick the spp range that takes ~budget_s."""
+    if a.cpu_sample_spp:
+        return a.cpu_sample_spp
+    _, t1, _, _ = cpu_iteration_sample(a, n_gpus, 1, threads)
+    return int(max(1, min(a.spp * n_gpus, round(budget_s / max(t1, 1e-3)))))
+
+
 def run_reference(a):
     """--impl reference: the reference cannot be installed (no Mitsuba 3 / Dr.Jit wheel, DESIGN.md §3);
     its CPU restatement (oracle/, kind 'port') is timed on all host cores instead."""
@@ -153,9 +162,9 @@ def run_reference(a):
     n_gpus = a.gpus
     import oracle as O
     threads = O.default_threads()
-    sample_spp = a.cpu_sample_spp or 1
-    for _ in range(min(a.warmup, 1)):
-        cpu_iteration_sample(a, n_gpus, 1, threads)
+    # the whole --steps/--warmup run should end within a few minutes
+    budget = min(a.cpu_seconds, 150.0 / max(1, a.steps + min(a.warmup, 1)))
+    sample_spp = calibrated_sample_spp(a, n_gpus, threads, budget)      # doubles as the warm-up pass
     times, paths = [], 0
     for _ in range(a.steps):
         paths, t, _, _ = cpu_iteration_sample(a, n_gpus, sample_spp, threads)
@@ -296,8 +305,17 @@ def run_ours(a):
                                   "mpaths_s": 2 * lanes / k6_ms / 1e3},
     }
     dom = max(kernels, key=lambda k: kernels[k]["ms"])
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture of this workload (per launch)
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath) and (a.grid, a.res, a.spp, a.kind) == (256, 512, 64, "cube") and n_gpus == 1:
+        with open(tpath) as f:
+            tj = json.load(f)
+        if dom in tj:
+            traffic, traffic_src = tj[dom]["dram_bytes"] / 1e9, tj[dom]["capture"]
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kernels[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "frac": kernels[dom]["gbs"] / peak, "traffic": traffic, "traffic_unit": "GB per launch",
+                "traffic_source": traffic_src, "algorithmic_gb": kernels[dom]["algorithmic_gb"], "peak_source": peak_src,
                 "share_of_step": kernels[dom]["ms"] / ms_per_step}
 
     # ---- end to end through the host-buffer C-ABI call (pinned host memory, copies inside the timed region)
@@ -331,7 +349,7 @@ def run_ours(a):
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         import oracle as O
         threads = O.default_threads()
-        sample_spp = a.cpu_sample_spp or 1
+        sample_spp = calibrated_sample_spp(a, n_gpus, threads, a.cpu_seconds)
         paths, tt, t_primal, t_adj = cpu_iteration_sample(a, n_gpus, sample_spp, threads)
         cpu = {"value": paths / tt / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"samples [0,{sample_spp}) of {spp_total} spp of every pixel ({paths} paths): two-state render "

@@ -7,8 +7,8 @@
 //       run the per-lane event machines (rcv_*_wf.cuh): every round a warp
 //       refills its finished lanes from the record queue and executes ONE event
 //       handler — the tentative-collision step (the only place with a grid
-//       gather) or the vertex step — with the lanes waiting for it.  The
-//       adjoint's gradient scatters are executed cooperatively by the warp.
+//       gather), the vertex step or the batched slow step — with the lanes
+//       waiting for it.
 //   * SIMPLE   one thread per lane, nested loops (A/B baseline).
 //   * BATCH    persistent warps pulling 32-lane batches, nested loops (A/B baseline).
 // Results are schedule-independent: each lane owns its PCG32 stream, indexed
@@ -275,65 +275,6 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_twostates_wavefront(
     counter_flush(C, 6, sk.n_paths);
 }
 
-// --- cooperative gradient scatter ---------------------------------------------
-// One corner per lane.  The addends are computed with exactly the expressions
-// of vp_req_point (tri_weight(T,k) * sg), so only the order of the float
-// reductions differs from the serial version.
-__device__ __forceinline__ void coop_corner(const SceneK &S, const GridK &G, V3 p, int k, bool &inside, size_t &v, float &w) {
-    Tri T = tri_setup(S, G, p);
-    inside = T.inside;
-    v = tri_voxel(G, T, k);
-    w = tri_weight(T, k);
-}
-
-__device__ __forceinline__ void vp_req_flush_coop(const SceneK &S, const GridK &G, const GradK &D, const VpLane &ln, const VpReq &rq,
-                                                  VpsCounts &cnt) {
-    const unsigned lane = threadIdx.x & 31;
-    const int k = (int) (lane & 7u);
-    const int grp = (int) (lane >> 3);
-    // transmittance segments: 4 points x 8 corners = the 32 lanes, one requesting lane at a time
-    unsigned m = __ballot_sync(0xffffffffu, rq.has_seg);
-    while (m) {
-        int src = __ffs(m) - 1;
-        m &= m - 1;
-        V3 o = mk3(__shfl_sync(0xffffffffu, ln.o.x, src), __shfl_sync(0xffffffffu, ln.o.y, src), __shfl_sync(0xffffffffu, ln.o.z, src));
-        V3 d = mk3(__shfl_sync(0xffffffffu, ln.d.x, src), __shfl_sync(0xffffffffu, ln.d.y, src), __shfl_sync(0xffffffffu, ln.d.z, src));
-        float interval = __shfl_sync(0xffffffffu, rq.interval, src);
-        float sg = __shfl_sync(0xffffffffu, rq.sg_seg, src);
-        float u0 = __shfl_sync(0xffffffffu, rq.u[0], src), u1 = __shfl_sync(0xffffffffu, rq.u[1], src);
-        float u2 = __shfl_sync(0xffffffffu, rq.u[2], src), u3 = __shfl_sync(0xffffffffu, rq.u[3], src);
-        float u = (grp == 0) ? u0 : ((grp == 1) ? u1 : ((grp == 2) ? u2 : u3));
-        bool inside; size_t v; float w;
-        coop_corner(S, G, ray_at(o, d, u * interval), k, inside, v, w);
-        if (inside) {
-            red_add_f32(D.gsig + v, w * sg);
-            if (k == 0) cnt.g_sig++;
-        }
-    }
-    // single points: four requesting lanes at a time, 8 corners each
-    m = __ballot_sync(0xffffffffu, rq.has_pt);
-    while (m) {
-        unsigned src = __fns(m, 0, grp + 1);          // grp-th requesting lane, 0xffffffff if there is none
-        bool valid = src != 0xffffffffu;
-        int s = valid ? (int) src : 0;
-        V3 p = mk3(__shfl_sync(0xffffffffu, rq.p.x, s), __shfl_sync(0xffffffffu, rq.p.y, s), __shfl_sync(0xffffffffu, rq.p.z, s));
-        float sg = __shfl_sync(0xffffffffu, rq.sg, s);
-        int has_alb = __shfl_sync(0xffffffffu, (int) rq.has_alb, s);
-        V3 gal = mk3(__shfl_sync(0xffffffffu, rq.gal.x, s), __shfl_sync(0xffffffffu, rq.gal.y, s), __shfl_sync(0xffffffffu, rq.gal.z, s));
-        if (valid) {
-            bool inside; size_t v; float w;
-            coop_corner(S, G, p, k, inside, v, w);
-            if (inside) {
-                red_add_f32(D.gsig + v, w * sg);
-                if (has_alb) red_add_v4(D.galb + v, w * gal.x, w * gal.y, w * gal.z, 0.f);
-                if (k == 0) { cnt.g_sig++; if (has_alb) cnt.g_alb++; }
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) m &= m - 1;       // clears the four lowest set bits (0 stays 0)
-    }
-}
-
 template <bool BACKWARD>
 __global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_vps_wavefront(const __grid_constant__ SceneK S,
                                                                            const __grid_constant__ GridK G, GradK D, uint32_t seed,
@@ -358,18 +299,10 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_vps_wavefront(const 
             0xffffffffu, ln.ev == EV_SLOW || (ln.ev == EV_INIT && ((BACKWARD && (ln.flags & VF_PASS2)) || cc.more))));
         if (n_coll == 0 && n_scat == 0 && n_slow == 0) break;
         const int sel = pick_event(n_coll, n_scat, n_slow);
-        VpReq rq;
-        vp_req_clear(rq);
-        rq.p = mk3(0, 0, 0); rq.gal = mk3(0, 0, 0); rq.sg = 0.f; rq.interval = 0.f; rq.sg_seg = 0.f;
-        rq.u[0] = rq.u[1] = rq.u[2] = rq.u[3] = 0.f;
         if (sel == EV_COLL) {
-            if (ln.ev == EV_COLL) vp_collide<BACKWARD>(S, G, mu, inv_mu, ln, sk, rq);
-            if (BACKWARD) vp_req_flush_coop(S, G, D, ln, rq, sk.cnt);
+            if (ln.ev == EV_COLL) vp_collide<BACKWARD>(S, G, mu, inv_mu, ln, sk);
         } else if (sel == EV_SCAT) {
-            const bool mine = ln.ev == EV_SCAT;
-            if (mine) vp_vertex_a<BACKWARD>(S, G, ln, sk, rq);
-            if (BACKWARD) vp_req_flush_coop(S, G, D, ln, rq, sk.cnt);
-            if (mine) vp_vertex_b<BACKWARD>(S, ln, sk);
+            if (ln.ev == EV_SCAT) vp_vertex<BACKWARD>(S, G, ln, sk);
         } else {
             if (ln.ev == EV_SLOW) vp_slow<BACKWARD>(S, ln, sk);
             // resume lanes that finished pass 1 as pass 2; refill the finished ones

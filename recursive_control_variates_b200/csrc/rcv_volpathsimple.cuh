@@ -27,7 +27,7 @@ struct Mei1 {
 
 // Medium::sample_interaction of state `new` with a global majorant
 __device__ __forceinline__ void sample_interaction1(const SceneK &S, const GridK &G, float inv_mu, V3 o, V3 d, V3 id,
-                                                    float ray_maxt, float u, Mei1 &m, VpsCounts &cnt) {
+                                                    float ray_maxt, float u, Mei1 &m, Tri &T, VpsCounts &cnt) {
     float mint, maxt;
     bool active = medium_interval(S, o, d, id, ray_maxt, mint, maxt);
     float tau = -spec_log(1.f - u);
@@ -37,21 +37,34 @@ __device__ __forceinline__ void sample_interaction1(const SceneK &S, const GridK
     m.p = ray_at(o, d, t);
     m.st = 0.f;
     if (m.valid) {
-        Tri T = tri_setup(S, G, m.p);
+        T = tri_setup(S, G, m.p);
         m.st = lookup_sigma1(S, G, T);
         cnt.coll++;
     }
 }
+// convenience overload for callers that do not need the interpolation set-up
+__device__ __forceinline__ void sample_interaction1(const SceneK &S, const GridK &G, float inv_mu, V3 o, V3 d, V3 id,
+                                                    float ray_maxt, float u, Mei1 &m, VpsCounts &cnt) {
+    Tri T;
+    sample_interaction1(S, G, inv_mu, o, d, id, ray_maxt, u, m, T, cnt);
+}
 
-// AD of sigma_t(p) = scale * trilinear(grid): scatter w_corner * scale * g
+// AD of sigma_t(p) = scale * trilinear(grid): scatter w_corner * (scale * g) on a known interpolation set-up
+__device__ __forceinline__ void scatter_sigma_t_T(const GridK &G, const GradK &D, const Tri &T, float sg, VpsCounts &cnt) {
+    if (!T.inside) return;
+    size_t r[4];
+    tri_rows(G, T, r);
+    const float wzy[4] = {T.wz0 * T.wy0, T.wz0 * T.wy1, T.wz1 * T.wy0, T.wz1 * T.wy1};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        red_add_f32(D.gsig + r[k] + T.x0, (wzy[k] * T.wx0) * sg);
+        red_add_f32(D.gsig + r[k] + T.x1, (wzy[k] * T.wx1) * sg);
+    }
+    cnt.g_sig++;
+}
 __device__ __forceinline__ void scatter_sigma_t(const SceneK &S, const GridK &G, const GradK &D, V3 p, float g, VpsCounts &cnt) {
     Tri T = tri_setup(S, G, p);
-    if (!T.inside) return;
-    float sg = S.scale * g;
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-        red_add_f32(D.gsig + tri_voxel(G, T, k), tri_weight(T, k) * sg);
-    cnt.g_sig++;
+    scatter_sigma_t_T(G, D, T, S.scale * g, cnt);
 }
 
 // volpathsimple.py:449-517, ratio tracking from o along d over [0, tmax]

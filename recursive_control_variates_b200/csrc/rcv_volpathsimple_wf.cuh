@@ -14,19 +14,18 @@
 //              sample_real_interaction (:360-380) or a ratio-tracking step of
 //              estimate_transmittance (:478-515) — in the adjoint's NEE replay
 //              (:406-414) it emits the sigma_t gradient request of :496-505
-//   EV_SCAT    a path vertex (real collision or medium exit), in two halves:
-//              vp_vertex_a  coefficient gathers, the adjoint's scattering
-//                           (:165-185) and transmittance (:194-202, :597-620)
-//                           gradient requests
-//              vp_vertex_b  NEE set-up (:393-446) or phase sampling (:234-258)
+//   EV_SCAT    a path vertex (real collision or medium exit): coefficient gathers,
+//              the adjoint's scattering (:165-185) and transmittance (:194-202,
+//              :597-620) gradient scatters, then NEE set-up (:393-446) or phase
+//              sampling (:234-258)
 //   EV_SLOW    once-per-shadow-ray / once-per-pass work that would otherwise run
 //              with one or two lanes: end of the shadow ray, start of its
 //              adjoint replay, phase sampling after it, end of a pass; the
 //              scheduler also reloads / refills lanes in this step
 //
-// Gradient scatters are not executed by the handlers: they are returned as a
-// VpReq and flushed between the two vertex halves — cooperatively by the whole
-// warp on the GPU (rcv_trace.cu), serially in the host harness.
+// Gradient scatters run inside the handlers: vertex steps are batched (>= 12
+// lanes), so all requesting lanes issue their reductions together; the NEE
+// replay reuses the interpolation set-up of the collision's gather.
 // The handlers contain no warp intrinsics and also compile for the host
 // (RCV_HOST_EMU) where tests single-step them against the oracle.
 #pragma once
@@ -44,7 +43,6 @@ enum : uint32_t {
     VF_HEAD = 32u,        // next main-path collision starts with the loop head (:129-134)
     VF_DID_SCATTER = 64u,
     VF_PASS2 = 128u,      // pass 1 finished, the lane must reload its record as pass 2
-    VF_ACTIVE = 256u,     // `active` after :213, carried from vertex_a to vertex_b
     // work parked for the batched EV_SLOW step
     VF_POSTNEE = 512u,    // the shadow ray (or its replay) ended
     VF_END = 1024u        // the pass ended at a loop head (:132-133)
@@ -68,19 +66,6 @@ struct VpLane {
     V3 nee;                 // NEE contribution of this vertex (needed after the replay)
 };
 
-// gradient scatter requests of one handler invocation
-struct VpReq {
-    bool has_pt;            // one point: d sigma_t (+ d albedo at scattering vertices)
-    bool has_alb;
-    V3 p;
-    float sg;               // scale * g: weight of the sigma_t gradient
-    V3 gal;                 // albedo gradient
-    bool has_seg;           // transmittance term: 4 points u_j * interval along (ln.o, ln.d)
-    float interval, sg_seg;
-    float u[4];
-};
-__device__ __forceinline__ void vp_req_clear(VpReq &rq) { rq.has_pt = false; rq.has_alb = false; rq.has_seg = false; }
-
 struct VpSink {
     float4 *accum;          // primal render target (H,W,4) or null
     GradK D;                // gradient grids (adjoint)
@@ -89,30 +74,6 @@ struct VpSink {
     VpsCounts cnt;
     unsigned n_paths;
 };
-
-// serial execution of a request (host harness; the GPU kernels use the
-// cooperative version in rcv_trace.cu, which produces the same addends)
-__device__ __forceinline__ void vp_req_point(const SceneK &S, const GridK &G, const GradK &D, V3 p, float sg, bool has_alb, V3 gal,
-                                             VpsCounts &cnt) {
-    Tri T = tri_setup(S, G, p);
-    if (!T.inside) return;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        float w = tri_weight(T, k);
-        size_t v = tri_voxel(G, T, k);
-        red_add_f32(D.gsig + v, w * sg);
-        if (has_alb) red_add_v4(D.galb + v, w * gal.x, w * gal.y, w * gal.z, 0.f);
-    }
-    cnt.g_sig++;
-    if (has_alb) cnt.g_alb++;
-}
-__device__ __forceinline__ void vp_req_flush_serial(const SceneK &S, const GridK &G, const GradK &D, const VpLane &ln, const VpReq &rq,
-                                                    VpsCounts &cnt) {
-    if (rq.has_pt) vp_req_point(S, G, D, rq.p, rq.sg, rq.has_alb, rq.gal, cnt);
-    if (rq.has_seg)
-        for (int j = 0; j < 4; ++j)
-            vp_req_point(S, G, D, ray_at(ln.o, ln.d, rq.u[j] * rq.interval), rq.sg_seg, false, mk3(0, 0, 0), cnt);
-}
 
 template <bool BW>
 __device__ __forceinline__ void vp_end_pass(const SceneK &S, VpLane &ln, VpSink &sk) {
@@ -273,8 +234,7 @@ __device__ __forceinline__ void vp_nee_done(const SceneK &S, VpLane &ln, VpSink 
 }
 
 template <bool BW>
-__device__ __forceinline__ void vp_collide(const SceneK &S, const GridK &G, float mu, float inv_mu, VpLane &ln, VpSink &sk,
-                                           VpReq &rq) {
+__device__ __forceinline__ void vp_collide(const SceneK &S, const GridK &G, float mu, float inv_mu, VpLane &ln, VpSink &sk) {
     const bool nee = (ln.flags & VF_IN_NEE) != 0;
     if (!nee && (ln.flags & VF_HEAD)) {                               // loop head (:129-134)
         float q = fmin_(max3(ln.thr), 0.99f);
@@ -290,8 +250,8 @@ __device__ __forceinline__ void vp_collide(const SceneK &S, const GridK &G, floa
     // warp execute the gather together
     const V3 sd = nee ? ln.nd : ln.d;
     float u = pcg_f32(ln.rng);
-    Mei1 m;
-    sample_interaction1(S, G, inv_mu, ln.ro, sd, ln.id, ln.rmaxt, u, m, sk.cnt);
+    Mei1 m; Tri T;
+    sample_interaction1(S, G, inv_mu, ln.ro, sd, ln.id, ln.rmaxt, u, m, T, sk.cnt);
     if (nee) {
         // estimate_transmittance step (:478-515)
         float sn = m.valid ? (mu - m.st) : 0.f;
@@ -306,7 +266,7 @@ __device__ __forceinline__ void vp_collide(const SceneK &S, const GridK &G, floa
                 float k = (-inv_mu) / tr;
                 g += adjoint.x * k; g += adjoint.y * k; g += adjoint.z * k;
             }
-            rq.has_pt = true; rq.has_alb = false; rq.p = m.p; rq.sg = S.scale * g; rq.gal = mk3(0, 0, 0);
+            scatter_sigma_t_T(G, sk.D, T, S.scale * g, sk.cnt);           // the gather's set-up is reused
         }
         ln.tr_acc = ln.tr_acc * tr;                                   // :508
         ln.ro = m.p;                                                  // :510
@@ -338,17 +298,20 @@ __device__ __forceinline__ void vp_slow(const SceneK &S, VpLane &ln, VpSink &sk)
     }
 }
 
-// first half of a vertex: gathers, gradient requests, throughput/depth update
+// a path vertex: gathers, the adjoint's gradient scatters, throughput/depth update, then NEE set-up
+// or the continuation of the path
 template <bool BW>
-__device__ __forceinline__ void vp_vertex_a(const SceneK &S, const GridK &G, VpLane &ln, VpSink &sk, VpReq &rq) {
+__device__ __forceinline__ void vp_vertex(const SceneK &S, const GridK &G, VpLane &ln, VpSink &sk) {
     const bool did_scatter = (ln.flags & VF_DID_SCATTER) != 0;
     const bool adj = BW && (ln.flags & VF_ADJ);
     if (did_scatter) ln.flags |= VF_HAS_SCAT;                         // :150
     V3 mei_p = mk3(0, 0, 0), albedo = mk3(1, 1, 1);
     float st = 0.f;
+    Tri T;
+    T.inside = false;
     if (did_scatter) {
         mei_p = ray_at(ln.o, ln.d, ln.mei_t);                         // :384
-        Tri T = tri_setup(S, G, mei_p);
+        T = tri_setup(S, G, mei_p);
         if (adj) st = lookup_sigma1(S, G, T);                         // :386-388
         albedo = lookup_albedo(G, T, 1);                              // :154
         sk.cnt.scat++;
@@ -359,28 +322,33 @@ __device__ __forceinline__ void vp_vertex_a(const SceneK &S, const GridK &G, VpL
             V3 Li = ln.result / vmax3(splat3(1e-8f), albedo);
             V3 c = (ln.dL * Li) * inv_pdf;
             float g_st = (c.x * albedo.x + c.y * albedo.y) + c.z * albedo.z;
-            rq.has_pt = true; rq.has_alb = true; rq.p = mei_p; rq.sg = S.scale * g_st; rq.gal = c * splat3(st);
+            V3 g_al = c * splat3(st);
+            if (T.inside) {
+                float sg = S.scale * g_st;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    float w = tri_weight(T, k);
+                    size_t v = tri_voxel(G, T, k);
+                    red_add_f32(sk.D.gsig + v, w * sg);
+                    red_add_v4(sk.D.galb + v, w * g_al.x, w * g_al.y, w * g_al.z, 0.f);
+                }
+                sk.cnt.g_sig++; sk.cnt.g_alb++;
+            }
         }
         // transmittance term (:194-202, :597-620)
         V3 aw = ln.dL * ln.result;
         float interval = did_scatter ? ln.mei_t : ln.ray_maxt;        // :601 (si.t == ray.maxt)
         float inv_pdf = interval / 4.f;
         float g = -((aw.x * inv_pdf) + (aw.y * inv_pdf) + (aw.z * inv_pdf));
-        rq.has_seg = true; rq.interval = interval; rq.sg_seg = S.scale * g;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) rq.u[j] = pcg_f32(ln.alt);        // :608
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+            float t = pcg_f32(ln.alt) * interval;                     // :608
+            scatter_sigma_t(S, G, sk.D, ray_at(ln.o, ln.d, t), g, sk.cnt);
+        }
     }
     ln.thr = ln.thr * albedo;                                         // :206
     if (did_scatter) ln.depth += 1;                                   // :212
     bool active = did_scatter && (ln.depth < S.max_depth);            // :213
-    ln.flags = active ? (ln.flags | VF_ACTIVE) : (ln.flags & ~VF_ACTIVE);
-}
-
-// second half: NEE set-up or the continuation of the path
-template <bool BW>
-__device__ __forceinline__ void vp_vertex_b(const SceneK &S, VpLane &ln, VpSink &sk) {
-    const bool did_scatter = (ln.flags & VF_DID_SCATTER) != 0;
-    const bool active = (ln.flags & VF_ACTIVE) != 0;
     if (S.use_nee && did_scatter && active) {                         // :219-228 -> :393-446
         ln.saved = ln.rng.state;                                      // :396 sampler.clone()
         float s2x = pcg_f32(ln.rng), s2y = pcg_f32(ln.rng);           // :431

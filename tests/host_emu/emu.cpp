@@ -93,14 +93,10 @@ void run_vps(const SceneK &S, const GridK &G, VpSink &sk) {
                 vp_load(ln, sk, hq.Q, ln.qpos, true);
                 continue;
             }
-            VpReq rq; vp_req_clear(rq);
             if (ln.ev == EV_COLL) {
-                vp_collide<BW>(S, G, mu, inv_mu, ln, sk, rq);
-                if (BW) vp_req_flush_serial(S, G, sk.D, ln, rq, sk.cnt);
+                vp_collide<BW>(S, G, mu, inv_mu, ln, sk);
             } else if (ln.ev == EV_SCAT) {
-                vp_vertex_a<BW>(S, G, ln, sk, rq);
-                if (BW) vp_req_flush_serial(S, G, sk.D, ln, rq, sk.cnt);
-                vp_vertex_b<BW>(S, ln, sk);
+                vp_vertex<BW>(S, G, ln, sk);
             } else {
                 vp_slow<BW>(S, ln, sk);
             }
