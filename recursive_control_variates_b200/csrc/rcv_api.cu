@@ -45,7 +45,7 @@ struct rcv_ctx {
     int nx = 0, ny = 0, nz = 0;
     size_t nvox = 0;
     float2 *sig2 = nullptr;
-    float *sig1 = nullptr;
+    float4 *blk2 = nullptr, *blk1 = nullptr;
     float4 *alb2 = nullptr;
     float *grad = nullptr;       // [pad4(nvox) floats d sigma_t][nvox float4 d albedo]
     size_t grad_floats = 0;
@@ -87,7 +87,7 @@ struct rcv_ctx {
     }
     GridK gridk() const {
         GridK g;
-        g.sig2 = sig2; g.sig1 = sig1; g.alb2 = alb2; g.nx = nx; g.ny = ny; g.nz = nz; g.majorants = majorants;
+        g.sig2 = sig2; g.blk2 = blk2; g.blk1 = blk1; g.alb2 = alb2; g.nx = nx; g.ny = ny; g.nz = nz; g.majorants = majorants;
         return g;
     }
 };
@@ -101,8 +101,8 @@ int use_device(rcv_ctx *ctx) {
 }
 
 void free_medium(rcv_ctx *c) {
-    cudaFree(c->sig2); cudaFree(c->sig1); cudaFree(c->alb2); cudaFree(c->grad); cudaFree(c->block_max);
-    c->sig2 = nullptr; c->sig1 = nullptr; c->alb2 = nullptr; c->grad = nullptr; c->block_max = nullptr;
+    cudaFree(c->sig2); cudaFree(c->blk2); cudaFree(c->blk1); cudaFree(c->alb2); cudaFree(c->grad); cudaFree(c->block_max);
+    c->sig2 = nullptr; c->blk2 = nullptr; c->blk1 = nullptr; c->alb2 = nullptr; c->grad = nullptr; c->block_max = nullptr;
     c->nvox = 0; c->nx = c->ny = c->nz = 0;
 }
 
@@ -259,10 +259,12 @@ int rcv_medium_rotate(rcv_ctx *c, const float *sigma_t_in, const float *albedo_i
     size_t nvox = (size_t) nz * ny * nx;
     LaunchCfg cfg = c->cfg();
     if (nz != c->nz || ny != c->ny || nx != c->nx) {
-        float2 *sig2; float *sig1; float4 *alb2; float *grad; float *bm;
+        float2 *sig2; float4 *blk2, *blk1; float4 *alb2; float *grad; float *bm;
+        size_t ncell = (size_t) (nz + 1) * (ny + 1) * (nx + 1);
         size_t grad_floats = ((nvox + 3) / 4) * 4 + 4 * nvox;
         CK(cudaMalloc(&sig2, nvox * sizeof(float2)));
-        CK(cudaMalloc(&sig1, nvox * sizeof(float)));
+        CK(cudaMalloc(&blk2, 4 * ncell * sizeof(float4)));
+        CK(cudaMalloc(&blk1, 2 * ncell * sizeof(float4)));
         CK(cudaMalloc(&alb2, 2 * nvox * sizeof(float4)));
         CK(cudaMalloc(&grad, grad_floats * sizeof(float)));
         uint64_t want = (nvox + 255) / 256, cap = (uint64_t) c->sm_count * 8;
@@ -280,11 +282,11 @@ int rcv_medium_rotate(rcv_ctx *c, const float *sigma_t_in, const float *albedo_i
         }
         CK(cudaMemsetAsync(grad, 0, grad_floats * sizeof(float), c->stream));
         free_medium(c);
-        c->sig2 = sig2; c->sig1 = sig1; c->alb2 = alb2; c->grad = grad; c->block_max = bm; c->n_rot_blocks = nb;
+        c->sig2 = sig2; c->blk2 = blk2; c->blk1 = blk1; c->alb2 = alb2; c->grad = grad; c->block_max = bm; c->n_rot_blocks = nb;
         c->nz = nz; c->ny = ny; c->nx = nx; c->nvox = nvox; c->grad_floats = grad_floats;
     }
-    CK(launch_rotate(cfg, sigma_t_in, albedo_in, nvox, c->S.scale, c->sig2, c->sig1, c->alb2, c->block_max, c->n_rot_blocks,
-                     c->majorants));
+    CK(launch_rotate(cfg, sigma_t_in, albedo_in, nz, ny, nx, c->S.scale, c->sig2, c->blk2, c->blk1, c->alb2, c->block_max,
+                     c->n_rot_blocks, c->majorants));
     return RCV_OK;
 }
 

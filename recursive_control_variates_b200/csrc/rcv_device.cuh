@@ -58,13 +58,20 @@ struct SceneK {
 };
 
 // Packed medium state in HBM:
-//   sig2[v]      = (sigma_t_old, sigma_t_new) of voxel v         (8 B / voxel)
-//   sig1[v]      = sigma_t_new                                   (4 B / voxel)
+//   sig2[v]      = (sigma_t_old, sigma_t_new) of voxel v         (8 B / voxel; canonical state)
 //   alb2[2v + s] = (albedo rgb of state s, 0)                    (32 B / voxel)
-// v = (z * ny + y) * nx + x, x fastest (the reference's (Z,Y,X,C) layout).
+// v = (z * ny + y) * nx + x, x fastest (the reference's (Z,Y,X,C) layout), and the
+// gather bricks built from sig2 after every rotation: one brick per interpolation
+// cell c = (cz * (ny+1) + cy) * (nx+1) + cx, cx = floor(pos.x) + 1 in [0, nx], holding
+// the cell's 8 corner values (clamp addressing resolved at build time) contiguously,
+//   blk2[4c .. 4c+3] = 8 x (sigma_t_old, sigma_t_new)            (64 B / cell: two sectors)
+//   blk1[2c .. 2c+1] = 8 x  sigma_t_new                          (32 B / cell: one sector)
+// corner order k = 4*zbit + 2*ybit + xbit.  A tentative collision therefore reads ONE
+// contiguous brick instead of eight scattered voxels.
 struct GridK {
     const float2 *sig2;
-    const float *sig1;
+    const float4 *blk2;
+    const float4 *blk1;
     const float4 *alb2;
     int nx, ny, nz;
     const float *majorants;   // device: [0] = old, [1] = new  (scale * max)
@@ -352,10 +359,11 @@ __device__ __forceinline__ V3 offset_p(V3 p, V3 n, V3 d) {
 struct Tri {
     bool inside;
     int x0, x1, y0, y1, z0, z1;
+    int cx, cy, cz;           // interpolation cell = floor(pos) + 1 per axis, in [0, res]
     float wx0, wx1, wy0, wy1, wz0, wz1;
 };
 
-__device__ __forceinline__ void tri_axis(float p, float bmin, float inv_ext, int res, bool &inside, int &i0, int &i1,
+__device__ __forceinline__ void tri_axis(float p, float bmin, float inv_ext, int res, bool &inside, int &i0, int &i1, int &c,
                                          float &w0, float &w1) {
     float pl = (p - bmin) * inv_ext;
     inside = inside && (pl >= 0.f) && (pl <= 1.f);
@@ -366,13 +374,25 @@ __device__ __forceinline__ void tri_axis(float p, float bmin, float inv_ext, int
     w0 = 1.f - w1;
     i0 = min(max(i, 0), res - 1);
     i1 = min(max(i + 1, 0), res - 1);
+    c = min(max(i + 1, 0), res);
 }
 __device__ __forceinline__ Tri tri_setup(const SceneK &S, const GridK &G, V3 p) {
     Tri T; T.inside = true;
-    tri_axis(p.x, S.bmin[0], S.inv_ext[0], G.nx, T.inside, T.x0, T.x1, T.wx0, T.wx1);
-    tri_axis(p.y, S.bmin[1], S.inv_ext[1], G.ny, T.inside, T.y0, T.y1, T.wy0, T.wy1);
-    tri_axis(p.z, S.bmin[2], S.inv_ext[2], G.nz, T.inside, T.z0, T.z1, T.wz0, T.wz1);
+    tri_axis(p.x, S.bmin[0], S.inv_ext[0], G.nx, T.inside, T.x0, T.x1, T.cx, T.wx0, T.wx1);
+    tri_axis(p.y, S.bmin[1], S.inv_ext[1], G.ny, T.inside, T.y0, T.y1, T.cy, T.wy0, T.wy1);
+    tri_axis(p.z, S.bmin[2], S.inv_ext[2], G.nz, T.inside, T.z0, T.z1, T.cz, T.wz0, T.wz1);
     return T;
+}
+__device__ __forceinline__ size_t tri_cell(const GridK &G, const Tri &T) {
+    return ((size_t) T.cz * (G.ny + 1) + T.cy) * (G.nx + 1) + T.cx;
+}
+// the 8 corner voxels of cell (cx,cy,cz) in brick order — used by the brick builder
+__host__ __device__ __forceinline__ size_t cell_corner(int nx, int ny, int nz, int cx, int cy, int cz, int k) {
+    int x = (k & 1) ? cx : cx - 1, y = (k & 2) ? cy : cy - 1, z = (k & 4) ? cz : cz - 1;
+    x = x < 0 ? 0 : (x > nx - 1 ? nx - 1 : x);
+    y = y < 0 ? 0 : (y > ny - 1 ? ny - 1 : y);
+    z = z < 0 ? 0 : (z > nz - 1 ? nz - 1 : z);
+    return ((size_t) z * ny + y) * nx + x;
 }
 // v[k], k = 4*zbit + 2*ybit + xbit
 __device__ __forceinline__ float tri_lerp(const Tri &T, float v0_, float v1_, float v2_, float v3_, float v4_, float v5_,
@@ -407,29 +427,17 @@ __device__ __forceinline__ size_t tri_voxel(const GridK &G, const Tri &T, int k)
 // both states' sigma_t (scale * grid) with one gather of 8 float2
 __device__ __forceinline__ void lookup_sigma2(const SceneK &S, const GridK &G, const Tri &T, float &s_old, float &s_new) {
     if (!T.inside) { s_old = 0.f; s_new = 0.f; return; }
-    size_t r[4];
-    tri_rows(G, T, r);
-    float2 v[8];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        v[2 * k] = __ldg(G.sig2 + r[k] + T.x0);
-        v[2 * k + 1] = __ldg(G.sig2 + r[k] + T.x1);
-    }
-    s_old = S.scale * tri_lerp(T, v[0].x, v[1].x, v[2].x, v[3].x, v[4].x, v[5].x, v[6].x, v[7].x);
-    s_new = S.scale * tri_lerp(T, v[0].y, v[1].y, v[2].y, v[3].y, v[4].y, v[5].y, v[6].y, v[7].y);
+    const float4 *b = G.blk2 + 4 * tri_cell(G, T);
+    float4 q0 = __ldg(b), q1 = __ldg(b + 1), q2 = __ldg(b + 2), q3 = __ldg(b + 3);   // one 64-byte brick
+    s_old = S.scale * tri_lerp(T, q0.x, q0.z, q1.x, q1.z, q2.x, q2.z, q3.x, q3.z);
+    s_new = S.scale * tri_lerp(T, q0.y, q0.w, q1.y, q1.w, q2.y, q2.w, q3.y, q3.w);
 }
 // state `new` only
 __device__ __forceinline__ float lookup_sigma1(const SceneK &S, const GridK &G, const Tri &T) {
     if (!T.inside) return 0.f;
-    size_t r[4];
-    tri_rows(G, T, r);
-    float v[8];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        v[2 * k] = __ldg(G.sig1 + r[k] + T.x0);
-        v[2 * k + 1] = __ldg(G.sig1 + r[k] + T.x1);
-    }
-    return S.scale * tri_lerp(T, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+    const float4 *b = G.blk1 + 2 * tri_cell(G, T);
+    float4 q0 = __ldg(b), q1 = __ldg(b + 1);                                         // one 32-byte brick
+    return S.scale * tri_lerp(T, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w);
 }
 // albedo of state s (0 = old, 1 = new)
 __device__ __forceinline__ V3 lookup_albedo(const GridK &G, const Tri &T, int s) {

@@ -29,8 +29,9 @@ cudaError_t launch_vps_backward(const LaunchCfg &cfg, const SceneK &S, const Gri
 cudaError_t launch_film_weights(const LaunchCfg &cfg, const SceneK &S, uint32_t seed, uint32_t spp, float *film_w);
 
 // ---- medium state (rcv_pixel.cu)
-cudaError_t launch_rotate(const LaunchCfg &cfg, const float *sigma_in, const float *albedo_in, size_t nvox, float scale,
-                          float2 *sig2, float *sig1, float4 *alb2, float *block_max, int n_blocks, float *majorants);
+cudaError_t launch_rotate(const LaunchCfg &cfg, const float *sigma_in, const float *albedo_in, int nz, int ny, int nx, float scale,
+                          float2 *sig2, float4 *blk2, float4 *blk1, float4 *alb2, float *block_max, int n_blocks,
+                          float *majorants);
 cudaError_t launch_medium_read(const LaunchCfg &cfg, const float2 *sig2, const float4 *alb2, size_t nvox, int state,
                                float *sigma_out, float *albedo_out);
 

@@ -22,14 +22,13 @@ static inline unsigned grid_for(const LaunchCfg &cfg, uint64_t n_items, int per_
 // majorant (gridvolume max, recomputed by new_params.update()).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_rotate(const float *__restrict__ sigma_in, const float *__restrict__ albedo_in,
-                                                   size_t nvox, float2 *__restrict__ sig2, float *__restrict__ sig1,
-                                                   float4 *__restrict__ alb2, float *__restrict__ block_max) {
+                                                   size_t nvox, float2 *__restrict__ sig2, float4 *__restrict__ alb2,
+                                                   float *__restrict__ block_max) {
     float mx = -inf_();
     for (size_t v = (size_t) blockIdx.x * kBlock + threadIdx.x; v < nvox; v += (size_t) gridDim.x * kBlock) {
         float s_in = __ldg(sigma_in + v);
         float2 s = sig2[v];
         sig2[v] = make_float2(s.y, s_in);
-        sig1[v] = s_in;
         float4 a_new = alb2[2 * v + 1];
         alb2[2 * v] = a_new;
         alb2[2 * v + 1] = make_float4(__ldg(albedo_in + 3 * v), __ldg(albedo_in + 3 * v + 1), __ldg(albedo_in + 3 * v + 2), 0.f);
@@ -57,11 +56,33 @@ __global__ void k_majorant_final(const float *block_max, int n_blocks, float sca
         majorants[1] = scale * mx;
     }
 }
-cudaError_t launch_rotate(const LaunchCfg &cfg, const float *sigma_in, const float *albedo_in, size_t nvox, float scale,
-                          float2 *sig2, float *sig1, float4 *alb2, float *block_max, int n_blocks, float *majorants) {
-    k_rotate<<<n_blocks, kBlock, 0, cfg.stream>>>(sigma_in, albedo_in, nvox, sig2, sig1, alb2, block_max);
+// gather bricks: the 8 corner values of every interpolation cell, contiguous (rcv_device.cuh, GridK)
+__global__ void __launch_bounds__(kBlock) k_build_bricks(const float2 *__restrict__ sig2, int nx, int ny, int nz,
+                                                         float4 *__restrict__ blk2, float4 *__restrict__ blk1) {
+    const size_t ncell = (size_t) (nx + 1) * (ny + 1) * (nz + 1);
+    for (size_t c = (size_t) blockIdx.x * kBlock + threadIdx.x; c < ncell; c += (size_t) gridDim.x * kBlock) {
+        size_t r = c;
+        int cx = (int) (r % (nx + 1)); r /= (nx + 1);
+        int cy = (int) (r % (ny + 1)); r /= (ny + 1);
+        int cz = (int) r;
+        float2 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = __ldg(sig2 + cell_corner(nx, ny, nz, cx, cy, cz, k));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) blk2[4 * c + j] = make_float4(v[2 * j].x, v[2 * j].y, v[2 * j + 1].x, v[2 * j + 1].y);
+        blk1[2 * c] = make_float4(v[0].y, v[1].y, v[2].y, v[3].y);
+        blk1[2 * c + 1] = make_float4(v[4].y, v[5].y, v[6].y, v[7].y);
+    }
+}
+
+cudaError_t launch_rotate(const LaunchCfg &cfg, const float *sigma_in, const float *albedo_in, int nz, int ny, int nx, float scale,
+                          float2 *sig2, float4 *blk2, float4 *blk1, float4 *alb2, float *block_max, int n_blocks,
+                          float *majorants) {
+    size_t nvox = (size_t) nz * ny * nx, ncell = (size_t) (nz + 1) * (ny + 1) * (nx + 1);
+    k_rotate<<<n_blocks, kBlock, 0, cfg.stream>>>(sigma_in, albedo_in, nvox, sig2, alb2, block_max);
     k_majorant_final<<<1, 32, 0, cfg.stream>>>(block_max, n_blocks, scale, majorants);
-    (*cfg.launches) += 2;
+    k_build_bricks<<<grid_for(cfg, ncell, 16), kBlock, 0, cfg.stream>>>(sig2, nx, ny, nz, blk2, blk1);
+    (*cfg.launches) += 3;
     return cudaGetLastError();
 }
 

@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(kBlock) k_vps_simple(const __grid_constant__ S
 #define RCV_WF_BLOCK 128
 #endif
 #ifndef RCV_WF_MINBLOCKS
-#define RCV_WF_MINBLOCKS 5
+#define RCV_WF_MINBLOCKS 4
 #endif
 #ifndef RCV_EVENT_BATCH
 #define RCV_EVENT_BATCH 12

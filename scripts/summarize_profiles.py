@@ -40,6 +40,16 @@ for name in ("twostate", "vps"):
         for k in KEEP:
             if k in hdr:
                 f.write(f"{k},{units[hdr.index(k)]},{vals[hdr.index(k)]}\n")
+    # DRAM traffic per launch of this kernel, consumed by bench.py (roofline.traffic)
+    import json
+    tpath = os.path.join(dst, "traffic.json")
+    tj = json.load(open(tpath)) if os.path.exists(tpath) else {}
+    rd, wr = float(vals[hdr.index("dram__bytes_read.sum")]), float(vals[hdr.index("dram__bytes_write.sum")])
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    rd *= scale[units[hdr.index("dram__bytes_read.sum")]]; wr *= scale[units[hdr.index("dram__bytes_write.sum")]]
+    key = "twostate_primal" if name == "twostate" else "volpathsimple_adjoint"
+    tj[key] = {"dram_bytes": rd + wr, "dram_read": rd, "dram_write": wr, "capture": f"profiles/{tag}_{name}_metrics.csv"}
+    json.dump(tj, open(tpath, "w"), indent=1)
     sass = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(sass.splitlines()))
     hdr = rows[1]
@@ -59,14 +69,4 @@ for name in ("twostate", "vps"):
         for a, c in chunks.items():
             if c[0]:
                 f.write(f"0x{a & 0xfffff:05x},{c[0]},{100.0 * c[0] / total:.2f},{c[1] / c[0]:.1f},{c[2]}\n")
-    # DRAM traffic per launch of this kernel, consumed by bench.py (roofline.traffic)
-    import json
-    tpath = os.path.join(dst, "traffic.json")
-    tj = json.load(open(tpath)) if os.path.exists(tpath) else {}
-    rd, wr = float(vals[hdr.index("dram__bytes_read.sum")]), float(vals[hdr.index("dram__bytes_write.sum")])
-    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
-    rd *= scale[units[hdr.index("dram__bytes_read.sum")]]; wr *= scale[units[hdr.index("dram__bytes_write.sum")]]
-    key = "twostate_primal" if name == "twostate" else "volpathsimple_adjoint"
-    tj[key] = {"dram_bytes": rd + wr, "dram_read": rd, "dram_write": wr, "capture": f"profiles/{tag}_{name}_metrics.csv"}
-    json.dump(tj, open(tpath, "w"), indent=1)
     print(name, "ok")

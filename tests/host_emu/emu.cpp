@@ -17,7 +17,7 @@ namespace {
 
 struct Packed {
     std::vector<float2> sig2;
-    std::vector<float> sig1;
+    std::vector<float4> blk2, blk1;
     std::vector<float4> alb2;
     float maj[2];
     GridK G;
@@ -26,17 +26,30 @@ struct Packed {
 void pack(const rcv_scene_desc &d, const float *so, const float *ao, const float *sn, const float *an, int nz, int ny, int nx,
           Packed &P) {
     size_t n = (size_t) nz * ny * nx;
-    P.sig2.resize(n); P.sig1.resize(n); P.alb2.resize(2 * n);
+    P.sig2.resize(n); P.alb2.resize(2 * n);
     float mo = so[0], mn = sn[0];
     for (size_t v = 0; v < n; ++v) {
         P.sig2[v] = make_float2(so[v], sn[v]);
-        P.sig1[v] = sn[v];
         P.alb2[2 * v] = make_float4(ao[3 * v], ao[3 * v + 1], ao[3 * v + 2], 0.f);
         P.alb2[2 * v + 1] = make_float4(an[3 * v], an[3 * v + 1], an[3 * v + 2], 0.f);
         mo = fmax_(mo, so[v]); mn = fmax_(mn, sn[v]);
     }
     P.maj[0] = d.sigma_t_scale * mo; P.maj[1] = d.sigma_t_scale * mn;
-    P.G.sig2 = P.sig2.data(); P.G.sig1 = P.sig1.data(); P.G.alb2 = P.alb2.data();
+    // gather bricks, as k_build_bricks does on the device
+    size_t ncell = (size_t) (nz + 1) * (ny + 1) * (nx + 1);
+    P.blk2.resize(4 * ncell); P.blk1.resize(2 * ncell);
+    for (size_t c = 0; c < ncell; ++c) {
+        size_t r = c;
+        int cx = (int) (r % (nx + 1)); r /= (nx + 1);
+        int cy = (int) (r % (ny + 1)); r /= (ny + 1);
+        int cz = (int) r;
+        float2 v8[8];
+        for (int k = 0; k < 8; ++k) v8[k] = P.sig2[cell_corner(nx, ny, nz, cx, cy, cz, k)];
+        for (int j = 0; j < 4; ++j) P.blk2[4 * c + j] = make_float4(v8[2 * j].x, v8[2 * j].y, v8[2 * j + 1].x, v8[2 * j + 1].y);
+        P.blk1[2 * c] = make_float4(v8[0].y, v8[1].y, v8[2].y, v8[3].y);
+        P.blk1[2 * c + 1] = make_float4(v8[4].y, v8[5].y, v8[6].y, v8[7].y);
+    }
+    P.G.sig2 = P.sig2.data(); P.G.blk2 = P.blk2.data(); P.G.blk1 = P.blk1.data(); P.G.alb2 = P.alb2.data();
     P.G.nx = nx; P.G.ny = ny; P.G.nz = nz; P.G.majorants = P.maj;
 }
 
