@@ -146,6 +146,12 @@ __global__ void __launch_bounds__(kBlock) k_vps_simple(const __grid_constant__ S
 #ifndef RCV_WF_MINBLOCKS
 #define RCV_WF_MINBLOCKS 4
 #endif
+#ifndef RCV_TS_MINBLOCKS
+#define RCV_TS_MINBLOCKS RCV_WF_MINBLOCKS
+#endif
+#ifndef RCV_VP_MINBLOCKS
+#define RCV_VP_MINBLOCKS RCV_WF_MINBLOCKS
+#endif
 #ifndef RCV_EVENT_BATCH
 #define RCV_EVENT_BATCH 12
 #endif
@@ -237,7 +243,7 @@ __device__ __forceinline__ unsigned long long take_positions(ChunkCursor &cc, un
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_twostates_wavefront(const __grid_constant__ SceneK S,
+__global__ void __launch_bounds__(kWfBlock, RCV_TS_MINBLOCKS) k_twostates_wavefront(const __grid_constant__ SceneK S,
                                                                                  const __grid_constant__ GridK G, float4 *acc_old,
                                                                                  float4 *acc_new, PathQueue Q, Counters *C,
                                                                                  unsigned long long *work) {
@@ -276,7 +282,7 @@ __global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_twostates_wavefront(
 }
 
 template <bool BACKWARD>
-__global__ void __launch_bounds__(kWfBlock, kWfMinBlocks) k_vps_wavefront(const __grid_constant__ SceneK S,
+__global__ void __launch_bounds__(kWfBlock, RCV_VP_MINBLOCKS) k_vps_wavefront(const __grid_constant__ SceneK S,
                                                                            const __grid_constant__ GridK G, GradK D, uint32_t seed,
                                                                            uint32_t spp, uint32_t alt_seed, const float *grad_img,
                                                                            const float *film_w, float4 *accum, PathQueue Q,
