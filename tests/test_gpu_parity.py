@@ -185,3 +185,54 @@ def test_golden_fixture_on_gpu(oracle, gpu_ctx):
     assert rel_l2(gs.cpu().numpy(), ref["grad_sigma_t"]) < GRAD_TOL and rel_l2(ga.cpu().numpy(), ref["grad_albedo"]) < GRAD_TOL
     m = gpu_ctx.majorants()
     assert np.array_equal(np.array(m, np.float32), ref["majorants"])
+
+
+@pytest.mark.parametrize("tracer", [0, 1, 2])
+def test_hg_phase_rr_and_scaled_box(oracle, gpu_ctx, tracer):
+    """HG phase function, active Russian roulette, hide_emitters and a non-unit medium box
+    (janga scales the cube by [1, 1.2, 1.5], experiments.py:41,58): all three schedules vs the oracle."""
+    from recursive_control_variates_b200.scene import SceneConfig, look_at
+    cfg = SceneConfig(width=40, height=28, phase="hg", phase_g=0.877, max_depth=6, rr_depth=2, hide_emitters=True,
+                      bbox_min=(0.0, 0.0, 0.0), bbox_max=(1.0, 1.2, 1.5), env_radiance=(0.9, 1.0, 1.1),
+                      to_world=look_at([2.2, 0.3, 2.4], [0.5, 0.6, 0.75], [0, 1, 0]))
+    d = cfg.to_desc()
+    old, new = media(14)
+    mo, mn = oracle.OracleMedium(d, *old), oracle.OracleMedium(d, *new)
+    gpu_ctx.set_tracer(tracer)
+    gpu_ctx.set_scene(d)
+    gpu_set_states(gpu_ctx, old, new)
+    ao, an = oracle.render_twostates_accum(d, mo, mn, seed=21, spp=1)
+    go, gn = gpu_ctx.render_twostates_accum(seed=21, spp=1)
+    assert np.array_equal(go.cpu().numpy(), ao) and np.array_equal(gn.cpu().numpy(), an)
+    assert np.array_equal(gpu_ctx.render_adjoint_primal_accum(seed=22, spp=1).cpu().numpy(), oracle.vps_render_accum(d, mn, 22, 1))
+    gimg = np.full((d.film_height, d.film_width, 3), 1e-3, np.float32)
+    gs, ga = oracle.vps_backward(d, mn, 23, 3, gimg, threads=1)
+    gpu_ctx.grad_zero(); gpu_ctx.render_backward(23, 3, to_cuda(gimg))
+    ggs, gga = gpu_ctx.grad_read()
+    assert rel_l2(ggs.cpu().numpy(), gs) < GRAD_TOL and rel_l2(gga.cpu().numpy(), ga) < GRAD_TOL
+    gpu_ctx.set_tracer(0)
+
+
+def test_large_config_properties(gpu_ctx):
+    """Size-independent properties at a BASELINE-sized grid (128^3, 256x256, 16 spp): identity H == F,
+    shard invariance, film weights == spp, finite gradients (the oracle would take minutes here)."""
+    from recursive_control_variates_b200.scene import SceneConfig
+    from recursive_control_variates_b200.synthetic import make_medium
+    d = SceneConfig(width=256, height=256).to_desc()
+    gpu_ctx.set_scene(d)
+    new = make_medium(128, "plume", 5e-3)
+    gpu_set_states(gpu_ctx, new, new)
+    H, F = gpu_ctx.render_twostates(seed=1, spp=16)
+    assert np.array_equal(H.cpu().numpy(), F.cpu().numpy())
+    full = gpu_ctx.render_twostates_accum(seed=2, spp=16)
+    part = gpu_ctx.render_twostates_accum(seed=2, spp=16, spp_begin=0, spp_end=5)
+    part = gpu_ctx.render_twostates_accum(seed=2, spp=16, spp_begin=5, spp_end=16, out=part)
+    assert rel_l2(part[1].cpu().numpy(), full[1].cpu().numpy()) < 1e-6
+    w = full[0][..., 3].cpu().numpy()
+    assert abs(w.sum() - 256 * 256 * 16) < 1 and w.min() >= 14
+    g = to_cuda(np.full((256, 256, 3), 1.0 / (256 * 256 * 3), np.float32))
+    gpu_ctx.grad_zero(); gpu_ctx.render_backward(5, 16, g)
+    gs, ga = gpu_ctx.grad_read()
+    assert np.isfinite(gs.cpu().numpy()).all() and np.isfinite(ga.cpu().numpy()).all() and float(gs.abs().sum()) > 0
+    c = gpu_ctx.counters(True)
+    assert int(c[6]) > 0

@@ -106,3 +106,26 @@ def test_volpathsimple_event_machine_backward(oracle, emu, setup):
     assert [int(v) for v in cnt[2:7]] == [int(v) for v in oc[2:7]]
     assert rel_l2(g1, gs) < 1e-5       # float vs double accumulation
     assert rel_l2(g4[..., 0:3], ga) < 1e-5
+
+
+def test_hg_phase_and_shallow_depth(oracle, emu):
+    """Henyey-Greenstein phase function (experiments.py:179-182, g = 0.877) and a small
+    max_depth / rr_depth (Russian roulette active): event machines vs oracle, bit for bit."""
+    from recursive_control_variates_b200.scene import SceneConfig
+    d = SceneConfig(width=24, height=20, phase="hg", phase_g=0.877, max_depth=6, rr_depth=2).to_desc()
+    (so, ao), (sn, an) = media(12)
+    mo, mn = oracle.OracleMedium(d, so, ao), oracle.OracleMedium(d, sn, an)
+    H, W = d.film_height, d.film_width
+    acc_o = np.zeros((H, W, 4), np.float32); acc_n = np.zeros((H, W, 4), np.float32)
+    cnt = np.zeros(8, np.uint64)
+    emu.emu_twostates(C.addressof(d), so, ao, sn, an, *so.shape[:3], 4, 2, 0, acc_o, acc_n, cnt)
+    ref_o, ref_n = oracle.render_twostates_accum(d, mo, mn, 4, 2)
+    assert np.array_equal(acc_o, ref_o) and np.array_equal(acc_n, ref_n)
+    acc = np.zeros((H, W, 4), np.float32); g1 = np.zeros((*sn.shape[:3], 1), np.float32); g4 = np.zeros((*sn.shape[:3], 4), np.float32)
+    emu.emu_vps(C.addressof(d), sn, an, *sn.shape[:3], 6, 2, 0, 0, None, None, acc, g1, g4, cnt)
+    assert np.array_equal(acc, oracle.vps_render_accum(d, mn, 6, 2))
+    gimg = np.full((H, W, 3), 1e-3, np.float32)
+    film_w = oracle.film_weights(d, 9, 2)
+    emu.emu_vps(C.addressof(d), sn, an, *sn.shape[:3], 9, 2, 1, oracle.alt_seed(9), gimg.ctypes.data, film_w.ctypes.data, acc, g1, g4, cnt)
+    gs, ga = oracle.vps_backward(d, mn, 9, 2, gimg, threads=1, film_w=film_w)
+    assert rel_l2(g1, gs) < 1e-5 and rel_l2(g4[..., 0:3], ga) < 1e-5
