@@ -233,7 +233,7 @@ int rcv_ctx_set_stream(rcv_ctx *c, void *stream) {
 }
 int rcv_ctx_set_tracer(rcv_ctx *c, int kind) {
     if (!c) return fail(RCV_ERR_ARG, "null context");
-    if (kind < 0 || kind > 2) return fail(RCV_ERR_ARG, "unknown tracer kind");
+    if (kind < 0 || kind > 3) return fail(RCV_ERR_ARG, "unknown tracer kind");
     c->tracer = kind;
     return RCV_OK;
 }
@@ -311,7 +311,7 @@ static int check_render(rcv_ctx *c, uint32_t spp, uint32_t b, uint32_t e) {
     if (!c->sig2) return fail(RCV_ERR_STATE, "no medium state (call rcv_medium_rotate)");
     if (spp == 0 || b > e || e > spp) return fail(RCV_ERR_ARG, "invalid sample range");
     if ((uint64_t) c->S.W * c->S.H * spp > 0xffffffffull) return fail(RCV_ERR_ARG, "wavefront exceeds 2^32 lanes");
-    if (c->tracer == RCV_TRACER_WAVEFRONT)
+    if (c->tracer == RCV_TRACER_WAVEFRONT || c->tracer == RCV_TRACER_POOL)
         if (int r = ensure_queue(c, b, e)) return r;
     return RCV_OK;
 }

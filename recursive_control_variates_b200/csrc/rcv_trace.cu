@@ -18,6 +18,7 @@
 #include "rcv_twostate_wf.cuh"
 #include "rcv_volpathsimple.cuh"
 #include "rcv_volpathsimple_wf.cuh"
+#include "rcv_pool.cuh"
 
 namespace rcv {
 
@@ -330,6 +331,196 @@ __global__ void __launch_bounds__(kWfBlock, RCV_VP_MINBLOCKS) k_vps_wavefront(co
     counter_flush(C, 6, sk.n_paths);
 }
 
+
+// ===========================================================================
+// POOL schedule: warp-private pools of 64 lane states in shared memory (rcv_pool.cuh)
+// ===========================================================================
+#ifndef RCV_POOL_BLOCK
+#define RCV_POOL_BLOCK 128
+#endif
+#ifndef RCV_POOL_MINBLOCKS
+#define RCV_POOL_MINBLOCKS 4
+#endif
+static constexpr int kPoolBlock = RCV_POOL_BLOCK;
+static constexpr int kPoolWarps = kPoolBlock / 32;
+
+template <int WORDS>
+__host__ __device__ constexpr size_t pool_warp_floats() { return (size_t) WORDS * kPoolSlots + 2 * kPoolSlots / 4; }
+
+template <int MODE>
+__global__ void __launch_bounds__(kPoolBlock, RCV_POOL_MINBLOCKS) k_twostates_pool(const __grid_constant__ SceneK S,
+                                                                                   const __grid_constant__ GridK G, float4 *acc_old,
+                                                                                   float4 *acc_new, PathQueue Q, Counters *C,
+                                                                                   unsigned long long *work) {
+    extern __shared__ float smem[];
+    const unsigned lane = threadIdx.x & 31;
+    float *pw = smem + (threadIdx.x >> 5) * pool_warp_floats<kTsWords>();
+    unsigned char *cls = (unsigned char *) (pw + (size_t) kTsWords * kPoolSlots);
+    unsigned char *list = cls + kPoolSlots;
+    const float mu = combined_majorant<MODE>(G);
+    const float inv_mu = 1.f / mu;
+    const unsigned long long n_total = *Q.count;
+    TsSink sk; sk.acc_old = acc_old; sk.acc_new = acc_new; sk.n_coll = sk.n_scat = sk.n_paths = 0;
+    ChunkCursor cc; cc.next = 0; cc.end = 0; cc.more = true;
+    cls[lane] = EV_INIT; cls[lane + 32] = EV_INIT;
+    __syncwarp();
+    while (true) {
+        const int c0 = cls[lane], c1 = cls[lane + 32];
+        const unsigned coll_lo = __ballot_sync(0xffffffffu, c0 == EV_COLL), coll_hi = __ballot_sync(0xffffffffu, c1 == EV_COLL);
+        const unsigned scat_lo = __ballot_sync(0xffffffffu, c0 == EV_SCAT), scat_hi = __ballot_sync(0xffffffffu, c1 == EV_SCAT);
+        const unsigned slow_lo = __ballot_sync(0xffffffffu, c0 == EV_SLOW || (c0 == EV_INIT && cc.more));
+        const unsigned slow_hi = __ballot_sync(0xffffffffu, c1 == EV_SLOW || (c1 == EV_INIT && cc.more));
+        const int n_coll = __popc(coll_lo) + __popc(coll_hi), n_scat = __popc(scat_lo) + __popc(scat_hi);
+        const int n_slow = __popc(slow_lo) + __popc(slow_hi);
+        if (n_coll == 0 && n_scat == 0 && n_slow == 0) break;
+        const int sel = pool_pick(n_coll, n_scat, n_slow);
+        TsLane ln;
+        if (sel == EV_COLL) {
+            const int s = pool_select(coll_lo, coll_hi, list);
+            if (s >= 0) {
+                ts_pool_load_hot(pw, s, ln);
+                ln.ev = EV_COLL;
+                ts_collide<MODE>(S, G, mu, inv_mu, ln, sk);
+                ts_pool_store_coll(pw, s, ln);
+                cls[s] = (unsigned char) ln.ev;
+            }
+        } else if (sel == EV_SCAT) {
+            const int s = pool_select(scat_lo, scat_hi, list);
+            if (s >= 0) {
+                ts_pool_load_hot(pw, s, ln); ts_pool_load_cold(pw, s, ln);
+                ln.ev = EV_SCAT;
+                ts_scatter<MODE>(S, G, ln, sk);
+                ts_pool_store_all(pw, s, ln);
+                cls[s] = (unsigned char) ln.ev;
+            }
+        } else {
+            const int s = pool_select(slow_lo, slow_hi, list);
+            ln.ev = EV_INIT;
+            bool loaded = false;
+            if (s >= 0 && cls[s] == EV_SLOW) {
+                ts_pool_load_hot(pw, s, ln); ts_pool_load_cold(pw, s, ln);
+                ln.ev = EV_SLOW;
+                ts_slow<MODE>(S, ln, sk);
+                loaded = true;
+            }
+            // refill the slots that are (now) empty from the record queue
+            unsigned m_need = __ballot_sync(0xffffffffu, s >= 0 && ln.ev == EV_INIT);
+            if (m_need && cc.more) {
+                unsigned long long pos = take_positions(cc, work, n_total, m_need);
+                if (pos != ~0ull) { ts_load(ln, Q, pos); loaded = true; }
+            }
+            if (s >= 0) {
+                if (loaded && ln.ev != EV_INIT) ts_pool_store_all(pw, s, ln);
+                cls[s] = (unsigned char) ln.ev;
+            }
+        }
+        __syncwarp();
+    }
+    counter_flush(C, MODE == 0 ? 0 : 2, sk.n_coll);
+    counter_flush(C, MODE == 0 ? 1 : 3, sk.n_scat);
+    counter_flush(C, 6, sk.n_paths);
+}
+
+template <bool BACKWARD>
+__global__ void __launch_bounds__(kPoolBlock, RCV_POOL_MINBLOCKS) k_vps_pool(const __grid_constant__ SceneK S,
+                                                                             const __grid_constant__ GridK G, GradK D, uint32_t seed,
+                                                                             uint32_t spp, uint32_t alt_seed, const float *grad_img,
+                                                                             const float *film_w, float4 *accum, PathQueue Q,
+                                                                             Counters *C, unsigned long long *work) {
+    extern __shared__ float smem[];
+    const unsigned lane = threadIdx.x & 31;
+    float *pw = smem + (threadIdx.x >> 5) * pool_warp_floats<kVpWords>();
+    unsigned char *cls = (unsigned char *) (pw + (size_t) kVpWords * kPoolSlots);
+    unsigned char *list = cls + kPoolSlots;
+    const float mu = __ldg(G.majorants + 1);
+    const float inv_mu = 1.f / mu;
+    const unsigned long long n_total = *Q.count;
+    VpSink sk;
+    sk.accum = accum; sk.D = D; sk.grad_img = grad_img; sk.film_w = film_w;
+    sk.seed = seed; sk.spp = spp; sk.alt_seed = alt_seed;
+    sk.cnt.coll = sk.cnt.scat = sk.cnt.g_sig = sk.cnt.g_alb = 0; sk.n_paths = 0;
+    ChunkCursor cc; cc.next = 0; cc.end = 0; cc.more = true;
+    cls[lane] = EV_INIT; cls[lane + 32] = EV_INIT;
+    __syncwarp();
+    while (true) {
+        const int c0 = cls[lane], c1 = cls[lane + 32];
+        const unsigned coll_lo = __ballot_sync(0xffffffffu, c0 == EV_COLL), coll_hi = __ballot_sync(0xffffffffu, c1 == EV_COLL);
+        const unsigned scat_lo = __ballot_sync(0xffffffffu, c0 == EV_SCAT), scat_hi = __ballot_sync(0xffffffffu, c1 == EV_SCAT);
+        const unsigned slow_lo = __ballot_sync(0xffffffffu, c0 == EV_SLOW || c0 == EV_RESUME || (c0 == EV_INIT && cc.more));
+        const unsigned slow_hi = __ballot_sync(0xffffffffu, c1 == EV_SLOW || c1 == EV_RESUME || (c1 == EV_INIT && cc.more));
+        const int n_coll = __popc(coll_lo) + __popc(coll_hi), n_scat = __popc(scat_lo) + __popc(scat_hi);
+        const int n_slow = __popc(slow_lo) + __popc(slow_hi);
+        if (n_coll == 0 && n_scat == 0 && n_slow == 0) break;
+        const int sel = pool_pick(n_coll, n_scat, n_slow);
+        VpLane ln;
+        if (sel == EV_COLL) {
+            const int s = pool_select(coll_lo, coll_hi, list);
+            if (s >= 0) {
+                vp_pool_load_hot(pw, s, ln);
+                ln.ev = EV_COLL;
+                vp_collide<BACKWARD>(S, G, mu, inv_mu, ln, sk);
+                vp_pool_store_coll(pw, s, ln);
+                cls[s] = (unsigned char) ln.ev;
+            }
+        } else if (sel == EV_SCAT) {
+            const int s = pool_select(scat_lo, scat_hi, list);
+            if (s >= 0) {
+                vp_pool_load_hot(pw, s, ln); vp_pool_load_cold(pw, s, ln);
+                ln.ev = EV_SCAT;
+                vp_vertex<BACKWARD>(S, G, ln, sk);
+                vp_pool_store_all(pw, s, ln);
+                cls[s] = (unsigned char) ((BACKWARD && ln.ev == EV_INIT && (ln.flags & VF_PASS2)) ? EV_RESUME : ln.ev);
+            }
+        } else {
+            const int s = pool_select(slow_lo, slow_hi, list);
+            ln.ev = EV_INIT; ln.flags = 0;
+            const int c = (s >= 0) ? (int) cls[s] : EV_INIT;
+            bool loaded = false;
+            if (s >= 0 && (c == EV_SLOW || c == EV_RESUME)) {
+                vp_pool_load_hot(pw, s, ln); vp_pool_load_cold(pw, s, ln);
+                loaded = true;
+                if (c == EV_SLOW) { ln.ev = EV_SLOW; vp_slow<BACKWARD>(S, ln, sk); }
+                else { ln.ev = EV_INIT; }
+            }
+            // lanes that finished pass 1 resume as pass 2; empty slots take the next record
+            const bool resume = BACKWARD && s >= 0 && ln.ev == EV_INIT && (ln.flags & VF_PASS2);
+            if (resume) vp_load(ln, sk, Q, ln.qpos, true);
+            unsigned m_need = __ballot_sync(0xffffffffu, s >= 0 && ln.ev == EV_INIT && !resume);
+            if (m_need && cc.more) {
+                unsigned long long pos = take_positions(cc, work, n_total, m_need);
+                if (pos != ~0ull) { vp_load(ln, sk, Q, pos, false); loaded = true; }
+            }
+            if (s >= 0) {
+                if (loaded && ln.ev != EV_INIT) vp_pool_store_all(pw, s, ln);
+                cls[s] = (unsigned char) ln.ev;
+            }
+        }
+        __syncwarp();
+    }
+    counter_flush(C, 2, sk.cnt.coll);
+    counter_flush(C, 3, sk.cnt.scat);
+    counter_flush(C, 4, sk.cnt.g_sig);
+    counter_flush(C, 5, sk.cnt.g_alb);
+    counter_flush(C, 6, sk.n_paths);
+}
+
+// launch a pool kernel: dynamic shared memory opt-in, persistent grid
+template <typename K, typename... Args>
+static cudaError_t launch_pool(const LaunchCfg &cfg, K kernel, size_t smem_bytes, uint64_t n_items, Args... args) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_bytes);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kPoolBlock, smem_bytes);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    uint64_t want = (n_items + (uint64_t) kPoolWarps * kPoolSlots - 1) / ((uint64_t) kPoolWarps * kPoolSlots);
+    uint64_t b = (uint64_t) per_sm * cfg.sm_count;
+    if (b > want) b = want;
+    if (b < 1) b = 1;
+    kernel<<<(unsigned) b, kPoolBlock, smem_bytes, cfg.stream>>>(args...);
+    return cudaGetLastError();
+}
+
 // ===========================================================================
 // launchers
 // ===========================================================================
@@ -350,15 +541,21 @@ template <int MODE>
 static cudaError_t launch_twostates_mode(const LaunchCfg &cfg, const SceneK &S, const GridK &G, uint32_t seed, uint32_t spp,
                                          uint32_t spp_begin, uint32_t ns, uint64_t n_local, float4 *acc_old, float4 *acc_new) {
     cudaError_t e;
-    if (cfg.tracer == 0) {
+    if (cfg.tracer == 0 || cfg.tracer == 3) {
         if ((e = cudaMemsetAsync(cfg.work_counter, 0, sizeof(unsigned long long), cfg.stream)) != cudaSuccess) return e;
         if ((e = cudaMemsetAsync(cfg.queue.count, 0, sizeof(unsigned long long), cfg.stream)) != cudaSuccess) return e;
         k_twostates_raygen<MODE><<<(unsigned) ((n_local + kBlock - 1) / kBlock), kBlock, 0, cfg.stream>>>(
             S, seed, spp, spp_begin, ns, n_local, acc_old, acc_new, cfg.queue, cfg.counters);
-        unsigned blocks;
-        if ((e = persistent_grid(cfg, k_twostates_wavefront<MODE>, kWfBlock, n_local, blocks)) != cudaSuccess) return e;
-        k_twostates_wavefront<MODE><<<blocks, kWfBlock, 0, cfg.stream>>>(S, G, acc_old, acc_new, cfg.queue, cfg.counters,
-                                                                         cfg.work_counter);
+        if (cfg.tracer == 3) {
+            e = launch_pool(cfg, k_twostates_pool<MODE>, kPoolWarps * pool_warp_floats<kTsWords>() * sizeof(float), n_local, S, G,
+                            acc_old, acc_new, cfg.queue, cfg.counters, cfg.work_counter);
+            if (e != cudaSuccess) return e;
+        } else {
+            unsigned blocks;
+            if ((e = persistent_grid(cfg, k_twostates_wavefront<MODE>, kWfBlock, n_local, blocks)) != cudaSuccess) return e;
+            k_twostates_wavefront<MODE><<<blocks, kWfBlock, 0, cfg.stream>>>(S, G, acc_old, acc_new, cfg.queue, cfg.counters,
+                                                                             cfg.work_counter);
+        }
         (*cfg.launches) += 2;
     } else {
         int persistent = cfg.tracer == 2;
@@ -394,15 +591,21 @@ static cudaError_t launch_vps(const LaunchCfg &cfg, const SceneK &S, const GridK
     uint64_t n_local = (uint64_t) S.W * S.H * ns;
     if (n_local == 0) return cudaSuccess;
     cudaError_t e;
-    if (cfg.tracer == 0) {
+    if (cfg.tracer == 0 || cfg.tracer == 3) {
         if ((e = cudaMemsetAsync(cfg.work_counter, 0, sizeof(unsigned long long), cfg.stream)) != cudaSuccess) return e;
         if ((e = cudaMemsetAsync(cfg.queue.count, 0, sizeof(unsigned long long), cfg.stream)) != cudaSuccess) return e;
         k_vps_raygen<BACKWARD><<<(unsigned) ((n_local + kBlock - 1) / kBlock), kBlock, 0, cfg.stream>>>(
             S, seed, spp, spp_begin, ns, n_local, accum, cfg.queue, cfg.counters);
-        unsigned blocks;
-        if ((e = persistent_grid(cfg, k_vps_wavefront<BACKWARD>, kWfBlock, n_local, blocks)) != cudaSuccess) return e;
-        k_vps_wavefront<BACKWARD><<<blocks, kWfBlock, 0, cfg.stream>>>(S, G, D, seed, spp, alt_seed, grad_img, film_w, accum, cfg.queue,
-                                                                       cfg.counters, cfg.work_counter);
+        if (cfg.tracer == 3) {
+            e = launch_pool(cfg, k_vps_pool<BACKWARD>, kPoolWarps * pool_warp_floats<kVpWords>() * sizeof(float), n_local, S, G, D, seed,
+                            spp, alt_seed, grad_img, film_w, accum, cfg.queue, cfg.counters, cfg.work_counter);
+            if (e != cudaSuccess) return e;
+        } else {
+            unsigned blocks;
+            if ((e = persistent_grid(cfg, k_vps_wavefront<BACKWARD>, kWfBlock, n_local, blocks)) != cudaSuccess) return e;
+            k_vps_wavefront<BACKWARD><<<blocks, kWfBlock, 0, cfg.stream>>>(S, G, D, seed, spp, alt_seed, grad_img, film_w, accum,
+                                                                           cfg.queue, cfg.counters, cfg.work_counter);
+        }
         (*cfg.launches) += 2;
     } else {
         int persistent = cfg.tracer == 2;

@@ -25,7 +25,7 @@ def setup(oracle, gpu_ctx):
     return dict(cfg=cfg, desc=desc, old=old, new=new, mo=mo, mn=mn)
 
 
-@pytest.mark.parametrize("tracer", [0, 1])
+@pytest.mark.parametrize("tracer", [0, 1, 2, 3])
 def test_twostates_per_lane_bit_exact(oracle, gpu_ctx, setup, tracer):
     gpu_ctx.set_tracer(tracer)
     d = setup["desc"]
@@ -79,7 +79,7 @@ def test_spp_sharding_invariance(gpu_ctx, setup):
     assert np.array_equal(acc[0][..., 3].cpu().numpy(), full_o[..., 3].cpu().numpy())
 
 
-@pytest.mark.parametrize("tracer", [0, 1])
+@pytest.mark.parametrize("tracer", [0, 1, 2, 3])
 def test_volpathsimple_primal_bit_exact(oracle, gpu_ctx, setup, tracer):
     gpu_ctx.set_tracer(tracer)
     d = setup["desc"]
@@ -92,7 +92,9 @@ def test_volpathsimple_primal_bit_exact(oracle, gpu_ctx, setup, tracer):
     gpu_ctx.set_tracer(0)
 
 
-def test_volpathsimple_backward(oracle, gpu_ctx, setup):
+@pytest.mark.parametrize("tracer", [0, 1, 3])
+def test_volpathsimple_backward(oracle, gpu_ctx, setup, tracer):
+    gpu_ctx.set_tracer(tracer)
     d = setup["desc"]
     rng = np.random.default_rng(0)
     grad_img = (rng.standard_normal((d.film_height, d.film_width, 3)) / (d.film_height * d.film_width * 3)).astype(np.float32)
@@ -107,6 +109,7 @@ def test_volpathsimple_backward(oracle, gpu_ctx, setup):
     assert rel_l2(ggs.cpu().numpy(), gs) < GRAD_TOL
     assert rel_l2(gga.cpu().numpy(), ga) < GRAD_TOL
     assert rel_l2(ggs.cpu().numpy(), gs) < 1e-4    # float atomics vs double accumulation
+    gpu_ctx.set_tracer(0)
 
 
 def test_backward_sharding(gpu_ctx, setup):
@@ -187,7 +190,7 @@ def test_golden_fixture_on_gpu(oracle, gpu_ctx):
     assert np.array_equal(np.array(m, np.float32), ref["majorants"])
 
 
-@pytest.mark.parametrize("tracer", [0, 1, 2])
+@pytest.mark.parametrize("tracer", [0, 1, 2, 3])
 def test_hg_phase_rr_and_scaled_box(oracle, gpu_ctx, tracer):
     """HG phase function, active Russian roulette, hide_emitters and a non-unit medium box
     (janga scales the cube by [1, 1.2, 1.5], experiments.py:41,58): all three schedules vs the oracle."""
