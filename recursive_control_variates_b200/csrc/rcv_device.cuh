@@ -456,6 +456,38 @@ __device__ __forceinline__ V3 lookup_albedo(const GridK &G, const Tri &T, int s)
 }
 
 // ----------------------------------------------------------------------------
+// speculative L2 prefetch of the NEXT tentative collision's gather brick.
+// After a null collision the lane continues from p along d; its next free-flight
+// distance depends only on its random stream (`skip` draws are consumed before the
+// distance sample), not on the lookup that is still in flight.  The stream is
+// advanced on a copy; nothing observable changes (results are bit-identical with
+// or without the prefetch).
+// ----------------------------------------------------------------------------
+#ifndef RCV_PREFETCH
+#define RCV_PREFETCH 1
+#endif
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void) p;
+#endif
+}
+template <bool TWO>
+__device__ __forceinline__ void prefetch_next_brick(const SceneK &S, const GridK &G, float inv_mu, Pcg rng, int skip, V3 p, V3 d) {
+#if RCV_PREFETCH
+    for (int i = 0; i < skip; ++i) (void) pcg_u32(rng);
+    float u = pcg_f32(rng);
+    float t = (-spec_log(1.f - u)) * inv_mu;
+    Tri T = tri_setup(S, G, ray_at(p, d, t));
+    if (T.inside) {
+        if (TWO) prefetch_l2(G.blk2 + 4 * tri_cell(G, T));
+        else prefetch_l2(G.blk1 + 2 * tri_cell(G, T));
+    }
+#endif
+}
+
+// ----------------------------------------------------------------------------
 // sensor: lane -> (rng, camera ray, film pixel)
 // ----------------------------------------------------------------------------
 struct Lane {

@@ -209,6 +209,7 @@ __device__ __forceinline__ void ts_collide(const SceneK &S, const GridK &G, floa
             ln.tr_new = ln.tr_new * ((mu != 0.f) ? (sn_n * inv_mu) : sn_n);
             if (!(ln.tr_new != 0.f || ln.tr_old != 0.f)) { ln.flags |= F_POST_NEE; ln.ev = EV_SLOW; return; }
             ln.total += m.t;
+            prefetch_next_brick<true>(S, G, inv_mu, ln.rng, 0, ln.no, ln.nd);
             return;
         }
         float sp_new = m.sn * inv_mu, sp_old = m.so * inv_mu;         // :223-225
@@ -221,6 +222,7 @@ __device__ __forceinline__ void ts_collide(const SceneK &S, const GridK &G, floa
             ln.o = m.p;
             ln.si_t = ln.si_t - m.t;
             ln.thr_new = ln.thr_new * w_new; ln.thr_old = ln.thr_old * w_old;
+            prefetch_next_brick<true>(S, G, inv_mu, ln.rng, 1, ln.o, ln.d);      // next step: loop-head draw, then the distance
             return;
         }
         ln.depth += 1;                                                // :249

@@ -271,7 +271,8 @@ __device__ __forceinline__ void vp_collide(const SceneK &S, const GridK &G, floa
         ln.tr_acc = ln.tr_acc * tr;                                   // :508
         ln.ro = m.p;                                                  // :510
         ln.rmaxt = ln.rmaxt - m.t;
-        if (!(ln.tr_acc != 0.f)) { ln.flags |= VF_POSTNEE; ln.ev = EV_SLOW; }   // :515
+        if (!(ln.tr_acc != 0.f)) { ln.flags |= VF_POSTNEE; ln.ev = EV_SLOW; return; }   // :515
+        prefetch_next_brick<false>(S, G, inv_mu, ln.rng, 0, ln.ro, ln.nd);
         return;
     }
     // sample_real_interaction step (:360-380)
@@ -283,6 +284,7 @@ __device__ __forceinline__ void vp_collide(const SceneK &S, const GridK &G, floa
     ln.ro = ln.ro + ln.d * m.t;                                       // :378-380
     ln.rmaxt = ln.rmaxt - m.t;
     ln.running_t = ln.running_t + m.t;
+    prefetch_next_brick<false>(S, G, inv_mu, ln.rng, 0, ln.ro, ln.d);
 }
 
 // the batched slow step (see the header comment)
