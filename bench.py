@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--res", type=int, default=WORKLOAD["width"])
     ap.add_argument("--spp", type=int, default=WORKLOAD["spp_per_gpu"], help="samples per pixel per GPU")
     ap.add_argument("--kind", default=WORKLOAD["kind"])
-    ap.add_argument("--tracer", type=int, default=0)
+    ap.add_argument("--tracer", type=int, default=3, help="3 pool (default), 0 wavefront, 1 simple, 2 batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-spp", type=int, default=0, help="spp range of the CPU sample (0 = auto: ~15 s of CPU work)")
@@ -363,7 +363,7 @@ def run_ours(a):
                "config": {"workload": workload_name(a, n_gpus), "grid": a.grid, "film": [W, H], "spp_total": spp_total,
                           "spp_per_gpu": a.spp, "paths_per_step": paths_per_step, "parallelism": f"spp-shard x{n_gpus}",
                           "l2": "inputs larger than L2 (two-state grids %d MiB)" % (a.grid ** 3 * 40 // 2 ** 20),
-                          "tracer": "persistent" if a.tracer == 0 else "simple", "loss_last": float(loss.item())},
+                          "tracer": {0: "wavefront", 1: "simple", 2: "batch", 3: "pool"}[a.tracer], "loss_last": float(loss.item())},
                "clocks": clocks, "gpu_launches": int(cnt[7]), "roofline": roofline, "kernels": kernels,
                "e2e": e2e, "cpu_baseline": cpu}
         print(json.dumps(out))

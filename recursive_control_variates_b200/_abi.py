@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("RCV_B200_LIB") or os.path.join(_HERE, "librcv_b200.so
 RCV_PHASE_ISOTROPIC, RCV_PHASE_HG = 0, 1
 RCV_ADJOINT_VOLPATHSIMPLE = 0
 RCV_LOSS_L1, RCV_LOSS_L2 = 0, 1
-RCV_TRACER_WAVEFRONT, RCV_TRACER_SIMPLE = 0, 1
+RCV_TRACER_WAVEFRONT, RCV_TRACER_SIMPLE, RCV_TRACER_BATCH, RCV_TRACER_POOL = 0, 1, 2, 3
 
 
 class SceneDesc(C.Structure):

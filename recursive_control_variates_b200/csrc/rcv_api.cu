@@ -4,6 +4,7 @@
 // except in the *_host functions.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -37,7 +38,9 @@ struct rcv_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     int sm_count = 148;
-    int tracer = RCV_TRACER_WAVEFRONT;
+    int tracer = RCV_TRACER_POOL;
+    bool l2_persist = false;      // pin the d sigma_t grid in L2 while the adjoint runs (RCV_L2_PERSIST=1)
+    size_t l2_persist_max = 0, l2_window_max = 0;
     bool has_scene = false;
     rcv_scene_desc desc{};
     SceneK S{};
@@ -202,6 +205,10 @@ int rcv_ctx_create(int device, void *stream, rcv_ctx **out) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
+    c->l2_persist_max = (size_t) prop.persistingL2CacheMaxSize;
+    c->l2_window_max = (size_t) prop.accessPolicyMaxWindowSize;
+    if (const char *e = getenv("RCV_L2_PERSIST")) c->l2_persist = atoi(e) != 0;
+    if (c->l2_persist && c->l2_persist_max > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, c->l2_persist_max);
     CK(cudaMalloc(&c->counters, sizeof(Counters)));
     CK(cudaMemset(c->counters, 0, sizeof(Counters)));
     CK(cudaMalloc(&c->work, sizeof(unsigned long long)));
@@ -377,8 +384,26 @@ int rcv_render_backward(rcv_ctx *c, int adjoint_kind, uint32_t seed_grad, uint32
     LaunchCfg cfg = c->cfg();
     CK(launch_film_weights(cfg, c->S, seed_grad, spp_grad, c->film_w));
     GradK D = c->gradk();
+    const bool pin = c->l2_persist && c->l2_persist_max > 0 && c->l2_window_max > 0;
+    if (pin) {
+        // L2 access-policy window over the d sigma_t grid: the adjoint's scattered reductions hit L2
+        cudaStreamAttrValue a{};
+        size_t bytes = c->nvox * sizeof(float);
+        if (bytes > c->l2_window_max) bytes = c->l2_window_max;
+        a.accessPolicyWindow.base_ptr = (void *) D.gsig;
+        a.accessPolicyWindow.num_bytes = bytes;
+        a.accessPolicyWindow.hitRatio = bytes <= c->l2_persist_max ? 1.f : (float) c->l2_persist_max / (float) bytes;
+        a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        CK(cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &a));
+    }
     CK(launch_vps_backward(cfg, c->S, c->gridk(), D, seed_grad, spp_grad, spp_begin, spp_end, alt_seed_for(seed_grad), grad_img,
                            c->film_w));
+    if (pin) {
+        cudaStreamAttrValue a{};
+        a.accessPolicyWindow.num_bytes = 0;
+        CK(cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &a));
+    }
     return RCV_OK;
 }
 

@@ -424,11 +424,24 @@ __device__ __forceinline__ size_t tri_voxel(const GridK &G, const Tri &T, int k)
     return ((size_t) z * G.ny + y) * G.nx + x;
 }
 
+// brick loads: read-only; with RCV_BRICK_STREAMING they are marked evict-first in L2 (ld.global.cs) so that
+// the brick stream (0.5 - 1 GB at 256^3, no reuse) does not evict the gradient grid the adjoint reduces into
+#ifndef RCV_BRICK_STREAMING
+#define RCV_BRICK_STREAMING 0
+#endif
+__device__ __forceinline__ float4 ld_brick(const float4 *p) {
+#if RCV_BRICK_STREAMING && defined(__CUDA_ARCH__)
+    return __ldcs(p);
+#else
+    return __ldg(p);
+#endif
+}
+
 // both states' sigma_t (scale * grid) with one gather of 8 float2
 __device__ __forceinline__ void lookup_sigma2(const SceneK &S, const GridK &G, const Tri &T, float &s_old, float &s_new) {
     if (!T.inside) { s_old = 0.f; s_new = 0.f; return; }
     const float4 *b = G.blk2 + 4 * tri_cell(G, T);
-    float4 q0 = __ldg(b), q1 = __ldg(b + 1), q2 = __ldg(b + 2), q3 = __ldg(b + 3);   // one 64-byte brick
+    float4 q0 = ld_brick(b), q1 = ld_brick(b + 1), q2 = ld_brick(b + 2), q3 = ld_brick(b + 3);   // one 64-byte brick
     s_old = S.scale * tri_lerp(T, q0.x, q0.z, q1.x, q1.z, q2.x, q2.z, q3.x, q3.z);
     s_new = S.scale * tri_lerp(T, q0.y, q0.w, q1.y, q1.w, q2.y, q2.w, q3.y, q3.w);
 }
@@ -436,7 +449,7 @@ __device__ __forceinline__ void lookup_sigma2(const SceneK &S, const GridK &G, c
 __device__ __forceinline__ float lookup_sigma1(const SceneK &S, const GridK &G, const Tri &T) {
     if (!T.inside) return 0.f;
     const float4 *b = G.blk1 + 2 * tri_cell(G, T);
-    float4 q0 = __ldg(b), q1 = __ldg(b + 1);                                         // one 32-byte brick
+    float4 q0 = ld_brick(b), q1 = ld_brick(b + 1);                                   // one 32-byte brick
     return S.scale * tri_lerp(T, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w);
 }
 // albedo of state s (0 = old, 1 = new)
@@ -464,7 +477,7 @@ __device__ __forceinline__ V3 lookup_albedo(const GridK &G, const Tri &T, int s)
 // or without the prefetch).
 // ----------------------------------------------------------------------------
 #ifndef RCV_PREFETCH
-#define RCV_PREFETCH 1
+#define RCV_PREFETCH 0   // measured slower on B200 (profiles/README.md): the extra instructions cost more than the latency they hide
 #endif
 __device__ __forceinline__ void prefetch_l2(const void *p) {
 #if defined(__CUDA_ARCH__)

@@ -37,7 +37,7 @@ def test_twostates_per_lane_bit_exact(oracle, gpu_ctx, setup, tracer):
     assert np.array_equal(gn.cpu().numpy(), an), "new-state radiance differs from the oracle"
     assert int(oc[0]) == int(gc[0]) and int(oc[1]) == int(gc[1]), (oc, gc)
     assert int(gc[6]) == d.film_width * d.film_height
-    gpu_ctx.set_tracer(0)
+    gpu_ctx.set_tracer(3)
 
 
 def test_majorants(oracle, gpu_ctx, setup):
@@ -89,7 +89,7 @@ def test_volpathsimple_primal_bit_exact(oracle, gpu_ctx, setup, tracer):
     oc, gc = oracle.counters(True), gpu_ctx.counters(True)
     assert np.array_equal(g.cpu().numpy(), a)
     assert int(oc[2]) == int(gc[2]) and int(oc[3]) == int(gc[3]), (oc, gc)
-    gpu_ctx.set_tracer(0)
+    gpu_ctx.set_tracer(3)
 
 
 @pytest.mark.parametrize("tracer", [0, 1, 3])
@@ -109,7 +109,7 @@ def test_volpathsimple_backward(oracle, gpu_ctx, setup, tracer):
     assert rel_l2(ggs.cpu().numpy(), gs) < GRAD_TOL
     assert rel_l2(gga.cpu().numpy(), ga) < GRAD_TOL
     assert rel_l2(ggs.cpu().numpy(), gs) < 1e-4    # float atomics vs double accumulation
-    gpu_ctx.set_tracer(0)
+    gpu_ctx.set_tracer(3)
 
 
 def test_backward_sharding(gpu_ctx, setup):
@@ -213,7 +213,7 @@ def test_hg_phase_rr_and_scaled_box(oracle, gpu_ctx, tracer):
     gpu_ctx.grad_zero(); gpu_ctx.render_backward(23, 3, to_cuda(gimg))
     ggs, gga = gpu_ctx.grad_read()
     assert rel_l2(ggs.cpu().numpy(), gs) < GRAD_TOL and rel_l2(gga.cpu().numpy(), ga) < GRAD_TOL
-    gpu_ctx.set_tracer(0)
+    gpu_ctx.set_tracer(3)
 
 
 def test_large_config_properties(gpu_ctx):
