@@ -63,6 +63,9 @@ struct rcv_ctx {
     size_t film_w_pix = 0;
     PathQueue queue{nullptr, nullptr, nullptr, nullptr};
     size_t queue_cap = 0;
+    float4 *arena = nullptr;      // vertex records of the adjoint: slots x (max_depth + 1) x 64 B
+    size_t arena_records = 0;
+    uint32_t vcap = 0;
     double *loss_partial = nullptr;
     int n_partial = 0;
     // state of rcv_cv_iteration_host
@@ -81,6 +84,7 @@ struct rcv_ctx {
         LaunchCfg c;
         c.stream = stream; c.sm_count = sm_count; c.tracer = tracer;
         c.counters = counters; c.work_counter = work; c.launches = &launches; c.queue = queue;
+        c.arena = arena; c.vcap = vcap;
         return c;
     }
     GradK gradk() const {
@@ -167,6 +171,18 @@ int ensure_queue(rcv_ctx *c, uint32_t spp_begin, uint32_t spp_end) {
     return RCV_OK;
 }
 
+// vertex-record arena of the vertex-list adjoint: one slot of (max_depth + 1) records per lane in flight
+int ensure_arena(rcv_ctx *c) {
+    c->vcap = (uint32_t) c->S.max_depth + 1u;
+    size_t need = vps_backward_slots(c->cfg()) * (size_t) c->vcap;
+    if (need > c->arena_records) {
+        cudaFree(c->arena); c->arena = nullptr; c->arena_records = 0;
+        CK(cudaMalloc(&c->arena, need * 4 * sizeof(float4)));
+        c->arena_records = need;
+    }
+    return RCV_OK;
+}
+
 int ensure_film_w(rcv_ctx *c) {
     size_t npix = (size_t) c->S.W * c->S.H;
     if (c->film_w_pix != npix) {
@@ -225,7 +241,7 @@ int rcv_ctx_destroy(rcv_ctx *c) {
     cudaSetDevice(c->device);
     free_medium(c);
     cudaFree(c->counters); cudaFree(c->work); cudaFree(c->majorants); cudaFree(c->film_w); cudaFree(c->loss_partial);
-    cudaFree(c->queue.r0); cudaFree(c->queue.r1); cudaFree(c->queue.r2); cudaFree(c->queue.count);
+    cudaFree(c->queue.r0); cudaFree(c->queue.r1); cudaFree(c->queue.r2); cudaFree(c->queue.count); cudaFree(c->arena);
     auto &E = c->e2e;
     cudaFree(E.sigma); cudaFree(E.albedo); cudaFree(E.ref); cudaFree(E.acc); cudaFree(E.HF); cudaFree(E.cv);
     cudaFree(E.grad_img); cudaFree(E.loss); cudaFree(E.g_sigma); cudaFree(E.g_albedo);
@@ -381,7 +397,13 @@ int rcv_render_backward(rcv_ctx *c, int adjoint_kind, uint32_t seed_grad, uint32
     if (adjoint_kind != RCV_ADJOINT_VOLPATHSIMPLE) return fail(RCV_ERR_ARG, "unknown adjoint integrator");
     if (!grad_img) return fail(RCV_ERR_ARG, "null grad_img");
     if (int r = ensure_film_w(c)) return r;
+    // deep paths (max_depth = -1 ...) would need an unbounded vertex arena: use the replaying schedule for them
+    const int saved_tracer = c->tracer;
+    if ((c->tracer == RCV_TRACER_POOL || c->tracer == RCV_TRACER_WAVEFRONT) && c->S.max_depth >= 4096) c->tracer = RCV_TRACER_BATCH;
+    if (c->tracer == RCV_TRACER_POOL || c->tracer == RCV_TRACER_WAVEFRONT)
+        if (int r = ensure_arena(c)) { c->tracer = saved_tracer; return r; }
     LaunchCfg cfg = c->cfg();
+    c->tracer = saved_tracer;
     CK(launch_film_weights(cfg, c->S, seed_grad, spp_grad, c->film_w));
     GradK D = c->gradk();
     const bool pin = c->l2_persist && c->l2_persist_max > 0 && c->l2_window_max > 0;

@@ -14,6 +14,8 @@ struct LaunchCfg {
     Counters *counters;   // device
     unsigned long long *work_counter;   // device, persistent-kernel work queue head
     PathQueue queue;                    // device, path records of the wavefront schedule
+    float4 *arena;                      // device, vertex records of the adjoint (4 float4 each)
+    uint32_t vcap;                      // records per arena slot
     uint64_t *launches;   // host-side launch counter
 };
 
@@ -26,6 +28,7 @@ cudaError_t launch_vps_primal(const LaunchCfg &cfg, const SceneK &S, const GridK
 cudaError_t launch_vps_backward(const LaunchCfg &cfg, const SceneK &S, const GridK &G, const GradK &D, uint32_t seed_grad,
                                 uint32_t spp_grad, uint32_t spp_begin, uint32_t spp_end, uint32_t alt_seed,
                                 const float *grad_img, const float *film_w);
+size_t vps_backward_slots(const LaunchCfg &cfg);
 cudaError_t launch_film_weights(const LaunchCfg &cfg, const SceneK &S, uint32_t seed, uint32_t spp, float *film_w);
 
 // ---- medium state (rcv_pixel.cu)

@@ -15,7 +15,6 @@
 namespace rcv {
 
 static constexpr int kPoolSlots = 64;
-enum : int { EV_RESUME = 4 };   // volpathsimple: pass 1 finished, reload the record as pass 2
 
 __device__ __forceinline__ float pf_u(uint32_t v) { return __uint_as_float(v); }
 __device__ __forceinline__ uint32_t pu_f(float v) { return __float_as_uint(v); }
@@ -66,11 +65,11 @@ __device__ __forceinline__ void ts_pool_store_all(float *pw, int s, const TsLane
 
 // ---------------------------------------------------------------------------
 // VpLane <-> pool.  Word map:
-//  0 pix  1 depth  2 idx  3 flags  4 qpos  5-6 rng.state  7-8 rng.inc  9-10 alt.state  11-12 alt.inc
+//  0 pix  1 depth  2 idx  3 flags  4 vbase  5-6 rng.state  7-8 rng.inc  9-10 alt.state  11-12 alt.inc
 //  13-14 saved  15-17 o  18-20 d  21-23 id  24 ray_maxt  25-27 thr  28-30 result  31-33 dL  34 last_pdf
-//  35-37 ro  38 rmaxt  39 running_t  40 mei_t  41-43 nd  44 tr_acc  45-47 nee
+//  35-37 ro  38 rmaxt  39 running_t  40 mei_t  41-43 nd  44 tr_acc  45-47 nee  48 nvert  49 vk
 // ---------------------------------------------------------------------------
-static constexpr int kVpWords = 48;
+static constexpr int kVpWords = 50;
 
 __device__ __forceinline__ void vp_pool_load_hot(const float *pw, int s, VpLane &ln) {
     ln.depth = (int) pu_f(PW(1)); ln.flags = pu_f(PW(3));
@@ -85,7 +84,8 @@ __device__ __forceinline__ void vp_pool_load_hot(const float *pw, int s, VpLane 
     ln.nee = mk3(PW(45), PW(46), PW(47));
 }
 __device__ __forceinline__ void vp_pool_load_cold(const float *pw, int s, VpLane &ln) {
-    ln.pix = (int) pu_f(PW(0)); ln.idx = pu_f(PW(2)); ln.qpos = pu_f(PW(4));
+    ln.pix = (int) pu_f(PW(0)); ln.idx = pu_f(PW(2)); ln.vbase = pu_f(PW(4));
+    ln.nvert = (int) pu_f(PW(48)); ln.vk = (int) pu_f(PW(49));
     ln.alt.state = (uint64_t) pu_f(PW(9)) | ((uint64_t) pu_f(PW(10)) << 32);
     ln.alt.inc = (uint64_t) pu_f(PW(11)) | ((uint64_t) pu_f(PW(12)) << 32);
     ln.saved = (uint64_t) pu_f(PW(13)) | ((uint64_t) pu_f(PW(14)) << 32);
@@ -102,7 +102,8 @@ __device__ __forceinline__ void vp_pool_store_coll(float *pw, int s, const VpLan
 }
 __device__ __forceinline__ void vp_pool_store_all(float *pw, int s, const VpLane &ln) {
     vp_pool_store_coll(pw, s, ln);
-    PW(0) = pf_u((uint32_t) ln.pix); PW(1) = pf_u((uint32_t) ln.depth); PW(2) = pf_u(ln.idx); PW(4) = pf_u(ln.qpos);
+    PW(0) = pf_u((uint32_t) ln.pix); PW(1) = pf_u((uint32_t) ln.depth); PW(2) = pf_u(ln.idx); PW(4) = pf_u(ln.vbase);
+    PW(48) = pf_u((uint32_t) ln.nvert); PW(49) = pf_u((uint32_t) ln.vk);
     PW(7) = pf_u((uint32_t) ln.rng.inc); PW(8) = pf_u((uint32_t) (ln.rng.inc >> 32));
     PW(9) = pf_u((uint32_t) ln.alt.state); PW(10) = pf_u((uint32_t) (ln.alt.state >> 32));
     PW(11) = pf_u((uint32_t) ln.alt.inc); PW(12) = pf_u((uint32_t) (ln.alt.inc >> 32));

@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(kBlock) k_vps_raygen(const __grid_constant__ S
     uint64_t j = (uint64_t) blockIdx.x * kBlock + threadIdx.x;
     VpLane ln; ln.ev = EV_INIT; ln.flags = 0;
     VpSink sk; sk.accum = accum; sk.D.gsig = nullptr; sk.D.galb = nullptr; sk.grad_img = nullptr; sk.film_w = nullptr;
+    sk.arena = nullptr; sk.vcap = 0;
     sk.seed = seed; sk.spp = spp; sk.alt_seed = 0;
     sk.cnt.coll = sk.cnt.scat = sk.cnt.g_sig = sk.cnt.g_alb = 0; sk.n_paths = 0;
     if (j < n_local) vp_raygen<BACKWARD>(S, ln, sk, global_lane(j, spp, spp_begin, ns));
@@ -287,23 +288,24 @@ __global__ void __launch_bounds__(kWfBlock, RCV_VP_MINBLOCKS) k_vps_wavefront(co
                                                                            const __grid_constant__ GridK G, GradK D, uint32_t seed,
                                                                            uint32_t spp, uint32_t alt_seed, const float *grad_img,
                                                                            const float *film_w, float4 *accum, PathQueue Q,
-                                                                           Counters *C, unsigned long long *work) {
+                                                                           Counters *C, unsigned long long *work, float4 *arena,
+                                                                           uint32_t vcap) {
     const float mu = __ldg(G.majorants + 1);
     const float inv_mu = 1.f / mu;
     const unsigned long long n_total = *Q.count;
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;       // arena slot of this thread's lane
     VpLane ln;
     ln.ev = EV_INIT; ln.flags = 0;
     VpSink sk;
-    sk.accum = accum; sk.D = D; sk.grad_img = grad_img; sk.film_w = film_w;
+    sk.accum = accum; sk.D = D; sk.grad_img = grad_img; sk.film_w = film_w; sk.arena = arena; sk.vcap = vcap;
     sk.seed = seed; sk.spp = spp; sk.alt_seed = alt_seed;
     sk.cnt.coll = sk.cnt.scat = sk.cnt.g_sig = sk.cnt.g_alb = 0; sk.n_paths = 0;
     ChunkCursor cc; cc.next = 0; cc.end = 0; cc.more = true;
     while (true) {
         const int n_coll = __popc(__ballot_sync(0xffffffffu, ln.ev == EV_COLL));
         const int n_scat = __popc(__ballot_sync(0xffffffffu, ln.ev == EV_SCAT));
-        // lanes waiting for the slow step: parked work, lanes to resume as pass 2, empty lanes while records remain
-        const int n_slow = __popc(__ballot_sync(
-            0xffffffffu, ln.ev == EV_SLOW || (ln.ev == EV_INIT && ((BACKWARD && (ln.flags & VF_PASS2)) || cc.more))));
+        // lanes waiting for the slow step: parked work, or empty lanes while records remain
+        const int n_slow = __popc(__ballot_sync(0xffffffffu, ln.ev == EV_SLOW || (ln.ev == EV_INIT && cc.more)));
         if (n_coll == 0 && n_scat == 0 && n_slow == 0) break;
         const int sel = pick_event(n_coll, n_scat, n_slow);
         if (sel == EV_COLL) {
@@ -312,14 +314,11 @@ __global__ void __launch_bounds__(kWfBlock, RCV_VP_MINBLOCKS) k_vps_wavefront(co
             if (ln.ev == EV_SCAT) vp_vertex<BACKWARD>(S, G, ln, sk);
         } else {
             if (ln.ev == EV_SLOW) vp_slow<BACKWARD>(S, ln, sk);
-            // resume lanes that finished pass 1 as pass 2; refill the finished ones
-            const bool is_init = ln.ev == EV_INIT;
-            const bool resume = BACKWARD && is_init && (ln.flags & VF_PASS2);
-            if (resume) vp_load(ln, sk, Q, ln.qpos, true);
-            unsigned m_new = __ballot_sync(0xffffffffu, is_init && !resume);
+            // refill the finished lanes from the record queue
+            unsigned m_new = __ballot_sync(0xffffffffu, ln.ev == EV_INIT);
             if (m_new && cc.more) {
                 unsigned long long pos = take_positions(cc, work, n_total, m_new);
-                if (pos != ~0ull) vp_load(ln, sk, Q, pos, false);
+                if (pos != ~0ull) vp_load(ln, sk, Q, pos, slot);
             }
         }
         __syncwarp();
@@ -426,7 +425,8 @@ __global__ void __launch_bounds__(kPoolBlock, RCV_POOL_MINBLOCKS) k_vps_pool(con
                                                                              const __grid_constant__ GridK G, GradK D, uint32_t seed,
                                                                              uint32_t spp, uint32_t alt_seed, const float *grad_img,
                                                                              const float *film_w, float4 *accum, PathQueue Q,
-                                                                             Counters *C, unsigned long long *work) {
+                                                                             Counters *C, unsigned long long *work, float4 *arena,
+                                                                             uint32_t vcap) {
     extern __shared__ float smem[];
     const unsigned lane = threadIdx.x & 31;
     float *pw = smem + (threadIdx.x >> 5) * pool_warp_floats<kVpWords>();
@@ -436,9 +436,10 @@ __global__ void __launch_bounds__(kPoolBlock, RCV_POOL_MINBLOCKS) k_vps_pool(con
     const float inv_mu = 1.f / mu;
     const unsigned long long n_total = *Q.count;
     VpSink sk;
-    sk.accum = accum; sk.D = D; sk.grad_img = grad_img; sk.film_w = film_w;
+    sk.accum = accum; sk.D = D; sk.grad_img = grad_img; sk.film_w = film_w; sk.arena = arena; sk.vcap = vcap;
     sk.seed = seed; sk.spp = spp; sk.alt_seed = alt_seed;
     sk.cnt.coll = sk.cnt.scat = sk.cnt.g_sig = sk.cnt.g_alb = 0; sk.n_paths = 0;
+    const uint32_t slot0 = (blockIdx.x * kPoolWarps + (threadIdx.x >> 5)) * kPoolSlots;   // first arena slot of this warp's pool
     ChunkCursor cc; cc.next = 0; cc.end = 0; cc.more = true;
     cls[lane] = EV_INIT; cls[lane + 32] = EV_INIT;
     __syncwarp();
@@ -446,8 +447,8 @@ __global__ void __launch_bounds__(kPoolBlock, RCV_POOL_MINBLOCKS) k_vps_pool(con
         const int c0 = cls[lane], c1 = cls[lane + 32];
         const unsigned coll_lo = __ballot_sync(0xffffffffu, c0 == EV_COLL), coll_hi = __ballot_sync(0xffffffffu, c1 == EV_COLL);
         const unsigned scat_lo = __ballot_sync(0xffffffffu, c0 == EV_SCAT), scat_hi = __ballot_sync(0xffffffffu, c1 == EV_SCAT);
-        const unsigned slow_lo = __ballot_sync(0xffffffffu, c0 == EV_SLOW || c0 == EV_RESUME || (c0 == EV_INIT && cc.more));
-        const unsigned slow_hi = __ballot_sync(0xffffffffu, c1 == EV_SLOW || c1 == EV_RESUME || (c1 == EV_INIT && cc.more));
+        const unsigned slow_lo = __ballot_sync(0xffffffffu, c0 == EV_SLOW || (c0 == EV_INIT && cc.more));
+        const unsigned slow_hi = __ballot_sync(0xffffffffu, c1 == EV_SLOW || (c1 == EV_INIT && cc.more));
         const int n_coll = __popc(coll_lo) + __popc(coll_hi), n_scat = __popc(scat_lo) + __popc(scat_hi);
         const int n_slow = __popc(slow_lo) + __popc(slow_hi);
         if (n_coll == 0 && n_scat == 0 && n_slow == 0) break;
@@ -469,26 +470,23 @@ __global__ void __launch_bounds__(kPoolBlock, RCV_POOL_MINBLOCKS) k_vps_pool(con
                 ln.ev = EV_SCAT;
                 vp_vertex<BACKWARD>(S, G, ln, sk);
                 vp_pool_store_all(pw, s, ln);
-                cls[s] = (unsigned char) ((BACKWARD && ln.ev == EV_INIT && (ln.flags & VF_PASS2)) ? EV_RESUME : ln.ev);
+                cls[s] = (unsigned char) ln.ev;
             }
         } else {
             const int s = pool_select(slow_lo, slow_hi, list);
             ln.ev = EV_INIT; ln.flags = 0;
-            const int c = (s >= 0) ? (int) cls[s] : EV_INIT;
             bool loaded = false;
-            if (s >= 0 && (c == EV_SLOW || c == EV_RESUME)) {
+            if (s >= 0 && cls[s] == EV_SLOW) {
                 vp_pool_load_hot(pw, s, ln); vp_pool_load_cold(pw, s, ln);
                 loaded = true;
-                if (c == EV_SLOW) { ln.ev = EV_SLOW; vp_slow<BACKWARD>(S, ln, sk); }
-                else { ln.ev = EV_INIT; }
+                ln.ev = EV_SLOW;
+                vp_slow<BACKWARD>(S, ln, sk);
             }
-            // lanes that finished pass 1 resume as pass 2; empty slots take the next record
-            const bool resume = BACKWARD && s >= 0 && ln.ev == EV_INIT && (ln.flags & VF_PASS2);
-            if (resume) vp_load(ln, sk, Q, ln.qpos, true);
-            unsigned m_need = __ballot_sync(0xffffffffu, s >= 0 && ln.ev == EV_INIT && !resume);
+            // empty slots take the next record
+            unsigned m_need = __ballot_sync(0xffffffffu, s >= 0 && ln.ev == EV_INIT);
             if (m_need && cc.more) {
                 unsigned long long pos = take_positions(cc, work, n_total, m_need);
-                if (pos != ~0ull) { vp_load(ln, sk, Q, pos, false); loaded = true; }
+                if (pos != ~0ull) { vp_load(ln, sk, Q, pos, slot0 + (uint32_t) s); loaded = true; }
             }
             if (s >= 0) {
                 if (loaded && ln.ev != EV_INIT) vp_pool_store_all(pw, s, ln);
@@ -598,13 +596,14 @@ static cudaError_t launch_vps(const LaunchCfg &cfg, const SceneK &S, const GridK
             S, seed, spp, spp_begin, ns, n_local, accum, cfg.queue, cfg.counters);
         if (cfg.tracer == 3) {
             e = launch_pool(cfg, k_vps_pool<BACKWARD>, kPoolWarps * pool_warp_floats<kVpWords>() * sizeof(float), n_local, S, G, D, seed,
-                            spp, alt_seed, grad_img, film_w, accum, cfg.queue, cfg.counters, cfg.work_counter);
+                            spp, alt_seed, grad_img, film_w, accum, cfg.queue, cfg.counters, cfg.work_counter, cfg.arena, cfg.vcap);
             if (e != cudaSuccess) return e;
         } else {
             unsigned blocks;
             if ((e = persistent_grid(cfg, k_vps_wavefront<BACKWARD>, kWfBlock, n_local, blocks)) != cudaSuccess) return e;
             k_vps_wavefront<BACKWARD><<<blocks, kWfBlock, 0, cfg.stream>>>(S, G, D, seed, spp, alt_seed, grad_img, film_w, accum,
-                                                                           cfg.queue, cfg.counters, cfg.work_counter);
+                                                                           cfg.queue, cfg.counters, cfg.work_counter, cfg.arena,
+                                                                           cfg.vcap);
         }
         (*cfg.launches) += 2;
     } else {
@@ -619,6 +618,25 @@ static cudaError_t launch_vps(const LaunchCfg &cfg, const SceneK &S, const GridK
         (*cfg.launches)++;
     }
     return cudaGetLastError();
+}
+
+// upper bound of the arena slots (lanes in flight) the adjoint launch of this schedule can use
+size_t vps_backward_slots(const LaunchCfg &cfg) {
+    if (cfg.tracer == 3) {
+        int per_sm = 0;
+        size_t smem = kPoolWarps * pool_warp_floats<kVpWords>() * sizeof(float);
+        cudaFuncSetAttribute(k_vps_pool<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vps_pool<true>, kPoolBlock, smem) != cudaSuccess || per_sm < 1)
+            per_sm = 1;
+        return (size_t) per_sm * cfg.sm_count * kPoolWarps * kPoolSlots;
+    }
+    if (cfg.tracer == 0) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vps_wavefront<true>, kWfBlock, 0) != cudaSuccess || per_sm < 1)
+            per_sm = 1;
+        return (size_t) per_sm * cfg.sm_count * kWfBlock;
+    }
+    return 0;
 }
 
 cudaError_t launch_vps_primal(const LaunchCfg &cfg, const SceneK &S, const GridK &G, uint32_t seed, uint32_t spp,

@@ -1,31 +1,39 @@
 // rcv_volpathsimple_wf.cuh — VolpathSimpleIntegrator (plugins/volpathsimple.py,
 // use_drt = False) as a per-lane event machine, for the persistent-warp
-// scheduler.  Same estimator, same random streams and the same arithmetic as
-// rcv_volpathsimple.cuh; cut into
+// schedulers.  Same estimator, same random streams and the same arithmetic as
+// rcv_volpathsimple.cuh (the straight-line restatement kept as A/B baseline), but
+// the adjoint is organised as a VERTEX LIST:
+//
+//   pass 1 (primal, RBIntegrator.render_backward's first sample() call) traces the
+//     path and writes one 64-byte record per path vertex (real collision or
+//     medium exit) into a small per-slot arena: ray, segment length, whether a
+//     shadow ray was cast, the sampler state before it, its direction and its
+//     contribution;
+//   pass 2 (adjoint) does NOT re-trace the path: it walks the vertex list and
+//     evaluates, per vertex, exactly the terms the reference evaluates while
+//     replaying — scattering term (:165-185), transmittance term (:194-202,
+//     :597-620) and the shadow ray's transmittance gradients (:406-414,
+//     :496-505), the only part that needs tracing again (with the parked sampler
+//     state, like the reference's cloned sampler).  The null collisions of the
+//     main path and the primal shadow rays are not repeated: ~44 % fewer gathers
+//     than replaying, identical gradient terms.
 //
 //   vp_raygen  (its own, fully convergent kernel) camera ray, dummy channel
 //              draw (:84), reach_medium (:305-332), alt_seed_rnd draw (:112);
 //              paths that never enter the medium end here, the others become
 //              48-byte path records in HBM
-//   vp_load    a lane picks up a record: to begin pass 1 (primal) or to resume
-//              the same path as pass 2 (adjoint replay of the identical stream,
-//              RBIntegrator.render_backward)
 //   EV_COLL    ONE tentative collision: a delta-tracking step of
 //              sample_real_interaction (:360-380) or a ratio-tracking step of
-//              estimate_transmittance (:478-515) — in the adjoint's NEE replay
-//              (:406-414) it emits the sigma_t gradient request of :496-505
-//   EV_SCAT    a path vertex (real collision or medium exit): coefficient gathers,
-//              the adjoint's scattering (:165-185) and transmittance (:194-202,
-//              :597-620) gradient scatters, then NEE set-up (:393-446) or phase
-//              sampling (:234-258)
+//              estimate_transmittance (:478-515), in pass 2 with the sigma_t
+//              gradient scatter of :496-505
+//   EV_SCAT    pass 1: a path vertex — albedo gather, throughput/depth update,
+//              vertex record, NEE set-up (:393-446) or phase sampling (:234-258);
+//              pass 2: the next vertex of the list — coefficient gathers,
+//              gradient scatters, start of the shadow-ray replay
 //   EV_SLOW    once-per-shadow-ray / once-per-pass work that would otherwise run
-//              with one or two lanes: end of the shadow ray, start of its
-//              adjoint replay, phase sampling after it, end of a pass; the
-//              scheduler also reloads / refills lanes in this step
+//              with one or two lanes: end of a shadow ray (+ phase sampling) or of
+//              its replay, end of a pass; the scheduler refills lanes in this step
 //
-// Gradient scatters run inside the handlers: vertex steps are batched (>= 12
-// lanes), so all requesting lanes issue their reductions together; the NEE
-// replay reuses the interpolation set-up of the collision's gather.
 // The handlers contain no warp intrinsics and also compile for the host
 // (RCV_HOST_EMU) where tests single-step them against the oracle.
 #pragma once
@@ -39,21 +47,25 @@ enum : uint32_t {
     VF_HAS_SCAT = 2u,
     VF_ESCAPED = 4u,
     VF_IN_NEE = 8u,
-    VF_REPLAY = 16u,      // NEE transmittance replay with gradients
+    VF_REPLAY = 16u,      // shadow-ray transmittance replay with gradients (pass 2)
     VF_HEAD = 32u,        // next main-path collision starts with the loop head (:129-134)
     VF_DID_SCATTER = 64u,
-    VF_PASS2 = 128u,      // pass 1 finished, the lane must reload its record as pass 2
     // work parked for the batched EV_SLOW step
     VF_POSTNEE = 512u,    // the shadow ray (or its replay) ended
     VF_END = 1024u        // the pass ended at a loop head (:132-133)
 };
 
+// vertex record flags
+enum : uint32_t { VR_SCATTER = 1u, VR_NEE = 2u };
+static constexpr int kVertexCapMax = 4096;   // largest supported max_depth + 1 for the vertex-list adjoint
+
 struct VpLane {
     int ev, pix, depth;
     uint32_t idx, flags;
-    uint32_t qpos;          // position of the path's record in the queue
+    uint32_t vbase;         // first record of this lane's arena slot
+    int nvert, vk;          // vertices recorded in pass 1 / cursor of pass 2
     Pcg rng, alt;
-    uint64_t saved;         // main sampler state parked during the NEE / its replay
+    uint64_t saved;         // main sampler state before the shadow ray (:396 sampler.clone())
     V3 o, d;                // current ray (origin = last vertex)
     V3 id;                  // 1/direction of the current segment (ray, or shadow ray during NEE)
     float ray_maxt;         // distance to the boundary along the ray (== si.t)
@@ -63,35 +75,46 @@ struct VpLane {
     float rmaxt, running_t, mei_t;
     V3 nd;                  // shadow-ray direction
     float tr_acc;
-    V3 nee;                 // NEE contribution of this vertex (needed after the replay)
+    V3 nee;                 // NEE contribution of the current vertex
 };
 
 struct VpSink {
     float4 *accum;          // primal render target (H,W,4) or null
     GradK D;                // gradient grids (adjoint)
     const float *grad_img, *film_w;
+    float4 *arena;          // vertex records, 4 float4 each
+    uint32_t vcap;          // records per arena slot (>= max_depth + 1)
     uint32_t seed, spp, alt_seed;
     VpsCounts cnt;
     unsigned n_paths;
 };
 
+__device__ __forceinline__ float4 *vp_record(const VpSink &sk, const VpLane &ln, int k) {
+    return sk.arena + ((size_t) ln.vbase + (size_t) k) * 4;
+}
+
+// end of pass 2 (or of a render-only path)
+__device__ __forceinline__ void vp_finish(VpLane &ln, VpSink &sk) {
+    sk.n_paths++;
+    ln.flags = 0;
+    ln.ev = EV_INIT;
+}
+
+// end of pass 1: environment contribution (:276-300); then either splat (render) or start pass 2
 template <bool BW>
 __device__ __forceinline__ void vp_end_pass(const SceneK &S, VpLane &ln, VpSink &sk) {
-    sk.n_paths++;
-    if (ln.flags & VF_ADJ) { ln.flags = 0; ln.ev = EV_INIT; return; }
-    // primal pass: environment contribution of escaped lanes (:276-300)
     if ((ln.flags & VF_ESCAPED) && !((ln.depth <= 0) && S.hide_emitters)) {
         const V3 env = mk3(S.env[0], S.env[1], S.env[2]);
         float w = 1.f;
         if (S.use_nee) w = mis_weight(ln.last_pdf, (ln.flags & VF_HAS_SCAT) ? RCV_INV_FOURPI : 0.f);
         ln.result = ln.result + (ln.thr * w) * env;
     }
-    ln.ev = EV_INIT;
     if (!BW) {
         if (ln.pix >= 0) red_add_v4(sk.accum + ln.pix, ln.result.x, ln.result.y, ln.result.z, 1.f);
-        ln.flags = 0;
+        vp_finish(ln, sk);
         return;
     }
+    sk.n_paths++;                                   // pass 1 complete
     // dL = d(develop o put)/dL * grad_in: box filter -> grad_in[pixel] / W[pixel]
     ln.dL = mk3(0, 0, 0);
     if (ln.pix >= 0) {
@@ -100,7 +123,12 @@ __device__ __forceinline__ void vp_end_pass(const SceneK &S, VpLane &ln, VpSink 
         ln.dL = mk3(__ldg(sk.grad_img + 3 * ln.pix) / dv, __ldg(sk.grad_img + 3 * ln.pix + 1) / dv,
                     __ldg(sk.grad_img + 3 * ln.pix + 2) / dv);
     }
-    ln.flags = VF_PASS2;
+    // pass 2 starts from state_in = the pass-1 result (:68) with the secondary sampler (:119-120)
+    sampler_seed(ln.alt, sk.alt_seed, ln.idx);
+    ln.flags = VF_ADJ;
+    ln.vk = 0;
+    if (ln.nvert > 0) ln.ev = EV_SCAT;
+    else vp_finish(ln, sk);
 }
 
 // Start of a path up to the first loop iteration: camera ray, dummy channel
@@ -118,6 +146,7 @@ __device__ __forceinline__ void vp_raygen(const SceneK &S, VpLane &ln, VpSink &s
     ln.depth = 0;
     ln.last_pdf = 1.f;
     ln.flags = 0;
+    ln.nvert = 0; ln.vk = 0;
     (void) pcg_f32(ln.rng);                                           // :84
     Hit si = box_hit(S, ln.o, ln.d, ln.id, RCV_LARGEST);              // :311
     bool active = si.valid;
@@ -148,22 +177,22 @@ __device__ __forceinline__ void vp_store(const VpLane &ln, const PathQueue &Q, u
     Q.r1[pos] = make_float4(ln.o.x, ln.o.y, ln.o.z, ln.ray_maxt);
     Q.r2[pos] = make_float4(ln.d.x, ln.d.y, ln.d.z, __uint_as_float(ln.idx));
 }
-// begin pass 1 (adj = false) or pass 2 (adj = true) of the path recorded at pos
-__device__ __forceinline__ void vp_load(VpLane &ln, const VpSink &sk, const PathQueue &Q, unsigned long long pos, bool adj) {
+// begin pass 1 of the path recorded at pos in arena slot `slot`
+__device__ __forceinline__ void vp_load(VpLane &ln, const VpSink &sk, const PathQueue &Q, unsigned long long pos, uint32_t slot) {
     float4 a = __ldg(Q.r0 + pos), b = __ldg(Q.r1 + pos), c = __ldg(Q.r2 + pos);
-    ln.qpos = (uint32_t) pos;
     ln.rng.state = (uint64_t) __float_as_uint(a.x) | ((uint64_t) __float_as_uint(a.y) << 32);
     ln.rng.inc = ((uint64_t) __float_as_uint(a.z) << 1) | 1u;
     ln.pix = (int) __float_as_uint(a.w);
     ln.o = mk3(b.x, b.y, b.z); ln.ray_maxt = b.w;
     ln.d = mk3(c.x, c.y, c.z); ln.idx = __float_as_uint(c.w);
     ln.id = rcp3(ln.d);
-    if (adj) sampler_seed(ln.alt, sk.alt_seed, ln.idx);               // :119-120
-    else ln.result = mk3(0, 0, 0);                                    // :68 (pass 2 starts from state_in = pass-1 result)
+    ln.result = mk3(0, 0, 0);                                         // :68
     ln.thr = mk3(1, 1, 1);
     ln.depth = 0;
     ln.last_pdf = 1.f;
-    ln.flags = (adj ? VF_ADJ : 0u) | VF_HEAD;
+    ln.flags = VF_HEAD;
+    ln.vbase = slot * sk.vcap;
+    ln.nvert = 0; ln.vk = 0;
     ln.ev = EV_COLL;
 }
 
@@ -177,7 +206,7 @@ __device__ __forceinline__ bool vp_nee_start(const SceneK &S, VpLane &ln) {
     return si.valid;
 }
 
-// after the vertex (and its NEE): phase sampling, new ray, boundary distance (:234-258)
+// pass 1, after the vertex (and its NEE): phase sampling, new ray, boundary distance (:234-258)
 template <bool BW>
 __device__ __forceinline__ void vp_post_vertex(const SceneK &S, VpLane &ln, VpSink &sk, bool active) {
     const bool did_scatter = (ln.flags & VF_DID_SCATTER) != 0;
@@ -202,35 +231,33 @@ __device__ __forceinline__ void vp_post_vertex(const SceneK &S, VpLane &ln, VpSi
     ln.ev = EV_COLL;
 }
 
-// the shadow ray (or its replay) ended
+// pass 1: the shadow ray ended — its contribution (:401-404, :225), the vertex record, then the path continues
 template <bool BW>
 __device__ __forceinline__ void vp_nee_done(const SceneK &S, VpLane &ln, VpSink &sk) {
-    while (true) {
-        if (!(ln.flags & VF_REPLAY)) {
-            const V3 env = mk3(S.env[0], S.env[1], S.env[2]);
-            V3 wi = mk3(-ln.d.x, -ln.d.y, -ln.d.z);
-            V3 emitted = mk3(S.env_over_pdf[0], S.env_over_pdf[1], S.env_over_pdf[2]) * splat3(ln.tr_acc);
-            float phase_val = phase_eval(S, wi, ln.nd);               // :401
-            ln.nee = ((ln.thr * phase_val) * mis_weight(RCV_INV_FOURPI, phase_val)) * emitted;   // :404
-            if (BW && (ln.flags & VF_ADJ)) {
-                // replay with the cloned sampler (:396, :412-414): park the advanced state
-                uint64_t after = ln.rng.state;
-                ln.rng.state = ln.saved;
-                ln.saved = after;
-                (void) pcg_u32(ln.rng); (void) pcg_u32(ln.rng);       // the direction sample (:431), same values
-                ln.flags |= VF_REPLAY;
-                if (vp_nee_start(S, ln)) return;                      // EV_COLL continues in replay mode
-                continue;                                             // no extent: replay ends immediately
-            }
-            ln.result = ln.result + ln.nee;                           // :225
-        } else {
-            ln.rng.state = ln.saved;                                  // back to the main sampler
-            ln.result = ln.result - ln.nee;                           // :227
-        }
-        ln.flags &= ~(VF_IN_NEE | VF_REPLAY);
-        vp_post_vertex<BW>(S, ln, sk, true);
-        return;
+    V3 wi = mk3(-ln.d.x, -ln.d.y, -ln.d.z);
+    V3 emitted = mk3(S.env_over_pdf[0], S.env_over_pdf[1], S.env_over_pdf[2]) * splat3(ln.tr_acc);
+    float phase_val = phase_eval(S, wi, ln.nd);                       // :401
+    ln.nee = ((ln.thr * phase_val) * mis_weight(RCV_INV_FOURPI, phase_val)) * emitted;   // :404
+    ln.result = ln.result + ln.nee;                                   // :225
+    if (BW) {
+        float4 *r = vp_record(sk, ln, ln.nvert - 1);
+        r[2] = make_float4(__uint_as_float((uint32_t) ln.saved), __uint_as_float((uint32_t) (ln.saved >> 32)), ln.nee.x, ln.nee.y);
+        r[3] = make_float4(ln.nee.z, ln.nd.x, ln.nd.y, ln.nd.z);
     }
+    ln.flags &= ~VF_IN_NEE;
+    vp_post_vertex<BW>(S, ln, sk, true);
+}
+
+// pass 2: the replay of a shadow ray ended (:227), next vertex
+__device__ __forceinline__ void vp_next_vertex(VpLane &ln, VpSink &sk) {
+    ln.vk += 1;
+    if (ln.vk < ln.nvert) ln.ev = EV_SCAT;
+    else vp_finish(ln, sk);
+}
+__device__ __forceinline__ void vp_replay_done(VpLane &ln, VpSink &sk) {
+    ln.result = ln.result - ln.nee;                                   // :227
+    ln.flags &= ~(VF_IN_NEE | VF_REPLAY);
+    vp_next_vertex(ln, sk);
 }
 
 template <bool BW>
@@ -271,8 +298,7 @@ __device__ __forceinline__ void vp_collide(const SceneK &S, const GridK &G, floa
         ln.tr_acc = ln.tr_acc * tr;                                   // :508
         ln.ro = m.p;                                                  // :510
         ln.rmaxt = ln.rmaxt - m.t;
-        if (!(ln.tr_acc != 0.f)) { ln.flags |= VF_POSTNEE; ln.ev = EV_SLOW; return; }   // :515
-        prefetch_next_brick<false>(S, G, inv_mu, ln.rng, 0, ln.ro, ln.nd);
+        if (!(ln.tr_acc != 0.f)) { ln.flags |= VF_POSTNEE; ln.ev = EV_SLOW; }   // :515
         return;
     }
     // sample_real_interaction step (:360-380)
@@ -284,7 +310,6 @@ __device__ __forceinline__ void vp_collide(const SceneK &S, const GridK &G, floa
     ln.ro = ln.ro + ln.d * m.t;                                       // :378-380
     ln.rmaxt = ln.rmaxt - m.t;
     ln.running_t = ln.running_t + m.t;
-    prefetch_next_brick<false>(S, G, inv_mu, ln.rng, 0, ln.ro, ln.d);
 }
 
 // the batched slow step (see the header comment)
@@ -293,65 +318,37 @@ __device__ __forceinline__ void vp_slow(const SceneK &S, VpLane &ln, VpSink &sk)
     if (ln.flags & VF_POSTNEE) {
         ln.flags &= ~VF_POSTNEE;
         ln.ev = EV_COLL;
-        vp_nee_done<BW>(S, ln, sk);
+        if (BW && (ln.flags & VF_ADJ)) vp_replay_done(ln, sk);
+        else vp_nee_done<BW>(S, ln, sk);
     } else {
         ln.flags &= ~VF_END;
         vp_end_pass<BW>(S, ln, sk);
     }
 }
 
-// a path vertex: gathers, the adjoint's gradient scatters, throughput/depth update, then NEE set-up
-// or the continuation of the path
+// pass 1 vertex: albedo gather, throughput/depth update (:150-213), vertex record, NEE set-up or continuation
 template <bool BW>
-__device__ __forceinline__ void vp_vertex(const SceneK &S, const GridK &G, VpLane &ln, VpSink &sk) {
+__device__ __forceinline__ void vp_vertex1(const SceneK &S, const GridK &G, VpLane &ln, VpSink &sk) {
     const bool did_scatter = (ln.flags & VF_DID_SCATTER) != 0;
-    const bool adj = BW && (ln.flags & VF_ADJ);
     if (did_scatter) ln.flags |= VF_HAS_SCAT;                         // :150
-    V3 mei_p = mk3(0, 0, 0), albedo = mk3(1, 1, 1);
-    float st = 0.f;
-    Tri T;
-    T.inside = false;
+    V3 albedo = mk3(1, 1, 1);
     if (did_scatter) {
-        mei_p = ray_at(ln.o, ln.d, ln.mei_t);                         // :384
-        T = tri_setup(S, G, mei_p);
-        if (adj) st = lookup_sigma1(S, G, T);                         // :386-388
+        V3 mei_p = ray_at(ln.o, ln.d, ln.mei_t);                      // :384
+        Tri T = tri_setup(S, G, mei_p);
         albedo = lookup_albedo(G, T, 1);                              // :154
         sk.cnt.scat++;
-    }
-    if (adj) {
-        if (did_scatter) {                                            // scattering term (:165-185)
-            V3 inv_pdf = splat3(1.f / st);
-            V3 Li = ln.result / vmax3(splat3(1e-8f), albedo);
-            V3 c = (ln.dL * Li) * inv_pdf;
-            float g_st = (c.x * albedo.x + c.y * albedo.y) + c.z * albedo.z;
-            V3 g_al = c * splat3(st);
-            if (T.inside) {
-                float sg = S.scale * g_st;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    float w = tri_weight(T, k);
-                    size_t v = tri_voxel(G, T, k);
-                    red_add_f32(sk.D.gsig + v, w * sg);
-                    red_add_v4(sk.D.galb + v, w * g_al.x, w * g_al.y, w * g_al.z, 0.f);
-                }
-                sk.cnt.g_sig++; sk.cnt.g_alb++;
-            }
-        }
-        // transmittance term (:194-202, :597-620)
-        V3 aw = ln.dL * ln.result;
-        float interval = did_scatter ? ln.mei_t : ln.ray_maxt;        // :601 (si.t == ray.maxt)
-        float inv_pdf = interval / 4.f;
-        float g = -((aw.x * inv_pdf) + (aw.y * inv_pdf) + (aw.z * inv_pdf));
-#pragma unroll 1
-        for (int j = 0; j < 4; ++j) {
-            float t = pcg_f32(ln.alt) * interval;                     // :608
-            scatter_sigma_t(S, G, sk.D, ray_at(ln.o, ln.d, t), g, sk.cnt);
-        }
     }
     ln.thr = ln.thr * albedo;                                         // :206
     if (did_scatter) ln.depth += 1;                                   // :212
     bool active = did_scatter && (ln.depth < S.max_depth);            // :213
-    if (S.use_nee && did_scatter && active) {                         // :219-228 -> :393-446
+    const bool do_nee = S.use_nee && did_scatter && active;           // :219-220
+    if (BW) {
+        float4 *r = vp_record(sk, ln, ln.nvert);
+        r[0] = make_float4(ln.o.x, ln.o.y, ln.o.z, did_scatter ? ln.mei_t : ln.ray_maxt);   // interval of :601
+        r[1] = make_float4(ln.d.x, ln.d.y, ln.d.z, __uint_as_float((did_scatter ? VR_SCATTER : 0u) | (do_nee ? VR_NEE : 0u)));
+        ln.nvert += 1;
+    }
+    if (do_nee) {                                                     // :393-446
         ln.saved = ln.rng.state;                                      // :396 sampler.clone()
         float s2x = pcg_f32(ln.rng), s2y = pcg_f32(ln.rng);           // :431
         ln.nd = uniform_sphere(s2x, s2y);
@@ -362,6 +359,71 @@ __device__ __forceinline__ void vp_vertex(const SceneK &S, const GridK &G, VpLan
         return;
     }
     vp_post_vertex<BW>(S, ln, sk, active);
+}
+
+// pass 2 vertex: the gradient terms of vertex vk, then the replay of its shadow ray
+__device__ __forceinline__ void vp_vertex2(const SceneK &S, const GridK &G, VpLane &ln, VpSink &sk) {
+    const float4 *r = vp_record(sk, ln, ln.vk);
+    float4 r0 = r[0], r1 = r[1];
+    ln.o = mk3(r0.x, r0.y, r0.z); ln.d = mk3(r1.x, r1.y, r1.z);
+    const float interval = r0.w;
+    const uint32_t vf = __float_as_uint(r1.w);
+    const bool did_scatter = (vf & VR_SCATTER) != 0;
+    ln.mei_t = interval;
+    if (did_scatter) {
+        V3 mei_p = ray_at(ln.o, ln.d, interval);                      // :384
+        Tri T = tri_setup(S, G, mei_p);
+        float st = lookup_sigma1(S, G, T);                            // :386-388
+        V3 albedo = lookup_albedo(G, T, 1);                           // :154
+        sk.cnt.scat++;
+        // scattering term (:165-185): backward_from(dL * (sigma_t * albedo) * Li * inv_pdf)
+        V3 inv_pdf = splat3(1.f / st);
+        V3 Li = ln.result / vmax3(splat3(1e-8f), albedo);
+        V3 c = (ln.dL * Li) * inv_pdf;
+        float g_st = (c.x * albedo.x + c.y * albedo.y) + c.z * albedo.z;
+        V3 g_al = c * splat3(st);
+        if (T.inside) {
+            float sg = S.scale * g_st;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float w = tri_weight(T, k);
+                size_t v = tri_voxel(G, T, k);
+                red_add_f32(sk.D.gsig + v, w * sg);
+                red_add_v4(sk.D.galb + v, w * g_al.x, w * g_al.y, w * g_al.z, 0.f);
+            }
+            sk.cnt.g_sig++; sk.cnt.g_alb++;
+        }
+    }
+    // transmittance term (:194-202, :597-620): 4 uniform points on the segment
+    {
+        V3 aw = ln.dL * ln.result;                                    // :198
+        float inv_pdf = interval / 4.f;                               // :617
+        float g = -((aw.x * inv_pdf) + (aw.y * inv_pdf) + (aw.z * inv_pdf));
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+            float t = pcg_f32(ln.alt) * interval;                     // :608
+            scatter_sigma_t(S, G, sk.D, ray_at(ln.o, ln.d, t), g, sk.cnt);
+        }
+    }
+    if (vf & VR_NEE) {                                                // :406-414: replay with the cloned sampler
+        float4 r2 = r[2], r3 = r[3];
+        ln.rng.state = (uint64_t) __float_as_uint(r2.x) | ((uint64_t) __float_as_uint(r2.y) << 32);
+        (void) pcg_u32(ln.rng); (void) pcg_u32(ln.rng);               // the direction sample (:431), same values
+        ln.nee = mk3(r2.z, r2.w, r3.x);
+        ln.nd = mk3(r3.y, r3.z, r3.w);
+        ln.id = rcp3(ln.nd);
+        ln.flags |= VF_IN_NEE | VF_REPLAY;
+        ln.ev = EV_COLL;
+        if (!vp_nee_start(S, ln)) vp_replay_done(ln, sk);
+        return;
+    }
+    vp_next_vertex(ln, sk);
+}
+
+template <bool BW>
+__device__ __forceinline__ void vp_vertex(const SceneK &S, const GridK &G, VpLane &ln, VpSink &sk) {
+    if (BW && (ln.flags & VF_ADJ)) vp_vertex2(S, G, ln, sk);
+    else vp_vertex1<BW>(S, G, ln, sk);
 }
 
 }  // namespace rcv

@@ -92,6 +92,8 @@ void run_vps(const SceneK &S, const GridK &G, VpSink &sk) {
     const float inv_mu = 1.f / mu;
     uint64_t n = (uint64_t) S.W * S.H * sk.spp;
     HostQueue hq(n);
+    std::vector<float4> arena((size_t) 4 * (S.max_depth + 1));       // one arena slot: the lanes run one after the other
+    sk.arena = arena.data(); sk.vcap = (uint32_t) S.max_depth + 1u;
     for (uint64_t idx = 0; idx < n; ++idx) {
         VpLane ln; ln.ev = EV_INIT; ln.flags = 0;
         vp_raygen<BW>(S, ln, sk, idx);
@@ -99,13 +101,8 @@ void run_vps(const SceneK &S, const GridK &G, VpSink &sk) {
     }
     for (unsigned long long pos = 0; pos < hq.count; ++pos) {
         VpLane ln; ln.flags = 0;
-        vp_load(ln, sk, hq.Q, pos, false);
-        while (true) {
-            if (ln.ev == EV_INIT) {
-                if (!(BW && (ln.flags & VF_PASS2))) break;
-                vp_load(ln, sk, hq.Q, ln.qpos, true);
-                continue;
-            }
+        vp_load(ln, sk, hq.Q, pos, 0u);
+        while (ln.ev != EV_INIT) {
             if (ln.ev == EV_COLL) {
                 vp_collide<BW>(S, G, mu, inv_mu, ln, sk);
             } else if (ln.ev == EV_SCAT) {

@@ -105,7 +105,11 @@ def test_volpathsimple_backward(oracle, gpu_ctx, setup, tracer):
     gpu_ctx.render_backward(seed_grad, spp_grad, to_cuda(grad_img))
     ggs, gga = gpu_ctx.grad_read()
     oc, gc = oracle.counters(True), gpu_ctx.counters(True)
-    assert [int(v) for v in oc[2:6]] == [int(v) for v in gc[2:6]], (oc, gc)
+    assert [int(v) for v in oc[3:6]] == [int(v) for v in gc[3:6]], (oc, gc)
+    if tracer in (1, 2):
+        assert int(oc[2]) == int(gc[2])            # straight replay: every collision is repeated
+    else:
+        assert int(gc[2]) < 0.7 * int(oc[2])       # vertex-list adjoint: only the shadow rays are traced again
     assert rel_l2(ggs.cpu().numpy(), gs) < GRAD_TOL
     assert rel_l2(gga.cpu().numpy(), ga) < GRAD_TOL
     assert rel_l2(ggs.cpu().numpy(), gs) < 1e-4    # float atomics vs double accumulation
