@@ -224,6 +224,7 @@ int rcv_ctx_create(int device, void *stream, rcv_ctx **out) {
     c->l2_persist_max = (size_t) prop.persistingL2CacheMaxSize;
     c->l2_window_max = (size_t) prop.accessPolicyMaxWindowSize;
     if (const char *e = getenv("RCV_L2_PERSIST")) c->l2_persist = atoi(e) != 0;
+    if (getenv("RCV_VERBOSE")) fprintf(stderr, "rcv: L2 %d MB, persisting max %zu MB, window max %zu MB\n", prop.l2CacheSize >> 20, c->l2_persist_max >> 20, c->l2_window_max >> 20);
     if (c->l2_persist && c->l2_persist_max > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, c->l2_persist_max);
     CK(cudaMalloc(&c->counters, sizeof(Counters)));
     CK(cudaMemset(c->counters, 0, sizeof(Counters)));
@@ -425,6 +426,7 @@ int rcv_render_backward(rcv_ctx *c, int adjoint_kind, uint32_t seed_grad, uint32
         cudaStreamAttrValue a{};
         a.accessPolicyWindow.num_bytes = 0;
         CK(cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &a));
+        CK(cudaCtxResetPersistingL2Cache());       // give the set-aside lines back to the kernels that follow
     }
     return RCV_OK;
 }
