@@ -424,16 +424,22 @@ __device__ __forceinline__ size_t tri_voxel(const GridK &G, const Tri &T, int k)
     return ((size_t) z * G.ny + y) * G.nx + x;
 }
 
-// brick loads: read-only; with RCV_BRICK_STREAMING they are marked evict-first in L2 (ld.global.cs) so that
-// the brick stream (0.5 - 1 GB at 256^3, no reuse) does not evict the gradient grid the adjoint reduces into
-#ifndef RCV_BRICK_STREAMING
-#define RCV_BRICK_STREAMING 0
+// brick loads: read-only, one 256-bit load per 32 bytes (sm_100 LDG.256: half the load instructions and half the L1
+// wavefronts of 128-bit loads) with the L2::64B prefetch-size hint — without it every L2 miss of these random
+// gathers fetches a 128-byte line from HBM (measured: scripts/microbench/gather_bw.cu, profiles/README.md).
+// RCV_BRICK_LOAD: 0 = four/two 128-bit __ldg, 1 = 256-bit, 2 = 256-bit + L2::64B (default)
+#ifndef RCV_BRICK_LOAD
+#define RCV_BRICK_LOAD 2
 #endif
-__device__ __forceinline__ float4 ld_brick(const float4 *p) {
-#if RCV_BRICK_STREAMING && defined(__CUDA_ARCH__)
-    return __ldcs(p);
+__device__ __forceinline__ void ld_brick32(const float4 *p, float4 &a, float4 &b) {
+#if RCV_BRICK_LOAD == 0 || !defined(__CUDA_ARCH__)
+    a = __ldg(p); b = __ldg(p + 1);
+#elif RCV_BRICK_LOAD == 1
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
 #else
-    return __ldg(p);
+    asm("ld.global.nc.L2::64B.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
 #endif
 }
 
@@ -441,7 +447,8 @@ __device__ __forceinline__ float4 ld_brick(const float4 *p) {
 __device__ __forceinline__ void lookup_sigma2(const SceneK &S, const GridK &G, const Tri &T, float &s_old, float &s_new) {
     if (!T.inside) { s_old = 0.f; s_new = 0.f; return; }
     const float4 *b = G.blk2 + 4 * tri_cell(G, T);
-    float4 q0 = ld_brick(b), q1 = ld_brick(b + 1), q2 = ld_brick(b + 2), q3 = ld_brick(b + 3);   // one 64-byte brick
+    float4 q0, q1, q2, q3;
+    ld_brick32(b, q0, q1); ld_brick32(b + 2, q2, q3);                                // one 64-byte brick
     s_old = S.scale * tri_lerp(T, q0.x, q0.z, q1.x, q1.z, q2.x, q2.z, q3.x, q3.z);
     s_new = S.scale * tri_lerp(T, q0.y, q0.w, q1.y, q1.w, q2.y, q2.w, q3.y, q3.w);
 }
@@ -449,8 +456,19 @@ __device__ __forceinline__ void lookup_sigma2(const SceneK &S, const GridK &G, c
 __device__ __forceinline__ float lookup_sigma1(const SceneK &S, const GridK &G, const Tri &T) {
     if (!T.inside) return 0.f;
     const float4 *b = G.blk1 + 2 * tri_cell(G, T);
-    float4 q0 = ld_brick(b), q1 = ld_brick(b + 1);                                   // one 32-byte brick
+    float4 q0, q1;
+    ld_brick32(b, q0, q1);                                                           // one 32-byte brick
     return S.scale * tri_lerp(T, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w);
+}
+// 16-byte read-only load with the same L2::64B hint (albedo corners: scattered 32-byte voxel records)
+__device__ __forceinline__ float4 ld_corner16(const float4 *p) {
+#if RCV_BRICK_LOAD != 2 || !defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    float4 a;
+    asm("ld.global.nc.L2::64B.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(p));
+    return a;
+#endif
 }
 // albedo of state s (0 = old, 1 = new)
 __device__ __forceinline__ V3 lookup_albedo(const GridK &G, const Tri &T, int s) {
@@ -460,12 +478,30 @@ __device__ __forceinline__ V3 lookup_albedo(const GridK &G, const Tri &T, int s)
     float4 v[8];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        v[2 * k] = __ldg(G.alb2 + 2 * (r[k] + T.x0) + s);
-        v[2 * k + 1] = __ldg(G.alb2 + 2 * (r[k] + T.x1) + s);
+        v[2 * k] = ld_corner16(G.alb2 + 2 * (r[k] + T.x0) + s);
+        v[2 * k + 1] = ld_corner16(G.alb2 + 2 * (r[k] + T.x1) + s);
     }
     return mk3(tri_lerp(T, v[0].x, v[1].x, v[2].x, v[3].x, v[4].x, v[5].x, v[6].x, v[7].x),
                tri_lerp(T, v[0].y, v[1].y, v[2].y, v[3].y, v[4].y, v[5].y, v[6].y, v[7].y),
                tri_lerp(T, v[0].z, v[1].z, v[2].z, v[3].z, v[4].z, v[5].z, v[6].z, v[7].z));
+}
+// both states' albedo: the two records of a voxel are adjacent, one 256-bit load per corner
+__device__ __forceinline__ void lookup_albedo2(const GridK &G, const Tri &T, V3 &a_old, V3 &a_new) {
+    if (!T.inside) { a_old = mk3(0, 0, 0); a_new = mk3(0, 0, 0); return; }
+    size_t r[4];
+    tri_rows(G, T, r);
+    float4 o[8], n[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        ld_brick32(G.alb2 + 2 * (r[k] + T.x0), o[2 * k], n[2 * k]);
+        ld_brick32(G.alb2 + 2 * (r[k] + T.x1), o[2 * k + 1], n[2 * k + 1]);
+    }
+    a_old = mk3(tri_lerp(T, o[0].x, o[1].x, o[2].x, o[3].x, o[4].x, o[5].x, o[6].x, o[7].x),
+                tri_lerp(T, o[0].y, o[1].y, o[2].y, o[3].y, o[4].y, o[5].y, o[6].y, o[7].y),
+                tri_lerp(T, o[0].z, o[1].z, o[2].z, o[3].z, o[4].z, o[5].z, o[6].z, o[7].z));
+    a_new = mk3(tri_lerp(T, n[0].x, n[1].x, n[2].x, n[3].x, n[4].x, n[5].x, n[6].x, n[7].x),
+                tri_lerp(T, n[0].y, n[1].y, n[2].y, n[3].y, n[4].y, n[5].y, n[6].y, n[7].y),
+                tri_lerp(T, n[0].z, n[1].z, n[2].z, n[3].z, n[4].z, n[5].z, n[6].z, n[7].z));
 }
 
 // ----------------------------------------------------------------------------

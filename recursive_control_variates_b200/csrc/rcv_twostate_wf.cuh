@@ -243,8 +243,9 @@ __device__ __forceinline__ void ts_scatter(const SceneK &S, const GridK &G, TsLa
     sk.n_scat++;
     const float st_old = ln.tr_old, st_new = ln.tr_new;
     Tri T = tri_setup(S, G, ln.o);
-    V3 a_new = (MODE == 1) ? lookup_albedo(G, T, 0) : lookup_albedo(G, T, 1);
-    V3 a_old = (MODE == 0) ? lookup_albedo(G, T, 0) : a_new;
+    V3 a_new, a_old;
+    if (MODE == 0) lookup_albedo2(G, T, a_old, a_new);
+    else { a_new = lookup_albedo(G, T, MODE == 1 ? 0 : 1); a_old = a_new; }
     V3 ss_new = splat3(st_new) * a_new, ss_old = splat3(st_old) * a_old;
     float rden = 1.f / (st_new + st_old);                             // :259-260
     ln.thr_new = ln.thr_new * ((ss_new * 2.f) * rden);

@@ -57,7 +57,9 @@ def test_twostates_image(oracle, gpu_ctx, setup):
 def test_identity_H_equals_F(gpu_ctx, setup):
     gpu_set_states(gpu_ctx, setup["new"], setup["new"])
     H, F = gpu_ctx.render_twostates(seed=11, spp=4)
-    assert np.array_equal(H.cpu().numpy(), F.cpu().numpy())
+    # identical states give identical per-lane radiance; the two film accumulators receive their atomic adds in
+    # (possibly) different orders, so the images agree to rounding, not bit for bit
+    assert rel_l2(H.cpu().numpy(), F.cpu().numpy()) < 1e-6
     gpu_set_states(gpu_ctx, setup["old"], setup["new"])
 
 
@@ -230,7 +232,9 @@ def test_large_config_properties(gpu_ctx):
     new = make_medium(128, "plume", 5e-3)
     gpu_set_states(gpu_ctx, new, new)
     H, F = gpu_ctx.render_twostates(seed=1, spp=16)
-    assert np.array_equal(H.cpu().numpy(), F.cpu().numpy())
+    # identical states give identical per-lane radiance; the two film accumulators receive their atomic adds in
+    # (possibly) different orders, so the images agree to rounding, not bit for bit
+    assert rel_l2(H.cpu().numpy(), F.cpu().numpy()) < 1e-6
     full = gpu_ctx.render_twostates_accum(seed=2, spp=16)
     part = gpu_ctx.render_twostates_accum(seed=2, spp=16, spp_begin=0, spp_end=5)
     part = gpu_ctx.render_twostates_accum(seed=2, spp=16, spp_begin=5, spp_end=16, out=part)
