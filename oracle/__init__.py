@@ -26,7 +26,8 @@ _u64p = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
 class Medium(C.Structure):
     _fields_ = [("sigma_t", C.c_void_p), ("albedo", C.c_void_p),
                 ("nz", C.c_int32), ("ny", C.c_int32), ("nx", C.c_int32),
-                ("majorant", C.c_float)]
+                ("majorant", C.c_float),
+                ("majorant_grid", C.c_void_p), ("mz", C.c_int32), ("my", C.c_int32), ("mx", C.c_int32)]
 
 
 def build(force: bool = False) -> str:
@@ -52,7 +53,9 @@ def lib() -> C.CDLL:
         L.orc_logf.argtypes = [f]; L.orc_logf.restype = f
         L.orc_sincosf.argtypes = [f, C.POINTER(f), C.POINTER(f)]
         L.orc_majorant.argtypes = [SP, _f32p, C.c_size_t]; L.orc_majorant.restype = f
+        L.orc_majorant_grid.argtypes = [SP, _f32p, i32, i32, i32, i32, _f32p]; L.orc_majorant_grid.restype = i32
         L.orc_alt_seed.argtypes = [u32]; L.orc_alt_seed.restype = u32
+        L.orc_dda_sample.argtypes = [SP, C.c_void_p, MP, _f32p, _f32p, f, f, f]; L.orc_dda_sample.restype = f
         L.orc_counters.argtypes = [_u64p, i32]
         L.orc_twostates_lanes.argtypes = [SP, MP, MP, u32, u32, u64, u64, _f32p, _f32p, _i32p, i32]
         L.orc_render_twostates.argtypes = [SP, MP, MP, u32, u32, u32, u32, _f32p, _f32p, i32]
@@ -98,6 +101,12 @@ def sincosf(x: float):
     return s.value, c.value
 
 
+def dda_sample(desc, m_old, m_new, o, d, mint, maxt, tau) -> float:
+    """Free-flight distance through the majorant supergrid(s) (test hook); m_old may be None."""
+    return float(lib().orc_dda_sample(C.addressof(desc), C.addressof(m_old.c) if m_old is not None else None, C.byref(m_new.c),
+                                      np.asarray(o, np.float32), np.asarray(d, np.float32), mint, maxt, tau))
+
+
 def alt_seed(seed_grad: int) -> int:
     return lib().orc_alt_seed(seed_grad)
 
@@ -111,7 +120,9 @@ def counters(reset: bool = True) -> np.ndarray:
 class OracleMedium:
     """One medium state; keeps the numpy arrays alive for the C struct."""
 
-    def __init__(self, desc, sigma_t: np.ndarray, albedo: np.ndarray):
+    def __init__(self, desc, sigma_t: np.ndarray, albedo: np.ndarray, majorant_factor: int = 0):
+        """majorant_factor > 0: majorant supergrid with cells of that many voxels (heterogeneous
+        `majorant_resolution_factor`); 0: one majorant for the whole volume."""
         self.sigma_t = np.ascontiguousarray(sigma_t, dtype=np.float32)
         self.albedo = np.ascontiguousarray(albedo, dtype=np.float32)
         nz, ny, nx = self.sigma_t.shape[:3]
@@ -122,6 +133,17 @@ class OracleMedium:
         self.c.albedo = self.albedo.ctypes.data
         self.c.nz, self.c.ny, self.c.nx = nz, ny, nx
         self.c.majorant = lib().orc_majorant(C.addressof(desc), self.sigma_t.reshape(-1), self.sigma_t.size)
+        self.majorant_grid = None
+        self.c.majorant_grid = None
+        if majorant_factor > 0:
+            f = int(majorant_factor)
+            if nz % f or ny % f or nx % f:
+                raise ValueError(f"grid resolution {(nz, ny, nx)} must be divisible by the majorant factor {f}")
+            self.majorant_grid = np.zeros((nz // f, ny // f, nx // f), np.float32)
+            rc = lib().orc_majorant_grid(C.addressof(desc), self.sigma_t.reshape(-1), nz, ny, nx, f, self.majorant_grid.reshape(-1))
+            assert rc == 0
+            self.c.majorant_grid = self.majorant_grid.ctypes.data
+            self.c.mz, self.c.my, self.c.mx = self.majorant_grid.shape
 
     @property
     def majorant(self) -> float:

@@ -352,6 +352,106 @@ float orc_majorant(const rcv_scene_desc *S, const float *sigma_t, size_t n) {
 /* ------------------------------------------------------------------------- */
 /* event counters (roofline accounting + path-identity checks)               */
 /* ------------------------------------------------------------------------- */
+/* ------------------------------------------------------------------------- */
+/* majorant supergrid  [UPSTREAM heterogeneous.cpp update_majorant_supergrid /  */
+/* gridvolume.cpp local_majorants; sources absent from /root/reference, restated */
+/* from the published Mitsuba 3 algorithm — [SPEC] marks the choices made here]  */
+/* Each supergrid cell stores scale * max of the fine voxels whose trilinear      */
+/* support can reach the cell: voxel indices [c*f - 1, c*f + f] per axis, clamped.*/
+/* ------------------------------------------------------------------------- */
+int orc_majorant_grid(const rcv_scene_desc *S, const float *sigma_t, int nz, int ny, int nx, int factor, float *out) {
+    if (factor <= 0 || nz % factor || ny % factor || nx % factor) return -1;
+    int mz = nz / factor, my = ny / factor, mx = nx / factor;
+    for (int cz = 0; cz < mz; ++cz)
+        for (int cy = 0; cy < my; ++cy)
+            for (int cx = 0; cx < mx; ++cx) {
+                float m = 0.f;                                   /* densities are >= 0 */
+                for (int dz = -1; dz <= factor; ++dz)
+                    for (int dy = -1; dy <= factor; ++dy)
+                        for (int dx = -1; dx <= factor; ++dx) {
+                            int z = cz * factor + dz, y = cy * factor + dy, x = cx * factor + dx;
+                            z = z < 0 ? 0 : (z > nz - 1 ? nz - 1 : z);
+                            y = y < 0 ? 0 : (y > ny - 1 ? ny - 1 : y);
+                            x = x < 0 ? 0 : (x > nx - 1 ? nx - 1 : x);
+                            m = fmaxf_(m, sigma_t[((size_t) z * ny + y) * nx + x]);
+                        }
+                out[((size_t) cz * my + cy) * mx + cx] = S->sigma_t_scale * m;
+            }
+    return 0;
+}
+
+/* nearest-neighbour lookup of the supergrid at a world position (majorant_grid.eval_1), clamped to the border cells */
+static inline float majorant_at(const rcv_scene_desc *S, const orc_medium *M, v3 p) {
+    float pp[3] = {p.x, p.y, p.z};
+    int res[3] = {M->mx, M->my, M->mz}, idx[3];
+    for (int a = 0; a < 3; ++a) {
+        float ext_inv = 1.f / (S->bbox_max[a] - S->bbox_min[a]);
+        float pl = (pp[a] - S->bbox_min[a]) * ext_inv;
+        int i = (int) floorf(pl * (float) res[a]);               /* [SPEC] clamped, no inside test: see dda_sample */
+        idx[a] = i < 0 ? 0 : (i > res[a] - 1 ? res[a] - 1 : i);
+    }
+    return M->majorant_grid[((size_t) idx[2] * M->my + idx[1]) * M->mx + idx[0]];
+}
+/* max over the one or two states that take part (Mo may be NULL) */
+static inline float majorant2_at(const rcv_scene_desc *S, const orc_medium *Mo, const orc_medium *Mn, v3 p) {
+    float m = majorant_at(S, Mn, p);
+    return Mo ? fmaxf_(majorant_at(S, Mo, p), m) : m;
+}
+
+/* DDA free-flight sampling through the supergrid (twostatemedium.py:25-70; Medium::prepare_dda_traversal and the
+ * identical single-state loop of Medium::sample_interaction are [UPSTREAM]).  Returns the sampled t or inf. */
+static float dda_sample(const rcv_scene_desc *S, const orc_medium *Mo, const orc_medium *Mn, const ray_t *ray,
+                        float mint, float maxt, float desired_tau) {
+    /* prepare_dda_traversal: the ray in the unit cube of the supergrid */
+    float o[3] = {ray->o.x, ray->o.y, ray->o.z}, d[3] = {ray->d.x, ray->d.y, ray->d.z};
+    int res[3] = {Mn->mx, Mn->my, Mn->mz};
+    float tmax3[3], tdelta[3];
+    for (int a = 0; a < 3; ++a) {
+        float ext_inv = 1.f / (S->bbox_max[a] - S->bbox_min[a]);
+        float lo = (o[a] - S->bbox_min[a]) * ext_inv, ld = d[a] * ext_inv;
+        float fres = (float) res[a], voxel = 1.f / fres;
+        int cur = (int) floorf(fmaf(ld, mint, lo) * fres);       /* [SPEC] p * res instead of p / voxel_size */
+        int last = (int) floorf(fmaf(ld, maxt, lo) * fres);
+        cur = cur < 0 ? 0 : (cur > res[a] - 1 ? res[a] - 1 : cur);
+        last = last < 0 ? 0 : (last > res[a] - 1 ? res[a] - 1 : last);
+        int step = (ld >= 0.f) ? 1 : -1;
+        float nb = (float) (cur + step) * voxel;
+        if (cur != last && ld < 0.f) nb += voxel;
+        if (ld != 0.f) {
+            float rld = 1.f / ld;                                /* [SPEC] one reciprocal per axis */
+            tmax3[a] = (nb - lo) * rld;
+            tdelta[a] = ((float) step * voxel) * rld;
+        } else {
+            tmax3[a] = ORC_INF; tdelta[a] = ORC_INF;
+        }
+    }
+    float dda_t = mint, tau_acc = 0.f;
+    int reached = 0, active = 1;
+    while (active) {                                             /* :39-66 */
+        float t_next = fminf_(fminf_(tmax3[0], tmax3[1]), tmax3[2]);
+        int axis = (tmax3[0] == t_next) ? 0 : ((tmax3[1] == t_next) ? 1 : 2);   /* first axis that attains the minimum */
+        /* :53 looks the cell up at the midpoint of [dda_t, t_next].  In the last cell t_next can lie beyond the
+         * exit (prepare_dda_traversal puts the next boundary of an axis the ray no longer crosses one cell
+         * further), so the midpoint may leave the volume or the cell; [SPEC] clip the interval to maxt first. */
+        float tmid = 0.5f * (dda_t + fminf_(t_next, maxt));
+        float majorant = majorant2_at(S, Mo, Mn, ray_at(ray->o, ray->d, tmid));
+        float tau_next = tau_acc + (majorant * (t_next - dda_t));
+        float t_precise = dda_t + ((desired_tau - tau_acc) / majorant);
+        reached = reached || ((majorant > 0.f) && (t_precise < maxt) && (tau_next >= desired_tau));
+        dda_t = reached ? t_precise : t_next;
+        active = !reached && (t_next < maxt);
+        if (active) { tmax3[axis] = tmax3[axis] + tdelta[axis]; tau_acc = tau_next; }
+    }
+    return reached ? dda_t : ORC_INF;                            /* :70 */
+}
+
+/* test hook: the DDA alone (single state when Mo == NULL) */
+float orc_dda_sample(const rcv_scene_desc *S, const orc_medium *Mo, const orc_medium *Mn, const float o[3], const float d[3],
+                     float mint, float maxt, float desired_tau) {
+    ray_t r; r.o = V3(o[0], o[1], o[2]); r.d = V3(d[0], d[1], d[2]); r.maxt = maxt;
+    return dda_sample(S, Mo, Mn, &r, mint, maxt, desired_tau);
+}
+
 typedef struct { uint64_t c[8]; } counters_t;
 static counters_t g_counters;
 void orc_counters(uint64_t out[8], int reset) {
@@ -466,15 +566,23 @@ static void sample_interaction_twostates(const rcv_scene_desc *S, const orc_medi
     float mint, maxt;
     active = prepare_interaction_sampling(S, ray, active, &mint, &maxt);       /* :22 */
     float desired_tau = -orc_logf(1.f - sample);                               /* :24 */
-    /* single majorant for the whole volume (:71-78); majorant supergrid (:25-70) is a "next" row */
-    float combined_extinction = fmaxf_(Mo->majorant, Mn->majorant);            /* :73-75 */
-    float m = combined_extinction;                                             /* :76, channel 0 */
-    float inv_m = 1.f / m;                                                     /* [SPEC] x / majorant == x * (1 / majorant) */
-    float sampled_t = mint + (desired_tau * inv_m);                            /* :78 */
+    float combined_extinction, sampled_t;
+    if (Mn->majorant_grid) {
+        /* spatially varying majorant: DDA through max(old, new) supergrids (:25-70) */
+        sampled_t = active ? dda_sample(S, Mo, Mn, ray, mint, maxt, desired_tau) : ORC_INF;
+        combined_extinction = 0.f;
+    } else {
+        /* single majorant for the whole volume (:71-78) */
+        combined_extinction = fmaxf_(Mo->majorant, Mn->majorant);              /* :73-75 */
+        float m = combined_extinction;                                         /* :76, channel 0 */
+        float inv_m = 1.f / m;                                                 /* [SPEC] x / majorant == x * (1 / majorant) */
+        sampled_t = mint + (desired_tau * inv_m);                              /* :78 */
+    }
     int valid_mi = active && (sampled_t <= maxt);                              /* :80 */
     mei_t mn;
     mn.t = valid_mi ? sampled_t : ORC_INF;                                     /* :88 */
     mn.p = ray_at(ray->o, ray->d, sampled_t);                                  /* :89 */
+    if (Mn->majorant_grid && valid_mi) combined_extinction = majorant2_at(S, Mo, Mn, mn.p);   /* :82-86 */
     mn.mint = mint;
     v3 ss_o = V3(0, 0, 0), st_o = V3(0, 0, 0), ss_n = V3(0, 0, 0), st_n = V3(0, 0, 0);
     if (valid_mi) {
@@ -941,13 +1049,18 @@ static void sample_interaction(const rcv_scene_desc *S, const orc_medium *M, con
     float mint, maxt;
     active = prepare_interaction_sampling(S, ray, active, &mint, &maxt);
     float desired_tau = -orc_logf(1.f - sample);
-    float m = M->majorant;
-    float inv_m = 1.f / m;                           /* [SPEC] reciprocal majorant */
-    float sampled_t = mint + (desired_tau * inv_m);
+    float m = M->majorant, sampled_t;
+    if (M->majorant_grid) {
+        sampled_t = active ? dda_sample(S, NULL, M, ray, mint, maxt, desired_tau) : ORC_INF;
+    } else {
+        float inv_m = 1.f / m;                       /* [SPEC] reciprocal majorant */
+        sampled_t = mint + (desired_tau * inv_m);
+    }
     int valid = active && (sampled_t <= maxt);
     mei->t = valid ? sampled_t : ORC_INF;
     mei->p = ray_at(ray->o, ray->d, sampled_t);
     mei->mint = mint;
+    if (M->majorant_grid && valid) m = majorant_at(S, M, mei->p);   /* the local majorant at the sampled point */
     v3 st = V3(0, 0, 0), ss = V3(0, 0, 0);
     if (valid) {
         tri_t T = tri_setup(S, M, mei->p);
@@ -997,7 +1110,8 @@ static void sample_real_interaction(const rcv_scene_desc *S, const orc_medium *M
         float s = lookup_sigma_t(S, M, &T);
         v3 a = lookup_albedo(M, &T);
         mei->sigma_t = V3(s, s, s); mei->sigma_s = vmul(mei->sigma_t, a);
-        mei->sigma_n = vsub(V3(M->majorant, M->majorant, M->majorant), mei->sigma_t);
+        { float mj = M->majorant_grid ? majorant_at(S, M, mei->p) : M->majorant;
+          mei->sigma_n = vsub(V3(mj, mj, mj), mei->sigma_t); }
         cnt->c[3]++;
     }
 }

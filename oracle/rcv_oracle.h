@@ -19,6 +19,9 @@ typedef struct orc_medium {
     const float *albedo;    /* (nz,ny,nx,3) */
     int32_t nz, ny, nx;
     float majorant;         /* scale * max(sigma_t) */
+    /* majorant supergrid (heterogeneous `majorant_resolution_factor` > 0), NULL = one majorant for the volume */
+    const float *majorant_grid;   /* (mz,my,mx), scale baked in */
+    int32_t mz, my, mx;
 } orc_medium;
 
 void orc_tea32(uint32_t v0, uint32_t v1, uint32_t *o0, uint32_t *o1);
@@ -27,6 +30,10 @@ float orc_u32_to_f32(uint32_t v);
 float orc_logf(float x);
 void orc_sincosf(float x, float *s, float *c);
 float orc_majorant(const rcv_scene_desc *S, const float *sigma_t, size_t n);
+/* local majorants of a (nz,ny,nx) grid on a supergrid with cells of `factor` voxels; out: (nz/f, ny/f, nx/f); -1 if not divisible */
+int orc_majorant_grid(const rcv_scene_desc *S, const float *sigma_t, int nz, int ny, int nx, int factor, float *out);
+float orc_dda_sample(const rcv_scene_desc *S, const orc_medium *Mo, const orc_medium *Mn, const float o[3], const float d[3],
+                     float mint, float maxt, float desired_tau);
 uint32_t orc_alt_seed(uint32_t seed_grad);
 void orc_counters(uint64_t out[8], int reset);
 

@@ -84,6 +84,8 @@ _SIGNATURES = {
     "rcv_medium_rotate": [_P, _P, _P, C.c_int, C.c_int, C.c_int],
     "rcv_medium_majorants_host": [_P, C.POINTER(_f * 2)],
     "rcv_medium_read": [_P, C.c_int, _P, _P],
+    "rcv_medium_set_majorant_factor": [_P, C.c_int],
+    "rcv_medium_majorant_grid_host": [_P, _P, _P, C.POINTER(C.c_int * 3)],
     "rcv_render_twostates": [_P, _u32, _u32, _u32, _u32, _P, _P],
     "rcv_render_primal": [_P, C.c_int, _u32, _u32, _u32, _u32, _P],
     "rcv_develop": [_P, _P, _P],

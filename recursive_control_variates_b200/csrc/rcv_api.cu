@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "../../include/rcv_b200.h"
 #include "rcv_internal.h"
@@ -49,6 +50,10 @@ struct rcv_ctx {
     size_t nvox = 0;
     float2 *sig2 = nullptr;
     float4 *blk2 = nullptr, *blk1 = nullptr;
+    int maj_factor = 0;           // majorant supergrid: voxels per supercell side (0 = one majorant for the volume)
+    float2 *mgrid = nullptr;      // (old, new) local majorants, (nz/f, ny/f, nx/f)
+    size_t mgrid_cells = 0;
+    bool mgrid_valid = false;     // mgrid matches the current grids and factor
     float4 *alb2 = nullptr;
     float *grad = nullptr;       // [pad4(nvox) floats d sigma_t][nvox float4 d albedo]
     size_t grad_floats = 0;
@@ -92,9 +97,14 @@ struct rcv_ctx {
         g.gsig = grad; g.galb = (float4 *) (grad + ((nvox + 3) / 4) * 4);
         return g;
     }
-    GridK gridk() const {
-        GridK g;
+    GridKS gridk() const {
+        GridKS g;
         g.sig2 = sig2; g.blk2 = blk2; g.blk1 = blk1; g.alb2 = alb2; g.nx = nx; g.ny = ny; g.nz = nz; g.majorants = majorants;
+        g.mgrid = nullptr; g.mx = g.my = g.mz = 0; g.vox[0] = g.vox[1] = g.vox[2] = 0.f;
+        if (maj_factor > 0 && mgrid_valid) {
+            g.mgrid = mgrid; g.mx = nx / maj_factor; g.my = ny / maj_factor; g.mz = nz / maj_factor;
+            g.vox[0] = 1.f / (float) g.mx; g.vox[1] = 1.f / (float) g.my; g.vox[2] = 1.f / (float) g.mz;
+        }
         return g;
     }
 };
@@ -183,6 +193,25 @@ int ensure_arena(rcv_ctx *c) {
     return RCV_OK;
 }
 
+// (re)build the majorant supergrid from the current two-state grid.  No-op while the factor is 0 or no medium is set;
+// a factor that does not divide the current grid leaves the supergrid invalid (renders are refused until the next
+// rotation brings a grid it divides: utils.py:177-192 changes the factor before it pushes the upsampled grid).
+int build_majorant_grid(rcv_ctx *c) {
+    c->mgrid_valid = false;
+    if (c->maj_factor <= 0 || !c->sig2) return RCV_OK;
+    const int f = c->maj_factor;
+    if (c->nz % f || c->ny % f || c->nx % f) return RCV_OK;
+    size_t cells = (size_t) (c->nz / f) * (c->ny / f) * (c->nx / f);
+    if (cells > c->mgrid_cells) {
+        cudaFree(c->mgrid); c->mgrid = nullptr; c->mgrid_cells = 0;
+        CK(cudaMalloc(&c->mgrid, cells * sizeof(float2)));
+        c->mgrid_cells = cells;
+    }
+    CK(launch_majorant_grid(c->cfg(), c->sig2, c->nz, c->ny, c->nx, f, c->S.scale, c->mgrid));
+    c->mgrid_valid = true;
+    return RCV_OK;
+}
+
 int ensure_film_w(rcv_ctx *c) {
     size_t npix = (size_t) c->S.W * c->S.H;
     if (c->film_w_pix != npix) {
@@ -242,7 +271,7 @@ int rcv_ctx_destroy(rcv_ctx *c) {
     cudaSetDevice(c->device);
     free_medium(c);
     cudaFree(c->counters); cudaFree(c->work); cudaFree(c->majorants); cudaFree(c->film_w); cudaFree(c->loss_partial);
-    cudaFree(c->queue.r0); cudaFree(c->queue.r1); cudaFree(c->queue.r2); cudaFree(c->queue.count); cudaFree(c->arena);
+    cudaFree(c->queue.r0); cudaFree(c->queue.r1); cudaFree(c->queue.r2); cudaFree(c->queue.count); cudaFree(c->arena); cudaFree(c->mgrid);
     auto &E = c->e2e;
     cudaFree(E.sigma); cudaFree(E.albedo); cudaFree(E.ref); cudaFree(E.acc); cudaFree(E.HF); cudaFree(E.cv);
     cudaFree(E.grad_img); cudaFree(E.loss); cudaFree(E.g_sigma); cudaFree(E.g_albedo);
@@ -280,6 +309,8 @@ int rcv_medium_rotate(rcv_ctx *c, const float *sigma_t_in, const float *albedo_i
     if (int r = use_device(c)) return r;
     if (!c->has_scene) return fail(RCV_ERR_STATE, "rcv_scene_set must be called before rcv_medium_rotate");
     if (!sigma_t_in || !albedo_in || nz <= 0 || ny <= 0 || nx <= 0) return fail(RCV_ERR_ARG, "invalid grid");
+    if (c->maj_factor > 0 && (nz % c->maj_factor || ny % c->maj_factor || nx % c->maj_factor))
+        return fail(RCV_ERR_ARG, "grid resolution must be divisible by the majorant resolution factor");
     size_t nvox = (size_t) nz * ny * nx;
     LaunchCfg cfg = c->cfg();
     if (nz != c->nz || ny != c->ny || nx != c->nx) {
@@ -311,6 +342,30 @@ int rcv_medium_rotate(rcv_ctx *c, const float *sigma_t_in, const float *albedo_i
     }
     CK(launch_rotate(cfg, sigma_t_in, albedo_in, nz, ny, nx, c->S.scale, c->sig2, c->blk2, c->blk1, c->alb2, c->block_max,
                      c->n_rot_blocks, c->majorants));
+    return build_majorant_grid(c);
+}
+
+int rcv_medium_set_majorant_factor(rcv_ctx *c, int factor) {
+    if (int r = use_device(c)) return r;
+    if (factor < 0) return fail(RCV_ERR_ARG, "majorant resolution factor must be >= 0");
+    if (factor == 1) factor = 0;     /* utils.py:36-37: a factor <= 1 disables the supergrid */
+    c->maj_factor = factor;
+    return build_majorant_grid(c);
+}
+
+int rcv_medium_majorant_grid_host(rcv_ctx *c, float *out_old, float *out_new, int dims[3]) {
+    if (int r = use_device(c)) return r;
+    if (!dims) return fail(RCV_ERR_ARG, "null argument");
+    dims[0] = dims[1] = dims[2] = 0;
+    if (c->maj_factor <= 0 || !c->mgrid_valid) return RCV_OK;
+    int mz = c->nz / c->maj_factor, my = c->ny / c->maj_factor, mx = c->nx / c->maj_factor;
+    dims[0] = mz; dims[1] = my; dims[2] = mx;
+    if (!out_old && !out_new) return RCV_OK;
+    size_t n = (size_t) mz * my * mx;
+    std::vector<float2> h(n);
+    CK(cudaMemcpyAsync(h.data(), c->mgrid, n * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < n; ++i) { if (out_old) out_old[i] = h[i].x; if (out_new) out_new[i] = h[i].y; }
     return RCV_OK;
 }
 
@@ -334,6 +389,8 @@ static int check_render(rcv_ctx *c, uint32_t spp, uint32_t b, uint32_t e) {
     if (!c->has_scene) return fail(RCV_ERR_STATE, "no scene set");
     if (!c->sig2) return fail(RCV_ERR_STATE, "no medium state (call rcv_medium_rotate)");
     if (spp == 0 || b > e || e > spp) return fail(RCV_ERR_ARG, "invalid sample range");
+    if (c->maj_factor > 0 && !c->mgrid_valid)
+        return fail(RCV_ERR_STATE, "the majorant resolution factor does not divide the current grid resolution");
     if ((uint64_t) c->S.W * c->S.H * spp > 0xffffffffull) return fail(RCV_ERR_ARG, "wavefront exceeds 2^32 lanes");
     if (c->tracer == RCV_TRACER_WAVEFRONT || c->tracer == RCV_TRACER_POOL)
         if (int r = ensure_queue(c, b, e)) return r;

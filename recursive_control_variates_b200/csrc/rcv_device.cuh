@@ -69,12 +69,22 @@ struct SceneK {
 // corner order k = 4*zbit + 2*ybit + xbit.  A tentative collision therefore reads ONE
 // contiguous brick instead of eight scattered voxels.
 struct GridK {
+    static constexpr bool kSupergrid = false;
     const float2 *sig2;
     const float4 *blk2;
     const float4 *blk1;
     const float4 *alb2;
     int nx, ny, nz;
     const float *majorants;   // device: [0] = old, [1] = new  (scale * max)
+};
+// ... plus the majorant supergrid (heterogeneous `majorant_resolution_factor` > 0): per supercell of f^3 voxels the
+// (old, new) local majorants, scale baked in.  Kernels are instantiated for GridK (one majorant for the volume) and
+// for GridKS (DDA free-flight sampling through the supergrid, twostatemedium.py:25-70).
+struct GridKS : GridK {
+    static constexpr bool kSupergrid = true;
+    const float2 *mgrid;      // [(z * my + y) * mx + x]
+    int mx, my, mz;
+    float vox[3];             // 1 / (mx, my, mz)
 };
 
 // gradient grids: d sigma_t as one float per voxel — dense, so the
@@ -502,6 +512,69 @@ __device__ __forceinline__ void lookup_albedo2(const GridK &G, const Tri &T, V3 
     a_new = mk3(tri_lerp(T, n[0].x, n[1].x, n[2].x, n[3].x, n[4].x, n[5].x, n[6].x, n[7].x),
                 tri_lerp(T, n[0].y, n[1].y, n[2].y, n[3].y, n[4].y, n[5].y, n[6].y, n[7].y),
                 tri_lerp(T, n[0].z, n[1].z, n[2].z, n[3].z, n[4].z, n[5].z, n[6].z, n[7].z));
+}
+
+// ----------------------------------------------------------------------------
+// majorant supergrid: nearest lookup (clamped) and DDA free-flight sampling.
+// The arithmetic and its order are part of the numerical specification: the CPU restatement used by
+// the tests evaluates exactly these expressions.
+// SEL: 0 = max(old, new), 1 = old, 2 = new.
+// ----------------------------------------------------------------------------
+template <int SEL>
+__device__ __forceinline__ float majorant_at(const SceneK &S, const GridKS &G, V3 p) {
+    int ix = (int) floorf(((p.x - S.bmin[0]) * S.inv_ext[0]) * (float) G.mx);
+    int iy = (int) floorf(((p.y - S.bmin[1]) * S.inv_ext[1]) * (float) G.my);
+    int iz = (int) floorf(((p.z - S.bmin[2]) * S.inv_ext[2]) * (float) G.mz);
+    ix = min(max(ix, 0), G.mx - 1); iy = min(max(iy, 0), G.my - 1); iz = min(max(iz, 0), G.mz - 1);
+    float2 m = __ldg(G.mgrid + ((size_t) iz * G.my + iy) * G.mx + ix);
+    return (SEL == 1) ? m.x : ((SEL == 2) ? m.y : fmax_(m.x, m.y));
+}
+
+__device__ __forceinline__ void dda_axis(float o, float d, float bmin, float inv_ext, int res, float voxel, float mint, float maxt,
+                                         float &tmax, float &tdelta) {
+    float lo = (o - bmin) * inv_ext, ld = d * inv_ext;
+    float fres = (float) res;
+    int cur = (int) floorf(__fmaf_rn(ld, mint, lo) * fres);
+    int last = (int) floorf(__fmaf_rn(ld, maxt, lo) * fres);
+    cur = min(max(cur, 0), res - 1);
+    last = min(max(last, 0), res - 1);
+    int step = (ld >= 0.f) ? 1 : -1;
+    float nb = (float) (cur + step) * voxel;
+    if (cur != last && ld < 0.f) nb += voxel;
+    if (ld != 0.f) {
+        float rld = 1.f / ld;
+        tmax = (nb - lo) * rld;
+        tdelta = ((float) step * voxel) * rld;
+    } else {
+        tmax = inf_(); tdelta = inf_();
+    }
+}
+
+// sampled free-flight distance (or inf) for optical depth `tau` along o + t d, t in [mint, maxt]
+template <int SEL>
+__device__ __forceinline__ float dda_sample(const SceneK &S, const GridKS &G, V3 o, V3 d, float mint, float maxt, float tau) {
+    float tx, ty, tz, dx, dy, dz;
+    dda_axis(o.x, d.x, S.bmin[0], S.inv_ext[0], G.mx, G.vox[0], mint, maxt, tx, dx);
+    dda_axis(o.y, d.y, S.bmin[1], S.inv_ext[1], G.my, G.vox[1], mint, maxt, ty, dy);
+    dda_axis(o.z, d.z, S.bmin[2], S.inv_ext[2], G.mz, G.vox[2], mint, maxt, tz, dz);
+    float dda_t = mint, tau_acc = 0.f;
+    bool reached = false, active = true;
+    while (active) {
+        float t_next = fmin_(fmin_(tx, ty), tz);
+        int axis = (tx == t_next) ? 0 : ((ty == t_next) ? 1 : 2);
+        float tmid = 0.5f * (dda_t + fmin_(t_next, maxt));
+        float majorant = majorant_at<SEL>(S, G, ray_at(o, d, tmid));
+        float tau_next = tau_acc + (majorant * (t_next - dda_t));
+        float t_precise = dda_t + ((tau - tau_acc) / majorant);
+        reached = reached || ((majorant > 0.f) && (t_precise < maxt) && (tau_next >= tau));
+        dda_t = reached ? t_precise : t_next;
+        active = !reached && (t_next < maxt);
+        if (active) {
+            if (axis == 0) tx = tx + dx; else if (axis == 1) ty = ty + dy; else tz = tz + dz;
+            tau_acc = tau_next;
+        }
+    }
+    return reached ? dda_t : inf_();
 }
 
 // ----------------------------------------------------------------------------

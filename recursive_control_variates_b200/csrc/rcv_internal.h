@@ -21,11 +21,11 @@ struct LaunchCfg {
 
 // ---- tracing (rcv_trace.cu)
 // mode 0: two states -> acc_old & acc_new; mode 1 / 2: single state old / new -> acc_old / acc_new
-cudaError_t launch_twostates(const LaunchCfg &cfg, const SceneK &S, const GridK &G, int mode, uint32_t seed, uint32_t spp,
+cudaError_t launch_twostates(const LaunchCfg &cfg, const SceneK &S, const GridKS &G, int mode, uint32_t seed, uint32_t spp,
                              uint32_t spp_begin, uint32_t spp_end, float4 *acc_old, float4 *acc_new);
-cudaError_t launch_vps_primal(const LaunchCfg &cfg, const SceneK &S, const GridK &G, uint32_t seed, uint32_t spp,
+cudaError_t launch_vps_primal(const LaunchCfg &cfg, const SceneK &S, const GridKS &G, uint32_t seed, uint32_t spp,
                               uint32_t spp_begin, uint32_t spp_end, float4 *accum);
-cudaError_t launch_vps_backward(const LaunchCfg &cfg, const SceneK &S, const GridK &G, const GradK &D, uint32_t seed_grad,
+cudaError_t launch_vps_backward(const LaunchCfg &cfg, const SceneK &S, const GridKS &G, const GradK &D, uint32_t seed_grad,
                                 uint32_t spp_grad, uint32_t spp_begin, uint32_t spp_end, uint32_t alt_seed,
                                 const float *grad_img, const float *film_w);
 size_t vps_backward_slots(const LaunchCfg &cfg);
@@ -35,6 +35,8 @@ cudaError_t launch_film_weights(const LaunchCfg &cfg, const SceneK &S, uint32_t 
 cudaError_t launch_rotate(const LaunchCfg &cfg, const float *sigma_in, const float *albedo_in, int nz, int ny, int nx, float scale,
                           float2 *sig2, float4 *blk2, float4 *blk1, float4 *alb2, float *block_max, int n_blocks,
                           float *majorants);
+cudaError_t launch_majorant_grid(const LaunchCfg &cfg, const float2 *sig2, int nz, int ny, int nx, int factor, float scale,
+                                 float2 *mgrid);
 cudaError_t launch_medium_read(const LaunchCfg &cfg, const float2 *sig2, const float4 *alb2, size_t nvox, int state,
                                float *sigma_out, float *albedo_out);
 

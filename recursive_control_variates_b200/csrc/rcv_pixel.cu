@@ -86,6 +86,41 @@ cudaError_t launch_rotate(const LaunchCfg &cfg, const float *sigma_in, const flo
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------
+// majorant supergrid (heterogeneous `majorant_resolution_factor`, upstream update_majorant_supergrid):
+// cell (cx,cy,cz) of f^3 voxels stores scale * max over the voxels [c f - 1, c f + f] per axis (clamped) — every
+// voxel a trilinear lookup inside the cell can touch — for both states.  One warp per cell.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_majorant_grid(const float2 *__restrict__ sig2, int nx, int ny, int nz, int f, float scale,
+                                                          int mx, int my, int mz, float2 *__restrict__ mgrid) {
+    const int lane = threadIdx.x & 31;
+    const size_t ncell = (size_t) mx * my * mz, span = (size_t) (f + 2);
+    for (size_t c = ((size_t) blockIdx.x * kBlock + threadIdx.x) >> 5; c < ncell; c += ((size_t) gridDim.x * kBlock) >> 5) {
+        int cx = (int) (c % mx), cy = (int) ((c / mx) % my), cz = (int) (c / ((size_t) mx * my));
+        float mo = 0.f, mn = 0.f;
+        for (size_t k = lane; k < span * span * span; k += 32) {
+            int x = cx * f - 1 + (int) (k % span), y = cy * f - 1 + (int) ((k / span) % span), z = cz * f - 1 + (int) (k / (span * span));
+            x = min(max(x, 0), nx - 1); y = min(max(y, 0), ny - 1); z = min(max(z, 0), nz - 1);
+            float2 s = __ldg(sig2 + ((size_t) z * ny + y) * nx + x);
+            mo = fmaxf(mo, s.x); mn = fmaxf(mn, s.y);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mo = fmaxf(mo, __shfl_xor_sync(0xffffffffu, mo, o));
+            mn = fmaxf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        }
+        if (lane == 0) mgrid[c] = make_float2(scale * mo, scale * mn);
+    }
+}
+cudaError_t launch_majorant_grid(const LaunchCfg &cfg, const float2 *sig2, int nz, int ny, int nx, int factor, float scale,
+                                 float2 *mgrid) {
+    int mx = nx / factor, my = ny / factor, mz = nz / factor;
+    k_majorant_grid<<<grid_for(cfg, (size_t) mx * my * mz * 32), kBlock, 0, cfg.stream>>>(sig2, nx, ny, nz, factor, scale, mx, my, mz,
+                                                                                          mgrid);
+    (*cfg.launches)++;
+    return cudaGetLastError();
+}
+
 __global__ void __launch_bounds__(kBlock) k_medium_read(const float2 *__restrict__ sig2, const float4 *__restrict__ alb2,
                                                         size_t nvox, int state, float *sigma_out, float *albedo_out) {
     for (size_t v = (size_t) blockIdx.x * kBlock + threadIdx.x; v < nvox; v += (size_t) gridDim.x * kBlock) {

@@ -33,8 +33,8 @@ __device__ __forceinline__ uint64_t global_lane(uint64_t j, uint32_t spp, uint32
 // ===========================================================================
 // SIMPLE / BATCH schedules
 // ===========================================================================
-template <int MODE>
-__device__ __forceinline__ void twostates_lane(const SceneK &S, const GridK &G, uint32_t seed, uint32_t spp, uint64_t idx,
+template <int MODE, class GRID>
+__device__ __forceinline__ void twostates_lane(const SceneK &S, const GRID &G, uint32_t seed, uint32_t spp, uint64_t idx,
                                                float4 *acc_old, float4 *acc_new, unsigned &nc, unsigned &nsct) {
     Lane L = lane_setup(S, seed, spp, idx);
     V3 Lo, Ln;
@@ -46,8 +46,8 @@ __device__ __forceinline__ void twostates_lane(const SceneK &S, const GridK &G, 
     }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kBlock) k_twostates_simple(const __grid_constant__ SceneK S, const __grid_constant__ GridK G,
+template <int MODE, class GRID>
+__global__ void __launch_bounds__(kBlock) k_twostates_simple(const __grid_constant__ SceneK S, const __grid_constant__ GRID G,
                                                              uint32_t seed, uint32_t spp, uint32_t spp_begin, uint32_t ns,
                                                              uint64_t n_local, float4 *acc_old, float4 *acc_new, Counters *C,
                                                              unsigned long long *work, int persistent) {
@@ -78,8 +78,8 @@ __global__ void __launch_bounds__(kBlock) k_twostates_simple(const __grid_consta
     counter_flush(C, 6, np);
 }
 
-template <bool BACKWARD>
-__device__ __forceinline__ void vps_lane(const SceneK &S, const GridK &G, const GradK &D, uint32_t seed, uint32_t spp, uint64_t idx,
+template <bool BACKWARD, class GRID>
+__device__ __forceinline__ void vps_lane(const SceneK &S, const GRID &G, const GradK &D, uint32_t seed, uint32_t spp, uint64_t idx,
                                          uint32_t alt_seed, const float *grad_img, const float *film_w, float4 *accum,
                                          VpsCounts &cnt) {
     Lane L = lane_setup(S, seed, spp, idx);
@@ -103,8 +103,8 @@ __device__ __forceinline__ void vps_lane(const SceneK &S, const GridK &G, const 
     vps_trace<true>(S, G, D, L.rng, alt, L.o, L.d, dL, res, res2, cnt);
 }
 
-template <bool BACKWARD>
-__global__ void __launch_bounds__(kBlock) k_vps_simple(const __grid_constant__ SceneK S, const __grid_constant__ GridK G, GradK D,
+template <bool BACKWARD, class GRID>
+__global__ void __launch_bounds__(kBlock) k_vps_simple(const __grid_constant__ SceneK S, const __grid_constant__ GRID G, GradK D,
                                                        uint32_t seed, uint32_t spp, uint32_t spp_begin, uint32_t ns, uint64_t n_local,
                                                        uint32_t alt_seed, const float *grad_img, const float *film_w, float4 *accum,
                                                        Counters *C, unsigned long long *work, int persistent) {
@@ -244,9 +244,9 @@ __device__ __forceinline__ unsigned long long take_positions(ChunkCursor &cc, un
     return mine;
 }
 
-template <int MODE>
+template <int MODE, class GRID>
 __global__ void __launch_bounds__(kWfBlock, RCV_TS_MINBLOCKS) k_twostates_wavefront(const __grid_constant__ SceneK S,
-                                                                                 const __grid_constant__ GridK G, float4 *acc_old,
+                                                                                 const __grid_constant__ GRID G, float4 *acc_old,
                                                                                  float4 *acc_new, PathQueue Q, Counters *C,
                                                                                  unsigned long long *work) {
     const float mu = combined_majorant<MODE>(G);
@@ -283,9 +283,9 @@ __global__ void __launch_bounds__(kWfBlock, RCV_TS_MINBLOCKS) k_twostates_wavefr
     counter_flush(C, 6, sk.n_paths);
 }
 
-template <bool BACKWARD>
+template <bool BACKWARD, class GRID>
 __global__ void __launch_bounds__(kWfBlock, RCV_VP_MINBLOCKS) k_vps_wavefront(const __grid_constant__ SceneK S,
-                                                                           const __grid_constant__ GridK G, GradK D, uint32_t seed,
+                                                                           const __grid_constant__ GRID G, GradK D, uint32_t seed,
                                                                            uint32_t spp, uint32_t alt_seed, const float *grad_img,
                                                                            const float *film_w, float4 *accum, PathQueue Q,
                                                                            Counters *C, unsigned long long *work, float4 *arena,
@@ -346,9 +346,9 @@ static constexpr int kPoolWarps = kPoolBlock / 32;
 template <int WORDS>
 __host__ __device__ constexpr size_t pool_warp_floats() { return (size_t) WORDS * kPoolSlots + 2 * kPoolSlots / 4; }
 
-template <int MODE>
+template <int MODE, class GRID>
 __global__ void __launch_bounds__(kPoolBlock, RCV_POOL_MINBLOCKS) k_twostates_pool(const __grid_constant__ SceneK S,
-                                                                                   const __grid_constant__ GridK G, float4 *acc_old,
+                                                                                   const __grid_constant__ GRID G, float4 *acc_old,
                                                                                    float4 *acc_new, PathQueue Q, Counters *C,
                                                                                    unsigned long long *work) {
     extern __shared__ float smem[];
@@ -420,9 +420,9 @@ __global__ void __launch_bounds__(kPoolBlock, RCV_POOL_MINBLOCKS) k_twostates_po
     counter_flush(C, 6, sk.n_paths);
 }
 
-template <bool BACKWARD>
+template <bool BACKWARD, class GRID>
 __global__ void __launch_bounds__(kPoolBlock, RCV_POOL_MINBLOCKS) k_vps_pool(const __grid_constant__ SceneK S,
-                                                                             const __grid_constant__ GridK G, GradK D, uint32_t seed,
+                                                                             const __grid_constant__ GRID G, GradK D, uint32_t seed,
                                                                              uint32_t spp, uint32_t alt_seed, const float *grad_img,
                                                                              const float *film_w, float4 *accum, PathQueue Q,
                                                                              Counters *C, unsigned long long *work, float4 *arena,
@@ -535,8 +535,8 @@ static cudaError_t persistent_grid(const LaunchCfg &cfg, K kernel, int block, ui
     return cudaSuccess;
 }
 
-template <int MODE>
-static cudaError_t launch_twostates_mode(const LaunchCfg &cfg, const SceneK &S, const GridK &G, uint32_t seed, uint32_t spp,
+template <int MODE, class GRID>
+static cudaError_t launch_twostates_mode(const LaunchCfg &cfg, const SceneK &S, const GRID &G, uint32_t seed, uint32_t spp,
                                          uint32_t spp_begin, uint32_t ns, uint64_t n_local, float4 *acc_old, float4 *acc_new) {
     cudaError_t e;
     if (cfg.tracer == 0 || cfg.tracer == 3) {
@@ -545,13 +545,13 @@ static cudaError_t launch_twostates_mode(const LaunchCfg &cfg, const SceneK &S, 
         k_twostates_raygen<MODE><<<(unsigned) ((n_local + kBlock - 1) / kBlock), kBlock, 0, cfg.stream>>>(
             S, seed, spp, spp_begin, ns, n_local, acc_old, acc_new, cfg.queue, cfg.counters);
         if (cfg.tracer == 3) {
-            e = launch_pool(cfg, k_twostates_pool<MODE>, kPoolWarps * pool_warp_floats<kTsWords>() * sizeof(float), n_local, S, G,
+            e = launch_pool(cfg, k_twostates_pool<MODE, GRID>, kPoolWarps * pool_warp_floats<kTsWords>() * sizeof(float), n_local, S, G,
                             acc_old, acc_new, cfg.queue, cfg.counters, cfg.work_counter);
             if (e != cudaSuccess) return e;
         } else {
             unsigned blocks;
-            if ((e = persistent_grid(cfg, k_twostates_wavefront<MODE>, kWfBlock, n_local, blocks)) != cudaSuccess) return e;
-            k_twostates_wavefront<MODE><<<blocks, kWfBlock, 0, cfg.stream>>>(S, G, acc_old, acc_new, cfg.queue, cfg.counters,
+            if ((e = persistent_grid(cfg, k_twostates_wavefront<MODE, GRID>, kWfBlock, n_local, blocks)) != cudaSuccess) return e;
+            k_twostates_wavefront<MODE, GRID><<<blocks, kWfBlock, 0, cfg.stream>>>(S, G, acc_old, acc_new, cfg.queue, cfg.counters,
                                                                              cfg.work_counter);
         }
         (*cfg.launches) += 2;
@@ -560,29 +560,36 @@ static cudaError_t launch_twostates_mode(const LaunchCfg &cfg, const SceneK &S, 
         unsigned blocks = (unsigned) ((n_local + kBlock - 1) / kBlock);
         if (persistent) {
             if ((e = cudaMemsetAsync(cfg.work_counter, 0, sizeof(unsigned long long), cfg.stream)) != cudaSuccess) return e;
-            if ((e = persistent_grid(cfg, k_twostates_simple<MODE>, kBlock, n_local, blocks)) != cudaSuccess) return e;
+            if ((e = persistent_grid(cfg, k_twostates_simple<MODE, GRID>, kBlock, n_local, blocks)) != cudaSuccess) return e;
         }
-        k_twostates_simple<MODE><<<blocks, kBlock, 0, cfg.stream>>>(S, G, seed, spp, spp_begin, ns, n_local, acc_old, acc_new,
+        k_twostates_simple<MODE, GRID><<<blocks, kBlock, 0, cfg.stream>>>(S, G, seed, spp, spp_begin, ns, n_local, acc_old, acc_new,
                                                                     cfg.counters, cfg.work_counter, persistent);
         (*cfg.launches)++;
     }
     return cudaGetLastError();
 }
 
-cudaError_t launch_twostates(const LaunchCfg &cfg, const SceneK &S, const GridK &G, int mode, uint32_t seed, uint32_t spp,
-                             uint32_t spp_begin, uint32_t spp_end, float4 *acc_old, float4 *acc_new) {
-    uint32_t ns = spp_end - spp_begin;
-    uint64_t n_local = (uint64_t) S.W * S.H * ns;
-    if (n_local == 0) return cudaSuccess;
+template <class GRID>
+static cudaError_t launch_twostates_grid(const LaunchCfg &cfg, const SceneK &S, const GRID &G, int mode, uint32_t seed, uint32_t spp,
+                                         uint32_t spp_begin, uint32_t ns, uint64_t n_local, float4 *acc_old, float4 *acc_new) {
     switch (mode) {
         case 0: return launch_twostates_mode<0>(cfg, S, G, seed, spp, spp_begin, ns, n_local, acc_old, acc_new);
         case 1: return launch_twostates_mode<1>(cfg, S, G, seed, spp, spp_begin, ns, n_local, acc_old, acc_new);
         default: return launch_twostates_mode<2>(cfg, S, G, seed, spp, spp_begin, ns, n_local, acc_old, acc_new);
     }
 }
+// G.mgrid != nullptr selects the kernels that sample free flights through the majorant supergrid
+cudaError_t launch_twostates(const LaunchCfg &cfg, const SceneK &S, const GridKS &G, int mode, uint32_t seed, uint32_t spp,
+                             uint32_t spp_begin, uint32_t spp_end, float4 *acc_old, float4 *acc_new) {
+    uint32_t ns = spp_end - spp_begin;
+    uint64_t n_local = (uint64_t) S.W * S.H * ns;
+    if (n_local == 0) return cudaSuccess;
+    if (G.mgrid) return launch_twostates_grid<GridKS>(cfg, S, G, mode, seed, spp, spp_begin, ns, n_local, acc_old, acc_new);
+    return launch_twostates_grid<GridK>(cfg, S, G, mode, seed, spp, spp_begin, ns, n_local, acc_old, acc_new);
+}
 
-template <bool BACKWARD>
-static cudaError_t launch_vps(const LaunchCfg &cfg, const SceneK &S, const GridK &G, const GradK &D, uint32_t seed, uint32_t spp,
+template <bool BACKWARD, class GRID>
+static cudaError_t launch_vps(const LaunchCfg &cfg, const SceneK &S, const GRID &G, const GradK &D, uint32_t seed, uint32_t spp,
                               uint32_t spp_begin, uint32_t spp_end, uint32_t alt_seed, const float *grad_img, const float *film_w,
                               float4 *accum) {
     uint32_t ns = spp_end - spp_begin;
@@ -595,13 +602,13 @@ static cudaError_t launch_vps(const LaunchCfg &cfg, const SceneK &S, const GridK
         k_vps_raygen<BACKWARD><<<(unsigned) ((n_local + kBlock - 1) / kBlock), kBlock, 0, cfg.stream>>>(
             S, seed, spp, spp_begin, ns, n_local, accum, cfg.queue, cfg.counters);
         if (cfg.tracer == 3) {
-            e = launch_pool(cfg, k_vps_pool<BACKWARD>, kPoolWarps * pool_warp_floats<kVpWords>() * sizeof(float), n_local, S, G, D, seed,
+            e = launch_pool(cfg, k_vps_pool<BACKWARD, GRID>, kPoolWarps * pool_warp_floats<kVpWords>() * sizeof(float), n_local, S, G, D, seed,
                             spp, alt_seed, grad_img, film_w, accum, cfg.queue, cfg.counters, cfg.work_counter, cfg.arena, cfg.vcap);
             if (e != cudaSuccess) return e;
         } else {
             unsigned blocks;
-            if ((e = persistent_grid(cfg, k_vps_wavefront<BACKWARD>, kWfBlock, n_local, blocks)) != cudaSuccess) return e;
-            k_vps_wavefront<BACKWARD><<<blocks, kWfBlock, 0, cfg.stream>>>(S, G, D, seed, spp, alt_seed, grad_img, film_w, accum,
+            if ((e = persistent_grid(cfg, k_vps_wavefront<BACKWARD, GRID>, kWfBlock, n_local, blocks)) != cudaSuccess) return e;
+            k_vps_wavefront<BACKWARD, GRID><<<blocks, kWfBlock, 0, cfg.stream>>>(S, G, D, seed, spp, alt_seed, grad_img, film_w, accum,
                                                                            cfg.queue, cfg.counters, cfg.work_counter, cfg.arena,
                                                                            cfg.vcap);
         }
@@ -611,9 +618,9 @@ static cudaError_t launch_vps(const LaunchCfg &cfg, const SceneK &S, const GridK
         unsigned blocks = (unsigned) ((n_local + kBlock - 1) / kBlock);
         if (persistent) {
             if ((e = cudaMemsetAsync(cfg.work_counter, 0, sizeof(unsigned long long), cfg.stream)) != cudaSuccess) return e;
-            if ((e = persistent_grid(cfg, k_vps_simple<BACKWARD>, kBlock, n_local, blocks)) != cudaSuccess) return e;
+            if ((e = persistent_grid(cfg, k_vps_simple<BACKWARD, GRID>, kBlock, n_local, blocks)) != cudaSuccess) return e;
         }
-        k_vps_simple<BACKWARD><<<blocks, kBlock, 0, cfg.stream>>>(S, G, D, seed, spp, spp_begin, ns, n_local, alt_seed, grad_img, film_w,
+        k_vps_simple<BACKWARD, GRID><<<blocks, kBlock, 0, cfg.stream>>>(S, G, D, seed, spp, spp_begin, ns, n_local, alt_seed, grad_img, film_w,
                                                                   accum, cfg.counters, cfg.work_counter, persistent);
         (*cfg.launches)++;
     }
@@ -625,30 +632,33 @@ size_t vps_backward_slots(const LaunchCfg &cfg) {
     if (cfg.tracer == 3) {
         int per_sm = 0;
         size_t smem = kPoolWarps * pool_warp_floats<kVpWords>() * sizeof(float);
-        cudaFuncSetAttribute(k_vps_pool<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vps_pool<true>, kPoolBlock, smem) != cudaSuccess || per_sm < 1)
+        cudaFuncSetAttribute(k_vps_pool<true, GridK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vps_pool<true, GridK>, kPoolBlock, smem) != cudaSuccess || per_sm < 1)
             per_sm = 1;
         return (size_t) per_sm * cfg.sm_count * kPoolWarps * kPoolSlots;
     }
     if (cfg.tracer == 0) {
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vps_wavefront<true>, kWfBlock, 0) != cudaSuccess || per_sm < 1)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vps_wavefront<true, GridK>, kWfBlock, 0) != cudaSuccess || per_sm < 1)
             per_sm = 1;
         return (size_t) per_sm * cfg.sm_count * kWfBlock;
     }
     return 0;
 }
 
-cudaError_t launch_vps_primal(const LaunchCfg &cfg, const SceneK &S, const GridK &G, uint32_t seed, uint32_t spp,
+cudaError_t launch_vps_primal(const LaunchCfg &cfg, const SceneK &S, const GridKS &G, uint32_t seed, uint32_t spp,
                               uint32_t spp_begin, uint32_t spp_end, float4 *accum) {
     GradK D; D.gsig = nullptr; D.galb = nullptr;
-    return launch_vps<false>(cfg, S, G, D, seed, spp, spp_begin, spp_end, 0u, nullptr, nullptr, accum);
+    if (G.mgrid) return launch_vps<false, GridKS>(cfg, S, G, D, seed, spp, spp_begin, spp_end, 0u, nullptr, nullptr, accum);
+    return launch_vps<false, GridK>(cfg, S, G, D, seed, spp, spp_begin, spp_end, 0u, nullptr, nullptr, accum);
 }
 
-cudaError_t launch_vps_backward(const LaunchCfg &cfg, const SceneK &S, const GridK &G, const GradK &D, uint32_t seed_grad,
+cudaError_t launch_vps_backward(const LaunchCfg &cfg, const SceneK &S, const GridKS &G, const GradK &D, uint32_t seed_grad,
                                 uint32_t spp_grad, uint32_t spp_begin, uint32_t spp_end, uint32_t alt_seed,
                                 const float *grad_img, const float *film_w) {
-    return launch_vps<true>(cfg, S, G, D, seed_grad, spp_grad, spp_begin, spp_end, alt_seed, grad_img, film_w, nullptr);
+    if (G.mgrid)
+        return launch_vps<true, GridKS>(cfg, S, G, D, seed_grad, spp_grad, spp_begin, spp_end, alt_seed, grad_img, film_w, nullptr);
+    return launch_vps<true, GridK>(cfg, S, G, D, seed_grad, spp_grad, spp_begin, spp_end, alt_seed, grad_img, film_w, nullptr);
 }
 
 // per-pixel film weight of ALL spp samples (a pure function of the first two

@@ -27,6 +27,7 @@ struct Mei2 {
     float t;        // inf when invalid
     V3 p;
     float so, sn;   // sigma_t of the old / new state at p
+    float mu, inv_mu;   // the majorant the collision was sampled with: the volume's, or the supergrid cell's at p
 };
 
 template <int MODE>
@@ -39,31 +40,35 @@ __device__ __forceinline__ float combined_majorant(const GridK &G) {
 // twostatemedium.py:15-107 with a global majorant.  Only sigma_t is fetched
 // here; sigma_s (albedo) is needed at real scatters only and fetched there —
 // the results are identical to fetching it at every tentative collision.
-template <int MODE>
-__device__ __forceinline__ void sample_interaction2(const SceneK &S, const GridK &G, float inv_mu, V3 o, V3 d, V3 id,
+template <int MODE, class GRID>
+__device__ __forceinline__ void sample_interaction2(const SceneK &S, const GRID &G, float mu, float inv_mu, V3 o, V3 d, V3 id,
                                                     float ray_maxt, float u, Mei2 &m, Tri &T, unsigned &n_coll) {
     float mint, maxt;
     bool active = medium_interval(S, o, d, id, ray_maxt, mint, maxt);   // :22
     float tau = -spec_log(1.f - u);                                   // :24
-    float t = mint + (tau * inv_mu);                                  // :78
+    float t;
+    if constexpr (GRID::kSupergrid) t = active ? dda_sample<MODE>(S, G, o, d, mint, maxt, tau) : inf_();   // :25-70
+    else t = mint + (tau * inv_mu);                                   // :78
     bool valid = active && (t <= maxt);                               // :80
     m.t = valid ? t : inf_();                                         // :88
     m.p = ray_at(o, d, t);                                            // :89
     m.so = 0.f; m.sn = 0.f;
+    m.mu = mu; m.inv_mu = inv_mu;
     if (valid) {                                                      // :93-94
         T = tri_setup(S, G, m.p);
         lookup_sigma2(S, G, T, m.so, m.sn);
         n_coll++;
         if (MODE == 1) m.sn = m.so;
         if (MODE == 2) m.so = m.sn;
+        if constexpr (GRID::kSupergrid) { m.mu = majorant_at<MODE>(S, G, m.p); m.inv_mu = 1.f / m.mu; }   // :82-86
     }
 }
 
 // twostatevolpath.py:387-479: emitter direction sample + two-state ratio
 // tracking towards it.  Transmittances are scalars: all three channels carry
 // the same value because sigma_t is monochromatic.
-template <int MODE>
-__device__ __forceinline__ void nee_twostates(const SceneK &S, const GridK &G, float mu, float inv_mu, Pcg &rng, V3 ref_p,
+template <int MODE, class GRID>
+__device__ __forceinline__ void nee_twostates(const SceneK &S, const GRID &G, float mu, float inv_mu, Pcg &rng, V3 ref_p,
                                               float &tr_old, float &tr_new, V3 &dir, unsigned &n_coll) {
     float s2x = pcg_f32(rng), s2y = pcg_f32(rng);                     // :393
     V3 d = uniform_sphere(s2x, s2y);
@@ -80,14 +85,14 @@ __device__ __forceinline__ void nee_twostates(const SceneK &S, const GridK &G, f
         if (in_medium) {
             float u = pcg_f32(rng);                                   // :422
             Mei2 m; Tri T;
-            sample_interaction2<MODE>(S, G, inv_mu, o, d, id, remaining, u, m, T, n_coll);
+            sample_interaction2<MODE>(S, G, mu, inv_mu, o, d, id, remaining, u, m, T, n_coll);
             if (si.t < m.t) m.t = inf_();                             // :423-424
             if (m.t < inf_()) {                                       // :444
                 o = m.p;                                              // :445
                 si.t = si.t - m.t;                                    // :446
-                float sn_o = mu - m.so, sn_n = mu - m.sn;
-                tr_old = tr_old * ((mu != 0.f) ? (sn_o * inv_mu) : sn_o); // :447-452, :462-463
-                tr_new = tr_new * ((mu != 0.f) ? (sn_n * inv_mu) : sn_n);
+                float sn_o = m.mu - m.so, sn_n = m.mu - m.sn;
+                tr_old = tr_old * ((m.mu != 0.f) ? (sn_o * m.inv_mu) : sn_o); // :447-452, :462-463
+                tr_new = tr_new * ((m.mu != 0.f) ? (sn_n * m.inv_mu) : sn_n);
                 if (!(tr_new != 0.f || tr_old != 0.f)) break;         // :472
                 total_dist += m.t;                                    // :473
                 continue;
@@ -104,8 +109,8 @@ __device__ __forceinline__ void nee_twostates(const SceneK &S, const GridK &G, f
     dir = d;
 }
 
-template <int MODE>
-__device__ __forceinline__ void trace_twostates(const SceneK &S, const GridK &G, Pcg &rng, V3 o, V3 d, V3 &L_old, V3 &L_new,
+template <int MODE, class GRID>
+__device__ __forceinline__ void trace_twostates(const SceneK &S, const GRID &G, Pcg &rng, V3 o, V3 d, V3 &L_old, V3 &L_new,
                                                 unsigned &n_coll, unsigned &n_scat) {
     const float mu = combined_majorant<MODE>(G);
     const float inv_mu = 1.f / mu;
@@ -132,16 +137,16 @@ __device__ __forceinline__ void trace_twostates(const SceneK &S, const GridK &G,
         if (in_medium) {
             float u = pcg_f32(rng);                                   // :194
             Mei2 m; Tri T;
-            sample_interaction2<MODE>(S, G, inv_mu, o, d, id, RCV_LARGEST, u, m, T, n_coll);   // :196
+            sample_interaction2<MODE>(S, G, mu, inv_mu, o, d, id, RCV_LARGEST, u, m, T, n_coll);   // :196
             if (needs_isect) { si = box_hit(S, o, d, id, RCV_LARGEST); needs_isect = false; }   // :200-204
             if (si.t < m.t) m.t = inf_();                             // :205-206
             if (m.t < inf_()) {                                       // :217
-                float sp_new = m.sn * inv_mu, sp_old = m.so * inv_mu; // :223-224
-                float prob = (mu != 0.f) ? (sp_new + sp_old) * 0.5f : 0.f;   // :225
+                float sp_new = m.sn * m.inv_mu, sp_old = m.so * m.inv_mu; // :223-224
+                float prob = (m.mu != 0.f) ? (sp_new + sp_old) * 0.5f : 0.f;   // :225
                 float xi = pcg_f32(rng);                              // :227
                 if (xi >= prob) {
                     // null collision (:230-231, :256-257, :265-266)
-                    float sn_n = mu - m.sn, sn_o = mu - m.so;
+                    float sn_n = m.mu - m.sn, sn_o = m.mu - m.so;
                     float rden = 1.f / (sn_n + sn_o);
                     float w_new = (sn_n * 2.f) * rden, w_old = (sn_o * 2.f) * rden;
                     o = m.p;

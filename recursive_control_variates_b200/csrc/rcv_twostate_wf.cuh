@@ -179,8 +179,8 @@ __device__ __forceinline__ void ts_slow(const SceneK &S, TsLane &ln, TsSink &sk)
     ts_finish<MODE>(ln, sk);
 }
 
-template <int MODE>
-__device__ __forceinline__ void ts_collide(const SceneK &S, const GridK &G, float mu, float inv_mu, TsLane &ln, TsSink &sk) {
+template <int MODE, class GRID>
+__device__ __forceinline__ void ts_collide(const SceneK &S, const GRID &G, float mu_vol, float inv_mu_vol, TsLane &ln, TsSink &sk) {
     const bool nee = (ln.flags & F_IN_NEE) != 0;
     V3 so, sd; float maxt;
     if (!nee) {
@@ -193,7 +193,8 @@ __device__ __forceinline__ void ts_collide(const SceneK &S, const GridK &G, floa
     }
     float u = pcg_f32(ln.rng);                                        // :194 / :422
     Mei2 m; Tri T;
-    sample_interaction2<MODE>(S, G, inv_mu, so, sd, ln.id, maxt, u, m, T, sk.n_coll);
+    sample_interaction2<MODE>(S, G, mu_vol, inv_mu_vol, so, sd, ln.id, maxt, u, m, T, sk.n_coll);
+    const float mu = m.mu, inv_mu = m.inv_mu;                         // the volume's majorant, or the supergrid cell's at m.p
     if (ln.flags & F_NEEDS_ISECT) {                                   // :200-204 / :414-416
         Hit h = box_hit(S, so, sd, ln.id, maxt);
         ln.si_t = h.t;

@@ -23,30 +23,37 @@ struct Mei1 {
     V3 p;
     float st;     // sigma_t(p) (0 when invalid)
     bool valid;
+    float mu, inv_mu;   // the majorant the collision was sampled with (volume or supergrid cell at p)
 };
 
-// Medium::sample_interaction of state `new` with a global majorant
-__device__ __forceinline__ void sample_interaction1(const SceneK &S, const GridK &G, float inv_mu, V3 o, V3 d, V3 id,
+// Medium::sample_interaction of state `new`: one majorant for the volume, or DDA through the majorant supergrid
+template <class GRID>
+__device__ __forceinline__ void sample_interaction1(const SceneK &S, const GRID &G, float mu, float inv_mu, V3 o, V3 d, V3 id,
                                                     float ray_maxt, float u, Mei1 &m, Tri &T, VpsCounts &cnt) {
     float mint, maxt;
     bool active = medium_interval(S, o, d, id, ray_maxt, mint, maxt);
     float tau = -spec_log(1.f - u);
-    float t = mint + (tau * inv_mu);
+    float t;
+    if constexpr (GRID::kSupergrid) t = active ? dda_sample<2>(S, G, o, d, mint, maxt, tau) : inf_();
+    else t = mint + (tau * inv_mu);
     m.valid = active && (t <= maxt);
     m.t = m.valid ? t : inf_();
     m.p = ray_at(o, d, t);
     m.st = 0.f;
+    m.mu = mu; m.inv_mu = inv_mu;
     if (m.valid) {
         T = tri_setup(S, G, m.p);
         m.st = lookup_sigma1(S, G, T);
         cnt.coll++;
+        if constexpr (GRID::kSupergrid) { m.mu = majorant_at<2>(S, G, m.p); m.inv_mu = 1.f / m.mu; }
     }
 }
 // convenience overload for callers that do not need the interpolation set-up
-__device__ __forceinline__ void sample_interaction1(const SceneK &S, const GridK &G, float inv_mu, V3 o, V3 d, V3 id,
+template <class GRID>
+__device__ __forceinline__ void sample_interaction1(const SceneK &S, const GRID &G, float mu, float inv_mu, V3 o, V3 d, V3 id,
                                                     float ray_maxt, float u, Mei1 &m, VpsCounts &cnt) {
     Tri T;
-    sample_interaction1(S, G, inv_mu, o, d, id, ray_maxt, u, m, T, cnt);
+    sample_interaction1(S, G, mu, inv_mu, o, d, id, ray_maxt, u, m, T, cnt);
 }
 
 // AD of sigma_t(p) = scale * trilinear(grid): scatter w_corner * (scale * g) on a known interpolation set-up
@@ -68,8 +75,8 @@ __device__ __forceinline__ void scatter_sigma_t(const SceneK &S, const GridK &G,
 }
 
 // volpathsimple.py:449-517, ratio tracking from o along d over [0, tmax]
-template <bool ADJ>
-__device__ __forceinline__ float estimate_transmittance(const SceneK &S, const GridK &G, const GradK &D, float mu, float inv_mu,
+template <bool ADJ, class GRID>
+__device__ __forceinline__ float estimate_transmittance(const SceneK &S, const GRID &G, const GradK &D, float mu, float inv_mu,
                                                         Pcg &rng, V3 o, V3 d, V3 id, float tmax, bool active, V3 adjoint,
                                                         VpsCounts &cnt) {
     o = ray_at(o, d, 0.f);                                            // :467 (tmin = 0)
@@ -77,16 +84,16 @@ __device__ __forceinline__ float estimate_transmittance(const SceneK &S, const G
     while (active) {                                                  // :478
         float u = pcg_f32(rng);
         Mei1 m;
-        sample_interaction1(S, G, inv_mu, o, d, id, tmax, u, m, cnt); // :482
-        float sn = m.valid ? (mu - m.st) : 0.f;
-        float ce = m.valid ? mu : 0.f;
-        float tr = (ce != 0.f) ? (sn * inv_mu) : sn;                  // :486-489
+        sample_interaction1(S, G, mu, inv_mu, o, d, id, tmax, u, m, cnt); // :482
+        float sn = m.valid ? (m.mu - m.st) : 0.f;
+        float ce = m.valid ? m.mu : 0.f;
+        float tr = (ce != 0.f) ? (sn * m.inv_mu) : sn;                // :486-489
         if (m.t > tmax) m.t = inf_();                                 // :493
         if (!(m.t < inf_())) break;                                   // :494
         if (ADJ) {                                                    // :496-505
             float g = 0.f;
             if (tr > 0.f) {
-                float k = (-inv_mu) / tr;
+                float k = (-m.inv_mu) / tr;
                 g += adjoint.x * k; g += adjoint.y * k; g += adjoint.z * k;
             }
             scatter_sigma_t(S, G, D, m.p, g, cnt);
@@ -100,8 +107,8 @@ __device__ __forceinline__ float estimate_transmittance(const SceneK &S, const G
 }
 
 // volpathsimple.py:419-446; returns the scalar transmittance, the sampled direction in `dir`
-template <bool ADJ>
-__device__ __forceinline__ float vps_sample_emitter(const SceneK &S, const GridK &G, const GradK &D, float mu, float inv_mu,
+template <bool ADJ, class GRID>
+__device__ __forceinline__ float vps_sample_emitter(const SceneK &S, const GRID &G, const GradK &D, float mu, float inv_mu,
                                                     Pcg &rng, V3 ref_p, V3 adjoint, V3 &dir, VpsCounts &cnt) {
     float s2x = pcg_f32(rng), s2y = pcg_f32(rng);                     // :431
     V3 d = uniform_sphere(s2x, s2y);
@@ -111,8 +118,8 @@ __device__ __forceinline__ float vps_sample_emitter(const SceneK &S, const GridK
     return estimate_transmittance<ADJ>(S, G, D, mu, inv_mu, rng, ref_p, d, id, si.t, si.valid, adjoint, cnt);   // :443
 }
 
-template <bool ADJ>
-__device__ __forceinline__ void vps_trace(const SceneK &S, const GridK &G, const GradK &D, Pcg &rng, Pcg &alt, V3 o, V3 d, V3 dL,
+template <bool ADJ, class GRID>
+__device__ __forceinline__ void vps_trace(const SceneK &S, const GRID &G, const GradK &D, Pcg &rng, Pcg &alt, V3 o, V3 d, V3 dL,
                                           V3 state_in, V3 &result, VpsCounts &cnt) {
     const float mu = __ldg(G.majorants + 1);       // state `new` (twostatemedium.py:125-136)
     const float inv_mu = 1.f / mu;
@@ -149,10 +156,10 @@ __device__ __forceinline__ void vps_trace(const SceneK &S, const GridK &G, const
         while (true) {                                                // :360
             float u = pcg_f32(rng);
             Mei1 m;
-            sample_interaction1(S, G, inv_mu, ro, d, id, rmaxt, u, m, cnt);   // :361
+            sample_interaction1(S, G, mu, inv_mu, ro, d, id, rmaxt, u, m, cnt);   // :361
             mei_t = m.t + running_t;                                  // :364
             if (!m.valid) { did_scatter = false; break; }             // :371
-            float r = (mu != 0.f) ? (m.st * inv_mu) : 0.f;            // :367
+            float r = (m.mu != 0.f) ? (m.st * m.inv_mu) : 0.f;        // :367
             float xi = pcg_f32(rng);                                  // :372
             if (!(xi >= r)) { did_scatter = true; break; }
             ro = ro + d * m.t;                                        // :378-380

@@ -260,8 +260,8 @@ __device__ __forceinline__ void vp_replay_done(VpLane &ln, VpSink &sk) {
     vp_next_vertex(ln, sk);
 }
 
-template <bool BW>
-__device__ __forceinline__ void vp_collide(const SceneK &S, const GridK &G, float mu, float inv_mu, VpLane &ln, VpSink &sk) {
+template <bool BW, class GRID>
+__device__ __forceinline__ void vp_collide(const SceneK &S, const GRID &G, float mu_vol, float inv_mu_vol, VpLane &ln, VpSink &sk) {
     const bool nee = (ln.flags & VF_IN_NEE) != 0;
     if (!nee && (ln.flags & VF_HEAD)) {                               // loop head (:129-134)
         float q = fmin_(max3(ln.thr), 0.99f);
@@ -278,7 +278,8 @@ __device__ __forceinline__ void vp_collide(const SceneK &S, const GridK &G, floa
     const V3 sd = nee ? ln.nd : ln.d;
     float u = pcg_f32(ln.rng);
     Mei1 m; Tri T;
-    sample_interaction1(S, G, inv_mu, ln.ro, sd, ln.id, ln.rmaxt, u, m, T, sk.cnt);
+    sample_interaction1(S, G, mu_vol, inv_mu_vol, ln.ro, sd, ln.id, ln.rmaxt, u, m, T, sk.cnt);
+    const float mu = m.mu, inv_mu = m.inv_mu;                         // the volume's majorant, or the supergrid cell's at m.p
     if (nee) {
         // estimate_transmittance step (:478-515)
         float sn = m.valid ? (mu - m.st) : 0.f;

@@ -35,10 +35,11 @@ def _scene_dict(method, target_res, film, kind, scale=20.0):
 
 
 def scene_synthetic(method, output_dir, grid=64, init_grid=16, film=(128, 128), spp=16, kind="cube", n_steps=100,
-                    upsample=(0.16, 0.48)):
+                    upsample=(0.16, 0.48), supergrid=False):
     """Coarse-to-fine recovery of a synthetic density/albedo cube (C1 of BASELINE.json by default):
     the target is the `grid`^3 medium; optimisation starts from constant init_grid^3 grids and
-    doubles the resolution at the `upsample` fractions of the run (experiments.py:99-133)."""
+    doubles the resolution at the `upsample` fractions of the run (experiments.py:99-133).  supergrid = the
+    reference's `use_majorant_supergrid` (experiments.py:114,228): majorant supergrid + DDA free-flight sampling."""
     scene = mi.load_dict(_scene_dict(method, grid, film, kind))
     v = init_grid
     dev = "cuda" if torch.cuda.is_available() else "cpu"
@@ -49,7 +50,7 @@ def scene_synthetic(method, output_dir, grid=64, init_grid=16, film=(128, 128), 
             "object.interior_medium.albedo.data": {"init": torch.full((v, v, v, 3), 0.6, device=dev), "clamp": (0.0, 1.0),
                                                    "lr_factor": 2.0},
         },
-        "use_majorant_supergrid": False, "recomp_freq": 50, "upsample": list(upsample), "schedule": [0.75, 0.85, 0.95],
+        "use_majorant_supergrid": bool(supergrid), "recomp_freq": 50, "upsample": list(upsample), "schedule": [0.75, 0.85, 0.95],
         "benchmark": True, "n_steps": n_steps, "method": method, "lr": 5e-3, "spp": spp, "spp_grad": spp,
         "spp_ref": max(64, spp), "ref_passes": 2, "spp_inf": 64, "output_dir": output_dir,
         "integrator": mi.load_dict({"type": "twostateprbvolpath" if method == "cv_ps" else "prbvolpath", "max_depth": 64, "rr_depth": 64}),
@@ -66,8 +67,9 @@ def scene_synthetic_c2(method, output_dir):
 
 
 def scene_synthetic_plume(method, output_dir):
+    # like the reference's volume scenes (dust devil / janga: experiments.py:114,228) with the majorant supergrid
     return scene_synthetic(method, output_dir, grid=256, init_grid=32, film=(1024, 1024), spp=256, kind="plume",
-                           upsample=(0.04, 0.16, 0.36))
+                           upsample=(0.04, 0.16, 0.36), supergrid=True)
 
 
 AVAILABLE_SCENES = [name[len("scene_"):] for name in list(globals()) if name.startswith("scene_")]

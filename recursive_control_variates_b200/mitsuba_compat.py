@@ -77,11 +77,22 @@ class HeterogeneousMedium:
         self.phase_g = float(phase.get("g", 0.0))
         if props.get("has_spectral_extinction", False):
             raise ValueError("spectrally varying extinction is not supported (utils.py:66)")
-        if props.get("majorant_resolution_factor", 0):
-            raise ValueError("majorant supergrids are not supported yet (SURVEY.md §8f)")
+        # heterogeneous `majorant_resolution_factor` (experiments.py:70,187,306): > 1 = majorant supergrid + DDA
+        self._majorant_factor = int(props.get("majorant_resolution_factor", 0))
+        if self._majorant_factor <= 1:
+            self._majorant_factor = 0
 
     def is_twostate(self) -> bool:
         return False
+
+    def majorant_resolution_factor(self) -> int:
+        return self._majorant_factor
+
+    def set_majorant_resolution_factor(self, factor: int):
+        self._majorant_factor = int(factor) if int(factor) > 1 else 0
+
+    def has_majorant_grid(self) -> bool:
+        return self._majorant_factor > 0
 
     def parameters(self) -> Dict[str, torch.Tensor]:
         return {"sigma_t.data": self.sigma_t.data, "albedo.data": self.albedo.data}
@@ -213,9 +224,17 @@ class Scene:
             pending, self._pending = self._pending[-2:], []      # only the last two states can matter
             for sig, alb in pending:
                 self._rotate(sig, alb)
+        self._sync_majorant_factor()
         return self._ctx
 
+    def _sync_majorant_factor(self):
+        """medium.set_majorant_resolution_factor (utils.py:41-43) takes effect on the device context here."""
+        f = int(self.medium().majorant_resolution_factor())
+        if f != getattr(self._ctx, "majorant_factor", 0):
+            self._ctx.set_majorant_factor(f)
+
     def _rotate(self, sig: torch.Tensor, alb: torch.Tensor):
+        self._sync_majorant_factor()
         dev = self._ctx.torch_device
         self._ctx.rotate(sig.detach().to(dev).contiguous(), alb.detach().to(dev).contiguous())
 

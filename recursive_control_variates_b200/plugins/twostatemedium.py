@@ -30,6 +30,17 @@ class TwoStateMedium:
     def is_homogeneous(self):
         return False
 
+    # majorant supergrid (twostatemedium.py:141-172): both states share the factor
+    def majorant_resolution_factor(self) -> int:
+        return self.new.majorant_resolution_factor()
+
+    def set_majorant_resolution_factor(self, factor: int):
+        self.old.set_majorant_resolution_factor(factor)      # :150-154
+        self.new.set_majorant_resolution_factor(factor)
+
+    def has_majorant_grid(self) -> bool:
+        return self.new.has_majorant_grid()
+
     def traverse(self):
         """Only `incoming` is exposed to the optimiser (twostatemedium.py:186-187)."""
         return self.incoming.parameters()

@@ -54,6 +54,7 @@ class Context:
         self._h = h
         self.desc: Optional[SceneDesc] = None
         self.grid_shape: Optional[Tuple[int, int, int]] = None
+        self.majorant_factor = 0
 
     def close(self):
         if getattr(self, "_h", None):
@@ -99,6 +100,25 @@ class Context:
         out = (C.c_float * 2)()
         check(self.lib.rcv_medium_majorants_host(self._h, C.byref(out)))
         return float(out[0]), float(out[1])
+
+    def set_majorant_factor(self, factor: int) -> None:
+        """TwoStateMedium.set_majorant_resolution_factor (plugins/twostatemedium.py:150-154): factor > 1 switches every
+        free-flight sample to DDA traversal of a majorant supergrid with factor^3-voxel cells; 0 / 1 switches back."""
+        self._sync_stream()
+        check(self.lib.rcv_medium_set_majorant_factor(self._h, int(factor)))
+        self.majorant_factor = 0 if factor <= 1 else int(factor)
+
+    def majorant_grid(self):
+        """(old, new) local majorants as numpy (mz,my,mx) arrays, or None while the supergrid is disabled."""
+        import numpy as np
+        self._sync_stream()
+        dims = (C.c_int * 3)()
+        check(self.lib.rcv_medium_majorant_grid_host(self._h, None, None, C.byref(dims)))
+        if dims[0] == 0:
+            return None
+        o = np.zeros((dims[0], dims[1], dims[2]), np.float32); n = np.zeros_like(o)
+        check(self.lib.rcv_medium_majorant_grid_host(self._h, o.ctypes.data, n.ctypes.data, C.byref(dims)))
+        return o, n
 
     def medium_read(self, state: int):
         nz, ny, nx = self.grid_shape

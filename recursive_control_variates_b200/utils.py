@@ -55,6 +55,20 @@ class Stopwatch:
         return self.e0.elapsed_time(self.e1)
 
 
+def adjust_majorant_res_factor(scene, density_res):
+    """utils.py:27-43: the largest factor <= 8 that leaves a supergrid of at least 4 cells per side, else none.
+    (Upstream requires the grid resolution to be divisible by the factor; so does rcv_medium_rotate.)"""
+    res_factor = 8
+    min_side = int(min(density_res[:3]))
+    while res_factor > 1 and (min_side // res_factor) < 4:
+        res_factor -= 1
+    if res_factor <= 1:
+        res_factor = 0
+    medium = scene.medium()
+    if medium.majorant_resolution_factor() != res_factor:
+        medium.set_majorant_resolution_factor(res_factor)
+
+
 def initialize_parameters(params, opt, scene, scene_params):
     """utils.py:62-87.  Runs twice for cv_ps so that old == new == init."""
     for _ in range(2 if params["method"] == "cv_ps" else 1):
@@ -63,7 +77,7 @@ def initialize_parameters(params, opt, scene, scene_params):
             if "sigma_t" in key:
                 assert init_state.shape[-1] == 1
                 if params.get("use_majorant_supergrid", False):
-                    raise NotImplementedError("majorant supergrids are not supported yet (SURVEY.md §8f)")
+                    adjust_majorant_res_factor(scene, init_state.shape)        # utils.py:75-76
             opt[key] = init_state
             scene_params[key] = opt[key]
             if "lr_factor" in param:
@@ -115,6 +129,8 @@ def upsample(scene, params, opt, integrator):
         if old.dim() != 4:
             raise ValueError(f"Upsampling expects a 4D tensor. Got {old.dim()}.")
         opt[key] = ctx.upsample2x(old.data.contiguous())
+        if ".sigma_t." in key and params.get("use_majorant_supergrid", False):   # utils.py:187-188
+            adjust_majorant_res_factor(scene, opt[key].shape)
     integrator.reset()
 
 

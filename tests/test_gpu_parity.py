@@ -317,3 +317,71 @@ def test_camera_inside_medium_and_no_emitter_sampling(oracle, gpu_ctx):
         assert np.array_equal(go.cpu().numpy(), ao) and np.array_equal(gn.cpu().numpy(), an)
         assert np.array_equal(gpu_ctx.render_adjoint_primal_accum(seed=32, spp=1).cpu().numpy(),
                               oracle.vps_render_accum(d, mn, 32, 1))
+
+
+@pytest.mark.parametrize("tracer", [0, 1, 2, 3])
+@pytest.mark.parametrize("factor", [2, 4])
+def test_majorant_supergrid_dda(oracle, gpu_ctx, tracer, factor):
+    """Majorant supergrid + DDA free-flight sampling (plugins/twostatemedium.py:25-70):
+    the supergrid itself, per-lane radiance of the two-state and the single-state tracer (bit-exact) and the
+    adjoint's gradients, for every schedule."""
+    cfg = small_scene(width=40, height=32, max_depth=16, rr_depth=5)
+    d = cfg.to_desc()
+    old, new = media(16, "plume")
+    mo = oracle.OracleMedium(d, *old, majorant_factor=factor)
+    mn = oracle.OracleMedium(d, *new, majorant_factor=factor)
+    gpu_ctx.set_tracer(tracer)
+    gpu_ctx.set_scene(d)
+    gpu_ctx.set_majorant_factor(factor)
+    try:
+        gpu_set_states(gpu_ctx, old, new)
+        g_old, g_new = gpu_ctx.majorant_grid()
+        assert np.array_equal(g_old, mo.majorant_grid) and np.array_equal(g_new, mn.majorant_grid)
+        oracle.counters(True); gpu_ctx.counters(True)
+        ao, an = oracle.render_twostates_accum(d, mo, mn, seed=41, spp=1)
+        go, gn = gpu_ctx.render_twostates_accum(seed=41, spp=1)
+        oc, gc = oracle.counters(True), gpu_ctx.counters(True)
+        assert np.array_equal(go.cpu().numpy(), ao) and np.array_equal(gn.cpu().numpy(), an)
+        assert int(oc[0]) == int(gc[0]) and int(oc[1]) == int(gc[1])
+        assert np.array_equal(gpu_ctx.render_adjoint_primal_accum(seed=42, spp=1).cpu().numpy(),
+                              oracle.vps_render_accum(d, mn, 42, 1))
+        gimg = np.full((d.film_height, d.film_width, 3), 1e-3, np.float32)
+        gs, ga = oracle.vps_backward(d, mn, 43, 3, gimg, threads=1)
+        gpu_ctx.grad_zero(); gpu_ctx.render_backward(43, 3, to_cuda(gimg))
+        ggs, gga = gpu_ctx.grad_read()
+        assert rel_l2(ggs.cpu().numpy(), gs) < GRAD_TOL and rel_l2(gga.cpu().numpy(), ga) < GRAD_TOL
+        # fewer tentative collisions than with one majorant for the volume, same image in expectation
+        m0o, m0n = oracle.OracleMedium(d, *old), oracle.OracleMedium(d, *new)
+        H1, F1 = gpu_ctx.render_twostates(seed=44, spp=64)
+        c1 = gpu_ctx.counters(True)
+        gpu_ctx.set_majorant_factor(0)
+        assert gpu_ctx.majorant_grid() is None
+        H0, F0 = gpu_ctx.render_twostates(seed=44, spp=64)
+        c0 = gpu_ctx.counters(True)
+        assert int(c1[0]) < int(c0[0])
+        assert abs(float(F1.mean()) - float(F0.mean())) < 5e-3 * float(F0.mean())
+    finally:
+        gpu_ctx.set_majorant_factor(0)
+        gpu_ctx.set_tracer(3)
+
+
+def test_majorant_factor_errors(gpu_ctx):
+    from recursive_control_variates_b200._abi import RcvError
+    d = small_scene(width=8, height=8).to_desc()
+    gpu_ctx.set_scene(d)
+    old, new = media(12)
+    gpu_set_states(gpu_ctx, old, new)
+    gpu_ctx.set_majorant_factor(5)               # 12 % 5 != 0: accepted (a rotation may follow) but nothing renders
+    assert gpu_ctx.majorant_grid() is None
+    with pytest.raises(RcvError):
+        gpu_ctx.render_twostates_accum(seed=1, spp=1)
+    with pytest.raises(RcvError):
+        gpu_ctx.set_majorant_factor(-1)
+    gpu_ctx.set_majorant_factor(1)               # <= 1 disables (utils.py:36-37)
+    assert gpu_ctx.majorant_grid() is None
+    gpu_ctx.set_majorant_factor(4)
+    o, n = gpu_ctx.majorant_grid()
+    assert o.shape == (3, 3, 3)
+    with pytest.raises(RcvError):                # a rotation to a grid the factor does not divide is refused
+        gpu_set_states(gpu_ctx, media(10)[0], media(10)[1])
+    gpu_ctx.set_majorant_factor(0)

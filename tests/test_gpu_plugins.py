@@ -125,3 +125,19 @@ def test_gradient_through_render_op(mi, oracle):
     m = oracle.OracleMedium(desc, sig, alb)
     ogs, oga = oracle.vps_backward(desc, m, tea32(3, 1)[0], 2, gimg)
     assert rel_l2(gs, ogs) < 1e-3 and rel_l2(ga, oga) < 1e-3
+
+
+def test_run_opt_loop_with_majorant_supergrid(mi):
+    """`use_majorant_supergrid` (experiments.py:114, utils.py:27-43,75-76,187-188): the factor follows the grid
+    resolution through the coarse-to-fine schedule and the whole loop runs on the DDA kernels."""
+    import torch
+    from recursive_control_variates_b200.optimize import run_opt
+    p = _params("cv_ps", supergrid=True)
+    res = run_opt(p)
+    scene = p["scene"]
+    s = res["opt"]["object.interior_medium.sigma_t.data"]
+    assert s.shape == (16, 16, 16, 1)
+    assert scene.medium().majorant_resolution_factor() == 4           # 8^3 -> factor 2, 16^3 -> factor 4
+    o, n = scene._ctx.majorant_grid()
+    assert o.shape == (4, 4, 4) and float(n.max()) > 0
+    assert torch.isfinite(s).all() and np.isfinite(res["loss"]).all()
