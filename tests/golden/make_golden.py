@@ -35,7 +35,14 @@ def compute(O):
     for it in range(5):
         O.cv_update(H * (1 + 0.01 * it), F * (1 + 0.012 * it), st, it, 1, n, 0.9, 0.999)
         n += it > 0
-    return {"acc_old": acc_o, "acc_new": acc_n, "vps_acc": vps, "grad_sigma_t": gs.astype(np.float32),
+    # the same with the majorant supergrid (factor 4: a 2^3 supergrid) and DDA free-flight sampling
+    so, sn = O.OracleMedium(desc, *old, majorant_factor=4), O.OracleMedium(desc, *new, majorant_factor=4)
+    sg_o, sg_n = O.render_twostates_accum(desc, so, sn, seed=7, spp=1, threads=1)
+    sg_vps = O.vps_render_accum(desc, sn, seed=8, spp=1, threads=1)
+    sg_gs, sg_ga = O.vps_backward(desc, sn, 0x5D8714D7, 2, gimg, threads=1)
+    sg = {"sg_acc_old": sg_o, "sg_acc_new": sg_n, "sg_vps_acc": sg_vps, "sg_grad_sigma_t": sg_gs.astype(np.float32),
+          "sg_grad_albedo": sg_ga.astype(np.float32), "sg_majorant_grid_old": so.majorant_grid, "sg_majorant_grid_new": sn.majorant_grid}
+    return {**sg, "acc_old": acc_o, "acc_new": acc_n, "vps_acc": vps, "grad_sigma_t": gs.astype(np.float32),
             "grad_albedo": ga.astype(np.float32), "cv_img": st["img"], "cv_w_s": st["w_s"],
             "alt_seed": np.array([O.alt_seed(0x5D8714D7)], np.uint32), "majorants": np.array([mo.majorant, mn.majorant], np.float32)}
 

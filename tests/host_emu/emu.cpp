@@ -20,11 +20,12 @@ struct Packed {
     std::vector<float4> blk2, blk1;
     std::vector<float4> alb2;
     float maj[2];
-    GridK G;
+    std::vector<float2> mgrid;      // majorant supergrid (factor > 0)
+    GridKS G;
 };
 
 void pack(const rcv_scene_desc &d, const float *so, const float *ao, const float *sn, const float *an, int nz, int ny, int nx,
-          Packed &P) {
+          Packed &P, int factor = 0) {
     size_t n = (size_t) nz * ny * nx;
     P.sig2.resize(n); P.alb2.resize(2 * n);
     float mo = so[0], mn = sn[0];
@@ -51,6 +52,28 @@ void pack(const rcv_scene_desc &d, const float *so, const float *ao, const float
     }
     P.G.sig2 = P.sig2.data(); P.G.blk2 = P.blk2.data(); P.G.blk1 = P.blk1.data(); P.G.alb2 = P.alb2.data();
     P.G.nx = nx; P.G.ny = ny; P.G.nz = nz; P.G.majorants = P.maj;
+    P.G.mgrid = nullptr; P.G.mx = P.G.my = P.G.mz = 0; P.G.vox[0] = P.G.vox[1] = P.G.vox[2] = 0.f;
+    if (factor > 0) {
+        // as k_majorant_grid does on the device: voxels [c f - 1, c f + f] per axis, clamped
+        int mx = nx / factor, my = ny / factor, mz = nz / factor;
+        P.mgrid.resize((size_t) mx * my * mz);
+        for (int cz = 0; cz < mz; ++cz)
+            for (int cy = 0; cy < my; ++cy)
+                for (int cx = 0; cx < mx; ++cx) {
+                    float mo2 = 0.f, mn2 = 0.f;
+                    for (int dz = -1; dz <= factor; ++dz)
+                        for (int dy = -1; dy <= factor; ++dy)
+                            for (int dx = -1; dx <= factor; ++dx) {
+                                int z = std::min(std::max(cz * factor + dz, 0), nz - 1), y = std::min(std::max(cy * factor + dy, 0), ny - 1),
+                                    x = std::min(std::max(cx * factor + dx, 0), nx - 1);
+                                float2 v = P.sig2[((size_t) z * ny + y) * nx + x];
+                                mo2 = fmax_(mo2, v.x); mn2 = fmax_(mn2, v.y);
+                            }
+                    P.mgrid[((size_t) cz * my + cy) * mx + cx] = make_float2(d.sigma_t_scale * mo2, d.sigma_t_scale * mn2);
+                }
+        P.G.mgrid = P.mgrid.data(); P.G.mx = mx; P.G.my = my; P.G.mz = mz;
+        P.G.vox[0] = 1.f / (float) mx; P.G.vox[1] = 1.f / (float) my; P.G.vox[2] = 1.f / (float) mz;
+    }
 }
 
 struct HostQueue {
@@ -62,8 +85,8 @@ struct HostQueue {
 
 // raygen for all lanes (as the GPU's ray-generation kernel), then the event
 // machines record by record
-template <int MODE>
-void run_twostates(const SceneK &S, const GridK &G, uint32_t seed, uint32_t spp, float4 *acc_old, float4 *acc_new, uint64_t *cnt) {
+template <int MODE, class GRID>
+void run_twostates(const SceneK &S, const GRID &G, uint32_t seed, uint32_t spp, float4 *acc_old, float4 *acc_new, uint64_t *cnt) {
     const float mu = combined_majorant<MODE>(G);
     const float inv_mu = 1.f / mu;
     TsSink sk; sk.acc_old = acc_old; sk.acc_new = acc_new; sk.n_coll = sk.n_scat = sk.n_paths = 0;
@@ -86,8 +109,8 @@ void run_twostates(const SceneK &S, const GridK &G, uint32_t seed, uint32_t spp,
     cnt[0] += sk.n_coll; cnt[1] += sk.n_scat; cnt[6] += sk.n_paths;
 }
 
-template <bool BW>
-void run_vps(const SceneK &S, const GridK &G, VpSink &sk) {
+template <bool BW, class GRID>
+void run_vps(const SceneK &S, const GRID &G, VpSink &sk) {
     const float mu = G.majorants[1];
     const float inv_mu = 1.f / mu;
     uint64_t n = (uint64_t) S.W * S.H * sk.spp;
@@ -118,32 +141,55 @@ void run_vps(const SceneK &S, const GridK &G, VpSink &sk) {
 
 extern "C" {
 
+// factor > 0: majorant supergrid + DDA (the GridKS instantiation of the handlers)
+int emu_twostates_sg(const rcv_scene_desc *d, const float *so, const float *ao, const float *sn, const float *an, int nz, int ny,
+                     int nx, uint32_t seed, uint32_t spp, int mode, int factor, float *acc_old, float *acc_new, uint64_t *counters) {
+    SceneK S; scene_from_desc(*d, S);
+    Packed P; pack(*d, so, ao, sn, an, nz, ny, nx, P, factor);
+    for (int i = 0; i < 8; ++i) counters[i] = 0;
+    float4 *ao4 = (float4 *) acc_old, *an4 = (float4 *) acc_new;
+    if (factor > 0) {
+        if (mode == 0) run_twostates<0>(S, P.G, seed, spp, ao4, an4, counters);
+        else if (mode == 1) run_twostates<1>(S, P.G, seed, spp, ao4, an4, counters);
+        else run_twostates<2>(S, P.G, seed, spp, ao4, an4, counters);
+    } else {
+        const GridK &G = P.G;
+        if (mode == 0) run_twostates<0>(S, G, seed, spp, ao4, an4, counters);
+        else if (mode == 1) run_twostates<1>(S, G, seed, spp, ao4, an4, counters);
+        else run_twostates<2>(S, G, seed, spp, ao4, an4, counters);
+    }
+    return 0;
+}
 int emu_twostates(const rcv_scene_desc *d, const float *so, const float *ao, const float *sn, const float *an, int nz, int ny,
                   int nx, uint32_t seed, uint32_t spp, int mode, float *acc_old, float *acc_new, uint64_t *counters) {
-    SceneK S; scene_from_desc(*d, S);
-    Packed P; pack(*d, so, ao, sn, an, nz, ny, nx, P);
-    for (int i = 0; i < 8; ++i) counters[i] = 0;
-    if (mode == 0) run_twostates<0>(S, P.G, seed, spp, (float4 *) acc_old, (float4 *) acc_new, counters);
-    else if (mode == 1) run_twostates<1>(S, P.G, seed, spp, (float4 *) acc_old, (float4 *) acc_new, counters);
-    else run_twostates<2>(S, P.G, seed, spp, (float4 *) acc_old, (float4 *) acc_new, counters);
-    return 0;
+    return emu_twostates_sg(d, so, ao, sn, an, nz, ny, nx, seed, spp, mode, 0, acc_old, acc_new, counters);
 }
 
 // volpathsimple: primal render (backward == 0) or the two-pass adjoint; the
 // gradient grids use the library's layout (float + float4 per voxel)
-int emu_vps(const rcv_scene_desc *d, const float *sn, const float *an, int nz, int ny, int nx, uint32_t seed, uint32_t spp,
-            int backward, uint32_t alt_seed, const float *grad_img, const float *film_w, float *accum, float *gsig,
-            float *galb4, uint64_t *counters) {
+int emu_vps_sg(const rcv_scene_desc *d, const float *sn, const float *an, int nz, int ny, int nx, uint32_t seed, uint32_t spp,
+               int backward, uint32_t alt_seed, const float *grad_img, const float *film_w, float *accum, float *gsig,
+               float *galb4, uint64_t *counters, int factor) {
     SceneK S; scene_from_desc(*d, S);
-    Packed P; pack(*d, sn, an, sn, an, nz, ny, nx, P);
+    Packed P; pack(*d, sn, an, sn, an, nz, ny, nx, P, factor);
     for (int i = 0; i < 8; ++i) counters[i] = 0;
     VpSink sk; sk.accum = (float4 *) accum; sk.D.gsig = gsig; sk.D.galb = (float4 *) galb4; sk.grad_img = grad_img; sk.film_w = film_w;
     sk.seed = seed; sk.spp = spp; sk.alt_seed = alt_seed;
     sk.cnt.coll = sk.cnt.scat = sk.cnt.g_sig = sk.cnt.g_alb = 0; sk.n_paths = 0;
-    if (backward) run_vps<true>(S, P.G, sk); else run_vps<false>(S, P.G, sk);
+    if (factor > 0) {
+        if (backward) run_vps<true>(S, P.G, sk); else run_vps<false>(S, P.G, sk);
+    } else {
+        const GridK &G = P.G;
+        if (backward) run_vps<true>(S, G, sk); else run_vps<false>(S, G, sk);
+    }
     counters[2] = sk.cnt.coll; counters[3] = sk.cnt.scat; counters[4] = sk.cnt.g_sig; counters[5] = sk.cnt.g_alb;
     counters[6] = sk.n_paths;
     return 0;
+}
+int emu_vps(const rcv_scene_desc *d, const float *sn, const float *an, int nz, int ny, int nx, uint32_t seed, uint32_t spp,
+            int backward, uint32_t alt_seed, const float *grad_img, const float *film_w, float *accum, float *gsig,
+            float *galb4, uint64_t *counters) {
+    return emu_vps_sg(d, sn, an, nz, ny, nx, seed, spp, backward, alt_seed, grad_img, film_w, accum, gsig, galb4, counters, 0);
 }
 
 }  // extern "C"

@@ -194,6 +194,19 @@ def test_golden_fixture_on_gpu(oracle, gpu_ctx):
     assert rel_l2(gs.cpu().numpy(), ref["grad_sigma_t"]) < GRAD_TOL and rel_l2(ga.cpu().numpy(), ref["grad_albedo"]) < GRAD_TOL
     m = gpu_ctx.majorants()
     assert np.array_equal(np.array(m, np.float32), ref["majorants"])
+    # majorant supergrid (factor 4) fixtures
+    gpu_ctx.set_majorant_factor(4)
+    try:
+        mg_o, mg_n = gpu_ctx.majorant_grid()
+        assert np.array_equal(mg_o, ref["sg_majorant_grid_old"]) and np.array_equal(mg_n, ref["sg_majorant_grid_new"])
+        go, gn = gpu_ctx.render_twostates_accum(seed=7, spp=1)
+        assert np.array_equal(go.cpu().numpy(), ref["sg_acc_old"]) and np.array_equal(gn.cpu().numpy(), ref["sg_acc_new"])
+        assert np.array_equal(gpu_ctx.render_adjoint_primal_accum(seed=8, spp=1).cpu().numpy(), ref["sg_vps_acc"])
+        gpu_ctx.grad_zero(); gpu_ctx.render_backward(0x5D8714D7, 2, to_cuda(gimg))
+        gs, ga = gpu_ctx.grad_read()
+        assert rel_l2(gs.cpu().numpy(), ref["sg_grad_sigma_t"]) < GRAD_TOL and rel_l2(ga.cpu().numpy(), ref["sg_grad_albedo"]) < GRAD_TOL
+    finally:
+        gpu_ctx.set_majorant_factor(0)
 
 
 @pytest.mark.parametrize("tracer", [0, 1, 2, 3])

@@ -27,6 +27,10 @@ def emu():
                                   f32, f32, u64]
     lib.emu_vps.argtypes = [C.c_void_p, f32, f32, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32,
                             C.c_void_p, C.c_void_p, f32, f32, f32, u64]
+    lib.emu_twostates_sg.argtypes = [C.c_void_p, f32, f32, f32, f32, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int,
+                                     C.c_int, f32, f32, u64]
+    lib.emu_vps_sg.argtypes = [C.c_void_p, f32, f32, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32,
+                               C.c_void_p, C.c_void_p, f32, f32, f32, u64, C.c_int]
     return lib
 
 
@@ -131,4 +135,32 @@ def test_hg_phase_and_shallow_depth(oracle, emu):
     film_w = oracle.film_weights(d, 9, 2)
     emu.emu_vps(C.addressof(d), sn, an, *sn.shape[:3], 9, 2, 1, oracle.alt_seed(9), gimg.ctypes.data, film_w.ctypes.data, acc, g1, g4, cnt)
     gs, ga = oracle.vps_backward(d, mn, 9, 2, gimg, threads=1, film_w=film_w)
+    assert rel_l2(g1, gs) < 1e-5 and rel_l2(g4[..., 0:3], ga) < 1e-5
+
+
+@pytest.mark.parametrize("factor", [2, 4])
+def test_majorant_supergrid_event_machines(oracle, emu, factor):
+    """Majorant supergrid + DDA free-flight sampling (plugins/twostatemedium.py:25-70) in the GridKS instantiation of
+    the event machines: two-state render, single-state primal and the adjoint against the oracle."""
+    d = small_scene(32, 28, max_depth=12, rr_depth=4).to_desc()
+    (so, ao), (sn, an) = media(16, "plume")
+    mo, mn = oracle.OracleMedium(d, so, ao, majorant_factor=factor), oracle.OracleMedium(d, sn, an, majorant_factor=factor)
+    H, W = d.film_height, d.film_width
+    acc_o = np.zeros((H, W, 4), np.float32); acc_n = np.zeros((H, W, 4), np.float32)
+    cnt = np.zeros(8, np.uint64)
+    emu.emu_twostates_sg(C.addressof(d), so, ao, sn, an, *so.shape[:3], 13, 2, 0, factor, acc_o, acc_n, cnt)
+    oracle.counters(True)
+    ref_o, ref_n = oracle.render_twostates_accum(d, mo, mn, 13, 2)
+    oc = oracle.counters(True)
+    assert np.array_equal(acc_o, ref_o) and np.array_equal(acc_n, ref_n)
+    assert int(cnt[0]) == int(oc[0]) and int(cnt[1]) == int(oc[1])
+    acc = np.zeros((H, W, 4), np.float32); g1 = np.zeros((*sn.shape[:3], 1), np.float32); g4 = np.zeros((*sn.shape[:3], 4), np.float32)
+    emu.emu_vps_sg(C.addressof(d), sn, an, *sn.shape[:3], 14, 1, 0, 0, None, None, acc, g1, g4, cnt, factor)
+    assert np.array_equal(acc, oracle.vps_render_accum(d, mn, 14, 1))
+    gimg = np.full((H, W, 3), 1e-3, np.float32)
+    film_w = oracle.film_weights(d, 15, 2)
+    acc[:] = 0
+    emu.emu_vps_sg(C.addressof(d), sn, an, *sn.shape[:3], 15, 2, 1, oracle.alt_seed(15), gimg.ctypes.data, film_w.ctypes.data,
+                   acc, g1, g4, cnt, factor)
+    gs, ga = oracle.vps_backward(d, mn, 15, 2, gimg, threads=1, film_w=film_w)
     assert rel_l2(g1, gs) < 1e-5 and rel_l2(g4[..., 0:3], ga) < 1e-5

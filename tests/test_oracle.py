@@ -170,3 +170,93 @@ def test_golden_outputs(oracle):
     cur = compute(oracle)
     for k in ref.files:
         assert np.array_equal(ref[k], cur[k], equal_nan=True), k
+
+
+# ---------------------------------------------------------------------------
+# majorant supergrid + DDA (plugins/twostatemedium.py:25-70)
+# ---------------------------------------------------------------------------
+def _numpy_majorant_grid(sigma_t, f, scale):
+    """Independent restatement: max over voxels [c f - 1, c f + f] per axis with edge clamping."""
+    s = np.pad(sigma_t[..., 0], 1, mode="edge")
+    nz, ny, nx = sigma_t.shape[:3]
+    out = np.zeros((nz // f, ny // f, nx // f), np.float32)
+    for cz in range(nz // f):
+        for cy in range(ny // f):
+            for cx in range(nx // f):
+                out[cz, cy, cx] = s[cz * f:cz * f + f + 2, cy * f:cy * f + f + 2, cx * f:cx * f + f + 2].max()
+    return (np.float32(scale) * out).astype(np.float32)
+
+
+def test_majorant_grid_bounds_the_density(oracle):
+    d = small_scene(width=8, height=8).to_desc()
+    _, (sig, alb) = media(16, "plume")
+    with pytest.raises(ValueError):
+        oracle.OracleMedium(d, sig, alb, majorant_factor=5)
+    for f in (2, 4, 8):
+        m = oracle.OracleMedium(d, sig, alb, majorant_factor=f)
+        assert np.array_equal(m.majorant_grid, _numpy_majorant_grid(sig, f, d.sigma_t_scale))
+        assert float(m.majorant_grid.max()) == m.majorant                  # the global majorant is the max of the local ones
+        # every trilinear lookup inside a supercell is bounded by the cell's majorant
+        rng = np.random.default_rng(f)
+        p = rng.random((4000, 3))
+        pos = p * 16 - 0.5
+        i0 = np.floor(pos).astype(int); w = pos - i0
+        val = np.zeros(len(p))
+        for dz in (0, 1):
+            for dy in (0, 1):
+                for dx in (0, 1):
+                    ix = np.clip(i0[:, 0] + dx, 0, 15); iy = np.clip(i0[:, 1] + dy, 0, 15); iz = np.clip(i0[:, 2] + dz, 0, 15)
+                    wt = np.where(dx, w[:, 0], 1 - w[:, 0]) * np.where(dy, w[:, 1], 1 - w[:, 1]) * np.where(dz, w[:, 2], 1 - w[:, 2])
+                    val += wt * sig[iz, iy, ix, 0]
+        cell = np.clip(np.floor(p * (16 // f)).astype(int), 0, 16 // f - 1)
+        bound = m.majorant_grid[cell[:, 2], cell[:, 1], cell[:, 0]]
+        assert (d.sigma_t_scale * val <= bound * (1 + 1e-6)).all()
+
+
+def test_dda_matches_brute_force_integration(oracle):
+    """The sampled free-flight distance inverts the optical depth of the piecewise-constant majorant along the ray."""
+    d = small_scene(width=8, height=8).to_desc()
+    _, (sig, alb) = media(16, "cube")
+    for f in (4, 8):
+        m = oracle.OracleMedium(d, sig, alb, majorant_factor=f)
+        mg = m.majorant_grid.astype(np.float64); res = np.array(mg.shape[::-1])
+        rng = np.random.default_rng(10 + f)
+        for _ in range(300):
+            o = rng.random(3); dd = rng.normal(size=3); dd /= np.linalg.norm(dd)
+            with np.errstate(divide="ignore"):
+                t_exit = np.maximum((0 - o) / dd, (1 - o) / dd).min()
+            tau = -math.log(1 - rng.random())
+            t = oracle.dda_sample(d, None, m, o, dd, 0.0, float(t_exit), float(tau))
+            n = 4000
+            ts = (np.arange(n) + 0.5) / n * t_exit
+            idx = np.clip(np.floor((o[None] + ts[:, None] * dd[None]) * res[None]).astype(int), 0, res[None] - 1)
+            cum = np.cumsum(mg[idx[:, 2], idx[:, 1], idx[:, 0]]) * t_exit / n
+            k = int(np.searchsorted(cum, tau))
+            if k >= n - 2 or abs(cum[-1] - tau) < 1e-3 * max(1.0, tau):
+                continue                                                   # at the exit: either answer is right
+            assert math.isfinite(t) and abs(t - ts[k]) < 2e-3 * max(1.0, t_exit), (t, ts[k])
+
+
+def test_supergrid_is_unbiased(oracle):
+    """Same expectation with and without the supergrid, for the two-state render and for the adjoint."""
+    cfg = small_scene(width=32, height=24, max_depth=16, rr_depth=8)
+    d = cfg.to_desc()
+    old, new = media(16, "plume")
+    ref_o, ref_n = oracle.OracleMedium(d, *old), oracle.OracleMedium(d, *new)
+    H0, F0 = oracle.render_twostates(d, ref_o, ref_n, seed=3, spp=512)
+    gimg = np.full((d.film_height, d.film_width, 3), 1.0 / (32 * 24 * 3), np.float32)
+    def grad_sums(m):      # the sigma_t gradient is noisy (std of one 512-spp run: 3-5 % of its sum): average 4 seeds
+        g = [oracle.vps_backward(d, m, 5 + k, 512, gimg) for k in range(4)]
+        return np.mean([x[0].sum() for x in g]), np.mean([x[1].sum() for x in g])
+    gs0, ga0 = grad_sums(ref_n)
+    for f in (2, 4):
+        mo, mn = oracle.OracleMedium(d, *old, majorant_factor=f), oracle.OracleMedium(d, *new, majorant_factor=f)
+        oracle.counters(True)
+        H, F = oracle.render_twostates(d, mo, mn, seed=3, spp=512)
+        assert abs(F.mean() - F0.mean()) < 2e-3 * F0.mean() and abs(H.mean() - H0.mean()) < 2e-3 * H0.mean()
+        assert rel_l2(F, F0) < 0.05                                         # pixel-wise: Monte Carlo noise only
+        # control-variate property is kept: H - F is still a small, highly correlated difference
+        assert np.abs(H - F).mean() < 0.1 * np.abs(F).mean()
+        gs, ga = grad_sums(mn)
+        assert abs(gs - gs0) < 0.08 * abs(gs0)
+        assert abs(ga - ga0) < 0.01 * abs(ga0)
