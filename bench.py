@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--tracer", type=int, default=3, help="3 pool (default), 0 wavefront, 1 simple, 2 batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--supergrid", type=int, default=8,
+                    help="also time the same iteration with a majorant supergrid of this factor (0 = skip); reported under `supergrid`")
     ap.add_argument("--cpu-sample-spp", type=int, default=0, help="spp range of the CPU sample (0 = auto: ~15 s of CPU work)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target duration of one CPU sample")
     return ap.parse_args()
@@ -313,13 +315,89 @@ def run_ours(a):
             tj = json.load(f)
         if dom in tj:
             traffic, traffic_src = tj[dom]["dram_bytes"] / 1e9, tj[dom]["capture"]
+    # informational: the random-gather ceiling of this GPU (scripts/microbench/gather_bw.cu, 64-byte granules, 1 GiB array)
+    gather_peak = None
+    gpath = os.path.join(ROOT, "profiles", "r24_gather_bw_1GiB.jsonl")
+    if os.path.exists(gpath):
+        with open(gpath) as f:
+            rows = [json.loads(l) for l in f if l.strip().startswith("{")]
+        g64 = [r["GBps"] for r in rows if r.get("granule_bytes") == 64]
+        gather_peak = max(g64) if g64 else None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["gbs"] / peak, "traffic": traffic, "traffic_unit": "GB per launch",
                 "traffic_source": traffic_src, "algorithmic_gb": kernels[dom]["algorithmic_gb"], "peak_source": peak_src,
-                "share_of_step": kernels[dom]["ms"] / ms_per_step}
+                "share_of_step": kernels[dom]["ms"] / ms_per_step,
+                "gather_peak": gather_peak, "gather_peak_source": "profiles/r24_gather_bw_1GiB.jsonl (random 64-B granules, useful GB/s)",
+                "frac_of_gather_peak": (kernels[dom]["gbs"] / gather_peak) if gather_peak else None}
+
+    # ---- the same iteration with the majorant supergrid + DDA (reference `use_majorant_supergrid`), informational
+    supergrid = None
+    if a.supergrid > 1 and a.grid % a.supergrid == 0:
+        ctx.set_majorant_factor(a.supergrid)
+        step(a.warmup + a.steps); barrier(); ctx.counters(True)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_sg = max(2, min(a.steps, 3))
+        s0.record()
+        for i in range(n_sg):
+            step(a.warmup + a.steps + 1 + i)
+        s1.record(); barrier()
+        sg_cnt = ctx.counters(True).astype(np.float64) / n_sg
+        tsg = torch.tensor([s0.elapsed_time(s1) / n_sg], device=dev)
+        if world > 1:
+            dist.all_reduce(tsg, op=dist.ReduceOp.MAX)
+        sg_ms = float(tsg.item())
+        supergrid = {"factor": a.supergrid, "ms_per_step": sg_ms, "value": paths_per_step / (sg_ms * 1e-3) / 1e6, "unit": UNIT,
+                     "twostate_collisions": sg_cnt[0], "adjoint_collisions": sg_cnt[2],
+                     "note": "same workload, free flights sampled by DDA through the majorant supergrid (not the headline config)"}
+        ctx.set_majorant_factor(0)
 
     # ---- end to end through the host-buffer C-ABI call (pinned host memory, copies inside the timed region)
     e2e = None
+    if not a.no_e2e and world > 1:
+        # N > 1: the same iteration through the Python API with pinned HOST buffers on every rank — parameters and target
+        # up, shard renders + NCCL all-reduces on the device, image / loss / gradients down
+        pin = lambda t_: t_.detach().cpu().contiguous().pin_memory()
+        hs, ha, href = pin(sigma), pin(albedo), pin(ref)
+        himg, hloss = torch.zeros(H, W, 3).pin_memory(), torch.zeros(1).pin_memory()
+        hgs, hga = torch.zeros_like(hs).pin_memory(), torch.zeros_like(ha).pin_memory()
+        d_s, d_a, d_ref = torch.empty_like(sigma), torch.empty_like(albedo), torch.empty_like(ref)
+        cv2 = ctx.new_cv_state()
+        st2 = {"it": 0, "n": 0}
+
+        def e2e_step(i):
+            seed = SEED0 + i
+            d_s.copy_(hs, non_blocking=True); d_a.copy_(ha, non_blocking=True); d_ref.copy_(href, non_blocking=True)
+            ctx.rotate(d_s, d_a)
+            acc[0].zero_(); acc[1].zero_()
+            ctx.render_twostates_accum(seed, spp_total, spp_b, spp_e, out=acc)
+            dist.all_reduce(acc[0]); dist.all_reduce(acc[1])
+            ctx.develop(acc[0], Himg); ctx.develop(acc[1], Fimg)
+            ctx.cv_update(Himg, Fimg, cv2, st2["it"], 1, st2["n"], 0.9, 0.999)
+            st2["n"] += st2["it"] > 0; st2["it"] += 1
+            l_, g_ = ctx.loss_grad(_abi.RCV_LOSS_L1, cv2["img"], d_ref)
+            ctx.grad_zero()
+            ctx.render_backward(tea32(seed, 1)[0], spp_total, g_, spp_b, spp_e)
+            dist.all_reduce(ctx.grad_packed())
+            gs_, ga_ = ctx.grad_read()
+            hgs.copy_(gs_, non_blocking=True); hga.copy_(ga_, non_blocking=True)
+            himg.copy_(cv2["img"], non_blocking=True); hloss.copy_(l_.reshape(1), non_blocking=True)
+            torch.cuda.synchronize()
+
+        e2e_step(0); e2e_step(1)
+        barrier()
+        n_e2e = max(2, min(a.steps, 3))
+        t0 = time.perf_counter()
+        for i in range(n_e2e):
+            e2e_step(2 + i)
+        barrier()
+        te = torch.tensor([(time.perf_counter() - t0) / n_e2e], device=dev)
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dt = float(te.item())
+        h2d = (hs.numel() + ha.numel() + href.numel()) * 4
+        d2h = (himg.numel() + 1 + hgs.numel() + hga.numel()) * 4
+        e2e = {"value": paths_per_step / dt / 1e6, "unit": UNIT, "ms_per_step": dt * 1e3, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "api": "Context API per rank with pinned host buffers (bytes are per rank); NCCL "
+               "all-reduce of film accumulators and gradients"}
     if not a.no_e2e and world == 1:
         pin = lambda t_: t_.detach().cpu().contiguous().pin_memory()
         hs, ha, href = pin(sigma), pin(albedo), pin(ref)
@@ -365,7 +443,7 @@ def run_ours(a):
                           "l2": "inputs larger than L2 (two-state grids %d MiB)" % (a.grid ** 3 * 40 // 2 ** 20),
                           "tracer": {0: "wavefront", 1: "simple", 2: "batch", 3: "pool"}[a.tracer], "loss_last": float(loss.item())},
                "clocks": clocks, "gpu_launches": int(cnt[7]), "roofline": roofline, "kernels": kernels,
-               "e2e": e2e, "cpu_baseline": cpu}
+               "e2e": e2e, "cpu_baseline": cpu, "supergrid": supergrid}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -436,8 +436,12 @@ static float dda_sample(const rcv_scene_desc *S, const orc_medium *Mo, const orc
         float tmid = 0.5f * (dda_t + fminf_(t_next, maxt));
         float majorant = majorant2_at(S, Mo, Mn, ray_at(ray->o, ray->d, tmid));
         float tau_next = tau_acc + (majorant * (t_next - dda_t));
-        float t_precise = dda_t + ((desired_tau - tau_acc) / majorant);
-        reached = reached || ((majorant > 0.f) && (t_precise < maxt) && (tau_next >= desired_tau));
+        /* :59-62; the division is only evaluated where its result can be used */
+        float t_precise = t_next;
+        if ((majorant > 0.f) && (tau_next >= desired_tau)) {
+            t_precise = dda_t + ((desired_tau - tau_acc) / majorant);
+            reached = t_precise < maxt;
+        }
         dda_t = reached ? t_precise : t_next;
         active = !reached && (t_next < maxt);
         if (active) { tmax3[axis] = tmax3[axis] + tdelta[axis]; tau_acc = tau_next; }

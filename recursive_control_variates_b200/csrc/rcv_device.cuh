@@ -565,8 +565,11 @@ __device__ __forceinline__ float dda_sample(const SceneK &S, const GridKS &G, V3
         float tmid = 0.5f * (dda_t + fmin_(t_next, maxt));
         float majorant = majorant_at<SEL>(S, G, ray_at(o, d, tmid));
         float tau_next = tau_acc + (majorant * (t_next - dda_t));
-        float t_precise = dda_t + ((tau - tau_acc) / majorant);
-        reached = reached || ((majorant > 0.f) && (t_precise < maxt) && (tau_next >= tau));
+        float t_precise = t_next;
+        if ((majorant > 0.f) && (tau_next >= tau)) {                  // the division only where its result can be used
+            t_precise = dda_t + ((tau - tau_acc) / majorant);
+            reached = t_precise < maxt;
+        }
         dda_t = reached ? t_precise : t_next;
         active = !reached && (t_next < maxt);
         if (active) {
