@@ -10,7 +10,7 @@ import numpy as np
 from . import experiments
 from .optimize import run_opt
 
-AVAILABLE_METHODS = ["baseline", "cv_ps"]
+AVAILABLE_METHODS = ["baseline", "cv_ps", "cv_pss"]
 
 
 def run_experiment(config):
@@ -36,12 +36,15 @@ def main(argv=None):
         parser.add_argument(f"--{name}", type=typ)
     parser.add_argument("--loss", type=str, choices=["L1", "L2"])
     parser.add_argument("--pre_update", action="store_true", default=None)
+    parser.add_argument("--force_baseline", action="store_true", default=None)
+    parser.add_argument("--all", action="store_true", help="also run cv_pss (run_experiment.py:63: not run by default)")
     args = parser.parse_args(argv)
     print(f"{'Experiment':^20} | {'Method':^20}")
     for experiment in args.experiment:
-        for method in (AVAILABLE_METHODS if args.method is None else [args.method]):
+        default_methods = AVAILABLE_METHODS if args.all else [m for m in AVAILABLE_METHODS if m != "cv_pss"]
+        for method in (default_methods if args.method is None else [args.method]):
             cfg = {"experiment": experiment, "method": method,
-                   **{k: v for k, v in vars(args).items() if v is not None and k not in ("experiment", "method")}}
+                   **{k: v for k, v in vars(args).items() if v is not None and k not in ("experiment", "method", "all")}}
             res = run_experiment(cfg)
             print(f"{experiment:^20} | {method:^20} | final loss {res['loss'][-1]:.5f}")
 

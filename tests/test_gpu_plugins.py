@@ -141,3 +141,39 @@ def test_run_opt_loop_with_majorant_supergrid(mi):
     o, n = scene._ctx.majorant_grid()
     assert o.shape == (4, 4, 4) and float(n.max()) > 0
     assert torch.isfinite(s).all() and np.isfinite(res["loss"]).all()
+
+
+def test_cv_pss_and_force_baseline(mi, oracle):
+    """(spp = 1: one sample per pixel, so renders are reproducible bit for bit.)  metaintegrator.py:90-91,117-128: the primary-sample-space control variate re-renders the previous state with
+    the next seed; force_baseline returns the noisy render while the CV state still advances."""
+    import torch
+    from recursive_control_variates_b200.optimize import run_opt
+    p = _params("cv_pss")
+    scene = p["scene"]
+    meta = mi.load_dict({"type": "meta", "method": "cv_pss", "integrator": p["integrator"],
+                         "adjoint_integrator": p["adjoint_integrator"]})
+    inner = p["integrator"]
+    img0 = meta.render(scene, 0, seed=5, spp=1)
+    F0 = inner.render(scene, 0, 5, 1)
+    assert torch.equal(meta.F, F0) and torch.equal(img0, F0)            # it = 0: w = 0, img = F
+    assert torch.equal(meta.H, inner.render(scene, 0, 6, 1))            # H = current state at the NEXT seed (:117-119)
+    H_prev = meta.H.clone()
+    meta.render(scene, 0, seed=6, spp=1)
+    # unchanged parameters and the same seed: the control (previous state, seed 6) equals the new render exactly
+    assert torch.equal(meta.F, H_prev)
+    # against the oracle's recursion on the same H / F
+    st = {k: np.zeros(tuple(F0.shape), np.float32) for k in ("img", "v_n", "w_s", "mean_x", "mean_y", "var_x", "var_y", "cov")}
+    z = np.zeros(tuple(F0.shape), np.float32)
+    oracle.cv_update(z, F0.cpu().numpy(), st, 0, 1, 0, 0.9, 0.999)
+    oracle.cv_update(H_prev.cpu().numpy(), meta.F.cpu().numpy(), st, 1, 1, 0, 0.9, 0.999)
+    assert np.array_equal(meta.img.cpu().numpy(), st["img"])
+    # force_baseline: same statistics, noisy image returned
+    fb = mi.load_dict({"type": "meta", "method": "cv_ps", "force_baseline": True,
+                       "integrator": _params("cv_ps")["integrator"], "adjoint_integrator": p["adjoint_integrator"]})
+    p2 = _params("cv_ps")
+    out = fb.render(p2["scene"], 0, seed=3, spp=1)
+    assert torch.equal(out, fb.integrator.render(p2["scene"], 0, 3, 1)) and fb.it == 1
+    with pytest.raises(NotImplementedError):
+        mi.load_dict({"type": "meta", "method": "cv_ps", "denoise": True, "integrator": p2["integrator"]})
+    res = run_opt(_params("cv_pss"))
+    assert np.isfinite(res["loss"]).all()

@@ -82,8 +82,12 @@ def test_error_behaviour_matches_reference():
         mi.load_dict({"type": "cv", "integrator": {"type": "volpathsimple"}})
     with pytest.raises(NotImplementedError):
         mi.load_dict({"type": "volpathsimple", "use_drt": True})
+    with pytest.raises(NotImplementedError):  # OptiX denoiser + AOVs: outside the hot path
+        mi.load_dict({"type": "meta", "method": "cv_pss", "denoise": True, "integrator": {"type": "prbvolpath"}})
     with pytest.raises(NotImplementedError):
-        mi.load_dict({"type": "meta", "method": "cv_pss", "integrator": {"type": "prbvolpath"}})
+        mi.load_dict({"type": "meta", "method": "cv_xyz", "integrator": {"type": "prbvolpath"}})
+    pss = mi.load_dict({"type": "meta", "method": "cv_pss", "force_baseline": True, "integrator": {"type": "prbvolpath"}})
+    assert pss.method == "cv_pss" and pss.force_baseline
     with pytest.raises(ValueError):
         mi.load_dict({"type": "scene", "object": {"type": "cube", "bsdf": {"type": "diffuse"}, "interior": {}}})
     integ = mi.load_dict({"type": "twostateprbvolpath"})
