@@ -485,18 +485,27 @@ static inline lane_t lane_setup(const rcv_scene_desc *S, uint32_t seed, uint32_t
     int ix = (int) fx, iy = (int) fy;
     L.pix = (ix >= 0 && ix < (int) W && iy >= 0 && iy < (int) H) ? (int32_t) (iy * (int) W + ix) : -1;
     float sx = pfx * (1.f / (float) W), sy = pfy * (1.f / (float) H);   /* pos_adjusted */
+    const float *A = S->cam_axes, *O = S->cam_origin;
+    if (S->n_sensors > 1) {
+        /* `batch` sensor [UPSTREAM batch.cpp sample_ray]: the view is chosen by the film column and sees
+         * the sample at its own normalised position */
+        float fs = sx * (float) S->n_sensors;
+        uint32_t iu = (uint32_t) fs;
+        uint32_t si = iu < S->n_sensors - 1 ? iu : S->n_sensors - 1;
+        sx = fs - (float) iu;
+        A = S->batch_axes[si]; O = S->batch_origin[si];
+    }
     /* near-plane point in camera space (x to the left, y up, z forward) */
     float nx = fmaf(sx, -2.f * S->cam_tan_x, S->cam_tan_x);
     float ny = fmaf(sy, -2.f * S->cam_tan_y, S->cam_tan_y);
     float len2 = fmaf(nx, nx, fmaf(ny, ny, 1.f));
     float inv = 1.f / sqrtf(len2);
     float dx = nx * inv, dy = ny * inv, dz = inv;
-    const float *A = S->cam_axes;
     v3 d = V3(fmaf(A[0], dx, fmaf(A[1], dy, A[2] * dz)),
               fmaf(A[3], dx, fmaf(A[4], dy, A[5] * dz)),
               fmaf(A[6], dx, fmaf(A[7], dy, A[8] * dz)));
     float near_t = S->cam_near_clip / dz;
-    L.ray.o = ray_at(V3(S->cam_origin[0], S->cam_origin[1], S->cam_origin[2]), d, near_t);
+    L.ray.o = ray_at(V3(O[0], O[1], O[2]), d, near_t);
     L.ray.d = d;
     L.ray.maxt = ORC_LARGEST;
     return L;

@@ -19,6 +19,9 @@ RCV_LOSS_L1, RCV_LOSS_L2 = 0, 1
 RCV_TRACER_WAVEFRONT, RCV_TRACER_SIMPLE, RCV_TRACER_BATCH, RCV_TRACER_POOL = 0, 1, 2, 3
 
 
+RCV_MAX_SENSORS = 16
+
+
 class SceneDesc(C.Structure):
     """struct rcv_scene_desc (include/rcv_b200.h)."""
     _fields_ = [
@@ -42,6 +45,9 @@ class SceneDesc(C.Structure):
         ("rr_depth", C.c_int32),
         ("hide_emitters", C.c_int32),
         ("use_nee", C.c_int32),
+        ("n_sensors", C.c_uint32),
+        ("batch_origin", (C.c_float * 3) * RCV_MAX_SENSORS),
+        ("batch_axes", (C.c_float * 9) * RCV_MAX_SENSORS),
     ]
 
 
@@ -125,7 +131,7 @@ def load_library() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = C.c_int
         fn.argtypes = argtypes
-    if lib.rcv_abi_version() != 1:
+    if lib.rcv_abi_version() != 2:
         raise RcvError("librcv_b200.so ABI version mismatch")
     _lib = lib
     return lib

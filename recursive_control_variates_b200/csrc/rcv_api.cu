@@ -299,6 +299,8 @@ int rcv_scene_set(rcv_ctx *c, const rcv_scene_desc *d) {
     for (int a = 0; a < 3; ++a)
         if (!(d->bbox_max[a] > d->bbox_min[a])) return fail(RCV_ERR_ARG, "degenerate medium bounding box");
     if (d->rr_depth < 0 || d->max_depth < 1) return fail(RCV_ERR_ARG, "rr_depth must be >= 0 and max_depth >= 1");
+    if (d->n_sensors > RCV_MAX_SENSORS) return fail(RCV_ERR_ARG, "too many sensors in the batch (RCV_MAX_SENSORS)");
+    if (d->n_sensors > 1 && d->film_width % d->n_sensors) return fail(RCV_ERR_ARG, "the film width must be a multiple of the number of batched sensors");
     c->desc = *d;
     scene_from_desc(*d, c->S);
     c->has_scene = true;

@@ -55,6 +55,8 @@ struct SceneK {
     float env_over_pdf[3];    // env[c] / (1 / 4 pi): constant.cpp sample_direction value (radiance / pdf)
     float env_dist;
     int max_depth, rr_depth, hide_emitters, use_nee;
+    int n_sensors;            // `batch` sensor: views side by side on the film (<= 1: the single camera above)
+    float batch_o[16 * 3], batch_axes[16 * 9];
 };
 
 // Packed medium state in HBM:
@@ -630,17 +632,24 @@ __device__ __forceinline__ Lane lane_setup(const SceneK &S, uint32_t seed, uint3
     int ix = (int) floorf(pfx), iy = (int) floorf(pfy);
     L.pix = (ix >= 0 && ix < (int) S.W && iy >= 0 && iy < (int) S.H) ? iy * (int) S.W + ix : -1;
     float sx = pfx * S.rcpW, sy = pfy * S.rcpH;
+    const float *A = S.cam_axes, *O = S.cam_o;
+    if (S.n_sensors > 1) {                                 // batch.cpp sample_ray: view by film column
+        float fs = sx * (float) S.n_sensors;
+        uint32_t iu = (uint32_t) fs;
+        int si = (int) (iu < (uint32_t) (S.n_sensors - 1) ? iu : (uint32_t) (S.n_sensors - 1));
+        sx = fs - (float) iu;
+        A = S.batch_axes + 9 * si; O = S.batch_o + 3 * si;
+    }
     float nx = __fmaf_rn(sx, -2.f * S.tan_x, S.tan_x);
     float ny = __fmaf_rn(sy, -2.f * S.tan_y, S.tan_y);
     float len2 = __fmaf_rn(nx, nx, __fmaf_rn(ny, ny, 1.f));
     float inv = 1.f / sqrtf(len2);
     float dx = nx * inv, dy = ny * inv, dz = inv;
-    const float *A = S.cam_axes;
     L.d = mk3(__fmaf_rn(A[0], dx, __fmaf_rn(A[1], dy, A[2] * dz)),
               __fmaf_rn(A[3], dx, __fmaf_rn(A[4], dy, A[5] * dz)),
               __fmaf_rn(A[6], dx, __fmaf_rn(A[7], dy, A[8] * dz)));
     float near_t = S.near_clip / dz;
-    L.o = ray_at(mk3(S.cam_o[0], S.cam_o[1], S.cam_o[2]), L.d, near_t);
+    L.o = ray_at(mk3(O[0], O[1], O[2]), L.d, near_t);
     return L;
 }
 

@@ -18,7 +18,22 @@ from .synthetic import make_medium
 OUTPUT_DIR = os.path.join(os.path.dirname(os.path.dirname(__file__)), "output")
 
 
-def _scene_dict(method, target_res, film, kind, scale=20.0):
+def _batch_sensor(film, views):
+    """The reference's sensor set-up (experiments.py:28-50): `views` perspective cameras on a circle around the
+    medium, side by side on one film of width views * film[0]."""
+    import math
+    sensor = {"type": "batch",
+              "film": {"type": "hdrfilm", "width": film[0] * views, "height": film[1], "rfilter": {"type": "box"}},
+              "sampler": {"type": "independent", "sample_count": 1}}
+    for i in range(views):
+        theta = 2 * math.pi / views * i + 0.1
+        sensor[f"sensor_{i:02d}"] = {"type": "perspective", "fov": 45,
+                                     "to_world": look_at([0.5 + 2 * math.cos(theta), 0.5, 0.5 + 2 * math.sin(theta)],
+                                                         [0.5, 0.5, 0.5], [0, 1, 0])}
+    return sensor
+
+
+def _scene_dict(method, target_res, film, kind, scale=20.0, views=1):
     sig, alb = make_medium(target_res, kind, 0.0)
     medium = {"type": "heterogeneous",
               "sigma_t": {"type": "gridvolume", "data": torch.from_numpy(sig)},
@@ -26,6 +41,9 @@ def _scene_dict(method, target_res, film, kind, scale=20.0):
               "scale": scale, "sample_emitters": True, "has_spectral_extinction": False, "majorant_resolution_factor": 0}
     obj = {"type": "cube", "bsdf": {"type": "null"}}
     obj["interior"] = {"type": "twostatemedium", "old": medium, "new": medium, "incoming": medium} if method == "cv_ps" else medium
+    if views > 1:
+        return {"type": "scene", "object": obj, "emitter": {"type": "constant", "radiance": 1.0},
+                "sensor": _batch_sensor(film, views)}
     return {"type": "scene", "object": obj,
             "emitter": {"type": "constant", "radiance": 1.0},
             "sensor": {"type": "perspective", "fov": 45,
@@ -35,12 +53,13 @@ def _scene_dict(method, target_res, film, kind, scale=20.0):
 
 
 def scene_synthetic(method, output_dir, grid=64, init_grid=16, film=(128, 128), spp=16, kind="cube", n_steps=100,
-                    upsample=(0.16, 0.48), supergrid=False):
+                    upsample=(0.16, 0.48), supergrid=False, views=1):
     """Coarse-to-fine recovery of a synthetic density/albedo cube (C1 of BASELINE.json by default):
     the target is the `grid`^3 medium; optimisation starts from constant init_grid^3 grids and
     doubles the resolution at the `upsample` fractions of the run (experiments.py:99-133).  supergrid = the
-    reference's `use_majorant_supergrid` (experiments.py:114,228): majorant supergrid + DDA free-flight sampling."""
-    scene = mi.load_dict(_scene_dict(method, grid, film, kind))
+    reference's `use_majorant_supergrid` (experiments.py:114,228): majorant supergrid + DDA free-flight sampling;
+    views > 1 = the reference's `batch` sensor with that many cameras around the medium (film = views x `film`)."""
+    scene = mi.load_dict(_scene_dict(method, grid, film, kind, views=views))
     v = init_grid
     dev = "cuda" if torch.cuda.is_available() else "cpu"
     return {
@@ -64,6 +83,12 @@ def scene_synthetic_c1(method, output_dir):
 
 def scene_synthetic_c2(method, output_dir):
     return scene_synthetic(method, output_dir, grid=256, init_grid=32, film=(512, 512), spp=64, upsample=(0.04, 0.16, 0.36))
+
+
+def scene_synthetic_multiview(method, output_dir):
+    # the janga set-up (experiments.py:20-133): 8 views of 256x256 on one film, supergrid, coarse-to-fine
+    return scene_synthetic(method, output_dir, grid=128, init_grid=16, film=(256, 256), spp=16, kind="plume",
+                           upsample=(0.04, 0.16, 0.36), supergrid=True, views=8)
 
 
 def scene_synthetic_plume(method, output_dir):

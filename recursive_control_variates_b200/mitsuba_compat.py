@@ -128,15 +128,28 @@ class Film:
 
 
 class Sensor:
+    """`perspective`, or `batch` of perspective views side by side on one film (experiments.py:28-50)."""
+
     def __init__(self, d: dict):
-        if d.get("type") != "perspective":
-            raise ValueError("only `perspective` sensors are supported (batch sensors: SURVEY.md §8f)")
+        views = None
+        if d.get("type") == "batch":
+            subs = [v for k, v in sorted(d.items()) if isinstance(v, dict) and v.get("type") == "perspective"]
+            if not subs:
+                raise ValueError("batch sensor without perspective sub-sensors")
+            if len({float(v.get("fov", 45.0)) for v in subs}) != 1:
+                raise ValueError("the views of a batch sensor must share one field of view")
+            views = [np.asarray(v["to_world"], dtype=np.float64) for v in subs]
+            d = {**subs[0], "film": d.get("film", {})}
+        elif d.get("type") != "perspective":
+            raise ValueError("only `perspective` and `batch` sensors are supported")
         film = d.get("film", {})
         if film.get("rfilter", {"type": "box"}).get("type", "box") != "box":
             raise ValueError("only the box reconstruction filter is supported (SURVEY.md §8f)")
         self._film = Film(film.get("width", 768), film.get("height", 576))
         self.fov = float(d.get("fov", 45.0))
         self.to_world = np.asarray(d.get("to_world", look_at([0.5, 0.5, -2.0], [0.5, 0.5, 0.5], [0, 1, 0])), dtype=np.float64)
+        if views is not None:
+            self.to_world = np.stack(views)           # (n, 4, 4): SceneConfig lays the views out side by side
         self.near_clip = float(d.get("near_clip", 1e-2))
 
     def film(self) -> Film:
@@ -172,7 +185,7 @@ class Scene:
             t = v.get("type")
             if t in ("cube", "obj", "box"):
                 self._shapes.append(Shape(v)); self.shape_key = key
-            elif t == "perspective":
+            elif t in ("perspective", "batch"):
                 self._sensors.append(Sensor(v))
             elif t == "constant":
                 rad = v.get("radiance", 1.0)

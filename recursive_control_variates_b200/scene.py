@@ -15,7 +15,7 @@ from typing import Sequence
 
 import numpy as np
 
-from ._abi import SceneDesc, RCV_PHASE_ISOTROPIC, RCV_PHASE_HG
+from ._abi import SceneDesc, RCV_MAX_SENSORS, RCV_PHASE_ISOTROPIC, RCV_PHASE_HG
 import ctypes as C
 
 RAY_EPSILON = 1500.0 * 2.0 ** -24  # Mitsuba RayEpsilon (float32)
@@ -60,12 +60,22 @@ class SceneConfig:
         d = SceneDesc()
         d.struct_size = C.sizeof(SceneDesc)
         d.film_width, d.film_height = int(self.width), int(self.height)
-        m = np.asarray(self.to_world, dtype=np.float64)
+        views = np.asarray(self.to_world, dtype=np.float64)
+        batch = views.ndim == 3                       # `batch` sensor: a list of to_world matrices, side by side
+        m = views[0] if batch else views
         d.cam_origin[:] = [float(np.float32(v)) for v in m[:3, 3]]
         axes = m[:3, :3].astype(np.float32)          # columns = left, up, forward
         d.cam_axes[:] = [float(v) for v in axes.reshape(-1)]
+        n_views = len(views) if batch else 1
+        if batch:
+            if n_views > RCV_MAX_SENSORS or self.width % n_views:
+                raise ValueError("batch sensor: at most 16 views and a film width divisible by their number")
+            d.n_sensors = n_views
+            for k, mk in enumerate(views):
+                d.batch_origin[k][:] = [float(np.float32(v)) for v in mk[:3, 3]]
+                d.batch_axes[k][:] = [float(v) for v in mk[:3, :3].astype(np.float32).reshape(-1)]
         tan_x = math.tan(math.radians(self.fov) * 0.5)
-        aspect = self.width / self.height
+        aspect = (self.width / n_views) / self.height
         d.cam_tan_x = float(np.float32(tan_x))
         d.cam_tan_y = float(np.float32(tan_x / aspect))
         d.cam_near_clip = float(np.float32(self.near_clip))

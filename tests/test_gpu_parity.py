@@ -398,3 +398,36 @@ def test_majorant_factor_errors(gpu_ctx):
     with pytest.raises(RcvError):                # a rotation to a grid the factor does not divide is refused
         gpu_set_states(gpu_ctx, media(10)[0], media(10)[1])
     gpu_ctx.set_majorant_factor(0)
+
+
+@pytest.mark.parametrize("tracer", [1, 3])
+def test_batch_sensor(oracle, gpu_ctx, tracer):
+    """`batch` sensor (experiments.py:28-50): views side by side on one film, per-lane bit-exact against the oracle
+    (two-state render, single-state primal, adjoint)."""
+    import math
+    from recursive_control_variates_b200.scene import SceneConfig, look_at
+    from recursive_control_variates_b200._abi import RcvError
+    views = [look_at([0.5 + 2.5 * math.cos(t), 0.6, 0.5 + 2.5 * math.sin(t)], [0.5, 0.5, 0.5], [0, 1, 0]) for t in (0.1, 1.7, 3.9, 5.0)]
+    cfg = SceneConfig(width=4 * 20, height=18, to_world=np.stack(views), max_depth=8, rr_depth=4)
+    d = cfg.to_desc()
+    old, new = media(12)
+    mo, mn = oracle.OracleMedium(d, *old), oracle.OracleMedium(d, *new)
+    gpu_ctx.set_tracer(tracer)
+    gpu_ctx.set_scene(d)
+    gpu_set_states(gpu_ctx, old, new)
+    ao, an = oracle.render_twostates_accum(d, mo, mn, seed=51, spp=1)
+    go, gn = gpu_ctx.render_twostates_accum(seed=51, spp=1)
+    assert np.array_equal(go.cpu().numpy(), ao) and np.array_equal(gn.cpu().numpy(), an)
+    # the four sub-films are different views: their images differ
+    sub = [an[:, 20 * k:20 * (k + 1), :3] for k in range(4)]
+    assert not np.array_equal(sub[0], sub[1]) and not np.array_equal(sub[2], sub[3])
+    assert np.array_equal(gpu_ctx.render_adjoint_primal_accum(seed=52, spp=1).cpu().numpy(), oracle.vps_render_accum(d, mn, 52, 1))
+    gimg = np.full((d.film_height, d.film_width, 3), 1e-3, np.float32)
+    gs, ga = oracle.vps_backward(d, mn, 53, 2, gimg, threads=1)
+    gpu_ctx.grad_zero(); gpu_ctx.render_backward(53, 2, to_cuda(gimg))
+    ggs, gga = gpu_ctx.grad_read()
+    assert rel_l2(ggs.cpu().numpy(), gs) < GRAD_TOL and rel_l2(gga.cpu().numpy(), ga) < GRAD_TOL
+    bad = cfg.to_desc(); bad.film_width = 81                  # not a multiple of the number of views
+    with pytest.raises(RcvError):
+        gpu_ctx.set_scene(bad)
+    gpu_ctx.set_tracer(3)

@@ -177,3 +177,15 @@ def test_cv_pss_and_force_baseline(mi, oracle):
         mi.load_dict({"type": "meta", "method": "cv_ps", "denoise": True, "integrator": p2["integrator"]})
     res = run_opt(_params("cv_pss"))
     assert np.isfinite(res["loss"]).all()
+
+
+def test_run_opt_loop_multiview(mi):
+    """The reference's sensor set-up: a `batch` of views on one film (experiments.py:28-50) through the whole loop."""
+    import torch
+    from recursive_control_variates_b200.optimize import run_opt
+    p = _params("cv_ps", views=3)
+    scene = p["scene"]
+    assert scene.sensors()[0].film().size() == (96, 24) and scene.sensors()[0].to_world.shape == (3, 4, 4)
+    res = run_opt(p)
+    s = res["opt"]["object.interior_medium.sigma_t.data"]
+    assert torch.isfinite(s).all() and np.isfinite(res["loss"]).all() and float((s - 0.04).abs().max()) > 0

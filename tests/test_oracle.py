@@ -260,3 +260,24 @@ def test_supergrid_is_unbiased(oracle):
         gs, ga = grad_sums(mn)
         assert abs(gs - gs0) < 0.08 * abs(gs0)
         assert abs(ga - ga0) < 0.01 * abs(ga0)
+
+
+def test_batch_sensor_views(oracle):
+    """`batch` sensor (experiments.py:28-50): n views side by side on one film; each sub-film shows what the single
+    camera of that view renders (same expectation; the lanes differ, so the comparison is statistical)."""
+    from recursive_control_variates_b200.scene import SceneConfig, look_at
+    views = [look_at([0.5 + 2.5 * math.cos(t), 0.6, 0.5 + 2.5 * math.sin(t)], [0.5, 0.5, 0.5], [0, 1, 0]) for t in (0.1, 1.7, 3.9)]
+    old, new = media(12)
+    cfg = SceneConfig(width=3 * 24, height=20, to_world=np.stack(views), max_depth=8, rr_depth=4)
+    d = cfg.to_desc()
+    assert d.n_sensors == 3
+    mo, mn = oracle.OracleMedium(d, *old), oracle.OracleMedium(d, *new)
+    H, F = oracle.render_twostates(d, mo, mn, seed=2, spp=256)
+    for k, v in enumerate(views):
+        ds = SceneConfig(width=24, height=20, to_world=v, max_depth=8, rr_depth=4).to_desc()
+        assert ds.cam_tan_y == d.cam_tan_y                                   # aspect of the sub-film
+        Hs, Fs = oracle.render_twostates(ds, oracle.OracleMedium(ds, *old), oracle.OracleMedium(ds, *new), seed=3, spp=256)
+        sub = F[:, 24 * k:24 * (k + 1)]
+        assert rel_l2(sub, Fs) < 0.05 and abs(sub.mean() - Fs.mean()) < 5e-3 * Fs.mean()
+    with pytest.raises(ValueError):
+        SceneConfig(width=70, height=20, to_world=np.stack(views)).to_desc()  # 70 % 3 != 0
