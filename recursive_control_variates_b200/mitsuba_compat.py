@@ -52,7 +52,7 @@ def _as_tensor(data, channels: int) -> torch.Tensor:
 
 
 class GridVolume:
-    """`gridvolume` with an in-memory tensor (Z, Y, X, C) (experiments.py:104-112)."""
+    """`gridvolume` from an in-memory tensor (Z, Y, X, C) (experiments.py:104-112), a constant, or a `.vol` file."""
 
     def __init__(self, props: Properties, channels: int):
         if "data" in props:
@@ -60,8 +60,14 @@ class GridVolume:
         elif "value" in props:
             res = props.get("resolution", (16, 16, 16))
             self.data = torch.full((*res, channels), float(props["value"]), dtype=torch.float32)
+        elif "filename" in props:                       # Mitsuba .vol grid (experiments.py:56,62)
+            from .volio import read_vol
+            data, _, _ = read_vol(props["filename"])
+            if data.shape[-1] != channels:
+                raise ValueError(f"{props['filename']}: {data.shape[-1]} channels, expected {channels}")
+            self.data = _as_tensor(data, channels)
         else:
-            raise ValueError("gridvolume needs `data` (tensor) or `value`: volume files are not supported")
+            raise ValueError("gridvolume needs `data` (tensor), `value` or `filename` (.vol)")
 
 
 class HeterogeneousMedium:

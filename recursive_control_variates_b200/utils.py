@@ -135,7 +135,21 @@ def upsample(scene, params, opt, integrator):
 
 
 def save_final_state(params, opt, output_dir):
-    """utils.py:45-60; .npz instead of .vol / .exr."""
+    """utils.py:45-60: 4-D grids as Mitsuba `.vol` files (mi.VolumeGrid.write), everything else into
+    final_state.json; 3-D textures (EXR upstream) go to `.npy`."""
+    import json
+    from .volio import write_vol
     os.makedirs(output_dir, exist_ok=True)
-    np.savez(os.path.join(output_dir, "final_state.npz"),
-             **{k.replace(".", "_"): opt[k].detach().cpu().numpy() for k in params["variables"]})
+    final_state = {}
+    for key in params["variables"]:
+        param = opt[key].detach().cpu()
+        name = key.replace(".", "_")
+        if param.dim() == 4:
+            write_vol(os.path.join(output_dir, f"{name}_final.vol"), param)
+        elif param.dim() == 3:
+            np.save(os.path.join(output_dir, f"{name}_final.npy"), param.numpy())
+        else:
+            final_state[key] = param.numpy().tolist()
+    if final_state:
+        with open(os.path.join(output_dir, "final_state.json"), "w") as f:
+            json.dump(final_state, f)

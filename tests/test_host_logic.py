@@ -126,3 +126,34 @@ def test_adam_bookkeeping():
     assert opt.t["a"] == 0 and opt.state["a"][0].shape == (4, 4, 4, 1)
     opt.set_learning_rate(0.005)
     assert opt.learning_rate("a") == 0.005
+
+
+def test_vol_files_round_trip(tmp_path):
+    """Mitsuba .vol grids (utils.py:45-60 save_final_state; experiments.py:56 gridvolume filename)."""
+    import struct
+    import torch
+    from recursive_control_variates_b200.volio import read_vol, write_vol
+    from recursive_control_variates_b200.utils import save_final_state
+    rng = np.random.default_rng(0)
+    g = rng.random((3, 4, 5, 3), dtype=np.float32)
+    path = str(tmp_path / "a.vol")
+    write_vol(path, g, (0, 0, 0), (1.0, 1.2, 1.5))
+    raw = open(path, "rb").read()
+    assert raw[:4] == b"VOL\x03" and struct.unpack("<iiiii", raw[4:24]) == (1, 5, 4, 3, 3)       # encoding, x, y, z, channels
+    assert struct.unpack("<6f", raw[24:48])[3:] == pytest.approx((1.0, 1.2, 1.5))
+    assert struct.unpack("<f", raw[48:52])[0] == g[0, 0, 0, 0] and len(raw) == 48 + g.size * 4
+    back, bmin, bmax = read_vol(path)
+    assert np.array_equal(back, g) and bmin == (0.0, 0.0, 0.0) and bmax == pytest.approx((1.0, 1.2, 1.5))
+    vol = mi.GridVolume(mi.Properties({"filename": path}), 3)
+    assert torch.equal(vol.data, torch.from_numpy(g))
+    with pytest.raises(ValueError):
+        mi.GridVolume(mi.Properties({"filename": path}), 1)              # channel mismatch
+    open(str(tmp_path / "bad.vol"), "wb").write(raw[:100])
+    with pytest.raises(ValueError):
+        read_vol(str(tmp_path / "bad.vol"))                              # truncated
+    opt = {"m.sigma_t.data": torch.from_numpy(g[..., :1].copy()), "m.scalar": torch.tensor([0.5])}
+    save_final_state({"variables": {k: {} for k in opt}}, opt, str(tmp_path))
+    s, _, _ = read_vol(str(tmp_path / "m_sigma_t_data_final.vol"))
+    assert np.array_equal(s, g[..., :1])
+    import json
+    assert json.load(open(str(tmp_path / "final_state.json"))) == {"m.scalar": [0.5]}
