@@ -226,29 +226,47 @@ def run_ours(a):
     acc = (torch.zeros(H, W, 4, device=dev), torch.zeros(H, W, 4, device=dev))
     Himg, Fimg = torch.zeros(H, W, 3, device=dev), torch.zeros(H, W, 3, device=dev)
     cv = ctx.new_cv_state()
+    film_w = torch.zeros(H, W, device=dev)
     state = {"it": 0, "stats_n": 0, "t": 0}
     npix = W * H
     paths_per_step = npix * a.spp * 3 * n_gpus     # primal + adjoint pass 1 + adjoint pass 2, all ranks
 
-    def step(i):
+    def step(i, marks=None):
+        def mark(name):
+            if marks is not None:
+                e = torch.cuda.Event(enable_timing=True); e.record(); marks.append((name, e))
         seed = SEED0 + i
         seed_grad = tea32(seed, 1)[0]
+        mark("start")
         ctx.rotate(sigma, albedo)                                            # scene_params.update(opt)
+        mark("rotate")
         acc[0].zero_(); acc[1].zero_()
         ctx.render_twostates_accum(seed, spp_total, spp_b, spp_e, out=acc)   # mi.render -> render_twostates
+        mark("twostate_render")
         if world > 1:
             dist.all_reduce(acc[0]); dist.all_reduce(acc[1])
+            mark("allreduce_film")
         ctx.develop(acc[0], Himg); ctx.develop(acc[1], Fimg)
         ctx.cv_update(Himg, Fimg, cv, state["it"], 1, state["stats_n"], 0.9, 0.999)
         state["stats_n"] += state["it"] > 0
         state["it"] += 1
         loss, g = ctx.loss_grad(_abi.RCV_LOSS_L1, cv["img"], ref)           # l1_loss + dr.backward seed
         ctx.grad_zero()
-        ctx.render_backward(seed_grad, spp_total, g, spp_b, spp_e)           # adjoint_integrator.render_backward
+        mark("develop_cv_loss")
+        fw = None
+        if world > 1:                                                        # film weights: own samples, then all-reduce
+            film_w.zero_()
+            fw = ctx.film_weights(seed_grad, spp_total, spp_b, spp_e, out=film_w)
+            dist.all_reduce(fw)
+            mark("film_weights")
+        ctx.render_backward(seed_grad, spp_total, g, spp_b, spp_e, film_w=fw)   # adjoint_integrator.render_backward
+        mark("adjoint")
         if world > 1:
             dist.all_reduce(ctx.grad_packed())
+            mark("allreduce_grad")
         state["t"] += 1
         ctx.adam_step(sigma, albedo, m_s, v_s, m_a, v_a, state["t"], 5e-3, 1e-2)   # opt.step() + clamp
+        mark("adam_clamp")
         return loss
 
     def barrier():
@@ -278,6 +296,16 @@ def run_ours(a):
     ms = float(t.item())
     ms_per_step = ms / a.steps
     value = paths_per_step / (ms_per_step * 1e-3) / 1e6
+
+    # ---- where a step spends its time on this rank (CUDA events between the phases of two extra steps)
+    phases = {}
+    for r in range(2):
+        marks = []
+        step(a.warmup + a.steps + 100 + r, marks)
+        torch.cuda.synchronize()
+        for (_, e_prev), (name, e_cur) in zip(marks[:-1], marks[1:]):
+            phases[name] = phases.get(name, 0.0) + e_prev.elapsed_time(e_cur) / 2
+    barrier()
 
     # ---- per-kernel timing (CUDA events on the launching stream) + roofline of the dominant kernel
     peak, peak_src = measured_peaks()
@@ -366,7 +394,10 @@ def run_ours(a):
 
         def e2e_step(i):
             seed = SEED0 + i
-            d_s.copy_(hs, non_blocking=True); d_a.copy_(ha, non_blocking=True); d_ref.copy_(href, non_blocking=True)
+            # the host-side optimiser lives on rank 0: its buffers go up once and reach the other ranks over NVLink
+            if rank == 0:
+                d_s.copy_(hs, non_blocking=True); d_a.copy_(ha, non_blocking=True); d_ref.copy_(href, non_blocking=True)
+            dist.broadcast(d_s, 0); dist.broadcast(d_a, 0); dist.broadcast(d_ref, 0)
             ctx.rotate(d_s, d_a)
             acc[0].zero_(); acc[1].zero_()
             ctx.render_twostates_accum(seed, spp_total, spp_b, spp_e, out=acc)
@@ -376,11 +407,15 @@ def run_ours(a):
             st2["n"] += st2["it"] > 0; st2["it"] += 1
             l_, g_ = ctx.loss_grad(_abi.RCV_LOSS_L1, cv2["img"], d_ref)
             ctx.grad_zero()
-            ctx.render_backward(tea32(seed, 1)[0], spp_total, g_, spp_b, spp_e)
+            film_w.zero_()
+            fw_ = ctx.film_weights(tea32(seed, 1)[0], spp_total, spp_b, spp_e, out=film_w)
+            dist.all_reduce(fw_)
+            ctx.render_backward(tea32(seed, 1)[0], spp_total, g_, spp_b, spp_e, film_w=fw_)
             dist.all_reduce(ctx.grad_packed())
-            gs_, ga_ = ctx.grad_read()
-            hgs.copy_(gs_, non_blocking=True); hga.copy_(ga_, non_blocking=True)
-            himg.copy_(cv2["img"], non_blocking=True); hloss.copy_(l_.reshape(1), non_blocking=True)
+            if rank == 0:
+                gs_, ga_ = ctx.grad_read()
+                hgs.copy_(gs_, non_blocking=True); hga.copy_(ga_, non_blocking=True)
+                himg.copy_(cv2["img"], non_blocking=True); hloss.copy_(l_.reshape(1), non_blocking=True)
             torch.cuda.synchronize()
 
         e2e_step(0); e2e_step(1)
@@ -396,8 +431,8 @@ def run_ours(a):
         h2d = (hs.numel() + ha.numel() + href.numel()) * 4
         d2h = (himg.numel() + 1 + hgs.numel() + hga.numel()) * 4
         e2e = {"value": paths_per_step / dt / 1e6, "unit": UNIT, "ms_per_step": dt * 1e3, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "api": "Context API per rank with pinned host buffers (bytes are per rank); NCCL "
-               "all-reduce of film accumulators and gradients"}
+               "d2h_bytes_per_step": d2h, "api": "Context API with pinned host buffers on rank 0 (parameters + target up, NCCL broadcast to the "
+               "other ranks; image, loss and all-reduced gradients down from rank 0)"}
     if not a.no_e2e and world == 1:
         pin = lambda t_: t_.detach().cpu().contiguous().pin_memory()
         hs, ha, href = pin(sigma), pin(albedo), pin(ref)
@@ -443,7 +478,7 @@ def run_ours(a):
                           "l2": "inputs larger than L2 (two-state grids %d MiB)" % (a.grid ** 3 * 40 // 2 ** 20),
                           "tracer": {0: "wavefront", 1: "simple", 2: "batch", 3: "pool"}[a.tracer], "loss_last": float(loss.item())},
                "clocks": clocks, "gpu_launches": int(cnt[7]), "roofline": roofline, "kernels": kernels,
-               "e2e": e2e, "cpu_baseline": cpu, "supergrid": supergrid}
+               "phases_ms_rank0": phases, "e2e": e2e, "cpu_baseline": cpu, "supergrid": supergrid}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -98,6 +98,8 @@ _SIGNATURES = {
     "rcv_cv_update": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _u64, _i32, _i32, _i32, _f, _f, _i32],
     "rcv_loss_grad": [_P, C.c_int, _P, _P, _u64, _P, _P],
     "rcv_render_backward": [_P, C.c_int, _u32, _u32, _u32, _u32, _P],
+    "rcv_render_backward_weighted": [_P, C.c_int, _u32, _u32, _u32, _u32, _P, _P],
+    "rcv_film_weights": [_P, _u32, _u32, _u32, _u32, _P],
     "rcv_render_adjoint_primal": [_P, C.c_int, _u32, _u32, _u32, _u32, _P],
     "rcv_grad_zero": [_P],
     "rcv_grad_buffer": [_P, C.POINTER(_P), C.POINTER(_u64)],

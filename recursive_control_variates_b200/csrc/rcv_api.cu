@@ -451,8 +451,21 @@ int rcv_loss_grad(rcv_ctx *c, int kind, const float *img, const float *ref, uint
     return RCV_OK;
 }
 
+int rcv_film_weights(rcv_ctx *c, uint32_t seed, uint32_t spp, uint32_t spp_begin, uint32_t spp_end, float *film_w) {
+    if (int r = use_device(c)) return r;
+    if (!c->has_scene) return fail(RCV_ERR_STATE, "no scene set");
+    if (!film_w || spp == 0 || spp_begin > spp_end || spp_end > spp) return fail(RCV_ERR_ARG, "invalid argument");
+    CK(launch_film_weights(c->cfg(), c->S, seed, spp, spp_begin, spp_end, film_w, false));
+    return RCV_OK;
+}
+
 int rcv_render_backward(rcv_ctx *c, int adjoint_kind, uint32_t seed_grad, uint32_t spp_grad, uint32_t spp_begin, uint32_t spp_end,
                         const float *grad_img) {
+    return rcv_render_backward_weighted(c, adjoint_kind, seed_grad, spp_grad, spp_begin, spp_end, grad_img, nullptr);
+}
+
+int rcv_render_backward_weighted(rcv_ctx *c, int adjoint_kind, uint32_t seed_grad, uint32_t spp_grad, uint32_t spp_begin,
+                                 uint32_t spp_end, const float *grad_img, const float *film_w) {
     if (int r = check_render(c, spp_grad, spp_begin, spp_end)) return r;
     if (adjoint_kind != RCV_ADJOINT_VOLPATHSIMPLE) return fail(RCV_ERR_ARG, "unknown adjoint integrator");
     if (!grad_img) return fail(RCV_ERR_ARG, "null grad_img");
@@ -464,7 +477,10 @@ int rcv_render_backward(rcv_ctx *c, int adjoint_kind, uint32_t seed_grad, uint32
         if (int r = ensure_arena(c)) { c->tracer = saved_tracer; return r; }
     LaunchCfg cfg = c->cfg();
     c->tracer = saved_tracer;
-    CK(launch_film_weights(cfg, c->S, seed_grad, spp_grad, c->film_w));
+    if (!film_w) {       // no weights supplied: those of ALL spp_grad samples are computed here
+        CK(launch_film_weights(cfg, c->S, seed_grad, spp_grad, 0, spp_grad, c->film_w, true));
+        film_w = c->film_w;
+    }
     GradK D = c->gradk();
     const bool pin = c->l2_persist && c->l2_persist_max > 0 && c->l2_window_max > 0;
     if (pin) {
@@ -480,7 +496,7 @@ int rcv_render_backward(rcv_ctx *c, int adjoint_kind, uint32_t seed_grad, uint32
         CK(cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &a));
     }
     CK(launch_vps_backward(cfg, c->S, c->gridk(), D, seed_grad, spp_grad, spp_begin, spp_end, alt_seed_for(seed_grad), grad_img,
-                           c->film_w));
+                           film_w));
     if (pin) {
         cudaStreamAttrValue a{};
         a.accessPolicyWindow.num_bytes = 0;

@@ -29,7 +29,8 @@ cudaError_t launch_vps_backward(const LaunchCfg &cfg, const SceneK &S, const Gri
                                 uint32_t spp_grad, uint32_t spp_begin, uint32_t spp_end, uint32_t alt_seed,
                                 const float *grad_img, const float *film_w);
 size_t vps_backward_slots(const LaunchCfg &cfg);
-cudaError_t launch_film_weights(const LaunchCfg &cfg, const SceneK &S, uint32_t seed, uint32_t spp, float *film_w);
+cudaError_t launch_film_weights(const LaunchCfg &cfg, const SceneK &S, uint32_t seed, uint32_t spp, uint32_t spp_begin,
+                                uint32_t spp_end, float *film_w, bool zero);
 
 // ---- medium state (rcv_pixel.cu)
 cudaError_t launch_rotate(const LaunchCfg &cfg, const float *sigma_in, const float *albedo_in, int nz, int ny, int nx, float scale,

@@ -665,9 +665,10 @@ cudaError_t launch_vps_backward(const LaunchCfg &cfg, const SceneK &S, const Gri
 // draws of every lane): the denominator of hdrfilm.develop, needed by the
 // adjoint to differentiate the weight division.
 __global__ void __launch_bounds__(kBlock) k_film_weights(const __grid_constant__ SceneK S, uint32_t seed, uint32_t spp,
-                                                         uint64_t n_lanes, float *film_w) {
-    uint64_t idx = (uint64_t) blockIdx.x * kBlock + threadIdx.x;
-    if (idx >= n_lanes) return;
+                                                         uint32_t spp_begin, uint32_t ns, uint64_t n_local, float *film_w) {
+    uint64_t j = (uint64_t) blockIdx.x * kBlock + threadIdx.x;
+    if (j >= n_local) return;
+    const uint64_t idx = global_lane(j, spp, spp_begin, ns);
     // only the film position of lane_setup is needed here
     Pcg rng;
     sampler_seed(rng, seed, (uint32_t) idx);
@@ -678,11 +679,17 @@ __global__ void __launch_bounds__(kBlock) k_film_weights(const __grid_constant__
     if (ix >= 0 && ix < (int) S.W && iy >= 0 && iy < (int) S.H) red_add_f32(film_w + (iy * (int) S.W + ix), 1.f);
 }
 
-cudaError_t launch_film_weights(const LaunchCfg &cfg, const SceneK &S, uint32_t seed, uint32_t spp, float *film_w) {
-    uint64_t n = (uint64_t) S.W * S.H * spp;
-    cudaError_t e = cudaMemsetAsync(film_w, 0, (size_t) S.W * S.H * sizeof(float), cfg.stream);
-    if (e != cudaSuccess) return e;
-    k_film_weights<<<(unsigned) ((n + kBlock - 1) / kBlock), kBlock, 0, cfg.stream>>>(S, seed, spp, n, film_w);
+// adds the film weights of samples [spp_begin, spp_end) of every pixel to film_w (zeroed first when `zero`)
+cudaError_t launch_film_weights(const LaunchCfg &cfg, const SceneK &S, uint32_t seed, uint32_t spp, uint32_t spp_begin,
+                                uint32_t spp_end, float *film_w, bool zero) {
+    uint32_t ns = spp_end - spp_begin;
+    uint64_t n = (uint64_t) S.W * S.H * ns;
+    if (zero) {
+        cudaError_t e = cudaMemsetAsync(film_w, 0, (size_t) S.W * S.H * sizeof(float), cfg.stream);
+        if (e != cudaSuccess) return e;
+    }
+    if (n == 0) return cudaSuccess;
+    k_film_weights<<<(unsigned) ((n + kBlock - 1) / kBlock), kBlock, 0, cfg.stream>>>(S, seed, spp, spp_begin, ns, n, film_w);
     (*cfg.launches)++;
     return cudaGetLastError();
 }

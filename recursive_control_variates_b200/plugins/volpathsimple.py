@@ -57,7 +57,11 @@ class VolpathSimpleIntegrator:
         b, e = parallel.shard_spp(spp, rank, world)
         with torch.no_grad():
             ctx.grad_zero()
-            ctx.render_backward(seed, spp, grad_in.contiguous(), b, e)
+            film_w = None
+            if world > 1:        # the film weights of all samples: every rank adds its own, one small all-reduce
+                film_w = ctx.film_weights(seed, spp, b, e)
+                parallel.allreduce_sum_([film_w])
+            ctx.render_backward(seed, spp, grad_in.contiguous(), b, e, film_w=film_w)
             parallel.allreduce_sum_([ctx.grad_packed()])                   # gradient grids before the Adam step
             g_sigma, g_albedo = ctx.grad_read()
         prefix = params.prefix if params is not None else ""

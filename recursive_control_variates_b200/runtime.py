@@ -188,11 +188,24 @@ class Context:
         check(self.lib.rcv_grad_zero(self._h))
 
     def render_backward(self, seed_grad: int, spp_grad: int, grad_img: torch.Tensor, spp_begin: int = 0,
-                        spp_end: Optional[int] = None):
+                        spp_end: Optional[int] = None, film_w: Optional[torch.Tensor] = None):
+        """film_w: (H,W) film weights of ALL spp_grad samples (see film_weights); None = computed inside the call."""
         spp_end = spp_grad if spp_end is None else spp_end
         self._sync_stream()
-        check(self.lib.rcv_render_backward(self._h, _abi.RCV_ADJOINT_VOLPATHSIMPLE, seed_grad & 0xFFFFFFFF, spp_grad,
-                                           spp_begin, spp_end, _ptr(grad_img)))
+        check(self.lib.rcv_render_backward_weighted(self._h, _abi.RCV_ADJOINT_VOLPATHSIMPLE, seed_grad & 0xFFFFFFFF, spp_grad,
+                                                    spp_begin, spp_end, _ptr(grad_img), _ptr(film_w)))
+
+    def film_weights(self, seed: int, spp: int, spp_begin: int = 0, spp_end: Optional[int] = None,
+                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Adds the film weights of samples [spp_begin, spp_end) to `out` (a new zeroed (H,W) buffer by default): the
+        per-rank piece of the weights the adjoint needs; all-reduce it across an spp-sharded job."""
+        spp_end = spp if spp_end is None else spp_end
+        H, W = self.film_shape
+        if out is None:
+            out = self._zeros(H, W)
+        self._sync_stream()
+        check(self.lib.rcv_film_weights(self._h, seed & 0xFFFFFFFF, spp, spp_begin, spp_end, _ptr(out)))
+        return out
 
     def grad_packed(self) -> torch.Tensor:
         """Flat view of the library's gradient grids (d sigma_t, d albedo) for an in-place all-reduce."""

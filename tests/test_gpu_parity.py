@@ -431,3 +431,23 @@ def test_batch_sensor(oracle, gpu_ctx, tracer):
     with pytest.raises(RcvError):
         gpu_ctx.set_scene(bad)
     gpu_ctx.set_tracer(3)
+
+
+def test_sharded_film_weights(gpu_ctx, setup):
+    """rcv_film_weights / rcv_render_backward_weighted: the weights of disjoint sample ranges add up to the weights of
+    all samples, and the adjoint with supplied weights equals the adjoint that computes them itself."""
+    import torch
+    d = setup["desc"]
+    gpu_ctx.set_scene(d)
+    gpu_set_states(gpu_ctx, setup["old"], setup["new"])
+    seed, spp = 77, 6
+    w_all = gpu_ctx.film_weights(seed, spp)
+    w_parts = gpu_ctx.film_weights(seed, spp, 0, 2)
+    gpu_ctx.film_weights(seed, spp, 2, 6, out=w_parts)
+    assert torch.equal(w_all, w_parts) and abs(float(w_all.sum()) - d.film_width * d.film_height * spp) < 1
+    gimg = to_cuda(np.full((d.film_height, d.film_width, 3), 1e-3, np.float32))
+    gpu_ctx.grad_zero(); gpu_ctx.render_backward(seed, spp, gimg, 1, 4)
+    a_s, a_a = gpu_ctx.grad_read()
+    gpu_ctx.grad_zero(); gpu_ctx.render_backward(seed, spp, gimg, 1, 4, film_w=w_all)
+    b_s, b_a = gpu_ctx.grad_read()
+    assert rel_l2(b_s.cpu().numpy(), a_s.cpu().numpy()) < 1e-5 and rel_l2(b_a.cpu().numpy(), a_a.cpu().numpy()) < 1e-5
