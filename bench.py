@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--tracer", type=int, default=3, help="3 pool (default), 0 wavefront, 1 simple, 2 batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--rfilter", default="box", choices=["box", "gaussian"], help="reconstruction filter of the film (headline: box)")
     ap.add_argument("--supergrid", type=int, default=8,
                     help="also time the same iteration with a majorant supergrid of this factor (0 = skip); reported under `supergrid`")
     ap.add_argument("--cpu-sample-spp", type=int, default=0, help="spp range of the CPU sample (0 = auto: ~15 s of CPU work)")
@@ -209,7 +210,7 @@ def run_ours(a):
     W = H = a.res
     spp_total = a.spp * n_gpus
     spp_b, spp_e = rank * a.spp, (rank + 1) * a.spp
-    desc = SceneConfig(width=W, height=H).to_desc()
+    desc = SceneConfig(width=W, height=H, rfilter=a.rfilter).to_desc()
     ctx = Context(local)
     ctx.set_scene(desc)
     ctx.set_tracer(a.tracer)
@@ -476,7 +477,7 @@ def run_ours(a):
                "config": {"workload": workload_name(a, n_gpus), "grid": a.grid, "film": [W, H], "spp_total": spp_total,
                           "spp_per_gpu": a.spp, "paths_per_step": paths_per_step, "parallelism": f"spp-shard x{n_gpus}",
                           "l2": "inputs larger than L2 (two-state grids %d MiB)" % (a.grid ** 3 * 40 // 2 ** 20),
-                          "tracer": {0: "wavefront", 1: "simple", 2: "batch", 3: "pool"}[a.tracer], "loss_last": float(loss.item())},
+                          "tracer": {0: "wavefront", 1: "simple", 2: "batch", 3: "pool"}[a.tracer], "rfilter": a.rfilter, "loss_last": float(loss.item())},
                "clocks": clocks, "gpu_launches": int(cnt[7]), "roofline": roofline, "kernels": kernels,
                "phases_ms_rank0": phases, "e2e": e2e, "cpu_baseline": cpu, "supergrid": supergrid}
         print(json.dumps(out))

@@ -156,6 +156,26 @@ float orc_logf(float x) {
     return r;
 }
 
+/* Cephes expf for x <= 0 of moderate size (reconstruction-filter weights), fixed operation order */
+float orc_expf(float x) {
+    float z = floorf(fmaf(1.44269504088896341f, x, 0.5f));      /* n = round(x / ln 2) */
+    x = fmaf(z, -0.693359375f, x);
+    x = fmaf(z, 2.12194440e-4f, x);
+    int n = (int) z;
+    float xx = x * x;
+    float y = 1.9875691500e-4f;
+    y = fmaf(y, x, 1.3981999507e-3f);
+    y = fmaf(y, x, 8.3334519073e-3f);
+    y = fmaf(y, x, 4.1665795894e-2f);
+    y = fmaf(y, x, 1.6666665459e-1f);
+    y = fmaf(y, x, 5.0000001201e-1f);
+    y = fmaf(y, xx, x);
+    y = y + 1.f;
+    if (n < -126) return 0.f;
+    union { float f; uint32_t u; } s2; s2.u = (uint32_t) (n + 127) << 23;   /* 2^n */
+    return y * s2.f;
+}
+
 void orc_sincosf(float x, float *s_out, float *c_out) {
     /* x >= 0 (x = 2*pi*u).  Cephes sinf/cosf with 3-term Cody-Waite reduction. */
     int j = (int) (x * 1.27323954473516f);   /* x * 4/pi */
@@ -470,7 +490,40 @@ static void counters_merge(const counters_t *c) {
 /* ------------------------------------------------------------------------- */
 /* sensor: ADIntegrator.sample_rays + perspective.sample_ray  [UPSTREAM]      */
 /* ------------------------------------------------------------------------- */
-typedef struct { pcg32 rng; ray_t ray; int32_t pix; } lane_t;
+typedef struct { pcg32 rng; ray_t ray; int32_t pix; float fx, fy; } lane_t;   /* (fx, fy): film position in pixels */
+
+/* ImageBlock.put [UPSTREAM imageblock.cpp]: the pixels a sample at film position (fx, fy) is splatted to and the
+ * reconstruction-filter weights.  Box: the pixel that contains the sample, weight 1.  Gaussian (gaussian.cpp, the
+ * hdrfilm default): radius r = 4 stddev, per-axis weight max(0, exp(a x^2) - exp(a r^2)), a = -1 / (2 stddev^2), at the
+ * pixel centres within the radius (2 ceil(r) <= 4 per axis); weights are not normalised, develop() divides. */
+typedef struct { int n; int32_t pix[16]; float w[16]; } footprint_t;
+static inline void film_footprint(const rcv_scene_desc *S, float fx, float fy, footprint_t *fp) {
+    int W = (int) S->film_width, H = (int) S->film_height;
+    fp->n = 0;
+    if (S->rfilter_type != RCV_RFILTER_GAUSSIAN) {
+        int ix = (int) floorf(fx), iy = (int) floorf(fy);
+        if (ix >= 0 && ix < W && iy >= 0 && iy < H) { fp->pix[0] = iy * W + ix; fp->w[0] = 1.f; fp->n = 1; }
+        return;
+    }
+    float sd = S->rfilter_stddev, r = 4.f * sd;
+    float alpha = -1.f / ((2.f * sd) * sd);
+    float bias = orc_expf(alpha * (r * r));
+    int count = 2 * (int) ceilf(r);
+    float px = fx - 0.5f, py = fy - 0.5f;                      /* pixel centres sit at integer + 0.5 */
+    int lox = (int) ceilf(px - r), loy = (int) ceilf(py - r);
+    float wx[4], wy[4];
+    for (int i = 0; i < count; ++i) {
+        float dx = (float) (lox + i) - px, dy = (float) (loy + i) - py;
+        wx[i] = fmaxf_(0.f, orc_expf(alpha * (dx * dx)) - bias);
+        wy[i] = fmaxf_(0.f, orc_expf(alpha * (dy * dy)) - bias);
+    }
+    for (int j = 0; j < count; ++j)
+        for (int i = 0; i < count; ++i) {
+            int x = lox + i, y = loy + j;
+            if (x < 0 || x >= W || y < 0 || y >= H) continue;
+            fp->pix[fp->n] = y * W + x; fp->w[fp->n] = wy[j] * wx[i]; fp->n++;
+        }
+}
 
 static inline lane_t lane_setup(const rcv_scene_desc *S, uint32_t seed, uint32_t spp, uint64_t idx) {
     lane_t L;
@@ -484,6 +537,7 @@ static inline lane_t lane_setup(const rcv_scene_desc *S, uint32_t seed, uint32_t
     float fx = floorf(pfx), fy = floorf(pfy);
     int ix = (int) fx, iy = (int) fy;
     L.pix = (ix >= 0 && ix < (int) W && iy >= 0 && iy < (int) H) ? (int32_t) (iy * (int) W + ix) : -1;
+    L.fx = pfx; L.fy = pfy;
     float sx = pfx * (1.f / (float) W), sy = pfy * (1.f / (float) H);   /* pos_adjusted */
     const float *A = S->cam_axes, *O = S->cam_origin;
     if (S->n_sensors > 1) {
@@ -894,7 +948,7 @@ int orc_render_twostates(const rcv_scene_desc *S, const orc_medium *Mo, const or
     const uint64_t chunk = 1u << 16;
     float *Lo = (float *) malloc(chunk * ns * 3 * sizeof(float));
     float *Ln = (float *) malloc(chunk * ns * 3 * sizeof(float));
-    int32_t *px = (int32_t *) malloc(chunk * ns * sizeof(int32_t));
+    float *px = (float *) malloc(chunk * ns * 2 * sizeof(float));     /* film positions */
     if (!Lo || !Ln || !px) return 1;
     if (nthreads < 1) nthreads = 1;
     for (uint64_t p0 = 0; p0 < npix; p0 += chunk) {
@@ -910,7 +964,7 @@ int orc_render_twostates(const rcv_scene_desc *S, const orc_medium *Mo, const or
                     lane_t ln = lane_setup(S, seed, spp, idx);
                     int valid;
                     sample_twostates(S, Mo, Mn, &ln.rng, ln.ray, Lo + 3 * o, Ln + 3 * o, &valid, &cnt);
-                    px[o] = ln.pix;
+                    px[2 * o] = ln.fx; px[2 * o + 1] = ln.fy;
                     cnt.c[6]++;
                 }
             }
@@ -918,10 +972,13 @@ int orc_render_twostates(const rcv_scene_desc *S, const orc_medium *Mo, const or
         }
         size_t n = (size_t) (p1 - p0) * ns;
         for (size_t o = 0; o < n; ++o) {            /* serial splat: deterministic summation order */
-            if (px[o] < 0) continue;
-            float *ao = accum_old + 4 * (size_t) px[o], *an = accum_new + 4 * (size_t) px[o];
-            ao[0] += Lo[3 * o]; ao[1] += Lo[3 * o + 1]; ao[2] += Lo[3 * o + 2]; ao[3] += 1.f;
-            an[0] += Ln[3 * o]; an[1] += Ln[3 * o + 1]; an[2] += Ln[3 * o + 2]; an[3] += 1.f;
+            footprint_t fp; film_footprint(S, px[2 * o], px[2 * o + 1], &fp);
+            for (int q = 0; q < fp.n; ++q) {
+                float *ao = accum_old + 4 * (size_t) fp.pix[q], *an = accum_new + 4 * (size_t) fp.pix[q];
+                float w = fp.w[q];
+                ao[0] += Lo[3 * o] * w; ao[1] += Lo[3 * o + 1] * w; ao[2] += Lo[3 * o + 2] * w; ao[3] += w;
+                an[0] += Ln[3 * o] * w; an[1] += Ln[3 * o + 1] * w; an[2] += Ln[3 * o + 2] * w; an[3] += w;
+            }
         }
     }
     free(Lo); free(Ln); free(px);
@@ -944,7 +1001,8 @@ void orc_film_weights(const rcv_scene_desc *S, uint32_t seed, uint32_t spp, floa
     memset(Wt, 0, npix * sizeof(float));
     for (uint64_t idx = 0; idx < npix * spp; ++idx) {
         lane_t ln = lane_setup(S, seed, spp, idx);
-        if (ln.pix >= 0) Wt[ln.pix] += 1.f;
+        footprint_t fp; film_footprint(S, ln.fx, ln.fy, &fp);
+        for (int q = 0; q < fp.n; ++q) Wt[fp.pix[q]] += fp.w[q];
     }
 }
 
@@ -1368,7 +1426,7 @@ int orc_vps_render(const rcv_scene_desc *S, const orc_medium *M, uint32_t seed, 
     uint64_t npix = (uint64_t) S->film_width * S->film_height;
     uint32_t ns = spp_end - spp_begin;
     float *L = (float *) malloc((size_t) ns * 3 * sizeof(float) * 4096);
-    int32_t *px = (int32_t *) malloc((size_t) ns * sizeof(int32_t) * 4096);
+    float *px = (float *) malloc((size_t) ns * 2 * sizeof(float) * 4096);
     if (!L || !px) return 1;
     if (nthreads < 1) nthreads = 1;
     for (uint64_t p0 = 0; p0 < npix; p0 += 4096) {
@@ -1382,16 +1440,19 @@ int orc_vps_render(const rcv_scene_desc *S, const orc_medium *M, uint32_t seed, 
                     size_t o = (size_t) (p - (int64_t) p0) * ns + (k - spp_begin);
                     lane_t ln = lane_setup(S, seed, spp, (uint64_t) p * spp + k);
                     vps_sample(S, M, 1, &ln.rng, NULL, ln.ray, V3(0, 0, 0), V3(0, 0, 0), L + 3 * o, NULL, &cnt);
-                    px[o] = ln.pix;
+                    px[2 * o] = ln.fx; px[2 * o + 1] = ln.fy;
                     cnt.c[6]++;
                 }
             counters_merge(&cnt);
         }
         size_t n = (size_t) (p1 - p0) * ns;
         for (size_t o = 0; o < n; ++o) {
-            if (px[o] < 0) continue;
-            float *a = accum + 4 * (size_t) px[o];
-            a[0] += L[3 * o]; a[1] += L[3 * o + 1]; a[2] += L[3 * o + 2]; a[3] += 1.f;
+            footprint_t fp; film_footprint(S, px[2 * o], px[2 * o + 1], &fp);
+            for (int q = 0; q < fp.n; ++q) {
+                float *a = accum + 4 * (size_t) fp.pix[q];
+                float w = fp.w[q];
+                a[0] += L[3 * o] * w; a[1] += L[3 * o + 1] * w; a[2] += L[3 * o + 2] * w; a[3] += w;
+            }
         }
     }
     free(L); free(px);
@@ -1399,8 +1460,8 @@ int orc_vps_render(const rcv_scene_desc *S, const orc_medium *M, uint32_t seed, 
 }
 
 /* RBIntegrator.render_backward [UPSTREAM common.py] driving volpathsimple:
- * pass 1 traces L per lane; dL = d(develop o put)/dL * grad_in = grad_in[pix] / W[pix]
- * for the box filter; pass 2 replays the identical stream and scatters gradients. */
+ * pass 1 traces L per lane; dL = d(develop o put)/dL * grad_in = sum_p w_p grad_in[p] / W[p] over the
+ * sample's filter footprint (one pixel, weight 1, for the box filter); pass 2 replays the identical stream and scatters gradients. */
 int orc_vps_backward(const rcv_scene_desc *S, const orc_medium *M, uint32_t seed_grad, uint32_t spp_grad,
                      uint32_t spp_begin, uint32_t spp_end, const float *grad_img, const float *film_w,
                      double *grad_sigma_t, double *grad_albedo, int nthreads) {
@@ -1419,11 +1480,16 @@ int orc_vps_backward(const rcv_scene_desc *S, const orc_medium *M, uint32_t seed
                 pcg32 rng1 = ln.rng;                       /* sampler.clone() for pass 1 */
                 float L[3];
                 vps_sample(S, M, 1, &rng1, NULL, ln.ray, V3(0, 0, 0), V3(0, 0, 0), L, NULL, &cnt);
+                /* dL = sum over the footprint of w * grad_in[p] / W[p] */
                 v3 dL = V3(0, 0, 0);
-                if (ln.pix >= 0) {
-                    float w = film_w[ln.pix];
+                footprint_t fp; film_footprint(S, ln.fx, ln.fy, &fp);
+                for (int q = 0; q < fp.n; ++q) {
+                    int pq = fp.pix[q];
+                    float w = film_w[pq];
                     float d = (w == 0.f) ? 1.f : w;
-                    dL = V3(grad_img[3 * ln.pix] / d, grad_img[3 * ln.pix + 1] / d, grad_img[3 * ln.pix + 2] / d);
+                    dL.x += fp.w[q] * (grad_img[3 * pq] / d);
+                    dL.y += fp.w[q] * (grad_img[3 * pq + 1] / d);
+                    dL.z += fp.w[q] * (grad_img[3 * pq + 2] / d);
                 }
                 pcg32 alt; sampler_seed(&alt, alt_seed, (uint32_t) idx);       /* volpathsimple.py:119-120 */
                 float L2[3];

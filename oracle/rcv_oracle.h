@@ -28,6 +28,7 @@ void orc_tea32(uint32_t v0, uint32_t v1, uint32_t *o0, uint32_t *o1);
 void orc_pcg32_kat(uint64_t initstate, uint64_t initseq, uint32_t *out, int n);
 float orc_u32_to_f32(uint32_t v);
 float orc_logf(float x);
+float orc_expf(float x);
 void orc_sincosf(float x, float *s, float *c);
 float orc_majorant(const rcv_scene_desc *S, const float *sigma_t, size_t n);
 /* local majorants of a (nz,ny,nx) grid on a supergrid with cells of `factor` voxels; out: (nz/f, ny/f, nx/f); -1 if not divisible */

@@ -20,6 +20,7 @@ RCV_TRACER_WAVEFRONT, RCV_TRACER_SIMPLE, RCV_TRACER_BATCH, RCV_TRACER_POOL = 0, 
 
 
 RCV_MAX_SENSORS = 16
+RCV_RFILTER_BOX, RCV_RFILTER_GAUSSIAN = 0, 1
 
 
 class SceneDesc(C.Structure):
@@ -48,6 +49,8 @@ class SceneDesc(C.Structure):
         ("n_sensors", C.c_uint32),
         ("batch_origin", (C.c_float * 3) * RCV_MAX_SENSORS),
         ("batch_axes", (C.c_float * 9) * RCV_MAX_SENSORS),
+        ("rfilter_type", C.c_int32),
+        ("rfilter_stddev", C.c_float),
     ]
 
 
@@ -133,7 +136,7 @@ def load_library() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = C.c_int
         fn.argtypes = argtypes
-    if lib.rcv_abi_version() != 2:
+    if lib.rcv_abi_version() != 3:
         raise RcvError("librcv_b200.so ABI version mismatch")
     _lib = lib
     return lib

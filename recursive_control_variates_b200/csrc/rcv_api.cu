@@ -66,7 +66,7 @@ struct rcv_ctx {
     uint64_t launches = 0;
     float *film_w = nullptr;
     size_t film_w_pix = 0;
-    PathQueue queue{nullptr, nullptr, nullptr, nullptr};
+    PathQueue queue{nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t queue_cap = 0;
     float4 *arena = nullptr;      // vertex records of the adjoint: slots x (max_depth + 1) x 64 B
     size_t arena_records = 0;
@@ -171,11 +171,12 @@ int ensure_queue(rcv_ctx *c, uint32_t spp_begin, uint32_t spp_end) {
     size_t n = (size_t) c->S.W * c->S.H * (spp_end - spp_begin);
     if (!c->queue.count) CK(cudaMalloc(&c->queue.count, sizeof(unsigned long long)));
     if (n > c->queue_cap) {
-        cudaFree(c->queue.r0); cudaFree(c->queue.r1); cudaFree(c->queue.r2);
-        c->queue.r0 = c->queue.r1 = c->queue.r2 = nullptr; c->queue_cap = 0;
+        cudaFree(c->queue.r0); cudaFree(c->queue.r1); cudaFree(c->queue.r2); cudaFree(c->queue.r3);
+        c->queue.r0 = c->queue.r1 = c->queue.r2 = c->queue.r3 = nullptr; c->queue_cap = 0;
         CK(cudaMalloc(&c->queue.r0, n * sizeof(float4)));
         CK(cudaMalloc(&c->queue.r1, n * sizeof(float4)));
         CK(cudaMalloc(&c->queue.r2, n * sizeof(float4)));
+        CK(cudaMalloc(&c->queue.r3, n * sizeof(float4)));
         c->queue_cap = n;
     }
     return RCV_OK;
@@ -271,7 +272,7 @@ int rcv_ctx_destroy(rcv_ctx *c) {
     cudaSetDevice(c->device);
     free_medium(c);
     cudaFree(c->counters); cudaFree(c->work); cudaFree(c->majorants); cudaFree(c->film_w); cudaFree(c->loss_partial);
-    cudaFree(c->queue.r0); cudaFree(c->queue.r1); cudaFree(c->queue.r2); cudaFree(c->queue.count); cudaFree(c->arena); cudaFree(c->mgrid);
+    cudaFree(c->queue.r0); cudaFree(c->queue.r1); cudaFree(c->queue.r2); cudaFree(c->queue.r3); cudaFree(c->queue.count); cudaFree(c->arena); cudaFree(c->mgrid);
     auto &E = c->e2e;
     cudaFree(E.sigma); cudaFree(E.albedo); cudaFree(E.ref); cudaFree(E.acc); cudaFree(E.HF); cudaFree(E.cv);
     cudaFree(E.grad_img); cudaFree(E.loss); cudaFree(E.g_sigma); cudaFree(E.g_albedo);
@@ -299,6 +300,9 @@ int rcv_scene_set(rcv_ctx *c, const rcv_scene_desc *d) {
     for (int a = 0; a < 3; ++a)
         if (!(d->bbox_max[a] > d->bbox_min[a])) return fail(RCV_ERR_ARG, "degenerate medium bounding box");
     if (d->rr_depth < 0 || d->max_depth < 1) return fail(RCV_ERR_ARG, "rr_depth must be >= 0 and max_depth >= 1");
+    if (d->rfilter_type != RCV_RFILTER_BOX && d->rfilter_type != RCV_RFILTER_GAUSSIAN) return fail(RCV_ERR_ARG, "unknown reconstruction filter");
+    if (d->rfilter_type == RCV_RFILTER_GAUSSIAN && !(d->rfilter_stddev > 0.f && d->rfilter_stddev <= 0.5f))
+        return fail(RCV_ERR_ARG, "gaussian reconstruction filter: 0 < stddev <= 0.5");
     if (d->n_sensors > RCV_MAX_SENSORS) return fail(RCV_ERR_ARG, "too many sensors in the batch (RCV_MAX_SENSORS)");
     if (d->n_sensors > 1 && d->film_width % d->n_sensors) return fail(RCV_ERR_ARG, "the film width must be a multiple of the number of batched sensors");
     c->desc = *d;

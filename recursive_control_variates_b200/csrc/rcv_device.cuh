@@ -31,6 +31,9 @@ static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); re
 static inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
+#ifndef __noinline__
+#define __noinline__ __attribute__((noinline))
+#endif
 using std::isfinite; using std::isnan; using std::isinf; using std::max; using std::min;
 #endif
 #endif
@@ -57,6 +60,8 @@ struct SceneK {
     int max_depth, rr_depth, hide_emitters, use_nee;
     int n_sensors;            // `batch` sensor: views side by side on the film (<= 1: the single camera above)
     float batch_o[16 * 3], batch_axes[16 * 9];
+    int rfilter;              // RCV_RFILTER_*
+    float rf_stddev;
 };
 
 // Packed medium state in HBM:
@@ -109,6 +114,7 @@ struct Counters {
 //   r2 = (d.x, d.y, d.z, lane id)    lane id: global PCG32 lane index (bit pattern)
 struct PathQueue {
     float4 *r0, *r1, *r2;
+    float4 *r3;                  // adjoint only: dL of the lane (d loss / d radiance of its sample), written by ray generation
     unsigned long long *count;   // number of records appended by the ray-generation kernel
 };
 
@@ -208,6 +214,25 @@ __device__ __forceinline__ float spec_log(float x) {
     float r = m + y;
     r = __fmaf_rn(fe, 0.693359375f, r);
     return r;
+}
+
+// Cephes expf for x <= 0 of moderate size (reconstruction-filter weights)
+__device__ __forceinline__ float spec_exp(float x) {
+    float z = floorf(__fmaf_rn(1.44269504088896341f, x, 0.5f));
+    x = __fmaf_rn(z, -0.693359375f, x);
+    x = __fmaf_rn(z, 2.12194440e-4f, x);
+    int n = (int) z;
+    float xx = x * x;
+    float y = 1.9875691500e-4f;
+    y = __fmaf_rn(y, x, 1.3981999507e-3f);
+    y = __fmaf_rn(y, x, 8.3334519073e-3f);
+    y = __fmaf_rn(y, x, 4.1665795894e-2f);
+    y = __fmaf_rn(y, x, 1.6666665459e-1f);
+    y = __fmaf_rn(y, x, 5.0000001201e-1f);
+    y = __fmaf_rn(y, xx, x);
+    y = y + 1.f;
+    if (n < -126) return 0.f;
+    return y * __uint_as_float((uint32_t) (n + 127) << 23);
 }
 
 __device__ __forceinline__ void spec_sincos(float x, float &s_out, float &c_out) {
@@ -621,6 +646,7 @@ struct Lane {
     Pcg rng;
     V3 o, d;
     int pix;   // -1: the sample fell outside the film
+    float fx, fy;   // film position in pixels
 };
 __device__ __forceinline__ Lane lane_setup(const SceneK &S, uint32_t seed, uint32_t spp, uint64_t idx) {
     Lane L;
@@ -631,6 +657,7 @@ __device__ __forceinline__ Lane lane_setup(const SceneK &S, uint32_t seed, uint3
     float pfx = (float) px + u1, pfy = (float) py + u2;
     int ix = (int) floorf(pfx), iy = (int) floorf(pfy);
     L.pix = (ix >= 0 && ix < (int) S.W && iy >= 0 && iy < (int) S.H) ? iy * (int) S.W + ix : -1;
+    L.fx = pfx; L.fy = pfy;
     float sx = pfx * S.rcpW, sy = pfy * S.rcpH;
     const float *A = S.cam_axes, *O = S.cam_o;
     if (S.n_sensors > 1) {                                 // batch.cpp sample_ray: view by film column
@@ -651,6 +678,51 @@ __device__ __forceinline__ Lane lane_setup(const SceneK &S, uint32_t seed, uint3
     float near_t = S.near_clip / dz;
     L.o = ray_at(mk3(O[0], O[1], O[2]), L.d, near_t);
     return L;
+}
+
+// the film position of lane idx alone (the first two draws of its stream)
+__device__ __forceinline__ void film_position(const SceneK &S, uint32_t seed, uint32_t spp, uint32_t idx, float &fx, float &fy) {
+    Pcg rng;
+    sampler_seed(rng, seed, idx);
+    uint32_t pixel = idx / spp;
+    uint32_t py = pixel / S.W, px = pixel - S.W * py;
+    float u1 = pcg_f32(rng), u2 = pcg_f32(rng);
+    fx = (float) px + u1; fy = (float) py + u2;
+}
+
+// ----------------------------------------------------------------------------
+// ImageBlock.put: f(pixel, weight) for every pixel a sample at film position (fx, fy) is splatted to.
+// Box: the pixel that contains it, weight 1.  Gaussian (hdrfilm default): radius 4 stddev, separable weights
+// max(0, exp(a x^2) - exp(a r^2)) at the pixel centres within the radius (at most 4 x 4).
+// ----------------------------------------------------------------------------
+template <class F>
+__device__ __forceinline__ void film_for_each(const SceneK &S, float fx, float fy, F f) {
+    const int W = (int) S.W, H = (int) S.H;
+    if (S.rfilter != 1) {
+        int ix = (int) floorf(fx), iy = (int) floorf(fy);
+        if (ix >= 0 && ix < W && iy >= 0 && iy < H) f(iy * W + ix, 1.f);
+        return;
+    }
+    const float sd = S.rf_stddev, r = 4.f * sd;
+    const float alpha = -1.f / ((2.f * sd) * sd);
+    const float bias = spec_exp(alpha * (r * r));
+    const int count = 2 * (int) ceilf(r);
+    const float px = fx - 0.5f, py = fy - 0.5f;
+    const int lox = (int) ceilf(px - r), loy = (int) ceilf(py - r);
+    float wx[4], wy[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float dx = (float) (lox + i) - px, dy = (float) (loy + i) - py;
+        wx[i] = (i < count) ? fmax_(0.f, spec_exp(alpha * (dx * dx)) - bias) : 0.f;
+        wy[i] = (i < count) ? fmax_(0.f, spec_exp(alpha * (dy * dy)) - bias) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int x = lox + i, y = loy + j;
+            if (i < count && j < count && x >= 0 && x < W && y >= 0 && y < H) f(y * W + x, wy[j] * wx[i]);
+        }
 }
 
 // ----------------------------------------------------------------------------
@@ -676,4 +748,29 @@ __device__ __forceinline__ void counter_flush(Counters *C, int slot, unsigned v)
 }
 #endif
 
+// d(develop o put)/dL * grad_in for a sample at film position (fx, fy): sum over its footprint of w * grad_in[p] / W[p]
+__device__ __forceinline__ V3 film_gather(const SceneK &S, const float *grad_img, const float *film_w, float fx, float fy) {
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    film_for_each(S, fx, fy, [&](int p, float w) {
+        float fw = film_w[p];
+        float dv = (fw == 0.f) ? 1.f : fw;
+        ax += w * (grad_img[3 * p] / dv);
+        ay += w * (grad_img[3 * p + 1] / dv);
+        az += w * (grad_img[3 * p + 2] / dv);
+    });
+    return mk3(ax, ay, az);
+}
+
+// Out-of-line forms for the gaussian filter, so that the (default) box path of the tracing kernels keeps its register
+// allocation: they run once per path, in the slow step.  Values travel in registers (no reference parameters).
+static __device__ __noinline__ void film_splat_filtered(const SceneK &S, float4 *acc, float fx, float fy, float lx, float ly, float lz) {
+    film_for_each(S, fx, fy, [&](int p, float w) { red_add_v4(acc + p, lx * w, ly * w, lz * w, w); });
+}
+// the same for the lane whose film position is recomputed from its stream
+static __device__ __noinline__ void film_splat_filtered_lane(const SceneK &S, float4 *acc, uint32_t seed, uint32_t spp, uint32_t idx,
+                                                             float lx, float ly, float lz) {
+    float fx, fy;
+    film_position(S, seed, spp, idx, fx, fy);
+    film_for_each(S, fx, fy, [&](int p, float w) { red_add_v4(acc + p, lx * w, ly * w, lz * w, w); });
+}
 }  // namespace rcv

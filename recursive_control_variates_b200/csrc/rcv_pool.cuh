@@ -24,9 +24,9 @@ __device__ __forceinline__ uint32_t pu_f(float v) { return __float_as_uint(v); }
 // TsLane <-> pool.  Word map:
 //  0 pix  1-2 rng.state  3-4 rng.inc  5-7 o  8-10 d  11-13 id  14-16 thr_old  17-19 thr_new
 //  20 si_t  21 depth  22 flags  23-25 no  26-28 nd  29 total  30 tr_old  31 tr_new
-//  32-34 L_old  35-37 L_new  38 last_pdf  39 phase_val  40 ratio
+//  32-34 L_old  35-37 L_new  38 last_pdf  39 phase_val  40 ratio  41-42 film position
 // ---------------------------------------------------------------------------
-static constexpr int kTsWords = 41;
+static constexpr int kTsWords = 43;
 
 __device__ __forceinline__ void ts_pool_load_hot(const float *pw, int s, TsLane &ln) {
     ln.rng.state = (uint64_t) pu_f(PW(1)) | ((uint64_t) pu_f(PW(2)) << 32);
@@ -41,6 +41,7 @@ __device__ __forceinline__ void ts_pool_load_cold(const float *pw, int s, TsLane
     ln.pix = (int) pu_f(PW(0));
     ln.L_old = mk3(PW(32), PW(33), PW(34)); ln.L_new = mk3(PW(35), PW(36), PW(37));
     ln.last_pdf = PW(38); ln.phase_val = PW(39); ln.ratio = PW(40);
+    ln.fx = PW(41); ln.fy = PW(42);
 }
 // what ts_collide can modify
 __device__ __forceinline__ void ts_pool_store_coll(float *pw, int s, const TsLane &ln) {
@@ -61,6 +62,7 @@ __device__ __forceinline__ void ts_pool_store_all(float *pw, int s, const TsLane
     PW(32) = ln.L_old.x; PW(33) = ln.L_old.y; PW(34) = ln.L_old.z;
     PW(35) = ln.L_new.x; PW(36) = ln.L_new.y; PW(37) = ln.L_new.z;
     PW(38) = ln.last_pdf; PW(39) = ln.phase_val; PW(40) = ln.ratio;
+    PW(41) = ln.fx; PW(42) = ln.fy;
 }
 
 // ---------------------------------------------------------------------------

@@ -20,6 +20,7 @@ inline void scene_from_desc(const rcv_scene_desc &d, SceneK &S) {
     S.scale = d.sigma_t_scale; S.phase = d.phase_type; S.g = d.phase_g;
     S.sample_emitters = d.sample_emitters; S.env_dist = d.env_dist;
     S.max_depth = d.max_depth; S.rr_depth = d.rr_depth; S.hide_emitters = d.hide_emitters; S.use_nee = d.use_nee;
+    S.rfilter = d.rfilter_type; S.rf_stddev = d.rfilter_stddev;
     S.n_sensors = (int) d.n_sensors;
     for (int k = 0; k < RCV_MAX_SENSORS; ++k) {
         for (int i = 0; i < 3; ++i) S.batch_o[3 * k + i] = d.batch_origin[k][i];

@@ -39,11 +39,11 @@ __device__ __forceinline__ void twostates_lane(const SceneK &S, const GRID &G, u
     Lane L = lane_setup(S, seed, spp, idx);
     V3 Lo, Ln;
     trace_twostates<MODE>(S, G, L.rng, L.o, L.d, Lo, Ln, nc, nsct);
-    if (L.pix >= 0) {
-        // ImageBlock.put with the box filter: (L * weight, weight) added at floor(pos)
-        if (MODE != 2) red_add_v4(acc_old + L.pix, Lo.x, Lo.y, Lo.z, 1.f);
-        if (MODE != 1) red_add_v4(acc_new + L.pix, Ln.x, Ln.y, Ln.z, 1.f);
-    }
+    // ImageBlock.put: (L * weight, weight) added to the pixels of the filter footprint
+    film_for_each(S, L.fx, L.fy, [&](int p, float w) {
+        if (MODE != 2) red_add_v4(acc_old + p, Lo.x * w, Lo.y * w, Lo.z * w, w);
+        if (MODE != 1) red_add_v4(acc_new + p, Ln.x * w, Ln.y * w, Ln.z * w, w);
+    });
 }
 
 template <int MODE, class GRID>
@@ -88,16 +88,18 @@ __device__ __forceinline__ void vps_lane(const SceneK &S, const GRID &G, const G
     Pcg rng1 = L.rng;                                   // RBIntegrator.render_backward: sampler.clone() for pass 1
     vps_trace<false>(S, G, D, rng1, alt, L.o, L.d, mk3(0, 0, 0), mk3(0, 0, 0), res, cnt);
     if (!BACKWARD) {
-        if (L.pix >= 0) red_add_v4(accum + L.pix, res.x, res.y, res.z, 1.f);
+        film_for_each(S, L.fx, L.fy, [&](int p, float w) { red_add_v4(accum + p, res.x * w, res.y * w, res.z * w, w); });
         return;
     }
-    // dL = d(develop o put)/dL * grad_in: box filter -> grad_in[pixel] / W[pixel]
+    // dL = d(develop o put)/dL * grad_in = sum over the filter footprint of w * grad_in[p] / W[p]
     V3 dL = mk3(0, 0, 0);
-    if (L.pix >= 0) {
-        float w = __ldg(film_w + L.pix);
-        float dv = (w == 0.f) ? 1.f : w;
-        dL = mk3(__ldg(grad_img + 3 * L.pix) / dv, __ldg(grad_img + 3 * L.pix + 1) / dv, __ldg(grad_img + 3 * L.pix + 2) / dv);
-    }
+    film_for_each(S, L.fx, L.fy, [&](int p, float w) {
+        float fw = __ldg(film_w + p);
+        float dv = (fw == 0.f) ? 1.f : fw;
+        dL.x += w * (__ldg(grad_img + 3 * p) / dv);
+        dL.y += w * (__ldg(grad_img + 3 * p + 1) / dv);
+        dL.z += w * (__ldg(grad_img + 3 * p + 2) / dv);
+    });
     sampler_seed(alt, alt_seed, (uint32_t) idx);        // volpathsimple.py:119-120
     V3 res2;
     vps_trace<true>(S, G, D, L.rng, alt, L.o, L.d, dL, res, res2, cnt);
@@ -190,7 +192,8 @@ __global__ void __launch_bounds__(kBlock) k_twostates_raygen(const __grid_consta
 
 template <bool BACKWARD>
 __global__ void __launch_bounds__(kBlock) k_vps_raygen(const __grid_constant__ SceneK S, uint32_t seed, uint32_t spp, uint32_t spp_begin,
-                                                       uint32_t ns, uint64_t n_local, float4 *accum, PathQueue Q, Counters *C) {
+                                                       uint32_t ns, uint64_t n_local, float4 *accum, PathQueue Q, Counters *C,
+                                                       const float *grad_img, const float *film_w) {
     uint64_t j = (uint64_t) blockIdx.x * kBlock + threadIdx.x;
     VpLane ln; ln.ev = EV_INIT; ln.flags = 0;
     VpSink sk; sk.accum = accum; sk.D.gsig = nullptr; sk.D.galb = nullptr; sk.grad_img = nullptr; sk.film_w = nullptr;
@@ -200,7 +203,17 @@ __global__ void __launch_bounds__(kBlock) k_vps_raygen(const __grid_constant__ S
     if (j < n_local) vp_raygen<BACKWARD>(S, ln, sk, global_lane(j, spp, spp_begin, ns));
     bool enter = (j < n_local) && ln.ev == EV_COLL;
     unsigned long long pos = queue_slot(Q.count, enter);
-    if (enter) vp_store(ln, Q, pos);
+    if (enter) {
+        vp_store(ln, Q, pos);
+        if (BACKWARD) {
+            // dL = d(develop o put)/dL * grad_in of this sample (volpathsimple.py:62-70 via RBIntegrator.render_backward):
+            // sum over the reconstruction filter's footprint of w * grad_in[p] / W[p]; the tracer reads it with the record
+            float fx, fy;
+            film_position(S, seed, spp, ln.idx, fx, fy);
+            V3 dL = film_gather(S, grad_img, film_w, fx, fy);
+            Q.r3[pos] = make_float4(dL.x, dL.y, dL.z, 0.f);
+        }
+    }
     counter_flush(C, 6, sk.n_paths);
 }
 
@@ -599,17 +612,19 @@ static cudaError_t launch_vps(const LaunchCfg &cfg, const SceneK &S, const GRID 
     if (cfg.tracer == 0 || cfg.tracer == 3) {
         if ((e = cudaMemsetAsync(cfg.work_counter, 0, sizeof(unsigned long long), cfg.stream)) != cudaSuccess) return e;
         if ((e = cudaMemsetAsync(cfg.queue.count, 0, sizeof(unsigned long long), cfg.stream)) != cudaSuccess) return e;
+        PathQueue qv = cfg.queue;
+        if (!BACKWARD) qv.r3 = nullptr;              // the primal render carries no dL
         k_vps_raygen<BACKWARD><<<(unsigned) ((n_local + kBlock - 1) / kBlock), kBlock, 0, cfg.stream>>>(
-            S, seed, spp, spp_begin, ns, n_local, accum, cfg.queue, cfg.counters);
+            S, seed, spp, spp_begin, ns, n_local, accum, qv, cfg.counters, grad_img, film_w);
         if (cfg.tracer == 3) {
             e = launch_pool(cfg, k_vps_pool<BACKWARD, GRID>, kPoolWarps * pool_warp_floats<kVpWords>() * sizeof(float), n_local, S, G, D, seed,
-                            spp, alt_seed, grad_img, film_w, accum, cfg.queue, cfg.counters, cfg.work_counter, cfg.arena, cfg.vcap);
+                            spp, alt_seed, grad_img, film_w, accum, qv, cfg.counters, cfg.work_counter, cfg.arena, cfg.vcap);
             if (e != cudaSuccess) return e;
         } else {
             unsigned blocks;
             if ((e = persistent_grid(cfg, k_vps_wavefront<BACKWARD, GRID>, kWfBlock, n_local, blocks)) != cudaSuccess) return e;
             k_vps_wavefront<BACKWARD, GRID><<<blocks, kWfBlock, 0, cfg.stream>>>(S, G, D, seed, spp, alt_seed, grad_img, film_w, accum,
-                                                                           cfg.queue, cfg.counters, cfg.work_counter, cfg.arena,
+                                                                           qv, cfg.counters, cfg.work_counter, cfg.arena,
                                                                            cfg.vcap);
         }
         (*cfg.launches) += 2;
@@ -669,14 +684,9 @@ __global__ void __launch_bounds__(kBlock) k_film_weights(const __grid_constant__
     uint64_t j = (uint64_t) blockIdx.x * kBlock + threadIdx.x;
     if (j >= n_local) return;
     const uint64_t idx = global_lane(j, spp, spp_begin, ns);
-    // only the film position of lane_setup is needed here
-    Pcg rng;
-    sampler_seed(rng, seed, (uint32_t) idx);
-    uint32_t pixel = (uint32_t) (idx / spp);
-    uint32_t py = pixel / S.W, px = pixel - S.W * py;
-    float u1 = pcg_f32(rng), u2 = pcg_f32(rng);
-    int ix = (int) floorf((float) px + u1), iy = (int) floorf((float) py + u2);
-    if (ix >= 0 && ix < (int) S.W && iy >= 0 && iy < (int) S.H) red_add_f32(film_w + (iy * (int) S.W + ix), 1.f);
+    float fx, fy;
+    film_position(S, seed, spp, (uint32_t) idx, fx, fy);
+    film_for_each(S, fx, fy, [&](int p, float w) { red_add_f32(film_w + p, w); });
 }
 
 // adds the film weights of samples [spp_begin, spp_end) of every pixel to film_w (zeroed first when `zero`)

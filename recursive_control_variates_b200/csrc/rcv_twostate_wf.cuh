@@ -39,6 +39,7 @@ enum : uint32_t {
 struct TsLane {
     int ev;
     int pix;                // film pixel of the path (-1: outside the film)
+    float fx, fy;           // film position (the reconstruction filter's footprint is centred here)
     Pcg rng;
     V3 o, d;                // main-path ray
     V3 id;                  // 1/d of the CURRENT segment (main ray, or the shadow ray during NEE)
@@ -59,10 +60,15 @@ struct TsSink {
 };
 
 template <int MODE>
-__device__ __forceinline__ void ts_finish(TsLane &ln, TsSink &sk) {
-    if (ln.pix >= 0) {
-        if (MODE != 2) red_add_v4(sk.acc_old + ln.pix, ln.L_old.x, ln.L_old.y, ln.L_old.z, 1.f);
-        if (MODE != 1) red_add_v4(sk.acc_new + ln.pix, ln.L_new.x, ln.L_new.y, ln.L_new.z, 1.f);
+__device__ __forceinline__ void ts_finish(const SceneK &S, TsLane &ln, TsSink &sk) {
+    if (S.rfilter == 0) {                               // box filter: the pixel that contains the sample, weight 1
+        if (ln.pix >= 0) {
+            if (MODE != 2) red_add_v4(sk.acc_old + ln.pix, ln.L_old.x, ln.L_old.y, ln.L_old.z, 1.f);
+            if (MODE != 1) red_add_v4(sk.acc_new + ln.pix, ln.L_new.x, ln.L_new.y, ln.L_new.z, 1.f);
+        }
+    } else {
+        if (MODE != 2) film_splat_filtered(S, sk.acc_old, ln.fx, ln.fy, ln.L_old.x, ln.L_old.y, ln.L_old.z);
+        if (MODE != 1) film_splat_filtered(S, sk.acc_new, ln.fx, ln.fy, ln.L_new.x, ln.L_new.y, ln.L_new.z);
     }
     sk.n_paths++;
     ln.ev = EV_INIT;
@@ -103,7 +109,7 @@ __device__ __forceinline__ bool ts_loop_head(const SceneK &S, TsLane &ln) {
 template <int MODE>
 __device__ __forceinline__ void ts_raygen(const SceneK &S, TsLane &ln, TsSink &sk, uint32_t seed, uint32_t spp, uint64_t idx) {
     Lane L = lane_setup(S, seed, spp, idx);
-    ln.rng = L.rng; ln.o = L.o; ln.d = L.d; ln.pix = L.pix;
+    ln.rng = L.rng; ln.o = L.o; ln.d = L.d; ln.pix = L.pix; ln.fx = L.fx; ln.fy = L.fy;
     ln.id = rcp3(ln.d);
     ln.depth = 0;
     ln.L_old = mk3(0, 0, 0); ln.L_new = mk3(0, 0, 0);
@@ -112,9 +118,9 @@ __device__ __forceinline__ void ts_raygen(const SceneK &S, TsLane &ln, TsSink &s
     ln.flags = F_NEEDS_ISECT | F_SPECULAR;
     (void) pcg_f32(ln.rng);                                           // :173 channel draw
     while (true) {
-        if (!ts_loop_head(S, ln)) { ts_finish<MODE>(ln, sk); return; }
+        if (!ts_loop_head(S, ln)) { ts_finish<MODE>(S, ln, sk); return; }
         Hit h = box_hit(S, ln.o, ln.d, ln.id, RCV_LARGEST);
-        if (!h.valid) { ts_env_hit(S, ln); ts_finish<MODE>(ln, sk); return; }
+        if (!h.valid) { ts_env_hit(S, ln); ts_finish<MODE>(S, ln, sk); return; }
         (void) pcg_f32(ln.rng); (void) pcg_f32(ln.rng); (void) pcg_f32(ln.rng);   // :347-348
         ln.o = offset_p(h.p, h.n, ln.d);
         if (!(dot3(h.n, ln.d) > 0.f)) { ln.ev = EV_COLL; return; }   // :378-379 entered the medium
@@ -127,8 +133,8 @@ __device__ __forceinline__ void ts_raygen(const SceneK &S, TsLane &ln, TsSink &s
 __device__ __forceinline__ void ts_store(const TsLane &ln, const PathQueue &Q, unsigned long long pos) {
     Q.r0[pos] = make_float4(__uint_as_float((uint32_t) ln.rng.state), __uint_as_float((uint32_t) (ln.rng.state >> 32)),
                             __uint_as_float((uint32_t) (ln.rng.inc >> 1)), __int_as_float(ln.pix));
-    Q.r1[pos] = make_float4(ln.o.x, ln.o.y, ln.o.z, 0.f);
-    Q.r2[pos] = make_float4(ln.d.x, ln.d.y, ln.d.z, 0.f);
+    Q.r1[pos] = make_float4(ln.o.x, ln.o.y, ln.o.z, ln.fx);
+    Q.r2[pos] = make_float4(ln.d.x, ln.d.y, ln.d.z, ln.fy);
 }
 __device__ __forceinline__ void ts_load(TsLane &ln, const PathQueue &Q, unsigned long long pos) {
     float4 a = __ldg(Q.r0 + pos), b = __ldg(Q.r1 + pos), c = __ldg(Q.r2 + pos);
@@ -136,6 +142,7 @@ __device__ __forceinline__ void ts_load(TsLane &ln, const PathQueue &Q, unsigned
     ln.rng.inc = ((uint64_t) __float_as_uint(a.z) << 1) | 1u;
     ln.pix = (int) __float_as_uint(a.w);
     ln.o = mk3(b.x, b.y, b.z); ln.d = mk3(c.x, c.y, c.z);
+    ln.fx = b.w; ln.fy = c.w;
     ln.id = rcp3(ln.d);
     ln.depth = 0;
     ln.L_old = mk3(0, 0, 0); ln.L_new = mk3(0, 0, 0);
@@ -176,7 +183,7 @@ __device__ __forceinline__ void ts_slow(const SceneK &S, TsLane &ln, TsSink &sk)
             if (ts_loop_head(S, ln)) ts_env_hit(S, ln);
         }
     }
-    ts_finish<MODE>(ln, sk);
+    ts_finish<MODE>(S, ln, sk);
 }
 
 template <int MODE, class GRID>

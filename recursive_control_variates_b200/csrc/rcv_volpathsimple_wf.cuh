@@ -110,19 +110,16 @@ __device__ __forceinline__ void vp_end_pass(const SceneK &S, VpLane &ln, VpSink 
         ln.result = ln.result + (ln.thr * w) * env;
     }
     if (!BW) {
-        if (ln.pix >= 0) red_add_v4(sk.accum + ln.pix, ln.result.x, ln.result.y, ln.result.z, 1.f);
+        if (S.rfilter == 0) {
+            if (ln.pix >= 0) red_add_v4(sk.accum + ln.pix, ln.result.x, ln.result.y, ln.result.z, 1.f);
+        } else {
+            film_splat_filtered_lane(S, sk.accum, sk.seed, sk.spp, ln.idx, ln.result.x, ln.result.y, ln.result.z);
+        }
         vp_finish(ln, sk);
         return;
     }
     sk.n_paths++;                                   // pass 1 complete
-    // dL = d(develop o put)/dL * grad_in: box filter -> grad_in[pixel] / W[pixel]
-    ln.dL = mk3(0, 0, 0);
-    if (ln.pix >= 0) {
-        float w = __ldg(sk.film_w + ln.pix);
-        float dv = (w == 0.f) ? 1.f : w;
-        ln.dL = mk3(__ldg(sk.grad_img + 3 * ln.pix) / dv, __ldg(sk.grad_img + 3 * ln.pix + 1) / dv,
-                    __ldg(sk.grad_img + 3 * ln.pix + 2) / dv);
-    }
+    // ln.dL = d(develop o put)/dL * grad_in of this sample came with the path record (computed by ray generation)
     // pass 2 starts from state_in = the pass-1 result (:68) with the secondary sampler (:119-120)
     sampler_seed(ln.alt, sk.alt_seed, ln.idx);
     ln.flags = VF_ADJ;
@@ -177,9 +174,11 @@ __device__ __forceinline__ void vp_store(const VpLane &ln, const PathQueue &Q, u
     Q.r1[pos] = make_float4(ln.o.x, ln.o.y, ln.o.z, ln.ray_maxt);
     Q.r2[pos] = make_float4(ln.d.x, ln.d.y, ln.d.z, __uint_as_float(ln.idx));
 }
-// begin pass 1 of the path recorded at pos in arena slot `slot`
+// begin pass 1 of the path recorded at pos in arena slot `slot` (Q.r3 != null: the adjoint, the record carries dL)
 __device__ __forceinline__ void vp_load(VpLane &ln, const VpSink &sk, const PathQueue &Q, unsigned long long pos, uint32_t slot) {
     float4 a = __ldg(Q.r0 + pos), b = __ldg(Q.r1 + pos), c = __ldg(Q.r2 + pos);
+    ln.dL = mk3(0, 0, 0);
+    if (Q.r3) { float4 g = __ldg(Q.r3 + pos); ln.dL = mk3(g.x, g.y, g.z); }
     ln.rng.state = (uint64_t) __float_as_uint(a.x) | ((uint64_t) __float_as_uint(a.y) << 32);
     ln.rng.inc = ((uint64_t) __float_as_uint(a.z) << 1) | 1u;
     ln.pix = (int) __float_as_uint(a.w);

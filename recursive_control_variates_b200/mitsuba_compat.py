@@ -149,8 +149,12 @@ class Sensor:
         elif d.get("type") != "perspective":
             raise ValueError("only `perspective` and `batch` sensors are supported")
         film = d.get("film", {})
-        if film.get("rfilter", {"type": "box"}).get("type", "box") != "box":
-            raise ValueError("only the box reconstruction filter is supported (SURVEY.md §8f)")
+        # hdrfilm: Mitsuba's default reconstruction filter is `gaussian` (stddev 0.5); `box` must be asked for
+        rf = film.get("rfilter", {"type": "gaussian"})
+        self.rfilter = rf.get("type", "gaussian")
+        self.rfilter_stddev = float(rf.get("stddev", 0.5))
+        if self.rfilter not in ("box", "gaussian"):
+            raise ValueError("only the `box` and `gaussian` reconstruction filters are supported")
         self._film = Film(film.get("width", 768), film.get("height", 576))
         self.fov = float(d.get("fov", 45.0))
         self.to_world = np.asarray(d.get("to_world", look_at([0.5, 0.5, -2.0], [0.5, 0.5, 0.5], [0, 1, 0])), dtype=np.float64)
@@ -228,7 +232,8 @@ class Scene:
         return SceneConfig(width=s.film().width, height=s.film().height, fov=s.fov, to_world=s.to_world, near_clip=s.near_clip,
                            bbox_min=sh.bbox_min, bbox_max=sh.bbox_max, sigma_t_scale=m.scale, phase=m.phase, phase_g=m.phase_g,
                            sample_emitters=m.sample_emitters, env_radiance=self.env_radiance, max_depth=max_depth,
-                           rr_depth=rr_depth, hide_emitters=hide_emitters, use_nee=use_nee)
+                           rr_depth=rr_depth, hide_emitters=hide_emitters, use_nee=use_nee, rfilter=s.rfilter,
+                           rfilter_stddev=s.rfilter_stddev)
 
     def context(self, max_depth: int, rr_depth: int, hide_emitters: bool = False, use_nee: bool = True) -> Context:
         """The rcv_ctx of this scene, configured for the calling integrator."""

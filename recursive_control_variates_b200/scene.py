@@ -55,6 +55,8 @@ class SceneConfig:
     rr_depth: int = 64
     hide_emitters: bool = False
     use_nee: bool = True
+    rfilter: str = "box"                    # "box" or "gaussian" (Mitsuba's hdrfilm default)
+    rfilter_stddev: float = 0.5
 
     def to_desc(self) -> SceneDesc:
         d = SceneDesc()
@@ -94,4 +96,8 @@ class SceneConfig:
         d.env_dist = float(np.float32(2.0 * radius))
         d.max_depth, d.rr_depth = int(self.max_depth), int(self.rr_depth)
         d.hide_emitters, d.use_nee = int(self.hide_emitters), int(self.use_nee)
+        if self.rfilter not in ("box", "gaussian"):
+            raise ValueError("rfilter must be 'box' or 'gaussian'")
+        d.rfilter_type = 1 if self.rfilter == "gaussian" else 0
+        d.rfilter_stddev = float(np.float32(self.rfilter_stddev))
         return d

@@ -77,10 +77,12 @@ void pack(const rcv_scene_desc &d, const float *so, const float *ao, const float
 }
 
 struct HostQueue {
-    std::vector<float4> r0, r1, r2;
+    std::vector<float4> r0, r1, r2, r3;
     unsigned long long count;
     PathQueue Q;
-    explicit HostQueue(size_t n) : r0(n), r1(n), r2(n), count(0) { Q.r0 = r0.data(); Q.r1 = r1.data(); Q.r2 = r2.data(); Q.count = &count; }
+    explicit HostQueue(size_t n) : r0(n), r1(n), r2(n), r3(n), count(0) {
+        Q.r0 = r0.data(); Q.r1 = r1.data(); Q.r2 = r2.data(); Q.r3 = nullptr; Q.count = &count;
+    }
 };
 
 // raygen for all lanes (as the GPU's ray-generation kernel), then the event
@@ -120,7 +122,16 @@ void run_vps(const SceneK &S, const GRID &G, VpSink &sk) {
     for (uint64_t idx = 0; idx < n; ++idx) {
         VpLane ln; ln.ev = EV_INIT; ln.flags = 0;
         vp_raygen<BW>(S, ln, sk, idx);
-        if (ln.ev == EV_COLL) vp_store(ln, hq.Q, hq.count++);
+        if (ln.ev == EV_COLL) {
+            if (BW) {      // as k_vps_raygen: the record carries dL
+                hq.Q.r3 = hq.r3.data();
+                float fx, fy;
+                film_position(S, sk.seed, sk.spp, ln.idx, fx, fy);
+                V3 dL = film_gather(S, sk.grad_img, sk.film_w, fx, fy);
+                hq.r3[hq.count] = make_float4(dL.x, dL.y, dL.z, 0.f);
+            }
+            vp_store(ln, hq.Q, hq.count++);
+        }
     }
     for (unsigned long long pos = 0; pos < hq.count; ++pos) {
         VpLane ln; ln.flags = 0;

@@ -35,9 +35,9 @@ def test_header_symbols_exported(lib):
 
 def test_struct_layouts_match_header(lib):
     from recursive_control_variates_b200 import _abi
-    # 4 + 2*4 + 3*4 + 9*4 + 3*4 + 6*4 + 4 + 4 + 4 + 4 + 3*4 + 4 + 4*4 = 144, + n_sensors 4 + 16 * (3 + 9) * 4 = 916
-    assert C.sizeof(_abi.SceneDesc) == 916
-    assert lib.rcv_abi_version() == 2
+    # 4 + 2*4 + 3*4 + 9*4 + 3*4 + 6*4 + 4 + 4 + 4 + 4 + 3*4 + 4 + 4*4 = 144, + n_sensors 4 + 16 * (3 + 9) * 4 = 916, + rfilter 8 = 924
+    assert C.sizeof(_abi.SceneDesc) == 924
+    assert lib.rcv_abi_version() == 3
 
 
 def test_no_cpu_fallback(lib):

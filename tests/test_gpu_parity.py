@@ -451,3 +451,36 @@ def test_sharded_film_weights(gpu_ctx, setup):
     gpu_ctx.grad_zero(); gpu_ctx.render_backward(seed, spp, gimg, 1, 4, film_w=w_all)
     b_s, b_a = gpu_ctx.grad_read()
     assert rel_l2(b_s.cpu().numpy(), a_s.cpu().numpy()) < 1e-5 and rel_l2(b_a.cpu().numpy(), a_a.cpu().numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("tracer", [0, 1, 3])
+def test_gaussian_reconstruction_filter(oracle, gpu_ctx, tracer):
+    """hdrfilm's default gaussian filter: every sample is splatted to up to 4 x 4 pixels, so even at spp = 1 a pixel
+    sums several contributions in an order that differs between the oracle and the atomics: images to 1e-6."""
+    cfg = small_scene(width=44, height=36, max_depth=12, rr_depth=4, rfilter="gaussian")
+    d = cfg.to_desc()
+    old, new = media(14)
+    mo, mn = oracle.OracleMedium(d, *old), oracle.OracleMedium(d, *new)
+    gpu_ctx.set_tracer(tracer)
+    gpu_ctx.set_scene(d)
+    gpu_set_states(gpu_ctx, old, new)
+    ao, an = oracle.render_twostates_accum(d, mo, mn, seed=61, spp=3)
+    go, gn = gpu_ctx.render_twostates_accum(seed=61, spp=3)
+    assert rel_l2(go.cpu().numpy(), ao) < 1e-6 and rel_l2(gn.cpu().numpy(), an) < 1e-6
+    H, F = oracle.render_twostates(d, mo, mn, seed=61, spp=3)
+    gH, gF = gpu_ctx.render_twostates(seed=61, spp=3)
+    assert rel_l2(gH.cpu().numpy(), H) < IMG_TOL and rel_l2(gF.cpu().numpy(), F) < IMG_TOL
+    assert rel_l2(gpu_ctx.render_adjoint_primal_accum(seed=62, spp=2).cpu().numpy(), oracle.vps_render_accum(d, mn, 62, 2)) < 1e-6
+    fw = gpu_ctx.film_weights(63, 3).cpu().numpy()
+    assert rel_l2(fw, oracle.film_weights(d, 63, 3)) < 1e-6
+    rng = np.random.default_rng(7)
+    gimg = (rng.standard_normal((d.film_height, d.film_width, 3)) / (d.film_height * d.film_width * 3)).astype(np.float32)
+    gs, ga = oracle.vps_backward(d, mn, 63, 3, gimg, threads=1)
+    gpu_ctx.grad_zero(); gpu_ctx.render_backward(63, 3, to_cuda(gimg))
+    ggs, gga = gpu_ctx.grad_read()
+    assert rel_l2(ggs.cpu().numpy(), gs) < GRAD_TOL and rel_l2(gga.cpu().numpy(), ga) < GRAD_TOL
+    from recursive_control_variates_b200._abi import RcvError
+    bad = cfg.to_desc(); bad.rfilter_stddev = 0.8
+    with pytest.raises(RcvError):
+        gpu_ctx.set_scene(bad)
+    gpu_ctx.set_tracer(3)

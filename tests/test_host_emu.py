@@ -164,3 +164,28 @@ def test_majorant_supergrid_event_machines(oracle, emu, factor):
                    acc, g1, g4, cnt, factor)
     gs, ga = oracle.vps_backward(d, mn, 15, 2, gimg, threads=1, film_w=film_w)
     assert rel_l2(g1, gs) < 1e-5 and rel_l2(g4[..., 0:3], ga) < 1e-5
+
+
+def test_gaussian_filter_event_machines(oracle, emu):
+    """hdrfilm's default gaussian reconstruction filter: footprint splats of the two-state render and of the
+    single-state primal, and the adjoint's dL gathered over the footprint (sums differ only in their order)."""
+    d = small_scene(28, 24, max_depth=10, rr_depth=4, rfilter="gaussian").to_desc()
+    (so, ao), (sn, an) = media(12)
+    mo, mn = oracle.OracleMedium(d, so, ao), oracle.OracleMedium(d, sn, an)
+    H, W = d.film_height, d.film_width
+    acc_o = np.zeros((H, W, 4), np.float32); acc_n = np.zeros((H, W, 4), np.float32)
+    cnt = np.zeros(8, np.uint64)
+    emu.emu_twostates(C.addressof(d), so, ao, sn, an, *so.shape[:3], 31, 2, 0, acc_o, acc_n, cnt)
+    ref_o, ref_n = oracle.render_twostates_accum(d, mo, mn, 31, 2)
+    assert rel_l2(acc_o, ref_o) < 1e-6 and rel_l2(acc_n, ref_n) < 1e-6
+    assert abs(float(acc_n[..., 3].sum()) - float(ref_n[..., 3].sum())) < 1e-3 * float(ref_n[..., 3].sum())
+    acc = np.zeros((H, W, 4), np.float32); g1 = np.zeros((*sn.shape[:3], 1), np.float32); g4 = np.zeros((*sn.shape[:3], 4), np.float32)
+    emu.emu_vps(C.addressof(d), sn, an, *sn.shape[:3], 32, 2, 0, 0, None, None, acc, g1, g4, cnt)
+    assert rel_l2(acc, oracle.vps_render_accum(d, mn, 32, 2)) < 1e-6
+    rng = np.random.default_rng(5)
+    gimg = (rng.standard_normal((H, W, 3)) / (H * W * 3)).astype(np.float32)
+    film_w = oracle.film_weights(d, 33, 2)
+    acc[:] = 0
+    emu.emu_vps(C.addressof(d), sn, an, *sn.shape[:3], 33, 2, 1, oracle.alt_seed(33), gimg.ctypes.data, film_w.ctypes.data, acc, g1, g4, cnt)
+    gs, ga = oracle.vps_backward(d, mn, 33, 2, gimg, threads=1, film_w=film_w)
+    assert rel_l2(g1, gs) < 1e-5 and rel_l2(g4[..., 0:3], ga) < 1e-5

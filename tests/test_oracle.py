@@ -281,3 +281,39 @@ def test_batch_sensor_views(oracle):
         assert rel_l2(sub, Fs) < 0.05 and abs(sub.mean() - Fs.mean()) < 5e-3 * Fs.mean()
     with pytest.raises(ValueError):
         SceneConfig(width=70, height=20, to_world=np.stack(views)).to_desc()  # 70 % 3 != 0
+
+
+def test_gaussian_reconstruction_filter(oracle):
+    """hdrfilm's default reconstruction filter (gaussian.cpp, stddev 0.5, radius 2) [upstream, restated]: a sample is
+    splatted to the 4 x 4 pixel centres within the radius, develop() divides by the accumulated weight."""
+    import ctypes as C
+    L = oracle.lib()
+    L.orc_expf.argtypes = [C.c_float]; L.orc_expf.restype = C.c_float
+    for x in (0.0, -1e-3, -0.5, -2.0, -7.99, -8.0, -20.0, -80.0):
+        xr = float(np.float32(x))
+        assert abs(L.orc_expf(x) - math.exp(xr)) <= 3e-7 * math.exp(xr) + 1e-45
+    old, new = media(12)
+    box = small_scene(width=24, height=20, max_depth=8, rr_depth=4)
+    gau = small_scene(width=24, height=20, max_depth=8, rr_depth=4, rfilter="gaussian")
+    db, dg = box.to_desc(), gau.to_desc()
+    assert dg.rfilter_type == 1 and dg.rfilter_stddev == 0.5
+    mb, mg = oracle.OracleMedium(db, *new), oracle.OracleMedium(dg, *new)
+    # film weights: a constant image stays constant; interior pixels collect spp * (sum of the 2-D filter) on average
+    ab = oracle.vps_render_accum(db, mb, 9, 64)
+    ag = oracle.vps_render_accum(dg, mg, 9, 64)
+    w1 = np.array([max(0.0, math.exp(-2 * x * x) - math.exp(-8.0)) for x in (-1.5, -0.5, 0.5, 1.5)])
+    assert abs(ag[4:-4, 4:-4, 3].mean() / 64 - np.add.outer(w1, w1).size * 0 - (w1.sum() ** 2)) < 0.05 * w1.sum() ** 2
+    ib, ig = oracle.develop(ab), oracle.develop(ag)
+    assert abs(ig.mean() - ib.mean()) < 0.01 * ib.mean()                     # same image in expectation ...
+    # ... with less noise: every pixel is fed by the samples of its neighbours too
+    noise = lambda d_, m_: float(np.mean((oracle.develop(oracle.vps_render_accum(d_, m_, 21, 16)) -
+                                          oracle.develop(oracle.vps_render_accum(d_, m_, 22, 16))) ** 2))
+    assert noise(dg, mg) < 0.7 * noise(db, mb)
+    # the same lanes (same streams), only the splat differs: energy is redistributed, not lost
+    assert abs((ag[..., :3].sum() / ag[..., 3].sum()) - (ab[..., :3].sum() / ab[..., 3].sum())) < 0.02 * ib.mean()
+    # adjoint: gradients with the filter are finite and close to the box-filter ones for a smooth image gradient
+    gimg = np.full((20, 24, 3), 1.0 / (20 * 24 * 3), np.float32)
+    gb = oracle.vps_backward(db, mb, 11, 64, gimg)
+    gg = oracle.vps_backward(dg, mg, 11, 64, gimg)
+    assert np.isfinite(gg[0]).all() and abs(gg[0].sum() - gb[0].sum()) < 0.1 * abs(gb[0].sum())
+    assert abs(gg[1].sum() - gb[1].sum()) < 0.02 * abs(gb[1].sum())
