@@ -130,7 +130,7 @@ def cpu_iteration_sample(a, n_gpus, sample_spp, threads):
     from recursive_control_variates_b200.scene import SceneConfig
     from recursive_control_variates_b200.synthetic import make_medium
     O.build()
-    desc = SceneConfig(width=a.res, height=a.res).to_desc()
+    desc = SceneConfig(width=a.res, height=a.res, rfilter=a.rfilter).to_desc()
     old, new = make_medium(a.grid, a.kind, 0.0), make_medium(a.grid, a.kind, 5e-3)
     mo, mn = O.OracleMedium(desc, *old), O.OracleMedium(desc, *new)
     spp = a.spp * n_gpus
