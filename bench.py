@@ -352,6 +352,9 @@ def run_ours(a):
             rows = [json.loads(l) for l in f if l.strip().startswith("{")]
         g64 = [r["GBps"] for r in rows if r.get("granule_bytes") == 64]
         gather_peak = max(g64) if g64 else None
+    for kv in kernels.values():
+        kv["frac_of_hbm_peak"] = kv["gbs"] / peak
+        kv["frac_of_gather_peak"] = (kv["gbs"] / gather_peak) if gather_peak else None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["gbs"] / peak, "traffic": traffic, "traffic_unit": "GB per launch",
                 "traffic_source": traffic_src, "algorithmic_gb": kernels[dom]["algorithmic_gb"], "peak_source": peak_src,
