@@ -61,6 +61,7 @@ def lib() -> C.CDLL:
         L.orc_render_twostates.argtypes = [SP, MP, MP, u32, u32, u32, u32, _f32p, _f32p, i32]
         L.orc_develop.argtypes = [_f32p, _f32p, u64]
         L.orc_film_weights.argtypes = [SP, u32, u32, _f32p]
+        L.orc_film_weights_range.argtypes = [SP, u32, u32, u32, u32, _f32p]
         L.orc_cv_update.argtypes = [_f32p] * 10 + [u64, i32, i32, i32, f, f, i32]
         L.orc_loss_grad.argtypes = [i32, _f32p, _f32p, u64, C.c_void_p]; L.orc_loss_grad.restype = C.c_double
         L.orc_vps_lanes.argtypes = [SP, MP, u32, u32, u64, u64, _f32p, _i32p, i32]
@@ -180,9 +181,10 @@ def render_twostates(desc, m_old, m_new, seed, spp, threads=None):
     return develop(ao), develop(an)
 
 
-def film_weights(desc, seed, spp) -> np.ndarray:
+def film_weights(desc, seed, spp, spp_begin=0, spp_end=None) -> np.ndarray:
+    """Film weights of samples [spp_begin, spp_end) of every pixel (all samples by default)."""
     Wt = np.zeros((desc.film_height, desc.film_width), np.float32)
-    lib().orc_film_weights(C.addressof(desc), seed, spp, Wt)
+    lib().orc_film_weights_range(C.addressof(desc), seed, spp, spp_begin, spp if spp_end is None else spp_end, Wt)
     return Wt
 
 

@@ -999,11 +999,17 @@ void orc_develop(const float *accum, float *img, uint64_t npix) {
 void orc_film_weights(const rcv_scene_desc *S, uint32_t seed, uint32_t spp, float *Wt) {
     uint64_t npix = (uint64_t) S->film_width * S->film_height;
     memset(Wt, 0, npix * sizeof(float));
-    for (uint64_t idx = 0; idx < npix * spp; ++idx) {
-        lane_t ln = lane_setup(S, seed, spp, idx);
-        footprint_t fp; film_footprint(S, ln.fx, ln.fy, &fp);
-        for (int q = 0; q < fp.n; ++q) Wt[fp.pix[q]] += fp.w[q];
-    }
+    orc_film_weights_range(S, seed, spp, 0, spp, Wt);
+}
+/* the weights of samples [spp_begin, spp_end) of every pixel, ADDED to Wt (one rank's piece of an spp-sharded job) */
+void orc_film_weights_range(const rcv_scene_desc *S, uint32_t seed, uint32_t spp, uint32_t spp_begin, uint32_t spp_end, float *Wt) {
+    uint64_t npix = (uint64_t) S->film_width * S->film_height;
+    for (uint64_t p = 0; p < npix; ++p)
+        for (uint32_t k = spp_begin; k < spp_end; ++k) {
+            lane_t ln = lane_setup(S, seed, spp, p * spp + k);
+            footprint_t fp; film_footprint(S, ln.fx, ln.fy, &fp);
+            for (int q = 0; q < fp.n; ++q) Wt[fp.pix[q]] += fp.w[q];
+        }
 }
 
 /* ------------------------------------------------------------------------- */

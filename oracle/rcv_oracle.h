@@ -46,6 +46,7 @@ int orc_render_twostates(const rcv_scene_desc *S, const orc_medium *Mo, const or
                          float *accum_old, float *accum_new, int nthreads);
 void orc_develop(const float *accum, float *img, uint64_t npix);
 void orc_film_weights(const rcv_scene_desc *S, uint32_t seed, uint32_t spp, float *Wt);
+void orc_film_weights_range(const rcv_scene_desc *S, uint32_t seed, uint32_t spp, uint32_t spp_begin, uint32_t spp_end, float *Wt);
 
 void orc_cv_update(const float *H, const float *F, float *img, float *v_n, float *w_s,
                    float *mean_x, float *mean_y, float *var_x, float *var_y, float *cov,

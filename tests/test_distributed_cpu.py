@@ -33,7 +33,11 @@ def _worker(rank, world, port, out_dir):
     b, e = parallel.shard_spp(spp, rank, world)
     acc_o, acc_n = O.render_twostates_accum(desc, mo, mn, 11, spp, b, e, threads=1)
     gimg = np.full((12, 16, 3), 1e-3, np.float32)
-    gs, ga = O.vps_backward(desc, mn, 99, spp, gimg, b, e, threads=1)
+    # the film weights of ALL samples: every rank contributes its own, one small all-reduce (rcv_film_weights)
+    fw = torch.from_numpy(O.film_weights(desc, 99, spp, b, e))
+    parallel.allreduce_sum_([fw])
+    assert np.array_equal(fw.numpy(), O.film_weights(desc, 99, spp))
+    gs, ga = O.vps_backward(desc, mn, 99, spp, gimg, b, e, threads=1, film_w=fw.numpy())
     ts = [torch.from_numpy(acc_o), torch.from_numpy(acc_n), torch.from_numpy(gs), torch.from_numpy(ga)]
     parallel.allreduce_sum_(ts)
     if rank == 0:
