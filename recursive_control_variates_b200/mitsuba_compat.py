@@ -5,8 +5,8 @@ hot path is driven through (`mi.load_dict`, `mi.traverse`, `mi.render`,
  without a Mitsuba install.
 
 Only the scene class of the volumetric experiments is understood
-(experiments.py:20-133): a perspective sensor with an hdrfilm (box filter), one
-box shape with a `null` BSDF whose interior is a `heterogeneous` grid medium
+(experiments.py:20-133): a perspective sensor or a `batch` of them with an hdrfilm
+(box or gaussian reconstruction filter), one box shape with a `null` BSDF whose interior is a `heterogeneous` grid medium
 (optionally wrapped in a `twostatemedium`), and a `constant` emitter.
 
 Tensors are torch CUDA tensors; differentiation goes through torch autograd:

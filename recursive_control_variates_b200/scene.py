@@ -1,8 +1,8 @@
 """Host-side scene description -> struct rcv_scene_desc.
 
 Covers the subset of `mi.load_dict` the reference's volumetric experiments use
-(experiments.py:20-133): a perspective sensor + hdrfilm (box filter), a box
-shape with a `null` BSDF containing a heterogeneous grid medium, a `constant`
+(experiments.py:20-133): a perspective sensor (or a batch of views) + hdrfilm (box or
+gaussian filter), a box shape with a `null` BSDF containing a heterogeneous grid medium, a `constant`
 environment emitter.  All derived quantities (camera frame, tan(fov/2), scene
 bounding sphere) are computed here in float64 and rounded once to float32, so
 the CUDA kernels and the test oracle receive identical numbers.
