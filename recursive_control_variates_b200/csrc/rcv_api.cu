@@ -185,7 +185,7 @@ int ensure_queue(rcv_ctx *c, uint32_t spp_begin, uint32_t spp_end) {
 // vertex-record arena of the vertex-list adjoint: one slot of (max_depth + 1) records per lane in flight
 int ensure_arena(rcv_ctx *c) {
     c->vcap = (uint32_t) c->S.max_depth + 1u;
-    size_t need = vps_backward_slots(c->cfg()) * (size_t) c->vcap;
+    size_t need = vps_backward_slots(c->cfg()) * ((size_t) c->vcap + 16);      // + the shadow-ray collision records (kNeeCap / 4)
     if (need > c->arena_records) {
         cudaFree(c->arena); c->arena = nullptr; c->arena_records = 0;
         CK(cudaMalloc(&c->arena, need * 4 * sizeof(float4)));

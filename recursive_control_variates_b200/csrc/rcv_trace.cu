@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(kWfBlock, RCV_VP_MINBLOCKS) k_vps_wavefront(co
         } else if (sel == EV_SCAT) {
             if (ln.ev == EV_SCAT) vp_vertex<BACKWARD>(S, G, ln, sk);
         } else {
-            if (ln.ev == EV_SLOW) vp_slow<BACKWARD>(S, ln, sk);
+            if (ln.ev == EV_SLOW) vp_slow<BACKWARD>(S, G, ln, sk);
             // refill the finished lanes from the record queue
             unsigned m_new = __ballot_sync(0xffffffffu, ln.ev == EV_INIT);
             if (m_new && cc.more) {
@@ -472,6 +472,7 @@ __global__ void __launch_bounds__(kPoolBlock, RCV_POOL_MINBLOCKS) k_vps_pool(con
             if (s >= 0) {
                 vp_pool_load_hot(pw, s, ln);
                 ln.ev = EV_COLL;
+                ln.vbase = (slot0 + (uint32_t) s) * (vcap + kNeeCap / 4);    // a cold word; the collision records live behind it
                 vp_collide<BACKWARD>(S, G, mu, inv_mu, ln, sk);
                 vp_pool_store_coll(pw, s, ln);
                 cls[s] = (unsigned char) ln.ev;
@@ -493,7 +494,7 @@ __global__ void __launch_bounds__(kPoolBlock, RCV_POOL_MINBLOCKS) k_vps_pool(con
                 vp_pool_load_hot(pw, s, ln); vp_pool_load_cold(pw, s, ln);
                 loaded = true;
                 ln.ev = EV_SLOW;
-                vp_slow<BACKWARD>(S, ln, sk);
+                vp_slow<BACKWARD>(S, G, ln, sk);
             }
             // empty slots take the next record
             unsigned m_need = __ballot_sync(0xffffffffu, s >= 0 && ln.ev == EV_INIT);

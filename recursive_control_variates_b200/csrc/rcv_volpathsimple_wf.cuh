@@ -50,13 +50,17 @@ enum : uint32_t {
     VF_REPLAY = 16u,      // shadow-ray transmittance replay with gradients (pass 2)
     VF_HEAD = 32u,        // next main-path collision starts with the loop head (:129-134)
     VF_DID_SCATTER = 64u,
+    VF_NEE_OVF = 128u,    // pass 1: the shadow ray had more tentative collisions than its record buffer holds
     // work parked for the batched EV_SLOW step
     VF_POSTNEE = 512u,    // the shadow ray (or its replay) ended
     VF_END = 1024u        // the pass ended at a loop head (:132-133)
 };
 
 // vertex record flags
-enum : uint32_t { VR_SCATTER = 1u, VR_NEE = 2u };
+enum : uint32_t { VR_SCATTER = 1u, VR_NEE = 2u, VR_NEE_DONE = 4u /* its transmittance gradients were scattered in pass 1 */ };
+// records (position, -1 / (majorant * tr)) of the tentative collisions of one shadow ray, kept per arena slot behind the
+// vertex records; 16 vertex-record equivalents
+static constexpr int kNeeCap = 64;
 static constexpr int kVertexCapMax = 4096;   // largest supported max_depth + 1 for the vertex-list adjoint
 
 struct VpLane {
@@ -91,6 +95,9 @@ struct VpSink {
 
 __device__ __forceinline__ float4 *vp_record(const VpSink &sk, const VpLane &ln, int k) {
     return sk.arena + ((size_t) ln.vbase + (size_t) k) * 4;
+}
+__device__ __forceinline__ float4 *vp_nee_record(const VpSink &sk, const VpLane &ln, int i) {
+    return sk.arena + ((size_t) ln.vbase + (size_t) sk.vcap) * 4 + i;
 }
 
 // end of pass 2 (or of a render-only path)
@@ -190,7 +197,7 @@ __device__ __forceinline__ void vp_load(VpLane &ln, const VpSink &sk, const Path
     ln.depth = 0;
     ln.last_pdf = 1.f;
     ln.flags = VF_HEAD;
-    ln.vbase = slot * sk.vcap;
+    ln.vbase = slot * (sk.vcap + kNeeCap / 4);
     ln.nvert = 0; ln.vk = 0;
     ln.ev = EV_COLL;
 }
@@ -232,7 +239,7 @@ __device__ __forceinline__ void vp_post_vertex(const SceneK &S, VpLane &ln, VpSi
 
 // pass 1: the shadow ray ended — its contribution (:401-404, :225), the vertex record, then the path continues
 template <bool BW>
-__device__ __forceinline__ void vp_nee_done(const SceneK &S, VpLane &ln, VpSink &sk) {
+__device__ __forceinline__ void vp_nee_done(const SceneK &S, const GridK &G, VpLane &ln, VpSink &sk) {
     V3 wi = mk3(-ln.d.x, -ln.d.y, -ln.d.z);
     V3 emitted = mk3(S.env_over_pdf[0], S.env_over_pdf[1], S.env_over_pdf[2]) * splat3(ln.tr_acc);
     float phase_val = phase_eval(S, wi, ln.nd);                       // :401
@@ -242,6 +249,20 @@ __device__ __forceinline__ void vp_nee_done(const SceneK &S, VpLane &ln, VpSink 
         float4 *r = vp_record(sk, ln, ln.nvert - 1);
         r[2] = make_float4(__uint_as_float((uint32_t) ln.saved), __uint_as_float((uint32_t) (ln.saved >> 32)), ln.nee.x, ln.nee.y);
         r[3] = make_float4(ln.nee.z, ln.nd.x, ln.nd.y, ln.nd.z);
+        if (!(ln.flags & VF_NEE_OVF)) {
+            // transmittance gradients of the shadow ray (:406-414, :496-505) from the recorded collisions: the same
+            // values the replay in pass 2 would compute, scattered now
+            const V3 adjoint = ln.dL * ln.nee;                        // :412
+            const int n = __float_as_int(ln.running_t);
+            for (int i = 0; i < n; ++i) {
+                float4 c = *vp_nee_record(sk, ln, i);
+                float g = 0.f;
+                g += adjoint.x * c.w; g += adjoint.y * c.w; g += adjoint.z * c.w;
+                scatter_sigma_t(S, G, sk.D, mk3(c.x, c.y, c.z), g, sk.cnt);
+            }
+            r[1].w = __uint_as_float(__float_as_uint(r[1].w) | VR_NEE_DONE);
+        }
+        ln.flags &= ~VF_NEE_OVF;
     }
     ln.flags &= ~VF_IN_NEE;
     vp_post_vertex<BW>(S, ln, sk, true);
@@ -286,6 +307,15 @@ __device__ __forceinline__ void vp_collide(const SceneK &S, const GRID &G, float
         float tr = (ce != 0.f) ? (sn * inv_mu) : sn;                  // :486-489
         if (m.t > ln.rmaxt) m.t = inf_();                             // :493
         if (!(m.t < inf_())) { ln.flags |= VF_POSTNEE; ln.ev = EV_SLOW; return; }  // :494
+        if (BW && !(ln.flags & VF_ADJ)) {
+            // pass 1 of the adjoint: remember this tentative collision.  Its gradient, adjoint * d log(tr) / d sigma_t
+            // (:496-505), needs the finished shadow ray's contribution; it is scattered when the ray ends (vp_nee_done)
+            // instead of replaying the ray in pass 2.  running_t is idle during a shadow ray: it counts the records.
+            int n = __float_as_int(ln.running_t);
+            if (n < kNeeCap) *vp_nee_record(sk, ln, n) = make_float4(m.p.x, m.p.y, m.p.z, (tr > 0.f) ? ((-inv_mu) / tr) : 0.f);
+            else ln.flags |= VF_NEE_OVF;
+            ln.running_t = __int_as_float(n + 1);
+        }
         if (BW && (ln.flags & VF_REPLAY)) {                           // :496-505
             V3 adjoint = ln.dL * ln.nee;                              // :412
             float g = 0.f;
@@ -314,12 +344,12 @@ __device__ __forceinline__ void vp_collide(const SceneK &S, const GRID &G, float
 
 // the batched slow step (see the header comment)
 template <bool BW>
-__device__ __forceinline__ void vp_slow(const SceneK &S, VpLane &ln, VpSink &sk) {
+__device__ __forceinline__ void vp_slow(const SceneK &S, const GridK &G, VpLane &ln, VpSink &sk) {
     if (ln.flags & VF_POSTNEE) {
         ln.flags &= ~VF_POSTNEE;
         ln.ev = EV_COLL;
         if (BW && (ln.flags & VF_ADJ)) vp_replay_done(ln, sk);
-        else vp_nee_done<BW>(S, ln, sk);
+        else vp_nee_done<BW>(S, G, ln, sk);
     } else {
         ln.flags &= ~VF_END;
         vp_end_pass<BW>(S, ln, sk);
@@ -354,8 +384,9 @@ __device__ __forceinline__ void vp_vertex1(const SceneK &S, const GridK &G, VpLa
         ln.nd = uniform_sphere(s2x, s2y);
         ln.id = rcp3(ln.nd);
         ln.flags |= VF_IN_NEE;
+        ln.running_t = __int_as_float(0);                             // shadow-ray collision records (vp_collide)
         ln.ev = EV_COLL;
-        if (!vp_nee_start(S, ln)) vp_nee_done<BW>(S, ln, sk);
+        if (!vp_nee_start(S, ln)) vp_nee_done<BW>(S, G, ln, sk);
         return;
     }
     vp_post_vertex<BW>(S, ln, sk, active);
@@ -404,6 +435,13 @@ __device__ __forceinline__ void vp_vertex2(const SceneK &S, const GridK &G, VpLa
             float t = pcg_f32(ln.alt) * interval;                     // :608
             scatter_sigma_t(S, G, sk.D, ray_at(ln.o, ln.d, t), g, sk.cnt);
         }
+    }
+    if (vf & VR_NEE_DONE) {                                           // the shadow ray's gradients were scattered in pass 1
+        float4 r2 = r[2], r3 = r[3];
+        ln.nee = mk3(r2.z, r2.w, r3.x);
+        ln.result = ln.result - ln.nee;                               // :227
+        vp_next_vertex(ln, sk);
+        return;
     }
     if (vf & VR_NEE) {                                                // :406-414: replay with the cloned sampler
         float4 r2 = r[2], r3 = r[3];

@@ -117,7 +117,7 @@ void run_vps(const SceneK &S, const GRID &G, VpSink &sk) {
     const float inv_mu = 1.f / mu;
     uint64_t n = (uint64_t) S.W * S.H * sk.spp;
     HostQueue hq(n);
-    std::vector<float4> arena((size_t) 4 * (S.max_depth + 1));       // one arena slot: the lanes run one after the other
+    std::vector<float4> arena((size_t) 4 * (S.max_depth + 1) + kNeeCap);       // one arena slot: the lanes run one after the other
     sk.arena = arena.data(); sk.vcap = (uint32_t) S.max_depth + 1u;
     for (uint64_t idx = 0; idx < n; ++idx) {
         VpLane ln; ln.ev = EV_INIT; ln.flags = 0;
@@ -142,7 +142,7 @@ void run_vps(const SceneK &S, const GRID &G, VpSink &sk) {
             } else if (ln.ev == EV_SCAT) {
                 vp_vertex<BW>(S, G, ln, sk);
             } else {
-                vp_slow<BW>(S, ln, sk);
+                vp_slow<BW>(S, G, ln, sk);
             }
         }
     }
