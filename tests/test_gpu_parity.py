@@ -484,3 +484,21 @@ def test_gaussian_reconstruction_filter(oracle, gpu_ctx, tracer):
     with pytest.raises(RcvError):
         gpu_ctx.set_scene(bad)
     gpu_ctx.set_tracer(3)
+
+
+@pytest.mark.parametrize("tracer", [0, 3])
+def test_long_shadow_rays_fall_back_to_the_replay(oracle, gpu_ctx, tracer):
+    """Dense medium (scale 150): shadow rays with more than 64 tentative collisions overflow their record buffer and are
+    replayed in pass 2 instead (volpathsimple.py:406-414); gradients still within tolerance."""
+    d = small_scene(width=20, height=16, max_depth=6, rr_depth=3, sigma_t_scale=150.0).to_desc()
+    old, new = media(10, "dense")
+    mn = oracle.OracleMedium(d, *new)
+    gpu_ctx.set_tracer(tracer)
+    gpu_ctx.set_scene(d)
+    gpu_set_states(gpu_ctx, old, new)
+    gimg = np.full((d.film_height, d.film_width, 3), 1e-3, np.float32)
+    gs, ga = oracle.vps_backward(d, mn, 71, 2, gimg, threads=1)
+    gpu_ctx.grad_zero(); gpu_ctx.render_backward(71, 2, to_cuda(gimg))
+    ggs, gga = gpu_ctx.grad_read()
+    assert rel_l2(ggs.cpu().numpy(), gs) < GRAD_TOL and rel_l2(gga.cpu().numpy(), ga) < GRAD_TOL
+    gpu_ctx.set_tracer(3)

@@ -189,3 +189,24 @@ def test_gaussian_filter_event_machines(oracle, emu):
     emu.emu_vps(C.addressof(d), sn, an, *sn.shape[:3], 33, 2, 1, oracle.alt_seed(33), gimg.ctypes.data, film_w.ctypes.data, acc, g1, g4, cnt)
     gs, ga = oracle.vps_backward(d, mn, 33, 2, gimg, threads=1, film_w=film_w)
     assert rel_l2(g1, gs) < 1e-5 and rel_l2(g4[..., 0:3], ga) < 1e-5
+
+
+def test_long_shadow_rays_fall_back_to_the_replay(oracle, emu):
+    """A dense medium (scale 150): shadow rays with more tentative collisions than the 64 records a slot holds take the
+    fall-back — the replay of the ray in pass 2 with the parked sampler (volpathsimple.py:406-414) — and the gradients
+    still match the oracle."""
+    d = small_scene(16, 12, max_depth=6, rr_depth=3, sigma_t_scale=150.0).to_desc()
+    (so, ao), (sn, an) = media(10, "dense")
+    mn = oracle.OracleMedium(d, sn, an)
+    H, W = d.film_height, d.film_width
+    gimg = np.full((H, W, 3), 1e-3, np.float32)
+    film_w = oracle.film_weights(d, 71, 2)
+    acc = np.zeros((H, W, 4), np.float32); g1 = np.zeros((*sn.shape[:3], 1), np.float32); g4 = np.zeros((*sn.shape[:3], 4), np.float32)
+    cnt = np.zeros(8, np.uint64)
+    emu.emu_vps(C.addressof(d), sn, an, *sn.shape[:3], 71, 2, 1, oracle.alt_seed(71), gimg.ctypes.data, film_w.ctypes.data, acc, g1, g4, cnt)
+    oracle.counters(True)
+    gs, ga = oracle.vps_backward(d, mn, 71, 2, gimg, threads=1, film_w=film_w)
+    oc = oracle.counters(True)
+    assert [int(v) for v in cnt[3:7]] == [int(v) for v in oc[3:7]]
+    assert int(oc[2]) / max(1, int(oc[3])) > 40        # dense enough: tens of tentative collisions per vertex
+    assert rel_l2(g1, gs) < 1e-5 and rel_l2(g4[..., 0:3], ga) < 1e-5
