@@ -45,6 +45,36 @@ __global__ void __launch_bounds__(kBlock) k_rotate(const float *__restrict__ sig
         block_max[blockIdx.x] = m;
     }
 }
+// the same, four voxels per thread with 16-byte accesses only (needs 16-byte aligned inputs; the scalar kernel above
+// takes the tail and unaligned callers).  block_max slots [gridDim.x, 2 gridDim.x) of the scalar launch are not used.
+__global__ void __launch_bounds__(kBlock) k_rotate4(const float4 *__restrict__ sigma_in4, const float4 *__restrict__ albedo_in4,
+                                                    size_t nquad, float4 *__restrict__ sig2q, float4 *__restrict__ alb2,
+                                                    float *__restrict__ block_max) {
+    float mx = -inf_();
+    for (size_t q = (size_t) blockIdx.x * kBlock + threadIdx.x; q < nquad; q += (size_t) gridDim.x * kBlock) {
+        const float4 s_in = __ldg(sigma_in4 + q);
+        const float4 a0 = __ldg(albedo_in4 + 3 * q), a1 = __ldg(albedo_in4 + 3 * q + 1), a2 = __ldg(albedo_in4 + 3 * q + 2);
+        const float4 s01 = sig2q[2 * q], s23 = sig2q[2 * q + 1];          // (old0, new0, old1, new1), (old2, new2, old3, new3)
+        float4 n0 = alb2[8 * q + 1], n1 = alb2[8 * q + 3], n2 = alb2[8 * q + 5], n3 = alb2[8 * q + 7];
+        sig2q[2 * q] = make_float4(s01.y, s_in.x, s01.w, s_in.y);
+        sig2q[2 * q + 1] = make_float4(s23.y, s_in.z, s23.w, s_in.w);
+        alb2[8 * q] = n0; alb2[8 * q + 1] = make_float4(a0.x, a0.y, a0.z, 0.f);
+        alb2[8 * q + 2] = n1; alb2[8 * q + 3] = make_float4(a0.w, a1.x, a1.y, 0.f);
+        alb2[8 * q + 4] = n2; alb2[8 * q + 5] = make_float4(a1.z, a1.w, a2.x, 0.f);
+        alb2[8 * q + 6] = n3; alb2[8 * q + 7] = make_float4(a2.y, a2.z, a2.w, 0.f);
+        mx = fmax_(mx, fmax_(fmax_(s_in.x, s_in.y), fmax_(s_in.z, s_in.w)));
+    }
+    __shared__ float red[kBlock / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax_(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m = red[0];
+        for (int i = 1; i < kBlock / 32; ++i) m = fmax_(m, red[i]);
+        block_max[blockIdx.x] = m;
+    }
+}
 __global__ void k_majorant_final(const float *block_max, int n_blocks, float scale, float *majorants) {
     // one warp; majorants[0] (old) <- majorants[1] (new); new <- scale * max
     float mx = -inf_();
@@ -79,7 +109,19 @@ cudaError_t launch_rotate(const LaunchCfg &cfg, const float *sigma_in, const flo
                           float2 *sig2, float4 *blk2, float4 *blk1, float4 *alb2, float *block_max, int n_blocks,
                           float *majorants) {
     size_t nvox = (size_t) nz * ny * nx, ncell = (size_t) (nz + 1) * (ny + 1) * (nx + 1);
-    k_rotate<<<n_blocks, kBlock, 0, cfg.stream>>>(sigma_in, albedo_in, nvox, sig2, alb2, block_max);
+    const bool aligned = ((((uintptr_t) sigma_in) | ((uintptr_t) albedo_in)) & 15u) == 0 && nvox >= 4;
+    if (aligned && n_blocks >= 2) {
+        // four voxels per thread; the (< 4 voxel) tail goes through the scalar kernel with one block
+        const size_t nquad = nvox / 4, tail = nvox - 4 * nquad;
+        const int nb = n_blocks - 1;
+        k_rotate4<<<nb, kBlock, 0, cfg.stream>>>((const float4 *) sigma_in, (const float4 *) albedo_in, nquad, (float4 *) sig2, alb2,
+                                                 block_max);
+        k_rotate<<<1, kBlock, 0, cfg.stream>>>(sigma_in + 4 * nquad, albedo_in + 12 * nquad, tail, sig2 + 4 * nquad, alb2 + 8 * nquad,
+                                               block_max + nb);
+        (*cfg.launches)++;
+    } else {
+        k_rotate<<<n_blocks, kBlock, 0, cfg.stream>>>(sigma_in, albedo_in, nvox, sig2, alb2, block_max);
+    }
     k_majorant_final<<<1, 32, 0, cfg.stream>>>(block_max, n_blocks, scale, majorants);
     k_build_bricks<<<grid_for(cfg, ncell, 16), kBlock, 0, cfg.stream>>>(sig2, nx, ny, nz, blk2, blk1);
     (*cfg.launches) += 3;
@@ -326,11 +368,50 @@ __global__ void __launch_bounds__(kBlock) k_adam_packed(const float *__restrict_
         }
     }
 }
+// the same with 16-byte accesses only: sigma_t four voxels at a time, then albedo as a flat array of 3 nvox floats, four
+// elements (of one or two voxels) at a time.  Needs nvox % 4 == 0 and 16-byte aligned arrays.
+__global__ void __launch_bounds__(kBlock) k_adam_packed4(const float4 *__restrict__ gsig4, const float4 *__restrict__ galb, size_t nvox,
+                                                         float4 *sigma4, float4 *albedo4, float4 *m_s4, float4 *v_s4, float4 *m_a4,
+                                                         float4 *v_a4, float lr_t_s, float lr_t_a, float b1, float b2, float eps,
+                                                         float slo, float shi, float alo, float ahi) {
+    const size_t tid = (size_t) blockIdx.x * kBlock + threadIdx.x, stride = (size_t) gridDim.x * kBlock;
+    for (size_t q = tid; q < nvox / 4; q += stride) {
+        float4 p = sigma4[q], g = __ldg(gsig4 + q), m = m_s4[q], v = v_s4[q];
+        p.x = fmin_(fmax_(adam_elem(p.x, g.x, m.x, v.x, lr_t_s, b1, b2, eps), slo), shi);
+        p.y = fmin_(fmax_(adam_elem(p.y, g.y, m.y, v.y, lr_t_s, b1, b2, eps), slo), shi);
+        p.z = fmin_(fmax_(adam_elem(p.z, g.z, m.z, v.z, lr_t_s, b1, b2, eps), slo), shi);
+        p.w = fmin_(fmax_(adam_elem(p.w, g.w, m.w, v.w, lr_t_s, b1, b2, eps), slo), shi);
+        sigma4[q] = p; m_s4[q] = m; v_s4[q] = v;
+    }
+    for (size_t q = tid; q < 3 * (nvox / 4); q += stride) {
+        // elements 4q .. 4q+3 of the (nvox, 3) albedo array: voxel e / 3, channel e % 3
+        const size_t e0 = 4 * q, v0 = e0 / 3;
+        const int c0 = (int) (e0 - 3 * v0);
+        const float4 ga = __ldg(galb + v0), gb = __ldg(galb + (v0 + 1 < nvox ? v0 + 1 : v0));
+        float g0, g1, g2, g3;
+        if (c0 == 0) { g0 = ga.x; g1 = ga.y; g2 = ga.z; g3 = gb.x; }
+        else if (c0 == 1) { g0 = ga.y; g1 = ga.z; g2 = gb.x; g3 = gb.y; }
+        else { g0 = ga.z; g1 = gb.x; g2 = gb.y; g3 = gb.z; }
+        float4 p = albedo4[q], m = m_a4[q], v = v_a4[q];
+        p.x = fmin_(fmax_(adam_elem(p.x, g0, m.x, v.x, lr_t_a, b1, b2, eps), alo), ahi);
+        p.y = fmin_(fmax_(adam_elem(p.y, g1, m.y, v.y, lr_t_a, b1, b2, eps), alo), ahi);
+        p.z = fmin_(fmax_(adam_elem(p.z, g2, m.z, v.z, lr_t_a, b1, b2, eps), alo), ahi);
+        p.w = fmin_(fmax_(adam_elem(p.w, g3, m.w, v.w, lr_t_a, b1, b2, eps), alo), ahi);
+        albedo4[q] = p; m_a4[q] = m; v_a4[q] = v;
+    }
+}
 cudaError_t launch_adam_packed(const LaunchCfg &cfg, const GradK &D, size_t nvox, float *sigma, float *albedo, float *m_s,
                                float *v_s, float *m_a, float *v_a, float lr_t_s, float lr_t_a, float beta1, float beta2,
                                float eps, float slo, float shi, float alo, float ahi) {
-    k_adam_packed<<<grid_for(cfg, nvox), kBlock, 0, cfg.stream>>>(D.gsig, D.galb, nvox, sigma, albedo, m_s, v_s, m_a, v_a, lr_t_s, lr_t_a,
-                                                                   beta1, beta2, eps, slo, shi, alo, ahi);
+    const uintptr_t bits = (uintptr_t) D.gsig | (uintptr_t) sigma | (uintptr_t) albedo | (uintptr_t) m_s | (uintptr_t) v_s |
+                           (uintptr_t) m_a | (uintptr_t) v_a;
+    if (nvox % 4 == 0 && (bits & 15u) == 0)
+        k_adam_packed4<<<grid_for(cfg, nvox), kBlock, 0, cfg.stream>>>((const float4 *) D.gsig, D.galb, nvox, (float4 *) sigma,
+                                                                      (float4 *) albedo, (float4 *) m_s, (float4 *) v_s, (float4 *) m_a,
+                                                                      (float4 *) v_a, lr_t_s, lr_t_a, beta1, beta2, eps, slo, shi, alo, ahi);
+    else
+        k_adam_packed<<<grid_for(cfg, nvox), kBlock, 0, cfg.stream>>>(D.gsig, D.galb, nvox, sigma, albedo, m_s, v_s, m_a, v_a, lr_t_s,
+                                                                       lr_t_a, beta1, beta2, eps, slo, shi, alo, ahi);
     (*cfg.launches)++;
     return cudaGetLastError();
 }
