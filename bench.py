@@ -51,8 +51,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--rfilter", default="box", choices=["box", "gaussian"], help="reconstruction filter of the film (headline: box)")
-    ap.add_argument("--supergrid", type=int, default=8,
-                    help="also time the same iteration with a majorant supergrid of this factor (0 = skip); reported under `supergrid`")
+    ap.add_argument("--supergrid", type=int, nargs="*", default=[8, 32],
+                    help="also time the same iteration with majorant supergrids of these factors (none = skip); reported under "
+                         "`supergrid` (8 = what the reference's utils.adjust_majorant_res_factor picks, 32 = what suits these kernels)")
     ap.add_argument("--cpu-sample-spp", type=int, default=0, help="spp range of the CPU sample (0 = auto: ~15 s of CPU work)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target duration of one CPU sample")
     return ap.parse_args()
@@ -363,9 +364,9 @@ def run_ours(a):
                 "frac_of_gather_peak": (kernels[dom]["gbs"] / gather_peak) if gather_peak else None}
 
     # ---- the same iteration with the majorant supergrid + DDA (reference `use_majorant_supergrid`), informational
-    supergrid = None
-    if a.supergrid > 1 and a.grid % a.supergrid == 0:
-        ctx.set_majorant_factor(a.supergrid)
+    supergrid = []
+    for sg_f in [f for f in a.supergrid if f > 1 and a.grid % f == 0]:
+        ctx.set_majorant_factor(sg_f)
         step(a.warmup + a.steps); barrier(); ctx.counters(True)
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n_sg = max(2, min(a.steps, 3))
@@ -378,10 +379,10 @@ def run_ours(a):
         if world > 1:
             dist.all_reduce(tsg, op=dist.ReduceOp.MAX)
         sg_ms = float(tsg.item())
-        supergrid = {"factor": a.supergrid, "ms_per_step": sg_ms, "value": paths_per_step / (sg_ms * 1e-3) / 1e6, "unit": UNIT,
-                     "twostate_collisions": sg_cnt[0], "adjoint_collisions": sg_cnt[2],
-                     "note": "same workload, free flights sampled by DDA through the majorant supergrid (not the headline config)"}
-        ctx.set_majorant_factor(0)
+        supergrid.append({"factor": sg_f, "ms_per_step": sg_ms, "value": paths_per_step / (sg_ms * 1e-3) / 1e6, "unit": UNIT,
+                          "twostate_collisions": sg_cnt[0], "adjoint_collisions": sg_cnt[2],
+                          "note": "same workload, free flights sampled by DDA through the majorant supergrid (not the headline config)"})
+    ctx.set_majorant_factor(0)
 
     # ---- end to end through the host-buffer C-ABI call (pinned host memory, copies inside the timed region)
     e2e = None

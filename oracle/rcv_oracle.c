@@ -419,53 +419,58 @@ static inline float majorant2_at(const rcv_scene_desc *S, const orc_medium *Mo, 
 }
 
 /* DDA free-flight sampling through the supergrid (twostatemedium.py:25-70; Medium::prepare_dda_traversal and the
- * identical single-state loop of Medium::sample_interaction are [UPSTREAM]).  Returns the sampled t or inf. */
+ * identical single-state loop of Medium::sample_interaction are [UPSTREAM]).  Returns the sampled t (or inf) and, in
+ * *maj_out, the majorant of the cell the sample fell into.
+ * [SPEC] The traversal is the classic incremental one the reference's code was adapted from (fast voxel traversal):
+ * the supercell index is carried along and advanced by +-1 on the axis whose boundary is crossed, instead of being
+ * recovered from the midpoint of every interval (:53) — same cells except where float rounding puts a midpoint on the
+ * other side of a boundary, where the one-voxel margin of the supergrid keeps either majorant valid — and the majorant
+ * used for the collision weights is that of the stopping cell (:82-86 looks it up again at the sampled point). */
 static float dda_sample(const rcv_scene_desc *S, const orc_medium *Mo, const orc_medium *Mn, const ray_t *ray,
-                        float mint, float maxt, float desired_tau) {
-    /* prepare_dda_traversal: the ray in the unit cube of the supergrid */
+                        float mint, float maxt, float desired_tau, float *maj_out) {
     float o[3] = {ray->o.x, ray->o.y, ray->o.z}, d[3] = {ray->d.x, ray->d.y, ray->d.z};
     int res[3] = {Mn->mx, Mn->my, Mn->mz};
     float tmax3[3], tdelta[3];
+    int cell[3], step[3];
     for (int a = 0; a < 3; ++a) {
-        float ext_inv = 1.f / (S->bbox_max[a] - S->bbox_min[a]);
+        float ext = S->bbox_max[a] - S->bbox_min[a];
+        float ext_inv = 1.f / ext;
         float lo = (o[a] - S->bbox_min[a]) * ext_inv, ld = d[a] * ext_inv;
         float fres = (float) res[a], voxel = 1.f / fres;
-        int cur = (int) floorf(fmaf(ld, mint, lo) * fres);       /* [SPEC] p * res instead of p / voxel_size */
-        int last = (int) floorf(fmaf(ld, maxt, lo) * fres);
+        int cur = (int) floorf(fmaf(ld, mint, lo) * fres);
         cur = cur < 0 ? 0 : (cur > res[a] - 1 ? res[a] - 1 : cur);
-        last = last < 0 ? 0 : (last > res[a] - 1 ? res[a] - 1 : last);
-        int step = (ld >= 0.f) ? 1 : -1;
-        float nb = (float) (cur + step) * voxel;
-        if (cur != last && ld < 0.f) nb += voxel;
+        cell[a] = cur;
+        step[a] = (ld >= 0.f) ? 1 : -1;
+        float nb = (float) (cur + (ld >= 0.f ? 1 : 0)) * voxel;  /* the boundary ahead */
         if (ld != 0.f) {
-            float rld = 1.f / ld;                                /* [SPEC] one reciprocal per axis */
+            float rld = (1.f / d[a]) * ext;                      /* 1 / ld from the ray's cached reciprocal direction */
             tmax3[a] = (nb - lo) * rld;
-            tdelta[a] = ((float) step * voxel) * rld;
+            tdelta[a] = ((float) step[a] * voxel) * rld;
         } else {
             tmax3[a] = ORC_INF; tdelta[a] = ORC_INF;
         }
     }
-    float dda_t = mint, tau_acc = 0.f;
-    int reached = 0, active = 1;
-    while (active) {                                             /* :39-66 */
+    float dda_t = mint, tau_acc = 0.f, majorant = 0.f;
+    int reached = 0;
+    while (1) {                                                  /* :39-66 */
         float t_next = fminf_(fminf_(tmax3[0], tmax3[1]), tmax3[2]);
         int axis = (tmax3[0] == t_next) ? 0 : ((tmax3[1] == t_next) ? 1 : 2);   /* first axis that attains the minimum */
-        /* :53 looks the cell up at the midpoint of [dda_t, t_next].  In the last cell t_next can lie beyond the
-         * exit (prepare_dda_traversal puts the next boundary of an axis the ray no longer crosses one cell
-         * further), so the midpoint may leave the volume or the cell; [SPEC] clip the interval to maxt first. */
-        float tmid = 0.5f * (dda_t + fminf_(t_next, maxt));
-        float majorant = majorant2_at(S, Mo, Mn, ray_at(ray->o, ray->d, tmid));
+        size_t idx = ((size_t) cell[2] * Mn->my + cell[1]) * Mn->mx + cell[0];
+        majorant = Mn->majorant_grid[idx];
+        if (Mo) majorant = fmaxf_(Mo->majorant_grid[idx], majorant);
         float tau_next = tau_acc + (majorant * (t_next - dda_t));
-        /* :59-62; the division is only evaluated where its result can be used */
-        float t_precise = t_next;
-        if ((majorant > 0.f) && (tau_next >= desired_tau)) {
-            t_precise = dda_t + ((desired_tau - tau_acc) / majorant);
-            reached = t_precise < maxt;
+        if ((majorant > 0.f) && (tau_next >= desired_tau)) {     /* :59-62; the division only where it is used */
+            float t_precise = dda_t + ((desired_tau - tau_acc) / majorant);
+            if (t_precise < maxt) { dda_t = t_precise; reached = 1; break; }
         }
-        dda_t = reached ? t_precise : t_next;
-        active = !reached && (t_next < maxt);
-        if (active) { tmax3[axis] = tmax3[axis] + tdelta[axis]; tau_acc = tau_next; }
+        dda_t = t_next;
+        if (!(t_next < maxt)) break;
+        cell[axis] += step[axis];
+        if (cell[axis] < 0 || cell[axis] >= res[axis]) break;    /* left the supergrid (rounding at the exit) */
+        tmax3[axis] = tmax3[axis] + tdelta[axis];
+        tau_acc = tau_next;
     }
+    *maj_out = majorant;
     return reached ? dda_t : ORC_INF;                            /* :70 */
 }
 
@@ -473,7 +478,8 @@ static float dda_sample(const rcv_scene_desc *S, const orc_medium *Mo, const orc
 float orc_dda_sample(const rcv_scene_desc *S, const orc_medium *Mo, const orc_medium *Mn, const float o[3], const float d[3],
                      float mint, float maxt, float desired_tau) {
     ray_t r; r.o = V3(o[0], o[1], o[2]); r.d = V3(d[0], d[1], d[2]); r.maxt = maxt;
-    return dda_sample(S, Mo, Mn, &r, mint, maxt, desired_tau);
+    float mj;
+    return dda_sample(S, Mo, Mn, &r, mint, maxt, desired_tau, &mj);
 }
 
 typedef struct { uint64_t c[8]; } counters_t;
@@ -636,8 +642,9 @@ static void sample_interaction_twostates(const rcv_scene_desc *S, const orc_medi
     float combined_extinction, sampled_t;
     if (Mn->majorant_grid) {
         /* spatially varying majorant: DDA through max(old, new) supergrids (:25-70) */
-        sampled_t = active ? dda_sample(S, Mo, Mn, ray, mint, maxt, desired_tau) : ORC_INF;
-        combined_extinction = 0.f;
+        float mj = 0.f;
+        sampled_t = active ? dda_sample(S, Mo, Mn, ray, mint, maxt, desired_tau, &mj) : ORC_INF;
+        combined_extinction = (active && (sampled_t <= maxt)) ? mj : 0.f;   /* the stopping cell's (:82-86) */
     } else {
         /* single majorant for the whole volume (:71-78) */
         combined_extinction = fmaxf_(Mo->majorant, Mn->majorant);              /* :73-75 */
@@ -649,7 +656,6 @@ static void sample_interaction_twostates(const rcv_scene_desc *S, const orc_medi
     mei_t mn;
     mn.t = valid_mi ? sampled_t : ORC_INF;                                     /* :88 */
     mn.p = ray_at(ray->o, ray->d, sampled_t);                                  /* :89 */
-    if (Mn->majorant_grid && valid_mi) combined_extinction = majorant2_at(S, Mo, Mn, mn.p);   /* :82-86 */
     mn.mint = mint;
     v3 ss_o = V3(0, 0, 0), st_o = V3(0, 0, 0), ss_n = V3(0, 0, 0), st_n = V3(0, 0, 0);
     if (valid_mi) {
@@ -1126,9 +1132,9 @@ static void sample_interaction(const rcv_scene_desc *S, const orc_medium *M, con
     float mint, maxt;
     active = prepare_interaction_sampling(S, ray, active, &mint, &maxt);
     float desired_tau = -orc_logf(1.f - sample);
-    float m = M->majorant, sampled_t;
+    float m = M->majorant, sampled_t, m_cell = 0.f;
     if (M->majorant_grid) {
-        sampled_t = active ? dda_sample(S, NULL, M, ray, mint, maxt, desired_tau) : ORC_INF;
+        sampled_t = active ? dda_sample(S, NULL, M, ray, mint, maxt, desired_tau, &m_cell) : ORC_INF;
     } else {
         float inv_m = 1.f / m;                       /* [SPEC] reciprocal majorant */
         sampled_t = mint + (desired_tau * inv_m);
@@ -1137,7 +1143,7 @@ static void sample_interaction(const rcv_scene_desc *S, const orc_medium *M, con
     mei->t = valid ? sampled_t : ORC_INF;
     mei->p = ray_at(ray->o, ray->d, sampled_t);
     mei->mint = mint;
-    if (M->majorant_grid && valid) m = majorant_at(S, M, mei->p);   /* the local majorant at the sampled point */
+    if (M->majorant_grid && valid) m = m_cell;                      /* the local majorant of the stopping cell */
     v3 st = V3(0, 0, 0), ss = V3(0, 0, 0);
     if (valid) {
         tri_t T = tri_setup(S, M, mei->p);

@@ -558,19 +558,17 @@ __device__ __forceinline__ float majorant_at(const SceneK &S, const GridKS &G, V
     return (SEL == 1) ? m.x : ((SEL == 2) ? m.y : fmax_(m.x, m.y));
 }
 
-__device__ __forceinline__ void dda_axis(float o, float d, float bmin, float inv_ext, int res, float voxel, float mint, float maxt,
-                                         float &tmax, float &tdelta) {
+__device__ __forceinline__ void dda_axis(float o, float d, float id, float bmin, float bmax, float inv_ext, int res, float voxel,
+                                         float mint, int &cell, int &step, float &tmax, float &tdelta) {
     float lo = (o - bmin) * inv_ext, ld = d * inv_ext;
     float fres = (float) res;
     int cur = (int) floorf(__fmaf_rn(ld, mint, lo) * fres);
-    int last = (int) floorf(__fmaf_rn(ld, maxt, lo) * fres);
     cur = min(max(cur, 0), res - 1);
-    last = min(max(last, 0), res - 1);
-    int step = (ld >= 0.f) ? 1 : -1;
-    float nb = (float) (cur + step) * voxel;
-    if (cur != last && ld < 0.f) nb += voxel;
+    cell = cur;
+    step = (ld >= 0.f) ? 1 : -1;
+    float nb = (float) (cur + (ld >= 0.f ? 1 : 0)) * voxel;            // the boundary ahead
     if (ld != 0.f) {
-        float rld = 1.f / ld;
+        float rld = id * (bmax - bmin);                               // 1 / ld from the ray's cached reciprocal direction
         tmax = (nb - lo) * rld;
         tdelta = ((float) step * voxel) * rld;
     } else {
@@ -578,33 +576,37 @@ __device__ __forceinline__ void dda_axis(float o, float d, float bmin, float inv
     }
 }
 
-// sampled free-flight distance (or inf) for optical depth `tau` along o + t d, t in [mint, maxt]
+// Sampled free-flight distance (or inf) for optical depth `tau` along o + t d, t in [mint, maxt], and the majorant of the
+// cell the sample fell into.  Incremental traversal: the supercell index is carried and advanced by +-1 on the axis
+// whose boundary is crossed (the numerical specification of DESIGN.md §2; id = 1 / d).
 template <int SEL>
-__device__ __forceinline__ float dda_sample(const SceneK &S, const GridKS &G, V3 o, V3 d, float mint, float maxt, float tau) {
+__device__ __forceinline__ float dda_sample(const SceneK &S, const GridKS &G, V3 o, V3 d, V3 id, float mint, float maxt, float tau,
+                                            float &maj_out) {
     float tx, ty, tz, dx, dy, dz;
-    dda_axis(o.x, d.x, S.bmin[0], S.inv_ext[0], G.mx, G.vox[0], mint, maxt, tx, dx);
-    dda_axis(o.y, d.y, S.bmin[1], S.inv_ext[1], G.my, G.vox[1], mint, maxt, ty, dy);
-    dda_axis(o.z, d.z, S.bmin[2], S.inv_ext[2], G.mz, G.vox[2], mint, maxt, tz, dz);
-    float dda_t = mint, tau_acc = 0.f;
-    bool reached = false, active = true;
-    while (active) {
+    int cx, cy, cz, sx, sy, sz;
+    dda_axis(o.x, d.x, id.x, S.bmin[0], S.bmax[0], S.inv_ext[0], G.mx, G.vox[0], mint, cx, sx, tx, dx);
+    dda_axis(o.y, d.y, id.y, S.bmin[1], S.bmax[1], S.inv_ext[1], G.my, G.vox[1], mint, cy, sy, ty, dy);
+    dda_axis(o.z, d.z, id.z, S.bmin[2], S.bmax[2], S.inv_ext[2], G.mz, G.vox[2], mint, cz, sz, tz, dz);
+    float dda_t = mint, tau_acc = 0.f, majorant = 0.f;
+    bool reached = false;
+    while (true) {
         float t_next = fmin_(fmin_(tx, ty), tz);
         int axis = (tx == t_next) ? 0 : ((ty == t_next) ? 1 : 2);
-        float tmid = 0.5f * (dda_t + fmin_(t_next, maxt));
-        float majorant = majorant_at<SEL>(S, G, ray_at(o, d, tmid));
+        float2 m = __ldg(G.mgrid + ((size_t) cz * G.my + cy) * G.mx + cx);
+        majorant = (SEL == 1) ? m.x : ((SEL == 2) ? m.y : fmax_(m.x, m.y));
         float tau_next = tau_acc + (majorant * (t_next - dda_t));
-        float t_precise = t_next;
         if ((majorant > 0.f) && (tau_next >= tau)) {                  // the division only where its result can be used
-            t_precise = dda_t + ((tau - tau_acc) / majorant);
-            reached = t_precise < maxt;
+            float t_precise = dda_t + ((tau - tau_acc) / majorant);
+            if (t_precise < maxt) { dda_t = t_precise; reached = true; break; }
         }
-        dda_t = reached ? t_precise : t_next;
-        active = !reached && (t_next < maxt);
-        if (active) {
-            if (axis == 0) tx = tx + dx; else if (axis == 1) ty = ty + dy; else tz = tz + dz;
-            tau_acc = tau_next;
-        }
+        dda_t = t_next;
+        if (!(t_next < maxt)) break;
+        if (axis == 0) { cx += sx; if (cx < 0 || cx >= G.mx) break; tx = tx + dx; }
+        else if (axis == 1) { cy += sy; if (cy < 0 || cy >= G.my) break; ty = ty + dy; }
+        else { cz += sz; if (cz < 0 || cz >= G.mz) break; tz = tz + dz; }
+        tau_acc = tau_next;
     }
+    maj_out = majorant;
     return reached ? dda_t : inf_();
 }
 

@@ -47,7 +47,8 @@ __device__ __forceinline__ void sample_interaction2(const SceneK &S, const GRID 
     bool active = medium_interval(S, o, d, id, ray_maxt, mint, maxt);   // :22
     float tau = -spec_log(1.f - u);                                   // :24
     float t;
-    if constexpr (GRID::kSupergrid) t = active ? dda_sample<MODE>(S, G, o, d, mint, maxt, tau) : inf_();   // :25-70
+    float m_cell = 0.f;
+    if constexpr (GRID::kSupergrid) t = active ? dda_sample<MODE>(S, G, o, d, id, mint, maxt, tau, m_cell) : inf_();   // :25-70
     else t = mint + (tau * inv_mu);                                   // :78
     bool valid = active && (t <= maxt);                               // :80
     m.t = valid ? t : inf_();                                         // :88
@@ -60,7 +61,7 @@ __device__ __forceinline__ void sample_interaction2(const SceneK &S, const GRID 
         n_coll++;
         if (MODE == 1) m.sn = m.so;
         if (MODE == 2) m.so = m.sn;
-        if constexpr (GRID::kSupergrid) { m.mu = majorant_at<MODE>(S, G, m.p); m.inv_mu = 1.f / m.mu; }   // :82-86
+        if constexpr (GRID::kSupergrid) { m.mu = m_cell; m.inv_mu = 1.f / m.mu; }   // :82-86: the stopping cell's majorant
     }
 }
 

@@ -34,7 +34,8 @@ __device__ __forceinline__ void sample_interaction1(const SceneK &S, const GRID 
     bool active = medium_interval(S, o, d, id, ray_maxt, mint, maxt);
     float tau = -spec_log(1.f - u);
     float t;
-    if constexpr (GRID::kSupergrid) t = active ? dda_sample<2>(S, G, o, d, mint, maxt, tau) : inf_();
+    float m_cell = 0.f;
+    if constexpr (GRID::kSupergrid) t = active ? dda_sample<2>(S, G, o, d, id, mint, maxt, tau, m_cell) : inf_();
     else t = mint + (tau * inv_mu);
     m.valid = active && (t <= maxt);
     m.t = m.valid ? t : inf_();
@@ -45,7 +46,7 @@ __device__ __forceinline__ void sample_interaction1(const SceneK &S, const GRID 
         T = tri_setup(S, G, m.p);
         m.st = lookup_sigma1(S, G, T);
         cnt.coll++;
-        if constexpr (GRID::kSupergrid) { m.mu = majorant_at<2>(S, G, m.p); m.inv_mu = 1.f / m.mu; }
+        if constexpr (GRID::kSupergrid) { m.mu = m_cell; m.inv_mu = 1.f / m.mu; }
     }
 }
 // convenience overload for callers that do not need the interpolation set-up

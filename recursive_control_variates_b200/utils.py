@@ -55,10 +55,11 @@ class Stopwatch:
         return self.e0.elapsed_time(self.e1)
 
 
-def adjust_majorant_res_factor(scene, density_res):
+def adjust_majorant_res_factor(scene, density_res, res_factor=8):
     """utils.py:27-43: the largest factor <= 8 that leaves a supergrid of at least 4 cells per side, else none.
-    (Upstream requires the grid resolution to be divisible by the factor; so does rcv_medium_rotate.)"""
-    res_factor = 8
+    (Upstream requires the grid resolution to be divisible by the factor; so does rcv_medium_rotate.)  The start value
+    is the reference's; these kernels prefer coarser supergrids at high resolutions (256^3: factor 32 is 13 % faster
+    than no supergrid, factor 8 is 14 % slower — profiles/README.md), which `params["majorant_res_factor"]` selects."""
     min_side = int(min(density_res[:3]))
     while res_factor > 1 and (min_side // res_factor) < 4:
         res_factor -= 1
@@ -77,7 +78,7 @@ def initialize_parameters(params, opt, scene, scene_params):
             if "sigma_t" in key:
                 assert init_state.shape[-1] == 1
                 if params.get("use_majorant_supergrid", False):
-                    adjust_majorant_res_factor(scene, init_state.shape)        # utils.py:75-76
+                    adjust_majorant_res_factor(scene, init_state.shape, params.get("majorant_res_factor", 8))   # utils.py:75-76
             opt[key] = init_state
             scene_params[key] = opt[key]
             if "lr_factor" in param:
@@ -130,7 +131,7 @@ def upsample(scene, params, opt, integrator):
             raise ValueError(f"Upsampling expects a 4D tensor. Got {old.dim()}.")
         opt[key] = ctx.upsample2x(old.data.contiguous())
         if ".sigma_t." in key and params.get("use_majorant_supergrid", False):   # utils.py:187-188
-            adjust_majorant_res_factor(scene, opt[key].shape)
+            adjust_majorant_res_factor(scene, opt[key].shape, params.get("majorant_res_factor", 8))
     integrator.reset()
 
 
