@@ -320,17 +320,26 @@ int rcv_medium_rotate(rcv_ctx *c, const float *sigma_t_in, const float *albedo_i
     size_t nvox = (size_t) nz * ny * nx;
     LaunchCfg cfg = c->cfg();
     if (nz != c->nz || ny != c->ny || nx != c->nx) {
-        float2 *sig2; float4 *blk2, *blk1; float4 *alb2; float *grad; float *bm;
+        // new buffers are owned by `fresh` until every allocation (and the state transfer) has succeeded: an
+        // out-of-memory error half-way leaves the context as it was and leaks nothing
+        struct Fresh {
+            void *p[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+            ~Fresh() { for (void *q : p) cudaFree(q); }
+            void release() { for (void *&q : p) q = nullptr; }
+        } fresh;
         size_t ncell = (size_t) (nz + 1) * (ny + 1) * (nx + 1);
         size_t grad_floats = ((nvox + 3) / 4) * 4 + 4 * nvox;
-        CK(cudaMalloc(&sig2, nvox * sizeof(float2)));
-        CK(cudaMalloc(&blk2, 4 * ncell * sizeof(float4)));
-        CK(cudaMalloc(&blk1, 2 * ncell * sizeof(float4)));
-        CK(cudaMalloc(&alb2, 2 * nvox * sizeof(float4)));
-        CK(cudaMalloc(&grad, grad_floats * sizeof(float)));
+        CK(cudaMalloc(&fresh.p[0], nvox * sizeof(float2)));
+        CK(cudaMalloc(&fresh.p[1], 4 * ncell * sizeof(float4)));
+        CK(cudaMalloc(&fresh.p[2], 2 * ncell * sizeof(float4)));
+        CK(cudaMalloc(&fresh.p[3], 2 * nvox * sizeof(float4)));
+        CK(cudaMalloc(&fresh.p[4], grad_floats * sizeof(float)));
         uint64_t want = (nvox + 255) / 256, cap = (uint64_t) c->sm_count * 8;
         int nb = (int) (want < cap ? want : cap);
-        CK(cudaMalloc(&bm, nb * sizeof(float)));
+        CK(cudaMalloc(&fresh.p[5], nb * sizeof(float)));
+        float2 *sig2 = (float2 *) fresh.p[0];
+        float4 *blk2 = (float4 *) fresh.p[1], *blk1 = (float4 *) fresh.p[2], *alb2 = (float4 *) fresh.p[3];
+        float *grad = (float *) fresh.p[4], *bm = (float *) fresh.p[5];
         if (c->sig2 && nz == 2 * c->nz && ny == 2 * c->ny && nx == 2 * c->nx) {
             k_upsample_state<<<c->sm_count * 8, 256, 0, c->stream>>>(c->sig2, c->alb2, c->nz, c->ny, c->nx, sig2, alb2);
             c->launches++;
@@ -343,6 +352,7 @@ int rcv_medium_rotate(rcv_ctx *c, const float *sigma_t_in, const float *albedo_i
         }
         CK(cudaMemsetAsync(grad, 0, grad_floats * sizeof(float), c->stream));
         free_medium(c);
+        fresh.release();
         c->sig2 = sig2; c->blk2 = blk2; c->blk1 = blk1; c->alb2 = alb2; c->grad = grad; c->block_max = bm; c->n_rot_blocks = nb;
         c->nz = nz; c->ny = ny; c->nx = nx; c->nvox = nvox; c->grad_floats = grad_floats;
     }

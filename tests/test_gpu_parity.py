@@ -502,3 +502,22 @@ def test_long_shadow_rays_fall_back_to_the_replay(oracle, gpu_ctx, tracer):
     ggs, gga = gpu_ctx.grad_read()
     assert rel_l2(ggs.cpu().numpy(), gs) < GRAD_TOL and rel_l2(gga.cpu().numpy(), ga) < GRAD_TOL
     gpu_ctx.set_tracer(3)
+
+
+def test_out_of_memory_is_an_error_not_a_leak(oracle, gpu_ctx, setup):
+    """A grid that cannot be allocated (4096^3: 0.5 TB of packed state) is refused with a CUDA error; nothing leaks, the
+    context keeps its medium and renders as before."""
+    import torch
+    from recursive_control_variates_b200._abi import RcvError, check
+    d = setup["desc"]
+    gpu_ctx.set_scene(d)
+    gpu_set_states(gpu_ctx, setup["old"], setup["new"])
+    free_before = torch.cuda.mem_get_info()[0]
+    dummy = torch.zeros(16, device="cuda")
+    with pytest.raises(RcvError):
+        check(gpu_ctx.lib.rcv_medium_rotate(gpu_ctx._h, dummy.data_ptr(), dummy.data_ptr(), 4096, 4096, 4096))
+    torch.cuda.synchronize()
+    assert torch.cuda.mem_get_info()[0] >= free_before - (64 << 20)
+    ao, an = oracle.render_twostates_accum(d, setup["mo"], setup["mn"], seed=3, spp=1)
+    go, gn = gpu_ctx.render_twostates_accum(seed=3, spp=1)
+    assert np.array_equal(go.cpu().numpy(), ao) and np.array_equal(gn.cpu().numpy(), an)
