@@ -318,6 +318,8 @@ int rcv_medium_rotate(rcv_ctx *c, const float *sigma_t_in, const float *albedo_i
     if (c->maj_factor > 0 && (nz % c->maj_factor || ny % c->maj_factor || nx % c->maj_factor))
         return fail(RCV_ERR_ARG, "grid resolution must be divisible by the majorant resolution factor");
     size_t nvox = (size_t) nz * ny * nx;
+    if ((size_t) (nz + 1) * (ny + 1) * (nx + 1) > 0xffffffffull)
+        return fail(RCV_ERR_ARG, "grid too large: voxels and interpolation cells are indexed with 32 bits");
     LaunchCfg cfg = c->cfg();
     if (nz != c->nz || ny != c->ny || nx != c->nx) {
         // new buffers are owned by `fresh` until every allocation (and the state transfer) has succeeded: an

@@ -421,8 +421,8 @@ __device__ __forceinline__ Tri tri_setup(const SceneK &S, const GridK &G, V3 p) 
     tri_axis(p.z, S.bmin[2], S.inv_ext[2], G.nz, T.inside, T.z0, T.z1, T.cz, T.wz0, T.wz1);
     return T;
 }
-__device__ __forceinline__ size_t tri_cell(const GridK &G, const Tri &T) {
-    return ((size_t) T.cz * (G.ny + 1) + T.cy) * (G.nx + 1) + T.cx;
+__device__ __forceinline__ uint32_t tri_cell(const GridK &G, const Tri &T) {
+    return ((uint32_t) T.cz * (uint32_t) (G.ny + 1) + (uint32_t) T.cy) * (uint32_t) (G.nx + 1) + (uint32_t) T.cx;
 }
 // the 8 corner voxels of cell (cx,cy,cz) in brick order — used by the brick builder
 __host__ __device__ __forceinline__ size_t cell_corner(int nx, int ny, int nz, int cx, int cy, int cz, int k) {
@@ -443,11 +443,12 @@ __device__ __forceinline__ float tri_lerp(const Tri &T, float v0_, float v1_, fl
     float b1 = __fmaf_rn(T.wy0, a2, T.wy1 * a3);
     return __fmaf_rn(T.wz0, b0, T.wz1 * b1);
 }
-__device__ __forceinline__ void tri_rows(const GridK &G, const Tri &T, size_t r[4]) {
-    r[0] = ((size_t) T.z0 * G.ny + T.y0) * G.nx;
-    r[1] = ((size_t) T.z0 * G.ny + T.y1) * G.nx;
-    r[2] = ((size_t) T.z1 * G.ny + T.y0) * G.nx;
-    r[3] = ((size_t) T.z1 * G.ny + T.y1) * G.nx;
+__device__ __forceinline__ void tri_rows(const GridK &G, const Tri &T, uint32_t r[4]) {
+    const uint32_t ny = (uint32_t) G.ny, nx = (uint32_t) G.nx;
+    r[0] = ((uint32_t) T.z0 * ny + (uint32_t) T.y0) * nx;
+    r[1] = ((uint32_t) T.z0 * ny + (uint32_t) T.y1) * nx;
+    r[2] = ((uint32_t) T.z1 * ny + (uint32_t) T.y0) * nx;
+    r[3] = ((uint32_t) T.z1 * ny + (uint32_t) T.y1) * nx;
 }
 __device__ __forceinline__ float tri_weight(const Tri &T, int k) {
     float wx = (k & 1) ? T.wx1 : T.wx0;
@@ -455,11 +456,11 @@ __device__ __forceinline__ float tri_weight(const Tri &T, int k) {
     float wz = (k & 4) ? T.wz1 : T.wz0;
     return (wz * wy) * wx;
 }
-__device__ __forceinline__ size_t tri_voxel(const GridK &G, const Tri &T, int k) {
+__device__ __forceinline__ uint32_t tri_voxel(const GridK &G, const Tri &T, int k) {
     int x = (k & 1) ? T.x1 : T.x0;
     int y = (k & 2) ? T.y1 : T.y0;
     int z = (k & 4) ? T.z1 : T.z0;
-    return ((size_t) z * G.ny + y) * G.nx + x;
+    return ((uint32_t) z * (uint32_t) G.ny + (uint32_t) y) * (uint32_t) G.nx + (uint32_t) x;
 }
 
 // brick loads: read-only, one 256-bit load per 32 bytes (sm_100 LDG.256: half the load instructions and half the L1
@@ -484,7 +485,7 @@ __device__ __forceinline__ void ld_brick32(const float4 *p, float4 &a, float4 &b
 // both states' sigma_t (scale * grid) with one gather of 8 float2
 __device__ __forceinline__ void lookup_sigma2(const SceneK &S, const GridK &G, const Tri &T, float &s_old, float &s_new) {
     if (!T.inside) { s_old = 0.f; s_new = 0.f; return; }
-    const float4 *b = G.blk2 + 4 * tri_cell(G, T);
+    const float4 *b = G.blk2 + 4 * (size_t) tri_cell(G, T);
     float4 q0, q1, q2, q3;
     ld_brick32(b, q0, q1); ld_brick32(b + 2, q2, q3);                                // one 64-byte brick
     s_old = S.scale * tri_lerp(T, q0.x, q0.z, q1.x, q1.z, q2.x, q2.z, q3.x, q3.z);
@@ -493,7 +494,7 @@ __device__ __forceinline__ void lookup_sigma2(const SceneK &S, const GridK &G, c
 // state `new` only
 __device__ __forceinline__ float lookup_sigma1(const SceneK &S, const GridK &G, const Tri &T) {
     if (!T.inside) return 0.f;
-    const float4 *b = G.blk1 + 2 * tri_cell(G, T);
+    const float4 *b = G.blk1 + 2 * (size_t) tri_cell(G, T);
     float4 q0, q1;
     ld_brick32(b, q0, q1);                                                           // one 32-byte brick
     return S.scale * tri_lerp(T, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w);
@@ -511,13 +512,13 @@ __device__ __forceinline__ float4 ld_corner16(const float4 *p) {
 // albedo of state s (0 = old, 1 = new)
 __device__ __forceinline__ V3 lookup_albedo(const GridK &G, const Tri &T, int s) {
     if (!T.inside) return mk3(0, 0, 0);
-    size_t r[4];
+    uint32_t r[4];
     tri_rows(G, T, r);
     float4 v[8];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        v[2 * k] = ld_corner16(G.alb2 + 2 * (r[k] + T.x0) + s);
-        v[2 * k + 1] = ld_corner16(G.alb2 + 2 * (r[k] + T.x1) + s);
+        v[2 * k] = ld_corner16(G.alb2 + 2 * (size_t) (r[k] + T.x0) + s);
+        v[2 * k + 1] = ld_corner16(G.alb2 + 2 * (size_t) (r[k] + T.x1) + s);
     }
     return mk3(tri_lerp(T, v[0].x, v[1].x, v[2].x, v[3].x, v[4].x, v[5].x, v[6].x, v[7].x),
                tri_lerp(T, v[0].y, v[1].y, v[2].y, v[3].y, v[4].y, v[5].y, v[6].y, v[7].y),
@@ -526,13 +527,13 @@ __device__ __forceinline__ V3 lookup_albedo(const GridK &G, const Tri &T, int s)
 // both states' albedo: the two records of a voxel are adjacent, one 256-bit load per corner
 __device__ __forceinline__ void lookup_albedo2(const GridK &G, const Tri &T, V3 &a_old, V3 &a_new) {
     if (!T.inside) { a_old = mk3(0, 0, 0); a_new = mk3(0, 0, 0); return; }
-    size_t r[4];
+    uint32_t r[4];
     tri_rows(G, T, r);
     float4 o[8], n[8];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        ld_brick32(G.alb2 + 2 * (r[k] + T.x0), o[2 * k], n[2 * k]);
-        ld_brick32(G.alb2 + 2 * (r[k] + T.x1), o[2 * k + 1], n[2 * k + 1]);
+        ld_brick32(G.alb2 + 2 * (size_t) (r[k] + T.x0), o[2 * k], n[2 * k]);
+        ld_brick32(G.alb2 + 2 * (size_t) (r[k] + T.x1), o[2 * k + 1], n[2 * k + 1]);
     }
     a_old = mk3(tri_lerp(T, o[0].x, o[1].x, o[2].x, o[3].x, o[4].x, o[5].x, o[6].x, o[7].x),
                 tri_lerp(T, o[0].y, o[1].y, o[2].y, o[3].y, o[4].y, o[5].y, o[6].y, o[7].y),
@@ -636,8 +637,8 @@ __device__ __forceinline__ void prefetch_next_brick(const SceneK &S, const GridK
     float t = (-spec_log(1.f - u)) * inv_mu;
     Tri T = tri_setup(S, G, ray_at(p, d, t));
     if (T.inside) {
-        if (TWO) prefetch_l2(G.blk2 + 4 * tri_cell(G, T));
-        else prefetch_l2(G.blk1 + 2 * tri_cell(G, T));
+        if (TWO) prefetch_l2(G.blk2 + 4 * (size_t) tri_cell(G, T));
+        else prefetch_l2(G.blk1 + 2 * (size_t) tri_cell(G, T));
     }
 #endif
 }

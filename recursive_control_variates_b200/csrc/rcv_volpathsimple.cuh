@@ -60,7 +60,7 @@ __device__ __forceinline__ void sample_interaction1(const SceneK &S, const GRID 
 // AD of sigma_t(p) = scale * trilinear(grid): scatter w_corner * (scale * g) on a known interpolation set-up
 __device__ __forceinline__ void scatter_sigma_t_T(const GridK &G, const GradK &D, const Tri &T, float sg, VpsCounts &cnt) {
     if (!T.inside) return;
-    size_t r[4];
+    uint32_t r[4];
     tri_rows(G, T, r);
     const float wzy[4] = {T.wz0 * T.wy0, T.wz0 * T.wy1, T.wz1 * T.wy0, T.wz1 * T.wy1};
 #pragma unroll
@@ -192,7 +192,7 @@ __device__ __forceinline__ void vps_trace(const SceneK &S, const GRID &G, const 
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         float w = tri_weight(T, k);
-                        size_t v = tri_voxel(G, T, k);
+                        uint32_t v = tri_voxel(G, T, k);
                         red_add_f32(D.gsig + v, w * sg);
                         red_add_v4(D.galb + v, w * g_al.x, w * g_al.y, w * g_al.z, 0.f);
                     }

@@ -418,7 +418,7 @@ __device__ __forceinline__ void vp_vertex2(const SceneK &S, const GridK &G, VpLa
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 float w = tri_weight(T, k);
-                size_t v = tri_voxel(G, T, k);
+                uint32_t v = tri_voxel(G, T, k);
                 red_add_f32(sk.D.gsig + v, w * sg);
                 red_add_v4(sk.D.galb + v, w * g_al.x, w * g_al.y, w * g_al.z, 0.f);
             }

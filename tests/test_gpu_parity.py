@@ -505,7 +505,7 @@ def test_long_shadow_rays_fall_back_to_the_replay(oracle, gpu_ctx, tracer):
 
 
 def test_out_of_memory_is_an_error_not_a_leak(oracle, gpu_ctx, setup):
-    """A grid that cannot be allocated (4096^3: 0.5 TB of packed state) is refused with a CUDA error; nothing leaks, the
+    """A grid that cannot be allocated (1500^3: 0.3 TB of packed state) is refused with a CUDA error; nothing leaks, the
     context keeps its medium and renders as before."""
     import torch
     from recursive_control_variates_b200._abi import RcvError, check
@@ -515,6 +515,8 @@ def test_out_of_memory_is_an_error_not_a_leak(oracle, gpu_ctx, setup):
     free_before = torch.cuda.mem_get_info()[0]
     dummy = torch.zeros(16, device="cuda")
     with pytest.raises(RcvError):
+        check(gpu_ctx.lib.rcv_medium_rotate(gpu_ctx._h, dummy.data_ptr(), dummy.data_ptr(), 1500, 1500, 1500))
+    with pytest.raises(RcvError):           # 2^32 or more interpolation cells: refused before any allocation
         check(gpu_ctx.lib.rcv_medium_rotate(gpu_ctx._h, dummy.data_ptr(), dummy.data_ptr(), 4096, 4096, 4096))
     torch.cuda.synchronize()
     assert torch.cuda.mem_get_info()[0] >= free_before - (64 << 20)
