@@ -353,6 +353,9 @@ __global__ void __launch_bounds__(kWfBlock, RCV_VP_MINBLOCKS) k_vps_wavefront(co
 #ifndef RCV_POOL_MINBLOCKS
 #define RCV_POOL_MINBLOCKS 4
 #endif
+#ifndef RCV_TS_POOL_MINBLOCKS
+#define RCV_TS_POOL_MINBLOCKS RCV_POOL_MINBLOCKS
+#endif
 static constexpr int kPoolBlock = RCV_POOL_BLOCK;
 static constexpr int kPoolWarps = kPoolBlock / 32;
 
@@ -360,7 +363,7 @@ template <int WORDS>
 __host__ __device__ constexpr size_t pool_warp_floats() { return (size_t) WORDS * kPoolSlots + 2 * kPoolSlots / 4; }
 
 template <int MODE, class GRID>
-__global__ void __launch_bounds__(kPoolBlock, RCV_POOL_MINBLOCKS) k_twostates_pool(const __grid_constant__ SceneK S,
+__global__ void __launch_bounds__(kPoolBlock, RCV_TS_POOL_MINBLOCKS) k_twostates_pool(const __grid_constant__ SceneK S,
                                                                                    const __grid_constant__ GRID G, float4 *acc_old,
                                                                                    float4 *acc_new, PathQueue Q, Counters *C,
                                                                                    unsigned long long *work) {
