@@ -135,10 +135,20 @@ def upsample(scene, params, opt, integrator):
     integrator.reset()
 
 
+def save_img(img, output_dir, img_name, it):
+    """utils.py:8-14: <output_dir>/<img_name>/<it:04d>.exr (an uncompressed float32 OpenEXR file)."""
+    from .exrio import write_exr
+    filename = os.path.join(output_dir, img_name, f"{it:04d}.exr")
+    os.makedirs(os.path.dirname(filename), exist_ok=True)
+    write_exr(filename, img)
+    return filename
+
+
 def save_final_state(params, opt, output_dir):
     """utils.py:45-60: 4-D grids as Mitsuba `.vol` files (mi.VolumeGrid.write), everything else into
-    final_state.json; 3-D textures (EXR upstream) go to `.npy`."""
+    final_state.json; 3-D textures as `.exr` (mi.Bitmap.write upstream)."""
     import json
+    from .exrio import write_exr
     from .volio import write_vol
     os.makedirs(output_dir, exist_ok=True)
     final_state = {}
@@ -148,7 +158,7 @@ def save_final_state(params, opt, output_dir):
         if param.dim() == 4:
             write_vol(os.path.join(output_dir, f"{name}_final.vol"), param)
         elif param.dim() == 3:
-            np.save(os.path.join(output_dir, f"{name}_final.npy"), param.numpy())
+            write_exr(os.path.join(output_dir, f"{name}_final.exr"), param)
         else:
             final_state[key] = param.numpy().tolist()
     if final_state:

@@ -157,3 +157,23 @@ def test_vol_files_round_trip(tmp_path):
     assert np.array_equal(s, g[..., :1])
     import json
     assert json.load(open(str(tmp_path / "final_state.json"))) == {"m.scalar": [0.5]}
+
+
+def test_exr_files_round_trip(tmp_path):
+    """Uncompressed float32 scanline OpenEXR (utils.save_img, utils.py:8-14): header fields and pixel round trip."""
+    import struct
+    from recursive_control_variates_b200.exrio import read_exr, write_exr
+    from recursive_control_variates_b200.utils import save_img
+    rng = np.random.default_rng(1)
+    img = rng.random((5, 7, 3), dtype=np.float32)
+    path = save_img(img, str(tmp_path), "img", 12)
+    assert path.endswith("img/0012.exr")
+    raw = open(path, "rb").read()
+    assert struct.unpack_from("<ii", raw, 0) == (20000630, 2) and b"channels\0chlist\0" in raw and b"dataWindow\0box2i\0" in raw
+    back, names = read_exr(path)
+    assert names == ["B", "G", "R"] and np.array_equal(back[..., ::-1], img)          # stored alphabetically
+    write_exr(str(tmp_path / "y.exr"), img[..., 0])
+    y, n1 = read_exr(str(tmp_path / "y.exr"))
+    assert n1 == ["Y"] and np.array_equal(y[..., 0], img[..., 0])
+    # header length + offset table + scanlines
+    assert len(raw) == raw.index(b"screenWindowWidth") + len("screenWindowWidth\0float\0") + 4 + 4 + 1 + 8 * 5 + 5 * (8 + 4 * 7 * 3)
