@@ -129,6 +129,10 @@ class Film:
     def __init__(self, width: int, height: int):
         self.width, self.height = int(width), int(height)
 
+    def set_size(self, size):
+        """scene_params['sensor.film.size'] = size (utils.py:117-118,125-126)."""
+        self.width, self.height = int(size[0]), int(size[1])
+
     def size(self):
         return (self.width, self.height)
 

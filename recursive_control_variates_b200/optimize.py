@@ -10,7 +10,7 @@ import torch
 from . import mitsuba_compat as mi
 from . import plugins  # noqa: F401  (registers the integrators)
 from .utils import (Stopwatch, checkpoint, clamp, initialize_parameters, l1_loss, l2_loss, precondition, render_reference,
-                    save_final_state, upsample)
+                    render_display, save_final_state, upsample)
 
 
 def run_opt(params):
@@ -80,6 +80,9 @@ def run_opt(params):
     with torch.no_grad():
         scene_params.update(opt)
     if output_dir:
+        from .exrio import write_exr
+        img_final = render_display(params, scene, base_integrator)           # optimize.py:148-152
+        write_exr(os.path.join(output_dir, "img_final.exr"), img_final)
         save_final_state(params, opt, output_dir)
     result_dict["opt"] = opt
     return result_dict

@@ -97,6 +97,24 @@ def render_reference(params, scene, integrator):
     return img_ref
 
 
+def render_display(params, scene, integrator):
+    """utils.py:113-127: the final state at the visualisation resolution `final_res` (default: the training film),
+    averaged over ref_passes renders of spp_ref samples."""
+    film = scene.sensors()[0].film()
+    opt_res = film.size()
+    film.set_size(params.get("final_res", opt_res))
+    try:
+        img = None
+        with torch.no_grad():
+            for j in range(params.get("ref_passes", 1)):
+                part = mi.render(scene, seed=17843 + j, integrator=integrator, spp=params.get("spp_ref", params.get("spp", 1)))
+                part = part / params.get("ref_passes", 1)
+                img = part if img is None else img + part
+    finally:
+        film.set_size(opt_res)
+    return img
+
+
 def checkpoint(scene, params, i, integrator, loss_func, img, img_ref, result_dict):
     """utils.py:129-165: loss / variance against a higher-spp render every recomp_freq iterations."""
     recomp_freq = params.get("recomp_freq", 10)

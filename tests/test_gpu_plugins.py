@@ -189,3 +189,19 @@ def test_run_opt_loop_multiview(mi):
     res = run_opt(p)
     s = res["opt"]["object.interior_medium.sigma_t.data"]
     assert torch.isfinite(s).all() and np.isfinite(res["loss"]).all() and float((s - 0.04).abs().max()) > 0
+
+
+def test_run_opt_writes_the_reference_outputs(mi, tmp_path):
+    """optimize.py:145-155: img_final.exr at `final_res`, the optimised grids as Mitsuba .vol files."""
+    from recursive_control_variates_b200.exrio import read_exr
+    from recursive_control_variates_b200.optimize import run_opt
+    from recursive_control_variates_b200.volio import read_vol
+    p = _params("cv_ps")
+    p["output_dir"] = str(tmp_path / "out")
+    p["final_res"] = (48, 36)
+    res = run_opt(p)
+    img, names = read_exr(str(tmp_path / "out" / "img_final.exr"))
+    assert img.shape == (36, 48, 3) and names == ["B", "G", "R"] and np.isfinite(img).all() and img.mean() > 0
+    s, _, _ = read_vol(str(tmp_path / "out" / "object_interior_medium_sigma_t_data_final.vol"))
+    assert np.array_equal(s, res["opt"]["object.interior_medium.sigma_t.data"].detach().cpu().numpy())
+    assert p["scene"].sensors()[0].film().size() == (32, 24)               # the training film is restored
