@@ -116,14 +116,35 @@ def render_display(params, scene, integrator):
 
 
 def checkpoint(scene, params, i, integrator, loss_func, img, img_ref, result_dict):
-    """utils.py:129-165: loss / variance against a higher-spp render every recomp_freq iterations."""
+    """utils.py:129-165: loss / variance against a higher-spp render every recomp_freq iterations; with `save`, the
+    images of that iteration (EXR); at `bias_steps`, a ground-truth render of the current state."""
     recomp_freq = params.get("recomp_freq", 10)
     spp_inf = params.get("spp_inf", 64)
+    save = params.get("save", False) and params.get("output_dir")
+    output_dir = params.get("output_dir")
     if i % recomp_freq == 0:
         with torch.no_grad():
             img_inf = mi.render(scene, integrator=integrator.integrator, seed=i + 1, spp=spp_inf)
+            if save:
+                save_img(img_inf, output_dir, "img_inf", i // recomp_freq)
             result_dict["loss"][i // recomp_freq] = float(loss_func(img_ref, img_inf))
             result_dict["var"][i // recomp_freq] = float(torch.mean((img_inf - img.detach()) ** 2))
+        if save:
+            save_img(integrator.img, output_dir, "img", i // recomp_freq)
+            if params.get("method", "baseline") != "baseline" and integrator.stats.n > integrator.warmup:
+                save_img(integrator.w_s, output_dir, "weights", i // recomp_freq)
+                save_img(integrator.H, output_dir, "img_H", i // recomp_freq)
+                save_img(integrator.F, output_dir, "img_F", i // recomp_freq)
+    if "bias_steps" in params and i in params["bias_steps"] and output_dir:
+        with torch.no_grad():
+            ref_passes = params.get("ref_passes", 1)
+            spp_ref = params.get("spp_ref", params.get("spp", 1))
+            img_gt = None
+            for j in range(ref_passes):
+                part = mi.render(scene, seed=17843 + j, integrator=integrator, spp=spp_ref) / ref_passes
+                img_gt = part if img_gt is None else img_gt + part
+            save_img(img_gt, output_dir, "bias_gt", i)
+            save_img(img.detach(), output_dir, "bias_img", i)
 
 
 def precondition(params, opt):

@@ -199,7 +199,12 @@ def test_run_opt_writes_the_reference_outputs(mi, tmp_path):
     p = _params("cv_ps")
     p["output_dir"] = str(tmp_path / "out")
     p["final_res"] = (48, 36)
+    p["save"] = True; p["recomp_freq"] = 3; p["bias_steps"] = [2]
     res = run_opt(p)
+    out = tmp_path / "out"
+    for name in ("img_inf/0000.exr", "img/0001.exr", "weights/0001.exr", "img_H/0001.exr", "img_F/0001.exr", "bias_gt/0002.exr",
+                 "bias_img/0002.exr"):
+        assert (out / name).is_file(), name
     img, names = read_exr(str(tmp_path / "out" / "img_final.exr"))
     assert img.shape == (36, 48, 3) and names == ["B", "G", "R"] and np.isfinite(img).all() and img.mean() > 0
     s, _, _ = read_vol(str(tmp_path / "out" / "object_interior_medium_sigma_t_data_final.vol"))
