@@ -48,6 +48,9 @@ def parse():
     ap.add_argument("--spp", type=int, default=WORKLOAD["spp_per_gpu"], help="samples per pixel per GPU")
     ap.add_argument("--kind", default=WORKLOAD["kind"])
     ap.add_argument("--tracer", type=int, default=3, help="3 pool (default), 0 wavefront, 1 simple, 2 batch")
+    ap.add_argument("--use-drt", action="store_true",
+                    help="adjoint with volpathsimple's use_drt/subsampling/mis = True (reference default); the headline is "
+                         "use_drt=False, the configuration SURVEY.md 8(d) measures")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--rfilter", default="box", choices=["box", "gaussian"], help="reconstruction filter of the film (headline: box)")
@@ -61,7 +64,8 @@ def parse():
 
 def workload_name(a, n_gpus):
     return (f"synthetic {a.kind} {a.grid}^3 sigma_t+albedo two-state grid, {a.res}x{a.res}, {a.spp * n_gpus} spp "
-            f"({a.spp}/GPU), cv_ps, constant environment emitter, box filter, max_depth=rr_depth=64")
+            f"({a.spp}/GPU), cv_ps, constant environment emitter, box filter, max_depth=rr_depth=64, "
+            f"adjoint volpathsimple use_drt={bool(getattr(a, 'use_drt', False))}")
 
 
 # ----------------------------------------------------------------------------
@@ -215,6 +219,7 @@ def run_ours(a):
     ctx = Context(local)
     ctx.set_scene(desc)
     ctx.set_tracer(a.tracer)
+    ctx.set_drt(a.use_drt)
 
     # synthetic theta_{i-1}, theta_i and a target (generated on the host once; resident in HBM before timing)
     old, new = make_medium(a.grid, a.kind, 0.0), make_medium(a.grid, a.kind, 5e-3)

@@ -1295,28 +1295,149 @@ static void backpropagate_transmittance(const rcv_scene_desc *S, const orc_mediu
     }
 }
 
-/* volpathsimple.py:51-303; reach_medium :305-332 */
-static void vps_sample(const rcv_scene_desc *S, const orc_medium *M, int primal, pcg32 *rng, pcg32 *alt,
-                       ray_t ray, v3 dL, v3 state_in, float result_out[3], grad_sink *G, counters_t *cnt) {
+/* ------------------------------------------------------------------------- */
+/* DRT (differential ratio tracking) in-scattering term, volpathsimple.py:520-594,623-778.         */
+/* ORACLE ONLY so far: the CUDA path implements use_drt = False.                                                      */
+/* ------------------------------------------------------------------------- */
+typedef struct { int use_drt, use_drt_subsampling, use_drt_mis; } drt_opts;
+
+/* PathState / DRTPathState / DRTReservoir with n = 1 (:673-778) */
+typedef struct {
+    v3 wsum, current_weight;
+    int depth;              /* -1: never set */
+    si_t si; ray_t ray; int active;
+} drt_reservoir;
+static inline float mean3(v3 a) { return ((a.x + a.y) + a.z) / 3.f; }
+
+static void reservoir_update(drt_reservoir *R, int depth, si_t si, ray_t ray, v3 weight, float sample, int active) {   /* :757-765 */
+    if (!active) return;
+    R->wsum = vadd(R->wsum, weight);
+    float ratio = mean3(vdiv(weight, R->wsum));
+    if (sample <= ratio) { R->current_weight = weight; R->depth = depth; R->si = si; R->ray = ray; R->active = active; }
+}
+static v3 reservoir_weight(const drt_reservoir *R) {                                                /* :768-772 */
+    float d = mean3(R->current_weight);
+    if (d != 0.f) return vscale(R->current_weight, mean3(R->wsum) / d);
+    return V3(0, 0, 0);
+}
+
+/* Medium::sample_interaction_drt [UPSTREAM, absent]: restated from differential ratio tracking (Nimier-David et al. 2022):
+ * tentative collisions t_i with the majorant; w_i = prod_{j<i} (1 - sigma_t(t_j) / mu) estimates T(t_i); one of them is kept
+ * with probability proportional to w_i (reservoir), weight = (sum_i w_i) / mu.  [SPEC] two draws per tentative collision
+ * (distance, reservoir), global majorant. */
+static float sample_interaction_drt(const rcv_scene_desc *S, const orc_medium *M, const ray_t *ray, pcg32 *alt, int active,
+                                    mei_t *mei, counters_t *cnt) {
+    float mint, maxt;
+    active = prepare_interaction_sampling(S, ray, active, &mint, &maxt);
+    mei->t = ORC_INF; mei->p = V3(0, 0, 0); mei->mint = mint;
+    float m = M->majorant, inv_m = 1.f / m;
+    float wsum = 0.f, w = 1.f, t = mint;
+    while (active) {
+        float u = next_1d(alt, 1);
+        t = t + ((-orc_logf(1.f - u)) * inv_m);
+        if (!(t <= maxt)) break;
+        wsum = wsum + w;
+        float xi = next_1d(alt, 1);
+        if (xi * wsum <= w) mei->t = t;
+        tri_t T = tri_setup(S, M, ray_at(ray->o, ray->d, t));
+        float st = lookup_sigma_t(S, M, &T);
+        cnt->c[2]++;
+        w = w * ((m - st) * inv_m);
+        if (!(w > 0.f)) break;
+    }
+    if (mei->t < ORC_INF) mei->p = ray_at(ray->o, ray->d, mei->t);
+    return wsum * inv_m;
+}
+
+static void vps_sample_core(const rcv_scene_desc *S, const orc_medium *M, int primal, pcg32 *rng, pcg32 *alt, ray_t ray, v3 dL,
+                            v3 state_in, float result_out[3], grad_sink *G, counters_t *cnt, const drt_opts *drt,
+                            int from_state, int ps_active, int ps_depth, si_t ps_si, float ps_last_pdf);
+
+/* sample_recursive (:623-668): a detached primal path from mei, on the secondary sampler */
+static v3 sample_recursive(const rcv_scene_desc *S, const orc_medium *M, pcg32 *alt, const ray_t *ray, v3 mei_p, int depth,
+                           int active, counters_t *cnt) {
+    v3 result = V3(0, 0, 0);
+    v3 wi = V3(-ray->d.x, -ray->d.y, -ray->d.z);
+    if (S->use_nee)                                                            /* :635-638 */
+        result = vadd(result, sample_emitter_for_nee(S, M, mei_p, wi, alt, V3(1, 1, 1), active, 1, V3(0, 0, 0), NULL, cnt));
+    float s1 = next_1d(alt, active), s2x = next_1d(alt, active), s2y = next_1d(alt, active);      /* :644-646 */
+    ray_t rec_ray = *ray;
+    float phase_pdf = 1.f;
+    if (active) {
+        v3 wo = phase_sample(S, wi, s1, s2x, s2y, &phase_pdf);
+        rec_ray = spawn_ray(mei_p, V3(0, 0, 0), wo);                           /* :647-648 */
+    }
+    si_t si_next; si_next.valid = 0; si_next.t = ORC_INF; si_next.p = V3(0, 0, 0); si_next.n = V3(0, 0, 0);
+    if (active) {
+        si_next = scene_intersect(S, &rec_ray);                                /* :651 */
+        rec_ray.maxt = isfinite(si_next.t) ? si_next.t : ORC_LARGEST;          /* :653-654 */
+    }
+    int next_depth = active ? depth + 1 : depth;
+    float Li[3];
+    vps_sample_core(S, M, 1, alt, NULL, rec_ray, V3(0, 0, 0), V3(0, 0, 0), Li, NULL, cnt, NULL, 1,
+                    active && (next_depth < S->max_depth), next_depth, si_next, active ? phase_pdf : 1.f);   /* :656-665 */
+    result = vadd(result, V3(Li[0], Li[1], Li[2]));
+    return active ? result : V3(0, 0, 0);                                      /* :668 */
+}
+
+/* backpropagate_scattering_drt without a reservoir (:551-594) */
+static void backpropagate_scattering_drt(const rcv_scene_desc *S, const orc_medium *M, pcg32 *alt, ray_t ray, si_t si, int depth,
+                                         v3 adjoint, int active, const drt_opts *drt, grad_sink *G, counters_t *cnt) {
+    ray_t sub_ray = ray;
+    if (active) sub_ray.maxt = isfinite(si.t) ? si.t : ORC_LARGEST;            /* :553-555 */
+    mei_t mei_sub;
+    float drt_weight = sample_interaction_drt(S, M, &sub_ray, alt, active, &mei_sub, cnt);   /* :560-561 */
+    active = active && mei_valid(&mei_sub);                                    /* :568 */
+    float st = 0.f; v3 albedo = V3(0, 0, 0);
+    if (active) {
+        tri_t T = tri_setup(S, M, mei_sub.p);
+        st = lookup_sigma_t(S, M, &T); albedo = lookup_albedo(M, &T);
+    }
+    v3 drt_Li = sample_recursive(S, M, alt, &sub_ray, mei_sub.p, depth, active, cnt);      /* :575-578 */
+    if (!active) return;
+    float mis = drt->use_drt_mis ? (1.f / (1.f + st * st)) : 1.f;              /* :581-585 */
+    /* backward_from(mis * drt_weight * adjoint * (sigma_t * albedo) * drt_Li) (:587-591) */
+    v3 c = vmul(vscale(adjoint, mis * drt_weight), drt_Li);
+    float g_st = (c.x * albedo.x + c.y * albedo.y) + c.z * albedo.z;
+    v3 g_al = vscale(c, st);
+    scatter_sigma_t(S, M, G, mei_sub.p, g_st, cnt);
+    scatter_albedo(S, M, G, mei_sub.p, g_al, cnt);
+}
+
+/* volpathsimple.py:51-303; reach_medium :305-332.  from_state: a recursive call that restores a PathState (:75-81) */
+static void vps_sample_core(const rcv_scene_desc *S, const orc_medium *M, int primal, pcg32 *rng, pcg32 *alt, ray_t ray, v3 dL,
+                            v3 state_in, float result_out[3], grad_sink *G, counters_t *cnt, const drt_opts *drt,
+                            int from_state, int ps_active, int ps_depth, si_t ps_si, float ps_last_pdf) {
     v3 result = primal ? V3(0, 0, 0) : state_in;                               /* :68 */
     v3 throughput = V3(1, 1, 1);
-    int active = 1;                                                            /* :82 */
-    int depth = 0;
-    (void) next_1d(rng, active);                                               /* :84 */
-    /* reach_medium (:305-332) */
-    si_t si = scene_intersect(S, &ray);                                        /* :311 */
-    int escaped = active && !si.valid;
-    active = active && si.valid;
-    if (active) ray = spawn_ray(si.p, si.n, ray.d);                            /* :319 */
-    si_t si_new; si_new.valid = 0; si_new.t = ORC_INF; si_new.p = V3(0, 0, 0); si_new.n = V3(0, 0, 0);
-    if (active) si_new = scene_intersect(S, &ray);                             /* :320 */
-    active = active && si_new.valid;                                           /* :323 */
-    if (active) {                                                              /* :329-330 */
-        ray.maxt = isfinite(si_new.t) ? si_new.t : ORC_LARGEST;
-        si = si_new;
+    int active, depth, escaped, has_scattered;
+    float last_scatter_direction_pdf;
+    si_t si;
+    if (from_state) {                                                          /* :75-81, :98-100 */
+        active = ps_active; depth = ps_depth; si = ps_si; escaped = 0;
+        has_scattered = active && !escaped;
+        last_scatter_direction_pdf = ps_last_pdf;
+    } else {
+        active = 1;                                                            /* :82 */
+        depth = 0;
+        (void) next_1d(rng, active);                                           /* :84 */
+        /* reach_medium (:305-332) */
+        si = scene_intersect(S, &ray);                                         /* :311 */
+        escaped = active && !si.valid;
+        active = active && si.valid;
+        if (active) ray = spawn_ray(si.p, si.n, ray.d);                        /* :319 */
+        si_t si_new; si_new.valid = 0; si_new.t = ORC_INF; si_new.p = V3(0, 0, 0); si_new.n = V3(0, 0, 0);
+        if (active) si_new = scene_intersect(S, &ray);                         /* :320 */
+        active = active && si_new.valid;                                       /* :323 */
+        if (active) {                                                          /* :329-330 */
+            ray.maxt = isfinite(si_new.t) ? si_new.t : ORC_LARGEST;
+            si = si_new;
+        }
+        has_scattered = 0;                                                     /* :101 */
+        last_scatter_direction_pdf = 1.f;
     }
-    int has_scattered = 0;                                                     /* :101 */
-    float last_scatter_direction_pdf = 1.f;
+    const int use_drt = (!primal) && drt && drt->use_drt;
+    drt_reservoir R; memset(&R, 0, sizeof(R)); R.depth = -1; R.active = active;   /* :107-109 */
     (void) next_1d(rng, active);                                               /* :112 alt_seed_rnd */
 
     while (active) {                                                           /* :127 */
@@ -1338,12 +1459,23 @@ static void vps_sample(const rcv_scene_desc *S, const orc_medium *M, int primal,
             albedo = lookup_albedo(M, &T);
         }
         if (!primal) {
-            if (did_scatter) {
-                /* scattering term (:165-185), drt_mis_weight = 1 without DRT */
+            if (use_drt) {                                                     /* :156-163 */
+                if (drt->use_drt_subsampling) {
+                    float xi = next_1d(alt, active);                           /* :546 */
+                    reservoir_update(&R, depth, si, ray, throughput, xi, active);
+                } else {
+                    backpropagate_scattering_drt(S, M, alt, ray, si, depth, vmul(dL, throughput), active, drt, G, cnt);
+                }
+            }
+            if (did_scatter && (!use_drt || drt->use_drt_mis)) {
+                /* scattering term (:165-185) */
+                float mis = 1.f;
+                if (use_drt && drt->use_drt_mis) { float s2 = mei.sigma_t.x * mei.sigma_t.x; mis = s2 / (1.f + s2); }   /* :169-170 */
                 v3 inv_pdf = V3(1.f / mei.sigma_t.x, 1.f / mei.sigma_t.y, 1.f / mei.sigma_t.z);   /* :175 */
                 v3 Li = vdiv(result, vmax(V3(1e-8f, 1e-8f, 1e-8f), albedo));                       /* :180 */
-                /* backward_from(dL * (sigma_t * albedo) * Li * inv_pdf) (:183) */
+                /* backward_from(drt_mis_weight * dL * (sigma_t * albedo) * Li * inv_pdf) (:183) */
                 v3 c = vmul(vmul(dL, Li), inv_pdf);
+                if (use_drt && drt->use_drt_mis) c = vscale(c, mis);
                 float g_st = (c.x * albedo.x + c.y * albedo.y) + c.z * albedo.z;
                 v3 g_al = vmul(c, mei.sigma_t);
                 scatter_sigma_t(S, M, G, mei.p, g_st, cnt);
@@ -1383,6 +1515,10 @@ static void vps_sample(const rcv_scene_desc *S, const orc_medium *M, int primal,
             escaped = 1;
         }
     }
+    if (use_drt && drt->use_drt_subsampling) {                                 /* :262-272 */
+        v3 adjoint = vmul(reservoir_weight(&R), dL);
+        backpropagate_scattering_drt(S, M, alt, R.ray, R.si, R.depth, adjoint, R.active && (R.depth != -1), drt, G, cnt);
+    }
     if (primal) {                                                              /* :276-300 */
         int si_update_needed = escaped && si.valid;
         if (si_update_needed) si = scene_intersect(S, &ray);                   /* :278 */
@@ -1399,6 +1535,12 @@ static void vps_sample(const rcv_scene_desc *S, const orc_medium *M, int primal,
         }
     }
     result_out[0] = result.x; result_out[1] = result.y; result_out[2] = result.z;
+}
+
+static void vps_sample(const rcv_scene_desc *S, const orc_medium *M, int primal, pcg32 *rng, pcg32 *alt,
+                       ray_t ray, v3 dL, v3 state_in, float result_out[3], grad_sink *G, counters_t *cnt) {
+    si_t none; memset(&none, 0, sizeof(none));
+    vps_sample_core(S, M, primal, rng, alt, ray, dL, state_in, result_out, G, cnt, NULL, 0, 0, 0, none, 1.f);
 }
 
 /* the seed of the adjoint's secondary sampler (volpathsimple.py:112-120): the
@@ -1474,9 +1616,9 @@ int orc_vps_render(const rcv_scene_desc *S, const orc_medium *M, uint32_t seed, 
 /* RBIntegrator.render_backward [UPSTREAM common.py] driving volpathsimple:
  * pass 1 traces L per lane; dL = d(develop o put)/dL * grad_in = sum_p w_p grad_in[p] / W[p] over the
  * sample's filter footprint (one pixel, weight 1, for the box filter); pass 2 replays the identical stream and scatters gradients. */
-int orc_vps_backward(const rcv_scene_desc *S, const orc_medium *M, uint32_t seed_grad, uint32_t spp_grad,
-                     uint32_t spp_begin, uint32_t spp_end, const float *grad_img, const float *film_w,
-                     double *grad_sigma_t, double *grad_albedo, int nthreads) {
+static int vps_backward_impl(const rcv_scene_desc *S, const orc_medium *M, uint32_t seed_grad, uint32_t spp_grad,
+                             uint32_t spp_begin, uint32_t spp_end, const float *grad_img, const float *film_w,
+                             double *grad_sigma_t, double *grad_albedo, int nthreads, const drt_opts *drt) {
     uint64_t npix = (uint64_t) S->film_width * S->film_height;
     uint32_t alt_seed = orc_alt_seed(seed_grad);
     if (nthreads < 1) nthreads = 1;
@@ -1505,12 +1647,27 @@ int orc_vps_backward(const rcv_scene_desc *S, const orc_medium *M, uint32_t seed
                 }
                 pcg32 alt; sampler_seed(&alt, alt_seed, (uint32_t) idx);       /* volpathsimple.py:119-120 */
                 float L2[3];
-                vps_sample(S, M, 0, &ln.rng, &alt, ln.ray, dL, V3(L[0], L[1], L[2]), L2, &G, &cnt);
+                si_t none; memset(&none, 0, sizeof(none));
+                vps_sample_core(S, M, 0, &ln.rng, &alt, ln.ray, dL, V3(L[0], L[1], L[2]), L2, &G, &cnt, drt, 0, 0, 0, none, 1.f);
                 cnt.c[6] += 2;
             }
         counters_merge(&cnt);
     }
     return 0;
+}
+int orc_vps_backward(const rcv_scene_desc *S, const orc_medium *M, uint32_t seed_grad, uint32_t spp_grad,
+                     uint32_t spp_begin, uint32_t spp_end, const float *grad_img, const float *film_w,
+                     double *grad_sigma_t, double *grad_albedo, int nthreads) {
+    return vps_backward_impl(S, M, seed_grad, spp_grad, spp_begin, spp_end, grad_img, film_w, grad_sigma_t, grad_albedo,
+                             nthreads, NULL);
+}
+/* the same with use_drt = True (volpathsimple.py:33-36): ORACLE ONLY, see the DRT block above */
+int orc_vps_backward_drt(const rcv_scene_desc *S, const orc_medium *M, uint32_t seed_grad, uint32_t spp_grad,
+                         uint32_t spp_begin, uint32_t spp_end, const float *grad_img, const float *film_w,
+                         double *grad_sigma_t, double *grad_albedo, int nthreads, int use_drt_subsampling, int use_drt_mis) {
+    drt_opts o; o.use_drt = 1; o.use_drt_subsampling = use_drt_subsampling; o.use_drt_mis = use_drt_mis;
+    return vps_backward_impl(S, M, seed_grad, spp_grad, spp_begin, spp_end, grad_img, film_w, grad_sigma_t, grad_albedo,
+                             nthreads, &o);
 }
 
 /* ------------------------------------------------------------------------- */

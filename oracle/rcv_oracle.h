@@ -61,6 +61,10 @@ int orc_vps_render(const rcv_scene_desc *S, const orc_medium *M, uint32_t seed, 
 int orc_vps_backward(const rcv_scene_desc *S, const orc_medium *M, uint32_t seed_grad, uint32_t spp_grad,
                      uint32_t spp_begin, uint32_t spp_end, const float *grad_img, const float *film_w,
                      double *grad_sigma_t, double *grad_albedo, int nthreads);
+/* use_drt = True (volpathsimple.py:33-36, :520-594, :623-778): oracle only, not part of the product ABI */
+int orc_vps_backward_drt(const rcv_scene_desc *S, const orc_medium *M, uint32_t seed_grad, uint32_t spp_grad,
+                         uint32_t spp_begin, uint32_t spp_end, const float *grad_img, const float *film_w,
+                         double *grad_sigma_t, double *grad_albedo, int nthreads, int use_drt_subsampling, int use_drt_mis);
 
 float orc_adam_lr_t(float lr, float beta1, float beta2, int t);
 void orc_adam(float *p, const float *g, float *m, float *v, uint64_t n, int t, float lr, float beta1,

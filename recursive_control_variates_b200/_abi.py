@@ -89,6 +89,7 @@ _SIGNATURES = {
     "rcv_ctx_destroy": [_P],
     "rcv_ctx_set_stream": [_P, _P],
     "rcv_ctx_set_tracer": [_P, C.c_int],
+    "rcv_adjoint_set_drt": [_P, C.c_int, C.c_int, C.c_int],
     "rcv_scene_set": [_P, C.POINTER(SceneDesc)],
     "rcv_medium_rotate": [_P, _P, _P, C.c_int, C.c_int, C.c_int],
     "rcv_medium_majorants_host": [_P, C.POINTER(_f * 2)],

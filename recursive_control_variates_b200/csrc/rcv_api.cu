@@ -40,6 +40,7 @@ struct rcv_ctx {
     cudaStream_t stream = nullptr;
     int sm_count = 148;
     int tracer = RCV_TRACER_POOL;
+    int drt_flags = 0;                 // volpathsimple's use_drt / use_drt_subsampling / use_drt_mis
     bool l2_persist = false;      // pin the d sigma_t grid in L2 while the adjoint runs (RCV_L2_PERSIST=1)
     size_t l2_persist_max = 0, l2_window_max = 0;
     bool has_scene = false;
@@ -87,7 +88,7 @@ struct rcv_ctx {
 
     LaunchCfg cfg() {
         LaunchCfg c;
-        c.stream = stream; c.sm_count = sm_count; c.tracer = tracer;
+        c.stream = stream; c.sm_count = sm_count; c.tracer = tracer; c.drt_flags = drt_flags;
         c.counters = counters; c.work_counter = work; c.launches = &launches; c.queue = queue;
         c.arena = arena; c.vcap = vcap;
         return c;
@@ -292,6 +293,12 @@ int rcv_ctx_set_tracer(rcv_ctx *c, int kind) {
     return RCV_OK;
 }
 
+int rcv_adjoint_set_drt(rcv_ctx *c, int use_drt, int use_drt_subsampling, int use_drt_mis) {
+    if (!c) return fail(RCV_ERR_ARG, "null context");
+    c->drt_flags = use_drt ? (1 | (use_drt_subsampling ? 2 : 0) | (use_drt_mis ? 4 : 0)) : 0;
+    return RCV_OK;
+}
+
 int rcv_scene_set(rcv_ctx *c, const rcv_scene_desc *d) {
     if (!c || !d) return fail(RCV_ERR_ARG, "null argument");
     if (d->struct_size != sizeof(rcv_scene_desc)) return fail(RCV_ERR_ARG, "rcv_scene_desc size mismatch (ABI)");
@@ -489,7 +496,7 @@ int rcv_render_backward_weighted(rcv_ctx *c, int adjoint_kind, uint32_t seed_gra
     // deep paths (max_depth = -1 ...) would need an unbounded vertex arena: use the replaying schedule for them
     const int saved_tracer = c->tracer;
     if ((c->tracer == RCV_TRACER_POOL || c->tracer == RCV_TRACER_WAVEFRONT) && c->S.max_depth >= 4096) c->tracer = RCV_TRACER_BATCH;
-    if (c->tracer == RCV_TRACER_POOL || c->tracer == RCV_TRACER_WAVEFRONT)
+    if ((c->tracer == RCV_TRACER_POOL || c->tracer == RCV_TRACER_WAVEFRONT) && !(c->drt_flags & 1))
         if (int r = ensure_arena(c)) { c->tracer = saved_tracer; return r; }
     LaunchCfg cfg = c->cfg();
     c->tracer = saved_tracer;

@@ -11,6 +11,7 @@ struct LaunchCfg {
     cudaStream_t stream;
     int sm_count;
     int tracer;        // RCV_TRACER_*
+    int drt_flags;     // 0: use_drt = False; else bit 0 use_drt, bit 1 use_drt_subsampling, bit 2 use_drt_mis
     Counters *counters;   // device
     unsigned long long *work_counter;   // device, persistent-kernel work queue head
     PathQueue queue;                    // device, path records of the wavefront schedule

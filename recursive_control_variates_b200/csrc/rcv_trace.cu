@@ -140,6 +140,43 @@ __global__ void __launch_bounds__(kBlock) k_vps_simple(const __grid_constant__ S
     counter_flush(C, 6, np);
 }
 
+// use_drt = True (volpathsimple.py:33-47): the adjoint with the differential-ratio-tracking in-scattering term.  The DRT
+// estimate is one more full path per lane, drawn from the secondary sampler, so it runs as a persistent one-thread-per-lane
+// kernel under every tracer setting (the event machines above cover use_drt = False).
+#ifndef RCV_DRT_BLOCK
+#define RCV_DRT_BLOCK 128
+#endif
+#ifndef RCV_DRT_MINBLOCKS
+#define RCV_DRT_MINBLOCKS 4
+#endif
+static constexpr int kDrtBlock = RCV_DRT_BLOCK;
+template <class GRID>
+__global__ void __launch_bounds__(kDrtBlock, RCV_DRT_MINBLOCKS) k_vps_drt(const __grid_constant__ SceneK S, const __grid_constant__ GRID G, GradK D,
+                                                    uint32_t seed, uint32_t spp, uint32_t spp_begin, uint32_t ns, uint64_t n_local,
+                                                    uint32_t alt_seed, const float *grad_img, const float *film_w, int drt_flags,
+                                                    Counters *C, unsigned long long *work) {
+    VpsCounts cnt; cnt.coll = cnt.scat = cnt.g_sig = cnt.g_alb = 0;
+    unsigned np = 0;
+    const unsigned lane = threadIdx.x & 31;
+    while (true) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(work, 32ull);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n_local) break;
+        uint64_t j = base + lane;
+        if (j < n_local) {
+            vps_backward_lane(S, G, D, seed, spp, global_lane(j, spp, spp_begin, ns), alt_seed, grad_img, film_w, drt_flags, cnt);
+            np += 2;
+        }
+        __syncwarp();
+    }
+    counter_flush(C, 2, cnt.coll);
+    counter_flush(C, 3, cnt.scat);
+    counter_flush(C, 4, cnt.g_sig);
+    counter_flush(C, 5, cnt.g_alb);
+    counter_flush(C, 6, np);
+}
+
 // ===========================================================================
 // WAVEFRONT schedule
 // ===========================================================================
@@ -613,6 +650,15 @@ static cudaError_t launch_vps(const LaunchCfg &cfg, const SceneK &S, const GRID 
     uint64_t n_local = (uint64_t) S.W * S.H * ns;
     if (n_local == 0) return cudaSuccess;
     cudaError_t e;
+    if (BACKWARD && (cfg.drt_flags & 1)) {
+        unsigned blocks;
+        if ((e = cudaMemsetAsync(cfg.work_counter, 0, sizeof(unsigned long long), cfg.stream)) != cudaSuccess) return e;
+        if ((e = persistent_grid(cfg, k_vps_drt<GRID>, kDrtBlock, n_local, blocks)) != cudaSuccess) return e;
+        k_vps_drt<GRID><<<blocks, kDrtBlock, 0, cfg.stream>>>(S, G, D, seed, spp, spp_begin, ns, n_local, alt_seed, grad_img, film_w,
+                                                           cfg.drt_flags, cfg.counters, cfg.work_counter);
+        (*cfg.launches)++;
+        return cudaGetLastError();
+    }
     if (cfg.tracer == 0 || cfg.tracer == 3) {
         if ((e = cudaMemsetAsync(cfg.work_counter, 0, sizeof(unsigned long long), cfg.stream)) != cudaSuccess) return e;
         if ((e = cudaMemsetAsync(cfg.queue.count, 0, sizeof(unsigned long long), cfg.stream)) != cudaSuccess) return e;

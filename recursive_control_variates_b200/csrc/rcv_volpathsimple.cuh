@@ -1,8 +1,10 @@
 // rcv_volpathsimple.cuh — per-lane restatement of VolpathSimpleIntegrator
-// (plugins/volpathsimple.py) in Primal and Backward mode, use_drt = False:
+// (plugins/volpathsimple.py) in Primal and Backward mode:
 // sample (:51-303), reach_medium (:305-332), sample_real_interaction
 // (:336-390), sample_emitter_for_nee / sample_emitter / estimate_transmittance
-// (:393-517), backpropagate_transmittance (:597-620).
+// (:393-517), backpropagate_transmittance (:597-620); with DRT = true also the
+// differential-ratio-tracking in-scattering term: backpropagate_scattering_drt
+// (:520-594), sample_recursive (:623-668), PathState / DRTReservoir (:673-778).
 //
 // Backward mode replays the identical main random stream and turns the AD of
 // the trilinear gathers into reductions on the
@@ -119,9 +121,37 @@ __device__ __forceinline__ float vps_sample_emitter(const SceneK &S, const GRID 
     return estimate_transmittance<ADJ>(S, G, D, mu, inv_mu, rng, ref_p, d, id, si.t, si.valid, adjoint, cnt);   // :443
 }
 
-template <bool ADJ, class GRID>
-__device__ __forceinline__ void vps_trace(const SceneK &S, const GRID &G, const GradK &D, Pcg &rng, Pcg &alt, V3 o, V3 d, V3 dL,
-                                          V3 state_in, V3 &result, VpsCounts &cnt) {
+// PathState (volpathsimple.py:673-719): where a recursive call of `sample` resumes
+struct VpsState {
+    bool active;
+    int depth;
+    Hit si;
+    float ray_maxt, last_pdf;
+};
+// use_drt_subsampling / use_drt_mis (:41-47)
+struct DrtOpts {
+    bool subsampling, mis;
+};
+// DRTReservoir with n = 1 (:743-778): one path depth, kept with probability proportional to the throughput there
+struct DrtReservoir {
+    V3 wsum, cur, o, d;
+    float ray_maxt;
+    int depth;            // -1: never set
+    bool active;
+};
+__device__ __forceinline__ float mean3(V3 a) { return ((a.x + a.y) + a.z) / 3.f; }
+
+template <class GRID>
+__device__ __noinline__ void drt_backpropagate(const SceneK &S, const GRID &G, const GradK &D, float mu, float inv_mu, Pcg &alt,
+                                               V3 o, V3 d, float ray_maxt, int depth, V3 adjoint, bool active, bool use_mis,
+                                               VpsCounts &cnt);
+
+// ADJ: Backward mode.  DRT: use_drt (Backward only).  FROM_STATE: resume at `ps` (the recursive call of :656-665)
+// instead of starting at the sensor.
+template <bool ADJ, bool DRT, bool FROM_STATE, class GRID>
+__device__ __forceinline__ void vps_trace_core(const SceneK &S, const GRID &G, const GradK &D, Pcg &rng, Pcg &alt, V3 o, V3 d, V3 dL,
+                                               V3 state_in, V3 &result, VpsCounts &cnt, const VpsState &ps, DrtOpts drt) {
+    static_assert(!DRT || ADJ, "DRT is a term of the adjoint");
     const float mu = __ldg(G.majorants + 1);       // state `new` (twostatemedium.py:125-136)
     const float inv_mu = 1.f / mu;
     V3 id = rcp3(d);
@@ -129,19 +159,31 @@ __device__ __forceinline__ void vps_trace(const SceneK &S, const GRID &G, const 
     result = ADJ ? state_in : mk3(0, 0, 0);                           // :68
     V3 thr = mk3(1, 1, 1);
     int depth = 0;
-    (void) pcg_f32(rng);                                              // :84
-    // reach_medium (:305-332)
-    Hit si = box_hit(S, o, d, id, RCV_LARGEST);                       // :311
-    bool escaped = !si.valid, active = si.valid;
-    float ray_maxt = RCV_LARGEST;
-    if (active) {
-        o = offset_p(si.p, si.n, d);                                  // :319
-        Hit si2 = box_hit(S, o, d, id, RCV_LARGEST);                  // :320
-        active = si2.valid;                                           // :323
-        if (active) { ray_maxt = isfinite(si2.t) ? si2.t : RCV_LARGEST; si = si2; }   // :329-330
+    Hit si;
+    bool escaped, active, has_scattered = false;
+    float ray_maxt = RCV_LARGEST, last_pdf = 1.f;
+    if constexpr (FROM_STATE) {                                       // :75-81, :98-100
+        active = ps.active; depth = ps.depth; si = ps.si; ray_maxt = ps.ray_maxt;
+        escaped = false;
+        has_scattered = active;
+        last_pdf = ps.last_pdf;
+    } else {
+        (void) pcg_f32(rng);                                          // :84
+        // reach_medium (:305-332)
+        si = box_hit(S, o, d, id, RCV_LARGEST);                       // :311
+        escaped = !si.valid; active = si.valid;
+        if (active) {
+            o = offset_p(si.p, si.n, d);                              // :319
+            Hit si2 = box_hit(S, o, d, id, RCV_LARGEST);              // :320
+            active = si2.valid;                                       // :323
+            if (active) { ray_maxt = isfinite(si2.t) ? si2.t : RCV_LARGEST; si = si2; }   // :329-330
+        }
     }
-    bool has_scattered = false;
-    float last_pdf = 1.f;
+    DrtReservoir R;                                                   // :107-109
+    if constexpr (DRT) {
+        R.wsum = R.cur = R.o = R.d = mk3(0, 0, 0);
+        R.ray_maxt = 0.f; R.depth = -1; R.active = active;
+    }
     if (active) (void) pcg_f32(rng);                                  // :112 alt_seed_rnd
 
     while (active) {                                                  // :127
@@ -180,11 +222,26 @@ __device__ __forceinline__ void vps_trace(const SceneK &S, const GRID &G, const 
             cnt.scat++;
         }
         if (ADJ) {
-            if (did_scatter) {
-                // scattering term (:165-185): backward_from(dL * (sigma_t * albedo) * Li * inv_pdf)
+            if constexpr (DRT) {                                      // :156-163, :533-549
+                if (drt.subsampling) {
+                    float xi = pcg_f32(alt);                          // :546
+                    R.wsum = R.wsum + thr;                            // :757-765
+                    if (xi <= mean3(thr / R.wsum)) {
+                        R.cur = thr; R.depth = depth; R.o = o; R.d = d; R.ray_maxt = ray_maxt; R.active = true;
+                    }
+                } else {
+                    drt_backpropagate(S, G, D, mu, inv_mu, alt, o, d, ray_maxt, depth, dL * thr, true, drt.mis, cnt);
+                }
+            }
+            if (did_scatter && (!DRT || drt.mis)) {
+                // scattering term (:165-185): backward_from(drt_mis_weight * dL * (sigma_t * albedo) * Li * inv_pdf)
                 V3 inv_pdf = splat3(1.f / st);                        // :175
                 V3 Li = result / vmax3(splat3(1e-8f), albedo);        // :180
                 V3 c = (dL * Li) * inv_pdf;
+                if constexpr (DRT) {                                  // :167-170: power heuristic against the DRT estimate
+                    float s2 = st * st;
+                    c = c * (s2 / (1.f + s2));
+                }
                 float g_st = (c.x * albedo.x + c.y * albedo.y) + c.z * albedo.z;
                 V3 g_al = c * splat3(st);
                 if (T.inside) {
@@ -247,6 +304,14 @@ __device__ __forceinline__ void vps_trace(const SceneK &S, const GRID &G, const 
             escaped = true;
         }
     }
+    if constexpr (DRT) {                                              // :262-272: the one delayed DRT estimate of the lane
+        if (drt.subsampling) {
+            float dn = mean3(R.cur);                                  // :768-772
+            V3 wgt = (dn != 0.f) ? R.cur * (mean3(R.wsum) / dn) : mk3(0, 0, 0);
+            drt_backpropagate(S, G, D, mu, inv_mu, alt, R.o, R.d, R.ray_maxt, R.depth, wgt * dL, R.active && (R.depth != -1),
+                              drt.mis, cnt);
+        }
+    }
     if (!ADJ) {                                                       // :276-300
         if (escaped && si.valid) si = box_hit(S, o, d, id, ray_maxt); // :277-278
         if (escaped && !si.valid && !((depth <= 0) && S.hide_emitters)) {
@@ -254,6 +319,128 @@ __device__ __forceinline__ void vps_trace(const SceneK &S, const GRID &G, const 
             if (S.use_nee) w = mis_weight(last_pdf, has_scattered ? RCV_INV_FOURPI : 0.f);   // :286-291
             result = result + (thr * w) * env;                        // :298
         }
+    }
+}
+
+template <bool ADJ, class GRID>
+__device__ __forceinline__ void vps_trace(const SceneK &S, const GRID &G, const GradK &D, Pcg &rng, Pcg &alt, V3 o, V3 d, V3 dL,
+                                          V3 state_in, V3 &result, VpsCounts &cnt) {
+    VpsState ps; ps.active = false; ps.depth = 0; ps.si.valid = false; ps.ray_maxt = RCV_LARGEST; ps.last_pdf = 1.f;
+    DrtOpts drt; drt.subsampling = drt.mis = false;
+    vps_trace_core<ADJ, false, false>(S, G, D, rng, alt, o, d, dL, state_in, result, cnt, ps, drt);
+}
+
+// ---------------------------------------------------------------------------
+// DRT in-scattering term (use_drt = True, volpathsimple.py:520-594, :623-668)
+// ---------------------------------------------------------------------------
+// Medium::sample_interaction_drt [UPSTREAM, source absent]: differential ratio tracking restated from the published
+// algorithm.  Tentative collisions t_i are sampled with the volume's majorant; w_i = prod_{j<i} (1 - sigma_t(t_j) / mu)
+// estimates the transmittance up to t_i; one t_i is kept with probability proportional to w_i and the estimate carries
+// (sum_i w_i) / mu.  Two secondary-sampler draws per tentative collision (distance, selection).
+template <class GRID>
+__device__ __forceinline__ float sample_interaction_drt(const SceneK &S, const GRID &G, float mu, float inv_mu, Pcg &alt, V3 o, V3 d,
+                                                        V3 id, float ray_maxt, bool active, float &sel_t, VpsCounts &cnt) {
+    float mint, maxt;
+    active = medium_interval(S, o, d, id, ray_maxt, mint, maxt) && active;
+    sel_t = inf_();
+    float wsum = 0.f, w = 1.f, t = mint;
+    while (active) {
+        float u = pcg_f32(alt);
+        t = t + ((-spec_log(1.f - u)) * inv_mu);
+        if (!(t <= maxt)) break;
+        wsum = wsum + w;
+        float xi = pcg_f32(alt);
+        if (xi * wsum <= w) sel_t = t;
+        Tri T = tri_setup(S, G, ray_at(o, d, t));
+        float st = lookup_sigma1(S, G, T);
+        cnt.coll++;
+        w = w * ((mu - st) * inv_mu);
+        if (!(w > 0.f)) break;
+    }
+    return wsum * inv_mu;
+}
+
+// sample_recursive (:623-668): a detached radiance estimate from `p`, drawn from the secondary sampler
+template <class GRID>
+__device__ __forceinline__ V3 sample_recursive(const SceneK &S, const GRID &G, const GradK &D, float mu, float inv_mu, Pcg &alt,
+                                               V3 ray_d, V3 p, int depth, VpsCounts &cnt) {
+    V3 result = mk3(0, 0, 0);
+    V3 wi = mk3(-ray_d.x, -ray_d.y, -ray_d.z);
+    if (S.use_nee) {                                                  // :635-638, throughput 1
+        V3 dir;
+        float tr = vps_sample_emitter<false>(S, G, D, mu, inv_mu, alt, p, mk3(0, 0, 0), dir, cnt);
+        V3 emitted = mk3(S.env_over_pdf[0], S.env_over_pdf[1], S.env_over_pdf[2]) * splat3(tr);
+        float phase_val = phase_eval(S, wi, dir);
+        result = result + ((mk3(1, 1, 1) * phase_val) * mis_weight(RCV_INV_FOURPI, phase_val)) * emitted;
+    }
+    (void) pcg_f32(alt);                                              // :644-646
+    float s2x = pcg_f32(alt), s2y = pcg_f32(alt);
+    float pdf;
+    V3 wo = phase_sample(S, wi, s2x, s2y, pdf);
+    V3 id = rcp3(wo);
+    VpsState ps;
+    ps.si = box_hit(S, p, wo, id, RCV_LARGEST);                       // :651
+    ps.ray_maxt = isfinite(ps.si.t) ? ps.si.t : RCV_LARGEST;          // :653-654
+    ps.depth = depth + 1;
+    ps.active = ps.depth < S.max_depth;
+    ps.last_pdf = pdf;
+    DrtOpts none; none.subsampling = none.mis = false;
+    V3 Li;
+    vps_trace_core<false, false, true>(S, G, D, alt, alt, p, wo, mk3(0, 0, 0), mk3(0, 0, 0), Li, cnt, ps, none);   // :656-665
+    return result + Li;
+}
+
+// backpropagate_scattering_drt without a reservoir (:551-594)
+template <class GRID>
+__device__ __noinline__ void drt_backpropagate(const SceneK &S, const GRID &G, const GradK &D, float mu, float inv_mu, Pcg &alt,
+                                               V3 o, V3 d, float ray_maxt, int depth, V3 adjoint, bool active, bool use_mis,
+                                               VpsCounts &cnt) {
+    V3 id = rcp3(d);
+    float sel_t;
+    float drt_weight = sample_interaction_drt(S, G, mu, inv_mu, alt, o, d, id, ray_maxt, active, sel_t, cnt);   // :560-561
+    if (!(active && (sel_t < inf_()))) return;                        // :568
+    V3 p = ray_at(o, d, sel_t);
+    Tri T = tri_setup(S, G, p);
+    float st = lookup_sigma1(S, G, T);
+    V3 albedo = lookup_albedo(G, T, 1);
+    V3 Li = sample_recursive(S, G, D, mu, inv_mu, alt, d, p, depth, cnt);   // :575-578
+    float mis = use_mis ? (1.f / (1.f + st * st)) : 1.f;              // :581-585
+    // backward_from(mis * drt_weight * adjoint * (sigma_t * albedo) * drt_Li) (:587-591)
+    V3 c = (adjoint * (mis * drt_weight)) * Li;
+    float g_st = (c.x * albedo.x + c.y * albedo.y) + c.z * albedo.z;
+    V3 g_al = c * splat3(st);
+    if (T.inside) {
+        float sg = S.scale * g_st;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float w = tri_weight(T, k);
+            uint32_t v = tri_voxel(G, T, k);
+            red_add_f32(D.gsig + v, w * sg);
+            red_add_v4(D.galb + v, w * g_al.x, w * g_al.y, w * g_al.z, 0.f);
+        }
+        cnt.g_sig++; cnt.g_alb++;
+    }
+}
+
+// RBIntegrator.render_backward for one lane: pass 1 traces L on a clone of the sampler, pass 2 replays the stream and
+// scatters the gradients.  drt_flags: 0 = use_drt False; else bit 0 use_drt, bit 1 use_drt_subsampling, bit 2 use_drt_mis.
+template <class GRID>
+__device__ __forceinline__ void vps_backward_lane(const SceneK &S, const GRID &G, const GradK &D, uint32_t seed, uint32_t spp,
+                                                  uint64_t idx, uint32_t alt_seed, const float *grad_img, const float *film_w,
+                                                  int drt_flags, VpsCounts &cnt) {
+    Lane L = lane_setup(S, seed, spp, idx);
+    Pcg alt; alt.state = 0; alt.inc = 1;
+    V3 res, res2;
+    Pcg rng1 = L.rng;                                   // sampler.clone() for pass 1
+    vps_trace<false>(S, G, D, rng1, alt, L.o, L.d, mk3(0, 0, 0), mk3(0, 0, 0), res, cnt);
+    V3 dL = film_gather(S, grad_img, film_w, L.fx, L.fy);
+    sampler_seed(alt, alt_seed, (uint32_t) idx);        // volpathsimple.py:119-120
+    if (drt_flags & 1) {
+        VpsState ps; ps.active = false; ps.depth = 0; ps.si.valid = false; ps.ray_maxt = RCV_LARGEST; ps.last_pdf = 1.f;
+        DrtOpts drt; drt.subsampling = (drt_flags & 2) != 0; drt.mis = (drt_flags & 4) != 0;
+        vps_trace_core<true, true, false>(S, G, D, L.rng, alt, L.o, L.d, dL, res, res2, cnt, ps, drt);
+    } else {
+        vps_trace<true>(S, G, D, L.rng, alt, L.o, L.d, dL, res, res2, cnt);
     }
 }
 

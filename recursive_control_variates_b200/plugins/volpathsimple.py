@@ -27,13 +27,12 @@ class VolpathSimpleIntegrator:
             self.max_depth = 0x7FFFFFFF
         self.hide_emitters = bool(props.get("hide_emitters", False))       # volpathsimple.py:35
         self.use_nee = bool(props.get("use_nee", True))                    # :37
-        # Differential ratio tracking (:39-47) needs Mitsuba's sample_interaction_drt, whose
-        # source is not part of the reference; this build implements the use_drt=False estimator.
-        self.use_drt = bool(props.get("use_drt", False))
+        # Differential ratio tracking (:39-47), on by default as in the reference.  Mitsuba's
+        # sample_interaction_drt is not part of the reference's sources: librcv_b200 restates it from
+        # the published algorithm, so this estimator is unbiased but its parity unpinned.
+        self.use_drt = bool(props.get("use_drt", True))
         self.use_drt_subsampling = bool(props.get("use_drt_subsampling", True))
         self.use_drt_mis = bool(props.get("use_drt_mis", True))
-        if self.use_drt:
-            raise NotImplementedError("use_drt=True is not implemented yet (SURVEY.md §8f); pass use_drt=False")
 
     def _ctx(self, scene):
         get_single_medium(scene)
@@ -61,6 +60,7 @@ class VolpathSimpleIntegrator:
             if world > 1:        # the film weights of all samples: every rank adds its own, one small all-reduce
                 film_w = ctx.film_weights(seed, spp, b, e)
                 parallel.allreduce_sum_([film_w])
+            ctx.set_drt(self.use_drt, self.use_drt_subsampling, self.use_drt_mis)
             ctx.render_backward(seed, spp, grad_in.contiguous(), b, e, film_w=film_w)
             parallel.allreduce_sum_([ctx.grad_packed()])                   # gradient grids before the Adam step
             g_sigma, g_albedo = ctx.grad_read()

@@ -74,6 +74,10 @@ class Context:
     def set_tracer(self, kind: int):
         check(self.lib.rcv_ctx_set_tracer(self._h, kind))
 
+    def set_drt(self, use_drt: bool, use_drt_subsampling: bool = True, use_drt_mis: bool = True):
+        """volpathsimple's use_drt / use_drt_subsampling / use_drt_mis (volpathsimple.py:39-47) for render_backward."""
+        check(self.lib.rcv_adjoint_set_drt(self._h, int(bool(use_drt)), int(bool(use_drt_subsampling)), int(bool(use_drt_mis))))
+
     def set_scene(self, scene):
         desc = scene.to_desc() if isinstance(scene, SceneConfig) else scene
         check(self.lib.rcv_scene_set(self._h, C.byref(desc)))

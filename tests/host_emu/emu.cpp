@@ -197,6 +197,24 @@ int emu_vps_sg(const rcv_scene_desc *d, const float *sn, const float *an, int nz
     counters[6] = sk.n_paths;
     return 0;
 }
+// the one-thread-per-lane adjoint (vps_backward_lane): drt_flags = 0 is use_drt = False, else bit 0 use_drt,
+// bit 1 use_drt_subsampling, bit 2 use_drt_mis
+int emu_vps_backward_lane(const rcv_scene_desc *d, const float *sn, const float *an, int nz, int ny, int nx, uint32_t seed,
+                          uint32_t spp, uint32_t alt_seed, const float *grad_img, const float *film_w, float *gsig, float *galb4,
+                          uint64_t *counters, int factor, int drt_flags) {
+    SceneK S; scene_from_desc(*d, S);
+    Packed P; pack(*d, sn, an, sn, an, nz, ny, nx, P, factor);
+    for (int i = 0; i < 8; ++i) counters[i] = 0;
+    GradK D; D.gsig = gsig; D.galb = (float4 *) galb4;
+    VpsCounts cnt; cnt.coll = cnt.scat = cnt.g_sig = cnt.g_alb = 0;
+    uint64_t n = (uint64_t) S.W * S.H * spp;
+    for (uint64_t idx = 0; idx < n; ++idx) {
+        if (factor > 0) vps_backward_lane(S, P.G, D, seed, spp, idx, alt_seed, grad_img, film_w, drt_flags, cnt);
+        else vps_backward_lane(S, (const GridK &) P.G, D, seed, spp, idx, alt_seed, grad_img, film_w, drt_flags, cnt);
+    }
+    counters[2] = cnt.coll; counters[3] = cnt.scat; counters[4] = cnt.g_sig; counters[5] = cnt.g_alb; counters[6] = 2 * n;
+    return 0;
+}
 int emu_vps(const rcv_scene_desc *d, const float *sn, const float *an, int nz, int ny, int nx, uint32_t seed, uint32_t spp,
             int backward, uint32_t alt_seed, const float *grad_img, const float *film_w, float *accum, float *gsig,
             float *galb4, uint64_t *counters) {

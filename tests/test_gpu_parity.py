@@ -118,6 +118,60 @@ def test_volpathsimple_backward(oracle, gpu_ctx, setup, tracer):
     gpu_ctx.set_tracer(3)
 
 
+@pytest.mark.parametrize("flags", [7, 5, 3, 1])
+def test_volpathsimple_backward_drt(oracle, gpu_ctx, setup, flags):
+    """use_drt = True (volpathsimple.py:39-47, :520-594, :623-778) through rcv_adjoint_set_drt: bit 1 of `flags` is
+    use_drt_subsampling, bit 2 use_drt_mis.  Same lanes, same draws and gradient sites as the oracle's restatement; the
+    gradients differ in summation order only.  Sharding the spp leaves the result unchanged."""
+    d = setup["desc"]
+    rng = np.random.default_rng(1)
+    grad_img = (rng.standard_normal((d.film_height, d.film_width, 3)) / (d.film_height * d.film_width * 3)).astype(np.float32)
+    seed_grad, spp_grad = 0x2468ACE1, 4
+    kw = dict(use_drt=True, use_drt_subsampling=bool(flags & 2), use_drt_mis=bool(flags & 4))
+    oracle.counters(True); gpu_ctx.counters(True)
+    gs, ga = oracle.vps_backward(d, setup["mn"], seed_grad, spp_grad, grad_img, threads=1, **kw)
+    try:
+        gpu_ctx.set_drt(True, bool(flags & 2), bool(flags & 4))
+        gpu_ctx.grad_zero()
+        gpu_ctx.render_backward(seed_grad, spp_grad, to_cuda(grad_img))
+        ggs, gga = gpu_ctx.grad_read()
+        oc, gc = oracle.counters(True), gpu_ctx.counters(True)
+        assert [int(v) for v in oc[2:6]] == [int(v) for v in gc[2:6]], (oc, gc)
+        assert rel_l2(ggs.cpu().numpy(), gs) < 1e-4 and rel_l2(gga.cpu().numpy(), ga) < 1e-4
+        if flags == 7:
+            gpu_ctx.grad_zero()
+            gpu_ctx.render_backward(seed_grad, spp_grad, to_cuda(grad_img), 0, 1)
+            gpu_ctx.render_backward(seed_grad, spp_grad, to_cuda(grad_img), 1, 4)
+            hs, ha = gpu_ctx.grad_read()
+            assert rel_l2(hs.cpu().numpy(), ggs.cpu().numpy()) < 1e-5 and rel_l2(ha.cpu().numpy(), gga.cpu().numpy()) < 1e-5
+    finally:
+        gpu_ctx.set_drt(False)
+    # a different estimator of the same gradient: far from the path-replay one sample by sample
+    ps, _ = oracle.vps_backward(d, setup["mn"], seed_grad, spp_grad, grad_img, threads=1)
+    assert rel_l2(gs, ps) > 1e-2
+
+
+def test_drt_with_majorant_supergrid(oracle, gpu_ctx):
+    """DRT on the DDA kernels: the main path samples free flights through the supergrid, the DRT distance sampler
+    keeps the volume's majorant."""
+    from recursive_control_variates_b200.scene import SceneConfig
+    d = SceneConfig(width=24, height=20, max_depth=16, rr_depth=8).to_desc()
+    _, (sn, an) = media(16)
+    mn = oracle.OracleMedium(d, sn, an, majorant_factor=4)
+    gimg = (np.random.default_rng(2).standard_normal((20, 24, 3)) / 1440).astype(np.float32)
+    gs, ga = oracle.vps_backward(d, mn, 91, 3, gimg, threads=1, use_drt=True)
+    from recursive_control_variates_b200.runtime import Context
+    ctx = Context(0)
+    ctx.set_scene(d)
+    ctx.set_majorant_factor(4)
+    gpu_set_states(ctx, (sn, an), (sn, an))
+    ctx.set_drt(True)
+    ctx.grad_zero()
+    ctx.render_backward(91, 3, to_cuda(gimg))
+    ggs, gga = ctx.grad_read()
+    assert rel_l2(ggs.cpu().numpy(), gs) < 1e-4 and rel_l2(gga.cpu().numpy(), ga) < 1e-4
+
+
 def test_backward_sharding(gpu_ctx, setup):
     d = setup["desc"]
     g = to_cuda(np.full((d.film_height, d.film_width, 3), 1e-4, np.float32))

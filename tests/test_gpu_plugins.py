@@ -98,12 +98,16 @@ def test_run_opt_loop(mi, method):
     assert np.isfinite(res["loss"]).all()
 
 
-def test_gradient_through_render_op(mi, oracle):
-    """mi.render(...).backward() == volpathsimple adjoint of d loss / d img (RenderOp boundary)."""
+@pytest.mark.parametrize("use_drt", [True, False])
+def test_gradient_through_render_op(mi, oracle, use_drt):
+    """mi.render(...).backward() == volpathsimple adjoint of d loss / d img (RenderOp boundary), with the
+    reference's default use_drt = True (volpathsimple.py:39-47) and with the plain path-replay estimator."""
     import torch
     from recursive_control_variates_b200.utils import l1_loss
     p = _params("cv_ps")
     scene = p["scene"]
+    assert p["adjoint_integrator"].use_drt and p["adjoint_integrator"].use_drt_subsampling and p["adjoint_integrator"].use_drt_mis
+    p["adjoint_integrator"].use_drt = use_drt
     integ = mi.load_dict({"type": "meta", "method": "cv_ps", "integrator": p["integrator"],
                           "adjoint_integrator": p["adjoint_integrator"]})
     opt = mi.Adam(lr=5e-3)
@@ -123,8 +127,11 @@ def test_gradient_through_render_op(mi, oracle):
     from recursive_control_variates_b200.runtime import tea32
     _, gimg = oracle.loss_grad(0, img.detach().cpu().numpy(), ref.cpu().numpy())
     m = oracle.OracleMedium(desc, sig, alb)
-    ogs, oga = oracle.vps_backward(desc, m, tea32(3, 1)[0], 2, gimg)
+    ogs, oga = oracle.vps_backward(desc, m, tea32(3, 1)[0], 2, gimg, use_drt=use_drt)
     assert rel_l2(gs, ogs) < 1e-3 and rel_l2(ga, oga) < 1e-3
+    if use_drt:        # and it is a different estimator from the path-replay one
+        pgs, _ = oracle.vps_backward(desc, m, tea32(3, 1)[0], 2, gimg)
+        assert rel_l2(gs, pgs) > 1e-2
 
 
 def test_run_opt_loop_with_majorant_supergrid(mi):

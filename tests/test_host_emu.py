@@ -31,6 +31,8 @@ def emu():
                                      C.c_int, f32, f32, u64]
     lib.emu_vps_sg.argtypes = [C.c_void_p, f32, f32, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32,
                                C.c_void_p, C.c_void_p, f32, f32, f32, u64, C.c_int]
+    lib.emu_vps_backward_lane.argtypes = [C.c_void_p, f32, f32, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32,
+                                          C.c_void_p, C.c_void_p, f32, f32, u64, C.c_int, C.c_int]
     return lib
 
 
@@ -210,3 +212,29 @@ def test_long_shadow_rays_fall_back_to_the_replay(oracle, emu):
     assert [int(v) for v in cnt[3:7]] == [int(v) for v in oc[3:7]]
     assert int(oc[2]) / max(1, int(oc[3])) > 40        # dense enough: tens of tentative collisions per vertex
     assert rel_l2(g1, gs) < 1e-5 and rel_l2(g4[..., 0:3], ga) < 1e-5
+
+
+@pytest.mark.parametrize("flags,factor", [(0, 0), (7, 0), (5, 0), (3, 0), (1, 0), (7, 5)])
+def test_per_lane_adjoint_with_drt(oracle, emu, flags, factor):
+    """vps_backward_lane (csrc/rcv_volpathsimple.cuh), the one-thread-per-lane adjoint behind use_drt = True
+    (volpathsimple.py:520-594, :623-778): flags 0 is the path-replay estimator, else bit 0 use_drt, bit 1
+    use_drt_subsampling, bit 2 use_drt_mis.  Same lanes, same draws, same gradient sites as the oracle."""
+    from recursive_control_variates_b200.scene import SceneConfig
+    d = SceneConfig(width=20, height=16, phase="hg", phase_g=0.5, max_depth=12, rr_depth=4).to_desc()
+    _, (sn, an) = media(10)
+    mn = oracle.OracleMedium(d, sn, an, majorant_factor=factor)
+    H, W = d.film_height, d.film_width
+    grad_img = (np.random.default_rng(5).standard_normal((H, W, 3)) / (H * W * 3)).astype(np.float32)
+    seed_grad, spp = 77, 3
+    film_w = oracle.film_weights(d, seed_grad, spp)
+    g1 = np.zeros((*sn.shape[:3], 1), np.float32); g4 = np.zeros((*sn.shape[:3], 4), np.float32)
+    cnt = np.zeros(8, np.uint64)
+    emu.emu_vps_backward_lane(C.addressof(d), sn, an, *sn.shape[:3], seed_grad, spp, oracle.alt_seed(seed_grad),
+                              grad_img.ctypes.data, film_w.ctypes.data, g1, g4, cnt, factor, flags)
+    oracle.counters(True)
+    gs, ga = oracle.vps_backward(d, mn, seed_grad, spp, grad_img, threads=1, film_w=film_w, use_drt=bool(flags & 1),
+                                 use_drt_subsampling=bool(flags & 2), use_drt_mis=bool(flags & 4))
+    oc = oracle.counters(True)
+    assert [int(v) for v in cnt[2:7]] == [int(v) for v in oc[2:7]]
+    assert rel_l2(g1, gs) < 1e-5       # float vs double accumulation
+    assert rel_l2(g4[..., 0:3], ga) < 1e-5

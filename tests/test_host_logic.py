@@ -80,8 +80,10 @@ def test_load_dict_and_properties():
 def test_error_behaviour_matches_reference():
     with pytest.raises(ValueError):          # cv_integrator.py:19-20
         mi.load_dict({"type": "cv", "integrator": {"type": "volpathsimple"}})
-    with pytest.raises(NotImplementedError):
-        mi.load_dict({"type": "volpathsimple", "use_drt": True})
+    vps = mi.load_dict({"type": "volpathsimple"})                      # volpathsimple.py:39-47: DRT is on by default
+    assert vps.use_drt and vps.use_drt_subsampling and vps.use_drt_mis
+    vps = mi.load_dict({"type": "volpathsimple", "use_drt": False, "use_drt_mis": False})
+    assert not vps.use_drt and vps.use_drt_subsampling and not vps.use_drt_mis
     with pytest.raises(NotImplementedError):  # OptiX denoiser + AOVs: outside the hot path
         mi.load_dict({"type": "meta", "method": "cv_pss", "denoise": True, "integrator": {"type": "prbvolpath"}})
     with pytest.raises(NotImplementedError):

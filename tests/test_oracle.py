@@ -148,6 +148,33 @@ def test_adjoint_matches_finite_differences(oracle):
     assert abs(float((ga * alb).sum()) - fd_a) < 0.03 * abs(fd_a)
 
 
+def test_drt_scattering_term_agrees_with_path_replay(oracle):
+    """use_drt = True (volpathsimple.py:520-594, :623-778; oracle only): differential ratio tracking, with and without
+    the reservoir sub-sampling and the sigma_t^2 / (1 + sigma_t^2) MIS, estimates the same gradient as the default
+    in-scattering term."""
+    from recursive_control_variates_b200.scene import SceneConfig
+    from recursive_control_variates_b200.synthetic import make_medium
+    d = SceneConfig(width=8, height=8, max_depth=16, rr_depth=16).to_desc()
+    sig, alb = make_medium(4, "cube", 0.0)
+    sig = (sig * 0.6 + 0.2).astype(np.float32)
+    gimg = (np.random.default_rng(0).random((8, 8, 3)) / 192).astype(np.float32)
+    m = oracle.OracleMedium(d, sig, alb)
+
+    def sums(**kw):
+        g = [oracle.vps_backward(d, m, seed, 4096, gimg, **kw) for seed in (11, 22)]
+        return np.mean([float((gs * sig).sum()) for gs, _ in g]), np.mean([float((ga * alb).sum()) for _, ga in g])
+
+    ref_s, ref_a = sums()
+    for kw in (dict(), dict(use_drt_mis=False), dict(use_drt_subsampling=False)):
+        s, a = sums(use_drt=True, **kw)
+        assert abs(s - ref_s) < 0.04 * abs(ref_s), (kw, s, ref_s)
+        assert abs(a - ref_a) < 0.01 * abs(ref_a), (kw, a, ref_a)
+    # the flag changes the estimator, not only its name
+    g0 = oracle.vps_backward(d, m, 11, 64, gimg)[0]
+    g1 = oracle.vps_backward(d, m, 11, 64, gimg, use_drt=True)[0]
+    assert not np.array_equal(g0, g1)
+
+
 def test_adam_clamp_upsample(oracle):
     p = np.array([0.5, 1.0], np.float32); g = np.array([1.0, -2.0], np.float32)
     m = np.zeros(2, np.float32); v = np.zeros(2, np.float32)
