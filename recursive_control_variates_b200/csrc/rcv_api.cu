@@ -69,6 +69,8 @@ struct rcv_ctx {
     size_t film_w_pix = 0;
     PathQueue queue{nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t queue_cap = 0;
+    PathQueue jobs{nullptr, nullptr, nullptr, nullptr, nullptr};     // DRT job records (use_drt on the pool tracer)
+    size_t jobs_cap = 0;
     float4 *arena = nullptr;      // vertex records of the adjoint: slots x (max_depth + 1) x 64 B
     size_t arena_records = 0;
     uint32_t vcap = 0;
@@ -89,7 +91,7 @@ struct rcv_ctx {
     LaunchCfg cfg() {
         LaunchCfg c;
         c.stream = stream; c.sm_count = sm_count; c.tracer = tracer; c.drt_flags = drt_flags;
-        c.counters = counters; c.work_counter = work; c.launches = &launches; c.queue = queue;
+        c.counters = counters; c.work_counter = work; c.launches = &launches; c.queue = queue; c.jobs = jobs;
         c.arena = arena; c.vcap = vcap;
         return c;
     }
@@ -183,9 +185,26 @@ int ensure_queue(rcv_ctx *c, uint32_t spp_begin, uint32_t spp_end) {
     return RCV_OK;
 }
 
-// vertex-record arena of the vertex-list adjoint: one slot of (max_depth + 1) records per lane in flight
+// job records of the DRT stages: one per lane of the launch
+int ensure_jobs(rcv_ctx *c, uint32_t spp_begin, uint32_t spp_end) {
+    size_t n = (size_t) c->S.W * c->S.H * (spp_end - spp_begin);
+    if (!c->jobs.count) CK(cudaMalloc(&c->jobs.count, sizeof(unsigned long long)));
+    if (n > c->jobs_cap) {
+        cudaFree(c->jobs.r0); cudaFree(c->jobs.r1); cudaFree(c->jobs.r2); cudaFree(c->jobs.r3);
+        c->jobs.r0 = c->jobs.r1 = c->jobs.r2 = c->jobs.r3 = nullptr; c->jobs_cap = 0;
+        CK(cudaMalloc(&c->jobs.r0, n * sizeof(float4)));
+        CK(cudaMalloc(&c->jobs.r1, n * sizeof(float4)));
+        CK(cudaMalloc(&c->jobs.r2, n * sizeof(float4)));
+        CK(cudaMalloc(&c->jobs.r3, n * sizeof(float4)));
+        c->jobs_cap = n;
+    }
+    return RCV_OK;
+}
+
+// vertex-record arena of the vertex-list adjoint: one slot of (max_depth + 1) vertex records per lane in flight, one
+// spare record (the DRT reservoir) and the shadow-ray collision records
 int ensure_arena(rcv_ctx *c) {
-    c->vcap = (uint32_t) c->S.max_depth + 1u;
+    c->vcap = (uint32_t) c->S.max_depth + 2u;
     size_t need = vps_backward_slots(c->cfg()) * ((size_t) c->vcap + 16);      // + the shadow-ray collision records (kNeeCap / 4)
     if (need > c->arena_records) {
         cudaFree(c->arena); c->arena = nullptr; c->arena_records = 0;
@@ -273,7 +292,8 @@ int rcv_ctx_destroy(rcv_ctx *c) {
     cudaSetDevice(c->device);
     free_medium(c);
     cudaFree(c->counters); cudaFree(c->work); cudaFree(c->majorants); cudaFree(c->film_w); cudaFree(c->loss_partial);
-    cudaFree(c->queue.r0); cudaFree(c->queue.r1); cudaFree(c->queue.r2); cudaFree(c->queue.r3); cudaFree(c->queue.count); cudaFree(c->arena); cudaFree(c->mgrid);
+    cudaFree(c->queue.r0); cudaFree(c->queue.r1); cudaFree(c->queue.r2); cudaFree(c->queue.r3); cudaFree(c->queue.count);
+    cudaFree(c->jobs.r0); cudaFree(c->jobs.r1); cudaFree(c->jobs.r2); cudaFree(c->jobs.r3); cudaFree(c->jobs.count); cudaFree(c->arena); cudaFree(c->mgrid);
     auto &E = c->e2e;
     cudaFree(E.sigma); cudaFree(E.albedo); cudaFree(E.ref); cudaFree(E.acc); cudaFree(E.HF); cudaFree(E.cv);
     cudaFree(E.grad_img); cudaFree(E.loss); cudaFree(E.g_sigma); cudaFree(E.g_albedo);
@@ -496,8 +516,13 @@ int rcv_render_backward_weighted(rcv_ctx *c, int adjoint_kind, uint32_t seed_gra
     // deep paths (max_depth = -1 ...) would need an unbounded vertex arena: use the replaying schedule for them
     const int saved_tracer = c->tracer;
     if ((c->tracer == RCV_TRACER_POOL || c->tracer == RCV_TRACER_WAVEFRONT) && c->S.max_depth >= 4096) c->tracer = RCV_TRACER_BATCH;
-    if ((c->tracer == RCV_TRACER_POOL || c->tracer == RCV_TRACER_WAVEFRONT) && !(c->drt_flags & 1))
+    // use_drt: sub-sampling on the pool tracer runs on the event machines (arena + job records), every other
+    // combination on the one-thread-per-lane kernel, which needs neither
+    const bool drt_pool = (c->drt_flags & 3) == 3 && c->tracer == RCV_TRACER_POOL;
+    if ((c->tracer == RCV_TRACER_POOL || c->tracer == RCV_TRACER_WAVEFRONT) && (!(c->drt_flags & 1) || drt_pool))
         if (int r = ensure_arena(c)) { c->tracer = saved_tracer; return r; }
+    if (drt_pool)
+        if (int r = ensure_jobs(c, spp_begin, spp_end)) { c->tracer = saved_tracer; return r; }
     LaunchCfg cfg = c->cfg();
     c->tracer = saved_tracer;
     if (!film_w) {       // no weights supplied: those of ALL spp_grad samples are computed here

@@ -15,6 +15,7 @@ struct LaunchCfg {
     Counters *counters;   // device
     unsigned long long *work_counter;   // device, persistent-kernel work queue head
     PathQueue queue;                    // device, path records of the wavefront schedule
+    PathQueue jobs;                     // device, DRT job records (use_drt on the pool tracer), else null
     float4 *arena;                      // device, vertex records of the adjoint (4 float4 each)
     uint32_t vcap;                      // records per arena slot
     uint64_t *launches;   // host-side launch counter

@@ -473,13 +473,32 @@ __global__ void __launch_bounds__(kPoolBlock, RCV_TS_POOL_MINBLOCKS) k_twostates
     counter_flush(C, 6, sk.n_paths);
 }
 
-template <bool BACKWARD, class GRID>
+// DRT stages 1 and 2 (rcv_volpathsimple_wf.cuh): what the scheduler does with a lane that just completed (VF_JOB).
+// Called by the whole warp; `done` is false for threads without such a lane.
+template <int DRT, class GRID>
+__device__ __forceinline__ void pool_drt_complete(const SceneK &S, const GRID &G, VpLane &ln, VpSink &sk, bool done) {
+    if (DRT == 1) {
+        float4 job[4];
+        const bool want = done && vp_drt_job(ln, sk, job);
+        const unsigned long long pos = queue_slot(sk.jobs.count, want);
+        if (want) { sk.jobs.r0[pos] = job[0]; sk.jobs.r1[pos] = job[1]; sk.jobs.r2[pos] = job[2]; sk.jobs.r3[pos] = job[3]; }
+    }
+    if (DRT == 2) {
+        if (done) {
+            float4 a = sk.jobs.r0[ln.pix], b = sk.jobs.r1[ln.pix];
+            vp_drt_scatter(S, G, sk.D, mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), ln.result, sk.cnt);
+        }
+    }
+    if (done) ln.flags = 0;
+}
+
+template <bool BACKWARD, class GRID, int DRT = 0>
 __global__ void __launch_bounds__(kPoolBlock, RCV_POOL_MINBLOCKS) k_vps_pool(const __grid_constant__ SceneK S,
                                                                              const __grid_constant__ GRID G, GradK D, uint32_t seed,
                                                                              uint32_t spp, uint32_t alt_seed, const float *grad_img,
                                                                              const float *film_w, float4 *accum, PathQueue Q,
                                                                              Counters *C, unsigned long long *work, float4 *arena,
-                                                                             uint32_t vcap) {
+                                                                             uint32_t vcap, PathQueue jobs, int drt_mis) {
     extern __shared__ float smem[];
     const unsigned lane = threadIdx.x & 31;
     float *pw = smem + (threadIdx.x >> 5) * pool_warp_floats<kVpWords>();
@@ -492,6 +511,7 @@ __global__ void __launch_bounds__(kPoolBlock, RCV_POOL_MINBLOCKS) k_vps_pool(con
     sk.accum = accum; sk.D = D; sk.grad_img = grad_img; sk.film_w = film_w; sk.arena = arena; sk.vcap = vcap;
     sk.seed = seed; sk.spp = spp; sk.alt_seed = alt_seed;
     sk.cnt.coll = sk.cnt.scat = sk.cnt.g_sig = sk.cnt.g_alb = 0; sk.n_paths = 0;
+    sk.jobs = jobs; sk.drt_mis = drt_mis;
     const uint32_t slot0 = (blockIdx.x * kPoolWarps + (threadIdx.x >> 5)) * kPoolSlots;   // first arena slot of this warp's pool
     ChunkCursor cc; cc.next = 0; cc.end = 0; cc.more = true;
     cls[lane] = EV_INIT; cls[lane + 32] = EV_INIT;
@@ -522,10 +542,11 @@ __global__ void __launch_bounds__(kPoolBlock, RCV_POOL_MINBLOCKS) k_vps_pool(con
             if (s >= 0) {
                 vp_pool_load_hot(pw, s, ln); vp_pool_load_cold(pw, s, ln);
                 ln.ev = EV_SCAT;
-                vp_vertex<BACKWARD>(S, G, ln, sk);
+                vp_vertex<BACKWARD, DRT>(S, G, ln, sk);
                 vp_pool_store_all(pw, s, ln);
                 cls[s] = (unsigned char) ln.ev;
             }
+            if (DRT != 0) pool_drt_complete<DRT>(S, G, ln, sk, s >= 0 && ln.ev == EV_INIT && (ln.flags & VF_JOB));
         } else {
             const int s = pool_select(slow_lo, slow_hi, list);
             ln.ev = EV_INIT; ln.flags = 0;
@@ -534,13 +555,14 @@ __global__ void __launch_bounds__(kPoolBlock, RCV_POOL_MINBLOCKS) k_vps_pool(con
                 vp_pool_load_hot(pw, s, ln); vp_pool_load_cold(pw, s, ln);
                 loaded = true;
                 ln.ev = EV_SLOW;
-                vp_slow<BACKWARD>(S, G, ln, sk);
+                vp_slow<BACKWARD, DRT>(S, G, ln, sk);
             }
+            if (DRT != 0) pool_drt_complete<DRT>(S, G, ln, sk, s >= 0 && ln.ev == EV_INIT && (ln.flags & VF_JOB));
             // empty slots take the next record
             unsigned m_need = __ballot_sync(0xffffffffu, s >= 0 && ln.ev == EV_INIT);
             if (m_need && cc.more) {
                 unsigned long long pos = take_positions(cc, work, n_total, m_need);
-                if (pos != ~0ull) { vp_load(ln, sk, Q, pos, slot0 + (uint32_t) s); loaded = true; }
+                if (pos != ~0ull) { vp_load<DRT>(ln, sk, Q, pos, slot0 + (uint32_t) s); loaded = true; }
             }
             if (s >= 0) {
                 if (loaded && ln.ev != EV_INIT) vp_pool_store_all(pw, s, ln);
@@ -554,6 +576,38 @@ __global__ void __launch_bounds__(kPoolBlock, RCV_POOL_MINBLOCKS) k_vps_pool(con
     counter_flush(C, 4, sk.cnt.g_sig);
     counter_flush(C, 5, sk.cnt.g_alb);
     counter_flush(C, 6, sk.n_paths);
+}
+
+// DRT, between the stages: one thread per job record (vp_drt_sample).  Estimates that are complete are scattered
+// here; the others become path records of the recursive radiance estimate (stage 2) in Q, with what to scatter at
+// their end left in the job's own slot.
+template <class GRID>
+__global__ void __launch_bounds__(kBlock) k_drt_sample(const __grid_constant__ SceneK S, const __grid_constant__ GRID G, GradK D,
+                                                       PathQueue JQ, PathQueue Q, int use_mis, Counters *C) {
+    VpsCounts cnt; cnt.coll = cnt.scat = cnt.g_sig = cnt.g_alb = 0;
+    const unsigned long long n = *JQ.count;
+    const unsigned long long stride = (unsigned long long) gridDim.x * kBlock;
+    for (unsigned long long base = (unsigned long long) blockIdx.x * kBlock; base < n; base += stride) {
+        const unsigned long long i = base + threadIdx.x;
+        int r = 0;
+        float4 rec[4];
+        V3 p, c, Li;
+        if (i < n) {
+            float4 job[4] = {__ldg(JQ.r0 + i), __ldg(JQ.r1 + i), __ldg(JQ.r2 + i), __ldg(JQ.r3 + i)};
+            r = vp_drt_sample(S, G, D, job, use_mis != 0, rec, p, c, Li, cnt);
+            if (r == 1) vp_drt_scatter(S, G, D, p, c, Li, cnt);
+        }
+        const unsigned long long pos = queue_slot(Q.count, r == 2);
+        if (r == 2) {
+            rec[0].w = __uint_as_float((uint32_t) i);
+            Q.r0[pos] = rec[0]; Q.r1[pos] = rec[1]; Q.r2[pos] = rec[2]; Q.r3[pos] = rec[3];
+            JQ.r0[i] = make_float4(p.x, p.y, p.z, c.x);
+            JQ.r1[i] = make_float4(c.y, c.z, 0.f, 0.f);
+        }
+    }
+    counter_flush(C, 2, cnt.coll);
+    counter_flush(C, 4, cnt.g_sig);
+    counter_flush(C, 5, cnt.g_alb);
 }
 
 // launch a pool kernel: dynamic shared memory opt-in, persistent grid
@@ -650,6 +704,29 @@ static cudaError_t launch_vps(const LaunchCfg &cfg, const SceneK &S, const GRID 
     uint64_t n_local = (uint64_t) S.W * S.H * ns;
     if (n_local == 0) return cudaSuccess;
     cudaError_t e;
+    if (BACKWARD && (cfg.drt_flags & 3) == 3 && cfg.tracer == 3) {
+        // use_drt with sub-sampling on the pool machines: adjoint + reservoir -> jobs -> recursive radiance estimate
+        const size_t smem = kPoolWarps * pool_warp_floats<kVpWords>() * sizeof(float);
+        const int mis = (cfg.drt_flags & 4) ? 1 : 0;
+        if ((e = cudaMemsetAsync(cfg.work_counter, 0, sizeof(unsigned long long), cfg.stream)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(cfg.queue.count, 0, sizeof(unsigned long long), cfg.stream)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(cfg.jobs.count, 0, sizeof(unsigned long long), cfg.stream)) != cudaSuccess) return e;
+        k_vps_raygen<true><<<(unsigned) ((n_local + kBlock - 1) / kBlock), kBlock, 0, cfg.stream>>>(
+            S, seed, spp, spp_begin, ns, n_local, accum, cfg.queue, cfg.counters, grad_img, film_w);
+        e = launch_pool(cfg, k_vps_pool<true, GRID, 1>, smem, n_local, S, G, D, seed, spp, alt_seed, grad_img, film_w, accum,
+                        cfg.queue, cfg.counters, cfg.work_counter, cfg.arena, cfg.vcap, cfg.jobs, mis);
+        if (e != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(cfg.queue.count, 0, sizeof(unsigned long long), cfg.stream)) != cudaSuccess) return e;
+        unsigned blocks;
+        if ((e = persistent_grid(cfg, k_drt_sample<GRID>, kBlock, n_local, blocks)) != cudaSuccess) return e;
+        k_drt_sample<GRID><<<blocks, kBlock, 0, cfg.stream>>>(S, G, D, cfg.jobs, cfg.queue, mis, cfg.counters);
+        if ((e = cudaMemsetAsync(cfg.work_counter, 0, sizeof(unsigned long long), cfg.stream)) != cudaSuccess) return e;
+        e = launch_pool(cfg, k_vps_pool<false, GRID, 2>, smem, n_local, S, G, D, seed, spp, alt_seed, grad_img, film_w, accum,
+                        cfg.queue, cfg.counters, cfg.work_counter, cfg.arena, cfg.vcap, cfg.jobs, mis);
+        if (e != cudaSuccess) return e;
+        (*cfg.launches) += 4;
+        return cudaGetLastError();
+    }
     if (BACKWARD && (cfg.drt_flags & 1)) {
         unsigned blocks;
         if ((e = cudaMemsetAsync(cfg.work_counter, 0, sizeof(unsigned long long), cfg.stream)) != cudaSuccess) return e;
@@ -668,7 +745,7 @@ static cudaError_t launch_vps(const LaunchCfg &cfg, const SceneK &S, const GRID 
             S, seed, spp, spp_begin, ns, n_local, accum, qv, cfg.counters, grad_img, film_w);
         if (cfg.tracer == 3) {
             e = launch_pool(cfg, k_vps_pool<BACKWARD, GRID>, kPoolWarps * pool_warp_floats<kVpWords>() * sizeof(float), n_local, S, G, D, seed,
-                            spp, alt_seed, grad_img, film_w, accum, qv, cfg.counters, cfg.work_counter, cfg.arena, cfg.vcap);
+                            spp, alt_seed, grad_img, film_w, accum, qv, cfg.counters, cfg.work_counter, cfg.arena, cfg.vcap, cfg.jobs, 0);
             if (e != cudaSuccess) return e;
         } else {
             unsigned blocks;
@@ -700,6 +777,13 @@ size_t vps_backward_slots(const LaunchCfg &cfg) {
         cudaFuncSetAttribute(k_vps_pool<true, GridK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vps_pool<true, GridK>, kPoolBlock, smem) != cudaSuccess || per_sm < 1)
             per_sm = 1;
+        if (cfg.drt_flags & 1) {         // the DRT instance of the adjoint may fit a different number of blocks
+            int per_sm_drt = 0;
+            cudaFuncSetAttribute(k_vps_pool<true, GridK, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_drt, k_vps_pool<true, GridK, 1>, kPoolBlock, smem) == cudaSuccess &&
+                per_sm_drt > per_sm)
+                per_sm = per_sm_drt;
+        }
         return (size_t) per_sm * cfg.sm_count * kPoolWarps * kPoolSlots;
     }
     if (cfg.tracer == 0) {

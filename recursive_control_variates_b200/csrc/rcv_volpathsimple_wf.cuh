@@ -34,6 +34,16 @@
 //              with one or two lanes: end of a shadow ray (+ phase sampling) or of
 //              its replay, end of a pass; the scheduler refills lanes in this step
 //
+// use_drt = True with sub-sampling (volpathsimple.py:39-47, :262-272) runs on the same machines in three stages
+// (template parameter DRT of the handlers):
+//   DRT = 1  the adjoint above, plus the DRTReservoir (:743-778) kept in the lane's arena slot during pass 1 (the
+//            secondary sampler's draws of pass 2 are known in advance: one reservoir draw, then four transmittance
+//            draws per vertex), the MIS weight of the path-replay term (:165-170), and at the end of pass 2 a JOB
+//            record: selected ray, depth, adjoint weight, state of the secondary sampler
+//   (k_drt_sample, rcv_trace.cu: distance sampling, shadow ray and phase sampling of the job: :560-561, :635-654)
+//   DRT = 2  the recursive radiance estimate (:656-665): the primal machine resumed from the job's PathState on the
+//            secondary sampler; its result is scattered into the gradient grids instead of the film
+//
 // The handlers contain no warp intrinsics and also compile for the host
 // (RCV_HOST_EMU) where tests single-step them against the oracle.
 #pragma once
@@ -53,7 +63,8 @@ enum : uint32_t {
     VF_NEE_OVF = 128u,    // pass 1: the shadow ray had more tentative collisions than its record buffer holds
     // work parked for the batched EV_SLOW step
     VF_POSTNEE = 512u,    // the shadow ray (or its replay) ended
-    VF_END = 1024u        // the pass ended at a loop head (:132-133)
+    VF_END = 1024u,       // the pass ended at a loop head (:132-133)
+    VF_JOB = 2048u        // DRT: the lane is complete and its job (DRT = 1) / its gradient (DRT = 2) is to be written
 };
 
 // vertex record flags
@@ -91,6 +102,8 @@ struct VpSink {
     uint32_t seed, spp, alt_seed;
     VpsCounts cnt;
     unsigned n_paths;
+    int drt_mis;            // use_drt_mis (DRT != 0)
+    PathQueue jobs;         // DRT = 1: job records written at the end of pass 2; DRT = 2: r0/r1 = where and what to scatter
 };
 
 __device__ __forceinline__ float4 *vp_record(const VpSink &sk, const VpLane &ln, int k) {
@@ -101,14 +114,18 @@ __device__ __forceinline__ float4 *vp_nee_record(const VpSink &sk, const VpLane 
 }
 
 // end of pass 2 (or of a render-only path)
+template <int DRT = 0>
 __device__ __forceinline__ void vp_finish(VpLane &ln, VpSink &sk) {
-    sk.n_paths++;
-    ln.flags = 0;
+    if (DRT != 2) sk.n_paths++;
+    ln.flags = (DRT != 0) ? (uint32_t) VF_JOB : 0u;
     ln.ev = EV_INIT;
 }
 
+// DRTReservoir (:743-778) of the lane: the spare last record of its arena slot
+__device__ __forceinline__ float4 *vp_reservoir(const VpSink &sk, const VpLane &ln) { return vp_record(sk, ln, (int) sk.vcap - 1); }
+
 // end of pass 1: environment contribution (:276-300); then either splat (render) or start pass 2
-template <bool BW>
+template <bool BW, int DRT = 0>
 __device__ __forceinline__ void vp_end_pass(const SceneK &S, VpLane &ln, VpSink &sk) {
     if ((ln.flags & VF_ESCAPED) && !((ln.depth <= 0) && S.hide_emitters)) {
         const V3 env = mk3(S.env[0], S.env[1], S.env[2]);
@@ -117,6 +134,7 @@ __device__ __forceinline__ void vp_end_pass(const SceneK &S, VpLane &ln, VpSink 
         ln.result = ln.result + (ln.thr * w) * env;
     }
     if (!BW) {
+        if (DRT == 2) { vp_finish<2>(ln, sk); return; }   // the scheduler scatters ln.result (vp_drt_scatter)
         if (S.rfilter == 0) {
             if (ln.pix >= 0) red_add_v4(sk.accum + ln.pix, ln.result.x, ln.result.y, ln.result.z, 1.f);
         } else {
@@ -132,7 +150,7 @@ __device__ __forceinline__ void vp_end_pass(const SceneK &S, VpLane &ln, VpSink 
     ln.flags = VF_ADJ;
     ln.vk = 0;
     if (ln.nvert > 0) ln.ev = EV_SCAT;
-    else vp_finish(ln, sk);
+    else vp_finish<DRT>(ln, sk);
 }
 
 // Start of a path up to the first loop iteration: camera ray, dummy channel
@@ -182,10 +200,11 @@ __device__ __forceinline__ void vp_store(const VpLane &ln, const PathQueue &Q, u
     Q.r2[pos] = make_float4(ln.d.x, ln.d.y, ln.d.z, __uint_as_float(ln.idx));
 }
 // begin pass 1 of the path recorded at pos in arena slot `slot` (Q.r3 != null: the adjoint, the record carries dL)
+template <int DRT = 0>
 __device__ __forceinline__ void vp_load(VpLane &ln, const VpSink &sk, const PathQueue &Q, unsigned long long pos, uint32_t slot) {
     float4 a = __ldg(Q.r0 + pos), b = __ldg(Q.r1 + pos), c = __ldg(Q.r2 + pos);
     ln.dL = mk3(0, 0, 0);
-    if (Q.r3) { float4 g = __ldg(Q.r3 + pos); ln.dL = mk3(g.x, g.y, g.z); }
+    if (DRT != 2 && Q.r3) { float4 g = __ldg(Q.r3 + pos); ln.dL = mk3(g.x, g.y, g.z); }
     ln.rng.state = (uint64_t) __float_as_uint(a.x) | ((uint64_t) __float_as_uint(a.y) << 32);
     ln.rng.inc = ((uint64_t) __float_as_uint(a.z) << 1) | 1u;
     ln.pix = (int) __float_as_uint(a.w);
@@ -200,6 +219,22 @@ __device__ __forceinline__ void vp_load(VpLane &ln, const VpSink &sk, const Path
     ln.vbase = slot * (sk.vcap + kNeeCap / 4);
     ln.nvert = 0; ln.vk = 0;
     ln.ev = EV_COLL;
+    if (DRT == 1) {
+        // the secondary sampler (:119-120) already in pass 1, for the reservoir's draws; pass 2 re-seeds it
+        sampler_seed(ln.alt, sk.alt_seed, ln.idx);
+        float4 *R = vp_reservoir(sk, ln);
+        R[0] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));        // wsum, selected vertex
+        R[1] = make_float4(0.f, 0.f, 0.f, 0.f);                       // current_weight
+    }
+    if (DRT == 2) {
+        // PathState of the recursive call (:75-81, :98-100, :656-665): a path record written by k_drt_sample.
+        // pix = its job, idx word = depth, r3 = radiance so far (the NEE of :635-638) and the phase pdf
+        float4 g = __ldg(Q.r3 + pos);
+        ln.depth = (int) ln.idx; ln.idx = 0;
+        ln.result = mk3(g.x, g.y, g.z);
+        ln.last_pdf = g.w;
+        ln.flags = VF_HEAD | VF_HAS_SCAT;
+    }
 }
 
 // (re)start the shadow ray at the current vertex; false when it has no extent
@@ -213,12 +248,12 @@ __device__ __forceinline__ bool vp_nee_start(const SceneK &S, VpLane &ln) {
 }
 
 // pass 1, after the vertex (and its NEE): phase sampling, new ray, boundary distance (:234-258)
-template <bool BW>
+template <bool BW, int DRT = 0>
 __device__ __forceinline__ void vp_post_vertex(const SceneK &S, VpLane &ln, VpSink &sk, bool active) {
     const bool did_scatter = (ln.flags & VF_DID_SCATTER) != 0;
     if (!did_scatter) {                                               // did_escape (:257-258)
         ln.flags |= VF_ESCAPED;
-        vp_end_pass<BW>(S, ln, sk);
+        vp_end_pass<BW, DRT>(S, ln, sk);
         return;
     }
     V3 mei_p = ray_at(ln.o, ln.d, ln.mei_t);
@@ -232,13 +267,13 @@ __device__ __forceinline__ void vp_post_vertex(const SceneK &S, VpLane &ln, VpSi
     Hit si = box_hit(S, ln.o, ln.d, ln.id, RCV_LARGEST);              // :247
     ln.ray_maxt = isfinite(si.t) ? si.t : RCV_LARGEST;                // :248
     if (!si.valid) active = false;                                    // :253-254
-    if (!active) { vp_end_pass<BW>(S, ln, sk); return; }
+    if (!active) { vp_end_pass<BW, DRT>(S, ln, sk); return; }
     ln.flags |= VF_HEAD;
     ln.ev = EV_COLL;
 }
 
 // pass 1: the shadow ray ended — its contribution (:401-404, :225), the vertex record, then the path continues
-template <bool BW>
+template <bool BW, int DRT = 0>
 __device__ __forceinline__ void vp_nee_done(const SceneK &S, const GridK &G, VpLane &ln, VpSink &sk) {
     V3 wi = mk3(-ln.d.x, -ln.d.y, -ln.d.z);
     V3 emitted = mk3(S.env_over_pdf[0], S.env_over_pdf[1], S.env_over_pdf[2]) * splat3(ln.tr_acc);
@@ -265,19 +300,21 @@ __device__ __forceinline__ void vp_nee_done(const SceneK &S, const GridK &G, VpL
         ln.flags &= ~VF_NEE_OVF;
     }
     ln.flags &= ~VF_IN_NEE;
-    vp_post_vertex<BW>(S, ln, sk, true);
+    vp_post_vertex<BW, DRT>(S, ln, sk, true);
 }
 
 // pass 2: the replay of a shadow ray ended (:227), next vertex
+template <int DRT = 0>
 __device__ __forceinline__ void vp_next_vertex(VpLane &ln, VpSink &sk) {
     ln.vk += 1;
     if (ln.vk < ln.nvert) ln.ev = EV_SCAT;
-    else vp_finish(ln, sk);
+    else vp_finish<DRT>(ln, sk);
 }
+template <int DRT = 0>
 __device__ __forceinline__ void vp_replay_done(VpLane &ln, VpSink &sk) {
     ln.result = ln.result - ln.nee;                                   // :227
     ln.flags &= ~(VF_IN_NEE | VF_REPLAY);
-    vp_next_vertex(ln, sk);
+    vp_next_vertex<DRT>(ln, sk);
 }
 
 template <bool BW, class GRID>
@@ -343,24 +380,39 @@ __device__ __forceinline__ void vp_collide(const SceneK &S, const GRID &G, float
 }
 
 // the batched slow step (see the header comment)
-template <bool BW>
+template <bool BW, int DRT = 0>
 __device__ __forceinline__ void vp_slow(const SceneK &S, const GridK &G, VpLane &ln, VpSink &sk) {
     if (ln.flags & VF_POSTNEE) {
         ln.flags &= ~VF_POSTNEE;
         ln.ev = EV_COLL;
-        if (BW && (ln.flags & VF_ADJ)) vp_replay_done(ln, sk);
-        else vp_nee_done<BW>(S, G, ln, sk);
+        if (BW && (ln.flags & VF_ADJ)) vp_replay_done<DRT>(ln, sk);
+        else vp_nee_done<BW, DRT>(S, G, ln, sk);
     } else {
         ln.flags &= ~VF_END;
-        vp_end_pass<BW>(S, ln, sk);
+        vp_end_pass<BW, DRT>(S, ln, sk);
     }
 }
 
 // pass 1 vertex: albedo gather, throughput/depth update (:150-213), vertex record, NEE set-up or continuation
-template <bool BW>
+template <bool BW, int DRT = 0>
 __device__ __forceinline__ void vp_vertex1(const SceneK &S, const GridK &G, VpLane &ln, VpSink &sk) {
     const bool did_scatter = (ln.flags & VF_DID_SCATTER) != 0;
     if (did_scatter) ln.flags |= VF_HAS_SCAT;                         // :150
+    if (DRT == 1) {
+        // DRTReservoir.update (:546, :757-765) with the throughput at the head of this iteration.  The draw is the
+        // first one the secondary sampler makes for this vertex in pass 2; the four that follow belong to the
+        // transmittance term (:608)
+        float xi = pcg_f32(ln.alt);
+        (void) pcg_u32(ln.alt); (void) pcg_u32(ln.alt); (void) pcg_u32(ln.alt); (void) pcg_u32(ln.alt);
+        float4 *R = vp_reservoir(sk, ln);
+        float4 a = R[0];
+        V3 wsum = mk3(a.x, a.y, a.z) + ln.thr;
+        if (xi <= mean3(ln.thr / wsum)) {
+            a.w = __int_as_float(ln.nvert);
+            R[1] = make_float4(ln.thr.x, ln.thr.y, ln.thr.z, 0.f);
+        }
+        R[0] = make_float4(wsum.x, wsum.y, wsum.z, a.w);
+    }
     V3 albedo = mk3(1, 1, 1);
     if (did_scatter) {
         V3 mei_p = ray_at(ln.o, ln.d, ln.mei_t);                      // :384
@@ -386,14 +438,16 @@ __device__ __forceinline__ void vp_vertex1(const SceneK &S, const GridK &G, VpLa
         ln.flags |= VF_IN_NEE;
         ln.running_t = __int_as_float(0);                             // shadow-ray collision records (vp_collide)
         ln.ev = EV_COLL;
-        if (!vp_nee_start(S, ln)) vp_nee_done<BW>(S, G, ln, sk);
+        if (!vp_nee_start(S, ln)) vp_nee_done<BW, DRT>(S, G, ln, sk);
         return;
     }
-    vp_post_vertex<BW>(S, ln, sk, active);
+    vp_post_vertex<BW, DRT>(S, ln, sk, active);
 }
 
 // pass 2 vertex: the gradient terms of vertex vk, then the replay of its shadow ray
+template <int DRT = 0>
 __device__ __forceinline__ void vp_vertex2(const SceneK &S, const GridK &G, VpLane &ln, VpSink &sk) {
+    if (DRT == 1) (void) pcg_u32(ln.alt);                             // the reservoir's draw (:546), used in pass 1
     const float4 *r = vp_record(sk, ln, ln.vk);
     float4 r0 = r[0], r1 = r[1];
     ln.o = mk3(r0.x, r0.y, r0.z); ln.d = mk3(r1.x, r1.y, r1.z);
@@ -407,13 +461,17 @@ __device__ __forceinline__ void vp_vertex2(const SceneK &S, const GridK &G, VpLa
         float st = lookup_sigma1(S, G, T);                            // :386-388
         V3 albedo = lookup_albedo(G, T, 1);                           // :154
         sk.cnt.scat++;
-        // scattering term (:165-185): backward_from(dL * (sigma_t * albedo) * Li * inv_pdf)
+        // scattering term (:165-185): backward_from(drt_mis_weight * dL * (sigma_t * albedo) * Li * inv_pdf)
         V3 inv_pdf = splat3(1.f / st);
         V3 Li = ln.result / vmax3(splat3(1e-8f), albedo);
         V3 c = (ln.dL * Li) * inv_pdf;
+        if (DRT == 1) {                                               // :167-170 (the term is dropped without MIS, :165)
+            float s2 = st * st;
+            c = c * (s2 / (1.f + s2));
+        }
         float g_st = (c.x * albedo.x + c.y * albedo.y) + c.z * albedo.z;
         V3 g_al = c * splat3(st);
-        if (T.inside) {
+        if (T.inside && (DRT != 1 || sk.drt_mis)) {
             float sg = S.scale * g_st;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -440,7 +498,7 @@ __device__ __forceinline__ void vp_vertex2(const SceneK &S, const GridK &G, VpLa
         float4 r2 = r[2], r3 = r[3];
         ln.nee = mk3(r2.z, r2.w, r3.x);
         ln.result = ln.result - ln.nee;                               // :227
-        vp_next_vertex(ln, sk);
+        vp_next_vertex<DRT>(ln, sk);
         return;
     }
     if (vf & VR_NEE) {                                                // :406-414: replay with the cloned sampler
@@ -452,16 +510,114 @@ __device__ __forceinline__ void vp_vertex2(const SceneK &S, const GridK &G, VpLa
         ln.id = rcp3(ln.nd);
         ln.flags |= VF_IN_NEE | VF_REPLAY;
         ln.ev = EV_COLL;
-        if (!vp_nee_start(S, ln)) vp_replay_done(ln, sk);
+        if (!vp_nee_start(S, ln)) vp_replay_done<DRT>(ln, sk);
         return;
     }
-    vp_next_vertex(ln, sk);
+    vp_next_vertex<DRT>(ln, sk);
 }
 
-template <bool BW>
+template <bool BW, int DRT = 0>
 __device__ __forceinline__ void vp_vertex(const SceneK &S, const GridK &G, VpLane &ln, VpSink &sk) {
-    if (BW && (ln.flags & VF_ADJ)) vp_vertex2(S, G, ln, sk);
-    else vp_vertex1<BW>(S, G, ln, sk);
+    if (BW && (ln.flags & VF_ADJ)) vp_vertex2<DRT>(S, G, ln, sk);
+    else vp_vertex1<BW, DRT>(S, G, ln, sk);
+}
+
+// ---------------------------------------------------------------------------
+// DRT stages (see the header comment).  Job record at index i of a PathQueue:
+//   r0 = secondary sampler (state lo, state hi, inc >> 1), depth     r1 = ray origin, adjoint.x
+//   r2 = ray direction, adjoint.y                                     r3 = adjoint.z
+// ---------------------------------------------------------------------------
+// DRT = 1, a lane whose pass 2 just ended (VF_JOB): DRTReservoir.get (:768-772) and the delayed estimate's inputs
+// (:262-272).  false: the reservoir is empty, nothing to estimate.
+__device__ __forceinline__ bool vp_drt_job(const VpLane &ln, const VpSink &sk, float4 job[4]) {
+    const float4 *R = vp_reservoir(sk, ln);
+    float4 a = R[0], b = R[1];
+    const int sel = __float_as_int(a.w);
+    if (sel < 0) return false;
+    V3 wsum = mk3(a.x, a.y, a.z), cur = mk3(b.x, b.y, b.z);
+    float dn = mean3(cur);
+    V3 wgt = (dn != 0.f) ? cur * (mean3(wsum) / dn) : mk3(0, 0, 0);
+    V3 adjoint = wgt * ln.dL;
+    const float4 *r = vp_record(sk, ln, sel);
+    float4 r0 = r[0], r1 = r[1];
+    job[0] = make_float4(__uint_as_float((uint32_t) ln.alt.state), __uint_as_float((uint32_t) (ln.alt.state >> 32)),
+                         __uint_as_float((uint32_t) (ln.alt.inc >> 1)), __int_as_float(sel));   // depth == vertex index
+    job[1] = make_float4(r0.x, r0.y, r0.z, adjoint.x);
+    job[2] = make_float4(r1.x, r1.y, r1.z, adjoint.y);
+    job[3] = make_float4(adjoint.z, 0.f, 0.f, 0.f);
+    return true;
+}
+
+// backward_from(mis * drt_weight * adjoint * (sigma_t * albedo) * drt_Li) (:587-591) at p, c = mis * drt_weight * adjoint
+template <class GRID>
+__device__ __forceinline__ void vp_drt_scatter(const SceneK &S, const GRID &G, const GradK &D, V3 p, V3 c, V3 Li, VpsCounts &cnt) {
+    Tri T = tri_setup(S, G, p);
+    float st = lookup_sigma1(S, G, T);
+    V3 albedo = lookup_albedo(G, T, 1);
+    c = c * Li;
+    float g_st = (c.x * albedo.x + c.y * albedo.y) + c.z * albedo.z;
+    V3 g_al = c * splat3(st);
+    if (T.inside) {
+        float sg = S.scale * g_st;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float w = tri_weight(T, k);
+            uint32_t v = tri_voxel(G, T, k);
+            red_add_f32(D.gsig + v, w * sg);
+            red_add_v4(D.galb + v, w * g_al.x, w * g_al.y, w * g_al.z, 0.f);
+        }
+        cnt.g_sig++; cnt.g_alb++;
+    }
+}
+
+// The job between the stages (:551-578 up to the recursive call): distance sampling on the selected ray, the shadow
+// ray and the phase sample of sample_recursive, all on the secondary sampler.  Returns 0 when there is nothing to
+// scatter, 1 when the estimate is complete (Li holds it; the recursive path would start beyond max_depth), 2 when
+// the recursive path is to be traced: rec[] is its path record (see vp_load<2>), p / c go with it.
+template <class GRID>
+__device__ __forceinline__ int vp_drt_sample(const SceneK &S, const GRID &G, const GradK &D, const float4 job[4], bool use_mis,
+                                             float4 rec[4], V3 &p, V3 &c, V3 &Li, VpsCounts &cnt) {
+    const float mu = __ldg(G.majorants + 1), inv_mu = 1.f / mu;
+    Pcg alt;
+    alt.state = (uint64_t) __float_as_uint(job[0].x) | ((uint64_t) __float_as_uint(job[0].y) << 32);
+    alt.inc = ((uint64_t) __float_as_uint(job[0].z) << 1) | 1u;
+    const int depth = __float_as_int(job[0].w);
+    V3 o = mk3(job[1].x, job[1].y, job[1].z), d = mk3(job[2].x, job[2].y, job[2].z);
+    V3 adjoint = mk3(job[1].w, job[2].w, job[3].x);
+    V3 id = rcp3(d);
+    Hit si = box_hit(S, o, d, id, RCV_LARGEST);                       // the ray's own boundary distance (:553-555)
+    float ray_maxt = isfinite(si.t) ? si.t : RCV_LARGEST;
+    float sel_t;
+    float drt_weight = sample_interaction_drt(S, G, mu, inv_mu, alt, o, d, id, ray_maxt, true, sel_t, cnt);   // :560-561
+    if (!(sel_t < inf_())) return 0;                                  // :568
+    p = ray_at(o, d, sel_t);
+    Tri T = tri_setup(S, G, p);
+    float st = lookup_sigma1(S, G, T);
+    float mis = use_mis ? (1.f / (1.f + st * st)) : 1.f;              // :581-585
+    c = adjoint * (mis * drt_weight);
+    // sample_recursive (:623-668) up to the recursive call
+    V3 wi = mk3(-d.x, -d.y, -d.z);
+    Li = mk3(0, 0, 0);
+    if (S.use_nee) {                                                  // :635-638, throughput 1
+        V3 dir;
+        float tr = vps_sample_emitter<false>(S, G, D, mu, inv_mu, alt, p, mk3(0, 0, 0), dir, cnt);
+        V3 emitted = mk3(S.env_over_pdf[0], S.env_over_pdf[1], S.env_over_pdf[2]) * splat3(tr);
+        float phase_val = phase_eval(S, wi, dir);
+        Li = Li + ((mk3(1, 1, 1) * phase_val) * mis_weight(RCV_INV_FOURPI, phase_val)) * emitted;
+    }
+    (void) pcg_f32(alt);                                              // :644-646
+    float s2x = pcg_f32(alt), s2y = pcg_f32(alt);
+    float pdf;
+    V3 wo = phase_sample(S, wi, s2x, s2y, pdf);
+    if (!(depth + 1 < S.max_depth)) return 1;                         // :660: the recursive call starts inactive
+    (void) pcg_f32(alt);                                              // :112 of the recursive call (its alt_seed_rnd draw)
+    Hit sn = box_hit(S, p, wo, rcp3(wo), RCV_LARGEST);                // :651
+    rec[0] = make_float4(__uint_as_float((uint32_t) alt.state), __uint_as_float((uint32_t) (alt.state >> 32)),
+                         __uint_as_float((uint32_t) (alt.inc >> 1)), 0.f);      // .w: the job's index, set by the caller
+    rec[1] = make_float4(p.x, p.y, p.z, isfinite(sn.t) ? sn.t : RCV_LARGEST);   // :653-654
+    rec[2] = make_float4(wo.x, wo.y, wo.z, __uint_as_float((uint32_t) (depth + 1)));
+    rec[3] = make_float4(Li.x, Li.y, Li.z, pdf);
+    return 2;
 }
 
 }  // namespace rcv

@@ -117,8 +117,8 @@ void run_vps(const SceneK &S, const GRID &G, VpSink &sk) {
     const float inv_mu = 1.f / mu;
     uint64_t n = (uint64_t) S.W * S.H * sk.spp;
     HostQueue hq(n);
-    std::vector<float4> arena((size_t) 4 * (S.max_depth + 1) + kNeeCap);       // one arena slot: the lanes run one after the other
-    sk.arena = arena.data(); sk.vcap = (uint32_t) S.max_depth + 1u;
+    std::vector<float4> arena((size_t) 4 * (S.max_depth + 2) + kNeeCap);       // one arena slot: the lanes run one after the other
+    sk.arena = arena.data(); sk.vcap = (uint32_t) S.max_depth + 2u;
     for (uint64_t idx = 0; idx < n; ++idx) {
         VpLane ln; ln.ev = EV_INIT; ln.flags = 0;
         vp_raygen<BW>(S, ln, sk, idx);
@@ -148,9 +148,95 @@ void run_vps(const SceneK &S, const GRID &G, VpSink &sk) {
     }
 }
 
+// use_drt with sub-sampling on the event machines: stage 1 (adjoint + reservoir -> job records), the job step
+// (vp_drt_sample) and stage 2 (the recursive radiance estimate), as k_vps_pool<true, GRID, 1>, k_drt_sample and
+// k_vps_pool<false, GRID, 2> run them
+template <class GRID>
+void run_vps_drt(const SceneK &S, const GRID &G, VpSink &sk) {
+    const float mu = G.majorants[1];
+    const float inv_mu = 1.f / mu;
+    uint64_t n = (uint64_t) S.W * S.H * sk.spp;
+    HostQueue hq(n), jq(n);
+    jq.Q.r3 = jq.r3.data();
+    std::vector<float4> arena((size_t) 4 * (S.max_depth + 2) + kNeeCap);
+    sk.arena = arena.data(); sk.vcap = (uint32_t) S.max_depth + 2u;
+    sk.jobs = jq.Q;
+    hq.Q.r3 = hq.r3.data();
+    for (uint64_t idx = 0; idx < n; ++idx) {
+        VpLane ln; ln.ev = EV_INIT; ln.flags = 0;
+        vp_raygen<true>(S, ln, sk, idx);
+        if (ln.ev == EV_COLL) {
+            float fx, fy;
+            film_position(S, sk.seed, sk.spp, ln.idx, fx, fy);
+            V3 dL = film_gather(S, sk.grad_img, sk.film_w, fx, fy);
+            hq.r3[hq.count] = make_float4(dL.x, dL.y, dL.z, 0.f);
+            vp_store(ln, hq.Q, hq.count++);
+        }
+    }
+    for (unsigned long long pos = 0; pos < hq.count; ++pos) {
+        VpLane ln; ln.flags = 0;
+        vp_load<1>(ln, sk, hq.Q, pos, 0u);
+        while (ln.ev != EV_INIT) {
+            if (ln.ev == EV_COLL) vp_collide<true>(S, G, mu, inv_mu, ln, sk);
+            else if (ln.ev == EV_SCAT) vp_vertex<true, 1>(S, G, ln, sk);
+            else vp_slow<true, 1>(S, G, ln, sk);
+        }
+        float4 job[4];
+        if ((ln.flags & VF_JOB) && vp_drt_job(ln, sk, job)) {
+            jq.r0[jq.count] = job[0]; jq.r1[jq.count] = job[1]; jq.r2[jq.count] = job[2]; jq.r3[jq.count] = job[3];
+            jq.count++;
+        }
+    }
+    hq.count = 0;
+    for (unsigned long long i = 0; i < jq.count; ++i) {
+        float4 job[4] = {jq.r0[i], jq.r1[i], jq.r2[i], jq.r3[i]}, rec[4];
+        V3 p, c, Li;
+        int r = vp_drt_sample(S, G, sk.D, job, sk.drt_mis != 0, rec, p, c, Li, sk.cnt);
+        if (r == 1) vp_drt_scatter(S, G, sk.D, p, c, Li, sk.cnt);
+        if (r == 2) {
+            rec[0].w = __uint_as_float((uint32_t) i);
+            hq.r0[hq.count] = rec[0]; hq.r1[hq.count] = rec[1]; hq.r2[hq.count] = rec[2]; hq.r3[hq.count] = rec[3];
+            hq.count++;
+            jq.r0[i] = make_float4(p.x, p.y, p.z, c.x);
+            jq.r1[i] = make_float4(c.y, c.z, 0.f, 0.f);
+        }
+    }
+    for (unsigned long long pos = 0; pos < hq.count; ++pos) {
+        VpLane ln; ln.flags = 0;
+        vp_load<2>(ln, sk, hq.Q, pos, 0u);
+        while (ln.ev != EV_INIT) {
+            if (ln.ev == EV_COLL) vp_collide<false>(S, G, mu, inv_mu, ln, sk);
+            else if (ln.ev == EV_SCAT) vp_vertex<false, 2>(S, G, ln, sk);
+            else vp_slow<false, 2>(S, G, ln, sk);
+        }
+        if (ln.flags & VF_JOB) {
+            float4 a = jq.r0[ln.pix], b = jq.r1[ln.pix];
+            vp_drt_scatter(S, G, sk.D, mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), ln.result, sk.cnt);
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" {
+
+// the three DRT stages of the pool tracer (use_drt + use_drt_subsampling; use_mis = use_drt_mis)
+int emu_vps_drt_stages(const rcv_scene_desc *d, const float *sn, const float *an, int nz, int ny, int nx, uint32_t seed, uint32_t spp,
+                       uint32_t alt_seed, const float *grad_img, const float *film_w, float *gsig, float *galb4,
+                       uint64_t *counters, int factor, int use_mis) {
+    SceneK S; scene_from_desc(*d, S);
+    Packed P; pack(*d, sn, an, sn, an, nz, ny, nx, P, factor);
+    for (int i = 0; i < 8; ++i) counters[i] = 0;
+    VpSink sk; sk.accum = nullptr; sk.D.gsig = gsig; sk.D.galb = (float4 *) galb4; sk.grad_img = grad_img; sk.film_w = film_w;
+    sk.seed = seed; sk.spp = spp; sk.alt_seed = alt_seed; sk.drt_mis = use_mis;
+    sk.cnt.coll = sk.cnt.scat = sk.cnt.g_sig = sk.cnt.g_alb = 0; sk.n_paths = 0;
+    if (factor > 0) run_vps_drt(S, P.G, sk);
+    else run_vps_drt(S, (const GridK &) P.G, sk);
+    counters[2] = sk.cnt.coll; counters[3] = sk.cnt.scat; counters[4] = sk.cnt.g_sig; counters[5] = sk.cnt.g_alb;
+    counters[6] = sk.n_paths;
+    return 0;
+}
+
 
 // factor > 0: majorant supergrid + DDA (the GridKS instantiation of the handlers)
 int emu_twostates_sg(const rcv_scene_desc *d, const float *so, const float *ao, const float *sn, const float *an, int nz, int ny,
@@ -185,7 +271,7 @@ int emu_vps_sg(const rcv_scene_desc *d, const float *sn, const float *an, int nz
     Packed P; pack(*d, sn, an, sn, an, nz, ny, nx, P, factor);
     for (int i = 0; i < 8; ++i) counters[i] = 0;
     VpSink sk; sk.accum = (float4 *) accum; sk.D.gsig = gsig; sk.D.galb = (float4 *) galb4; sk.grad_img = grad_img; sk.film_w = film_w;
-    sk.seed = seed; sk.spp = spp; sk.alt_seed = alt_seed;
+    sk.seed = seed; sk.spp = spp; sk.alt_seed = alt_seed; sk.drt_mis = 0;
     sk.cnt.coll = sk.cnt.scat = sk.cnt.g_sig = sk.cnt.g_alb = 0; sk.n_paths = 0;
     if (factor > 0) {
         if (backward) run_vps<true>(S, P.G, sk); else run_vps<false>(S, P.G, sk);

@@ -118,11 +118,12 @@ def test_volpathsimple_backward(oracle, gpu_ctx, setup, tracer):
     gpu_ctx.set_tracer(3)
 
 
-@pytest.mark.parametrize("flags", [7, 5, 3, 1])
-def test_volpathsimple_backward_drt(oracle, gpu_ctx, setup, flags):
+@pytest.mark.parametrize("flags,tracer", [(7, 3), (3, 3), (5, 3), (1, 3), (7, 2), (7, 0), (7, 1)])
+def test_volpathsimple_backward_drt(oracle, gpu_ctx, setup, flags, tracer):
     """use_drt = True (volpathsimple.py:39-47, :520-594, :623-778) through rcv_adjoint_set_drt: bit 1 of `flags` is
-    use_drt_subsampling, bit 2 use_drt_mis.  Same lanes, same draws and gradient sites as the oracle's restatement; the
-    gradients differ in summation order only.  Sharding the spp leaves the result unchanged."""
+    use_drt_subsampling, bit 2 use_drt_mis.  With sub-sampling the pool tracer runs the three DRT stages on the event
+    machines; every other combination runs the one-thread-per-lane kernel.  Same lanes, same draws and gradient sites
+    as the oracle's restatement; the gradients differ in summation order only.  Sharding the spp changes nothing."""
     d = setup["desc"]
     rng = np.random.default_rng(1)
     grad_img = (rng.standard_normal((d.film_height, d.film_width, 3)) / (d.film_height * d.film_width * 3)).astype(np.float32)
@@ -130,15 +131,21 @@ def test_volpathsimple_backward_drt(oracle, gpu_ctx, setup, flags):
     kw = dict(use_drt=True, use_drt_subsampling=bool(flags & 2), use_drt_mis=bool(flags & 4))
     oracle.counters(True); gpu_ctx.counters(True)
     gs, ga = oracle.vps_backward(d, setup["mn"], seed_grad, spp_grad, grad_img, threads=1, **kw)
+    staged = tracer == 3 and (flags & 2)
     try:
+        gpu_ctx.set_tracer(tracer)
         gpu_ctx.set_drt(True, bool(flags & 2), bool(flags & 4))
         gpu_ctx.grad_zero()
         gpu_ctx.render_backward(seed_grad, spp_grad, to_cuda(grad_img))
         ggs, gga = gpu_ctx.grad_read()
         oc, gc = oracle.counters(True), gpu_ctx.counters(True)
-        assert [int(v) for v in oc[2:6]] == [int(v) for v in gc[2:6]], (oc, gc)
+        assert [int(v) for v in oc[3:7]] == [int(v) for v in gc[3:7]], (oc, gc)
+        if staged:
+            assert int(gc[2]) < int(oc[2])         # vertex-list adjoint: the main path's null collisions are not repeated
+        else:
+            assert int(gc[2]) == int(oc[2])
         assert rel_l2(ggs.cpu().numpy(), gs) < 1e-4 and rel_l2(gga.cpu().numpy(), ga) < 1e-4
-        if flags == 7:
+        if flags == 7 and tracer == 3:
             gpu_ctx.grad_zero()
             gpu_ctx.render_backward(seed_grad, spp_grad, to_cuda(grad_img), 0, 1)
             gpu_ctx.render_backward(seed_grad, spp_grad, to_cuda(grad_img), 1, 4)
@@ -146,9 +153,30 @@ def test_volpathsimple_backward_drt(oracle, gpu_ctx, setup, flags):
             assert rel_l2(hs.cpu().numpy(), ggs.cpu().numpy()) < 1e-5 and rel_l2(ha.cpu().numpy(), gga.cpu().numpy()) < 1e-5
     finally:
         gpu_ctx.set_drt(False)
+        gpu_ctx.set_tracer(3)
     # a different estimator of the same gradient: far from the path-replay one sample by sample
     ps, _ = oracle.vps_backward(d, setup["mn"], seed_grad, spp_grad, grad_img, threads=1)
     assert rel_l2(gs, ps) > 1e-2
+
+
+def test_drt_stages_at_bench_depth(oracle, gpu_ctx):
+    """The DRT stages at the depth of the experiments (max_depth = rr_depth = 64, experiments.py:130-131) on a denser
+    medium and a film larger than one pool refill, with the gaussian reconstruction filter."""
+    from recursive_control_variates_b200.scene import SceneConfig
+    from recursive_control_variates_b200.runtime import Context
+    d = SceneConfig(width=64, height=48, rfilter="gaussian").to_desc()
+    _, (sn, an) = media(20)
+    mn = oracle.OracleMedium(d, sn, an)
+    gimg = (np.random.default_rng(4).standard_normal((48, 64, 3)) / (48 * 64 * 3)).astype(np.float32)
+    gs, ga = oracle.vps_backward(d, mn, 123, 4, gimg, use_drt=True)
+    ctx = Context(0)
+    ctx.set_scene(d)
+    gpu_set_states(ctx, (sn, an), (sn, an))
+    ctx.set_drt(True)
+    ctx.grad_zero()
+    ctx.render_backward(123, 4, to_cuda(gimg))
+    ggs, gga = ctx.grad_read()
+    assert rel_l2(ggs.cpu().numpy(), gs) < 1e-4 and rel_l2(gga.cpu().numpy(), ga) < 1e-4
 
 
 def test_drt_with_majorant_supergrid(oracle, gpu_ctx):

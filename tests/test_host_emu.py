@@ -33,6 +33,8 @@ def emu():
                                C.c_void_p, C.c_void_p, f32, f32, f32, u64, C.c_int]
     lib.emu_vps_backward_lane.argtypes = [C.c_void_p, f32, f32, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32,
                                           C.c_void_p, C.c_void_p, f32, f32, u64, C.c_int, C.c_int]
+    lib.emu_vps_drt_stages.argtypes = [C.c_void_p, f32, f32, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32,
+                                       C.c_void_p, C.c_void_p, f32, f32, u64, C.c_int, C.c_int]
     return lib
 
 
@@ -237,4 +239,31 @@ def test_per_lane_adjoint_with_drt(oracle, emu, flags, factor):
     oc = oracle.counters(True)
     assert [int(v) for v in cnt[2:7]] == [int(v) for v in oc[2:7]]
     assert rel_l2(g1, gs) < 1e-5       # float vs double accumulation
+    assert rel_l2(g4[..., 0:3], ga) < 1e-5
+
+
+@pytest.mark.parametrize("use_mis,factor,depths", [(1, 0, (12, 4)), (0, 0, (12, 4)), (1, 5, (12, 4)), (1, 0, (3, 1)), (1, 0, (64, 64))])
+def test_drt_stages_of_the_event_machines(oracle, emu, use_mis, factor, depths):
+    """use_drt + use_drt_subsampling on the event machines: stage 1 (adjoint, reservoir kept during pass 1, job records),
+    the job step (distance sampling, shadow ray, phase sample) and stage 2 (the primal machine resumed from the job's
+    PathState, its result scattered into the gradient grids) against the oracle's straight-line restatement: the
+    secondary sampler's draws are reordered across the stages but each is the same number."""
+    from recursive_control_variates_b200.scene import SceneConfig
+    d = SceneConfig(width=20, height=16, phase="hg", phase_g=0.5, max_depth=depths[0], rr_depth=depths[1]).to_desc()
+    _, (sn, an) = media(10)
+    mn = oracle.OracleMedium(d, sn, an, majorant_factor=factor)
+    H, W = d.film_height, d.film_width
+    grad_img = (np.random.default_rng(6).standard_normal((H, W, 3)) / (H * W * 3)).astype(np.float32)
+    seed_grad, spp = 78, 3
+    film_w = oracle.film_weights(d, seed_grad, spp)
+    g1 = np.zeros((*sn.shape[:3], 1), np.float32); g4 = np.zeros((*sn.shape[:3], 4), np.float32)
+    cnt = np.zeros(8, np.uint64)
+    emu.emu_vps_drt_stages(C.addressof(d), sn, an, *sn.shape[:3], seed_grad, spp, oracle.alt_seed(seed_grad),
+                           grad_img.ctypes.data, film_w.ctypes.data, g1, g4, cnt, factor, use_mis)
+    oracle.counters(True)
+    gs, ga = oracle.vps_backward(d, mn, seed_grad, spp, grad_img, threads=1, film_w=film_w, use_drt=True, use_drt_mis=bool(use_mis))
+    oc = oracle.counters(True)
+    assert [int(v) for v in cnt[3:7]] == [int(v) for v in oc[3:7]]
+    assert int(cnt[2]) < int(oc[2])          # vertex-list adjoint: the main path's null collisions are not repeated
+    assert rel_l2(g1, gs) < 1e-5             # float vs double accumulation
     assert rel_l2(g4[..., 0:3], ga) < 1e-5
