@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--use-drt", action="store_true",
                     help="adjoint with volpathsimple's use_drt/subsampling/mis = True (reference default); the headline is "
                          "use_drt=False, the configuration SURVEY.md 8(d) measures")
+    ap.add_argument("--no-drt", action="store_true", help="skip the informational use_drt=True timing")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--rfilter", default="box", choices=["box", "gaussian"], help="reconstruction filter of the film (headline: box)")
@@ -389,6 +390,29 @@ def run_ours(a):
                           "note": "same workload, free flights sampled by DDA through the majorant supergrid (not the headline config)"})
     ctx.set_majorant_factor(0)
 
+    # ---- the same iteration with the adjoint's DRT term (volpathsimple.py:39-47: use_drt / use_drt_subsampling /
+    # use_drt_mis all True, the reference's default), informational unless --use-drt makes it the measured configuration
+    drt_info = None
+    if not a.use_drt and not a.no_drt:
+        ctx.set_drt(True)
+        step(a.warmup + a.steps); barrier(); ctx.counters(True)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_d = max(2, min(a.steps, 3))
+        s0.record()
+        for i in range(n_d):
+            step(a.warmup + a.steps + 1 + i)
+        s1.record(); barrier()
+        d_cnt = ctx.counters(True).astype(np.float64) / n_d
+        td = torch.tensor([s0.elapsed_time(s1) / n_d], device=dev)
+        if world > 1:
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+        d_ms = float(td.item())
+        drt_info = {"ms_per_step": d_ms, "value": paths_per_step / (d_ms * 1e-3) / 1e6, "unit": UNIT,
+                    "adjoint_collisions": d_cnt[2], "gpu_launches": d_cnt[7],
+                    "note": "same workload with the adjoint's differential-ratio-tracking term (use_drt, sub-sampling and MIS "
+                            "on: the reference default); paths_per_step does not count the DRT estimate's recursive path"}
+        ctx.set_drt(False)
+
     # ---- end to end through the host-buffer C-ABI call (pinned host memory, copies inside the timed region)
     e2e = None
     if not a.no_e2e and world > 1:
@@ -488,7 +512,7 @@ def run_ours(a):
                           "l2": "inputs larger than L2 (two-state grids %d MiB)" % (a.grid ** 3 * 40 // 2 ** 20),
                           "tracer": {0: "wavefront", 1: "simple", 2: "batch", 3: "pool"}[a.tracer], "rfilter": a.rfilter, "loss_last": float(loss.item())},
                "clocks": clocks, "gpu_launches": int(cnt[7]), "roofline": roofline, "kernels": kernels,
-               "phases_ms_rank0": phases, "e2e": e2e, "cpu_baseline": cpu, "supergrid": supergrid}
+               "phases_ms_rank0": phases, "e2e": e2e, "cpu_baseline": cpu, "supergrid": supergrid, "drt": drt_info}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
