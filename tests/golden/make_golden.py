@@ -42,6 +42,11 @@ def compute(O):
     sg_gs, sg_ga = O.vps_backward(desc, sn, 0x5D8714D7, 2, gimg, threads=1)
     sg = {"sg_acc_old": sg_o, "sg_acc_new": sg_n, "sg_vps_acc": sg_vps, "sg_grad_sigma_t": sg_gs.astype(np.float32),
           "sg_grad_albedo": sg_ga.astype(np.float32), "sg_majorant_grid_old": so.majorant_grid, "sg_majorant_grid_new": sn.majorant_grid}
+    # the adjoint with the DRT in-scattering term: sub-sampling + MIS (the reference default), and neither
+    d_gs, d_ga = O.vps_backward(desc, mn, 0x5D8714D7, 2, gimg, threads=1, use_drt=True)
+    e_gs, e_ga = O.vps_backward(desc, mn, 0x5D8714D7, 2, gimg, threads=1, use_drt=True, use_drt_subsampling=False, use_drt_mis=False)
+    sg.update({"drt_grad_sigma_t": d_gs.astype(np.float32), "drt_grad_albedo": d_ga.astype(np.float32),
+               "drt_plain_grad_sigma_t": e_gs.astype(np.float32), "drt_plain_grad_albedo": e_ga.astype(np.float32)})
     return {**sg, "acc_old": acc_o, "acc_new": acc_n, "vps_acc": vps, "grad_sigma_t": gs.astype(np.float32),
             "grad_albedo": ga.astype(np.float32), "cv_img": st["img"], "cv_w_s": st["w_s"],
             "alt_seed": np.array([O.alt_seed(0x5D8714D7)], np.uint32), "majorants": np.array([mo.majorant, mn.majorant], np.float32)}

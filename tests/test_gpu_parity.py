@@ -276,6 +276,16 @@ def test_golden_fixture_on_gpu(oracle, gpu_ctx):
     assert rel_l2(gs.cpu().numpy(), ref["grad_sigma_t"]) < GRAD_TOL and rel_l2(ga.cpu().numpy(), ref["grad_albedo"]) < GRAD_TOL
     m = gpu_ctx.majorants()
     assert np.array_equal(np.array(m, np.float32), ref["majorants"])
+    # the adjoint with the DRT term: sub-sampling + MIS (three stages on the pool machines), and neither (per-lane kernel)
+    try:
+        for sub_mis, key in ((True, "drt"), (False, "drt_plain")):
+            gpu_ctx.set_drt(True, sub_mis, sub_mis)
+            gpu_ctx.grad_zero(); gpu_ctx.render_backward(0x5D8714D7, 2, to_cuda(gimg))
+            gs, ga = gpu_ctx.grad_read()
+            assert rel_l2(gs.cpu().numpy(), ref[key + "_grad_sigma_t"]) < GRAD_TOL
+            assert rel_l2(ga.cpu().numpy(), ref[key + "_grad_albedo"]) < GRAD_TOL
+    finally:
+        gpu_ctx.set_drt(False)
     # majorant supergrid (factor 4) fixtures
     gpu_ctx.set_majorant_factor(4)
     try:
