@@ -175,6 +175,28 @@ def test_drt_scattering_term_agrees_with_path_replay(oracle):
     assert not np.array_equal(g0, g1)
 
 
+def test_drt_variance_behaviour(oracle):
+    """What the restated sampler is for (it is unpinned, so check its published behaviour): in a thin medium the DRT
+    term with MIS has clearly less variance in d/d sigma_t than the path-replay term, whose 1/sigma_t weight blows up
+    there; in a dense medium DRT alone is the worse one and the MIS combination is what keeps it at par."""
+    from recursive_control_variates_b200.scene import SceneConfig
+    from recursive_control_variates_b200.synthetic import make_medium
+    sig, alb = make_medium(4, "cube", 0.0)
+    sig = (sig * 0.6 + 0.2).astype(np.float32)
+    gimg = (np.random.default_rng(0).random((8, 8, 3)) / 192).astype(np.float32)
+
+    def total_var(scale, **kw):
+        d = SceneConfig(width=8, height=8, max_depth=16, rr_depth=16, sigma_t_scale=scale).to_desc()
+        m = oracle.OracleMedium(d, sig, alb)
+        g = np.stack([oracle.vps_backward(d, m, seed, 256, gimg, **kw)[0] for seed in range(1, 17)])
+        return float(g.var(0, ddof=1).sum())
+
+    assert total_var(2.0, use_drt=True) < 0.75 * total_var(2.0)
+    dense_mis, dense_plain = total_var(20.0, use_drt=True), total_var(20.0, use_drt=True, use_drt_mis=False)
+    assert dense_plain > 1.3 * dense_mis
+    assert dense_mis < 1.25 * total_var(20.0)
+
+
 def test_adam_clamp_upsample(oracle):
     p = np.array([0.5, 1.0], np.float32); g = np.array([1.0, -2.0], np.float32)
     m = np.zeros(2, np.float32); v = np.zeros(2, np.float32)
