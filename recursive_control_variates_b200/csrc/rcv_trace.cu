@@ -478,10 +478,10 @@ __global__ void __launch_bounds__(kPoolBlock, RCV_TS_POOL_MINBLOCKS) k_twostates
 template <int DRT, class GRID>
 __device__ __forceinline__ void pool_drt_complete(const SceneK &S, const GRID &G, VpLane &ln, VpSink &sk, bool done) {
     if (DRT == 1) {
-        float4 job[4];
-        const bool want = done && vp_drt_job(ln, sk, job);
+        float4 j0, j1, j2, j3;
+        const bool want = done && vp_drt_job(ln, sk, j0, j1, j2, j3);
         const unsigned long long pos = queue_slot(sk.jobs.count, want);
-        if (want) { sk.jobs.r0[pos] = job[0]; sk.jobs.r1[pos] = job[1]; sk.jobs.r2[pos] = job[2]; sk.jobs.r3[pos] = job[3]; }
+        if (want) { sk.jobs.r0[pos] = j0; sk.jobs.r1[pos] = j1; sk.jobs.r2[pos] = j2; sk.jobs.r3[pos] = j3; }
     }
     if (DRT == 2) {
         if (done) {

@@ -36,10 +36,11 @@
 //
 // use_drt = True with sub-sampling (volpathsimple.py:39-47, :262-272) runs on the same machines in three stages
 // (template parameter DRT of the handlers):
-//   DRT = 1  the adjoint above, plus the DRTReservoir (:743-778) kept in the lane's arena slot during pass 1 (the
-//            secondary sampler's draws of pass 2 are known in advance: one reservoir draw, then four transmittance
-//            draws per vertex), the MIS weight of the path-replay term (:165-170), and at the end of pass 2 a JOB
-//            record: selected ray, depth, adjoint weight, state of the secondary sampler
+//   DRT = 1  the adjoint above, plus the DRTReservoir (:743-778) updated while pass 2 walks the vertex list: the
+//            throughput at the head of every iteration is rebuilt from the albedos pass 2 gathers anyway and the
+//            Russian-roulette factors, in lane words that pass 2 does not use otherwise (thr, depth, last_pdf,
+//            saved); the MIS weight of the path-replay term (:165-170); at the end of pass 2 a JOB record:
+//            selected ray, depth, adjoint weight, state of the secondary sampler
 //   (k_drt_sample, rcv_trace.cu: distance sampling, shadow ray and phase sampling of the job: :560-561, :635-654)
 //   DRT = 2  the recursive radiance estimate (:656-665): the primal machine resumed from the job's PathState on the
 //            secondary sampler; its result is scattered into the gradient grids instead of the film
@@ -149,6 +150,14 @@ __device__ __forceinline__ void vp_end_pass(const SceneK &S, VpLane &ln, VpSink 
     sampler_seed(ln.alt, sk.alt_seed, ln.idx);
     ln.flags = VF_ADJ;
     ln.vk = 0;
+    if (DRT == 1) {
+        // pass 2 rebuilds the throughput (thr) for the DRTReservoir (:107-109): wsum in (last_pdf, saved), the
+        // selected vertex in depth, current_weight in the spare arena record
+        ln.thr = mk3(1, 1, 1);
+        ln.depth = -1;
+        ln.last_pdf = 0.f;
+        ln.saved = 0;
+    }
     if (ln.nvert > 0) ln.ev = EV_SCAT;
     else vp_finish<DRT>(ln, sk);
 }
@@ -219,13 +228,6 @@ __device__ __forceinline__ void vp_load(VpLane &ln, const VpSink &sk, const Path
     ln.vbase = slot * (sk.vcap + kNeeCap / 4);
     ln.nvert = 0; ln.vk = 0;
     ln.ev = EV_COLL;
-    if (DRT == 1) {
-        // the secondary sampler (:119-120) already in pass 1, for the reservoir's draws; pass 2 re-seeds it
-        sampler_seed(ln.alt, sk.alt_seed, ln.idx);
-        float4 *R = vp_reservoir(sk, ln);
-        R[0] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));        // wsum, selected vertex
-        R[1] = make_float4(0.f, 0.f, 0.f, 0.f);                       // current_weight
-    }
     if (DRT == 2) {
         // PathState of the recursive call (:75-81, :98-100, :656-665): a path record written by k_drt_sample.
         // pix = its job, idx word = depth, r3 = radiance so far (the NEE of :635-638) and the phase pdf
@@ -398,21 +400,6 @@ template <bool BW, int DRT = 0>
 __device__ __forceinline__ void vp_vertex1(const SceneK &S, const GridK &G, VpLane &ln, VpSink &sk) {
     const bool did_scatter = (ln.flags & VF_DID_SCATTER) != 0;
     if (did_scatter) ln.flags |= VF_HAS_SCAT;                         // :150
-    if (DRT == 1) {
-        // DRTReservoir.update (:546, :757-765) with the throughput at the head of this iteration.  The draw is the
-        // first one the secondary sampler makes for this vertex in pass 2; the four that follow belong to the
-        // transmittance term (:608)
-        float xi = pcg_f32(ln.alt);
-        (void) pcg_u32(ln.alt); (void) pcg_u32(ln.alt); (void) pcg_u32(ln.alt); (void) pcg_u32(ln.alt);
-        float4 *R = vp_reservoir(sk, ln);
-        float4 a = R[0];
-        V3 wsum = mk3(a.x, a.y, a.z) + ln.thr;
-        if (xi <= mean3(ln.thr / wsum)) {
-            a.w = __int_as_float(ln.nvert);
-            R[1] = make_float4(ln.thr.x, ln.thr.y, ln.thr.z, 0.f);
-        }
-        R[0] = make_float4(wsum.x, wsum.y, wsum.z, a.w);
-    }
     V3 albedo = mk3(1, 1, 1);
     if (did_scatter) {
         V3 mei_p = ray_at(ln.o, ln.d, ln.mei_t);                      // :384
@@ -447,7 +434,22 @@ __device__ __forceinline__ void vp_vertex1(const SceneK &S, const GridK &G, VpLa
 // pass 2 vertex: the gradient terms of vertex vk, then the replay of its shadow ray
 template <int DRT = 0>
 __device__ __forceinline__ void vp_vertex2(const SceneK &S, const GridK &G, VpLane &ln, VpSink &sk) {
-    if (DRT == 1) (void) pcg_u32(ln.alt);                             // the reservoir's draw (:546), used in pass 1
+    if (DRT == 1) {
+        // head of iteration vk as pass 1 ran it: Russian-roulette factor (:130-134; depth == vk), then
+        // DRTReservoir.update with the throughput there (:546, :757-765)
+        float xi = pcg_f32(ln.alt);
+        if (ln.vk > S.rr_depth) {
+            float q = fmin_(max3(ln.thr), 0.99f);
+            ln.thr = ln.thr * (1.f / q);
+        }
+        V3 wsum = mk3(ln.last_pdf, __uint_as_float((uint32_t) ln.saved), __uint_as_float((uint32_t) (ln.saved >> 32))) + ln.thr;
+        if (xi <= mean3(ln.thr / wsum)) {
+            ln.depth = ln.vk;
+            *vp_reservoir(sk, ln) = make_float4(ln.thr.x, ln.thr.y, ln.thr.z, 0.f);
+        }
+        ln.last_pdf = wsum.x;
+        ln.saved = (uint64_t) __float_as_uint(wsum.y) | ((uint64_t) __float_as_uint(wsum.z) << 32);
+    }
     const float4 *r = vp_record(sk, ln, ln.vk);
     float4 r0 = r[0], r1 = r[1];
     ln.o = mk3(r0.x, r0.y, r0.z); ln.d = mk3(r1.x, r1.y, r1.z);
@@ -461,6 +463,7 @@ __device__ __forceinline__ void vp_vertex2(const SceneK &S, const GridK &G, VpLa
         float st = lookup_sigma1(S, G, T);                            // :386-388
         V3 albedo = lookup_albedo(G, T, 1);                           // :154
         sk.cnt.scat++;
+        if (DRT == 1) ln.thr = ln.thr * albedo;                       // :206, for the next iteration's reservoir update
         // scattering term (:165-185): backward_from(drt_mis_weight * dL * (sigma_t * albedo) * Li * inv_pdf)
         V3 inv_pdf = splat3(1.f / st);
         V3 Li = ln.result / vmax3(splat3(1e-8f), albedo);
@@ -529,22 +532,22 @@ __device__ __forceinline__ void vp_vertex(const SceneK &S, const GridK &G, VpLan
 // ---------------------------------------------------------------------------
 // DRT = 1, a lane whose pass 2 just ended (VF_JOB): DRTReservoir.get (:768-772) and the delayed estimate's inputs
 // (:262-272).  false: the reservoir is empty, nothing to estimate.
-__device__ __forceinline__ bool vp_drt_job(const VpLane &ln, const VpSink &sk, float4 job[4]) {
-    const float4 *R = vp_reservoir(sk, ln);
-    float4 a = R[0], b = R[1];
-    const int sel = __float_as_int(a.w);
+__device__ __forceinline__ bool vp_drt_job(const VpLane &ln, const VpSink &sk, float4 &j0, float4 &j1, float4 &j2, float4 &j3) {
+    const int sel = ln.depth;
     if (sel < 0) return false;
-    V3 wsum = mk3(a.x, a.y, a.z), cur = mk3(b.x, b.y, b.z);
+    float4 b = *vp_reservoir(sk, ln);
+    V3 wsum = mk3(ln.last_pdf, __uint_as_float((uint32_t) ln.saved), __uint_as_float((uint32_t) (ln.saved >> 32)));
+    V3 cur = mk3(b.x, b.y, b.z);
     float dn = mean3(cur);
     V3 wgt = (dn != 0.f) ? cur * (mean3(wsum) / dn) : mk3(0, 0, 0);
     V3 adjoint = wgt * ln.dL;
     const float4 *r = vp_record(sk, ln, sel);
     float4 r0 = r[0], r1 = r[1];
-    job[0] = make_float4(__uint_as_float((uint32_t) ln.alt.state), __uint_as_float((uint32_t) (ln.alt.state >> 32)),
-                         __uint_as_float((uint32_t) (ln.alt.inc >> 1)), __int_as_float(sel));   // depth == vertex index
-    job[1] = make_float4(r0.x, r0.y, r0.z, adjoint.x);
-    job[2] = make_float4(r1.x, r1.y, r1.z, adjoint.y);
-    job[3] = make_float4(adjoint.z, 0.f, 0.f, 0.f);
+    j0 = make_float4(__uint_as_float((uint32_t) ln.alt.state), __uint_as_float((uint32_t) (ln.alt.state >> 32)),
+                     __uint_as_float((uint32_t) (ln.alt.inc >> 1)), __int_as_float(sel));       // depth == vertex index
+    j1 = make_float4(r0.x, r0.y, r0.z, adjoint.x);
+    j2 = make_float4(r1.x, r1.y, r1.z, adjoint.y);
+    j3 = make_float4(adjoint.z, 0.f, 0.f, 0.f);
     return true;
 }
 

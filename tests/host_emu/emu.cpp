@@ -181,9 +181,9 @@ void run_vps_drt(const SceneK &S, const GRID &G, VpSink &sk) {
             else if (ln.ev == EV_SCAT) vp_vertex<true, 1>(S, G, ln, sk);
             else vp_slow<true, 1>(S, G, ln, sk);
         }
-        float4 job[4];
-        if ((ln.flags & VF_JOB) && vp_drt_job(ln, sk, job)) {
-            jq.r0[jq.count] = job[0]; jq.r1[jq.count] = job[1]; jq.r2[jq.count] = job[2]; jq.r3[jq.count] = job[3];
+        float4 j0, j1, j2, j3;
+        if ((ln.flags & VF_JOB) && vp_drt_job(ln, sk, j0, j1, j2, j3)) {
+            jq.r0[jq.count] = j0; jq.r1[jq.count] = j1; jq.r2[jq.count] = j2; jq.r3[jq.count] = j3;
             jq.count++;
         }
     }
