@@ -38,10 +38,14 @@ def _worker(rank, world, port, out_dir):
     parallel.allreduce_sum_([fw])
     assert np.array_equal(fw.numpy(), O.film_weights(desc, 99, spp))
     gs, ga = O.vps_backward(desc, mn, 99, spp, gimg, b, e, threads=1, film_w=fw.numpy())
-    ts = [torch.from_numpy(acc_o), torch.from_numpy(acc_n), torch.from_numpy(gs), torch.from_numpy(ga)]
+    # the adjoint with the DRT term shards the same way: every lane owns its secondary sampler
+    ds, da = O.vps_backward(desc, mn, 99, spp, gimg, b, e, threads=1, film_w=fw.numpy(), use_drt=True)
+    ts = [torch.from_numpy(acc_o), torch.from_numpy(acc_n), torch.from_numpy(gs), torch.from_numpy(ga), torch.from_numpy(ds),
+          torch.from_numpy(da)]
     parallel.allreduce_sum_(ts)
     if rank == 0:
-        np.savez(os.path.join(out_dir, "sharded.npz"), acc_o=ts[0].numpy(), acc_n=ts[1].numpy(), gs=ts[2].numpy(), ga=ts[3].numpy())
+        np.savez(os.path.join(out_dir, "sharded.npz"), acc_o=ts[0].numpy(), acc_n=ts[1].numpy(), gs=ts[2].numpy(), ga=ts[3].numpy(),
+                 ds=ts[4].numpy(), da=ts[5].numpy())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -58,3 +62,5 @@ def test_spp_sharded_two_ranks_equal_single_process(oracle, tmp_path):
     assert rel_l2(got["acc_o"], acc_o) < 1e-6 and rel_l2(got["acc_n"], acc_n) < 1e-6
     assert np.array_equal(got["acc_o"][..., 3], acc_o[..., 3])          # film weights: exact
     assert rel_l2(got["gs"], gs) < 1e-9 and rel_l2(got["ga"], ga) < 1e-9
+    ds, da = oracle.vps_backward(desc, mn, 99, 5, np.full((12, 16, 3), 1e-3, np.float32), threads=1, use_drt=True)
+    assert rel_l2(got["ds"], ds) < 1e-9 and rel_l2(got["da"], da) < 1e-9
