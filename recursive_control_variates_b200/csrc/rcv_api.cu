@@ -57,6 +57,8 @@ struct rcv_ctx {
     bool mgrid_valid = false;     // mgrid matches the current grids and factor
     float4 *alb2 = nullptr;
     float *grad = nullptr;       // [pad4(nvox) floats d sigma_t][nvox float4 d albedo]
+    float4 *gbrick = nullptr;    // RCV_GRAD_BRICKS: per-cell d sigma_t bricks of the adjoint launch in flight (zero otherwise)
+    size_t gbrick_cells = 0;
     size_t grad_floats = 0;
     float *majorants = nullptr;
     float *block_max = nullptr;
@@ -98,6 +100,7 @@ struct rcv_ctx {
     GradK gradk() const {
         GradK g;
         g.gsig = grad; g.galb = (float4 *) (grad + ((nvox + 3) / 4) * 4);
+        g.gbrick = gbrick;
         return g;
     }
     GridKS gridk() const {
@@ -185,12 +188,27 @@ int ensure_queue(rcv_ctx *c, uint32_t spp_begin, uint32_t spp_end) {
     return RCV_OK;
 }
 
+// RCV_GRAD_BRICKS: the per-cell gradient bricks of the current grid, zero-filled once (k_unbrick leaves them zero)
+int ensure_gbrick(rcv_ctx *c) {
+#if RCV_GRAD_BRICKS
+    size_t ncell = (size_t) (c->nz + 1) * (c->ny + 1) * (c->nx + 1);
+    if (ncell != c->gbrick_cells) {
+        cudaFree(c->gbrick); c->gbrick = nullptr; c->gbrick_cells = 0;
+        CK(cudaMalloc(&c->gbrick, 2 * ncell * sizeof(float4)));
+        CK(cudaMemsetAsync(c->gbrick, 0, 2 * ncell * sizeof(float4), c->stream));
+        c->gbrick_cells = ncell;
+    }
+#endif
+    return RCV_OK;
+}
+
 // job records of the DRT stages: one per lane of the launch
 int ensure_jobs(rcv_ctx *c, uint32_t spp_begin, uint32_t spp_end) {
     size_t n = (size_t) c->S.W * c->S.H * (spp_end - spp_begin);
     if (!c->jobs.count) CK(cudaMalloc(&c->jobs.count, sizeof(unsigned long long)));
     if (n > c->jobs_cap) {
-        cudaFree(c->jobs.r0); cudaFree(c->jobs.r1); cudaFree(c->jobs.r2); cudaFree(c->jobs.r3);
+        cudaFree(c->gbrick);
+    cudaFree(c->jobs.r0); cudaFree(c->jobs.r1); cudaFree(c->jobs.r2); cudaFree(c->jobs.r3);
         c->jobs.r0 = c->jobs.r1 = c->jobs.r2 = c->jobs.r3 = nullptr; c->jobs_cap = 0;
         CK(cudaMalloc(&c->jobs.r0, n * sizeof(float4)));
         CK(cudaMalloc(&c->jobs.r1, n * sizeof(float4)));
@@ -529,6 +547,7 @@ int rcv_render_backward_weighted(rcv_ctx *c, int adjoint_kind, uint32_t seed_gra
         CK(launch_film_weights(cfg, c->S, seed_grad, spp_grad, 0, spp_grad, c->film_w, true));
         film_w = c->film_w;
     }
+    if (int r = ensure_gbrick(c)) return r;
     GradK D = c->gradk();
     const bool pin = c->l2_persist && c->l2_persist_max > 0 && c->l2_window_max > 0;
     if (pin) {
@@ -545,6 +564,9 @@ int rcv_render_backward_weighted(rcv_ctx *c, int adjoint_kind, uint32_t seed_gra
     }
     CK(launch_vps_backward(cfg, c->S, c->gridk(), D, seed_grad, spp_grad, spp_begin, spp_end, alt_seed_for(seed_grad), grad_img,
                            film_w));
+#if RCV_GRAD_BRICKS
+    CK(launch_unbrick(cfg, D, c->nx, c->ny, c->nz));
+#endif
     if (pin) {
         cudaStreamAttrValue a{};
         a.accessPolicyWindow.num_bytes = 0;

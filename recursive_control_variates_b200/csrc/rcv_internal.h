@@ -60,6 +60,7 @@ struct CvArgs {
 cudaError_t launch_cv_update(const LaunchCfg &cfg, const CvArgs &a);
 cudaError_t launch_loss_grad(const LaunchCfg &cfg, int kind, const float *img, const float *ref, uint64_t n, double *partial,
                              int n_partial, float *loss_out, float *grad_img);
+cudaError_t launch_unbrick(const LaunchCfg &cfg, const GradK &D, int nx, int ny, int nz);
 cudaError_t launch_grad_unpack(const LaunchCfg &cfg, const GradK &D, size_t nvox, float *g_sigma, float *g_albedo);
 cudaError_t launch_adam_packed(const LaunchCfg &cfg, const GradK &D, size_t nvox, float *sigma, float *albedo, float *m_s,
                                float *v_s, float *m_a, float *v_a, float lr_t_s, float lr_t_a, float beta1, float beta2,

@@ -341,6 +341,35 @@ cudaError_t launch_grad_unpack(const LaunchCfg &cfg, const GradK &D, size_t nvox
     return cudaGetLastError();
 }
 
+// RCV_GRAD_BRICKS: fold the per-cell gradient bricks of an adjoint launch into the voxel grid and leave them zero for
+// the next launch.  One thread per cell; most cells are untouched (zero) and cost one 32-byte read.
+__global__ void __launch_bounds__(kBlock) k_unbrick(float4 *__restrict__ gbrick, int nx, int ny, int nz, float *__restrict__ gsig) {
+    const size_t ncell = (size_t) (nx + 1) * (ny + 1) * (nz + 1);
+    for (size_t c = (size_t) blockIdx.x * kBlock + threadIdx.x; c < ncell; c += (size_t) gridDim.x * kBlock) {
+        float4 a = gbrick[2 * c], b = gbrick[2 * c + 1];
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) any = any || (v[k] != 0.f);
+        if (!any) continue;
+        size_t r = c;
+        const int cx = (int) (r % (size_t) (nx + 1)); r /= (size_t) (nx + 1);
+        const int cy = (int) (r % (size_t) (ny + 1)); r /= (size_t) (ny + 1);
+        const int cz = (int) r;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (v[k] != 0.f) red_add_f32(gsig + cell_corner(nx, ny, nz, cx, cy, cz, k), v[k]);
+        gbrick[2 * c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        gbrick[2 * c + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+cudaError_t launch_unbrick(const LaunchCfg &cfg, const GradK &D, int nx, int ny, int nz) {
+    const size_t ncell = (size_t) (nx + 1) * (ny + 1) * (nz + 1);
+    k_unbrick<<<grid_for(cfg, ncell), kBlock, 0, cfg.stream>>>(D.gbrick, nx, ny, nz, D.gsig);
+    (*cfg.launches)++;
+    return cudaGetLastError();
+}
+
 // mi.ad.Adam.step [UPSTREAM]: m,v EMA; p = fma(-lr_t / (sqrt(v) + eps), m, p)
 __device__ __forceinline__ float adam_elem(float p, float g, float &m, float &v, float lr_t, float b1, float b2, float eps) {
     float m_t = b1 * m + (1.f - b1) * g;

@@ -797,7 +797,7 @@ size_t vps_backward_slots(const LaunchCfg &cfg) {
 
 cudaError_t launch_vps_primal(const LaunchCfg &cfg, const SceneK &S, const GridKS &G, uint32_t seed, uint32_t spp,
                               uint32_t spp_begin, uint32_t spp_end, float4 *accum) {
-    GradK D; D.gsig = nullptr; D.galb = nullptr;
+    GradK D; D.gsig = nullptr; D.galb = nullptr; D.gbrick = nullptr;
     if (G.mgrid) return launch_vps<false, GridKS>(cfg, S, G, D, seed, spp, spp_begin, spp_end, 0u, nullptr, nullptr, accum);
     return launch_vps<false, GridK>(cfg, S, G, D, seed, spp, spp_begin, spp_end, 0u, nullptr, nullptr, accum);
 }

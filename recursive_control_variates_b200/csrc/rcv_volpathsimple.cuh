@@ -60,16 +60,26 @@ __device__ __forceinline__ void sample_interaction1(const SceneK &S, const GRID 
 }
 
 // AD of sigma_t(p) = scale * trilinear(grid): scatter w_corner * (scale * g) on a known interpolation set-up
-__device__ __forceinline__ void scatter_sigma_t_T(const GridK &G, const GradK &D, const Tri &T, float sg, VpsCounts &cnt) {
-    if (!T.inside) return;
+// the eight reductions of one site: corner weight x sg, k = 4 zbit + 2 ybit + xbit
+__device__ __forceinline__ void red_sigma_site(const GridK &G, const GradK &D, const Tri &T, float sg) {
+    const float wzy[4] = {T.wz0 * T.wy0, T.wz0 * T.wy1, T.wz1 * T.wy0, T.wz1 * T.wy1};
+#if RCV_GRAD_BRICKS
+    float4 *b = D.gbrick + 2 * (size_t) tri_cell(G, T);
+    red_add_v4(b, (wzy[0] * T.wx0) * sg, (wzy[0] * T.wx1) * sg, (wzy[1] * T.wx0) * sg, (wzy[1] * T.wx1) * sg);
+    red_add_v4(b + 1, (wzy[2] * T.wx0) * sg, (wzy[2] * T.wx1) * sg, (wzy[3] * T.wx0) * sg, (wzy[3] * T.wx1) * sg);
+#else
     uint32_t r[4];
     tri_rows(G, T, r);
-    const float wzy[4] = {T.wz0 * T.wy0, T.wz0 * T.wy1, T.wz1 * T.wy0, T.wz1 * T.wy1};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         red_add_f32(D.gsig + r[k] + T.x0, (wzy[k] * T.wx0) * sg);
         red_add_f32(D.gsig + r[k] + T.x1, (wzy[k] * T.wx1) * sg);
     }
+#endif
+}
+__device__ __forceinline__ void scatter_sigma_t_T(const GridK &G, const GradK &D, const Tri &T, float sg, VpsCounts &cnt) {
+    if (!T.inside) return;
+    red_sigma_site(G, D, T, sg);
     cnt.g_sig++;
 }
 __device__ __forceinline__ void scatter_sigma_t(const SceneK &S, const GridK &G, const GradK &D, V3 p, float g, VpsCounts &cnt) {
@@ -250,9 +260,14 @@ __device__ __forceinline__ void vps_trace_core(const SceneK &S, const GRID &G, c
                     for (int k = 0; k < 8; ++k) {
                         float w = tri_weight(T, k);
                         uint32_t v = tri_voxel(G, T, k);
+#if !RCV_GRAD_BRICKS
                         red_add_f32(D.gsig + v, w * sg);
+#endif
                         red_add_v4(D.galb + v, w * g_al.x, w * g_al.y, w * g_al.z, 0.f);
                     }
+#if RCV_GRAD_BRICKS
+                    red_sigma_site(G, D, T, sg);
+#endif
                     cnt.g_sig++; cnt.g_alb++;
                 }
             }
@@ -415,9 +430,14 @@ __device__ __noinline__ void drt_backpropagate(const SceneK &S, const GRID &G, c
         for (int k = 0; k < 8; ++k) {
             float w = tri_weight(T, k);
             uint32_t v = tri_voxel(G, T, k);
+#if !RCV_GRAD_BRICKS
             red_add_f32(D.gsig + v, w * sg);
+#endif
             red_add_v4(D.galb + v, w * g_al.x, w * g_al.y, w * g_al.z, 0.f);
         }
+#if RCV_GRAD_BRICKS
+        red_sigma_site(G, D, T, sg);
+#endif
         cnt.g_sig++; cnt.g_alb++;
     }
 }

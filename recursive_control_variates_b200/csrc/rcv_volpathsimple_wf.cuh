@@ -480,9 +480,14 @@ __device__ __forceinline__ void vp_vertex2(const SceneK &S, const GridK &G, VpLa
             for (int k = 0; k < 8; ++k) {
                 float w = tri_weight(T, k);
                 uint32_t v = tri_voxel(G, T, k);
+#if !RCV_GRAD_BRICKS
                 red_add_f32(sk.D.gsig + v, w * sg);
+#endif
                 red_add_v4(sk.D.galb + v, w * g_al.x, w * g_al.y, w * g_al.z, 0.f);
             }
+#if RCV_GRAD_BRICKS
+            red_sigma_site(G, sk.D, T, sg);
+#endif
             sk.cnt.g_sig++; sk.cnt.g_alb++;
         }
     }
@@ -566,9 +571,14 @@ __device__ __forceinline__ void vp_drt_scatter(const SceneK &S, const GRID &G, c
         for (int k = 0; k < 8; ++k) {
             float w = tri_weight(T, k);
             uint32_t v = tri_voxel(G, T, k);
+#if !RCV_GRAD_BRICKS
             red_add_f32(D.gsig + v, w * sg);
+#endif
             red_add_v4(D.galb + v, w * g_al.x, w * g_al.y, w * g_al.z, 0.f);
         }
+#if RCV_GRAD_BRICKS
+        red_sigma_site(G, D, T, sg);
+#endif
         cnt.g_sig++; cnt.g_alb++;
     }
 }

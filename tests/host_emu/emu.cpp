@@ -76,6 +76,26 @@ void pack(const rcv_scene_desc &d, const float *so, const float *ao, const float
     }
 }
 
+// RCV_GRAD_BRICKS: host stand-in for the gradient bricks and launch_unbrick
+struct HostBricks {
+    std::vector<float4> b;
+    int nx, ny, nz;
+    HostBricks(int nx_, int ny_, int nz_, GradK &D) : b((size_t) 2 * (nx_ + 1) * (ny_ + 1) * (nz_ + 1), make_float4(0.f, 0.f, 0.f, 0.f)),
+                                                     nx(nx_), ny(ny_), nz(nz_) {
+        D.gbrick = RCV_GRAD_BRICKS ? b.data() : nullptr;
+    }
+    void fold(float *gsig) {
+        if (!RCV_GRAD_BRICKS) return;
+        size_t c = 0;
+        for (int cz = 0; cz <= nz; ++cz)
+            for (int cy = 0; cy <= ny; ++cy)
+                for (int cx = 0; cx <= nx; ++cx, ++c) {
+                    const float v[8] = {b[2 * c].x, b[2 * c].y, b[2 * c].z, b[2 * c].w, b[2 * c + 1].x, b[2 * c + 1].y, b[2 * c + 1].z, b[2 * c + 1].w};
+                    for (int k = 0; k < 8; ++k) gsig[cell_corner(nx, ny, nz, cx, cy, cz, k)] += v[k];
+                }
+    }
+};
+
 struct HostQueue {
     std::vector<float4> r0, r1, r2, r3;
     unsigned long long count;
@@ -230,8 +250,10 @@ int emu_vps_drt_stages(const rcv_scene_desc *d, const float *sn, const float *an
     VpSink sk; sk.accum = nullptr; sk.D.gsig = gsig; sk.D.galb = (float4 *) galb4; sk.grad_img = grad_img; sk.film_w = film_w;
     sk.seed = seed; sk.spp = spp; sk.alt_seed = alt_seed; sk.drt_mis = use_mis;
     sk.cnt.coll = sk.cnt.scat = sk.cnt.g_sig = sk.cnt.g_alb = 0; sk.n_paths = 0;
+    HostBricks hb(nx, ny, nz, sk.D);
     if (factor > 0) run_vps_drt(S, P.G, sk);
     else run_vps_drt(S, (const GridK &) P.G, sk);
+    hb.fold(gsig);
     counters[2] = sk.cnt.coll; counters[3] = sk.cnt.scat; counters[4] = sk.cnt.g_sig; counters[5] = sk.cnt.g_alb;
     counters[6] = sk.n_paths;
     return 0;
@@ -273,12 +295,14 @@ int emu_vps_sg(const rcv_scene_desc *d, const float *sn, const float *an, int nz
     VpSink sk; sk.accum = (float4 *) accum; sk.D.gsig = gsig; sk.D.galb = (float4 *) galb4; sk.grad_img = grad_img; sk.film_w = film_w;
     sk.seed = seed; sk.spp = spp; sk.alt_seed = alt_seed; sk.drt_mis = 0;
     sk.cnt.coll = sk.cnt.scat = sk.cnt.g_sig = sk.cnt.g_alb = 0; sk.n_paths = 0;
+    HostBricks hb(nx, ny, nz, sk.D);
     if (factor > 0) {
         if (backward) run_vps<true>(S, P.G, sk); else run_vps<false>(S, P.G, sk);
     } else {
         const GridK &G = P.G;
         if (backward) run_vps<true>(S, G, sk); else run_vps<false>(S, G, sk);
     }
+    if (backward) hb.fold(gsig);
     counters[2] = sk.cnt.coll; counters[3] = sk.cnt.scat; counters[4] = sk.cnt.g_sig; counters[5] = sk.cnt.g_alb;
     counters[6] = sk.n_paths;
     return 0;
@@ -292,12 +316,14 @@ int emu_vps_backward_lane(const rcv_scene_desc *d, const float *sn, const float 
     Packed P; pack(*d, sn, an, sn, an, nz, ny, nx, P, factor);
     for (int i = 0; i < 8; ++i) counters[i] = 0;
     GradK D; D.gsig = gsig; D.galb = (float4 *) galb4;
+    HostBricks hb(nx, ny, nz, D);
     VpsCounts cnt; cnt.coll = cnt.scat = cnt.g_sig = cnt.g_alb = 0;
     uint64_t n = (uint64_t) S.W * S.H * spp;
     for (uint64_t idx = 0; idx < n; ++idx) {
         if (factor > 0) vps_backward_lane(S, P.G, D, seed, spp, idx, alt_seed, grad_img, film_w, drt_flags, cnt);
         else vps_backward_lane(S, (const GridK &) P.G, D, seed, spp, idx, alt_seed, grad_img, film_w, drt_flags, cnt);
     }
+    hb.fold(gsig);
     counters[2] = cnt.coll; counters[3] = cnt.scat; counters[4] = cnt.g_sig; counters[5] = cnt.g_alb; counters[6] = 2 * n;
     return 0;
 }
