@@ -207,8 +207,7 @@ int ensure_jobs(rcv_ctx *c, uint32_t spp_begin, uint32_t spp_end) {
     size_t n = (size_t) c->S.W * c->S.H * (spp_end - spp_begin);
     if (!c->jobs.count) CK(cudaMalloc(&c->jobs.count, sizeof(unsigned long long)));
     if (n > c->jobs_cap) {
-        cudaFree(c->gbrick);
-    cudaFree(c->jobs.r0); cudaFree(c->jobs.r1); cudaFree(c->jobs.r2); cudaFree(c->jobs.r3);
+        cudaFree(c->jobs.r0); cudaFree(c->jobs.r1); cudaFree(c->jobs.r2); cudaFree(c->jobs.r3);
         c->jobs.r0 = c->jobs.r1 = c->jobs.r2 = c->jobs.r3 = nullptr; c->jobs_cap = 0;
         CK(cudaMalloc(&c->jobs.r0, n * sizeof(float4)));
         CK(cudaMalloc(&c->jobs.r1, n * sizeof(float4)));
@@ -311,7 +310,8 @@ int rcv_ctx_destroy(rcv_ctx *c) {
     free_medium(c);
     cudaFree(c->counters); cudaFree(c->work); cudaFree(c->majorants); cudaFree(c->film_w); cudaFree(c->loss_partial);
     cudaFree(c->queue.r0); cudaFree(c->queue.r1); cudaFree(c->queue.r2); cudaFree(c->queue.r3); cudaFree(c->queue.count);
-    cudaFree(c->jobs.r0); cudaFree(c->jobs.r1); cudaFree(c->jobs.r2); cudaFree(c->jobs.r3); cudaFree(c->jobs.count); cudaFree(c->arena); cudaFree(c->mgrid);
+    cudaFree(c->jobs.r0); cudaFree(c->jobs.r1); cudaFree(c->jobs.r2); cudaFree(c->jobs.r3); cudaFree(c->jobs.count);
+    cudaFree(c->gbrick); cudaFree(c->arena); cudaFree(c->mgrid);
     auto &E = c->e2e;
     cudaFree(E.sigma); cudaFree(E.albedo); cudaFree(E.ref); cudaFree(E.acc); cudaFree(E.HF); cudaFree(E.cv);
     cudaFree(E.grad_img); cudaFree(E.loss); cudaFree(E.g_sigma); cudaFree(E.g_albedo);

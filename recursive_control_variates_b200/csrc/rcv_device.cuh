@@ -100,11 +100,11 @@ struct GridKS : GridK {
 // sites) hit an array that fits in L2 at 256^3 — and d albedo as float4 per
 // voxel (rgb + one unused lane) so a scattering vertex needs one
 // red.global.add.v4.f32 per corner.
-// RCV_GRAD_BRICKS = 1: the d sigma_t reductions of one interpolation site go to ONE 32-byte "gradient brick" of the
-// site's cell (two red.v4, one sector) instead of eight scalar reds in four sectors of the voxel grid; launch_unbrick
-// folds the bricks into gsig after the adjoint launch.
+// RCV_GRAD_BRICKS = 1 (default): the d sigma_t reductions of one interpolation site go to ONE 32-byte "gradient brick"
+// of the site's cell (two red.v4, one sector) instead of eight scalar reds in four sectors of the voxel grid;
+// launch_unbrick folds the bricks into gsig after the adjoint launch and leaves them zero.  0 = reds on the voxel grid.
 #ifndef RCV_GRAD_BRICKS
-#define RCV_GRAD_BRICKS 0
+#define RCV_GRAD_BRICKS 1
 #endif
 struct GradK {
     float *gsig;
