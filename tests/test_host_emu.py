@@ -17,10 +17,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 EMU_DIR = os.path.join(HERE, "host_emu")
 
 
-@pytest.fixture(scope="module")
-def emu():
-    subprocess.run(["make", "-C", EMU_DIR], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
-    lib = C.CDLL(os.path.join(EMU_DIR, "librcv_emu.so"))
+def _load_emu(name):
+    subprocess.run(["make", "-C", EMU_DIR, "all"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+    lib = C.CDLL(os.path.join(EMU_DIR, name))
     f32 = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
     u64 = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
     lib.emu_twostates.argtypes = [C.c_void_p, f32, f32, f32, f32, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int,
@@ -36,6 +35,17 @@ def emu():
     lib.emu_vps_drt_stages.argtypes = [C.c_void_p, f32, f32, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32,
                                        C.c_void_p, C.c_void_p, f32, f32, u64, C.c_int, C.c_int]
     return lib
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return _load_emu("librcv_emu.so")
+
+
+@pytest.fixture(scope="module")
+def emu_voxelreds():
+    """The same machines built with RCV_GRAD_BRICKS=0 (d sigma_t reductions straight into the voxel grid)."""
+    return _load_emu("librcv_emu_voxelreds.so")
 
 
 @pytest.fixture(scope="module")
@@ -267,3 +277,31 @@ def test_drt_stages_of_the_event_machines(oracle, emu, use_mis, factor, depths):
     assert int(cnt[2]) < int(oc[2])          # vertex-list adjoint: the main path's null collisions are not repeated
     assert rel_l2(g1, gs) < 1e-5             # float vs double accumulation
     assert rel_l2(g4[..., 0:3], ga) < 1e-5
+
+
+def test_gradient_bricks_and_voxel_reductions_agree(oracle, emu, emu_voxelreds, setup):
+    """RCV_GRAD_BRICKS: the d sigma_t contributions of a site go to the site's 32-byte gradient brick and are folded into
+    the voxel grid after the launch (default), or straight into the voxel grid (0).  Same sites, same values: the two
+    builds differ in float summation order only, for the path-replay adjoint and for the DRT stages."""
+    d = setup["desc"]
+    sn, an = setup["new"]
+    H, W = d.film_height, d.film_width
+    grad_img = (np.random.default_rng(8).standard_normal((H, W, 3)) / (H * W * 3)).astype(np.float32)
+    seed_grad, spp = 4242, 2
+    film_w = oracle.film_weights(d, seed_grad, spp)
+    out = {}
+    for name, lib in (("bricks", emu), ("voxels", emu_voxelreds)):
+        acc = np.zeros((H, W, 4), np.float32)
+        g1 = np.zeros((*sn.shape[:3], 1), np.float32); g4 = np.zeros((*sn.shape[:3], 4), np.float32); cnt = np.zeros(8, np.uint64)
+        lib.emu_vps(C.addressof(d), sn, an, *sn.shape[:3], seed_grad, spp, 1, oracle.alt_seed(seed_grad),
+                    grad_img.ctypes.data, film_w.ctypes.data, acc, g1, g4, cnt)
+        d1 = np.zeros_like(g1); d4 = np.zeros_like(g4); dcnt = np.zeros(8, np.uint64)
+        lib.emu_vps_drt_stages(C.addressof(d), sn, an, *sn.shape[:3], seed_grad, spp, oracle.alt_seed(seed_grad),
+                               grad_img.ctypes.data, film_w.ctypes.data, d1, d4, dcnt, 0, 1)
+        out[name] = (g1, g4, cnt, d1, d4, dcnt)
+    b, v = out["bricks"], out["voxels"]
+    assert np.array_equal(b[2], v[2]) and np.array_equal(b[5], v[5])            # same events
+    assert np.array_equal(b[1], v[1]) and np.array_equal(b[4], v[4])            # the albedo gradient does not use bricks
+    assert rel_l2(b[0], v[0]) < 1e-6 and rel_l2(b[3], v[3]) < 1e-6
+    gs, _ = oracle.vps_backward(d, setup["mn"], seed_grad, spp, grad_img, threads=1, film_w=film_w)
+    assert rel_l2(b[0], gs) < 1e-5 and rel_l2(v[0], gs) < 1e-5
