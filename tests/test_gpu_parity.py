@@ -200,6 +200,50 @@ def test_drt_with_majorant_supergrid(oracle, gpu_ctx):
     assert rel_l2(ggs.cpu().numpy(), gs) < 1e-4 and rel_l2(gga.cpu().numpy(), ga) < 1e-4
 
 
+def test_analytic_pins_on_gpu():
+    """The closed forms of tests/test_oracle.py (Beer-Lambert image and gradient of a purely absorbing medium, white
+    furnace) against the CUDA path directly — no oracle in the loop."""
+    from helpers import analytic_transmittance
+    from recursive_control_variates_b200.runtime import Context
+    from recursive_control_variates_b200.scene import SceneConfig
+    from recursive_control_variates_b200.synthetic import make_medium
+    cfg = SceneConfig(width=16, height=16, sigma_t_scale=4.0, env_radiance=(0.8, 1.0, 1.2))
+    sig = np.full((6, 6, 6, 1), 0.5, np.float32); alb = np.zeros((6, 6, 6, 3), np.float32)
+    ctx = Context(0)
+    ctx.set_scene(cfg.to_desc())
+    gpu_set_states(ctx, (sig, alb), (sig, alb))
+    T, lT = analytic_transmittance(cfg, 4.0 * 0.5)
+    env = np.array([0.8, 1.0, 1.2])
+    spp = 512
+    H_, F_ = ctx.render_twostates(seed=6, spp=spp)
+    imgs = [ctx.develop(ctx.render_adjoint_primal_accum(seed=5, spp=spp)).cpu().numpy(), H_.cpu().numpy(), F_.cpu().numpy()]
+    for img in imgs:
+        err = img - T[..., None] * env
+        assert np.abs(err).max() < 5 * 1.2 * np.sqrt(0.25 / spp) and abs(err.mean()) < 4e-3
+    gimg = np.full((16, 16, 3), 1.0 / (16 * 16 * 3), np.float32)
+    analytic = float((-(2.0 * lT)[..., None] * env * gimg).sum())
+    for drt in (False, True):
+        ctx.set_drt(drt)
+        ctx.grad_zero(); ctx.render_backward(9, spp, to_cuda(gimg))
+        gs, ga = ctx.grad_read()
+        assert abs(float((gs.cpu().numpy().astype(np.float64) * sig).sum()) - analytic) < 0.03 * abs(analytic), drt
+    # white furnace: albedo 1, uniform environment
+    sig, _ = make_medium(8, "dense", 0.0)
+    alb = np.ones((8, 8, 8, 3), np.float32)
+    kw = dict(width=12, height=12, sigma_t_scale=6.0, env_radiance=(1, 1, 1), max_depth=256, rr_depth=256, phase="hg", phase_g=0.6)
+    for nee in (True, False):
+        ctx = Context(0)
+        ctx.set_scene(SceneConfig(use_nee=nee, sample_emitters=nee, **kw).to_desc())
+        gpu_set_states(ctx, (sig, alb), (sig, alb))
+        H_, F_ = ctx.render_twostates(seed=4, spp=512 if nee else 64)
+        imgs = [ctx.develop(ctx.render_adjoint_primal_accum(seed=3, spp=512 if nee else 64)).cpu().numpy(), H_.cpu().numpy(), F_.cpu().numpy()]
+        for img in imgs:
+            if nee:
+                assert abs(float(img.mean()) - 1.0) < 4e-3 and 0.9 < img.min() and img.max() < 1.1
+            else:
+                assert np.abs(img - 1.0).max() < 1e-5
+
+
 def test_backward_sharding(gpu_ctx, setup):
     d = setup["desc"]
     g = to_cuda(np.full((d.film_height, d.film_width, 3), 1e-4, np.float32))

@@ -305,3 +305,41 @@ def test_gradient_bricks_and_voxel_reductions_agree(oracle, emu, emu_voxelreds, 
     assert rel_l2(b[0], v[0]) < 1e-6 and rel_l2(b[3], v[3]) < 1e-6
     gs, _ = oracle.vps_backward(d, setup["mn"], seed_grad, spp, grad_img, threads=1, film_w=film_w)
     assert rel_l2(b[0], gs) < 1e-5 and rel_l2(v[0], gs) < 1e-5
+
+
+@pytest.mark.parametrize("case", ["absorbing", "furnace"])
+def test_limit_media_on_the_event_machines(oracle, emu, case):
+    """The media of the analytic pins (tests/test_oracle.py): albedo 0 (the throughput dies at the first real collision)
+    and albedo 1 with max_depth = 256 — lane for lane against the oracle, both tracers and the adjoint."""
+    from recursive_control_variates_b200.scene import SceneConfig
+    from recursive_control_variates_b200.synthetic import make_medium
+    if case == "absorbing":
+        d = SceneConfig(width=16, height=16, sigma_t_scale=4.0, env_radiance=(0.8, 1.0, 1.2)).to_desc()
+        sn = np.full((6, 6, 6, 1), 0.5, np.float32); an = np.zeros((6, 6, 6, 3), np.float32)
+    else:
+        d = SceneConfig(width=12, height=12, sigma_t_scale=6.0, env_radiance=(1, 1, 1), max_depth=256, rr_depth=256,
+                        phase="hg", phase_g=0.6).to_desc()
+        sn, _ = make_medium(8, "dense", 0.0); an = np.ones((8, 8, 8, 3), np.float32)
+    m = oracle.OracleMedium(d, sn, an)
+    H, W = d.film_height, d.film_width
+    acc_o = np.zeros((H, W, 4), np.float32); acc_n = np.zeros((H, W, 4), np.float32); cnt = np.zeros(8, np.uint64)
+    emu.emu_twostates(C.addressof(d), sn, an, sn, an, *sn.shape[:3], 21, 1, 0, acc_o, acc_n, cnt)
+    ref_o, ref_n = oracle.render_twostates_accum(d, m, m, 21, 1)
+    assert np.array_equal(acc_o, ref_o) and np.array_equal(acc_n, ref_n)
+    acc = np.zeros((H, W, 4), np.float32); g1 = np.zeros((*sn.shape[:3], 1), np.float32); g4 = np.zeros((*sn.shape[:3], 4), np.float32)
+    emu.emu_vps(C.addressof(d), sn, an, *sn.shape[:3], 22, 1, 0, 0, None, None, acc, g1, g4, cnt)
+    assert np.array_equal(acc, oracle.vps_render_accum(d, m, 22, 1))
+    gimg = np.full((H, W, 3), 1.0 / (H * W * 3), np.float32)
+    film_w = oracle.film_weights(d, 23, 2)
+    emu.emu_vps(C.addressof(d), sn, an, *sn.shape[:3], 23, 2, 1, oracle.alt_seed(23), gimg.ctypes.data, film_w.ctypes.data, acc, g1, g4, cnt)
+    gs, ga = oracle.vps_backward(d, m, 23, 2, gimg, threads=1, film_w=film_w)
+    assert rel_l2(g1, gs) < 1e-5
+    assert (not ga.any() and not g4.any()) if case == "absorbing" else rel_l2(g4[..., 0:3], ga) < 1e-5
+    d1 = np.zeros_like(g1); d4 = np.zeros_like(g4)
+    emu.emu_vps_drt_stages(C.addressof(d), sn, an, *sn.shape[:3], 23, 2, oracle.alt_seed(23), gimg.ctypes.data, film_w.ctypes.data,
+                           d1, d4, cnt, 0, 1)
+    ds, da = oracle.vps_backward(d, m, 23, 2, gimg, threads=1, film_w=film_w, use_drt=True)
+    assert rel_l2(d1, ds) < 1e-5
+    # (with albedo 0 the path-replay term has no albedo gradient, its throughput being 0 past the vertex; the DRT
+    # term does: d(sigma_t * albedo * L_i) / d albedo = sigma_t * L_i)
+    assert da.any() and rel_l2(d4[..., 0:3], da) < 1e-5

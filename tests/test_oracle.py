@@ -197,6 +197,52 @@ def test_drt_variance_behaviour(oracle):
     assert dense_mis < 1.25 * total_var(20.0)
 
 
+# ---------------------------------------------------------------------------
+# analytic pins: the restatement against closed forms, independent of any restated code
+# ---------------------------------------------------------------------------
+def test_absorbing_medium_matches_beer_lambert(oracle):
+    """Homogeneous, purely absorbing medium (albedo 0): every pixel is env * exp(-sigma_t * chord) and the gradient of
+    sum(g * img) along sigma_t -> sigma_t (1 + eps) is -sum(g * env * sigma_t * chord * exp(-sigma_t * chord)).  Pins the
+    camera model, the box intersection, delta tracking, the film and the transmittance term of the adjoint."""
+    from helpers import analytic_transmittance
+    from recursive_control_variates_b200.scene import SceneConfig
+    cfg = SceneConfig(width=16, height=16, sigma_t_scale=4.0, env_radiance=(0.8, 1.0, 1.2))
+    d = cfg.to_desc()
+    sig = np.full((6, 6, 6, 1), 0.5, np.float32); alb = np.zeros((6, 6, 6, 3), np.float32)
+    m = oracle.OracleMedium(d, sig, alb)
+    T, lT = analytic_transmittance(cfg, 4.0 * 0.5)
+    env = np.array([0.8, 1.0, 1.2])
+    spp = 512
+    for img in (oracle.develop(oracle.vps_render_accum(d, m, 5, spp)), *oracle.render_twostates(d, m, m, 6, spp)):
+        err = img - T[..., None] * env
+        assert np.abs(err).max() < 5 * 1.2 * np.sqrt(0.25 / spp)          # 5 sigma of a Bernoulli(T) mean
+        assert abs(err.mean()) < 4e-3
+    gimg = np.full((16, 16, 3), 1.0 / (16 * 16 * 3), np.float32)
+    gs, ga = oracle.vps_backward(d, m, 9, spp, gimg)
+    analytic = float((-(2.0 * lT)[..., None] * env * gimg).sum())
+    assert abs(float((gs * sig).sum()) - analytic) < 0.02 * abs(analytic)
+    assert not ga.any()                                                    # no scattering, no albedo gradient
+
+
+@pytest.mark.parametrize("phase,g", [("isotropic", 0.0), ("hg", 0.6)])
+def test_white_furnace(oracle, phase, g):
+    """Albedo 1 under a uniform environment of radiance 1: every pixel is 1 in expectation for any density, with emitter
+    sampling + MIS (to Monte Carlo noise) and without (exactly: every path ends in the environment).  Pins the phase
+    function's sampling against its pdf, the emitter pdf, the MIS weights and the environment term of both tracers."""
+    from recursive_control_variates_b200.scene import SceneConfig
+    from recursive_control_variates_b200.synthetic import make_medium
+    sig, _ = make_medium(8, "dense", 0.0)
+    alb = np.ones((8, 8, 8, 3), np.float32)
+    kw = dict(width=12, height=12, sigma_t_scale=6.0, env_radiance=(1, 1, 1), max_depth=256, rr_depth=256, phase=phase, phase_g=g)
+    d = SceneConfig(**kw).to_desc()
+    m = oracle.OracleMedium(d, sig, alb)
+    for img in (oracle.develop(oracle.vps_render_accum(d, m, 3, 512)), *oracle.render_twostates(d, m, m, 4, 512)):
+        assert abs(float(img.mean()) - 1.0) < 4e-3 and 0.9 < img.min() and img.max() < 1.1
+    d = SceneConfig(use_nee=False, sample_emitters=False, **kw).to_desc()
+    for img in (oracle.develop(oracle.vps_render_accum(d, m, 3, 64)), *oracle.render_twostates(d, m, m, 4, 64)):
+        assert np.abs(img - 1.0).max() < 1e-6
+
+
 def test_adam_clamp_upsample(oracle):
     p = np.array([0.5, 1.0], np.float32); g = np.array([1.0, -2.0], np.float32)
     m = np.zeros(2, np.float32); v = np.zeros(2, np.float32)
