@@ -195,7 +195,7 @@ int ensure_gbrick(rcv_ctx *c) {
     if (ncell != c->gbrick_cells) {
         cudaFree(c->gbrick); c->gbrick = nullptr; c->gbrick_cells = 0;
         CK(cudaMalloc(&c->gbrick, 2 * ncell * sizeof(float4)));
-        CK(cudaMemsetAsync(c->gbrick, 0, 2 * ncell * sizeof(float4), c->stream));
+        CK(cudaMemset(c->gbrick, 0, 2 * ncell * sizeof(float4)));     // once per grid shape; synchronous: the stream may change
         c->gbrick_cells = ncell;
     }
 #endif
