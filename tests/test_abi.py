@@ -54,6 +54,13 @@ def test_no_cpu_fallback(lib):
         Context()
 
 
+def test_null_context_is_an_argument_error(lib):
+    """Setters reject a null context before touching the device (no compute call, runs without a GPU)."""
+    for fn, args in ((lib.rcv_ctx_set_tracer, (None, 3)), (lib.rcv_adjoint_set_drt, (None, 1, 1, 1)),
+                     (lib.rcv_ctx_set_stream, (None, None))):
+        assert fn(*args) == 1 and b"null" in lib.rcv_last_error()            # RCV_ERR_ARG
+
+
 def test_product_does_not_import_oracle():
     """Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may touch oracle/."""
     pkg = os.path.join(ROOT, "recursive_control_variates_b200")
