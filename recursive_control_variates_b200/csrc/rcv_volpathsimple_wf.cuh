@@ -69,7 +69,14 @@ enum : uint32_t {
 };
 
 // vertex record flags
-enum : uint32_t { VR_SCATTER = 1u, VR_NEE = 2u, VR_NEE_DONE = 4u /* its transmittance gradients were scattered in pass 1 */ };
+enum : uint32_t { VR_SCATTER = 1u, VR_NEE = 2u, VR_NEE_DONE = 4u /* its transmittance gradients were scattered in pass 1 */,
+                  VR_ALBEDO = 8u /* the record carries the vertex's albedo (RCV_VERTEX_ALBEDO) */ };
+// RCV_VERTEX_ALBEDO = 1: pass 1 leaves the albedo it gathered at a scattering vertex in the vertex record (in the words
+// that hold the shadow-ray direction, which only the replay fall-back needs), so pass 2 does not gather its eight
+// corners again.  Same value, same arithmetic.  Off by default: built and checked on the host, not yet measured.
+#ifndef RCV_VERTEX_ALBEDO
+#define RCV_VERTEX_ALBEDO 0
+#endif
 // records (position, -1 / (majorant * tr)) of the tentative collisions of one shadow ray, kept per arena slot behind the
 // vertex records; 16 vertex-record equivalents
 static constexpr int kNeeCap = 64;
@@ -285,7 +292,16 @@ __device__ __forceinline__ void vp_nee_done(const SceneK &S, const GridK &G, VpL
     if (BW) {
         float4 *r = vp_record(sk, ln, ln.nvert - 1);
         r[2] = make_float4(__uint_as_float((uint32_t) ln.saved), __uint_as_float((uint32_t) (ln.saved >> 32)), ln.nee.x, ln.nee.y);
+#if RCV_VERTEX_ALBEDO
+        if (ln.flags & VF_NEE_OVF) {      // the replay needs the direction: the albedo gives way
+            r[3] = make_float4(ln.nee.z, ln.nd.x, ln.nd.y, ln.nd.z);
+            r[1].w = __uint_as_float(__float_as_uint(r[1].w) & ~VR_ALBEDO);
+        } else {
+            r[3].x = ln.nee.z;
+        }
+#else
         r[3] = make_float4(ln.nee.z, ln.nd.x, ln.nd.y, ln.nd.z);
+#endif
         if (!(ln.flags & VF_NEE_OVF)) {
             // transmittance gradients of the shadow ray (:406-414, :496-505) from the recorded collisions: the same
             // values the replay in pass 2 would compute, scattered now
@@ -414,7 +430,13 @@ __device__ __forceinline__ void vp_vertex1(const SceneK &S, const GridK &G, VpLa
     if (BW) {
         float4 *r = vp_record(sk, ln, ln.nvert);
         r[0] = make_float4(ln.o.x, ln.o.y, ln.o.z, did_scatter ? ln.mei_t : ln.ray_maxt);   // interval of :601
+#if RCV_VERTEX_ALBEDO
+        r[1] = make_float4(ln.d.x, ln.d.y, ln.d.z,
+                           __uint_as_float((did_scatter ? (VR_SCATTER | VR_ALBEDO) : 0u) | (do_nee ? VR_NEE : 0u)));
+        if (did_scatter) r[3] = make_float4(0.f, albedo.x, albedo.y, albedo.z);
+#else
         r[1] = make_float4(ln.d.x, ln.d.y, ln.d.z, __uint_as_float((did_scatter ? VR_SCATTER : 0u) | (do_nee ? VR_NEE : 0u)));
+#endif
         ln.nvert += 1;
     }
     if (do_nee) {                                                     // :393-446
@@ -461,7 +483,13 @@ __device__ __forceinline__ void vp_vertex2(const SceneK &S, const GridK &G, VpLa
         V3 mei_p = ray_at(ln.o, ln.d, interval);                      // :384
         Tri T = tri_setup(S, G, mei_p);
         float st = lookup_sigma1(S, G, T);                            // :386-388
+#if RCV_VERTEX_ALBEDO
+        V3 albedo;
+        if (vf & VR_ALBEDO) { float4 r3 = r[3]; albedo = mk3(r3.y, r3.z, r3.w); }
+        else albedo = lookup_albedo(G, T, 1);
+#else
         V3 albedo = lookup_albedo(G, T, 1);                           // :154
+#endif
         sk.cnt.scat++;
         if (DRT == 1) ln.thr = ln.thr * albedo;                       // :206, for the next iteration's reservoir update
         // scattering term (:165-185): backward_from(drt_mis_weight * dL * (sigma_t * albedo) * Li * inv_pdf)

@@ -279,6 +279,39 @@ def test_drt_stages_of_the_event_machines(oracle, emu, use_mis, factor, depths):
     assert rel_l2(g4[..., 0:3], ga) < 1e-5
 
 
+@pytest.fixture(scope="module")
+def emu_vertex_albedo():
+    """The same machines built with RCV_VERTEX_ALBEDO=1 (pass 2 reads the albedo from the vertex record)."""
+    return _load_emu("librcv_emu_vertex_albedo.so")
+
+
+def test_vertex_record_albedo_is_the_same_adjoint(oracle, emu, emu_vertex_albedo):
+    """RCV_VERTEX_ALBEDO: the albedo pass 2 needs at a scattering vertex is the one pass 1 gathered; carried in the
+    vertex record it gives bit-identical gradients — also when shadow rays overflow their record buffer and the replay
+    takes the record's words back (dense medium), and for the DRT stages."""
+    from recursive_control_variates_b200.scene import SceneConfig
+    from recursive_control_variates_b200.synthetic import make_medium
+    for kind, scale, depth in (("cube", 20.0, 12), ("dense", 160.0, 6)):
+        d = SceneConfig(width=20, height=16, max_depth=depth, rr_depth=4, sigma_t_scale=scale).to_desc()
+        sn, an = make_medium(10, kind, 5e-3)
+        H, W = d.film_height, d.film_width
+        grad_img = (np.random.default_rng(9).standard_normal((H, W, 3)) / (H * W * 3)).astype(np.float32)
+        film_w = oracle.film_weights(d, 31, 2)
+        res = []
+        for lib in (emu, emu_vertex_albedo):
+            acc = np.zeros((H, W, 4), np.float32)
+            g1 = np.zeros((*sn.shape[:3], 1), np.float32); g4 = np.zeros((*sn.shape[:3], 4), np.float32); cnt = np.zeros(8, np.uint64)
+            lib.emu_vps(C.addressof(d), sn, an, *sn.shape[:3], 31, 2, 1, oracle.alt_seed(31), grad_img.ctypes.data,
+                        film_w.ctypes.data, acc, g1, g4, cnt)
+            d1 = np.zeros_like(g1); d4 = np.zeros_like(g4); dcnt = np.zeros(8, np.uint64)
+            lib.emu_vps_drt_stages(C.addressof(d), sn, an, *sn.shape[:3], 31, 2, oracle.alt_seed(31), grad_img.ctypes.data,
+                                   film_w.ctypes.data, d1, d4, dcnt, 0, 1)
+            res.append((g1, g4, cnt, d1, d4, dcnt))
+        for a, b in zip(*res):
+            assert np.array_equal(a, b)
+        assert res[0][0].any() and res[0][3].any()
+
+
 def test_gradient_bricks_and_voxel_reductions_agree(oracle, emu, emu_voxelreds, setup):
     """RCV_GRAD_BRICKS: the d sigma_t contributions of a site go to the site's 32-byte gradient brick and are folded into
     the voxel grid after the launch (default), or straight into the voxel grid (0).  Same sites, same values: the two
