@@ -68,6 +68,8 @@ def lib() -> C.CDLL:
         L.orc_vps_render.argtypes = [SP, MP, u32, u32, u32, u32, _f32p, i32]
         L.orc_vps_backward.argtypes = [SP, MP, u32, u32, u32, u32, _f32p, _f32p, _f64p, _f64p, i32]
         L.orc_vps_backward_drt.argtypes = [SP, MP, u32, u32, u32, u32, _f32p, _f32p, _f64p, _f64p, i32, i32, i32]
+        L.orc_phase_sample.argtypes = [SP, _f32p, f, f, _f32p]; L.orc_phase_sample.restype = f
+        L.orc_phase_eval.argtypes = [SP, _f32p, _f32p]; L.orc_phase_eval.restype = f
         L.orc_adam_lr_t.argtypes = [f, f, f, i32]; L.orc_adam_lr_t.restype = f
         L.orc_adam.argtypes = [_f32p, _f32p, _f32p, _f32p, u64, i32, f, f, f, f]
         L.orc_clamp.argtypes = [_f32p, u64, f, f]
@@ -236,6 +238,17 @@ def vps_backward(desc, m: OracleMedium, seed_grad, spp_grad, grad_img, spp_begin
         rc = lib().orc_vps_backward(*args)
     assert rc == 0
     return gs, ga
+
+
+def phase_sample(desc, wi, s2x, s2y):
+    """(wo, pdf) of the scene's phase function for incident direction wi (pointing away from the vertex)."""
+    wo = np.zeros(3, np.float32)
+    pdf = lib().orc_phase_sample(C.addressof(desc), np.ascontiguousarray(wi, np.float32), float(s2x), float(s2y), wo)
+    return wo, float(pdf)
+
+
+def phase_eval(desc, wi, wo):
+    return float(lib().orc_phase_eval(C.addressof(desc), np.ascontiguousarray(wi, np.float32), np.ascontiguousarray(wo, np.float32)))
 
 
 def adam(p, g, m, v, t, lr, beta1=0.9, beta2=0.999, eps=1e-8):

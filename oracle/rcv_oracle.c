@@ -1546,6 +1546,17 @@ static void vps_sample(const rcv_scene_desc *S, const orc_medium *M, int primal,
 /* the seed of the adjoint's secondary sampler (volpathsimple.py:112-120): the
  * float drawn by *lane 0* after the film and channel draws, reinterpreted as
  * an integer and scrambled.  A pure function of seed_grad. */
+/* test hooks for the phase function (isotropic / Henyey-Greenstein [UPSTREAM hg.cpp]) */
+float orc_phase_sample(const rcv_scene_desc *S, const float wi[3], float s2x, float s2y, float wo_out[3]) {
+    float pdf;
+    v3 wo = phase_sample(S, V3(wi[0], wi[1], wi[2]), 0.f, s2x, s2y, &pdf);
+    wo_out[0] = wo.x; wo_out[1] = wo.y; wo_out[2] = wo.z;
+    return pdf;
+}
+float orc_phase_eval(const rcv_scene_desc *S, const float wi[3], const float wo[3]) {
+    return phase_eval(S, V3(wi[0], wi[1], wi[2]), V3(wo[0], wo[1], wo[2]));
+}
+
 uint32_t orc_alt_seed(uint32_t seed_grad) {
     pcg32 r; sampler_seed(&r, seed_grad, 0);
     (void) next_1d(&r, 1); (void) next_1d(&r, 1);       /* film jitter */

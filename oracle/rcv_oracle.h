@@ -66,6 +66,9 @@ int orc_vps_backward_drt(const rcv_scene_desc *S, const orc_medium *M, uint32_t 
                          uint32_t spp_begin, uint32_t spp_end, const float *grad_img, const float *film_w,
                          double *grad_sigma_t, double *grad_albedo, int nthreads, int use_drt_subsampling, int use_drt_mis);
 
+float orc_phase_sample(const rcv_scene_desc *S, const float wi[3], float s2x, float s2y, float wo_out[3]);
+float orc_phase_eval(const rcv_scene_desc *S, const float wi[3], const float wo[3]);
+
 float orc_adam_lr_t(float lr, float beta1, float beta2, int t);
 void orc_adam(float *p, const float *g, float *m, float *v, uint64_t n, int t, float lr, float beta1,
               float beta2, float eps);

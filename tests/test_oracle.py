@@ -243,6 +243,35 @@ def test_white_furnace(oracle, phase, g):
         assert np.abs(img - 1.0).max() < 1e-6
 
 
+@pytest.mark.parametrize("g", [0.0, 0.6, 0.877, -0.4])
+def test_phase_function_against_henyey_greenstein(oracle, g):
+    """Sampled directions follow the analytic Henyey-Greenstein density p(mu) = (1 - g^2) / (2 (1 + g^2 - 2 g mu)^1.5) in
+    mu = cos(angle to the direction of travel, -wi) — positive g scatters forward, E[mu] = g — and the returned pdf is
+    the evaluated phase function, p(mu) / 2 pi (experiments.py:179-182 uses g = 0.877)."""
+    from recursive_control_variates_b200.scene import SceneConfig
+    d = SceneConfig(phase="hg" if g else "isotropic", phase_g=g).to_desc()
+    wi = np.array([0.3, -0.5, 0.81], np.float32); wi /= np.linalg.norm(wi)
+    rng = np.random.default_rng(1)
+    n = 20000
+    mu = np.empty(n)
+    for i in range(n):
+        wo, pdf = oracle.phase_sample(d, wi, rng.random(), rng.random())
+        mu[i] = float(np.dot(wo.astype(np.float64), -wi.astype(np.float64)))
+        if i < 100:
+            p_mu = (1 - g * g) / (2 * (1 + g * g - 2 * g * mu[i]) ** 1.5)
+            assert abs(pdf - p_mu / (2 * np.pi)) < 2e-4 * pdf
+            assert abs(oracle.phase_eval(d, wi, wo) - pdf) < 1e-4 * pdf
+            assert abs(np.linalg.norm(wo) - 1) < 1e-5
+    assert abs(mu.mean() - g) < 4 * mu.std() / np.sqrt(n) + 1e-3
+    # histogram against the analytic cumulative distribution (Kolmogorov-Smirnov, 1 % level: 1.63 / sqrt(n))
+    xs = np.sort(mu)
+    if g:
+        cdf = (1 - g * g) / (2 * g) * (1 / np.sqrt(1 + g * g - 2 * g * xs) - 1 / (1 + g))
+    else:
+        cdf = (xs + 1) / 2
+    assert np.abs(cdf - (np.arange(n) + 0.5) / n).max() < 1.63 / np.sqrt(n)
+
+
 def test_adam_clamp_upsample(oracle):
     p = np.array([0.5, 1.0], np.float32); g = np.array([1.0, -2.0], np.float32)
     m = np.zeros(2, np.float32); v = np.zeros(2, np.float32)
