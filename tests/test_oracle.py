@@ -272,6 +272,22 @@ def test_phase_function_against_henyey_greenstein(oracle, g):
     assert np.abs(cdf - (np.arange(n) + 0.5) / n).max() < 1.63 / np.sqrt(n)
 
 
+def test_image_orientation_follows_mitsuba(oracle):
+    """Mitsuba's sensor frame is right-handed with +z forward and +y up, so +x is to the LEFT of the view; film pixel (0, 0)
+    is the top-left corner [UPSTREAM perspective.cpp: scale(-0.5, -0.5 * aspect) in sample_to_camera].  The default camera
+    looks down +z: an absorber in the (+x, +y) half of the box darkens the top-left quadrant of the image — a mirrored or
+    flipped image would satisfy every other test here."""
+    from recursive_control_variates_b200.scene import SceneConfig
+    d = SceneConfig(width=16, height=16, sigma_t_scale=30.0).to_desc()
+    n = 8
+    sig = np.zeros((n, n, n, 1), np.float32)
+    sig[:, n // 2:, n // 2:, 0] = 1.0                       # grid order [z][y][x]: x >= 0.5 and y >= 0.5
+    m = oracle.OracleMedium(d, sig, np.zeros((n, n, n, 3), np.float32))
+    img = oracle.develop(oracle.vps_render_accum(d, m, 1, 64))[..., 0]
+    quad = {"tl": img[:8, :8].mean(), "tr": img[:8, 8:].mean(), "bl": img[8:, :8].mean(), "br": img[8:, 8:].mean()}
+    assert quad["tl"] < 0.8 and min(quad["tr"], quad["bl"], quad["br"]) > 0.9, quad
+
+
 def test_adam_clamp_upsample(oracle):
     p = np.array([0.5, 1.0], np.float32); g = np.array([1.0, -2.0], np.float32)
     m = np.zeros(2, np.float32); v = np.zeros(2, np.float32)
