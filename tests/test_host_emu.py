@@ -376,3 +376,61 @@ def test_limit_media_on_the_event_machines(oracle, emu, case):
     # (with albedo 0 the path-replay term has no albedo gradient, its throughput being 0 past the vertex; the DRT
     # term does: d(sigma_t * albedo * L_i) / d albedo = sigma_t * L_i)
     assert da.any() and rel_l2(d4[..., 0:3], da) < 1e-5
+
+
+@pytest.mark.parametrize("case", range(24))
+def test_randomised_scenes_lane_for_lane(oracle, emu, case):
+    """Seeded random scenes — ragged grids, cameras outside and inside the box, scaled boxes, both phase functions,
+    Russian roulette, box / gaussian film, multi-view films, majorant supergrids — through both tracers, the adjoint and
+    the DRT stages of the event machines: spp = 1 accumulators bit for bit, gradients to float-summation order."""
+    from recursive_control_variates_b200.scene import SceneConfig, look_at
+    rng = np.random.default_rng(1000 + case)
+    nz, ny, nx = (int(v) for v in rng.integers(1, 9, 3))
+    factor = 0
+    if case % 3 == 2:                                     # supergrid: dims must be multiples of the factor
+        factor = int(rng.integers(2, 4))
+        nz, ny, nx = (factor * int(v) for v in rng.integers(1, 4, 3))
+    bmax = [1.0, float(rng.uniform(0.6, 1.6)), float(rng.uniform(0.6, 1.6))]
+    inside = case % 4 == 3
+    eye = [float(rng.uniform(0.2, 0.8)) * b for b in bmax] if inside else \
+        [float(v) for v in (rng.uniform(1.5, 3.0, 3) * rng.choice([-1, 1], 3) + 0.5)]
+    target = [float(rng.uniform(0.3, 0.7)) * b for b in bmax]
+    n_views = 2 if case % 5 == 4 else 1
+    W = int(rng.integers(3, 14)) * n_views; H = int(rng.integers(3, 12))
+    views = look_at(eye, target, [0, 1, 0])
+    if n_views == 2:
+        views = np.stack([views, look_at([eye[2], eye[0], eye[1]], target, [0, 0, 1])])
+    hg = bool(rng.integers(0, 2))
+    d = SceneConfig(width=W, height=H, fov=float(rng.uniform(25, 70)), to_world=views, bbox_max=bmax,
+                    sigma_t_scale=float(rng.uniform(2, 40)), phase="hg" if hg else "isotropic",
+                    phase_g=float(rng.uniform(-0.8, 0.9)) if hg else 0.0, max_depth=int(rng.integers(1, 20)),
+                    rr_depth=int(rng.integers(0, 6)), hide_emitters=bool(rng.integers(0, 2)),
+                    env_radiance=tuple(float(v) for v in rng.uniform(0.2, 1.5, 3)),
+                    rfilter="gaussian" if case % 2 else "box", rfilter_stddev=float(rng.uniform(0.25, 0.5))).to_desc()
+    so = rng.random((nz, ny, nx, 1), dtype=np.float32); so[rng.random(so.shape) < 0.25] = 0.0
+    ao = rng.random((nz, ny, nx, 3), dtype=np.float32)
+    sn = np.clip(so + rng.normal(0, 0.02, so.shape).astype(np.float32), 0, 1).astype(np.float32)
+    an = np.clip(ao + rng.normal(0, 0.02, ao.shape).astype(np.float32), 0, 1).astype(np.float32)
+    mo = oracle.OracleMedium(d, so, ao, majorant_factor=factor); mn = oracle.OracleMedium(d, sn, an, majorant_factor=factor)
+    acc_o = np.zeros((H, W, 4), np.float32); acc_n = np.zeros((H, W, 4), np.float32); cnt = np.zeros(8, np.uint64)
+    emu.emu_twostates_sg(C.addressof(d), so, ao, sn, an, nz, ny, nx, 5, 1, 0, factor, acc_o, acc_n, cnt)
+    ref_o, ref_n = oracle.render_twostates_accum(d, mo, mn, 5, 1, threads=1)
+    # box filter: one sample per pixel, bit for bit; gaussian: footprints overlap, the splats sum in another order
+    same = (lambda a, b: np.array_equal(a, b, equal_nan=True)) if case % 2 == 0 else (lambda a, b: rel_l2(a, b) < 1e-6)
+    assert same(acc_o, ref_o) and same(acc_n, ref_n)
+    assert ref_n[..., 3].any() and int(cnt[0]) > 0           # the film is hit and the medium is entered
+    acc = np.zeros((H, W, 4), np.float32); g1 = np.zeros((nz, ny, nx, 1), np.float32); g4 = np.zeros((nz, ny, nx, 4), np.float32)
+    emu.emu_vps_sg(C.addressof(d), sn, an, nz, ny, nx, 6, 1, 0, 0, None, None, acc, g1, g4, cnt, factor)
+    assert same(acc, oracle.vps_render_accum(d, mn, 6, 1, threads=1))
+    gimg = (rng.standard_normal((H, W, 3)) / (H * W * 3)).astype(np.float32)
+    film_w = oracle.film_weights(d, 7, 2)
+    emu.emu_vps_sg(C.addressof(d), sn, an, nz, ny, nx, 7, 2, 1, oracle.alt_seed(7), gimg.ctypes.data, film_w.ctypes.data,
+                   acc, g1, g4, cnt, factor)
+    gs, ga = oracle.vps_backward(d, mn, 7, 2, gimg, threads=1, film_w=film_w)
+    tol = lambda a, b: rel_l2(a, b) < 2e-5 if np.any(b) else not np.any(a)
+    assert tol(g1, gs) and tol(g4[..., 0:3], ga)
+    d1 = np.zeros_like(g1); d4 = np.zeros_like(g4)
+    emu.emu_vps_drt_stages(C.addressof(d), sn, an, nz, ny, nx, 7, 2, oracle.alt_seed(7), gimg.ctypes.data, film_w.ctypes.data,
+                           d1, d4, cnt, factor, 1)
+    ds, da = oracle.vps_backward(d, mn, 7, 2, gimg, threads=1, film_w=film_w, use_drt=True)
+    assert tol(d1, ds) and tol(d4[..., 0:3], da)
