@@ -1,5 +1,5 @@
-// rcv_volpathsimple_wf.cuh — VolpathSimpleIntegrator (plugins/volpathsimple.py,
-// use_drt = False) as a per-lane event machine, for the persistent-warp
+// rcv_volpathsimple_wf.cuh — VolpathSimpleIntegrator (plugins/volpathsimple.py;
+// use_drt = True: see "DRT" below) as a per-lane event machine, for the persistent-warp
 // schedulers.  Same estimator, same random streams and the same arithmetic as
 // rcv_volpathsimple.cuh (the straight-line restatement kept as A/B baseline), but
 // the adjoint is organised as a VERTEX LIST:
