@@ -128,30 +128,94 @@ def measured_peaks():
 # ----------------------------------------------------------------------------
 # CPU arm: the oracle (CPU restatement of the reference path) on the host cores
 # ----------------------------------------------------------------------------
-def cpu_iteration_sample(a, n_gpus, sample_spp, threads):
+def cpu_iteration_sample(a, n_gpus, sample_spp, threads, keep=None, use_drt=False):
     """Times one bounded sample of the step on the CPU: samples [0, sample_spp) of every pixel
-    for the two-state render and for both adjoint passes, on the same grids/film/seeds."""
+    for the two-state render and for both adjoint passes, on the same grids/film/seeds.
+    keep: a dict that receives the oracle's outputs for that sample range (the parity block compares the GPU with them)."""
     import oracle as O
     from recursive_control_variates_b200.runtime import tea32
     from recursive_control_variates_b200.scene import SceneConfig
     from recursive_control_variates_b200.synthetic import make_medium
     O.build()
-    desc = SceneConfig(width=a.res, height=a.res, rfilter=a.rfilter).to_desc()
+    desc = scene_config(a).to_desc()
     old, new = make_medium(a.grid, a.kind, 0.0), make_medium(a.grid, a.kind, 5e-3)
-    mo, mn = O.OracleMedium(desc, *old), O.OracleMedium(desc, *new)
+    mo, mn = O.OracleMedium(desc, *old, majorant_factor=a.majorant_factor), O.OracleMedium(desc, *new, majorant_factor=a.majorant_factor)
     spp = a.spp * n_gpus
-    npix = a.res * a.res
+    npix = a.res * a.res * a.views
     seed = SEED0
     seed_grad = tea32(seed, 1)[0]
-    grad_img = np.full((a.res, a.res, 3), 1.0 / (npix * 3), np.float32)
-    film_w = np.full((a.res, a.res), float(spp), np.float32)
+    grad_img = np.full((a.res, a.res * a.views, 3), 1.0 / (npix * 3), np.float32)
+    film_w = O.film_weights(desc, seed_grad, spp) if a.rfilter != "box" else np.full((a.res, a.res * a.views), float(spp), np.float32)
     t0 = time.perf_counter()
-    O.render_twostates_accum(desc, mo, mn, seed, spp, 0, sample_spp, threads=threads)
+    acc = O.render_twostates_accum(desc, mo, mn, seed, spp, 0, sample_spp, threads=threads)
     t1 = time.perf_counter()
-    O.vps_backward(desc, mn, seed_grad, spp, grad_img, 0, sample_spp, threads=threads, film_w=film_w)
+    grads = O.vps_backward(desc, mn, seed_grad, spp, grad_img, 0, sample_spp, threads=threads, film_w=film_w, use_drt=use_drt)
     t2 = time.perf_counter()
+    if keep is not None:
+        keep.update(acc_old=acc[0], acc_new=acc[1], g_sigma=grads[0], g_albedo=grads[1], grad_img=grad_img, film_w=film_w,
+                    sample_spp=sample_spp, seed=seed, seed_grad=seed_grad, old=old, new=new)
     paths = npix * sample_spp * 3
     return paths, t2 - t0, t1 - t0, t2 - t1
+
+
+def scene_config(a):
+    """The bench scene: SURVEY.md 8(d)'s camera / medium box, `--config` decides filter, phase function and views."""
+    from recursive_control_variates_b200.scene import SceneConfig, look_at
+    kw = dict(width=a.res * a.views, height=a.res, rfilter=a.rfilter)
+    if a.hg != 0.0:
+        kw.update(phase="hg", phase_g=a.hg)
+    if a.views > 1:           # the reference's batch sensor (experiments.py:28-50): cameras on a circle around the medium
+        import math
+        kw["to_world"] = np.stack([look_at([0.5 + 2 * math.cos(2 * math.pi / a.views * i + 0.1), 0.5,
+                                            0.5 + 2 * math.sin(2 * math.pi / a.views * i + 0.1)], [0.5, 0.5, 0.5], [0, 1, 0])
+                                   for i in range(a.views)])
+    return SceneConfig(**kw)
+
+
+def rel_l2(x, y):
+    x, y = np.asarray(x, np.float64), np.asarray(y, np.float64)
+    return float(np.linalg.norm(x - y) / max(np.linalg.norm(y), 1e-300))
+
+
+def parity_block(a, ctx, dev, keep1, keepN, keep_drt, spp_total):
+    """GPU against the oracle at the MEASURED configuration: the same grids, film and seeds, sample range [0, n) of the
+    spp the bench runs (n = what the CPU leg could afford).  Images and gradients as relative L2; samples [0, 1) — one
+    lane per pixel under the box filter — compared bit for bit."""
+    import torch
+    cu = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    k = keepN
+    ctx.set_drt(False)
+    ctx.rotate(cu(k["old"][0]), cu(k["old"][1])); ctx.rotate(cu(k["new"][0]), cu(k["new"][1]))
+    out = {"config": f"{a.config}: the measured grids / film / seeds, samples [0,{k['sample_spp']}) of {spp_total} spp of every pixel",
+           "tolerance": "images 1e-4, gradients 1e-3 relative L2 (north_star); lanes bit-exact"}
+    dev_img = lambda acc: (acc[..., :3] / np.where(acc[..., 3:] == 0, 1, acc[..., 3:]))
+    if keep1 is not None:
+        g_old, g_new = ctx.render_twostates_accum(k["seed"], spp_total, 0, 1)
+        eq = np.array_equal(g_old.cpu().numpy(), keep1["acc_old"]) and np.array_equal(g_new.cpu().numpy(), keep1["acc_new"])
+        out["lanes_bit_exact"] = bool(eq) if a.rfilter == "box" else None
+        out["lanes_compared"] = int(np.prod(keep1["acc_old"].shape[:2]))
+    g_old, g_new = ctx.render_twostates_accum(k["seed"], spp_total, 0, k["sample_spp"])
+    out["img_rel_l2_old"] = rel_l2(dev_img(g_old.cpu().numpy()), dev_img(k["acc_old"]))
+    out["img_rel_l2_new"] = rel_l2(dev_img(g_new.cpu().numpy()), dev_img(k["acc_new"]))
+    gi, fw = cu(k["grad_img"]), cu(k["film_w"])
+    ctx.grad_zero()
+    ctx.render_backward(k["seed_grad"], spp_total, gi, 0, k["sample_spp"], film_w=fw)
+    gs, ga = ctx.grad_read()
+    out["grad_sigma_rel_l2"] = rel_l2(gs.cpu().numpy(), k["g_sigma"])
+    out["grad_albedo_rel_l2"] = rel_l2(ga.cpu().numpy(), k["g_albedo"])
+    if keep_drt is not None:
+        ctx.set_drt(True)
+        ctx.grad_zero()
+        ctx.render_backward(keep_drt["seed_grad"], spp_total, gi, 0, keep_drt["sample_spp"], film_w=fw)
+        gs, ga = ctx.grad_read()
+        out["drt"] = {"samples": f"[0,{keep_drt['sample_spp']})", "grad_sigma_rel_l2": rel_l2(gs.cpu().numpy(), keep_drt["g_sigma"]),
+                      "grad_albedo_rel_l2": rel_l2(ga.cpu().numpy(), keep_drt["g_albedo"]),
+                      "note": "use_drt / sub-sampling / MIS on; Medium::sample_interaction_drt is restated from the paper (unpinned)"}
+        ctx.set_drt(a.use_drt)
+    out["pass"] = bool(out["img_rel_l2_old"] < 1e-4 and out["img_rel_l2_new"] < 1e-4 and out["grad_sigma_rel_l2"] < 1e-3 and
+                       out["grad_albedo_rel_l2"] < 1e-3 and out.get("lanes_bit_exact") in (True, None) and
+                       (keep_drt is None or (out["drt"]["grad_sigma_rel_l2"] < 1e-3 and out["drt"]["grad_albedo_rel_l2"] < 1e-3)))
+    return out
 
 
 def calibrated_sample_spp(a, n_gpus, threads, budget_s):

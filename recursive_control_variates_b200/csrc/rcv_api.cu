@@ -550,6 +550,17 @@ int rcv_render_backward_weighted(rcv_ctx *c, int adjoint_kind, uint32_t seed_gra
     if (int r = ensure_gbrick(c)) return r;
     GradK D = c->gradk();
     const bool pin = c->l2_persist && c->l2_persist_max > 0 && c->l2_window_max > 0;
+    // the access-policy window is dropped (and the persisting lines released) on every way out, errors included
+    struct PinGuard {
+        cudaStream_t st; bool on;
+        ~PinGuard() {
+            if (!on) return;
+            cudaStreamAttrValue a{};
+            a.accessPolicyWindow.num_bytes = 0;
+            cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &a);
+            cudaCtxResetPersistingL2Cache();       // give the set-aside lines back to the kernels that follow
+        }
+    } guard{c->stream, false};
     if (pin) {
         // L2 access-policy window over the d sigma_t grid: the adjoint's scattered reductions hit L2
         cudaStreamAttrValue a{};
@@ -561,18 +572,13 @@ int rcv_render_backward_weighted(rcv_ctx *c, int adjoint_kind, uint32_t seed_gra
         a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
         a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
         CK(cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &a));
+        guard.on = true;
     }
     CK(launch_vps_backward(cfg, c->S, c->gridk(), D, seed_grad, spp_grad, spp_begin, spp_end, alt_seed_for(seed_grad), grad_img,
                            film_w));
 #if RCV_GRAD_BRICKS
     CK(launch_unbrick(cfg, D, c->nx, c->ny, c->nz));
 #endif
-    if (pin) {
-        cudaStreamAttrValue a{};
-        a.accessPolicyWindow.num_bytes = 0;
-        CK(cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &a));
-        CK(cudaCtxResetPersistingL2Cache());       // give the set-aside lines back to the kernels that follow
-    }
     return RCV_OK;
 }
 

@@ -506,6 +506,27 @@ __device__ __forceinline__ float lookup_sigma1(const SceneK &S, const GridK &G, 
     ld_brick32(b, q0, q1);                                                           // one 32-byte brick
     return S.scale * tri_lerp(T, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w);
 }
+// Two-phase lookups (rcv_pool.cuh, RCV_POOL_ILP > 1): *_issue starts the brick load of a tentative collision and *_finish
+// interpolates it, so that one thread can have the bricks of several lanes in flight before it consumes the first.
+// The loads are volatile: they stay where they are written (a pure asm would be sunk to its first use).  Same values
+// and the same arithmetic as lookup_sigma1.
+struct Brick1 { float4 q0, q1; };
+__device__ __forceinline__ void ld_brick32_issue(const float4 *p, float4 &a, float4 &b) {
+#if RCV_BRICK_LOAD != 2 || !defined(__CUDA_ARCH__)
+    a = __ldg(p); b = __ldg(p + 1);
+#else
+    asm volatile("ld.global.nc.L2::64B.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+#endif
+}
+__device__ __forceinline__ void sigma1_issue(const GridK &G, const Tri &T, Brick1 &b) {
+    b.q0 = make_float4(0.f, 0.f, 0.f, 0.f); b.q1 = b.q0;
+    if (T.inside) ld_brick32_issue(G.blk1 + 2 * (size_t) tri_cell(G, T), b.q0, b.q1);
+}
+__device__ __forceinline__ float sigma1_finish(const SceneK &S, const Tri &T, const Brick1 &b) {
+    if (!T.inside) return 0.f;
+    return S.scale * tri_lerp(T, b.q0.x, b.q0.y, b.q0.z, b.q0.w, b.q1.x, b.q1.y, b.q1.z, b.q1.w);
+}
 // 16-byte read-only load with the same L2::64B hint (albedo corners: scattered 32-byte voxel records)
 __device__ __forceinline__ float4 ld_corner16(const float4 *p) {
 #if RCV_BRICK_LOAD != 2 || !defined(__CUDA_ARCH__)

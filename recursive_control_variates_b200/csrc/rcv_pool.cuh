@@ -1,7 +1,7 @@
 // rcv_pool.cuh — warp-private lane pools in shared memory (POOL schedule).
 //
 // A warp owns kPoolSlots = 64 lane states, stored structure-of-arrays in shared
-// memory (word w of slot s at pool[w * 64 + s]: consecutive slots hit consecutive
+// memory (word w of slot s at pool[w * kPoolSlots + s]: consecutive slots hit consecutive
 // banks).  Every round the warp picks ONE event class and up to 32 slots waiting
 // for it, loads those lanes into registers, runs the handler of rcv_*_wf.cuh and
 // stores them back.  With twice as many lanes as threads the tentative-collision
@@ -15,6 +15,8 @@
 namespace rcv {
 
 static constexpr int kPoolSlots = 64;
+static constexpr int kPoolMaskWords = kPoolSlots / 32;
+static_assert(kPoolSlots <= 256, "slot indices are bytes");
 
 __device__ __forceinline__ float pf_u(uint32_t v) { return __uint_as_float(v); }
 __device__ __forceinline__ uint32_t pu_f(float v) { return __float_as_uint(v); }
@@ -120,26 +122,28 @@ __device__ __forceinline__ void vp_pool_store_all(float *pw, int s, const VpLane
 #undef PW
 
 // ---------------------------------------------------------------------------
-// slot selection: the (up to) 32 lowest slots whose class bit is set; thread k
-// receives the k-th of them (or -1).  `list` is a 64-byte warp-private scratch.
+// slot selection: list[r] = the r-th lowest slot whose class bit is set (m[j] covers slots 32 j .. 32 j + 31); returns
+// their number.  `list` is a kPoolSlots-byte warp-private scratch; thread k then reads list[k], list[k + 32], ...
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ int pool_select(unsigned m_lo, unsigned m_hi, unsigned char *list) {
+__device__ __forceinline__ int pool_list(const unsigned (&m)[kPoolMaskWords], unsigned char *list) {
     const unsigned lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
-    const int n_lo = __popc(m_lo);
-    if ((m_lo >> lane) & 1u) list[__popc(m_lo & lt)] = (unsigned char) lane;
-    if ((m_hi >> lane) & 1u) {
-        int r = n_lo + __popc(m_hi & lt);
-        if (r < kPoolSlots) list[r] = (unsigned char) (lane + 32);
+    int base = 0;
+#pragma unroll
+    for (int j = 0; j < kPoolMaskWords; ++j) {
+        if ((m[j] >> lane) & 1u) list[base + __popc(m[j] & lt)] = (unsigned char) (lane + 32 * j);
+        base += __popc(m[j]);
     }
     __syncwarp();
-    int n = n_lo + __popc(m_hi);
-    int slot = ((int) lane < n) ? (int) list[lane] : -1;
-    __syncwarp();
-    return slot;
+    return base;
+}
+// the slot of this thread in batch b of a round over the first n listed slots (or -1)
+__device__ __forceinline__ int pool_slot(const unsigned char *list, int n, int b) {
+    const int r = (int) (threadIdx.x & 31) + 32 * b;
+    return (r < n) ? (int) list[r] : -1;
 }
 
-// which class to run: collisions when a full warp of them is ready, otherwise the fullest queue
+// which class to run: collisions when a full round of them is ready, otherwise the fullest queue
 __device__ __forceinline__ int pool_pick(int n_coll, int n_scat, int n_slow) {
     if (n_coll >= 32) return EV_COLL;
     if (n_coll >= n_scat && n_coll >= n_slow && n_coll > 0) return EV_COLL;

@@ -387,17 +387,41 @@ __global__ void __launch_bounds__(kWfBlock, RCV_VP_MINBLOCKS) k_vps_wavefront(co
 #ifndef RCV_POOL_BLOCK
 #define RCV_POOL_BLOCK 128
 #endif
+// CTAs per SM.  Shared memory allows 4 pools of 4 warps; the adjoint's speculative collision step (two bricks in flight
+// per lane) needs ~165 registers, so its kernels run 3 (r2c: 4 CTAs at 128 registers spill, 18.6 ms against 15.3 ms).
 #ifndef RCV_POOL_MINBLOCKS
-#define RCV_POOL_MINBLOCKS 4
+#define RCV_POOL_MINBLOCKS (RCV_SPEC_COLLIDE > 1 ? 3 : 4)
 #endif
 #ifndef RCV_TS_POOL_MINBLOCKS
-#define RCV_TS_POOL_MINBLOCKS RCV_POOL_MINBLOCKS
+#define RCV_TS_POOL_MINBLOCKS 4
 #endif
-static constexpr int kPoolBlock = RCV_POOL_BLOCK;
-static constexpr int kPoolWarps = kPoolBlock / 32;
+#ifndef RCV_VP_POOL_BLOCK
+#define RCV_VP_POOL_BLOCK RCV_POOL_BLOCK
+#endif
+static constexpr int kPoolBlock = RCV_POOL_BLOCK;          // two-state kernels
+static constexpr int kVpPoolBlock = RCV_VP_POOL_BLOCK;     // volpathsimple kernels
 
 template <int WORDS>
 __host__ __device__ constexpr size_t pool_warp_floats() { return (size_t) WORDS * kPoolSlots + 2 * kPoolSlots / 4; }
+
+// the class of every slot of the warp's pool as ballot masks (slots 32 j .. 32 j + 31 in word j)
+struct PoolMasks {
+    unsigned coll[kPoolMaskWords], scat[kPoolMaskWords], slow[kPoolMaskWords];
+    int n_coll, n_scat, n_slow;
+};
+__device__ __forceinline__ void pool_masks(const unsigned char *cls, bool more, PoolMasks &M) {
+    const unsigned lane = threadIdx.x & 31;
+    M.n_coll = M.n_scat = M.n_slow = 0;
+#pragma unroll
+    for (int j = 0; j < kPoolMaskWords; ++j) {
+        const int c = cls[lane + 32 * j];
+        M.coll[j] = __ballot_sync(0xffffffffu, c == EV_COLL);
+        M.scat[j] = __ballot_sync(0xffffffffu, c == EV_SCAT);
+        // lanes waiting for the slow step: parked work, or empty slots while records remain
+        M.slow[j] = __ballot_sync(0xffffffffu, c == EV_SLOW || (c == EV_INIT && more));
+        M.n_coll += __popc(M.coll[j]); M.n_scat += __popc(M.scat[j]); M.n_slow += __popc(M.slow[j]);
+    }
+}
 
 template <int MODE, class GRID>
 __global__ void __launch_bounds__(kPoolBlock, RCV_TS_POOL_MINBLOCKS) k_twostates_pool(const __grid_constant__ SceneK S,
@@ -414,22 +438,19 @@ __global__ void __launch_bounds__(kPoolBlock, RCV_TS_POOL_MINBLOCKS) k_twostates
     const unsigned long long n_total = *Q.count;
     TsSink sk; sk.acc_old = acc_old; sk.acc_new = acc_new; sk.n_coll = sk.n_scat = sk.n_paths = 0;
     ChunkCursor cc; cc.next = 0; cc.end = 0; cc.more = true;
-    cls[lane] = EV_INIT; cls[lane + 32] = EV_INIT;
+#pragma unroll
+    for (int j = 0; j < kPoolMaskWords; ++j) cls[lane + 32 * j] = EV_INIT;
     __syncwarp();
     while (true) {
-        const int c0 = cls[lane], c1 = cls[lane + 32];
-        const unsigned coll_lo = __ballot_sync(0xffffffffu, c0 == EV_COLL), coll_hi = __ballot_sync(0xffffffffu, c1 == EV_COLL);
-        const unsigned scat_lo = __ballot_sync(0xffffffffu, c0 == EV_SCAT), scat_hi = __ballot_sync(0xffffffffu, c1 == EV_SCAT);
-        const unsigned slow_lo = __ballot_sync(0xffffffffu, c0 == EV_SLOW || (c0 == EV_INIT && cc.more));
-        const unsigned slow_hi = __ballot_sync(0xffffffffu, c1 == EV_SLOW || (c1 == EV_INIT && cc.more));
-        const int n_coll = __popc(coll_lo) + __popc(coll_hi), n_scat = __popc(scat_lo) + __popc(scat_hi);
-        const int n_slow = __popc(slow_lo) + __popc(slow_hi);
-        if (n_coll == 0 && n_scat == 0 && n_slow == 0) break;
-        const int sel = pool_pick(n_coll, n_scat, n_slow);
-        TsLane ln;
+        PoolMasks M;
+        pool_masks(cls, cc.more, M);
+        if (M.n_coll == 0 && M.n_scat == 0 && M.n_slow == 0) break;
+        const int sel = pool_pick(M.n_coll, M.n_scat, M.n_slow);
         if (sel == EV_COLL) {
-            const int s = pool_select(coll_lo, coll_hi, list);
+            const int n = min(pool_list(M.coll, list), 32);
+            const int s = pool_slot(list, n, 0);
             if (s >= 0) {
+                TsLane ln;
                 ts_pool_load_hot(pw, s, ln);
                 ln.ev = EV_COLL;
                 ts_collide<MODE>(S, G, mu, inv_mu, ln, sk);
@@ -437,8 +458,9 @@ __global__ void __launch_bounds__(kPoolBlock, RCV_TS_POOL_MINBLOCKS) k_twostates
                 cls[s] = (unsigned char) ln.ev;
             }
         } else if (sel == EV_SCAT) {
-            const int s = pool_select(scat_lo, scat_hi, list);
+            const int s = pool_slot(list, min(pool_list(M.scat, list), 32), 0);
             if (s >= 0) {
+                TsLane ln;
                 ts_pool_load_hot(pw, s, ln); ts_pool_load_cold(pw, s, ln);
                 ln.ev = EV_SCAT;
                 ts_scatter<MODE>(S, G, ln, sk);
@@ -446,7 +468,8 @@ __global__ void __launch_bounds__(kPoolBlock, RCV_TS_POOL_MINBLOCKS) k_twostates
                 cls[s] = (unsigned char) ln.ev;
             }
         } else {
-            const int s = pool_select(slow_lo, slow_hi, list);
+            const int s = pool_slot(list, min(pool_list(M.slow, list), 32), 0);
+            TsLane ln;
             ln.ev = EV_INIT;
             bool loaded = false;
             if (s >= 0 && cls[s] == EV_SLOW) {
@@ -493,7 +516,7 @@ __device__ __forceinline__ void pool_drt_complete(const SceneK &S, const GRID &G
 }
 
 template <bool BACKWARD, class GRID, int DRT = 0>
-__global__ void __launch_bounds__(kPoolBlock, RCV_POOL_MINBLOCKS) k_vps_pool(const __grid_constant__ SceneK S,
+__global__ void __launch_bounds__(kVpPoolBlock, RCV_POOL_MINBLOCKS) k_vps_pool(const __grid_constant__ SceneK S,
                                                                              const __grid_constant__ GRID G, GradK D, uint32_t seed,
                                                                              uint32_t spp, uint32_t alt_seed, const float *grad_img,
                                                                              const float *film_w, float4 *accum, PathQueue Q,
@@ -512,33 +535,34 @@ __global__ void __launch_bounds__(kPoolBlock, RCV_POOL_MINBLOCKS) k_vps_pool(con
     sk.seed = seed; sk.spp = spp; sk.alt_seed = alt_seed;
     sk.cnt.coll = sk.cnt.scat = sk.cnt.g_sig = sk.cnt.g_alb = 0; sk.n_paths = 0;
     sk.jobs = jobs; sk.drt_mis = drt_mis;
-    const uint32_t slot0 = (blockIdx.x * kPoolWarps + (threadIdx.x >> 5)) * kPoolSlots;   // first arena slot of this warp's pool
+    const uint32_t slot0 = (blockIdx.x * (kVpPoolBlock / 32) + (threadIdx.x >> 5)) * kPoolSlots;   // first arena slot of this warp's pool
     ChunkCursor cc; cc.next = 0; cc.end = 0; cc.more = true;
-    cls[lane] = EV_INIT; cls[lane + 32] = EV_INIT;
+#pragma unroll
+    for (int j = 0; j < kPoolMaskWords; ++j) cls[lane + 32 * j] = EV_INIT;
     __syncwarp();
     while (true) {
-        const int c0 = cls[lane], c1 = cls[lane + 32];
-        const unsigned coll_lo = __ballot_sync(0xffffffffu, c0 == EV_COLL), coll_hi = __ballot_sync(0xffffffffu, c1 == EV_COLL);
-        const unsigned scat_lo = __ballot_sync(0xffffffffu, c0 == EV_SCAT), scat_hi = __ballot_sync(0xffffffffu, c1 == EV_SCAT);
-        const unsigned slow_lo = __ballot_sync(0xffffffffu, c0 == EV_SLOW || (c0 == EV_INIT && cc.more));
-        const unsigned slow_hi = __ballot_sync(0xffffffffu, c1 == EV_SLOW || (c1 == EV_INIT && cc.more));
-        const int n_coll = __popc(coll_lo) + __popc(coll_hi), n_scat = __popc(scat_lo) + __popc(scat_hi);
-        const int n_slow = __popc(slow_lo) + __popc(slow_hi);
-        if (n_coll == 0 && n_scat == 0 && n_slow == 0) break;
-        const int sel = pool_pick(n_coll, n_scat, n_slow);
+        PoolMasks M;
+        pool_masks(cls, cc.more, M);
+        if (M.n_coll == 0 && M.n_scat == 0 && M.n_slow == 0) break;
+        const int sel = pool_pick(M.n_coll, M.n_scat, M.n_slow);
         VpLane ln;
         if (sel == EV_COLL) {
-            const int s = pool_select(coll_lo, coll_hi, list);
+            const int n = min(pool_list(M.coll, list), 32);
+            const int s = pool_slot(list, n, 0);
             if (s >= 0) {
                 vp_pool_load_hot(pw, s, ln);
                 ln.ev = EV_COLL;
                 ln.vbase = (slot0 + (uint32_t) s) * (vcap + kNeeCap / 4);    // a cold word; the collision records live behind it
+#if RCV_SPEC_COLLIDE > 1
+                vp_collide_spec<BACKWARD>(S, G, mu, inv_mu, ln, sk);
+#else
                 vp_collide<BACKWARD>(S, G, mu, inv_mu, ln, sk);
+#endif
                 vp_pool_store_coll(pw, s, ln);
                 cls[s] = (unsigned char) ln.ev;
             }
         } else if (sel == EV_SCAT) {
-            const int s = pool_select(scat_lo, scat_hi, list);
+            const int s = pool_slot(list, min(pool_list(M.scat, list), 32), 0);
             if (s >= 0) {
                 vp_pool_load_hot(pw, s, ln); vp_pool_load_cold(pw, s, ln);
                 ln.ev = EV_SCAT;
@@ -548,7 +572,7 @@ __global__ void __launch_bounds__(kPoolBlock, RCV_POOL_MINBLOCKS) k_vps_pool(con
             }
             if (DRT != 0) pool_drt_complete<DRT>(S, G, ln, sk, s >= 0 && ln.ev == EV_INIT && (ln.flags & VF_JOB));
         } else {
-            const int s = pool_select(slow_lo, slow_hi, list);
+            const int s = pool_slot(list, min(pool_list(M.slow, list), 32), 0);
             ln.ev = EV_INIT; ln.flags = 0;
             bool loaded = false;
             if (s >= 0 && cls[s] == EV_SLOW) {
@@ -612,18 +636,19 @@ __global__ void __launch_bounds__(kBlock) k_drt_sample(const __grid_constant__ S
 
 // launch a pool kernel: dynamic shared memory opt-in, persistent grid
 template <typename K, typename... Args>
-static cudaError_t launch_pool(const LaunchCfg &cfg, K kernel, size_t smem_bytes, uint64_t n_items, Args... args) {
+static cudaError_t launch_pool(const LaunchCfg &cfg, K kernel, int block, size_t smem_bytes, uint64_t n_items, Args... args) {
+    const int warps = block / 32;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_bytes);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kPoolBlock, smem_bytes);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem_bytes);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    uint64_t want = (n_items + (uint64_t) kPoolWarps * kPoolSlots - 1) / ((uint64_t) kPoolWarps * kPoolSlots);
+    uint64_t want = (n_items + (uint64_t) warps * kPoolSlots - 1) / ((uint64_t) warps * kPoolSlots);
     uint64_t b = (uint64_t) per_sm * cfg.sm_count;
     if (b > want) b = want;
     if (b < 1) b = 1;
-    kernel<<<(unsigned) b, kPoolBlock, smem_bytes, cfg.stream>>>(args...);
+    kernel<<<(unsigned) b, block, smem_bytes, cfg.stream>>>(args...);
     return cudaGetLastError();
 }
 
@@ -653,7 +678,7 @@ static cudaError_t launch_twostates_mode(const LaunchCfg &cfg, const SceneK &S, 
         k_twostates_raygen<MODE><<<(unsigned) ((n_local + kBlock - 1) / kBlock), kBlock, 0, cfg.stream>>>(
             S, seed, spp, spp_begin, ns, n_local, acc_old, acc_new, cfg.queue, cfg.counters);
         if (cfg.tracer == 3) {
-            e = launch_pool(cfg, k_twostates_pool<MODE, GRID>, kPoolWarps * pool_warp_floats<kTsWords>() * sizeof(float), n_local, S, G,
+            e = launch_pool(cfg, k_twostates_pool<MODE, GRID>, kPoolBlock, (kPoolBlock / 32) * pool_warp_floats<kTsWords>() * sizeof(float), n_local, S, G,
                             acc_old, acc_new, cfg.queue, cfg.counters, cfg.work_counter);
             if (e != cudaSuccess) return e;
         } else {
@@ -706,14 +731,14 @@ static cudaError_t launch_vps(const LaunchCfg &cfg, const SceneK &S, const GRID 
     cudaError_t e;
     if (BACKWARD && (cfg.drt_flags & 3) == 3 && cfg.tracer == 3) {
         // use_drt with sub-sampling on the pool machines: adjoint + reservoir -> jobs -> recursive radiance estimate
-        const size_t smem = kPoolWarps * pool_warp_floats<kVpWords>() * sizeof(float);
+        const size_t smem = (kVpPoolBlock / 32) * pool_warp_floats<kVpWords>() * sizeof(float);
         const int mis = (cfg.drt_flags & 4) ? 1 : 0;
         if ((e = cudaMemsetAsync(cfg.work_counter, 0, sizeof(unsigned long long), cfg.stream)) != cudaSuccess) return e;
         if ((e = cudaMemsetAsync(cfg.queue.count, 0, sizeof(unsigned long long), cfg.stream)) != cudaSuccess) return e;
         if ((e = cudaMemsetAsync(cfg.jobs.count, 0, sizeof(unsigned long long), cfg.stream)) != cudaSuccess) return e;
         k_vps_raygen<true><<<(unsigned) ((n_local + kBlock - 1) / kBlock), kBlock, 0, cfg.stream>>>(
             S, seed, spp, spp_begin, ns, n_local, accum, cfg.queue, cfg.counters, grad_img, film_w);
-        e = launch_pool(cfg, k_vps_pool<true, GRID, 1>, smem, n_local, S, G, D, seed, spp, alt_seed, grad_img, film_w, accum,
+        e = launch_pool(cfg, k_vps_pool<true, GRID, 1>, kVpPoolBlock, smem, n_local, S, G, D, seed, spp, alt_seed, grad_img, film_w, accum,
                         cfg.queue, cfg.counters, cfg.work_counter, cfg.arena, cfg.vcap, cfg.jobs, mis);
         if (e != cudaSuccess) return e;
         if ((e = cudaMemsetAsync(cfg.queue.count, 0, sizeof(unsigned long long), cfg.stream)) != cudaSuccess) return e;
@@ -721,7 +746,7 @@ static cudaError_t launch_vps(const LaunchCfg &cfg, const SceneK &S, const GRID 
         if ((e = persistent_grid(cfg, k_drt_sample<GRID>, kBlock, n_local, blocks)) != cudaSuccess) return e;
         k_drt_sample<GRID><<<blocks, kBlock, 0, cfg.stream>>>(S, G, D, cfg.jobs, cfg.queue, mis, cfg.counters);
         if ((e = cudaMemsetAsync(cfg.work_counter, 0, sizeof(unsigned long long), cfg.stream)) != cudaSuccess) return e;
-        e = launch_pool(cfg, k_vps_pool<false, GRID, 2>, smem, n_local, S, G, D, seed, spp, alt_seed, grad_img, film_w, accum,
+        e = launch_pool(cfg, k_vps_pool<false, GRID, 2>, kVpPoolBlock, smem, n_local, S, G, D, seed, spp, alt_seed, grad_img, film_w, accum,
                         cfg.queue, cfg.counters, cfg.work_counter, cfg.arena, cfg.vcap, cfg.jobs, mis);
         if (e != cudaSuccess) return e;
         (*cfg.launches) += 4;
@@ -744,7 +769,7 @@ static cudaError_t launch_vps(const LaunchCfg &cfg, const SceneK &S, const GRID 
         k_vps_raygen<BACKWARD><<<(unsigned) ((n_local + kBlock - 1) / kBlock), kBlock, 0, cfg.stream>>>(
             S, seed, spp, spp_begin, ns, n_local, accum, qv, cfg.counters, grad_img, film_w);
         if (cfg.tracer == 3) {
-            e = launch_pool(cfg, k_vps_pool<BACKWARD, GRID>, kPoolWarps * pool_warp_floats<kVpWords>() * sizeof(float), n_local, S, G, D, seed,
+            e = launch_pool(cfg, k_vps_pool<BACKWARD, GRID>, kVpPoolBlock, (kVpPoolBlock / 32) * pool_warp_floats<kVpWords>() * sizeof(float), n_local, S, G, D, seed,
                             spp, alt_seed, grad_img, film_w, accum, qv, cfg.counters, cfg.work_counter, cfg.arena, cfg.vcap, cfg.jobs, 0);
             if (e != cudaSuccess) return e;
         } else {
@@ -773,18 +798,18 @@ static cudaError_t launch_vps(const LaunchCfg &cfg, const SceneK &S, const GRID 
 size_t vps_backward_slots(const LaunchCfg &cfg) {
     if (cfg.tracer == 3) {
         int per_sm = 0;
-        size_t smem = kPoolWarps * pool_warp_floats<kVpWords>() * sizeof(float);
+        size_t smem = (kVpPoolBlock / 32) * pool_warp_floats<kVpWords>() * sizeof(float);
         cudaFuncSetAttribute(k_vps_pool<true, GridK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vps_pool<true, GridK>, kPoolBlock, smem) != cudaSuccess || per_sm < 1)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vps_pool<true, GridK>, kVpPoolBlock, smem) != cudaSuccess || per_sm < 1)
             per_sm = 1;
         if (cfg.drt_flags & 1) {         // the DRT instance of the adjoint may fit a different number of blocks
             int per_sm_drt = 0;
             cudaFuncSetAttribute(k_vps_pool<true, GridK, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_drt, k_vps_pool<true, GridK, 1>, kPoolBlock, smem) == cudaSuccess &&
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_drt, k_vps_pool<true, GridK, 1>, kVpPoolBlock, smem) == cudaSuccess &&
                 per_sm_drt > per_sm)
                 per_sm = per_sm_drt;
         }
-        return (size_t) per_sm * cfg.sm_count * kPoolWarps * kPoolSlots;
+        return (size_t) per_sm * cfg.sm_count * (kVpPoolBlock / 32) * kPoolSlots;
     }
     if (cfg.tracer == 0) {
         int per_sm = 0;

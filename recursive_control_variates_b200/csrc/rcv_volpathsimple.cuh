@@ -51,6 +51,34 @@ __device__ __forceinline__ void sample_interaction1(const SceneK &S, const GRID 
         if constexpr (GRID::kSupergrid) { m.mu = m_cell; m.inv_mu = 1.f / m.mu; }
     }
 }
+// the same in two phases (rcv_device.cuh "Two-phase lookups"): _issue samples the distance and starts the brick load,
+// _finish interpolates sigma_t
+template <class GRID>
+__device__ __forceinline__ void sample_interaction1_issue(const SceneK &S, const GRID &G, float mu, float inv_mu, V3 o, V3 d, V3 id,
+                                                          float ray_maxt, float u, Mei1 &m, Tri &T, Brick1 &b, VpsCounts &cnt) {
+    float mint, maxt;
+    bool active = medium_interval(S, o, d, id, ray_maxt, mint, maxt);
+    float tau = -spec_log(1.f - u);
+    float t;
+    float m_cell = 0.f;
+    if constexpr (GRID::kSupergrid) t = active ? dda_sample<2>(S, G, o, d, id, mint, maxt, tau, m_cell) : inf_();
+    else t = mint + (tau * inv_mu);
+    m.valid = active && (t <= maxt);
+    m.t = m.valid ? t : inf_();
+    m.p = ray_at(o, d, t);
+    m.st = 0.f;
+    m.mu = mu; m.inv_mu = inv_mu;
+    T.inside = false;
+    if (m.valid) {
+        T = tri_setup(S, G, m.p);
+        sigma1_issue(G, T, b);
+        cnt.coll++;
+        if constexpr (GRID::kSupergrid) { m.mu = m_cell; m.inv_mu = 1.f / m.mu; }
+    }
+}
+__device__ __forceinline__ void sample_interaction1_finish(const SceneK &S, Mei1 &m, const Tri &T, const Brick1 &b) {
+    if (m.valid) m.st = sigma1_finish(S, T, b);
+}
 // convenience overload for callers that do not need the interpolation set-up
 template <class GRID>
 __device__ __forceinline__ void sample_interaction1(const SceneK &S, const GRID &G, float mu, float inv_mu, V3 o, V3 d, V3 id,

@@ -73,9 +73,9 @@ enum : uint32_t { VR_SCATTER = 1u, VR_NEE = 2u, VR_NEE_DONE = 4u /* its transmit
                   VR_ALBEDO = 8u /* the record carries the vertex's albedo (RCV_VERTEX_ALBEDO) */ };
 // RCV_VERTEX_ALBEDO = 1: pass 1 leaves the albedo it gathered at a scattering vertex in the vertex record (in the words
 // that hold the shadow-ray direction, which only the replay fall-back needs), so pass 2 does not gather its eight
-// corners again.  Same value, same arithmetic.  Off by default: built and checked on the host, not yet measured.
+// corners again.  Same value, same arithmetic.  r2a (profiles/README.md): adjoint 17.8 -> 16.9 ms at C2; on by default.
 #ifndef RCV_VERTEX_ALBEDO
-#define RCV_VERTEX_ALBEDO 0
+#define RCV_VERTEX_ALBEDO 1
 #endif
 // records (position, -1 / (majorant * tr)) of the tentative collisions of one shadow ray, kept per arena slot behind the
 // vertex records; 16 vertex-record equivalents
@@ -291,29 +291,34 @@ __device__ __forceinline__ void vp_nee_done(const SceneK &S, const GridK &G, VpL
     ln.result = ln.result + ln.nee;                                   // :225
     if (BW) {
         float4 *r = vp_record(sk, ln, ln.nvert - 1);
+        const bool ovf = (ln.flags & VF_NEE_OVF) != 0;
         r[2] = make_float4(__uint_as_float((uint32_t) ln.saved), __uint_as_float((uint32_t) (ln.saved >> 32)), ln.nee.x, ln.nee.y);
 #if RCV_VERTEX_ALBEDO
-        if (ln.flags & VF_NEE_OVF) {      // the replay needs the direction: the albedo gives way
-            r[3] = make_float4(ln.nee.z, ln.nd.x, ln.nd.y, ln.nd.z);
-            r[1].w = __uint_as_float(__float_as_uint(r[1].w) & ~VR_ALBEDO);
-        } else {
-            r[3].x = ln.nee.z;
-        }
+        if (ovf) r[3] = make_float4(ln.nee.z, ln.nd.x, ln.nd.y, ln.nd.z);      // the replay needs the direction: the albedo gives way
+        else r[3].x = ln.nee.z;
 #else
         r[3] = make_float4(ln.nee.z, ln.nd.x, ln.nd.y, ln.nd.z);
 #endif
-        if (!(ln.flags & VF_NEE_OVF)) {
+        // a vertex that cast a shadow ray is a scattering vertex with VR_NEE set (vp_vertex1): its flag word is written
+        // whole, no read-modify-write of the record
+        r[1].w = __uint_as_float(VR_SCATTER | VR_NEE | (ovf ? 0u : (uint32_t) VR_NEE_DONE) |
+                                 ((RCV_VERTEX_ALBEDO && !ovf) ? (uint32_t) VR_ALBEDO : 0u));
+        if (!ovf) {
             // transmittance gradients of the shadow ray (:406-414, :496-505) from the recorded collisions: the same
-            // values the replay in pass 2 would compute, scattered now
+            // values the replay in pass 2 would compute, scattered now.  The records are read three ahead of their use
+            // (they are L2 hits a few hundred cycles away; one dependent load per iteration stalled the whole step).
             const V3 adjoint = ln.dL * ln.nee;                        // :412
             const int n = __float_as_int(ln.running_t);
+            const float4 *rec = vp_nee_record(sk, ln, 0);
+            const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 c0 = (0 < n) ? rec[0] : zero, c1 = (1 < n) ? rec[1] : zero, c2 = (2 < n) ? rec[2] : zero;
             for (int i = 0; i < n; ++i) {
-                float4 c = *vp_nee_record(sk, ln, i);
+                const float4 c3 = (i + 3 < n) ? rec[i + 3] : zero;
                 float g = 0.f;
-                g += adjoint.x * c.w; g += adjoint.y * c.w; g += adjoint.z * c.w;
-                scatter_sigma_t(S, G, sk.D, mk3(c.x, c.y, c.z), g, sk.cnt);
+                g += adjoint.x * c0.w; g += adjoint.y * c0.w; g += adjoint.z * c0.w;
+                scatter_sigma_t(S, G, sk.D, mk3(c0.x, c0.y, c0.z), g, sk.cnt);
+                c0 = c1; c1 = c2; c2 = c3;
             }
-            r[1].w = __uint_as_float(__float_as_uint(r[1].w) | VR_NEE_DONE);
         }
         ln.flags &= ~VF_NEE_OVF;
     }
@@ -335,8 +340,18 @@ __device__ __forceinline__ void vp_replay_done(VpLane &ln, VpSink &sk) {
     vp_next_vertex<DRT>(ln, sk);
 }
 
+// One tentative collision in two phases, so that a scheduler can start the bricks of several lanes before it consumes
+// the first (rcv_pool.cuh, RCV_POOL_ILP): _pre runs the loop head, samples the free flight and issues the brick load,
+// _post interpolates sigma_t and takes the null / real / escape decision.  vp_collide is the two back to back.
+struct VpColl {
+    bool go;            // false: the lane left the collision class at its loop head, nothing is in flight
+    Mei1 m; Tri T; Brick1 b;
+};
+
 template <bool BW, class GRID>
-__device__ __forceinline__ void vp_collide(const SceneK &S, const GRID &G, float mu_vol, float inv_mu_vol, VpLane &ln, VpSink &sk) {
+__device__ __forceinline__ void vp_collide_pre(const SceneK &S, const GRID &G, float mu_vol, float inv_mu_vol, VpLane &ln, VpSink &sk,
+                                               VpColl &c) {
+    c.go = false;
     const bool nee = (ln.flags & VF_IN_NEE) != 0;
     if (!nee && (ln.flags & VF_HEAD)) {                               // loop head (:129-134)
         float q = fmin_(max3(ln.thr), 0.99f);
@@ -352,8 +367,17 @@ __device__ __forceinline__ void vp_collide(const SceneK &S, const GRID &G, float
     // warp execute the gather together
     const V3 sd = nee ? ln.nd : ln.d;
     float u = pcg_f32(ln.rng);
-    Mei1 m; Tri T;
-    sample_interaction1(S, G, mu_vol, inv_mu_vol, ln.ro, sd, ln.id, ln.rmaxt, u, m, T, sk.cnt);
+    sample_interaction1_issue(S, G, mu_vol, inv_mu_vol, ln.ro, sd, ln.id, ln.rmaxt, u, c.m, c.T, c.b, sk.cnt);
+    c.go = true;
+}
+
+template <bool BW, class GRID>
+__device__ __forceinline__ void vp_collide_post(const SceneK &S, const GRID &G, VpLane &ln, VpSink &sk, const VpColl &c) {
+    if (!c.go) return;
+    const bool nee = (ln.flags & VF_IN_NEE) != 0;
+    Mei1 m = c.m;
+    const Tri &T = c.T;
+    sample_interaction1_finish(S, m, T, c.b);
     const float mu = m.mu, inv_mu = m.inv_mu;                         // the volume's majorant, or the supergrid cell's at m.p
     if (nee) {
         // estimate_transmittance step (:478-515)
@@ -395,6 +419,51 @@ __device__ __forceinline__ void vp_collide(const SceneK &S, const GRID &G, float
     ln.ro = ln.ro + ln.d * m.t;                                       // :378-380
     ln.rmaxt = ln.rmaxt - m.t;
     ln.running_t = ln.running_t + m.t;
+}
+
+template <bool BW, class GRID>
+__device__ __forceinline__ void vp_collide(const SceneK &S, const GRID &G, float mu_vol, float inv_mu_vol, VpLane &ln, VpSink &sk) {
+    VpColl c;
+    vp_collide_pre<BW>(S, G, mu_vol, inv_mu_vol, ln, sk, c);
+    vp_collide_post<BW>(S, G, ln, sk, c);
+}
+
+// RCV_SPEC_COLLIDE = 2: TWO consecutive tentative collisions of a segment per call, both bricks in flight together.
+// Where the next tentative collision falls does not depend on the lookup that is still in flight — only on the lane's
+// random stream and on the current one being a null collision (delta tracking) or an ordinary ratio-tracking step —
+// so its free flight is sampled and its brick requested speculatively, as if that were the case.  If the first
+// collision turns out real (or the segment ends) the speculation is dropped: the lane's stream was advanced on a copy
+// and nothing else was touched, so results are bit-identical with or without it.  A path then needs about half as
+// many dependent memory round trips, which is what bounds these kernels (profiles/README.md).
+#ifndef RCV_SPEC_COLLIDE
+#define RCV_SPEC_COLLIDE 2
+#endif
+template <bool BW, class GRID>
+__device__ __forceinline__ void vp_collide_spec(const SceneK &S, const GRID &G, float mu_vol, float inv_mu_vol, VpLane &ln, VpSink &sk) {
+    VpColl a;
+    vp_collide_pre<BW>(S, G, mu_vol, inv_mu_vol, ln, sk, a);
+    if (!a.go) return;
+    VpColl b; b.go = false;
+    Pcg rng_b = ln.rng;                                               // the stream after this collision's distance draw
+    VpsCounts spec; spec.coll = spec.scat = spec.g_sig = spec.g_alb = 0;
+    if (a.m.valid) {
+        const bool nee = (ln.flags & VF_IN_NEE) != 0;
+        V3 ro_b;
+        if (nee) { ro_b = a.m.p; }                                    // :510
+        else { (void) pcg_f32(rng_b); ro_b = ln.ro + ln.d * a.m.t; }  // the null / real draw (:372), then :378-380
+        const float rmaxt_b = ln.rmaxt - a.m.t;
+        const float u = pcg_f32(rng_b);
+        sample_interaction1_issue(S, G, mu_vol, inv_mu_vol, ro_b, nee ? ln.nd : ln.d, ln.id, rmaxt_b, u, b.m, b.T, b.b, spec);
+        b.go = true;
+    }
+    vp_collide_post<BW>(S, G, ln, sk, a);
+    if (b.go && ln.ev == EV_COLL) {
+        // the first was a null collision (or a ratio-tracking step that continues): the lane is where the speculation
+        // put it — same origin, same remaining distance — and its stream continues after the second distance draw
+        ln.rng = rng_b;
+        sk.cnt.coll += spec.coll;
+        vp_collide_post<BW>(S, G, ln, sk, b);
+    }
 }
 
 // the batched slow step (see the header comment)

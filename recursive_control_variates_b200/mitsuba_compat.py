@@ -55,6 +55,7 @@ class GridVolume:
     """`gridvolume` from an in-memory tensor (Z, Y, X, C) (experiments.py:104-112), a constant, or a `.vol` file."""
 
     def __init__(self, props: Properties, channels: int):
+        self.box = _axis_aligned_box(props["to_world"], 0.0, 1.0, "gridvolume") if "to_world" in props else None
         if "data" in props:
             self.data = _as_tensor(props["data"], channels)
         elif "value" in props:
@@ -76,6 +77,7 @@ class HeterogeneousMedium:
     def __init__(self, props: Properties):
         self.sigma_t = GridVolume(Properties(props["sigma_t"]), 1)
         self.albedo = GridVolume(Properties(props["albedo"]), 3)
+        self._check_resolution()
         self.scale = float(props.get("scale", 1.0))
         self.sample_emitters = bool(props.get("sample_emitters", True))
         phase = props.get("phase", {"type": "isotropic"})
@@ -91,6 +93,9 @@ class HeterogeneousMedium:
     def is_twostate(self) -> bool:
         return False
 
+    def volume_boxes(self):
+        return [self.sigma_t.box, self.albedo.box]
+
     def majorant_resolution_factor(self) -> int:
         return self._majorant_factor
 
@@ -102,6 +107,13 @@ class HeterogeneousMedium:
 
     def parameters(self) -> Dict[str, torch.Tensor]:
         return {"sigma_t.data": self.sigma_t.data, "albedo.data": self.albedo.data}
+
+    def _check_resolution(self):
+        # the packed two-state grid keeps sigma_t and albedo voxel for voxel; the reference lets them differ
+        # (janga: 264x136x136 sigma_t, 256x128x128 albedo, experiments.py:53-63) — refuse that here, not in the kernels
+        if tuple(self.sigma_t.data.shape[:3]) != tuple(self.albedo.data.shape[:3]):
+            raise ValueError(f"sigma_t {tuple(self.sigma_t.data.shape[:3])} and albedo {tuple(self.albedo.data.shape[:3])} "
+                             "grids must share one resolution (resample one of them before loading)")
 
     def set_parameter(self, key: str, value: torch.Tensor):
         vol = self.sigma_t if key.startswith("sigma_t") else self.albedo
@@ -170,15 +182,38 @@ class Sensor:
         return self._film
 
 
+def _axis_aligned_box(to_world, lo, hi, what):
+    """Image of the box [lo, hi]^3 under an axis-aligned `to_world` (scale + translation); anything else is refused."""
+    m = np.asarray(to_world, dtype=np.float64)
+    if m.shape != (4, 4) or np.abs(m[:3, :3] - np.diag(np.diag(m[:3, :3]))).max() > 1e-12 or np.any(np.diag(m[:3, :3]) == 0):
+        raise ValueError(f"{what}: only axis-aligned `to_world` transforms (scale + translation) are supported")
+    a, b = m[:3, :3] @ np.full(3, lo) + m[:3, 3], m[:3, :3] @ np.full(3, hi) + m[:3, 3]
+    return tuple(float(v) for v in np.minimum(a, b)), tuple(float(v) for v in np.maximum(a, b))
+
+
 class Shape:
+    """The medium container.  Mitsuba's `cube` spans [-1,1]^3 and the reference's `cube_unit.obj` [0,1]^3 before
+    `to_world` (experiments.py:73-80); without a `to_world` this shim keeps the unit cube [0,1]^3 of the synthetic
+    scenes for every type (or the explicit `bbox_min` / `bbox_max` keys, which are not Mitsuba's)."""
+
     def __init__(self, d: dict):
         if d.get("type") not in ("cube", "obj", "box"):
             raise ValueError("the medium container must be a box (`cube`)")
         if d.get("bsdf", {"type": "null"}).get("type") != "null":
             raise ValueError("the medium boundary must use a `null` BSDF (volpathsimple.py:24-30)")
-        self.bbox_min = tuple(float(v) for v in d.get("bbox_min", (0.0, 0.0, 0.0)))
-        self.bbox_max = tuple(float(v) for v in d.get("bbox_max", (1.0, 1.0, 1.0)))
+        if "to_world" in d:
+            if "bbox_min" in d or "bbox_max" in d:
+                raise ValueError("give the container either `to_world` or `bbox_min`/`bbox_max`, not both")
+            lo, hi = (-1.0, 1.0) if d.get("type") == "cube" else (0.0, 1.0)
+            self.bbox_min, self.bbox_max = _axis_aligned_box(d["to_world"], lo, hi, "medium container")
+        else:
+            self.bbox_min = tuple(float(v) for v in d.get("bbox_min", (0.0, 0.0, 0.0)))
+            self.bbox_max = tuple(float(v) for v in d.get("bbox_max", (1.0, 1.0, 1.0)))
         self._interior = _make_medium(d["interior"]) if "interior" in d else None
+        if self._interior is not None:                 # the grids must fill the container (use_grid_bbox = False)
+            for vol_box in self._interior.volume_boxes():
+                if vol_box is not None and not np.allclose(vol_box, (self.bbox_min, self.bbox_max), atol=1e-6):
+                    raise ValueError("a gridvolume's `to_world` must map [0,1]^3 onto the medium container")
 
     def interior_medium(self):
         return self._interior
@@ -337,7 +372,8 @@ class _RenderOp(torch.autograd.Function):
     def forward(ctx, scene, integrator, params, keys, sensor, seed, spp, seed_grad, spp_grad, *tensors):
         ctx.args = (scene, integrator, params, keys, sensor, seed_grad, spp_grad)
         with torch.no_grad():
-            return integrator.render(scene, sensor, seed, spp)
+            # a fresh tensor per call, like the reference: the CV integrators update their `img` buffer in place
+            return integrator.render(scene, sensor, seed, spp).clone()
 
     @staticmethod
     def backward(ctx, grad_out):
@@ -365,7 +401,7 @@ def render(scene: Scene, params: Optional[SceneParameters] = None, sensor: int =
                 keys.append(k); tensors.append(v)
     if not tensors:
         with torch.no_grad():
-            return integrator.render(scene, sensor, seed, spp)
+            return integrator.render(scene, sensor, seed, spp).clone()
     return _RenderOp.apply(scene, integrator, params, keys, sensor, seed, spp, seed_grad, spp_grad, *tensors)
 
 
@@ -413,8 +449,9 @@ class Adam:
         if isinstance(lr, dict):
             self.lr.update({k: float(v) for k, v in lr.items()})
         else:
+            # mi.ad.Optimizer.set_learning_rate(float) replaces the default only: per-key rates set through the
+            # dict form (e.g. experiments.py:111-116 albedo at lr_factor 2) survive optimize.py's schedule steps
             self.lr_default = float(lr)
-            self.lr = {}          # mi.ad.Adam.set_learning_rate(float) sets the default for all keys
 
     def learning_rate(self, key) -> float:
         return self.lr.get(key, self.lr_default)

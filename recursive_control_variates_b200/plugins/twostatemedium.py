@@ -20,6 +20,9 @@ class TwoStateMedium:
     def incoming_medium(self):
         return self.incoming
 
+    def volume_boxes(self):
+        return self.old.volume_boxes() + self.new.volume_boxes() + self.incoming.volume_boxes()
+
     # everything except the two-state sampling delegates to `new` (twostatemedium.py:117-184)
     def phase_function(self):
         return self.new.phase

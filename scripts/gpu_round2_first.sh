@@ -27,3 +27,6 @@ try:
     d=json.load(open('$f')); print('$f', d['ms_per_step'], d['value'], d['phases_ms_rank0'])
 except Exception as e: print('$f', 'failed', e)
 "; done
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_twostates_pool -s 1 -c 1 -o gpurun_out/${TAG}_ts \
+  python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-drt --supergrid > gpurun_out/${TAG}_ncu_ts_stdout.log 2>&1
+ls -la gpurun_out/*.ncu-rep

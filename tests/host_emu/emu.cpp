@@ -13,6 +13,13 @@
 
 using namespace rcv;
 
+// the collision handler the pool kernels run (rcv_trace.cu): the speculative two-step form when RCV_SPEC_COLLIDE > 1
+#if RCV_SPEC_COLLIDE > 1
+#define EMU_VP_COLLIDE vp_collide_spec
+#else
+#define EMU_VP_COLLIDE vp_collide
+#endif
+
 namespace {
 
 struct Packed {
@@ -158,7 +165,7 @@ void run_vps(const SceneK &S, const GRID &G, VpSink &sk) {
         vp_load(ln, sk, hq.Q, pos, 0u);
         while (ln.ev != EV_INIT) {
             if (ln.ev == EV_COLL) {
-                vp_collide<BW>(S, G, mu, inv_mu, ln, sk);
+                EMU_VP_COLLIDE<BW>(S, G, mu, inv_mu, ln, sk);
             } else if (ln.ev == EV_SCAT) {
                 vp_vertex<BW>(S, G, ln, sk);
             } else {
@@ -197,7 +204,7 @@ void run_vps_drt(const SceneK &S, const GRID &G, VpSink &sk) {
         VpLane ln; ln.flags = 0;
         vp_load<1>(ln, sk, hq.Q, pos, 0u);
         while (ln.ev != EV_INIT) {
-            if (ln.ev == EV_COLL) vp_collide<true>(S, G, mu, inv_mu, ln, sk);
+            if (ln.ev == EV_COLL) EMU_VP_COLLIDE<true>(S, G, mu, inv_mu, ln, sk);
             else if (ln.ev == EV_SCAT) vp_vertex<true, 1>(S, G, ln, sk);
             else vp_slow<true, 1>(S, G, ln, sk);
         }
@@ -225,7 +232,7 @@ void run_vps_drt(const SceneK &S, const GRID &G, VpSink &sk) {
         VpLane ln; ln.flags = 0;
         vp_load<2>(ln, sk, hq.Q, pos, 0u);
         while (ln.ev != EV_INIT) {
-            if (ln.ev == EV_COLL) vp_collide<false>(S, G, mu, inv_mu, ln, sk);
+            if (ln.ev == EV_COLL) EMU_VP_COLLIDE<false>(S, G, mu, inv_mu, ln, sk);
             else if (ln.ev == EV_SCAT) vp_vertex<false, 2>(S, G, ln, sk);
             else vp_slow<false, 2>(S, G, ln, sk);
         }

@@ -281,7 +281,8 @@ def test_drt_stages_of_the_event_machines(oracle, emu, use_mis, factor, depths):
 
 @pytest.fixture(scope="module")
 def emu_vertex_albedo():
-    """The same machines built with RCV_VERTEX_ALBEDO=1 (pass 2 reads the albedo from the vertex record)."""
+    """The same machines built with RCV_VERTEX_ALBEDO=0 (pass 2 gathers the albedo again; the default build reads it
+    from the vertex record)."""
     return _load_emu("librcv_emu_vertex_albedo.so")
 
 
@@ -310,6 +311,55 @@ def test_vertex_record_albedo_is_the_same_adjoint(oracle, emu, emu_vertex_albedo
         for a, b in zip(*res):
             assert np.array_equal(a, b)
         assert res[0][0].any() and res[0][3].any()
+
+
+@pytest.fixture(scope="module")
+def emu_spec():
+    """The same machines with the other setting of RCV_SPEC_COLLIDE than the default build's."""
+    return _load_emu("librcv_emu_spec.so")
+
+
+@pytest.mark.parametrize("factor", [0, 4])
+def test_speculative_collisions_change_nothing(oracle, emu, emu_spec, factor):
+    """RCV_SPEC_COLLIDE: the second tentative collision of a call is sampled on a copy of the lane's stream as if the
+    first were a null collision, and dropped otherwise.  Film accumulators, gradients and every counter are
+    bit-identical with and without it — main path and shadow rays, Russian roulette active (rr_depth 2: no
+    speculation on the two-state main path then), with and without the majorant supergrid."""
+    from recursive_control_variates_b200.scene import SceneConfig
+    from recursive_control_variates_b200.synthetic import make_medium
+    d = SceneConfig(width=24, height=20, max_depth=16, rr_depth=2, sigma_t_scale=30.0).to_desc()
+    so, ao = make_medium(12, "cube", 0.0)
+    sn, an = make_medium(12, "cube", 8e-3)
+    H, W = d.film_height, d.film_width
+    grad_img = (np.random.default_rng(3).standard_normal((H, W, 3)) / (H * W * 3)).astype(np.float32)
+    film_w = oracle.film_weights(d, 77, 3)
+    res = []
+    for lib in (emu, emu_spec):
+        out = []
+        for mode in (0, 2):
+            a_old = np.zeros((H, W, 4), np.float32); a_new = np.zeros_like(a_old); cnt = np.zeros(8, np.uint64)
+            if factor:
+                lib.emu_twostates_sg(C.addressof(d), so, ao, sn, an, *sn.shape[:3], 5, 3, mode, factor, a_old, a_new, cnt)
+            else:
+                lib.emu_twostates(C.addressof(d), so, ao, sn, an, *sn.shape[:3], 5, 3, mode, a_old, a_new, cnt)
+            out += [a_old, a_new, cnt]
+        acc = np.zeros((H, W, 4), np.float32)
+        g1 = np.zeros((*sn.shape[:3], 1), np.float32); g4 = np.zeros((*sn.shape[:3], 4), np.float32); cnt = np.zeros(8, np.uint64)
+        args = (C.addressof(d), sn, an, *sn.shape[:3], 77, 3, 1, oracle.alt_seed(77), grad_img.ctypes.data, film_w.ctypes.data,
+                acc, g1, g4, cnt)
+        if factor:
+            lib.emu_vps_sg(*args, factor)
+        else:
+            lib.emu_vps(*args)
+        out += [g1, g4, cnt]
+        d1 = np.zeros_like(g1); d4 = np.zeros_like(g4); dcnt = np.zeros(8, np.uint64)
+        lib.emu_vps_drt_stages(C.addressof(d), sn, an, *sn.shape[:3], 77, 3, oracle.alt_seed(77), grad_img.ctypes.data,
+                               film_w.ctypes.data, d1, d4, dcnt, factor, 1)
+        out += [d1, d4, dcnt]
+        res.append(out)
+    for a, b in zip(*res):
+        assert np.array_equal(a, b)
+    assert res[0][0].any() and res[0][6].any() and res[0][9].any()
 
 
 def test_gradient_bricks_and_voxel_reductions_agree(oracle, emu, emu_voxelreds, setup):

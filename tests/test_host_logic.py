@@ -97,6 +97,30 @@ def test_error_behaviour_matches_reference():
         integ.check_scene(_scene("baseline")["scene"])
 
 
+def test_container_to_world_and_grid_resolution():
+    """experiments.py:53-80 of the reference: T.scale([1,1.2,1.5]) on the container and on both volumes."""
+    import torch
+    T = np.diag([1.0, 1.2, 1.5, 1.0])
+    vol = lambda c, n=4, **kw: {"type": "gridvolume", "data": torch.zeros(n, n, n, c), **kw}
+    med = lambda **kw: {"type": "heterogeneous", "sigma_t": vol(1, **kw), "albedo": vol(3, **kw)}
+    cam = {"type": "perspective", "film": {"width": 8, "height": 8}}
+    sc = lambda obj: mi.load_dict({"type": "scene", "object": obj, "e": {"type": "constant"}, "sensor": cam})
+    s = sc({"type": "obj", "bsdf": {"type": "null"}, "to_world": T, "interior": med(to_world=T)})
+    assert s.shapes()[0].bbox_min == (0.0, 0.0, 0.0) and s.shapes()[0].bbox_max == (1.0, 1.2, 1.5)
+    # Mitsuba's `cube` is [-1,1]^3 before to_world
+    T2 = np.array([[0.5, 0, 0, 0.5], [0, 0.5, 0, 0.5], [0, 0, 0.5, 0.5], [0, 0, 0, 1.0]])
+    s = sc({"type": "cube", "bsdf": {"type": "null"}, "to_world": T2, "interior": med()})
+    assert s.shapes()[0].bbox_min == (0.0, 0.0, 0.0) and s.shapes()[0].bbox_max == (1.0, 1.0, 1.0)
+    with pytest.raises(ValueError):          # a volume that does not fill the container
+        sc({"type": "obj", "bsdf": {"type": "null"}, "to_world": T, "interior": med(to_world=np.eye(4))})
+    R = np.eye(4); R[:2, :2] = [[0, -1], [1, 0]]
+    with pytest.raises(ValueError):          # rotations are not supported: say so instead of rendering the wrong box
+        sc({"type": "obj", "bsdf": {"type": "null"}, "to_world": R, "interior": med()})
+    with pytest.raises(ValueError):          # janga's 264x136x136 sigma_t with a 256x128x128 albedo
+        sc({"type": "obj", "bsdf": {"type": "null"},
+            "interior": {"type": "heterogeneous", "sigma_t": vol(1, 6), "albedo": vol(3, 4)}})
+
+
 def test_scene_parameters_and_rotation_bookkeeping():
     import torch
     scene = _scene("cv_ps")["scene"]
@@ -126,8 +150,9 @@ def test_adam_bookkeeping():
     opt.t["a"] = 5
     opt["a"] = torch.zeros(4, 4, 4, 1)               # shape change (upsample) resets the state
     assert opt.t["a"] == 0 and opt.state["a"][0].shape == (4, 4, 4, 1)
-    opt.set_learning_rate(0.005)
-    assert opt.learning_rate("a") == 0.005
+    opt["b"] = torch.zeros(2)
+    opt.set_learning_rate(0.005)                     # float form: the default only, per-key rates are kept
+    assert opt.learning_rate("a") == 0.02 and opt.learning_rate("b") == 0.005
 
 
 def test_vol_files_round_trip(tmp_path):
