@@ -55,6 +55,9 @@ def lib() -> C.CDLL:
         L.orc_majorant.argtypes = [SP, _f32p, C.c_size_t]; L.orc_majorant.restype = f
         L.orc_majorant_grid.argtypes = [SP, _f32p, i32, i32, i32, i32, _f32p]; L.orc_majorant_grid.restype = i32
         L.orc_alt_seed.argtypes = [u32]; L.orc_alt_seed.restype = u32
+        L.orc_atan2f.argtypes = [f, f]; L.orc_atan2f.restype = f
+        L.orc_env_eval.argtypes = [SP, _f32p, _f32p, C.POINTER(f)]
+        L.orc_env_sample.argtypes = [SP, f, f, _f32p, C.POINTER(f), _f32p]
         L.orc_dda_sample.argtypes = [SP, C.c_void_p, MP, _f32p, _f32p, f, f, f]; L.orc_dda_sample.restype = f
         L.orc_counters.argtypes = [_u64p, i32]
         L.orc_twostates_lanes.argtypes = [SP, MP, MP, u32, u32, u64, u64, _f32p, _f32p, _i32p, i32]
@@ -109,6 +112,24 @@ def dda_sample(desc, m_old, m_new, o, d, mint, maxt, tau) -> float:
     """Free-flight distance through the majorant supergrid(s) (test hook); m_old may be None."""
     return float(lib().orc_dda_sample(C.addressof(desc), C.addressof(m_old.c) if m_old is not None else None, C.byref(m_new.c),
                                       np.asarray(o, np.float32), np.asarray(d, np.float32), mint, maxt, tau))
+
+
+def atan2f(y: float, x: float) -> float:
+    return float(lib().orc_atan2f(y, x))
+
+
+def env_eval(desc, d):
+    """(radiance rgb, solid-angle pdf) of the scene's environment emitter for a world direction d."""
+    rgb = np.zeros(3, np.float32); pdf = C.c_float()
+    lib().orc_env_eval(C.addressof(desc), np.ascontiguousarray(d, np.float32), rgb, C.byref(pdf))
+    return rgb, float(pdf.value)
+
+
+def env_sample(desc, u1: float, u2: float):
+    """(direction, pdf, radiance / pdf) of an environment sample."""
+    d = np.zeros(3, np.float32); val = np.zeros(3, np.float32); pdf = C.c_float()
+    lib().orc_env_sample(C.addressof(desc), float(u1), float(u2), d, C.byref(pdf), val)
+    return d, float(pdf.value), val
 
 
 def alt_seed(seed_grad: int) -> int:

@@ -218,6 +218,195 @@ static inline float mis_weight(float pdf_a, float pdf_b) {
     return isfinite(w) ? w : 0.f;
 }
 
+/* Cephes atanf / atan2f, fixed operation order (envmap direction -> (u, v)) */
+#define ORC_PI 3.14159265358979323846f
+#define ORC_PIO2 1.57079632679489661923f
+#define ORC_PIO4 0.78539816339744830962f
+static inline float spec_atanf(float xx) {
+    float x = fabsf(xx), y;
+    if (x > 2.414213562373095f) { y = ORC_PIO2; x = -(1.f / x); }
+    else if (x > 0.4142135623730950f) { y = ORC_PIO4; x = (x - 1.f) / (x + 1.f); }
+    else y = 0.f;
+    float z = x * x;
+    float p = 8.05374449538e-2f;
+    p = fmaf(p, z, -1.38776856032e-1f);
+    p = fmaf(p, z, 1.99777106478e-1f);
+    p = fmaf(p, z, -3.33329491539e-1f);
+    y = y + fmaf(p * z, x, x);
+    return (xx < 0.f) ? -y : y;
+}
+float orc_atan2f(float y, float x) {
+    if (x == 0.f) return (y > 0.f) ? ORC_PIO2 : ((y < 0.f) ? -ORC_PIO2 : 0.f);
+    float z = spec_atanf(y / x);
+    if (x < 0.f) z = (y < 0.f) ? z - ORC_PI : z + ORC_PI;
+    return z;
+}
+
+/* ------------------------------------------------------------------------- */
+/* `envmap` emitter [UPSTREAM envmap.cpp, restated; DESIGN.md §2]: lat-long   */
+/* texels at the nodes of a (H-1) x W cell grid (longitude wraps), bilinear    */
+/* radiance, piecewise-constant sampling density proportional to the cell      */
+/* mean of luminance * sin(theta).  Tables are built in float64, sequentially, */
+/* and rounded once (the library builds the same tables independently).        */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+    const float *key; int w, h; float scale;
+    float *data;      /* (h, w + 1, 3) scaled texels, column w = column 0 */
+    float *cdf_m;     /* h: cdf over the h - 1 cell rows */
+    float *cdf_c;     /* (h - 1, w + 1) */
+    float *pdf;       /* (h - 1, w): density over [0,1]^2 of (u, v) */
+} env_tables;
+static env_tables g_env = {0};
+
+static void env_build(const rcv_scene_desc *S) {
+    if (S->emitter_type != RCV_EMITTER_ENVMAP) return;
+    if (g_env.key == S->envmap_rgb && g_env.w == S->env_width && g_env.h == S->env_height && g_env.scale == S->env_scale) return;
+    free(g_env.data); free(g_env.cdf_m); free(g_env.cdf_c); free(g_env.pdf);
+    int w = S->env_width, h = S->env_height;
+    g_env.key = S->envmap_rgb; g_env.w = w; g_env.h = h; g_env.scale = S->env_scale;
+    g_env.data = (float *) malloc(sizeof(float) * 3 * (size_t) h * (w + 1));
+    g_env.cdf_m = (float *) malloc(sizeof(float) * h);
+    g_env.cdf_c = (float *) malloc(sizeof(float) * (size_t) (h - 1) * (w + 1));
+    g_env.pdf = (float *) malloc(sizeof(float) * (size_t) (h - 1) * w);
+    double *g = (double *) malloc(sizeof(double) * (size_t) h * (w + 1));
+    double *rowsum = (double *) malloc(sizeof(double) * (h - 1));
+    for (int r = 0; r < h; ++r) {
+        double st = sin(3.14159265358979323846 * (double) r / (double) (h - 1));
+        for (int c = 0; c <= w; ++c) {
+            const float *src = S->envmap_rgb + 3 * ((size_t) r * w + (c % w));
+            float *dst = g_env.data + 3 * ((size_t) r * (w + 1) + c);
+            for (int k = 0; k < 3; ++k) dst[k] = src[k] * S->env_scale;
+            g[(size_t) r * (w + 1) + c] = (0.2126 * (double) dst[0] + 0.7152 * (double) dst[1] + 0.0722 * (double) dst[2]) * st;
+        }
+    }
+    double total = 0.0;
+    for (int r = 0; r < h - 1; ++r) {
+        double s = 0.0;
+        for (int c = 0; c < w; ++c) {
+            size_t i = (size_t) r * (w + 1) + c;
+            s += 0.25 * (g[i] + g[i + 1] + g[i + w + 1] + g[i + w + 2]);
+        }
+        rowsum[r] = s; total += s;
+    }
+    double acc = 0.0;
+    g_env.cdf_m[0] = 0.f;
+    for (int r = 0; r < h - 1; ++r) {
+        acc += rowsum[r];
+        g_env.cdf_m[r + 1] = (total > 0.0) ? (float) (acc / total) : (float) (r + 1) / (float) (h - 1);
+        float *row = g_env.cdf_c + (size_t) r * (w + 1);
+        double a2 = 0.0;
+        row[0] = 0.f;
+        for (int c = 0; c < w; ++c) {
+            size_t i = (size_t) r * (w + 1) + c;
+            double f = 0.25 * (g[i] + g[i + 1] + g[i + w + 1] + g[i + w + 2]);
+            a2 += f;
+            row[c + 1] = (rowsum[r] > 0.0) ? (float) (a2 / rowsum[r]) : (float) (c + 1) / (float) w;
+            g_env.pdf[(size_t) r * w + c] = (total > 0.0) ? (float) (f / total * (double) w * (double) (h - 1)) : 1.f;
+        }
+        row[w] = 1.f;
+    }
+    g_env.cdf_m[h - 1] = 1.f;
+    free(g); free(rowsum);
+}
+
+/* world direction -> cell (r, c), in-cell position (fu, fv) and sin(theta) */
+static inline void env_locate(const rcv_scene_desc *S, v3 d, int *r, int *c, float *fu, float *fv, float *st_out) {
+    const float *R = S->env_to_world;
+    float lx = fmaf(R[0], d.x, fmaf(R[3], d.y, R[6] * d.z));       /* R^T d */
+    float ly = fmaf(R[1], d.x, fmaf(R[4], d.y, R[7] * d.z));
+    float lz = fmaf(R[2], d.x, fmaf(R[5], d.y, R[8] * d.z));
+    float st = sqrtf(fmaf(lx, lx, lz * lz));
+    float u = orc_atan2f(lx, -lz) * (0.5f / ORC_PI);
+    u = u - floorf(u);
+    if (!(u < 1.f)) u = 0.f;
+    float v = orc_atan2f(st, ly) * (1.f / ORC_PI);
+    float x = u * (float) g_env.w, y = v * (float) (g_env.h - 1);
+    int ci = (int) floorf(x), ri = (int) floorf(y);
+    ci = ci < g_env.w - 1 ? ci : g_env.w - 1; ri = ri < g_env.h - 2 ? ri : g_env.h - 2;
+    ci = ci > 0 ? ci : 0; ri = ri > 0 ? ri : 0;
+    *c = ci; *r = ri; *fu = x - (float) ci; *fv = y - (float) ri; *st_out = st;
+}
+static inline v3 env_eval(const rcv_scene_desc *S, v3 d) {
+    int r, c; float fu, fv, st;
+    env_locate(S, d, &r, &c, &fu, &fv, &st);
+    const float *t00 = g_env.data + 3 * ((size_t) r * (g_env.w + 1) + c), *t01 = t00 + 3;
+    const float *t10 = t00 + 3 * (g_env.w + 1), *t11 = t10 + 3;
+    float gu = 1.f - fu, gv = 1.f - fv, o[3];
+    for (int k = 0; k < 3; ++k) {
+        float a = fmaf(gu, t00[k], fu * t01[k]), b = fmaf(gu, t10[k], fu * t11[k]);
+        o[k] = fmaf(gv, a, fv * b);
+    }
+    return V3(o[0], o[1], o[2]);
+}
+static inline float env_pdf(const rcv_scene_desc *S, v3 d) {
+    int r, c; float fu, fv, st;
+    env_locate(S, d, &r, &c, &fu, &fv, &st);
+    return g_env.pdf[(size_t) r * g_env.w + c] / ((2.f * ORC_PI * ORC_PI) * fmaxf_(st, 1e-6f));
+}
+/* largest i in [0, n - 2] with cdf[i] <= u */
+static inline int cdf_find(const float *cdf, int n, float u) {
+    int lo = 0, hi = n - 1;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (cdf[mid] <= u) lo = mid; else hi = mid; }
+    return lo;
+}
+static inline v3 env_sample(const rcv_scene_desc *S, float u1, float u2) {
+    int r = cdf_find(g_env.cdf_m, g_env.h, u2);
+    float den = g_env.cdf_m[r + 1] - g_env.cdf_m[r];
+    float dv = (den > 0.f) ? (u2 - g_env.cdf_m[r]) / den : 0.5f;
+    const float *row = g_env.cdf_c + (size_t) r * (g_env.w + 1);
+    int c = cdf_find(row, g_env.w + 1, u1);
+    den = row[c + 1] - row[c];
+    float du = (den > 0.f) ? (u1 - row[c]) / den : 0.5f;
+    float u = ((float) c + du) / (float) g_env.w, v = ((float) r + dv) / (float) (g_env.h - 1);
+    float sp, cp, st, ct;
+    orc_sincosf(u * ORC_TWO_PI, &sp, &cp);
+    orc_sincosf(v * ORC_PI, &st, &ct);
+    float lx = sp * st, ly = ct, lz = -(cp * st);
+    const float *R = S->env_to_world;
+    return V3(fmaf(R[0], lx, fmaf(R[1], ly, R[2] * lz)), fmaf(R[3], lx, fmaf(R[4], ly, R[5] * lz)),
+              fmaf(R[6], lx, fmaf(R[7], ly, R[8] * lz)));
+}
+
+/* The scene's environment emitter (`constant` [UPSTREAM constant.cpp] or `envmap`): radiance arriving along a ray of
+ * direction d that leaves the scene, the solid-angle density of sampling d, and the direction sample.  For the envmap
+ * the sample's density and value are evaluated FROM the sampled direction (env_pdf / env_eval), so emitter hits and
+ * emitter samples use the same two functions. */
+static inline v3 emitter_eval(const rcv_scene_desc *S, v3 d) {
+    if (S->emitter_type == RCV_EMITTER_ENVMAP) return env_eval(S, d);
+    if (S->emitter_type == RCV_EMITTER_AREA) return V3(0, 0, 0);
+    return V3(S->env_radiance[0], S->env_radiance[1], S->env_radiance[2]);
+}
+static inline float emitter_pdf(const rcv_scene_desc *S, v3 d) {
+    if (S->emitter_type == RCV_EMITTER_ENVMAP) return env_pdf(S, d);
+    if (S->emitter_type == RCV_EMITTER_AREA) return 0.f;
+    return ORC_INV_FOURPI;
+}
+/* d, pdf and radiance / pdf of an environment sample */
+static inline void emitter_sample_env(const rcv_scene_desc *S, float s2x, float s2y, v3 *d, float *pdf, v3 *val) {
+    if (S->emitter_type == RCV_EMITTER_ENVMAP) {
+        *d = env_sample(S, s2x, s2y);
+        *pdf = env_pdf(S, *d);
+        v3 e = env_eval(S, *d);
+        *val = (*pdf != 0.f) ? V3(e.x / *pdf, e.y / *pdf, e.z / *pdf) : V3(0, 0, 0);
+        return;
+    }
+    *d = square_to_uniform_sphere(s2x, s2y);
+    *pdf = ORC_INV_FOURPI;
+    *val = V3(S->env_radiance[0] / *pdf, S->env_radiance[1] / *pdf, S->env_radiance[2] / *pdf);
+}
+/* test hooks */
+void orc_env_eval(const rcv_scene_desc *S, const float d[3], float rgb[3], float *pdf) {
+    env_build(S);
+    v3 e = emitter_eval(S, V3(d[0], d[1], d[2]));
+    rgb[0] = e.x; rgb[1] = e.y; rgb[2] = e.z; *pdf = emitter_pdf(S, V3(d[0], d[1], d[2]));
+}
+void orc_env_sample(const rcv_scene_desc *S, float u1, float u2, float d[3], float *pdf, float val[3]) {
+    env_build(S);
+    v3 dd, vv;
+    emitter_sample_env(S, u1, u2, &dd, pdf, &vv);
+    d[0] = dd.x; d[1] = dd.y; d[2] = dd.z; val[0] = vv.x; val[1] = vv.y; val[2] = vv.z;
+}
+
 /* ------------------------------------------------------------------------- */
 /* scene geometry: one axis-aligned box with a null BSDF                     */
 /* ------------------------------------------------------------------------- */
@@ -689,10 +878,8 @@ static void sample_emitter_twostates(const rcv_scene_desc *S, const orc_medium *
     float s2x = next_1d(rng, active), s2y = next_1d(rng, active);              /* :393 next_2d(active) */
     v3 d = V3(0, 0, 0); float pdf = 0.f, dist = 0.f; v3 emitter_val = V3(0, 0, 0);
     if (active) {
-        d = square_to_uniform_sphere(s2x, s2y);
-        pdf = ORC_INV_FOURPI;
+        emitter_sample_env(S, s2x, s2y, &d, &pdf, &emitter_val);               /* `constant` or `envmap` */
         dist = S->env_dist;
-        emitter_val = V3(S->env_radiance[0] / pdf, S->env_radiance[1] / pdf, S->env_radiance[2] / pdf);
     }
     int invalid = (pdf == 0.f);                                                /* :395 */
     if (invalid) emitter_val = V3(0, 0, 0);
@@ -857,9 +1044,9 @@ static void sample_twostates(const rcv_scene_desc *S, const orc_medium *Mo, cons
         int has_emitter = !si.valid;
         int active_e = active_surface && has_emitter && !((depth == 0) && S->hide_emitters);
         if (active_e) {
-            float emitter_pdf = S->use_nee ? ORC_INV_FOURPI : 0.f;             /* :297 pdf_emitter_direction */
-            v3 emitted = V3(S->env_radiance[0], S->env_radiance[1], S->env_radiance[2]);   /* :300 */
-            float mis_bsdf = mis_weight(last_scatter_direction_pdf, emitter_pdf);          /* :302 */
+            float emitter_pdf_ = S->use_nee ? emitter_pdf(S, ray.d) : 0.f;      /* :297 pdf_emitter_direction */
+            v3 emitted = emitter_eval(S, ray.d);                               /* :300 */
+            float mis_bsdf = mis_weight(last_scatter_direction_pdf, emitter_pdf_);         /* :302 */
             if (count_direct) {                                                /* :304-308 */
                 L_new = vadd(L_new, vmul(thr_new, emitted));
                 L_old = vadd(L_old, vmul(thr_old, emitted));
@@ -925,6 +1112,7 @@ static void sample_twostates(const rcv_scene_desc *S, const orc_medium *Mo, cons
 int orc_twostates_lanes(const rcv_scene_desc *S, const orc_medium *Mo, const orc_medium *Mn,
                         uint32_t seed, uint32_t spp, uint64_t lane_begin, uint64_t lane_end,
                         float *L_old, float *L_new, int32_t *pix, int nthreads) {
+    env_build(S);
     if (nthreads < 1) nthreads = 1;
 #pragma omp parallel num_threads(nthreads)
     {
@@ -949,6 +1137,7 @@ int orc_twostates_lanes(const rcv_scene_desc *S, const orc_medium *Mo, const orc
 int orc_render_twostates(const rcv_scene_desc *S, const orc_medium *Mo, const orc_medium *Mn,
                          uint32_t seed, uint32_t spp, uint32_t spp_begin, uint32_t spp_end,
                          float *accum_old, float *accum_new, int nthreads) {
+    env_build(S);
     uint64_t npix = (uint64_t) S->film_width * S->film_height;
     uint32_t ns = spp_end - spp_begin;
     const uint64_t chunk = 1u << 16;
@@ -1243,11 +1432,7 @@ static v3 vps_sample_emitter(const rcv_scene_desc *S, const orc_medium *M, v3 re
                              const v3 *adjoint, grad_sink *G, v3 *ds_d, float *ds_pdf, counters_t *cnt) {
     float s2x = next_1d(rng, active), s2y = next_1d(rng, active);              /* :431 */
     v3 d = V3(0, 0, 0); float pdf = 0.f; v3 emitter_val = V3(0, 0, 0);
-    if (active) {                                                              /* :432 constant emitter */
-        d = square_to_uniform_sphere(s2x, s2y);
-        pdf = ORC_INV_FOURPI;
-        emitter_val = V3(S->env_radiance[0] / pdf, S->env_radiance[1] / pdf, S->env_radiance[2] / pdf);
-    }
+    if (active) emitter_sample_env(S, s2x, s2y, &d, &pdf, &emitter_val);       /* :432 `constant` or `envmap` */
     int sampling_worked = (pdf != 0.f);                                        /* :434-436 */
     if (!sampling_worked) emitter_val = V3(0, 0, 0);
     active = active && sampling_worked;
@@ -1527,10 +1712,10 @@ static void vps_sample_core(const rcv_scene_desc *S, const orc_medium *M, int pr
         if (active_e) {
             float hit_mis_weight = 1.f;
             if (S->use_nee) {
-                float emitter_pdf = has_scattered ? ORC_INV_FOURPI : 0.f;      /* :286-290 */
-                hit_mis_weight = mis_weight(last_scatter_direction_pdf, emitter_pdf);
+                float emitter_pdf_ = has_scattered ? emitter_pdf(S, ray.d) : 0.f;   /* :286-290 */
+                hit_mis_weight = mis_weight(last_scatter_direction_pdf, emitter_pdf_);
             }
-            v3 contrib = V3(S->env_radiance[0], S->env_radiance[1], S->env_radiance[2]);
+            v3 contrib = emitter_eval(S, ray.d);
             result = vadd(result, vmul(vscale(throughput, hit_mis_weight), contrib));   /* :298 */
         }
     }
@@ -1569,6 +1754,7 @@ uint32_t orc_alt_seed(uint32_t seed_grad) {
 
 int orc_vps_lanes(const rcv_scene_desc *S, const orc_medium *M, uint32_t seed, uint32_t spp,
                   uint64_t lane_begin, uint64_t lane_end, float *L, int32_t *pix, int nthreads) {
+    env_build(S);
     if (nthreads < 1) nthreads = 1;
 #pragma omp parallel num_threads(nthreads)
     {
@@ -1588,6 +1774,7 @@ int orc_vps_lanes(const rcv_scene_desc *S, const orc_medium *M, uint32_t seed, u
 
 int orc_vps_render(const rcv_scene_desc *S, const orc_medium *M, uint32_t seed, uint32_t spp,
                    uint32_t spp_begin, uint32_t spp_end, float *accum, int nthreads) {
+    env_build(S);
     uint64_t npix = (uint64_t) S->film_width * S->film_height;
     uint32_t ns = spp_end - spp_begin;
     float *L = (float *) malloc((size_t) ns * 3 * sizeof(float) * 4096);
@@ -1630,6 +1817,7 @@ int orc_vps_render(const rcv_scene_desc *S, const orc_medium *M, uint32_t seed, 
 static int vps_backward_impl(const rcv_scene_desc *S, const orc_medium *M, uint32_t seed_grad, uint32_t spp_grad,
                              uint32_t spp_begin, uint32_t spp_end, const float *grad_img, const float *film_w,
                              double *grad_sigma_t, double *grad_albedo, int nthreads, const drt_opts *drt) {
+    env_build(S);
     uint64_t npix = (uint64_t) S->film_width * S->film_height;
     uint32_t alt_seed = orc_alt_seed(seed_grad);
     if (nthreads < 1) nthreads = 1;

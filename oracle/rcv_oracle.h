@@ -36,6 +36,10 @@ int orc_majorant_grid(const rcv_scene_desc *S, const float *sigma_t, int nz, int
 float orc_dda_sample(const rcv_scene_desc *S, const orc_medium *Mo, const orc_medium *Mn, const float o[3], const float d[3],
                      float mint, float maxt, float desired_tau);
 uint32_t orc_alt_seed(uint32_t seed_grad);
+float orc_atan2f(float y, float x);
+/* environment emitter test hooks: radiance + solid-angle density for a world direction; direction sample */
+void orc_env_eval(const rcv_scene_desc *S, const float d[3], float rgb[3], float *pdf);
+void orc_env_sample(const rcv_scene_desc *S, float u1, float u2, float d[3], float *pdf, float val[3]);
 void orc_counters(uint64_t out[8], int reset);
 
 int orc_twostates_lanes(const rcv_scene_desc *S, const orc_medium *Mo, const orc_medium *Mn,

@@ -14,13 +14,23 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RCV_B200_LIB") or os.path.join(_HERE, "librcv_b200.so")
 
 RCV_PHASE_ISOTROPIC, RCV_PHASE_HG = 0, 1
-RCV_ADJOINT_VOLPATHSIMPLE = 0
+RCV_ADJOINT_VOLPATHSIMPLE, RCV_ADJOINT_PRBVOLPATH = 0, 1
+RCV_EMITTER_CONSTANT, RCV_EMITTER_ENVMAP, RCV_EMITTER_AREA = 0, 1, 2
 RCV_LOSS_L1, RCV_LOSS_L2 = 0, 1
 RCV_TRACER_WAVEFRONT, RCV_TRACER_SIMPLE, RCV_TRACER_BATCH, RCV_TRACER_POOL = 0, 1, 2, 3
 
 
 RCV_MAX_SENSORS = 16
 RCV_RFILTER_BOX, RCV_RFILTER_GAUSSIAN = 0, 1
+
+
+RCV_MAX_QUADS = 8
+
+
+class Quad(C.Structure):
+    """struct rcv_quad (include/rcv_b200.h)."""
+    _fields_ = [("p0", C.c_float * 3), ("eu", C.c_float * 3), ("ev", C.c_float * 3),
+                ("reflectance", C.c_float * 3), ("radiance", C.c_float * 3)]
 
 
 class SceneDesc(C.Structure):
@@ -51,6 +61,15 @@ class SceneDesc(C.Structure):
         ("batch_axes", (C.c_float * 9) * RCV_MAX_SENSORS),
         ("rfilter_type", C.c_int32),
         ("rfilter_stddev", C.c_float),
+        ("emitter_type", C.c_int32),
+        ("envmap_rgb", C.c_void_p),
+        ("env_width", C.c_int32),
+        ("env_height", C.c_int32),
+        ("env_scale", C.c_float),
+        ("env_to_world", C.c_float * 9),
+        ("n_quads", C.c_uint32),
+        ("area_quad", C.c_int32),
+        ("quads", Quad * RCV_MAX_QUADS),
     ]
 
 
@@ -137,7 +156,7 @@ def load_library() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = C.c_int
         fn.argtypes = argtypes
-    if lib.rcv_abi_version() != 3:
+    if lib.rcv_abi_version() != 4:
         raise RcvError("librcv_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -69,6 +69,9 @@ struct rcv_ctx {
     uint64_t launches = 0;
     float *film_w = nullptr;
     size_t film_w_pix = 0;
+    // `envmap` emitter tables (rcv_scene_set)
+    float4 *env_data = nullptr;
+    float *env_cdf_m = nullptr, *env_cdf_c = nullptr, *env_pdf = nullptr;
     PathQueue queue{nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t queue_cap = 0;
     PathQueue jobs{nullptr, nullptr, nullptr, nullptr, nullptr};     // DRT job records (use_drt on the pool tracer)
@@ -312,6 +315,7 @@ int rcv_ctx_destroy(rcv_ctx *c) {
     cudaFree(c->queue.r0); cudaFree(c->queue.r1); cudaFree(c->queue.r2); cudaFree(c->queue.r3); cudaFree(c->queue.count);
     cudaFree(c->jobs.r0); cudaFree(c->jobs.r1); cudaFree(c->jobs.r2); cudaFree(c->jobs.r3); cudaFree(c->jobs.count);
     cudaFree(c->gbrick); cudaFree(c->arena); cudaFree(c->mgrid);
+    cudaFree(c->env_data); cudaFree(c->env_cdf_m); cudaFree(c->env_cdf_c); cudaFree(c->env_pdf);
     auto &E = c->e2e;
     cudaFree(E.sigma); cudaFree(E.albedo); cudaFree(E.ref); cudaFree(E.acc); cudaFree(E.HF); cudaFree(E.cv);
     cudaFree(E.grad_img); cudaFree(E.loss); cudaFree(E.g_sigma); cudaFree(E.g_albedo);
@@ -350,8 +354,41 @@ int rcv_scene_set(rcv_ctx *c, const rcv_scene_desc *d) {
         return fail(RCV_ERR_ARG, "gaussian reconstruction filter: 0 < stddev <= 0.5");
     if (d->n_sensors > RCV_MAX_SENSORS) return fail(RCV_ERR_ARG, "too many sensors in the batch (RCV_MAX_SENSORS)");
     if (d->n_sensors > 1 && d->film_width % d->n_sensors) return fail(RCV_ERR_ARG, "the film width must be a multiple of the number of batched sensors");
+    if (d->emitter_type != RCV_EMITTER_CONSTANT && d->emitter_type != RCV_EMITTER_ENVMAP && d->emitter_type != RCV_EMITTER_AREA)
+        return fail(RCV_ERR_ARG, "unknown emitter type");
+    if (d->emitter_type == RCV_EMITTER_ENVMAP && (!d->envmap_rgb || d->env_width < 1 || d->env_height < 2))
+        return fail(RCV_ERR_ARG, "envmap: a host pointer to (env_height >= 2, env_width >= 1, 3) texels is required");
+    float4 *e_data = nullptr; float *e_m = nullptr, *e_c = nullptr, *e_p = nullptr;
+    if (d->emitter_type == RCV_EMITTER_ENVMAP) {
+        if (int r = use_device(c)) return r;
+        EnvTables T;
+        env_tables_build(*d, T);
+        struct Fresh {
+            void *p[4] = {nullptr, nullptr, nullptr, nullptr};
+            ~Fresh() { for (void *q : p) cudaFree(q); }
+        } fresh;
+        CK(cudaMalloc(&fresh.p[0], T.data.size() * sizeof(float4)));
+        CK(cudaMalloc(&fresh.p[1], T.cdf_m.size() * sizeof(float)));
+        CK(cudaMalloc(&fresh.p[2], T.cdf_c.size() * sizeof(float)));
+        CK(cudaMalloc(&fresh.p[3], T.pdf.size() * sizeof(float)));
+        CK(cudaMemcpyAsync(fresh.p[0], T.data.data(), T.data.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(fresh.p[1], T.cdf_m.data(), T.cdf_m.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(fresh.p[2], T.cdf_c.data(), T.cdf_c.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(fresh.p[3], T.pdf.data(), T.pdf.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));       // the host tables go out of scope; kernels of the old scene are done
+        e_data = (float4 *) fresh.p[0]; e_m = (float *) fresh.p[1]; e_c = (float *) fresh.p[2]; e_p = (float *) fresh.p[3];
+        for (void *&q : fresh.p) q = nullptr;
+    }
+    if (c->env_data) {
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+        cudaFree(c->env_data); cudaFree(c->env_cdf_m); cudaFree(c->env_cdf_c); cudaFree(c->env_pdf);
+    }
+    c->env_data = e_data; c->env_cdf_m = e_m; c->env_cdf_c = e_c; c->env_pdf = e_p;
     c->desc = *d;
+    c->desc.envmap_rgb = nullptr;                    // the caller's texels are not referenced after this call
     scene_from_desc(*d, c->S);
+    c->S.env_data = c->env_data; c->S.env_cdf_m = c->env_cdf_m; c->S.env_cdf_c = c->env_cdf_c; c->S.env_pdf = c->env_pdf;
     c->has_scene = true;
     return RCV_OK;
 }

@@ -63,6 +63,14 @@ struct SceneK {
     float batch_o[16 * 3], batch_axes[16 * 9];
     int rfilter;              // RCV_RFILTER_*
     float rf_stddev;
+    // emitter: 0 `constant` environment, 1 `envmap`, 2 `area` light on a rectangle (no environment)
+    int emitter;
+    int env_w, env_h;         // envmap texels: nodes of a (env_h - 1) x env_w cell grid, longitude wraps
+    const float4 *env_data;   // (env_h, env_w + 1) scaled texels (rgb, 0), column env_w = column 0
+    const float *env_cdf_m;   // env_h: cdf over the cell rows
+    const float *env_cdf_c;   // (env_h - 1, env_w + 1): cdf over the cells of a row
+    const float *env_pdf;     // (env_h - 1, env_w): density of (u, v) on the unit square
+    float env_R[9];           // emitter frame -> world (row-major)
 };
 
 // Packed medium state in HBM:
@@ -267,6 +275,28 @@ __device__ __forceinline__ void spec_sincos(float x, float &s_out, float &c_out)
     s_out = s; c_out = c;
 }
 
+// Cephes atanf / atan2f, fixed operation order (envmap: direction -> (u, v))
+#define RCV_PI 3.14159265358979323846f
+__device__ __forceinline__ float spec_atan(float xx) {
+    float x = fabsf(xx), y;
+    if (x > 2.414213562373095f) { y = 1.57079632679489661923f; x = -(1.f / x); }
+    else if (x > 0.4142135623730950f) { y = 0.78539816339744830962f; x = (x - 1.f) / (x + 1.f); }
+    else y = 0.f;
+    float z = x * x;
+    float p = 8.05374449538e-2f;
+    p = __fmaf_rn(p, z, -1.38776856032e-1f);
+    p = __fmaf_rn(p, z, 1.99777106478e-1f);
+    p = __fmaf_rn(p, z, -3.33329491539e-1f);
+    y = y + __fmaf_rn(p * z, x, x);
+    return (xx < 0.f) ? -y : y;
+}
+__device__ __forceinline__ float spec_atan2(float y, float x) {
+    if (x == 0.f) return (y > 0.f) ? 1.57079632679489661923f : ((y < 0.f) ? -1.57079632679489661923f : 0.f);
+    float z = spec_atan(y / x);
+    if (x < 0.f) z = (y < 0.f) ? z - RCV_PI : z + RCV_PI;
+    return z;
+}
+
 __device__ __forceinline__ V3 uniform_sphere(float sx, float sy) {
     float z = __fmaf_rn(-2.f, sy, 1.f);
     float r2 = __fmaf_rn(-z, z, 1.f);
@@ -280,6 +310,86 @@ __device__ __forceinline__ float mis_weight(float pdf_a, float pdf_b) {
     float a2 = pdf_a * pdf_a, b2 = pdf_b * pdf_b;
     float w = a2 / (a2 + b2);
     return isfinite(w) ? w : 0.f;
+}
+
+// ----------------------------------------------------------------------------
+// environment emitter: `constant`, or `envmap` (upstream envmap.cpp restated): bilinear radiance over the
+// lat-long nodes, piecewise-constant sampling density per cell (tables built by rcv_scene_set).  A sample's density and
+// value are evaluated FROM the sampled direction, so emitter hits and emitter samples share env_pdf / env_eval.
+// Out of line: called once per path / per scattering vertex, in the vertex and slow steps.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void env_locate(const SceneK &S, V3 d, int &r, int &c, float &fu, float &fv, float &st) {
+    const float *R = S.env_R;
+    float lx = __fmaf_rn(R[0], d.x, __fmaf_rn(R[3], d.y, R[6] * d.z));
+    float ly = __fmaf_rn(R[1], d.x, __fmaf_rn(R[4], d.y, R[7] * d.z));
+    float lz = __fmaf_rn(R[2], d.x, __fmaf_rn(R[5], d.y, R[8] * d.z));
+    st = sqrtf(__fmaf_rn(lx, lx, lz * lz));
+    float u = spec_atan2(lx, -lz) * (0.5f / RCV_PI);
+    u = u - floorf(u);
+    if (!(u < 1.f)) u = 0.f;
+    float v = spec_atan2(st, ly) * (1.f / RCV_PI);
+    float x = u * (float) S.env_w, y = v * (float) (S.env_h - 1);
+    int ci = (int) floorf(x), ri = (int) floorf(y);
+    ci = min(ci, S.env_w - 1); ri = min(ri, S.env_h - 2);
+    ci = max(ci, 0); ri = max(ri, 0);
+    c = ci; r = ri; fu = x - (float) ci; fv = y - (float) ri;
+}
+static __device__ __noinline__ float4 env_eval_pdf(const SceneK &S, float dx, float dy, float dz) {
+    int r, c; float fu, fv, st;
+    env_locate(S, mk3(dx, dy, dz), r, c, fu, fv, st);
+    const float4 *t = S.env_data + (size_t) r * (S.env_w + 1) + c;
+    float4 t00 = __ldg(t), t01 = __ldg(t + 1), t10 = __ldg(t + S.env_w + 1), t11 = __ldg(t + S.env_w + 2);
+    float gu = 1.f - fu, gv = 1.f - fv;
+    float4 o;
+    o.x = __fmaf_rn(gv, __fmaf_rn(gu, t00.x, fu * t01.x), fv * __fmaf_rn(gu, t10.x, fu * t11.x));
+    o.y = __fmaf_rn(gv, __fmaf_rn(gu, t00.y, fu * t01.y), fv * __fmaf_rn(gu, t10.y, fu * t11.y));
+    o.z = __fmaf_rn(gv, __fmaf_rn(gu, t00.z, fu * t01.z), fv * __fmaf_rn(gu, t10.z, fu * t11.z));
+    o.w = __ldg(S.env_pdf + (size_t) r * S.env_w + c) / ((2.f * RCV_PI * RCV_PI) * fmax_(st, 1e-6f));
+    return o;
+}
+__device__ __forceinline__ int cdf_find(const float *cdf, int n, float u) {
+    int lo = 0, hi = n - 1;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (__ldg(cdf + mid) <= u) lo = mid; else hi = mid; }
+    return lo;
+}
+static __device__ __noinline__ float4 env_sample_dir(const SceneK &S, float u1, float u2) {
+    int r = cdf_find(S.env_cdf_m, S.env_h, u2);
+    float c0 = __ldg(S.env_cdf_m + r), den = __ldg(S.env_cdf_m + r + 1) - c0;
+    float dv = (den > 0.f) ? (u2 - c0) / den : 0.5f;
+    const float *row = S.env_cdf_c + (size_t) r * (S.env_w + 1);
+    int c = cdf_find(row, S.env_w + 1, u1);
+    c0 = __ldg(row + c); den = __ldg(row + c + 1) - c0;
+    float du = (den > 0.f) ? (u1 - c0) / den : 0.5f;
+    float u = ((float) c + du) / (float) S.env_w, v = ((float) r + dv) / (float) (S.env_h - 1);
+    float sp, cp, st, ct;
+    spec_sincos(u * RCV_TWO_PI, sp, cp);
+    spec_sincos(v * RCV_PI, st, ct);
+    float lx = sp * st, ly = ct, lz = -(cp * st);
+    const float *R = S.env_R;
+    return make_float4(__fmaf_rn(R[0], lx, __fmaf_rn(R[1], ly, R[2] * lz)), __fmaf_rn(R[3], lx, __fmaf_rn(R[4], ly, R[5] * lz)),
+                       __fmaf_rn(R[6], lx, __fmaf_rn(R[7], ly, R[8] * lz)), 0.f);
+}
+// radiance arriving along a ray of direction d that leaves the scene, and the solid-angle density of sampling d
+__device__ __forceinline__ V3 emitter_eval(const SceneK &S, V3 d, float &pdf) {
+    if (S.emitter == 1) { float4 e = env_eval_pdf(S, d.x, d.y, d.z); pdf = e.w; return mk3(e.x, e.y, e.z); }
+    if (S.emitter == 2) { pdf = 0.f; return mk3(0, 0, 0); }
+    pdf = RCV_INV_FOURPI;
+    return mk3(S.env[0], S.env[1], S.env[2]);
+}
+// direction of an environment sample
+__device__ __forceinline__ V3 emitter_sample_dir(const SceneK &S, float s2x, float s2y) {
+    if (S.emitter == 1) { float4 d = env_sample_dir(S, s2x, s2y); return mk3(d.x, d.y, d.z); }
+    return uniform_sphere(s2x, s2y);
+}
+// its density and radiance / density (0 density: the sample is invalid, value 0)
+__device__ __forceinline__ V3 emitter_sample_value(const SceneK &S, V3 d, float &pdf) {
+    if (S.emitter == 1) {
+        float4 e = env_eval_pdf(S, d.x, d.y, d.z);
+        pdf = e.w;
+        return (pdf != 0.f) ? mk3(e.x / pdf, e.y / pdf, e.z / pdf) : mk3(0, 0, 0);
+    }
+    pdf = RCV_INV_FOURPI;
+    return mk3(S.env_over_pdf[0], S.env_over_pdf[1], S.env_over_pdf[2]);
 }
 
 // ----------------------------------------------------------------------------

@@ -72,7 +72,14 @@ template <int MODE, class GRID>
 __device__ __forceinline__ void nee_twostates(const SceneK &S, const GRID &G, float mu, float inv_mu, Pcg &rng, V3 ref_p,
                                               float &tr_old, float &tr_new, V3 &dir, unsigned &n_coll) {
     float s2x = pcg_f32(rng), s2y = pcg_f32(rng);                     // :393
-    V3 d = uniform_sphere(s2x, s2y);
+    V3 d = emitter_sample_dir(S, s2x, s2y);
+    dir = d;
+    tr_old = 1.f; tr_new = 1.f;
+    if (S.emitter == 1) {                                             // :395-397 a sample of zero density is invalid
+        float epdf;
+        (void) emitter_sample_value(S, d, epdf);
+        if (epdf == 0.f) return;
+    }
     V3 id = rcp3(d);
     V3 o = ref_p;                                                     // :399 (n = 0: no offset)
     float total_dist = 0.f;
@@ -115,7 +122,6 @@ __device__ __forceinline__ void trace_twostates(const SceneK &S, const GRID &G, 
                                                 unsigned &n_coll, unsigned &n_scat) {
     const float mu = combined_majorant<MODE>(G);
     const float inv_mu = 1.f / mu;
-    const V3 env = mk3(S.env[0], S.env[1], S.env[2]);
     int depth = 0;
     L_old = mk3(0, 0, 0); L_new = mk3(0, 0, 0);
     V3 thr_old = mk3(1, 1, 1), thr_new = mk3(1, 1, 1);
@@ -182,9 +188,10 @@ __device__ __forceinline__ void trace_twostates(const SceneK &S, const GRID &G, 
                     if (scattered && S.sample_emitters) {
                         float tr_old, tr_new; V3 dir;
                         nee_twostates<MODE>(S, G, mu, inv_mu, rng, m.p, tr_old, tr_new, dir, n_coll);
-                        V3 emitter_val = mk3(S.env_over_pdf[0], S.env_over_pdf[1], S.env_over_pdf[2]);
+                        float epdf;
+                        V3 emitter_val = emitter_sample_value(S, dir, epdf);
                         float phase_val = phase_eval(S, wi, dir);     // :333-334
-                        float mis_em = mis_weight(RCV_INV_FOURPI, phase_val);   // :341
+                        float mis_em = mis_weight(epdf, phase_val);   // :341
                         L_new = L_new + ((thr_new * phase_val) * mis_em) * (emitter_val * splat3(tr_new));   // :343
                         L_old = L_old + ((thr_old * phase_val) * mis_em) * (emitter_val * splat3(tr_old));   // :344
                     }
@@ -204,11 +211,13 @@ __device__ __forceinline__ void trace_twostates(const SceneK &S, const GRID &G, 
         if (!si.valid) {
             if (!((depth == 0) && S.hide_emitters)) {
                 bool count_direct = (depth == 0) || specular_chain;
+                float epdf;
+                const V3 env = emitter_eval(S, d, epdf);
                 if (count_direct) {
                     L_new = L_new + thr_new * env;
                     L_old = L_old + thr_old * env;
                 } else {
-                    float mis_bsdf = mis_weight(last_pdf, S.use_nee ? RCV_INV_FOURPI : 0.f);
+                    float mis_bsdf = mis_weight(last_pdf, S.use_nee ? epdf : 0.f);
                     L_new = L_new + (thr_new * mis_bsdf) * env;
                     L_old = L_old + (thr_old * mis_bsdf) * env;
                 }

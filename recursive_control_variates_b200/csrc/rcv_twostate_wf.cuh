@@ -77,13 +77,14 @@ __device__ __forceinline__ void ts_finish(const SceneK &S, TsLane &ln, TsSink &s
 // environment "hit" of the main path (:288-308)
 __device__ __forceinline__ void ts_env_hit(const SceneK &S, TsLane &ln) {
     if ((ln.depth == 0) && S.hide_emitters) return;
-    const V3 env = mk3(S.env[0], S.env[1], S.env[2]);
+    float epdf;
+    const V3 env = emitter_eval(S, ln.d, epdf);
     bool count_direct = (ln.depth == 0) || (ln.flags & F_SPECULAR);
     if (count_direct) {
         ln.L_new = ln.L_new + ln.thr_new * env;
         ln.L_old = ln.L_old + ln.thr_old * env;
     } else {
-        float mis_bsdf = mis_weight(ln.last_pdf, S.use_nee ? RCV_INV_FOURPI : 0.f);
+        float mis_bsdf = mis_weight(ln.last_pdf, S.use_nee ? epdf : 0.f);
         ln.L_new = ln.L_new + (ln.thr_new * mis_bsdf) * env;
         ln.L_old = ln.L_old + (ln.thr_old * mis_bsdf) * env;
     }
@@ -155,9 +156,9 @@ __device__ __forceinline__ void ts_load(TsLane &ln, const PathQueue &Q, unsigned
 // end of the shadow ray: add the emitter-sampling contribution (:336-344),
 // then the phase ratio of the old state (:360-361); the main path resumes
 __device__ __forceinline__ void ts_nee_finish(const SceneK &S, TsLane &ln) {
-    const V3 env = mk3(S.env[0], S.env[1], S.env[2]);
-    V3 emitter_val = mk3(S.env_over_pdf[0], S.env_over_pdf[1], S.env_over_pdf[2]);
-    float mis_em = mis_weight(RCV_INV_FOURPI, ln.phase_val);
+    float epdf;
+    V3 emitter_val = emitter_sample_value(S, ln.nd, epdf);
+    float mis_em = mis_weight(epdf, ln.phase_val);
     ln.L_new = ln.L_new + ((ln.thr_new * ln.phase_val) * mis_em) * (emitter_val * splat3(ln.tr_new));
     ln.L_old = ln.L_old + ((ln.thr_old * ln.phase_val) * mis_em) * (emitter_val * splat3(ln.tr_old));
     ln.thr_old = ln.thr_old * ln.ratio;
@@ -274,7 +275,12 @@ __device__ __forceinline__ void ts_scatter(const SceneK &S, const GridK &G, TsLa
         if (!S.sample_emitters) ln.flags |= F_SPECULAR;
         if (S.sample_emitters) {
             float e2x = pcg_f32(ln.rng), e2y = pcg_f32(ln.rng);       // :393
-            ln.nd = uniform_sphere(e2x, e2y);
+            ln.nd = emitter_sample_dir(S, e2x, e2y);
+            if (S.emitter == 1) {                                     // :395-397 a sample of zero density is invalid
+                float epdf;
+                (void) emitter_sample_value(S, ln.nd, epdf);
+                if (epdf == 0.f) { ln.thr_old = ln.thr_old * ratio; ln.id = rcp3(ln.d); return; }
+            }
             ln.id = rcp3(ln.nd);
             ln.no = ln.o;
             ln.total = 0.f; ln.tr_old = 1.f; ln.tr_new = 1.f;

@@ -152,10 +152,15 @@ template <bool ADJ, class GRID>
 __device__ __forceinline__ float vps_sample_emitter(const SceneK &S, const GRID &G, const GradK &D, float mu, float inv_mu,
                                                     Pcg &rng, V3 ref_p, V3 adjoint, V3 &dir, VpsCounts &cnt) {
     float s2x = pcg_f32(rng), s2y = pcg_f32(rng);                     // :431
-    V3 d = uniform_sphere(s2x, s2y);
+    V3 d = emitter_sample_dir(S, s2x, s2y);
+    dir = d;
+    if (S.emitter == 1) {                                             // :434-436 a sample of zero density is invalid
+        float epdf;
+        (void) emitter_sample_value(S, d, epdf);
+        if (epdf == 0.f) return 0.f;
+    }
     V3 id = rcp3(d);
     Hit si = box_hit(S, ref_p, d, id, RCV_LARGEST);                   // :440-441
-    dir = d;
     return estimate_transmittance<ADJ>(S, G, D, mu, inv_mu, rng, ref_p, d, id, si.t, si.valid, adjoint, cnt);   // :443
 }
 
@@ -193,7 +198,6 @@ __device__ __forceinline__ void vps_trace_core(const SceneK &S, const GRID &G, c
     const float mu = __ldg(G.majorants + 1);       // state `new` (twostatemedium.py:125-136)
     const float inv_mu = 1.f / mu;
     V3 id = rcp3(d);
-    const V3 env = mk3(S.env[0], S.env[1], S.env[2]);
     result = ADJ ? state_in : mk3(0, 0, 0);                           // :68
     V3 thr = mk3(1, 1, 1);
     int depth = 0;
@@ -319,9 +323,10 @@ __device__ __forceinline__ void vps_trace_core(const SceneK &S, const GRID &G, c
             Pcg nee_rng = rng;                                        // :396 sampler.clone()
             V3 dir;
             float tr = vps_sample_emitter<false>(S, G, D, mu, inv_mu, rng, mei_p, mk3(0, 0, 0), dir, cnt);
-            V3 emitted = mk3(S.env_over_pdf[0], S.env_over_pdf[1], S.env_over_pdf[2]) * splat3(tr);
+            float epdf;
+            V3 emitted = emitter_sample_value(S, dir, epdf) * splat3(tr);
             float phase_val = phase_eval(S, wi, dir);                 // :401
-            V3 nee = ((thr * phase_val) * mis_weight(RCV_INV_FOURPI, phase_val)) * emitted;   // :404
+            V3 nee = ((thr * phase_val) * mis_weight(epdf, phase_val)) * emitted;   // :404
             if (ADJ) {
                 V3 dir2;
                 (void) vps_sample_emitter<true>(S, G, D, mu, inv_mu, nee_rng, mei_p, dL * nee, dir2, cnt);   // :412-414
@@ -358,8 +363,9 @@ __device__ __forceinline__ void vps_trace_core(const SceneK &S, const GRID &G, c
     if (!ADJ) {                                                       // :276-300
         if (escaped && si.valid) si = box_hit(S, o, d, id, ray_maxt); // :277-278
         if (escaped && !si.valid && !((depth <= 0) && S.hide_emitters)) {
-            float w = 1.f;
-            if (S.use_nee) w = mis_weight(last_pdf, has_scattered ? RCV_INV_FOURPI : 0.f);   // :286-291
+            float w = 1.f, epdf;
+            const V3 env = emitter_eval(S, d, epdf);
+            if (S.use_nee) w = mis_weight(last_pdf, has_scattered ? epdf : 0.f);   // :286-291
             result = result + (thr * w) * env;                        // :298
         }
     }
@@ -412,9 +418,10 @@ __device__ __forceinline__ V3 sample_recursive(const SceneK &S, const GRID &G, c
     if (S.use_nee) {                                                  // :635-638, throughput 1
         V3 dir;
         float tr = vps_sample_emitter<false>(S, G, D, mu, inv_mu, alt, p, mk3(0, 0, 0), dir, cnt);
-        V3 emitted = mk3(S.env_over_pdf[0], S.env_over_pdf[1], S.env_over_pdf[2]) * splat3(tr);
+        float epdf;
+        V3 emitted = emitter_sample_value(S, dir, epdf) * splat3(tr);
         float phase_val = phase_eval(S, wi, dir);
-        result = result + ((mk3(1, 1, 1) * phase_val) * mis_weight(RCV_INV_FOURPI, phase_val)) * emitted;
+        result = result + ((mk3(1, 1, 1) * phase_val) * mis_weight(epdf, phase_val)) * emitted;
     }
     (void) pcg_f32(alt);                                              // :644-646
     float s2x = pcg_f32(alt), s2y = pcg_f32(alt);

@@ -136,9 +136,9 @@ __device__ __forceinline__ float4 *vp_reservoir(const VpSink &sk, const VpLane &
 template <bool BW, int DRT = 0>
 __device__ __forceinline__ void vp_end_pass(const SceneK &S, VpLane &ln, VpSink &sk) {
     if ((ln.flags & VF_ESCAPED) && !((ln.depth <= 0) && S.hide_emitters)) {
-        const V3 env = mk3(S.env[0], S.env[1], S.env[2]);
-        float w = 1.f;
-        if (S.use_nee) w = mis_weight(ln.last_pdf, (ln.flags & VF_HAS_SCAT) ? RCV_INV_FOURPI : 0.f);
+        float w = 1.f, epdf;
+        const V3 env = emitter_eval(S, ln.d, epdf);
+        if (S.use_nee) w = mis_weight(ln.last_pdf, (ln.flags & VF_HAS_SCAT) ? epdf : 0.f);
         ln.result = ln.result + (ln.thr * w) * env;
     }
     if (!BW) {
@@ -285,9 +285,10 @@ __device__ __forceinline__ void vp_post_vertex(const SceneK &S, VpLane &ln, VpSi
 template <bool BW, int DRT = 0>
 __device__ __forceinline__ void vp_nee_done(const SceneK &S, const GridK &G, VpLane &ln, VpSink &sk) {
     V3 wi = mk3(-ln.d.x, -ln.d.y, -ln.d.z);
-    V3 emitted = mk3(S.env_over_pdf[0], S.env_over_pdf[1], S.env_over_pdf[2]) * splat3(ln.tr_acc);
+    float epdf;
+    V3 emitted = emitter_sample_value(S, ln.nd, epdf) * splat3(ln.tr_acc);
     float phase_val = phase_eval(S, wi, ln.nd);                       // :401
-    ln.nee = ((ln.thr * phase_val) * mis_weight(RCV_INV_FOURPI, phase_val)) * emitted;   // :404
+    ln.nee = ((ln.thr * phase_val) * mis_weight(epdf, phase_val)) * emitted;   // :404
     ln.result = ln.result + ln.nee;                                   // :225
     if (BW) {
         float4 *r = vp_record(sk, ln, ln.nvert - 1);
@@ -511,12 +512,19 @@ __device__ __forceinline__ void vp_vertex1(const SceneK &S, const GridK &G, VpLa
     if (do_nee) {                                                     // :393-446
         ln.saved = ln.rng.state;                                      // :396 sampler.clone()
         float s2x = pcg_f32(ln.rng), s2y = pcg_f32(ln.rng);           // :431
-        ln.nd = uniform_sphere(s2x, s2y);
+        ln.nd = emitter_sample_dir(S, s2x, s2y);
         ln.id = rcp3(ln.nd);
         ln.flags |= VF_IN_NEE;
         ln.running_t = __int_as_float(0);                             // shadow-ray collision records (vp_collide)
         ln.ev = EV_COLL;
-        if (!vp_nee_start(S, ln)) vp_nee_done<BW, DRT>(S, G, ln, sk);
+        bool valid = true;
+        if (S.emitter == 1) {                                         // :434-436 a sample of zero density is invalid
+            float epdf;
+            (void) emitter_sample_value(S, ln.nd, epdf);
+            valid = epdf != 0.f;
+            if (!valid) ln.tr_acc = 0.f;
+        }
+        if (!valid || !vp_nee_start(S, ln)) vp_nee_done<BW, DRT>(S, G, ln, sk);
         return;
     }
     vp_post_vertex<BW, DRT>(S, ln, sk, active);
@@ -711,9 +719,10 @@ __device__ __forceinline__ int vp_drt_sample(const SceneK &S, const GRID &G, con
     if (S.use_nee) {                                                  // :635-638, throughput 1
         V3 dir;
         float tr = vps_sample_emitter<false>(S, G, D, mu, inv_mu, alt, p, mk3(0, 0, 0), dir, cnt);
-        V3 emitted = mk3(S.env_over_pdf[0], S.env_over_pdf[1], S.env_over_pdf[2]) * splat3(tr);
+        float epdf;
+        V3 emitted = emitter_sample_value(S, dir, epdf) * splat3(tr);
         float phase_val = phase_eval(S, wi, dir);
-        Li = Li + ((mk3(1, 1, 1) * phase_val) * mis_weight(RCV_INV_FOURPI, phase_val)) * emitted;
+        Li = Li + ((mk3(1, 1, 1) * phase_val) * mis_weight(epdf, phase_val)) * emitted;
     }
     (void) pcg_f32(alt);                                              // :644-646
     float s2x = pcg_f32(alt), s2y = pcg_f32(alt);

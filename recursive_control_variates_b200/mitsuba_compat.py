@@ -7,7 +7,8 @@ hot path is driven through (`mi.load_dict`, `mi.traverse`, `mi.render`,
 Only the scene class of the volumetric experiments is understood
 (experiments.py:20-133): a perspective sensor or a `batch` of them with an hdrfilm
 (box or gaussian reconstruction filter), one box shape with a `null` BSDF whose interior is a `heterogeneous` grid medium
-(optionally wrapped in a `twostatemedium`), and a `constant` emitter.
+(optionally wrapped in a `twostatemedium`), one emitter (`constant`, `envmap`, or an `area` light on a `rectangle`) and
+diffuse `rectangle` shapes around the medium.
 
 Tensors are torch CUDA tensors; differentiation goes through torch autograd:
 `render()` returns an image whose backward calls the integrator's
@@ -228,6 +229,7 @@ class Scene:
     def __init__(self, d: dict):
         self._shapes, self._sensors, self.env_radiance = [], [], None
         self.shape_key = None
+        self.envmap, self.env_scale, self.env_to_world, self.quads = None, 1.0, None, []
         for key, v in d.items():
             if not isinstance(v, dict):
                 continue
@@ -241,14 +243,49 @@ class Scene:
                 if isinstance(rad, dict):
                     rad = rad.get("value", 1.0)
                 self.env_radiance = tuple(float(x) for x in (rad if np.ndim(rad) else (rad, rad, rad)))
-            elif t in ("envmap", "area"):
-                raise ValueError(f"emitter `{t}` is not supported yet (SURVEY.md §8f); use `constant`")
+            elif t == "envmap":                       # experiments.py:81-85
+                if "bitmap" in v:                     # in-memory (H, W, 3) texels (this shim's extension)
+                    tex = np.asarray(v["bitmap"], dtype=np.float32)
+                else:
+                    from .exrio import read_exr
+                    tex = np.asarray(read_exr(v["filename"]), dtype=np.float32)[..., :3]
+                self.envmap = np.ascontiguousarray(tex)
+                self.env_scale = float(v.get("scale", 1.0))
+                tw = np.asarray(v.get("to_world", np.eye(4)), dtype=np.float64)
+                self.env_to_world = tw[:3, :3]
+                if np.abs(self.env_to_world @ self.env_to_world.T - np.eye(3)).max() > 1e-6:
+                    raise ValueError("envmap: `to_world` must be a rotation")
+                self.env_radiance = (0.0, 0.0, 0.0)
+            elif t == "rectangle":                    # Mitsuba's rectangle: [-1,1]^2 in the xy plane, normal +z, under to_world
+                tw = np.asarray(v.get("to_world", np.eye(4)), dtype=np.float64)
+                p0 = tw[:3, :3] @ np.array([-1.0, -1.0, 0.0]) + tw[:3, 3]
+                eu, ev = tw[:3, :3] @ np.array([2.0, 0.0, 0.0]), tw[:3, :3] @ np.array([0.0, 2.0, 0.0])
+                if abs(float(eu @ ev)) > 1e-9 * float(np.linalg.norm(eu) * np.linalg.norm(ev)):
+                    raise ValueError("rectangle: `to_world` must keep the edges perpendicular")
+                bsdf = v.get("bsdf", {"type": "diffuse"})
+                if bsdf.get("type") != "diffuse":
+                    raise ValueError("rectangles carry a `diffuse` BSDF")
+                refl = bsdf.get("reflectance", 0.5)
+                refl = refl.get("value", 0.5) if isinstance(refl, dict) else refl
+                q = dict(p0=p0, eu=eu, ev=ev, reflectance=tuple(float(x) for x in (refl if np.ndim(refl) else (refl,) * 3)))
+                em = v.get("emitter")
+                if em is not None:
+                    if em.get("type") != "area":
+                        raise ValueError("a shape's emitter must be an `area` light")
+                    rad = em.get("radiance", 1.0)
+                    rad = rad.get("value", 1.0) if isinstance(rad, dict) else rad
+                    q["radiance"] = tuple(float(x) for x in (rad if np.ndim(rad) else (rad,) * 3))
+                    if self.env_radiance is None:
+                        self.env_radiance = (0.0, 0.0, 0.0)
+                self.quads.append(q)
+            elif t == "area":
+                raise ValueError("an `area` emitter belongs to a `rectangle` shape (its `emitter` entry)")
         if len(self._shapes) != 1 or self._shapes[0].interior_medium() is None:
             raise ValueError("expected a single shape with an interior medium (volpathsimple.py:16-19)")
         if len(self._sensors) != 1:
             raise ValueError("only scenes with a single sensor are supported (optimize.py:36)")
         if self.env_radiance is None:
-            raise ValueError("the scene needs a `constant` emitter")
+            raise ValueError("the scene needs an emitter: `constant`, `envmap` or an `area` light on a rectangle")
         self._ctx: Optional[Context] = None
         self._ctx_key = None
         # rotations requested before the device context exists; the scene file loads the same
@@ -272,7 +309,8 @@ class Scene:
                            bbox_min=sh.bbox_min, bbox_max=sh.bbox_max, sigma_t_scale=m.scale, phase=m.phase, phase_g=m.phase_g,
                            sample_emitters=m.sample_emitters, env_radiance=self.env_radiance, max_depth=max_depth,
                            rr_depth=rr_depth, hide_emitters=hide_emitters, use_nee=use_nee, rfilter=s.rfilter,
-                           rfilter_stddev=s.rfilter_stddev)
+                           rfilter_stddev=s.rfilter_stddev, envmap=self.envmap, env_scale=self.env_scale,
+                           env_to_world=self.env_to_world, quads=tuple(self.quads))
 
     def context(self, max_depth: int, rr_depth: int, hide_emitters: bool = False, use_nee: bool = True) -> Context:
         """The rcv_ctx of this scene, configured for the calling integrator."""

@@ -22,6 +22,19 @@ using namespace rcv;
 
 namespace {
 
+// SceneK of a description, with the `envmap` tables (host memory) when the scene has one
+struct HostScene {
+    SceneK S;
+    EnvTables env;
+    explicit HostScene(const rcv_scene_desc &d) {
+        scene_from_desc(d, S);
+        if (d.emitter_type == RCV_EMITTER_ENVMAP) {
+            env_tables_build(d, env);
+            S.env_data = env.data.data(); S.env_cdf_m = env.cdf_m.data(); S.env_cdf_c = env.cdf_c.data(); S.env_pdf = env.pdf.data();
+        }
+    }
+};
+
 struct Packed {
     std::vector<float2> sig2;
     std::vector<float4> blk2, blk1;
@@ -251,7 +264,7 @@ extern "C" {
 int emu_vps_drt_stages(const rcv_scene_desc *d, const float *sn, const float *an, int nz, int ny, int nx, uint32_t seed, uint32_t spp,
                        uint32_t alt_seed, const float *grad_img, const float *film_w, float *gsig, float *galb4,
                        uint64_t *counters, int factor, int use_mis) {
-    SceneK S; scene_from_desc(*d, S);
+    HostScene hs(*d); const SceneK &S = hs.S;
     Packed P; pack(*d, sn, an, sn, an, nz, ny, nx, P, factor);
     for (int i = 0; i < 8; ++i) counters[i] = 0;
     VpSink sk; sk.accum = nullptr; sk.D.gsig = gsig; sk.D.galb = (float4 *) galb4; sk.grad_img = grad_img; sk.film_w = film_w;
@@ -270,7 +283,7 @@ int emu_vps_drt_stages(const rcv_scene_desc *d, const float *sn, const float *an
 // factor > 0: majorant supergrid + DDA (the GridKS instantiation of the handlers)
 int emu_twostates_sg(const rcv_scene_desc *d, const float *so, const float *ao, const float *sn, const float *an, int nz, int ny,
                      int nx, uint32_t seed, uint32_t spp, int mode, int factor, float *acc_old, float *acc_new, uint64_t *counters) {
-    SceneK S; scene_from_desc(*d, S);
+    HostScene hs(*d); const SceneK &S = hs.S;
     Packed P; pack(*d, so, ao, sn, an, nz, ny, nx, P, factor);
     for (int i = 0; i < 8; ++i) counters[i] = 0;
     float4 *ao4 = (float4 *) acc_old, *an4 = (float4 *) acc_new;
@@ -296,7 +309,7 @@ int emu_twostates(const rcv_scene_desc *d, const float *so, const float *ao, con
 int emu_vps_sg(const rcv_scene_desc *d, const float *sn, const float *an, int nz, int ny, int nx, uint32_t seed, uint32_t spp,
                int backward, uint32_t alt_seed, const float *grad_img, const float *film_w, float *accum, float *gsig,
                float *galb4, uint64_t *counters, int factor) {
-    SceneK S; scene_from_desc(*d, S);
+    HostScene hs(*d); const SceneK &S = hs.S;
     Packed P; pack(*d, sn, an, sn, an, nz, ny, nx, P, factor);
     for (int i = 0; i < 8; ++i) counters[i] = 0;
     VpSink sk; sk.accum = (float4 *) accum; sk.D.gsig = gsig; sk.D.galb = (float4 *) galb4; sk.grad_img = grad_img; sk.film_w = film_w;
@@ -319,7 +332,7 @@ int emu_vps_sg(const rcv_scene_desc *d, const float *sn, const float *an, int nz
 int emu_vps_backward_lane(const rcv_scene_desc *d, const float *sn, const float *an, int nz, int ny, int nx, uint32_t seed,
                           uint32_t spp, uint32_t alt_seed, const float *grad_img, const float *film_w, float *gsig, float *galb4,
                           uint64_t *counters, int factor, int drt_flags) {
-    SceneK S; scene_from_desc(*d, S);
+    HostScene hs(*d); const SceneK &S = hs.S;
     Packed P; pack(*d, sn, an, sn, an, nz, ny, nx, P, factor);
     for (int i = 0; i < 8; ++i) counters[i] = 0;
     GradK D; D.gsig = gsig; D.galb = (float4 *) galb4;

@@ -36,8 +36,9 @@ def test_header_symbols_exported(lib):
 def test_struct_layouts_match_header(lib):
     from recursive_control_variates_b200 import _abi
     # 4 + 2*4 + 3*4 + 9*4 + 3*4 + 6*4 + 4 + 4 + 4 + 4 + 3*4 + 4 + 4*4 = 144, + n_sensors 4 + 16 * (3 + 9) * 4 = 916, + rfilter 8 = 924
-    assert C.sizeof(_abi.SceneDesc) == 924
-    assert lib.rcv_abi_version() == 3
+    # ABI 4: + emitter_type 4, envmap pointer 8, env_width/height 8, env_scale 4, env_to_world 36, n_quads 4, area_quad 4, 8 quads x 60
+    assert C.sizeof(_abi.SceneDesc) == 924 + 4 + 8 + 8 + 4 + 36 + 4 + 4 + 8 * 60 == 1472
+    assert lib.rcv_abi_version() == 4
 
 
 def test_no_cpu_fallback(lib):
