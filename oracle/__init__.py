@@ -70,6 +70,7 @@ def lib() -> C.CDLL:
         L.orc_vps_lanes.argtypes = [SP, MP, u32, u32, u64, u64, _f32p, _i32p, i32]
         L.orc_vps_render.argtypes = [SP, MP, u32, u32, u32, u32, _f32p, i32]
         L.orc_vps_backward.argtypes = [SP, MP, u32, u32, u32, u32, _f32p, _f32p, _f64p, _f64p, i32]
+        L.orc_prb_backward.argtypes = [SP, MP, u32, u32, u32, u32, _f32p, _f32p, _f64p, _f64p, i32]
         L.orc_vps_backward_drt.argtypes = [SP, MP, u32, u32, u32, u32, _f32p, _f32p, _f64p, _f64p, i32, i32, i32]
         L.orc_phase_sample.argtypes = [SP, _f32p, f, f, _f32p]; L.orc_phase_sample.restype = f
         L.orc_phase_eval.argtypes = [SP, _f32p, _f32p]; L.orc_phase_eval.restype = f
@@ -257,6 +258,20 @@ def vps_backward(desc, m: OracleMedium, seed_grad, spp_grad, grad_img, spp_begin
         rc = lib().orc_vps_backward_drt(*args, int(use_drt_subsampling), int(use_drt_mis))
     else:
         rc = lib().orc_vps_backward(*args)
+    assert rc == 0
+    return gs, ga
+
+
+def prb_backward(desc, m: OracleMedium, seed_grad, spp_grad, grad_img, spp_begin=0, spp_end=None, threads=None, film_w=None):
+    """render_backward of upstream prbvolpath (the adjoint twostateprbvolpath inherits) on state m."""
+    spp_end = spp_grad if spp_end is None else spp_end
+    nz, ny, nx = m.shape
+    gs = np.zeros((nz, ny, nx, 1), np.float64); ga = np.zeros((nz, ny, nx, 3), np.float64)
+    if film_w is None:
+        film_w = film_weights(desc, seed_grad, spp_grad)
+    rc = lib().orc_prb_backward(C.addressof(desc), C.byref(m.c), seed_grad, spp_grad, spp_begin, spp_end,
+                                np.ascontiguousarray(grad_img, np.float32).reshape(-1), film_w.reshape(-1),
+                                gs.reshape(-1), ga.reshape(-1), threads or default_threads())
     assert rc == 0
     return gs, ga
 

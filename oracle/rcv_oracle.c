@@ -258,7 +258,9 @@ typedef struct {
 } env_tables;
 static env_tables g_env = {0};
 
+static void quads_build(const rcv_scene_desc *S);
 static void env_build(const rcv_scene_desc *S) {
+    quads_build(S);
     if (S->emitter_type != RCV_EMITTER_ENVMAP) return;
     if (g_env.key == S->envmap_rgb && g_env.w == S->env_width && g_env.h == S->env_height && g_env.scale == S->env_scale) return;
     free(g_env.data); free(g_env.cdf_m); free(g_env.cdf_c); free(g_env.pdf);
@@ -414,6 +416,7 @@ typedef struct {
     int valid;     /* si.is_valid() */
     float t;       /* inf when invalid */
     v3 p, n;
+    int shape;     /* -1: the medium's box (null BSDF, medium transition); k >= 0: rectangle k (diffuse BSDF) */
 } si_t;
 
 typedef struct { v3 o, d; float maxt; } ray_t;
@@ -441,7 +444,7 @@ static inline int aabb_intersect(const rcv_scene_desc *S, v3 o, v3 d, float *min
  * (The reference's scene is a cube mesh traced by OptiX/Embree; the analytic
  * slab test is this build's equivalent) */
 static inline si_t scene_intersect(const rcv_scene_desc *S, const ray_t *ray) {
-    si_t si; si.valid = 0; si.t = ORC_INF; si.p = V3(0, 0, 0); si.n = V3(0, 0, 0);
+    si_t si; si.valid = 0; si.t = ORC_INF; si.p = V3(0, 0, 0); si.n = V3(0, 0, 0); si.shape = -1;
     const float *bmin = S->bbox_min, *bmax = S->bbox_max;
     float oo[3] = {ray->o.x, ray->o.y, ray->o.z}, dd[3] = {ray->d.x, ray->d.y, ray->d.z};
     float tn = -ORC_INF, tf = ORC_INF; int an = 0, af = 0;
@@ -468,6 +471,99 @@ static inline si_t scene_intersect(const rcv_scene_desc *S, const ray_t *ray) {
     si.valid = 1; si.t = t;
     si.p = V3(pp[0], pp[1], pp[2]); si.n = V3(nn[0], nn[1], nn[2]);
     return si;
+}
+
+/* ------------------------------------------------------------------------- */
+/* rectangles (ABI 4): `rectangle` shapes with a one-sided `diffuse` BSDF and, on one of them, the `area` light
+ * [UPSTREAM rectangle.cpp, diffuse.cpp, area.cpp, shape.cpp sample_direction / pdf_direction; restated].
+ * Derived quantities are computed in binary32 with the operation order below (the library does the same). */
+/* ------------------------------------------------------------------------- */
+#define ORC_INV_PI 0.31830988618379067154f
+typedef struct { v3 p0, eu, ev, n, s, t, refl, rad; float inv_eu2, inv_ev2, inv_area; } rquad_t;
+static rquad_t g_quads[RCV_MAX_QUADS];
+static inline float dot3(v3 a, v3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
+static inline v3 cross3(v3 a, v3 b) {
+    return V3(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x)));
+}
+static void quads_build(const rcv_scene_desc *S) {
+    for (uint32_t k = 0; k < S->n_quads && k < RCV_MAX_QUADS; ++k) {
+        const rcv_quad *q = &S->quads[k]; rquad_t *g = &g_quads[k];
+        g->p0 = V3(q->p0[0], q->p0[1], q->p0[2]); g->eu = V3(q->eu[0], q->eu[1], q->eu[2]); g->ev = V3(q->ev[0], q->ev[1], q->ev[2]);
+        g->refl = V3(q->reflectance[0], q->reflectance[1], q->reflectance[2]);
+        g->rad = V3(q->radiance[0], q->radiance[1], q->radiance[2]);
+        v3 c = cross3(g->eu, g->ev);
+        float len = sqrtf(dot3(c, c));
+        g->n = V3(c.x / len, c.y / len, c.z / len);
+        float lu2 = dot3(g->eu, g->eu), lv2 = dot3(g->ev, g->ev);
+        g->inv_eu2 = 1.f / lu2; g->inv_ev2 = 1.f / lv2; g->inv_area = 1.f / len;
+        float lu = sqrtf(lu2);
+        g->s = V3(g->eu.x / lu, g->eu.y / lu, g->eu.z / lu);          /* shading frame (s, t, n) */
+        g->t = cross3(g->n, g->s);
+    }
+}
+/* scene.ray_intersect: the nearest of the medium's box and the rectangles, 0 < t <= maxt */
+static inline si_t scene_intersect_all(const rcv_scene_desc *S, const ray_t *ray) {
+    si_t si = scene_intersect(S, ray);
+    for (uint32_t k = 0; k < S->n_quads; ++k) {
+        const rquad_t *q = &g_quads[k];
+        float denom = dot3(q->n, ray->d);
+        if (denom == 0.f) continue;
+        float t = dot3(q->n, vsub(q->p0, ray->o)) / denom;
+        if (!(t > 0.f) || !(t <= ray->maxt) || !(t < si.t)) continue;
+        v3 p = ray_at(ray->o, ray->d, t);
+        v3 rel = vsub(p, q->p0);
+        float a = dot3(rel, q->eu) * q->inv_eu2, b = dot3(rel, q->ev) * q->inv_ev2;
+        if (!(a >= 0.f && a <= 1.f && b >= 0.f && b <= 1.f)) continue;
+        si.valid = 1; si.t = t; si.p = p; si.n = q->n; si.shape = (int) k;
+    }
+    return si;
+}
+/* diffuse.cpp eval / pdf for incident ray direction d_in (wi = -d_in) and outgoing world direction wo */
+static inline void diffuse_eval_pdf(const rquad_t *q, v3 d_in, v3 wo, v3 *val, float *pdf) {
+    float ci = -dot3(q->n, d_in), co = dot3(q->n, wo);
+    if (ci > 0.f && co > 0.f) {
+        *pdf = ORC_INV_PI * co;
+        *val = vscale(vscale(q->refl, ORC_INV_PI), co);
+    } else { *pdf = 0.f; *val = V3(0, 0, 0); }
+}
+/* warp.square_to_cosine_hemisphere (concentric disk) [UPSTREAM warp.h] */
+static inline v3 square_to_cosine_hemisphere(float sx, float sy) {
+    float x = fmaf(2.f, sx, -1.f), y = fmaf(2.f, sy, -1.f);
+    int is_zero = (x == 0.f) && (y == 0.f), q13 = fabsf(x) < fabsf(y);
+    float r = q13 ? y : x, rp = q13 ? x : y;
+    float phi = (0.25f * ORC_PI) * (rp / r);
+    if (q13) phi = (0.5f * ORC_PI) - phi;
+    if (is_zero) phi = 0.f;
+    float sn, cs;
+    orc_sincosf(fabsf(phi), &sn, &cs);
+    if (phi < 0.f) sn = -sn;
+    float px = r * cs, py = r * sn;
+    float z = sqrtf(fmaxf_(1.f - fmaf(px, px, py * py), 0.f));
+    return V3(px, py, z);
+}
+/* area light on rectangle S->area_quad: sample_direction / pdf_direction / eval */
+static inline void area_sample(const rcv_scene_desc *S, v3 ref_p, float s2x, float s2y, v3 *d, float *dist, float *pdf, v3 *val) {
+    const rquad_t *q = &g_quads[S->area_quad];
+    v3 p = V3(fmaf(s2y, q->ev.x, fmaf(s2x, q->eu.x, q->p0.x)), fmaf(s2y, q->ev.y, fmaf(s2x, q->eu.y, q->p0.y)),
+              fmaf(s2y, q->ev.z, fmaf(s2x, q->eu.z, q->p0.z)));
+    v3 v = vsub(p, ref_p);
+    float dist2 = dot3(v, v);
+    *dist = sqrtf(dist2);
+    *d = V3(v.x / *dist, v.y / *dist, v.z / *dist);
+    float dp = dot3(*d, q->n);
+    float x = dist2 / fabsf(dp);
+    *pdf = isfinite(x) ? q->inv_area * x : 0.f;
+    int ok = (dp < 0.f) && (*pdf != 0.f);
+    *val = ok ? V3(q->rad.x / *pdf, q->rad.y / *pdf, q->rad.z / *pdf) : V3(0, 0, 0);
+}
+static inline float area_pdf(const rcv_scene_desc *S, v3 ref_p, v3 hit_p) {
+    const rquad_t *q = &g_quads[S->area_quad];
+    v3 v = vsub(hit_p, ref_p);
+    float dist2 = dot3(v, v), dist = sqrtf(dist2);
+    v3 d = V3(v.x / dist, v.y / dist, v.z / dist);
+    float dp = dot3(d, q->n);
+    float x = dist2 / fabsf(dp);
+    return ((dp < 0.f) && isfinite(x)) ? q->inv_area * x : 0.f;
 }
 
 /* Interaction::spawn_ray / offset_p [UPSTREAM interaction.h] */
@@ -805,6 +901,7 @@ typedef struct {
     float mint;
     v3 sigma_s, sigma_n, sigma_t;
     float combined_extinction;
+    v3 albedo;               /* of state `new` (sigma_s = sigma_t * albedo), for the prbvolpath adjoint */
 } mei_t;
 
 static inline int mei_valid(const mei_t *m) { return m->t < ORC_INF; } /* isfinite(t) */
@@ -846,6 +943,7 @@ static void sample_interaction_twostates(const rcv_scene_desc *S, const orc_medi
     mn.t = valid_mi ? sampled_t : ORC_INF;                                     /* :88 */
     mn.p = ray_at(ray->o, ray->d, sampled_t);                                  /* :89 */
     mn.mint = mint;
+    mn.albedo = V3(0, 0, 0);
     v3 ss_o = V3(0, 0, 0), st_o = V3(0, 0, 0), ss_n = V3(0, 0, 0), st_n = V3(0, 0, 0);
     if (valid_mi) {
         /* get_scattering_coefficients of both states at the same point (:93-94):
@@ -855,6 +953,7 @@ static void sample_interaction_twostates(const rcv_scene_desc *S, const orc_medi
         v3 ao = lookup_albedo(Mo, &T), an = lookup_albedo(Mn, &T);
         st_o = V3(so, so, so); st_n = V3(sn, sn, sn);
         ss_o = vmul(st_o, ao); ss_n = vmul(st_n, an);
+        mn.albedo = an;
         cnt->c[0]++;
     }
     v3 ce = V3(combined_extinction, combined_extinction, combined_extinction);
@@ -866,20 +965,72 @@ static void sample_interaction_twostates(const rcv_scene_desc *S, const orc_medi
 }
 
 /* ------------------------------------------------------------------------- */
+/* gradient sink (the adjoints scatter d loss / d sigma_t.data, d albedo.data) */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+    double *g_sigma_t;   /* (nz,ny,nx,1) or NULL in primal mode */
+    double *g_albedo;    /* (nz,ny,nx,3) */
+    int atomic;          /* use omp atomic (multi-threaded) */
+} grad_sink;
+
+static inline void sink_add(double *a, double v, int atomic) {
+    if (atomic) {
+#pragma omp atomic
+        *a += v;
+    } else *a += v;
+}
+/* AD of the trilinear gather = scatter-add of w_corner * grad (SURVEY §2.3 gridvolume) */
+static void scatter_sigma_t(const rcv_scene_desc *S, const orc_medium *M, grad_sink *G, v3 p, float g, counters_t *cnt) {
+    tri_t T = tri_setup(S, M, p);
+    if (!T.inside) return;
+    for (int k = 0; k < 8; ++k)
+        sink_add(&G->g_sigma_t[tri_index(M, &T, k)], (double) (tri_weight(&T, k) * (S->sigma_t_scale * g)), G->atomic);
+    cnt->c[4]++;
+}
+static void scatter_albedo(const rcv_scene_desc *S, const orc_medium *M, grad_sink *G, v3 p, v3 g, counters_t *cnt) {
+    tri_t T = tri_setup(S, M, p);
+    if (!T.inside) return;
+    for (int k = 0; k < 8; ++k) {
+        float w = tri_weight(&T, k);
+        size_t o = tri_index(M, &T, k) * 3;
+        sink_add(&G->g_albedo[o], (double) (w * g.x), G->atomic);
+        sink_add(&G->g_albedo[o + 1], (double) (w * g.y), G->atomic);
+        sink_add(&G->g_albedo[o + 2], (double) (w * g.z), G->atomic);
+    }
+    cnt->c[5]++;
+}
+
+/* PRBVolpathIntegrator.sample in Backward mode [UPSTREAM-RECALLED mi.ad.integrators.prbvolpath; the adjoint the
+ * two-state integrator inherits, plugins/twostatevolpath.py:11]: the same path as the primal pass (same stream), L
+ * starts as the primal result and every contribution is subtracted when it is met, so that at each medium event L is
+ * the radiance still to come; the event's weight w(sigma_t, albedo) is differentiated as dL * L * dw / w. */
+typedef struct {
+    v3 dL;          /* d loss / d radiance of this sample */
+    v3 L_total;     /* result of the primal pass */
+    grad_sink *G;
+} prb_adj;
+
+/* ------------------------------------------------------------------------- */
 /* sample_emitter_twostates  (plugins/twostatevolpath.py:387-479)             */
+/* `adjoint` != NULL: prbvolpath's sample_emitter in Backward mode — the same walk with the cloned sampler, scattering
+ * adjoint * d log(sigma_n / majorant) / d sigma_t at every ratio-tracking collision [UPSTREAM-RECALLED]            */
 /* ------------------------------------------------------------------------- */
 static void sample_emitter_twostates(const rcv_scene_desc *S, const orc_medium *Mo, const orc_medium *Mn,
                                      pcg32 *rng, v3 ref_p, v3 ref_n, int medium, int active,
                                      v3 *emitted_old, v3 *emitted_new, v3 *ds_d, float *ds_pdf,
-                                     counters_t *cnt) {
+                                     const v3 *adjoint, grad_sink *G, counters_t *cnt) {
     if (!active) medium = 0;                                                   /* :391 */
-    /* scene.sample_emitter_direction with one `constant` emitter [UPSTREAM constant.cpp]:
-     * d uniform on the sphere, pdf 1/(4 pi), dist = 2 * bsphere radius, value = radiance / pdf */
+    /* scene.sample_emitter_direction with the scene's one emitter: `constant` / `envmap` [UPSTREAM constant.cpp:
+     * d uniform on the sphere, pdf 1/(4 pi), dist = 2 * bsphere radius, value = radiance / pdf] or the `area` light
+     * (a point on the rectangle) */
     float s2x = next_1d(rng, active), s2y = next_1d(rng, active);              /* :393 next_2d(active) */
     v3 d = V3(0, 0, 0); float pdf = 0.f, dist = 0.f; v3 emitter_val = V3(0, 0, 0);
     if (active) {
-        emitter_sample_env(S, s2x, s2y, &d, &pdf, &emitter_val);               /* `constant` or `envmap` */
-        dist = S->env_dist;
+        if (S->emitter_type == RCV_EMITTER_AREA) area_sample(S, ref_p, s2x, s2y, &d, &dist, &pdf, &emitter_val);
+        else {
+            emitter_sample_env(S, s2x, s2y, &d, &pdf, &emitter_val);           /* `constant` or `envmap` */
+            dist = S->env_dist;
+        }
     }
     int invalid = (pdf == 0.f);                                                /* :395 */
     if (invalid) emitter_val = V3(0, 0, 0);
@@ -887,7 +1038,7 @@ static void sample_emitter_twostates(const rcv_scene_desc *S, const orc_medium *
 
     ray_t ray = spawn_ray(ref_p, ref_n, d);                                    /* :399 */
     float total_dist = 0.f;
-    si_t si; si.valid = 0; si.t = 0.f; si.p = V3(0, 0, 0); si.n = V3(0, 0, 0); /* dr.zeros(SurfaceInteraction3f) */
+    si_t si; si.valid = 0; si.t = 0.f; si.p = V3(0, 0, 0); si.n = V3(0, 0, 0); si.shape = -1; /* dr.zeros(SurfaceInteraction3f) */
     int needs_intersection = 1;
     v3 tr_old = V3(1, 1, 1), tr_new = V3(1, 1, 1);
     while (active) {                                                           /* :408 */
@@ -895,7 +1046,7 @@ static void sample_emitter_twostates(const rcv_scene_desc *S, const orc_medium *
         ray.maxt = remaining_dist;
         active = active && (remaining_dist > 0.f);
         needs_intersection = needs_intersection && active;                     /* :414 */
-        if (needs_intersection) si = scene_intersect(S, &ray);
+        if (needs_intersection) si = scene_intersect_all(S, &ray);
         needs_intersection = 0;
         int active_medium = active && (medium != 0);                           /* :418 */
         int active_surface = active && !active_medium;
@@ -911,15 +1062,21 @@ static void sample_emitter_twostates(const rcv_scene_desc *S, const orc_medium *
             ray.o = mn.p;                                                      /* :445 */
             si.t = si.t - mn.t;                                                /* :446 */
             float ce = mn.combined_extinction;
-            v3 cev = V3(ce, ce, ce);
             float inv_ce = 1.f / ce;                                           /* [SPEC] reciprocal majorant */
-            (void) cev;
             m_old = (ce != 0.f) ? vmul(m_old, vscale(mo.sigma_n, inv_ce)) : vmul(m_old, mo.sigma_n);   /* :447-449 */
             m_new = (ce != 0.f) ? vmul(m_new, vscale(mn.sigma_n, inv_ce)) : vmul(m_new, mn.sigma_n);   /* :450-452 */
+            if (adjoint && (m_new.x > 0.f)) {                                  /* prbvolpath sample_emitter, Backward */
+                float k = (-inv_ce) / m_new.x, g = 0.f;
+                g += adjoint->x * k; g += adjoint->y * k; g += adjoint->z * k;
+                scatter_sigma_t(S, Mn, G, mn.p, g, cnt);
+            }
         }
         active_surface = active_surface || escaped_medium;                     /* :455 */
         active_surface = active_surface && si.valid && !active_medium;
-        /* null BSDF: eval_null_transmission == 1 (:457-460) */
+        if (active_surface) {                                                  /* :457-460 eval_null_transmission */
+            float bsdf_val = (si.shape < 0) ? 1.f : 0.f;                       /* null BSDF: 1; diffuse: 0 */
+            m_old = vscale(m_old, bsdf_val); m_new = vscale(m_new, bsdf_val);
+        }
         tr_old = vmul(tr_old, m_old);                                          /* :462 */
         tr_new = vmul(tr_new, m_new);
         if (active_surface) {                                                  /* :466-467 */
@@ -930,7 +1087,7 @@ static void sample_emitter_twostates(const rcv_scene_desc *S, const orc_medium *
         needs_intersection = needs_intersection || active_surface;
         active = active && (active_medium || active_surface) && (any_nz(tr_new) || any_nz(tr_old)); /* :472 */
         if (active) total_dist += active_medium ? mn.t : si.t;                 /* :473 */
-        if (active_surface) {                                                  /* :476-477 si.is_medium_transition() */
+        if (active_surface && si.shape < 0) {                                  /* :476-477 si.is_medium_transition() */
             float dn = fmaf(si.n.x, ray.d.x, fmaf(si.n.y, ray.d.y, si.n.z * ray.d.z));
             medium = (dn > 0.f) ? 0 : 1;                                       /* target_medium(d): exterior / interior */
         }
@@ -942,16 +1099,17 @@ static void sample_emitter_twostates(const rcv_scene_desc *S, const orc_medium *
 
 /* ------------------------------------------------------------------------- */
 /* sample_twostates  (plugins/twostatevolpath.py:141-385)                     */
+/* adj != NULL: upstream prbvolpath's sample() in Backward mode on state `new` (call with Mo == Mn), see prb_adj      */
 /* ------------------------------------------------------------------------- */
 static void sample_twostates(const rcv_scene_desc *S, const orc_medium *Mo, const orc_medium *Mn,
                              pcg32 *rng, ray_t ray, float L_old_out[3], float L_new_out[3],
-                             int *valid_out, counters_t *cnt) {
+                             int *valid_out, counters_t *cnt, const prb_adj *adj) {
     int depth = 0;
-    v3 L_old = V3(0, 0, 0), L_new = V3(0, 0, 0);
+    v3 L_old = V3(0, 0, 0), L_new = adj ? adj->L_total : V3(0, 0, 0);
     v3 thr_old = V3(1, 1, 1), thr_new = V3(1, 1, 1);
     float eta = 1.f;
     int active = 1;
-    si_t si; si.valid = 0; si.t = 0.f; si.p = V3(0, 0, 0); si.n = V3(0, 0, 0);
+    si_t si; si.valid = 0; si.t = 0.f; si.p = V3(0, 0, 0); si.n = V3(0, 0, 0); si.shape = -1;
     int needs_intersection = 1;
     v3 last_scatter_p = V3(0, 0, 0);
     float last_scatter_direction_pdf = 1.f;
@@ -978,7 +1136,7 @@ static void sample_twostates(const rcv_scene_desc *S, const orc_medium *Mo, cons
         mei_t mo, mn;
         sample_interaction_twostates(S, Mo, Mn, &ray, u, active_medium, &mo, &mn, cnt);   /* :196 */
         int intersect = needs_intersection && active_medium;                   /* :200 */
-        if (intersect) si = scene_intersect(S, &ray);
+        if (intersect) si = scene_intersect_all(S, &ray);
         needs_intersection = needs_intersection && !active_medium;             /* :204 */
         if (active_medium && (si.t < mn.t)) mn.t = ORC_INF;                    /* :205 */
         if (active_medium && (si.t < mo.t)) mo.t = ORC_INF;
@@ -1018,6 +1176,22 @@ static void sample_twostates(const rcv_scene_desc *S, const orc_medium *Mo, cons
             thr_new = vmul(thr_new, weight_new);
             thr_old = vmul(thr_old, weight_old);
         }
+        if (adj && active_medium) {
+            /* prbvolpath Backward: dr.backward(dL * weight * L / max(1e-8, weight)) with weight = sigma_n * c (null) or
+             * sigma_t * albedo * c (real), c detached: dL * L * d log(weight) [UPSTREAM-RECALLED]; L = L_new is the
+             * radiance still to come */
+            float aw = (adj->dL.x * L_new.x + adj->dL.y * L_new.y) + adj->dL.z * L_new.z;
+            if (act_null_scatter) {
+                float sn = mn.sigma_n.x;
+                if (sn > 0.f) scatter_sigma_t(S, Mn, adj->G, mn.p, -(aw * (1.f / sn)), cnt);
+            } else if (act_medium_scatter) {
+                float st = mn.sigma_t.x;
+                v3 al = mn.albedo;
+                v3 Lo = vdiv(L_new, vmax(V3(1e-8f, 1e-8f, 1e-8f), al));
+                scatter_sigma_t(S, Mn, adj->G, mn.p, aw * (1.f / st), cnt);
+                scatter_albedo(S, Mn, adj->G, mn.p, vmul(adj->dL, Lo), cnt);
+            }
+        }
         valid_ray = valid_ray || act_medium_scatter;                           /* :274 */
         float s1 = next_1d(rng, act_medium_scatter);                           /* :275 */
         float s2x = next_1d(rng, act_medium_scatter), s2y = next_1d(rng, act_medium_scatter);
@@ -1035,31 +1209,36 @@ static void sample_twostates(const rcv_scene_desc *S, const orc_medium *Mo, cons
         /* ---- surface interactions (:283-286) */
         active_surface = active_surface || escaped_medium;
         intersect = active_surface && needs_intersection;
-        if (intersect) si = scene_intersect(S, &ray);
+        if (intersect) si = scene_intersect_all(S, &ray);
 
-        /* ---- intersection with emitters (:288-308); the only emitter is the
-         * environment, reached by rays whose si is invalid [UPSTREAM si.emitter(scene)] */
+        /* ---- intersection with emitters (:288-308): the `area` light's rectangle, or the environment for rays that
+         * hit nothing [UPSTREAM si.emitter(scene)] */
         int ray_from_camera = active_surface && (depth == 0);
         int count_direct = ray_from_camera || specular_chain;
-        int has_emitter = !si.valid;
+        int has_emitter = si.valid ? (S->emitter_type == RCV_EMITTER_AREA && si.shape == S->area_quad)
+                                   : (S->emitter_type != RCV_EMITTER_AREA);
         int active_e = active_surface && has_emitter && !((depth == 0) && S->hide_emitters);
         if (active_e) {
-            float emitter_pdf_ = S->use_nee ? emitter_pdf(S, ray.d) : 0.f;      /* :297 pdf_emitter_direction */
-            v3 emitted = emitter_eval(S, ray.d);                               /* :300 */
-            float mis_bsdf = mis_weight(last_scatter_direction_pdf, emitter_pdf_);         /* :302 */
-            if (count_direct) {                                                /* :304-308 */
-                L_new = vadd(L_new, vmul(thr_new, emitted));
-                L_old = vadd(L_old, vmul(thr_old, emitted));
+            float emitter_pdf_; v3 emitted;
+            if (si.valid) {                                                    /* area.cpp pdf_direction / eval */
+                emitter_pdf_ = S->use_nee ? area_pdf(S, last_scatter_p, si.p) : 0.f;
+                emitted = (-dot3(si.n, ray.d) > 0.f) ? g_quads[si.shape].rad : V3(0, 0, 0);
             } else {
-                L_new = vadd(L_new, vmul(vscale(thr_new, mis_bsdf), emitted));
-                L_old = vadd(L_old, vmul(vscale(thr_old, mis_bsdf), emitted));
+                emitter_pdf_ = S->use_nee ? emitter_pdf(S, ray.d) : 0.f;       /* :297 pdf_emitter_direction */
+                emitted = emitter_eval(S, ray.d);                              /* :300 */
             }
+            float mis_bsdf = mis_weight(last_scatter_direction_pdf, emitter_pdf_);         /* :302 */
+            v3 c_new = count_direct ? vmul(thr_new, emitted) : vmul(vscale(thr_new, mis_bsdf), emitted);   /* :304-308 */
+            v3 c_old = count_direct ? vmul(thr_old, emitted) : vmul(vscale(thr_old, mis_bsdf), emitted);
+            L_new = adj ? vsub(L_new, c_new) : vadd(L_new, c_new);
+            L_old = vadd(L_old, c_old);
         }
         active_surface = active_surface && si.valid;                           /* :310 */
 
         /* ---- emitter sampling (:315-344) */
         if (S->use_nee) {
-            int active_e_surface = 0;          /* null BSDF has no Smooth lobe (:316) */
+            int smooth = active_surface && (si.shape >= 0);                    /* diffuse: Smooth; null: not (:316) */
+            int active_e_surface = smooth && (depth + 1 < S->max_depth);
             int sample_emitters = S->sample_emitters;                          /* :317 */
             specular_chain = specular_chain && !act_medium_scatter;            /* :318 */
             specular_chain = specular_chain || (act_medium_scatter && !sample_emitters);
@@ -1069,35 +1248,74 @@ static void sample_twostates(const rcv_scene_desc *S, const orc_medium *Mo, cons
             if (act_medium_scatter) { ref_p = mn.p; }
             if (active_surface) { ref_p = si.p; ref_n = si.n; }
             v3 em_old, em_new, ds_d; float ds_pdf;
+            pcg32 nee_sampler = *rng;                                          /* prbvolpath: sampler.clone() (Backward) */
             sample_emitter_twostates(S, Mo, Mn, rng, ref_p, ref_n, medium, active_e2,
-                                     &em_old, &em_new, &ds_d, &ds_pdf, cnt);   /* :325 */
+                                     &em_old, &em_new, &ds_d, &ds_pdf, NULL, NULL, cnt);   /* :325 */
+            v3 bsdf_val = V3(0, 0, 0); float bsdf_pdf = 0.f;                   /* :329-330 eval_pdf; eval_old == eval */
+            if (active_e_surface) diffuse_eval_pdf(&g_quads[si.shape], ray.d, ds_d, &bsdf_val, &bsdf_pdf);
             float phase_val_new = active_e_medium ? phase_eval(S, scatter_wi, ds_d) : 0.f;   /* :333 */
             float phase_val_old = active_e_medium ? phase_eval(S, scatter_wi, ds_d) : 0.f;   /* :334 */
-            float nee_weight_new = phase_val_new, nee_weight_old = phase_val_old;            /* :336-337 */
-            float nee_directional_pdf = phase_val_new;                         /* :339 (ds.delta is false) */
+            v3 nee_weight_new = active_e_surface ? bsdf_val : V3(phase_val_new, phase_val_new, phase_val_new);   /* :336-337 */
+            v3 nee_weight_old = active_e_surface ? bsdf_val : V3(phase_val_old, phase_val_old, phase_val_old);
+            float nee_directional_pdf = active_e_surface ? bsdf_pdf : phase_val_new;       /* :339 (ds.delta is false) */
             float mis_em = mis_weight(ds_pdf, nee_directional_pdf);            /* :341 */
             if (active) {                                                      /* :343-344 */
-                L_new = vadd(L_new, vmul(vscale(vscale(thr_new, nee_weight_new), mis_em), em_new));
-                L_old = vadd(L_old, vmul(vscale(vscale(thr_old, nee_weight_old), mis_em), em_old));
+                v3 c_new = vmul(vscale(vmul(thr_new, nee_weight_new), mis_em), em_new);
+                v3 c_old = vmul(vscale(vmul(thr_old, nee_weight_old), mis_em), em_old);
+                L_new = adj ? vsub(L_new, c_new) : vadd(L_new, c_new);
+                L_old = vadd(L_old, c_old);
+                if (adj) {                                                     /* the shadow ray again, with gradients */
+                    v3 adjoint = vmul(adj->dL, c_new), e1, e2, d2; float p2;
+                    sample_emitter_twostates(S, Mo, Mn, &nee_sampler, ref_p, ref_n, medium, active_e2, &e1, &e2, &d2, &p2,
+                                             &adjoint, adj->G, cnt);
+                }
             }
         }
 
-        /* ---- BSDF sampling (:346-379); the only BSDF is `null`:
-         * wo = -wi, pdf = 1, weight = 1, sampled_type = Null (a Delta type) [UPSTREAM null.cpp] */
-        (void) next_1d(rng, active_surface);                                   /* :347 */
-        (void) next_1d(rng, active_surface); (void) next_1d(rng, active_surface);   /* :348 next_2d */
-        /* bs.pdf = 1 > 0 (:349); prev_bsdf_delta = True -> throughput_old *= bsdf_weight = 1 (:355-357) */
+        /* ---- BSDF sampling (:346-379).  `null`: wo = -wi, pdf = 1, weight = 1, sampled_type = Null (a Delta type)
+         * [UPSTREAM null.cpp]; `diffuse`: cosine-weighted wo, weight = reflectance [UPSTREAM diffuse.cpp] */
+        float b1 = next_1d(rng, active_surface);                               /* :347 */
+        float b2x = next_1d(rng, active_surface), b2y = next_1d(rng, active_surface);   /* :348 next_2d */
+        (void) b1;
+        int is_null = active_surface && (si.shape < 0);
+        v3 bs_wo = ray.d; float bs_pdf = 1.f;
+        if (active_surface && !is_null) {
+            const rquad_t *qd = &g_quads[si.shape];
+            float ci = -dot3(qd->n, ray.d);
+            v3 wl = square_to_cosine_hemisphere(b2x, b2y);
+            float pdf = ORC_INV_PI * wl.z;
+            int ok = (ci > 0.f) && (pdf > 0.f);
+            bs_pdf = ok ? pdf : 0.f;
+            active_surface = active_surface && (bs_pdf > 0.f);                 /* :349 */
+            if (active_surface) {
+                v3 val_old = vscale(vscale(qd->refl, ORC_INV_PI), wl.z);       /* :351 eval_old(bs.wo) */
+                v3 w_old = V3(val_old.x / bs_pdf, val_old.y / bs_pdf, val_old.z / bs_pdf);   /* :354 */
+                thr_old = vmul(thr_old, w_old);                                /* :355 (not delta) */
+                thr_new = vmul(thr_new, qd->refl);                             /* :357 */
+                bs_wo = V3(fmaf(qd->s.x, wl.x, fmaf(qd->t.x, wl.y, qd->n.x * wl.z)),
+                           fmaf(qd->s.y, wl.x, fmaf(qd->t.y, wl.y, qd->n.y * wl.z)),
+                           fmaf(qd->s.z, wl.x, fmaf(qd->t.z, wl.y, qd->n.z * wl.z)));   /* si.to_world(bs.wo) */
+            }
+        }
+        /* null: bs.pdf = 1 > 0 (:349); prev_bsdf_delta = True -> throughput_old *= bsdf_weight = 1 (:355-357) */
         if (act_medium_scatter) {                                              /* :360-361 */
             float phase_val = phase_eval(S, scatter_wi, wo);
             float ratio = phase_val / phase_pdf;
             thr_old = vscale(thr_old, ratio);
         }
         if (active_surface) {                                                  /* :363-367 */
-            ray = spawn_ray(si.p, si.n, ray.d);   /* si.to_world(-si.wi) == ray.d */
+            ray = spawn_ray(si.p, si.n, bs_wo);   /* null: si.to_world(-si.wi) == ray.d */
             needs_intersection = 1;
-            /* non_null_bsdf = False: depth, last_scatter_event, valid_ray, specular_chain unchanged (:368-377) */
-            float dn = fmaf(si.n.x, ray.d.x, fmaf(si.n.y, ray.d.y, si.n.z * ray.d.z));
-            medium = (dn > 0.f) ? 0 : 1;                                       /* :378-379 */
+            if (!is_null) {                                                    /* non_null_bsdf (:368-377) */
+                depth += 1;
+                last_scatter_p = si.p;
+                last_scatter_direction_pdf = bs_pdf;
+                valid_ray = 1;
+                specular_chain = 0;                                            /* a Smooth, non-Delta lobe was sampled */
+            } else {
+                float dn = fmaf(si.n.x, ray.d.x, fmaf(si.n.y, ray.d.y, si.n.z * ray.d.z));
+                medium = (dn > 0.f) ? 0 : 1;                                   /* :378-379 */
+            }
         }
         active = active && (active_surface || active_medium);                  /* :380 */
     }
@@ -1122,7 +1340,7 @@ int orc_twostates_lanes(const rcv_scene_desc *S, const orc_medium *Mo, const orc
             lane_t ln = lane_setup(S, seed, spp, (uint64_t) i);                /* :104-112 */
             int valid;
             size_t k = (size_t) (i - (int64_t) lane_begin);
-            sample_twostates(S, Mo, Mn, &ln.rng, ln.ray, L_old + 3 * k, L_new + 3 * k, &valid, &cnt);   /* :115 */
+            sample_twostates(S, Mo, Mn, &ln.rng, ln.ray, L_old + 3 * k, L_new + 3 * k, &valid, &cnt, NULL);   /* :115 */
             if (pix) pix[k] = ln.pix;
             cnt.c[6]++;
         }
@@ -1158,7 +1376,7 @@ int orc_render_twostates(const rcv_scene_desc *S, const orc_medium *Mo, const or
                     size_t o = ((size_t) (p - (int64_t) p0) * ns + (k - spp_begin));
                     lane_t ln = lane_setup(S, seed, spp, idx);
                     int valid;
-                    sample_twostates(S, Mo, Mn, &ln.rng, ln.ray, Lo + 3 * o, Ln + 3 * o, &valid, &cnt);
+                    sample_twostates(S, Mo, Mn, &ln.rng, ln.ray, Lo + 3 * o, Ln + 3 * o, &valid, &cnt, NULL);
                     px[2 * o] = ln.fx; px[2 * o + 1] = ln.fy;
                     cnt.c[6]++;
                 }
@@ -1281,39 +1499,6 @@ double orc_loss_grad(int kind, const float *img, const float *ref, uint64_t n, f
 /* ------------------------------------------------------------------------- */
 /* VolpathSimpleIntegrator  (plugins/volpathsimple.py), use_drt = False        */
 /* ------------------------------------------------------------------------- */
-typedef struct {
-    double *g_sigma_t;   /* (nz,ny,nx,1) or NULL in primal mode */
-    double *g_albedo;    /* (nz,ny,nx,3) */
-    int atomic;          /* use omp atomic (multi-threaded) */
-} grad_sink;
-
-static inline void sink_add(double *a, double v, int atomic) {
-    if (atomic) {
-#pragma omp atomic
-        *a += v;
-    } else *a += v;
-}
-/* AD of the trilinear gather = scatter-add of w_corner * grad (SURVEY §2.3 gridvolume) */
-static void scatter_sigma_t(const rcv_scene_desc *S, const orc_medium *M, grad_sink *G, v3 p, float g, counters_t *cnt) {
-    tri_t T = tri_setup(S, M, p);
-    if (!T.inside) return;
-    for (int k = 0; k < 8; ++k)
-        sink_add(&G->g_sigma_t[tri_index(M, &T, k)], (double) (tri_weight(&T, k) * (S->sigma_t_scale * g)), G->atomic);
-    cnt->c[4]++;
-}
-static void scatter_albedo(const rcv_scene_desc *S, const orc_medium *M, grad_sink *G, v3 p, v3 g, counters_t *cnt) {
-    tri_t T = tri_setup(S, M, p);
-    if (!T.inside) return;
-    for (int k = 0; k < 8; ++k) {
-        float w = tri_weight(&T, k);
-        size_t o = tri_index(M, &T, k) * 3;
-        sink_add(&G->g_albedo[o], (double) (w * g.x), G->atomic);
-        sink_add(&G->g_albedo[o + 1], (double) (w * g.y), G->atomic);
-        sink_add(&G->g_albedo[o + 2], (double) (w * g.z), G->atomic);
-    }
-    cnt->c[5]++;
-}
-
 /* Medium::sample_interaction [UPSTREAM medium.cpp], single state (state `new`,
  * twostatemedium.py:135-136), global majorant */
 static void sample_interaction(const rcv_scene_desc *S, const orc_medium *M, const ray_t *ray, float sample,
@@ -1867,6 +2052,48 @@ int orc_vps_backward_drt(const rcv_scene_desc *S, const orc_medium *M, uint32_t 
     drt_opts o; o.use_drt = 1; o.use_drt_subsampling = use_drt_subsampling; o.use_drt_mis = use_drt_mis;
     return vps_backward_impl(S, M, seed_grad, spp_grad, spp_begin, spp_end, grad_img, film_w, grad_sigma_t, grad_albedo,
                              nthreads, &o);
+}
+
+/* RBIntegrator.render_backward [UPSTREAM] driving the adjoint the two-state integrator inherits — upstream
+ * PRBVolpathIntegrator.sample (plugins/twostatevolpath.py:11; used by cv_integrator.py:87-94 / metaintegrator.py:140-147
+ * when the scene gives no `adjoint_integrator`): pass 1 = the primal estimator of state `new` (sample_twostates with
+ * old == new), pass 2 = the same stream again with gradients (prb_adj).  Handles surfaces and the area light. */
+int orc_prb_backward(const rcv_scene_desc *S, const orc_medium *M, uint32_t seed_grad, uint32_t spp_grad,
+                     uint32_t spp_begin, uint32_t spp_end, const float *grad_img, const float *film_w,
+                     double *grad_sigma_t, double *grad_albedo, int nthreads) {
+    env_build(S);
+    uint64_t npix = (uint64_t) S->film_width * S->film_height;
+    if (nthreads < 1) nthreads = 1;
+    grad_sink G; G.g_sigma_t = grad_sigma_t; G.g_albedo = grad_albedo; G.atomic = nthreads > 1;
+#pragma omp parallel num_threads(nthreads)
+    {
+        counters_t cnt; memset(&cnt, 0, sizeof(cnt));
+#pragma omp for schedule(dynamic, 16)
+        for (int64_t p = 0; p < (int64_t) npix; ++p)
+            for (uint32_t k = spp_begin; k < spp_end; ++k) {
+                uint64_t idx = (uint64_t) p * spp_grad + k;
+                lane_t ln = lane_setup(S, seed_grad, spp_grad, idx);
+                pcg32 rng1 = ln.rng;                       /* sampler.clone() for pass 1 */
+                float Lo[3], L[3]; int valid;
+                sample_twostates(S, M, M, &rng1, ln.ray, Lo, L, &valid, &cnt, NULL);
+                v3 dL = V3(0, 0, 0);
+                footprint_t fp; film_footprint(S, ln.fx, ln.fy, &fp);
+                for (int q = 0; q < fp.n; ++q) {
+                    int pq = fp.pix[q];
+                    float w = film_w[pq];
+                    float d = (w == 0.f) ? 1.f : w;
+                    dL.x += fp.w[q] * (grad_img[3 * pq] / d);
+                    dL.y += fp.w[q] * (grad_img[3 * pq + 1] / d);
+                    dL.z += fp.w[q] * (grad_img[3 * pq + 2] / d);
+                }
+                prb_adj adj; adj.dL = dL; adj.L_total = V3(L[0], L[1], L[2]); adj.G = &G;
+                float L2o[3], L2[3];
+                sample_twostates(S, M, M, &ln.rng, ln.ray, L2o, L2, &valid, &cnt, &adj);
+                cnt.c[6] += 2;
+            }
+        counters_merge(&cnt);
+    }
+    return 0;
 }
 
 /* ------------------------------------------------------------------------- */

@@ -65,6 +65,10 @@ int orc_vps_render(const rcv_scene_desc *S, const orc_medium *M, uint32_t seed, 
 int orc_vps_backward(const rcv_scene_desc *S, const orc_medium *M, uint32_t seed_grad, uint32_t spp_grad,
                      uint32_t spp_begin, uint32_t spp_end, const float *grad_img, const float *film_w,
                      double *grad_sigma_t, double *grad_albedo, int nthreads);
+/* render_backward with upstream prbvolpath (the adjoint twostateprbvolpath inherits): surfaces + area light */
+int orc_prb_backward(const rcv_scene_desc *S, const orc_medium *M, uint32_t seed_grad, uint32_t spp_grad,
+                     uint32_t spp_begin, uint32_t spp_end, const float *grad_img, const float *film_w,
+                     double *grad_sigma_t, double *grad_albedo, int nthreads);
 /* use_drt = True (volpathsimple.py:33-36, :520-594, :623-778): oracle only, not part of the product ABI */
 int orc_vps_backward_drt(const rcv_scene_desc *S, const orc_medium *M, uint32_t seed_grad, uint32_t spp_grad,
                          uint32_t spp_begin, uint32_t spp_end, const float *grad_img, const float *film_w,

@@ -44,3 +44,27 @@ def make_medium(n: int, kind: str = "cube", perturb: float = 0.0):
     a = np.clip(a, 0.0, 1.0)
     return (np.ascontiguousarray(s[..., None], dtype=np.float32),
             np.ascontiguousarray(a, dtype=np.float32))
+
+
+def boxed_quads(lo=(-1.0, -1.0, -2.5), hi=(2.0, 2.0, 2.0), reflectance=0.5, light_size=1.0, light_radiance=10.0,
+                light_center=(0.5, 0.5)):
+    """BASELINE.json configs[0..1]: "cube in a box with an area light"  — six diffuse rectangles with
+    inward normals enclosing the medium's unit cube and the camera, and a square `area` light just below the ceiling,
+    facing down.  Returns the `quads` of scene.SceneConfig."""
+    x0, y0, z0 = (float(v) for v in lo)
+    x1, y1, z1 = (float(v) for v in hi)
+    lx, ly, lz = x1 - x0, y1 - y0, z1 - z0
+    r = (reflectance,) * 3 if np.ndim(reflectance) == 0 else tuple(reflectance)
+    q = lambda p0, eu, ev, **kw: dict(p0=p0, eu=eu, ev=ev, reflectance=r, **kw)
+    s = float(light_size)
+    cx, cz = light_center
+    return (
+        q((x0, y0, z0), (0, 0, lz), (lx, 0, 0)),          # floor, normal +y
+        q((x0, y1, z0), (lx, 0, 0), (0, 0, lz)),          # ceiling, normal -y
+        q((x0, y0, z0), (0, ly, 0), (0, 0, lz)),          # x = x0, normal +x
+        q((x1, y0, z0), (0, 0, lz), (0, ly, 0)),          # x = x1, normal -x
+        q((x0, y0, z0), (lx, 0, 0), (0, ly, 0)),          # z = z0, normal +z
+        q((x0, y0, z1), (0, ly, 0), (lx, 0, 0)),          # z = z1, normal -z
+        dict(p0=(cx - s / 2, y1 - 0.01, cz - s / 2), eu=(s, 0, 0), ev=(0, 0, s), reflectance=(0.0, 0.0, 0.0),
+             radiance=(light_radiance,) * 3 if np.ndim(light_radiance) == 0 else tuple(light_radiance)),   # light, normal -y
+    )
