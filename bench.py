@@ -14,6 +14,8 @@ and ms per iteration.
 Configurations (BASELINE.json `configs`):
     c2          (default, the headline) 256^3 cube, 512x512, 64 spp per GPU, box filter, one majorant, use_drt = False
     c1          64^3 cube, 128x128, 16 spp — the L2-resident configuration (roofline against the measured L2 gather peak)
+    c1box/c2box the same cubes inside a diffuse box with an area light, as BASELINE.json words configs[0..1]: surface
+                transport and the inherited prbvolpath adjoint (the environment-lit c1 / c2 use volpathsimple)
     refdefault  what the reference's volume experiments run (experiments.py:20-133): use_drt + sub-sampling + MIS,
                 gaussian filter, majorant supergrid (factor 8), batch sensor of 8 views, HG g = 0.877 — C2-sized
     c3          plume 256^3, 1024x1024, 256 spp      (strong scaling: the spp of ONE image split over the GPUs)
@@ -48,15 +50,22 @@ CONFIGS = {
     "c1": dict(grid=64, res=128, spp=16, kind="cube", scaling="weak"),
     "refdefault": dict(grid=256, res=256, view_width=128, views=8, spp=64, kind="cube", scaling="weak", rfilter="gaussian",
                        hg=0.877, majorant_factor=8, use_drt=True),
+    # BASELINE.json configs[0..1] AS WORDED: the cube in a diffuse box with an area light (surface transport, the
+    # adjoint the two-state integrator inherits from upstream prbvolpath: RCV_ADJOINT_PRBVOLPATH)
+    "c1box": dict(grid=64, res=128, spp=16, kind="cube", scaling="weak", box=True),
+    "c2box": dict(grid=256, res=512, spp=64, kind="cube", scaling="weak", box=True),
     "c3": dict(grid=256, res=1024, spp=256, kind="plume", scaling="strong"),
     "c4": dict(grid=512, res=1024, spp=512, kind="dense", scaling="strong"),
+    # BASELINE.json configs[4]: the full optimisation loop (optimize.run_opt through the plugin layer: mi.render, the
+    # autograd boundary, recursive CV + Welford state, mi.ad.Adam on the device); --steps = iterations (default 200)
+    "c5": dict(grid=256, res=1024, spp=128, kind="plume", scaling="strong", loop=True),
 }
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default 5; c5: iterations of the loop, default 200)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
@@ -68,6 +77,7 @@ def parse():
     ap.add_argument("--views", type=int, default=None, help="batch sensor: views side by side on one film")
     ap.add_argument("--spp", type=int, default=None, help="samples per pixel (per GPU when --scaling weak)")
     ap.add_argument("--kind", default=None)
+    ap.add_argument("--box", action="store_true", default=None, help="diffuse box + area light around the medium (prbvolpath adjoint)")
     ap.add_argument("--hg", type=float, default=None, help="Henyey-Greenstein g (0 = isotropic)")
     ap.add_argument("--majorant-factor", type=int, default=None, help="majorant supergrid factor of the measured step (0 = one majorant)")
     ap.add_argument("--tracer", type=int, default=3, help="3 pool (default), 0 wavefront, 1 simple, 2 batch")
@@ -77,6 +87,7 @@ def parse():
     ap.add_argument("--no-drt", action="store_true", help="skip the informational use_drt=True timing")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1, weak scaling: skip the strong-scaling leg")
     ap.add_argument("--no-baseline-method", action="store_true", help="skip the method=baseline timing")
     ap.add_argument("--rfilter", default=None, choices=["box", "gaussian"], help="reconstruction filter of the film (headline: box)")
     ap.add_argument("--supergrid", type=int, nargs="*", default=None,
@@ -85,15 +96,20 @@ def parse():
     ap.add_argument("--cpu-sample-spp", type=int, default=0, help="spp range of the CPU sample (0 = auto: ~15 s of CPU work)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target duration of one CPU sample")
     a = ap.parse_args()
-    cfg = dict(rfilter="box", hg=0.0, views=1, view_width=None, majorant_factor=0, use_drt=False)
+    cfg = dict(rfilter="box", hg=0.0, views=1, view_width=None, majorant_factor=0, use_drt=False, box=False, loop=False)
     cfg.update(CONFIGS[a.config])
     for k, v in cfg.items():
         if getattr(a, k, None) is None:
             setattr(a, k, v)
+    a.loop = bool(CONFIGS[a.config].get("loop", False))
+    if a.steps is None:
+        a.steps = 200 if a.loop else 5
     if a.view_width is None:
         a.view_width = a.res
     if a.supergrid is None:
         a.supergrid = [8, 32] if a.config == "c2" else []
+    if a.box:
+        a.use_drt = False           # volpathsimple's DRT term does not exist in the inherited adjoint
     return a
 
 
@@ -110,9 +126,11 @@ def workload_name(a, n_gpus):
     film = f"{a.view_width * a.views}x{a.res}" + (f" ({a.views} views)" if a.views > 1 else "")
     phase = "isotropic" if a.hg == 0.0 else f"HG g={a.hg}"
     maj = "one majorant" if not a.majorant_factor else f"majorant supergrid factor {a.majorant_factor}"
+    light = "in a diffuse box [-1,2]x[-1,2]x[-2.5,2] (reflectance 0.5) with a 1x1 area light (radiance 10)" if a.box else \
+        "constant environment emitter"
+    adj = "adjoint prbvolpath (inherited)" if a.box else f"adjoint volpathsimple use_drt={bool(a.use_drt)}"
     return (f"synthetic {a.kind} {a.grid}^3 sigma_t+albedo two-state grid, {film}, {spp_total} spp "
-            f"({per}/GPU), cv_ps, constant environment emitter, {a.rfilter} filter, {phase}, {maj}, max_depth=rr_depth=64, "
-            f"adjoint volpathsimple use_drt={bool(a.use_drt)}")
+            f"({per}/GPU), cv_ps, {light}, {a.rfilter} filter, {phase}, {maj}, max_depth=rr_depth=64, {adj}")
 
 
 def config_keys(a, n_gpus):
@@ -122,7 +140,7 @@ def config_keys(a, n_gpus):
     return {"workload": workload_name(a, n_gpus), "name": a.config, "grid": a.grid, "film": [W, H], "spp_total": spp_total,
             "spp_per_gpu": ranges[0][1] - ranges[0][0], "paths_per_step": W * H * spp_total * 3,
             "parallelism": f"spp-shard x{n_gpus}", "rfilter": a.rfilter, "use_drt": bool(a.use_drt),
-            "majorant_factor": a.majorant_factor, "views": a.views, "phase_g": a.hg}
+            "majorant_factor": a.majorant_factor, "views": a.views, "phase_g": a.hg, "box": bool(a.box)}
 
 
 # ----------------------------------------------------------------------------
@@ -195,6 +213,9 @@ def scene_config(a):
     """The bench scene: SURVEY.md 8(d)'s camera / medium box; the configuration decides filter, phase function and views."""
     from recursive_control_variates_b200.scene import SceneConfig, look_at
     kw = dict(width=a.view_width * a.views, height=a.res, rfilter=a.rfilter)
+    if a.box:
+        from recursive_control_variates_b200.synthetic import boxed_quads
+        kw["quads"] = boxed_quads()
     if a.hg != 0.0:
         kw.update(phase="hg", phase_g=a.hg)
     if a.views > 1:           # the reference's batch sensor (experiments.py:28-50): cameras on a circle around the medium
@@ -203,6 +224,12 @@ def scene_config(a):
                                             0.5 + 2 * math.sin(2 * math.pi / a.views * i + 0.1)], [0.5, 0.5, 0.5], [0, 1, 0])
                                    for i in range(a.views)])
     return SceneConfig(**kw)
+
+
+def adjoint_kind(a):
+    """RCV_ADJOINT_*: volpathsimple for the environment-lit configurations (experiments.py:131), the inherited prbvolpath
+    adjoint where the scene has surfaces / an area light (volpathsimple.py:24-30 refuses those)."""
+    return 1 if a.box else 0
 
 
 def rel_l2(x, y):
@@ -236,7 +263,10 @@ def cpu_iteration_sample(a, n_gpus, sample_spp, threads, keep=None, use_drt=None
     t0 = time.perf_counter()
     acc = O.render_twostates_accum(desc, mo, mn, seed, spp, 0, sample_spp, threads=threads)
     t1 = time.perf_counter()
-    grads = O.vps_backward(desc, mn, seed_grad, spp, grad_img, 0, sample_spp, threads=threads, film_w=film_w, use_drt=drt)
+    if a.box:
+        grads = O.prb_backward(desc, mn, seed_grad, spp, grad_img, 0, sample_spp, threads=threads, film_w=film_w)
+    else:
+        grads = O.vps_backward(desc, mn, seed_grad, spp, grad_img, 0, sample_spp, threads=threads, film_w=film_w, use_drt=drt)
     t2 = time.perf_counter()
     if keep is not None:
         keep.update(acc_old=acc[0], acc_new=acc[1], g_sigma=grads[0], g_albedo=grads[1], grad_img=grad_img, film_w=film_w,
@@ -307,7 +337,7 @@ def parity_block(a, ctx, dev, keep1, keepN, keep_drt, spp_total):
     out["img_rel_l2_new"] = rel_l2(dev_img(g_new.cpu().numpy()), dev_img(k["acc_new"]))
     gi, fw = cu(k["grad_img"]), cu(k["film_w"])
     ctx.grad_zero()
-    ctx.render_backward(k["seed_grad"], spp_total, gi, 0, k["sample_spp"], film_w=fw)
+    ctx.render_backward(k["seed_grad"], spp_total, gi, 0, k["sample_spp"], film_w=fw, adjoint=adjoint_kind(a))
     gs, ga = ctx.grad_read()
     out["grad_sigma_rel_l2"] = rel_l2(gs.cpu().numpy(), k["g_sigma"])
     out["grad_albedo_rel_l2"] = rel_l2(ga.cpu().numpy(), k["g_albedo"])
@@ -380,7 +410,11 @@ def run_ours(a):
     paths_per_step = npix * spp_total * 3          # primal + adjoint pass 1 + adjoint pass 2, all ranks
     side = torch.cuda.Stream(device=dev) if world > 1 else None
 
+    lay = {"total": spp_total, "b": spp_b, "e": spp_e}       # the sample range this rank renders (the strong-scaling leg swaps it)
+
     def step(i, marks=None, method="cv_ps"):
+        spp_total, spp_b, spp_e = lay["total"], lay["b"], lay["e"]
+
         def mark(name):
             if marks is not None:
                 e = torch.cuda.Event(enable_timing=True); e.record(); marks.append((name, e))
@@ -423,7 +457,7 @@ def run_ours(a):
         mark("develop_cv_loss")
         if world > 1:
             torch.cuda.current_stream().wait_stream(side)
-        ctx.render_backward(seed_grad, spp_total, g, spp_b, spp_e, film_w=fw)   # adjoint_integrator.render_backward
+        ctx.render_backward(seed_grad, spp_total, g, spp_b, spp_e, film_w=fw, adjoint=adjoint_kind(a))   # adjoint_integrator.render_backward
         mark("adjoint")
         if world > 1:
             dist.all_reduce(ctx.grad_packed())
@@ -501,7 +535,8 @@ def run_ours(a):
     g_img = torch.full((H, W, 3), 1.0 / (npix * 3), device=dev)
     fw_all = ctx.film_weights(tea32(SEED0, 1)[0], spp_total)               # weights of ALL samples, computed once outside the timing
     k1_ms, k1_c = time_kernel(lambda: ctx.render_twostates_accum(SEED0, spp_total, spp_b, spp_e, out=acc))
-    k6_ms, k6_c = time_kernel(lambda: ctx.render_backward(tea32(SEED0, 1)[0], spp_total, g_img, spp_b, spp_e, film_w=fw_all))
+    k6_ms, k6_c = time_kernel(lambda: ctx.render_backward(tea32(SEED0, 1)[0], spp_total, g_img, spp_b, spp_e, film_w=fw_all,
+                                                          adjoint=adjoint_kind(a)))
     lanes = npix * spp_local
     # algorithmic bytes (SURVEY.md §8d / DESIGN.md §5)
     k1_bytes = k1_c[0] * 64 + k1_c[1] * 192 + lanes * (16 + 32)
@@ -509,7 +544,7 @@ def run_ours(a):
     kernels = {
         "twostate_primal": {"ms": k1_ms, "algorithmic_gb": k1_bytes / 1e9, "gbs": k1_bytes / k1_ms / 1e6,
                             "collisions": k1_c[0], "scatters": k1_c[1], "mpaths_s": lanes / k1_ms / 1e3},
-        "volpathsimple_adjoint": {"ms": k6_ms, "algorithmic_gb": k6_bytes / 1e9, "gbs": k6_bytes / k6_ms / 1e6,
+        ("prbvolpath_adjoint" if a.box else "volpathsimple_adjoint"): {"ms": k6_ms, "algorithmic_gb": k6_bytes / 1e9, "gbs": k6_bytes / k6_ms / 1e6,
                                   "collisions": k6_c[2], "scatters": k6_c[3], "grad_sites": k6_c[4] + k6_c[5],
                                   "mpaths_s": 2 * lanes / k6_ms / 1e3},
     }
@@ -549,6 +584,25 @@ def run_ours(a):
                                                   "(profiles/r38_convergence.json, scripts/demo_convergence.py, C1 recovery): the "
                                                   "baseline needs ~4.5x the samples for the same variance"}
 
+    # ---- N > 1: the same image with the spp of ONE job split over the GPUs (north_star's sharding; the headline above is
+    # weak scaling: `spp` per GPU)
+    strong = None
+    if world > 1 and a.scaling == "weak" and not a.no_strong:
+        s_total = a.spp
+        s_b, s_e = spp_layout(argparse.Namespace(spp=a.spp, scaling="strong"), n_gpus)[1][rank]
+        lay.update(total=s_total, b=s_b, e=s_e)
+        for i in range(2):
+            step(a.warmup + a.steps + i)
+        s_ms, _ = timed(max(3, min(a.steps, 5)), a.warmup + a.steps + 2)
+        s_marks = []
+        step(a.warmup + a.steps + 50, s_marks)
+        torch.cuda.synchronize()
+        s_ph = {name: e_prev.elapsed_time(e_cur) for (_, e_prev), (name, e_cur) in zip(s_marks[:-1], s_marks[1:])}
+        strong = {"spp_total": s_total, "spp_per_gpu": s_e - s_b, "ms_per_step": s_ms,
+                  "value": npix * s_total * 3 / (s_ms * 1e-3) / 1e6, "unit": UNIT, "phases_ms_rank0": s_ph,
+                  "note": "strong scaling: the %d spp of one %s image split over %d GPUs (same step, same kernels)" % (s_total, a.config, n_gpus)}
+        lay.update(total=spp_total, b=spp_b, e=spp_e)
+
     # ---- the same iteration with the majorant supergrid + DDA (reference `use_majorant_supergrid`), informational
     supergrid = []
     for sg_f in [f for f in a.supergrid if f > 1 and a.grid % f == 0 and f != a.majorant_factor]:
@@ -563,7 +617,7 @@ def run_ours(a):
     # ---- the same iteration with the adjoint's DRT term (volpathsimple.py:39-47: use_drt / use_drt_subsampling /
     # use_drt_mis all True, the reference's default), informational unless the configuration measures it
     drt_info = None
-    if not a.use_drt and not a.no_drt:
+    if not a.use_drt and not a.no_drt and not a.box:
         ctx.set_drt(True)
         for i in range(2):
             step(a.warmup + a.steps + i)
@@ -605,7 +659,7 @@ def run_ours(a):
             film_w.zero_()
             fw_ = ctx.film_weights(tea32(seed, 1)[0], spp_total, spp_b, spp_e, out=film_w)
             dist.all_reduce(fw_)
-            ctx.render_backward(tea32(seed, 1)[0], spp_total, g_, spp_b, spp_e, film_w=fw_)
+            ctx.render_backward(tea32(seed, 1)[0], spp_total, g_, spp_b, spp_e, film_w=fw_, adjoint=adjoint_kind(a))
             dist.all_reduce(ctx.grad_packed())
             if rank == 0:
                 gs_, ga_ = ctx.grad_read()
@@ -636,7 +690,8 @@ def run_ours(a):
 
         def e2e_step(i, reset=False):
             seed = SEED0 + i
-            ctx.cv_iteration_host(hs, ha, href, seed, spp_total, tea32(seed, 1)[0], spp_total, himg, hloss, hgs, hga, reset=reset)
+            ctx.cv_iteration_host(hs, ha, href, seed, spp_total, tea32(seed, 1)[0], spp_total, himg, hloss, hgs, hga, reset=reset,
+                                  adjoint=adjoint_kind(a))
 
         e2e_step(0, reset=True); e2e_step(1)
         torch.cuda.synchronize()
@@ -692,8 +747,9 @@ def run_ours(a):
                          f"{t_primal:.2f}s + volpathsimple adjoint {t_adj:.2f}s",
                "seconds": tt}
         # the adjoint with the other setting of use_drt on a third of that range
-        cpu_iteration_sample(a, n_gpus, max(1, sample_spp // 3), threads, keep=keepD, use_drt=not a.use_drt)
-        parity = parity_block(a, ctx, dev, keep1 if keep1 else None, keepN, keepD, spp_total)
+        if not a.box:
+            cpu_iteration_sample(a, n_gpus, max(1, sample_spp // 3), threads, keep=keepD, use_drt=not a.use_drt)
+        parity = parity_block(a, ctx, dev, keep1 if keep1 else None, keepN, keepD if keepD else None, spp_total)
 
     if rank == 0:
         cfg = config_keys(a, n_gpus)          # the same keys and values as the reference arm prints
@@ -705,7 +761,72 @@ def run_ours(a):
                "dtype": "f32", "data": "synthetic", "config": cfg, "run": run_info,
                "clocks": clocks, "gpu_launches": int(cnt[7]), "roofline": roofline, "kernels": kernels,
                "phases_ms_rank0": phases, "e2e": e2e, "e2e_device_optimizer": e2e_dev, "cpu_baseline": cpu, "parity": parity,
-               "baseline_method": baseline_method, "supergrid": supergrid, "drt": drt_info}
+               "baseline_method": baseline_method, "strong": strong, "supergrid": supergrid, "drt": drt_info}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_loop(a):
+    """--config c5: `--steps` iterations of optimize.run_opt (optimize.py:104-143 of the reference, unchanged in
+    structure) through the plugin layer, spp-sharded over the ranks: twostateprbvolpath inside `meta` (method cv_ps),
+    volpathsimple as adjoint_integrator, L1 loss, mi.ad.Adam + clamp on the device.  The whole loop is timed (wall clock,
+    device synchronised, max over ranks); the reference's own per-iteration stopwatch (benchmark = True: iterations
+    > 16) is reported beside it."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from recursive_control_variates_b200 import experiments
+    from recursive_control_variates_b200 import mitsuba_compat as mi
+    from recursive_control_variates_b200.optimize import run_opt
+    n_steps = a.steps
+    spp_total, ranges = spp_layout(a, world)
+    p = experiments.scene_synthetic("cv_ps", None, grid=a.grid, init_grid=a.grid, film=(a.res, a.res), spp=spp_total, kind=a.kind,
+                                    n_steps=n_steps, upsample=())
+    p["recomp_freq"] = max(n_steps, 1)            # one checkpoint render (iteration 0), as a run with recomp_freq = n_steps
+    p["spp_ref"], p["ref_passes"], p["spp_inf"] = spp_total, 1, min(spp_total, 64)
+    p["adjoint_integrator"] = mi.load_dict({"type": "volpathsimple", "max_depth": 64, "rr_depth": 64, "use_drt": bool(a.use_drt)})
+    sampler = ClockSampler(local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    res = run_opt(p)
+    barrier()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    te = torch.tensor([dt], device=torch.device("cuda", local))
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    dt = float(te.item())
+    if rank == 0:
+        W = H = a.res
+        paths = W * H * spp_total * 3
+        rt = res["runtime"][17:] if n_steps > 17 else res["runtime"][:0]
+        cfg = config_keys(a, world)
+        cfg["workload"] = (f"full optimisation loop: {n_steps} iterations of optimize.run_opt (cv_ps, L1, Adam lr 5e-3, clamp), "
+                           f"{a.kind} {a.grid}^3 grids from a constant start, {W}x{H}, {spp_total} spp ({ranges[0][1] - ranges[0][0]}/GPU), "
+                           f"adjoint volpathsimple use_drt={bool(a.use_drt)}; includes scene set-up, the reference render and one checkpoint render")
+        out = {"metric": METRIC, "value": paths * n_steps / dt / 1e6, "unit": UNIT, "n_gpus": world, "steps": n_steps, "warmup": 0,
+               "ms_per_step": dt / max(n_steps, 1) * 1e3, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
+               "dtype": "f32", "data": "synthetic", "config": cfg, "clocks": clocks, "loop_seconds": dt,
+               "stopwatch_ms": {"render": float(rt[:, 0].mean()) if len(rt) else None,
+                                "backward_step": float(rt[:, 1].mean()) if len(rt) else None,
+                                "note": "optimize.py's own Stopwatch (iterations > 16): mi.render + loss, then backward + Adam + clamp"},
+               "loss_first_last": [float(res["loss"][0]), float(res["loss"][-1])],
+               "gpu_launches": int(mi._any_context().counters(False)[7])}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -715,5 +836,7 @@ if __name__ == "__main__":
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.loop:
+        run_loop(args)
     else:
         run_ours(args)

@@ -85,7 +85,7 @@ class IterHostArgs(C.Structure):
         ("seed_grad", C.c_uint32), ("spp_grad", C.c_uint32),
         ("loss_kind", C.c_int32),
         ("beta1", C.c_float), ("beta2", C.c_float),
-        ("warmup", C.c_int32), ("reset", C.c_int32),
+        ("warmup", C.c_int32), ("reset", C.c_int32), ("adjoint_kind", C.c_int32),
         ("img_out", C.c_void_p),
         ("loss_out", C.c_void_p),
         ("grad_sigma_t_out", C.c_void_p),

@@ -358,6 +358,15 @@ int rcv_scene_set(rcv_ctx *c, const rcv_scene_desc *d) {
         return fail(RCV_ERR_ARG, "unknown emitter type");
     if (d->emitter_type == RCV_EMITTER_ENVMAP && (!d->envmap_rgb || d->env_width < 1 || d->env_height < 2))
         return fail(RCV_ERR_ARG, "envmap: a host pointer to (env_height >= 2, env_width >= 1, 3) texels is required");
+    if (d->n_quads > RCV_MAX_QUADS) return fail(RCV_ERR_ARG, "too many rectangles (RCV_MAX_QUADS)");
+    for (uint32_t k = 0; k < d->n_quads; ++k) {
+        const rcv_quad &q = d->quads[k];
+        double uu = 0, vv = 0, uv = 0;
+        for (int i = 0; i < 3; ++i) { uu += (double) q.eu[i] * q.eu[i]; vv += (double) q.ev[i] * q.ev[i]; uv += (double) q.eu[i] * q.ev[i]; }
+        if (!(uu > 0) || !(vv > 0) || uv * uv > 1e-10 * uu * vv) return fail(RCV_ERR_ARG, "rectangle: the edges must be non-zero and perpendicular");
+    }
+    if (d->emitter_type == RCV_EMITTER_AREA && (d->area_quad < 0 || (uint32_t) d->area_quad >= d->n_quads))
+        return fail(RCV_ERR_ARG, "area light: area_quad must index one of the rectangles");
     float4 *e_data = nullptr; float *e_m = nullptr, *e_c = nullptr, *e_p = nullptr;
     if (d->emitter_type == RCV_EMITTER_ENVMAP) {
         if (int r = use_device(c)) return r;
@@ -501,7 +510,10 @@ int rcv_render_twostates(rcv_ctx *c, uint32_t seed, uint32_t spp, uint32_t spp_b
                          float *accum_new) {
     if (int r = check_render(c, spp, spp_begin, spp_end)) return r;
     if (!accum_old || !accum_new) return fail(RCV_ERR_ARG, "null accumulator");
-    CK(launch_twostates(c->cfg(), c->S, c->gridk(), 0, seed, spp, spp_begin, spp_end, (float4 *) accum_old, (float4 *) accum_new));
+    if (c->S.n_quads > 0)      // surfaces: the machine of rcv_surface_wf.cuh
+        CK(launch_surface_primal(c->cfg(), c->S, c->gridk(), 0, seed, spp, spp_begin, spp_end, (float4 *) accum_old, (float4 *) accum_new));
+    else
+        CK(launch_twostates(c->cfg(), c->S, c->gridk(), 0, seed, spp, spp_begin, spp_end, (float4 *) accum_old, (float4 *) accum_new));
     return RCV_OK;
 }
 
@@ -509,8 +521,12 @@ int rcv_render_primal(rcv_ctx *c, int state, uint32_t seed, uint32_t spp, uint32
     if (int r = check_render(c, spp, spp_begin, spp_end)) return r;
     if (!accum) return fail(RCV_ERR_ARG, "null accumulator");
     if (state != 0 && state != 1) return fail(RCV_ERR_ARG, "state must be 0 (old) or 1 (new)");
-    CK(launch_twostates(c->cfg(), c->S, c->gridk(), state == 0 ? 1 : 2, seed, spp, spp_begin, spp_end, (float4 *) accum,
-                        (float4 *) accum));
+    if (c->S.n_quads > 0)
+        CK(launch_surface_primal(c->cfg(), c->S, c->gridk(), state == 0 ? 1 : 2, seed, spp, spp_begin, spp_end, (float4 *) accum,
+                                 (float4 *) accum));
+    else
+        CK(launch_twostates(c->cfg(), c->S, c->gridk(), state == 0 ? 1 : 2, seed, spp, spp_begin, spp_end, (float4 *) accum,
+                            (float4 *) accum));
     return RCV_OK;
 }
 
@@ -565,9 +581,27 @@ int rcv_render_backward(rcv_ctx *c, int adjoint_kind, uint32_t seed_grad, uint32
 int rcv_render_backward_weighted(rcv_ctx *c, int adjoint_kind, uint32_t seed_grad, uint32_t spp_grad, uint32_t spp_begin,
                                  uint32_t spp_end, const float *grad_img, const float *film_w) {
     if (int r = check_render(c, spp_grad, spp_begin, spp_end)) return r;
-    if (adjoint_kind != RCV_ADJOINT_VOLPATHSIMPLE) return fail(RCV_ERR_ARG, "unknown adjoint integrator");
+    if (adjoint_kind != RCV_ADJOINT_VOLPATHSIMPLE && adjoint_kind != RCV_ADJOINT_PRBVOLPATH)
+        return fail(RCV_ERR_ARG, "unknown adjoint integrator");
     if (!grad_img) return fail(RCV_ERR_ARG, "null grad_img");
+    if (adjoint_kind == RCV_ADJOINT_VOLPATHSIMPLE && (c->S.n_quads > 0 || c->S.emitter == RCV_EMITTER_AREA))
+        return fail(RCV_ERR_STATE, "volpathsimple handles neither surfaces nor area lights (volpathsimple.py:24-30): use RCV_ADJOINT_PRBVOLPATH");
     if (int r = ensure_film_w(c)) return r;
+    if (adjoint_kind == RCV_ADJOINT_PRBVOLPATH) {
+        // upstream prbvolpath (the adjoint twostateprbvolpath inherits): both walks on the surface machine
+        LaunchCfg cfg = c->cfg();
+        if (!film_w) {
+            CK(launch_film_weights(cfg, c->S, seed_grad, spp_grad, 0, spp_grad, c->film_w, true));
+            film_w = c->film_w;
+        }
+        if (int r = ensure_gbrick(c)) return r;
+        GradK D = c->gradk();
+        CK(launch_prb_backward(cfg, c->S, c->gridk(), D, seed_grad, spp_grad, spp_begin, spp_end, grad_img, film_w));
+#if RCV_GRAD_BRICKS
+        CK(launch_unbrick(cfg, D, c->nx, c->ny, c->nz));
+#endif
+        return RCV_OK;
+    }
     // deep paths (max_depth = -1 ...) would need an unbounded vertex arena: use the replaying schedule for them
     const int saved_tracer = c->tracer;
     if ((c->tracer == RCV_TRACER_POOL || c->tracer == RCV_TRACER_WAVEFRONT) && c->S.max_depth >= 4096) c->tracer = RCV_TRACER_BATCH;
@@ -622,7 +656,10 @@ int rcv_render_backward_weighted(rcv_ctx *c, int adjoint_kind, uint32_t seed_gra
 int rcv_render_adjoint_primal(rcv_ctx *c, int adjoint_kind, uint32_t seed, uint32_t spp, uint32_t spp_begin, uint32_t spp_end,
                               float *accum) {
     if (int r = check_render(c, spp, spp_begin, spp_end)) return r;
+    if (adjoint_kind == RCV_ADJOINT_PRBVOLPATH) return rcv_render_primal(c, 1, seed, spp, spp_begin, spp_end, accum);
     if (adjoint_kind != RCV_ADJOINT_VOLPATHSIMPLE) return fail(RCV_ERR_ARG, "unknown adjoint integrator");
+    if (c->S.n_quads > 0 || c->S.emitter == RCV_EMITTER_AREA)
+        return fail(RCV_ERR_STATE, "volpathsimple handles neither surfaces nor area lights (volpathsimple.py:24-30)");
     if (!accum) return fail(RCV_ERR_ARG, "null accumulator");
     CK(launch_vps_primal(c->cfg(), c->S, c->gridk(), seed, spp, spp_begin, spp_end, (float4 *) accum));
     return RCV_OK;
@@ -744,7 +781,7 @@ int rcv_cv_iteration_host(rcv_ctx *c, const rcv_iter_host_args *a) {
     E.it += 1;
     if (int r = rcv_loss_grad(c, a->loss_kind, cv, E.ref, n3, E.loss, E.grad_img)) return r;   // optimize.py:110-122
     if (int r = rcv_grad_zero(c)) return r;
-    if (int r = rcv_render_backward(c, RCV_ADJOINT_VOLPATHSIMPLE, a->seed_grad, a->spp_grad, 0, a->spp_grad, E.grad_img)) return r;
+    if (int r = rcv_render_backward(c, a->adjoint_kind, a->seed_grad, a->spp_grad, 0, a->spp_grad, E.grad_img)) return r;
     // device -> host: image, loss, gradients
     CK(cudaMemcpyAsync(a->img_out, cv, n3 * sizeof(float), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(a->loss_out, E.loss, sizeof(float), cudaMemcpyDeviceToHost, st));

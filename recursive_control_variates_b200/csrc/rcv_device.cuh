@@ -44,6 +44,12 @@ namespace rcv {
 // ----------------------------------------------------------------------------
 // kernel-side scene / medium parameter blocks (passed by value)
 // ----------------------------------------------------------------------------
+// A rectangle with its derived quantities (rcv_scene.h computes them in binary32, fixed operation order)
+struct QuadK {
+    float p0[3], eu[3], ev[3], n[3], s[3], t[3], refl[3], rad[3];
+    float inv_eu2, inv_ev2, inv_area;
+};
+
 struct SceneK {
     uint32_t W, H;
     float rcpW, rcpH;
@@ -71,6 +77,9 @@ struct SceneK {
     const float *env_cdf_c;   // (env_h - 1, env_w + 1): cdf over the cells of a row
     const float *env_pdf;     // (env_h - 1, env_w): density of (u, v) on the unit square
     float env_R[9];           // emitter frame -> world (row-major)
+    // rectangles outside the medium's box (diffuse BSDF; quads[area_quad] carries the `area` light when emitter == 2)
+    int n_quads, area_quad;
+    QuadK quads[8];
 };
 
 // Packed medium state in HBM:

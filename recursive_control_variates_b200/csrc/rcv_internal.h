@@ -31,6 +31,11 @@ cudaError_t launch_vps_backward(const LaunchCfg &cfg, const SceneK &S, const Gri
                                 uint32_t spp_grad, uint32_t spp_begin, uint32_t spp_end, uint32_t alt_seed,
                                 const float *grad_img, const float *film_w);
 size_t vps_backward_slots(const LaunchCfg &cfg);
+// ---- scenes with rectangles, and the adjoint inherited from upstream prbvolpath (rcv_surface.cu)
+cudaError_t launch_surface_primal(const LaunchCfg &cfg, const SceneK &S, const GridKS &G, int mode, uint32_t seed, uint32_t spp,
+                                  uint32_t spp_begin, uint32_t spp_end, float4 *acc_old, float4 *acc_new);
+cudaError_t launch_prb_backward(const LaunchCfg &cfg, const SceneK &S, const GridKS &G, const GradK &D, uint32_t seed_grad,
+                                uint32_t spp_grad, uint32_t spp_begin, uint32_t spp_end, const float *grad_img, const float *film_w);
 cudaError_t launch_film_weights(const LaunchCfg &cfg, const SceneK &S, uint32_t seed, uint32_t spp, uint32_t spp_begin,
                                 uint32_t spp_end, float *film_w, bool zero);
 

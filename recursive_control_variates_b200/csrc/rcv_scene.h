@@ -32,6 +32,28 @@ inline void scene_from_desc(const rcv_scene_desc &d, SceneK &S) {
     S.env_w = d.env_width; S.env_h = d.env_height;
     for (int i = 0; i < 9; ++i) S.env_R[i] = d.env_to_world[i];
     S.env_data = nullptr; S.env_cdf_m = nullptr; S.env_cdf_c = nullptr; S.env_pdf = nullptr;   // set by the owner of the tables
+    // rectangles: normal, shading frame and reciprocals in binary32 with this operation order (the oracle does the same)
+    S.n_quads = (int) d.n_quads; S.area_quad = d.area_quad;
+    auto dot = [](const float *a, const float *b) { return std::fmaf(a[0], b[0], std::fmaf(a[1], b[1], a[2] * b[2])); };
+    auto cross = [](const float *a, const float *b, float *c) {
+        c[0] = std::fmaf(a[1], b[2], -(a[2] * b[1])); c[1] = std::fmaf(a[2], b[0], -(a[0] * b[2])); c[2] = std::fmaf(a[0], b[1], -(a[1] * b[0]));
+    };
+    for (int k = 0; k < 8; ++k) {
+        QuadK &q = S.quads[k];
+        q = QuadK{};
+        if (k >= S.n_quads) continue;
+        const rcv_quad &r = d.quads[k];
+        for (int i = 0; i < 3; ++i) { q.p0[i] = r.p0[i]; q.eu[i] = r.eu[i]; q.ev[i] = r.ev[i]; q.refl[i] = r.reflectance[i]; q.rad[i] = r.radiance[i]; }
+        float c[3];
+        cross(q.eu, q.ev, c);
+        float len = std::sqrt(dot(c, c));
+        for (int i = 0; i < 3; ++i) q.n[i] = c[i] / len;
+        float lu2 = dot(q.eu, q.eu), lv2 = dot(q.ev, q.ev);
+        q.inv_eu2 = 1.f / lu2; q.inv_ev2 = 1.f / lv2; q.inv_area = 1.f / len;
+        float lu = std::sqrt(lu2);
+        for (int i = 0; i < 3; ++i) q.s[i] = q.eu[i] / lu;
+        cross(q.n, q.s, q.t);
+    }
 }
 
 // `envmap` tables (host): scaled texels with the wrap column, marginal / conditional cdfs over the (h - 1) x w cells and

@@ -230,6 +230,7 @@ class Scene:
         self._shapes, self._sensors, self.env_radiance = [], [], None
         self.shape_key = None
         self.envmap, self.env_scale, self.env_to_world, self.quads = None, 1.0, None, []
+        n_emitters = 0
         for key, v in d.items():
             if not isinstance(v, dict):
                 continue
@@ -239,11 +240,13 @@ class Scene:
             elif t in ("perspective", "batch"):
                 self._sensors.append(Sensor(v))
             elif t == "constant":
+                n_emitters += 1
                 rad = v.get("radiance", 1.0)
                 if isinstance(rad, dict):
                     rad = rad.get("value", 1.0)
                 self.env_radiance = tuple(float(x) for x in (rad if np.ndim(rad) else (rad, rad, rad)))
             elif t == "envmap":                       # experiments.py:81-85
+                n_emitters += 1
                 if "bitmap" in v:                     # in-memory (H, W, 3) texels (this shim's extension)
                     tex = np.asarray(v["bitmap"], dtype=np.float32)
                 else:
@@ -272,6 +275,7 @@ class Scene:
                 if em is not None:
                     if em.get("type") != "area":
                         raise ValueError("a shape's emitter must be an `area` light")
+                    n_emitters += 1
                     rad = em.get("radiance", 1.0)
                     rad = rad.get("value", 1.0) if isinstance(rad, dict) else rad
                     q["radiance"] = tuple(float(x) for x in (rad if np.ndim(rad) else (rad,) * 3))
@@ -280,6 +284,8 @@ class Scene:
                 self.quads.append(q)
             elif t == "area":
                 raise ValueError("an `area` emitter belongs to a `rectangle` shape (its `emitter` entry)")
+        if n_emitters > 1:
+            raise ValueError("one emitter per scene: `constant`, `envmap` or one `area` light")
         if len(self._shapes) != 1 or self._shapes[0].interior_medium() is None:
             raise ValueError("expected a single shape with an interior medium (volpathsimple.py:16-19)")
         if len(self._sensors) != 1:

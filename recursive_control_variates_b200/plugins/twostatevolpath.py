@@ -36,9 +36,26 @@ class PRBVolpathIntegrator:
         return ctx.develop(acc)
 
     def render_backward(self, scene, params, grad_in, sensor=0, seed=0, spp=0):
-        raise NotImplementedError(
-            "the inherited PRB adjoint of prbvolpath is not part of this build (SURVEY.md §8f); "
-            "pass adjoint_integrator={'type': 'volpathsimple', ...} as the volume experiments do (experiments.py:131)")
+        """RBIntegrator.render_backward driving upstream prbvolpath's sample() (Primal, then Backward on the same
+        stream) — the adjoint every integrator derived from it inherits, TwoStatePRBVolpathIntegrator included
+        (twostatevolpath.py:11), and the one scenes with surfaces or area lights need (volpathsimple.py:24-30 refuses
+        them).  Runs in librcv_b200 (rcv_render_backward, RCV_ADJOINT_PRBVOLPATH); returns {parameter key: gradient}."""
+        from .. import _abi
+        assert isinstance(sensor, int)
+        ctx = self._ctx(scene)
+        rank, world = parallel.world()
+        b, e = parallel.shard_spp(spp, rank, world)
+        with torch.no_grad():
+            ctx.grad_zero()
+            film_w = None
+            if world > 1:        # the film weights of all samples: every rank adds its own, one small all-reduce
+                film_w = ctx.film_weights(seed, spp, b, e)
+                parallel.allreduce_sum_([film_w])
+            ctx.render_backward(seed, spp, grad_in.contiguous(), b, e, film_w=film_w, adjoint=_abi.RCV_ADJOINT_PRBVOLPATH)
+            parallel.allreduce_sum_([ctx.grad_packed()])
+            g_sigma, g_albedo = ctx.grad_read()
+        prefix = params.prefix if params is not None else ""
+        return {prefix + "sigma_t.data": g_sigma, prefix + "albedo.data": g_albedo}
 
     def to_string(self):
         return f"PRBVolpathIntegrator[max_depth = {self.max_depth}]"

@@ -148,12 +148,13 @@ class Context:
         check(self.lib.rcv_render_primal(self._h, state, seed & 0xFFFFFFFF, spp, spp_begin, spp_end, _ptr(acc)))
         return acc
 
-    def render_adjoint_primal_accum(self, seed: int, spp: int, spp_begin: int = 0, spp_end: Optional[int] = None, out=None):
+    def render_adjoint_primal_accum(self, seed: int, spp: int, spp_begin: int = 0, spp_end: Optional[int] = None, out=None,
+                                    adjoint: int = _abi.RCV_ADJOINT_VOLPATHSIMPLE):
         H, W = self.film_shape
         spp_end = spp if spp_end is None else spp_end
         acc = out if out is not None else self._zeros(H, W, 4)
         self._sync_stream()
-        check(self.lib.rcv_render_adjoint_primal(self._h, _abi.RCV_ADJOINT_VOLPATHSIMPLE, seed & 0xFFFFFFFF, spp, spp_begin,
+        check(self.lib.rcv_render_adjoint_primal(self._h, adjoint, seed & 0xFFFFFFFF, spp, spp_begin,
                                                  spp_end, _ptr(acc)))
         return acc
 
@@ -192,11 +193,14 @@ class Context:
         check(self.lib.rcv_grad_zero(self._h))
 
     def render_backward(self, seed_grad: int, spp_grad: int, grad_img: torch.Tensor, spp_begin: int = 0,
-                        spp_end: Optional[int] = None, film_w: Optional[torch.Tensor] = None):
-        """film_w: (H,W) film weights of ALL spp_grad samples (see film_weights); None = computed inside the call."""
+                        spp_end: Optional[int] = None, film_w: Optional[torch.Tensor] = None,
+                        adjoint: int = _abi.RCV_ADJOINT_VOLPATHSIMPLE):
+        """film_w: (H,W) film weights of ALL spp_grad samples (see film_weights); None = computed inside the call.
+        adjoint: RCV_ADJOINT_VOLPATHSIMPLE (plugins/volpathsimple.py) or RCV_ADJOINT_PRBVOLPATH (the adjoint
+        twostateprbvolpath inherits from upstream prbvolpath; the one that handles surfaces and area lights)."""
         spp_end = spp_grad if spp_end is None else spp_end
         self._sync_stream()
-        check(self.lib.rcv_render_backward_weighted(self._h, _abi.RCV_ADJOINT_VOLPATHSIMPLE, seed_grad & 0xFFFFFFFF, spp_grad,
+        check(self.lib.rcv_render_backward_weighted(self._h, adjoint, seed_grad & 0xFFFFFFFF, spp_grad,
                                                     spp_begin, spp_end, _ptr(grad_img), _ptr(film_w)))
 
     def film_weights(self, seed: int, spp: int, spp_begin: int = 0, spp_end: Optional[int] = None,
@@ -258,7 +262,7 @@ class Context:
                           seed_grad: int, spp_grad: int, img_out: torch.Tensor, loss_out: torch.Tensor,
                           grad_sigma_t_out: Optional[torch.Tensor] = None, grad_albedo_out: Optional[torch.Tensor] = None,
                           loss_kind: int = _abi.RCV_LOSS_L1, beta1: float = 0.9, beta2: float = 0.999, warmup: int = 1,
-                          reset: bool = False):
+                          reset: bool = False, adjoint: int = _abi.RCV_ADJOINT_VOLPATHSIMPLE):
         """One optimize.py iteration with every user-visible buffer in (pinned) host memory."""
         for t in (sigma_t, albedo, ref, img_out, loss_out, grad_sigma_t_out, grad_albedo_out):
             assert t is None or (not t.is_cuda and t.dtype == torch.float32 and t.is_contiguous())
@@ -268,6 +272,7 @@ class Context:
         a.nz, a.ny, a.nx = (int(v) for v in sigma_t.shape[:3])
         a.seed, a.spp, a.seed_grad, a.spp_grad = seed & 0xFFFFFFFF, spp, seed_grad & 0xFFFFFFFF, spp_grad
         a.loss_kind, a.beta1, a.beta2, a.warmup, a.reset = loss_kind, beta1, beta2, warmup, int(reset)
+        a.adjoint_kind = int(adjoint)
         a.img_out, a.loss_out = img_out.data_ptr(), loss_out.data_ptr()
         a.grad_sigma_t_out = grad_sigma_t_out.data_ptr() if grad_sigma_t_out is not None else None
         a.grad_albedo_out = grad_albedo_out.data_ptr() if grad_albedo_out is not None else None

@@ -10,6 +10,7 @@
 #include "../../recursive_control_variates_b200/csrc/rcv_scene.h"
 #include "../../recursive_control_variates_b200/csrc/rcv_twostate_wf.cuh"
 #include "../../recursive_control_variates_b200/csrc/rcv_volpathsimple_wf.cuh"
+#include "../../recursive_control_variates_b200/csrc/rcv_surface_wf.cuh"
 
 using namespace rcv;
 
@@ -258,7 +259,51 @@ void run_vps_drt(const SceneK &S, const GRID &G, VpSink &sk) {
 
 }  // namespace
 
+// the surface machine (rcv_surface_wf.cuh), lane by lane from the sensor, as k_surface_wavefront runs it
+template <int MODE, bool ADJ, class GRID>
+void run_surface(const SceneK &S, const GRID &G, SfSink &sk) {
+    const float mu = combined_majorant<MODE>(G);
+    const float inv_mu = 1.f / mu;
+    uint64_t n = (uint64_t) S.W * S.H * sk.spp;
+    for (uint64_t idx = 0; idx < n; ++idx) {
+        SfLane ln; ln.flags = 0;
+        sf_begin(S, ln, sk.seed, sk.spp, (uint32_t) idx, 0u);
+        while (ln.ev != EV_INIT) {
+            if (ln.ev == EV_COLL) sf_collide<MODE, ADJ>(S, G, mu, inv_mu, ln, sk);
+            else if (ln.ev == EV_SCAT) sf_scatter<MODE, ADJ>(S, G, ln, sk);
+            else sf_slow<MODE, ADJ>(S, ln, sk);
+        }
+    }
+}
+
 extern "C" {
+
+// scenes with rectangles: the two-state / single-state primal (adj == 0; mode as emu_twostates) or the inherited
+// prbvolpath adjoint of state `new` (adj == 1)
+int emu_surface(const rcv_scene_desc *d, const float *so, const float *ao, const float *sn, const float *an, int nz, int ny, int nx,
+                uint32_t seed, uint32_t spp, int mode, int adj, const float *grad_img, const float *film_w, float *acc_old,
+                float *acc_new, float *gsig, float *galb4, uint64_t *counters, int factor) {
+    HostScene hs(*d); const SceneK &S = hs.S;
+    Packed P; pack(*d, so, ao, sn, an, nz, ny, nx, P, factor);
+    for (int i = 0; i < 8; ++i) counters[i] = 0;
+    SfSink sk; sk.acc_old = (float4 *) acc_old; sk.acc_new = (float4 *) acc_new; sk.D.gsig = gsig; sk.D.galb = (float4 *) galb4;
+    sk.D.gbrick = nullptr;
+    sk.grad_img = grad_img; sk.film_w = film_w; sk.seed = seed; sk.spp = spp;
+    sk.cnt.coll = sk.cnt.scat = sk.cnt.g_sig = sk.cnt.g_alb = 0; sk.n_paths = 0;
+    HostBricks hb(nx, ny, nz, sk.D);
+    const GridK &G = P.G;
+    if (adj) {
+        if (factor > 0) run_surface<2, true>(S, P.G, sk); else run_surface<2, true>(S, G, sk);
+        hb.fold(gsig);
+    } else if (factor > 0) {
+        if (mode == 0) run_surface<0, false>(S, P.G, sk); else if (mode == 1) run_surface<1, false>(S, P.G, sk); else run_surface<2, false>(S, P.G, sk);
+    } else {
+        if (mode == 0) run_surface<0, false>(S, G, sk); else if (mode == 1) run_surface<1, false>(S, G, sk); else run_surface<2, false>(S, G, sk);
+    }
+    counters[mode == 0 && !adj ? 0 : 2] = sk.cnt.coll; counters[mode == 0 && !adj ? 1 : 3] = sk.cnt.scat;
+    counters[4] = sk.cnt.g_sig; counters[5] = sk.cnt.g_alb; counters[6] = sk.n_paths;
+    return 0;
+}
 
 // the three DRT stages of the pool tracer (use_drt + use_drt_subsampling; use_mis = use_drt_mis)
 int emu_vps_drt_stages(const rcv_scene_desc *d, const float *sn, const float *an, int nz, int ny, int nx, uint32_t seed, uint32_t spp,

@@ -117,3 +117,233 @@ def test_prb_adjoint_agrees_with_volpathsimple_under_the_environment(oracle):
     g2 = oracle.vps_backward(d, m, 78, 8192, gimg)
     assert abs(float((g1[0] * sig).sum()) - float((g2[0] * sig).sum())) < 0.1 * abs(float((g2[0] * sig).sum()))
     assert abs(float((g1[1] * alb).sum()) - float((g2[1] * alb).sum())) < 0.05 * abs(float((g2[1] * alb).sum()))
+
+
+# ---- the surface machine (csrc/rcv_surface_wf.cuh) compiled for the host -------------------------------------------
+@pytest.fixture(scope="module")
+def emu():
+    import subprocess, os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_emu")
+    subprocess.run(["make", "-C", here, "all"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+    lib = C.CDLL(os.path.join(here, "librcv_emu.so"))
+    f32 = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+    u64 = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
+    lib.emu_surface.argtypes = [C.c_void_p, f32, f32, f32, f32, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
+                                C.c_void_p, C.c_void_p, f32, f32, f32, f32, u64, C.c_int]
+    return lib
+
+
+SCENES = {
+    "box": dict(),
+    "box_hg_rr": dict(phase="hg", phase_g=0.6, rr_depth=2, max_depth=12),
+    "box_gaussian_hidden": dict(rfilter="gaussian", hide_emitters=True, max_depth=5),
+    "box_no_nee": dict(use_nee=False, max_depth=6),
+    "walls_under_envmap": dict(quads=boxed_quads()[:1] + boxed_quads()[2:3], envmap="sky"),      # a floor and one wall, no area light
+    "big_light": dict(light_size=2.8, max_depth=3),
+}
+
+
+def surf_setup(oracle, name, n=10, res=(20, 16)):
+    kw = dict(SCENES[name])
+    if kw.get("envmap") == "sky":
+        from test_envmap import sky
+        kw["envmap"] = sky(10, 16); kw["env_scale"] = 0.5
+    cfg = boxed(*res, **kw)
+    desc = cfg.to_desc()
+    old, new = media(n)
+    return dict(desc=desc, old=old, new=new, mo=oracle.OracleMedium(desc, *old), mn=oracle.OracleMedium(desc, *new))
+
+
+def run_emu(emu, d, old, new, seed, spp, mode=0, adj=0, grad_img=None, film_w=None, factor=0):
+    (so, ao), (sn, an) = old, new
+    H, W = d.film_height, d.film_width
+    acc_o = np.zeros((H, W, 4), np.float32); acc_n = np.zeros((H, W, 4), np.float32)
+    g1 = np.zeros((*sn.shape[:3], 1), np.float32); g4 = np.zeros((*sn.shape[:3], 4), np.float32)
+    cnt = np.zeros(8, np.uint64)
+    emu.emu_surface(C.addressof(d), so, ao, sn, an, *sn.shape[:3], seed, spp, mode, adj,
+                    grad_img.ctypes.data if grad_img is not None else None, film_w.ctypes.data if film_w is not None else None,
+                    acc_o, acc_n, g1, g4, cnt, factor)
+    return acc_o, acc_n, g1, g4, cnt
+
+
+@pytest.mark.parametrize("name", sorted(SCENES))
+def test_emu_surface_machine_matches_oracle(oracle, emu, name):
+    s = surf_setup(oracle, name)
+    d = s["desc"]
+    acc_o, acc_n, _, _, cnt = run_emu(emu, d, s["old"], s["new"], 21, 2)
+    oracle.counters(True)
+    ref_o, ref_n = oracle.render_twostates_accum(d, s["mo"], s["mn"], 21, 2)
+    oc = oracle.counters(True)
+    assert ref_n[..., :3].max() > 0
+    assert np.array_equal(acc_o, ref_o) and np.array_equal(acc_n, ref_n)
+    assert int(cnt[0]) == int(oc[0]) and int(cnt[1]) == int(oc[1])
+    # single-state (mode 2) = the primal of the inherited adjoint
+    _, acc_n, _, _, _ = run_emu(emu, d, s["old"], s["new"], 22, 1, mode=2)
+    _, ref_n = oracle.render_twostates_accum(d, s["mn"], s["mn"], 22, 1)
+    assert np.array_equal(acc_n, ref_n)
+
+
+@pytest.mark.parametrize("name", ["box", "box_hg_rr", "box_gaussian_hidden", "walls_under_envmap"])
+def test_emu_prb_adjoint_matches_oracle(oracle, emu, name):
+    s = surf_setup(oracle, name)
+    d = s["desc"]
+    H, W = d.film_height, d.film_width
+    grad_img = (np.random.default_rng(3).standard_normal((H, W, 3)) / (H * W * 3)).astype(np.float32)
+    seed_grad, spp = 0xC09848F2, 2
+    film_w = oracle.film_weights(d, seed_grad, spp)
+    _, _, g1, g4, cnt = run_emu(emu, d, s["new"], s["new"], seed_grad, spp, mode=2, adj=1, grad_img=grad_img, film_w=film_w)
+    oracle.counters(True)
+    gs, ga = oracle.prb_backward(d, s["mn"], seed_grad, spp, grad_img, film_w=film_w)
+    oc = oracle.counters(True)
+    assert np.abs(gs).max() > 0 and np.abs(ga).max() > 0
+    assert rel_l2(g1, gs) < 1e-5 and rel_l2(g4[..., :3], ga) < 1e-5
+    assert int(cnt[4]) == int(oc[4]) and int(cnt[5]) == int(oc[5]) and int(cnt[2]) == int(oc[0])
+
+
+def test_emu_surface_supergrid(oracle, emu):
+    s = surf_setup(oracle, "box", n=12)
+    d = s["desc"]
+    mo, mn = oracle.OracleMedium(d, *s["old"], majorant_factor=4), oracle.OracleMedium(d, *s["new"], majorant_factor=4)
+    acc_o, acc_n, _, _, _ = run_emu(emu, d, s["old"], s["new"], 5, 1, factor=4)
+    ref_o, ref_n = oracle.render_twostates_accum(d, mo, mn, 5, 1)
+    assert np.array_equal(acc_o, ref_o) and np.array_equal(acc_n, ref_n)
+
+
+# ---- CUDA, through the C-ABI ------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(SCENES))
+def test_gpu_surface_parity(oracle, gpu_ctx, name):
+    from helpers import gpu_set_states, to_cuda
+    from recursive_control_variates_b200 import _abi
+    s = surf_setup(oracle, name, n=12, res=(28, 24))
+    d = s["desc"]
+    gpu_ctx.set_scene(d)
+    gpu_ctx.set_majorant_factor(0)
+    gpu_ctx.set_drt(False)
+    gpu_set_states(gpu_ctx, s["old"], s["new"])
+    # per-lane radiance, bit for bit (spp = 1; the gaussian filter splats a lane to several pixels: images instead)
+    ao, an = oracle.render_twostates_accum(d, s["mo"], s["mn"], 3, 1)
+    go, gn = gpu_ctx.render_twostates_accum(seed=3, spp=1)
+    if d.rfilter_type == 0:
+        assert np.array_equal(go.cpu().numpy(), ao) and np.array_equal(gn.cpu().numpy(), an)
+    else:
+        assert rel_l2(go.cpu().numpy(), ao) < 1e-6 and rel_l2(gn.cpu().numpy(), an) < 1e-6
+    H, F = oracle.render_twostates(d, s["mo"], s["mn"], 7, 8)
+    gH, gF = gpu_ctx.render_twostates(seed=7, spp=8)
+    assert rel_l2(gH.cpu().numpy(), H) < 1e-6 and rel_l2(gF.cpu().numpy(), F) < 1e-6          # tolerance of north_star: 1e-4
+    a1, _ = oracle.render_twostates_accum(d, s["mn"], s["mn"], 5, 1)
+    assert rel_l2(gpu_ctx.render_primal_accum(1, seed=5, spp=1).cpu().numpy(), a1) < 1e-6
+    # the inherited adjoint
+    Hh, Ww = d.film_height, d.film_width
+    grad_img = (np.random.default_rng(5).standard_normal((Hh, Ww, 3)) / (Hh * Ww * 3)).astype(np.float32)
+    gs, ga = oracle.prb_backward(d, s["mn"], 0xBEEF, 4, grad_img)
+    gpu_ctx.grad_zero()
+    gpu_ctx.render_backward(0xBEEF, 4, to_cuda(grad_img), adjoint=_abi.RCV_ADJOINT_PRBVOLPATH)
+    g_s, g_a = gpu_ctx.grad_read()
+    assert rel_l2(g_s.cpu().numpy(), gs) < 1e-4 and rel_l2(g_a.cpu().numpy(), ga) < 1e-4     # north_star: 1e-3
+    # spp shards add up
+    gpu_ctx.grad_zero()
+    fw = gpu_ctx.film_weights(0xBEEF, 4)
+    for b, e in ((0, 1), (1, 4)):
+        gpu_ctx.render_backward(0xBEEF, 4, to_cuda(grad_img), b, e, film_w=fw, adjoint=_abi.RCV_ADJOINT_PRBVOLPATH)
+    g_s2, _ = gpu_ctx.grad_read()
+    assert rel_l2(g_s2.cpu().numpy(), gs) < 1e-4
+    # volpathsimple refuses surfaces, as the reference does (volpathsimple.py:24-30)
+    with pytest.raises(_abi.RcvError):
+        gpu_ctx.render_backward(1, 1, to_cuda(grad_img))
+
+
+@pytest.mark.gpu
+def test_gpu_prb_adjoint_without_surfaces(oracle, gpu_ctx):
+    """The inherited adjoint in the environment-lit scene (supergrid on): what `cv` runs when no adjoint_integrator is given."""
+    from helpers import gpu_set_states, to_cuda
+    from recursive_control_variates_b200 import _abi
+    d = small_scene(24, 20).to_desc()
+    old, new = media(12)
+    gpu_ctx.set_scene(d)
+    gpu_set_states(gpu_ctx, old, new)
+    grad_img = (np.random.default_rng(6).standard_normal((20, 24, 3)) / (20 * 24 * 3)).astype(np.float32)
+    for f in (0, 4):
+        gpu_ctx.set_majorant_factor(f)
+        gs, ga = oracle.prb_backward(d, oracle.OracleMedium(d, *new, majorant_factor=f), 99, 4, grad_img)
+        gpu_ctx.grad_zero()
+        gpu_ctx.render_backward(99, 4, to_cuda(grad_img), adjoint=_abi.RCV_ADJOINT_PRBVOLPATH)
+        g_s, g_a = gpu_ctx.grad_read()
+        assert rel_l2(g_s.cpu().numpy(), gs) < 1e-4 and rel_l2(g_a.cpu().numpy(), ga) < 1e-4
+    gpu_ctx.set_majorant_factor(0)
+
+
+def _boxed_scene_dict(new, film=(24, 20)):
+    import torch
+    from recursive_control_variates_b200.scene import look_at
+
+    def rect(q):
+        # a to_world that maps Mitsuba's rectangle [-1,1]^2 x {0} onto p0 + s eu + t ev
+        p0, eu, ev = (np.asarray(q[k], np.float64) for k in ("p0", "eu", "ev"))
+        m = np.eye(4); m[:3, 0] = eu / 2; m[:3, 1] = ev / 2
+        m[:3, 2] = np.cross(eu, ev) / np.linalg.norm(np.cross(eu, ev)); m[:3, 3] = p0 + eu / 2 + ev / 2
+        out = {"type": "rectangle", "to_world": m,
+               "bsdf": {"type": "diffuse", "reflectance": {"type": "rgb", "value": list(q["reflectance"])}}}
+        if "radiance" in q:
+            out["emitter"] = {"type": "area", "radiance": {"type": "rgb", "value": list(q["radiance"])}}
+        return out
+
+    medium = {"type": "heterogeneous", "sigma_t": {"type": "gridvolume", "data": torch.from_numpy(new[0])},
+              "albedo": {"type": "gridvolume", "data": torch.from_numpy(new[1])}, "scale": 20.0}
+    d = {"type": "scene",
+         "object": {"type": "obj", "bsdf": {"type": "null"},
+                    "interior": {"type": "twostatemedium", "old": medium, "new": medium, "incoming": medium}},
+         "sensor": {"type": "perspective", "fov": 45, "to_world": look_at([0.5, 0.5, -2.0], [0.5, 0.5, 0.5], [0, 1, 0]),
+                    "film": {"type": "hdrfilm", "width": film[0], "height": film[1], "rfilter": {"type": "box"}}}}
+    for k, q in enumerate(boxed_quads()):
+        d[f"wall_{k}"] = rect(q)
+    return d
+
+
+def test_load_dict_rectangles_and_area_light():
+    """The Mitsuba-style scene dictionary (rectangle shapes with to_world, diffuse BSDFs, an area emitter) reaches the
+    C-ABI description unchanged; a second emitter is refused."""
+    from recursive_control_variates_b200 import mitsuba_compat as mi
+    from recursive_control_variates_b200 import plugins  # noqa: F401
+    from recursive_control_variates_b200 import _abi
+    _, new = media(6)
+    sd = _boxed_scene_dict(new)
+    scene = mi.load_dict(sd)
+    d = scene.scene_config(8, 8).to_desc()
+    ref = boxed(24, 20, max_depth=8, rr_depth=8).to_desc()
+    assert d.n_quads == 7 and d.area_quad == 6 and d.emitter_type == _abi.RCV_EMITTER_AREA
+    for k in range(7):
+        for f in ("p0", "eu", "ev", "reflectance", "radiance"):
+            assert np.allclose(list(getattr(d.quads[k], f)), list(getattr(ref.quads[k], f)), atol=1e-6), (k, f)
+    assert abs(d.env_dist - ref.env_dist) < 1e-6
+    sd["sky"] = {"type": "constant", "radiance": 1.0}
+    with pytest.raises(ValueError):
+        mi.load_dict(sd)
+
+
+@pytest.mark.gpu
+def test_gpu_boxed_scene_through_the_plugins(oracle):
+    """load_dict of a boxed scene (rectangles + area light), `cv` around twostateprbvolpath with its INHERITED adjoint
+    (no adjoint_integrator given, cv_integrator.py:21): F against the oracle, the gradient of sum(img) against the
+    oracle's prbvolpath adjoint."""
+    import torch
+    from recursive_control_variates_b200 import mitsuba_compat as mi
+    from recursive_control_variates_b200 import plugins  # noqa: F401  (registers the integrators)
+    _, new = media(10)
+    scene = mi.load_dict(_boxed_scene_dict(new))
+    integ = mi.load_dict({"type": "cv", "integrator": {"type": "twostateprbvolpath", "max_depth": 8, "rr_depth": 8}})
+    assert integ.adjoint_integrator is integ.integrator
+    opt = mi.Adam(lr=5e-3)
+    sp = mi.traverse(scene)
+    ks, ka = "object.interior_medium.sigma_t.data", "object.interior_medium.albedo.data"
+    for _ in range(2):
+        opt[ks] = torch.from_numpy(new[0]); opt[ka] = torch.from_numpy(new[1])
+        sp.update(opt)
+    img = mi.render(scene, sp, integrator=integ, seed=1, spp=4, seed_grad=2, spp_grad=4)
+    d = integ.integrator._ctx(scene).desc
+    m = oracle.OracleMedium(d, *new)
+    H, F = oracle.render_twostates(d, m, m, 1, 4)
+    assert rel_l2(integ.F.cpu().numpy(), F) < 1e-6 and F.max() > 0
+    img.sum().backward()
+    gs, ga = oracle.prb_backward(d, m, 2, 4, np.ones((20, 24, 3), np.float32))
+    assert rel_l2(opt[ks].grad.cpu().numpy(), gs) < 1e-4 and rel_l2(opt[ka].grad.cpu().numpy(), ga) < 1e-4
