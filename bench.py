@@ -825,7 +825,7 @@ def run_loop(a):
                "stopwatch_ms": {"render": float(rt[:, 0].mean()) if len(rt) else None,
                                 "backward_step": float(rt[:, 1].mean()) if len(rt) else None,
                                 "note": "optimize.py's own Stopwatch (iterations > 16): mi.render + loss, then backward + Adam + clamp"},
-               "loss_first_last": [float(res["loss"][0]), float(res["loss"][-1])],
+               "loss_at_iteration_0": float(res["loss"][0]),
                "gpu_launches": int(mi._any_context().counters(False)[7])}
         print(json.dumps(out))
     if world > 1:

@@ -40,12 +40,19 @@ __global__ void __launch_bounds__(kSfBlock, RCV_SF_MINBLOCKS) k_surface_wavefron
         const int n_coll = __popc(__ballot_sync(0xffffffffu, ln.ev == EV_COLL));
         const int n_scat = __popc(__ballot_sync(0xffffffffu, ln.ev == EV_SCAT));
         const int n_slow = __popc(__ballot_sync(0xffffffffu, ln.ev == EV_SLOW || (ln.ev == EV_INIT && cc.more)));
-        if (n_coll == 0 && n_scat == 0 && n_slow == 0) break;
-        const int sel = pick_event(n_coll, n_scat, n_slow);
+        const int n_nee = __popc(__ballot_sync(0xffffffffu, ln.ev == EV_NEE));
+        if (n_coll == 0 && n_scat == 0 && n_slow == 0 && n_nee == 0) break;
+        // the fullest class runs (every lane is in exactly one: the fullest holds a quarter of the live lanes at least)
+        int sel = EV_COLL, n_sel = n_coll;
+        if (n_slow > n_sel) { sel = EV_SLOW; n_sel = n_slow; }
+        if (n_nee > n_sel) { sel = EV_NEE; n_sel = n_nee; }
+        if (n_scat > n_sel) { sel = EV_SCAT; n_sel = n_scat; }
         if (sel == EV_COLL) {
             if (ln.ev == EV_COLL) sf_collide<MODE, ADJ>(S, G, mu, inv_mu, ln, sk);
         } else if (sel == EV_SCAT) {
             if (ln.ev == EV_SCAT) sf_scatter<MODE, ADJ>(S, G, ln, sk);
+        } else if (sel == EV_NEE) {
+            if (ln.ev == EV_NEE) sf_nee<ADJ>(S, ln);
         } else {
             if (ln.ev == EV_SLOW) sf_slow<MODE, ADJ>(S, ln, sk);
             unsigned m_init = __ballot_sync(0xffffffffu, ln.ev == EV_INIT);

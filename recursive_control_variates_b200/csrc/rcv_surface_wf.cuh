@@ -9,9 +9,10 @@
 //
 //   EV_COLL   one tentative collision inside the medium, on the main path (:180-266) or on a shadow ray (:408-452)
 //   EV_SCAT   a real scattering vertex (:259-344): albedo gather, phase sampling, emitter sample
-//   EV_SLOW   everything outside the medium: the surface block of an iteration (:283-380: intersection, emitter hit,
-//             emitter sampling at a diffuse surface, BSDF sampling, medium transition), the surface part of a
-//             shadow-ray iteration (:455-477), the end of a shadow ray, the end of the path
+//   EV_SLOW   the main path outside the medium: the surface block of an iteration (:283-380: intersection, emitter hit,
+//             emitter sampling at a diffuse surface, BSDF sampling, medium transition), the end of the path
+//   EV_NEE    a shadow ray outside the medium: the surface part of its iterations (:455-477) and its end (the
+//             contribution :336-344, then the BSDF sampling of the vertex it was cast from)
 //
 // ADJ = true (MODE 2 only) is upstream mi.ad.integrators.prbvolpath.PRBVolpathIntegrator.sample driven by
 // RBIntegrator.render_backward — the adjoint TwoStatePRBVolpathIntegrator inherits (twostatevolpath.py:11) and every
@@ -29,6 +30,9 @@
 namespace rcv {
 
 #define RCV_INV_PI 0.31830988618379067154f
+// a fourth event class: the shadow ray's work outside the medium (its surface iterations, its end).  Kept apart from
+// EV_SLOW so that a warp runs the main path's surface blocks and the shadow rays' each with their own lanes.
+enum : int { EV_NEE = 4 };
 
 enum : uint32_t {
     SF_NEEDS_ISECT = 1u, SF_SPECULAR = 2u, SF_IN_NEE = 4u, SF_SI_VALID = 8u,
@@ -41,7 +45,8 @@ enum : uint32_t {
     SF_POST_NEE = 1024u,     // the shadow ray ended
     SF_FIN = 2048u,          // the path ended
     SF_PASS2 = 4096u,        // adjoint: this is the second walk
-    SF_REPLAY = 8192u        // adjoint: the shadow ray is being walked again, with gradients
+    SF_REPLAY = 8192u,       // adjoint: the shadow ray is being walked again, with gradients
+    SF_BSDF = 16384u         // the BSDF sampling of the surface vertex is pending (after its shadow ray)
 };
 
 struct SfLane {
@@ -89,8 +94,9 @@ struct SHit {
 };
 __device__ __forceinline__ V3 v3of(const float *a) { return mk3(a[0], a[1], a[2]); }
 
-// scene.ray_intersect: the nearest of the medium's box and the rectangles, 0 < t <= maxt
-__device__ __forceinline__ SHit scene_hit_all(const SceneK &S, V3 o, V3 d, V3 id, float maxt) {
+// scene.ray_intersect: the nearest of the medium's box and the rectangles, 0 < t <= maxt.  Out of line: three call
+// sites, and the kernels' code size matters (instruction-cache misses were the top stall of the first version).
+static __device__ __noinline__ SHit scene_hit_all(const SceneK &S, V3 o, V3 d, V3 id, float maxt) {
     Hit h = box_hit(S, o, d, id, maxt);
     SHit r; r.valid = h.valid; r.t = h.t; r.p = h.p; r.n = h.n; r.shape = -1;
     for (int k = 0; k < S.n_quads; ++k) {
@@ -190,7 +196,7 @@ __device__ __forceinline__ void sf_nee_start(SfLane &ln) {
     if (ln.flags & SF_NEE_SURF) {
         ln.no = offset_p(ln.o, ln.vn, ln.nd);
         ln.flags = (ln.flags & ~(SF_NEE_MEDIUM | SF_NEE_ESC)) | SF_IN_NEE | SF_NEEDS_ISECT;
-        ln.ev = EV_SLOW;
+        ln.ev = EV_NEE;
     } else {
         ln.no = ln.o;
         ln.flags = (ln.flags & ~SF_NEE_ESC) | SF_IN_NEE | SF_NEE_MEDIUM | SF_NEEDS_ISECT;
@@ -263,7 +269,7 @@ __device__ __forceinline__ void sf_collide(const SceneK &S, const GRID &G, float
         so = ln.o; sd = ln.d; maxt = RCV_LARGEST;
     } else {
         float remaining = ln.ndist * (1.f - RCV_SHADOW_EPS) - ln.total;   // :409
-        if (!(remaining > 0.f)) { ln.flags |= SF_POST_NEE; ln.ev = EV_SLOW; return; }   // :411
+        if (!(remaining > 0.f)) { ln.flags |= SF_POST_NEE; ln.ev = EV_NEE; return; }   // :411
         so = ln.no; sd = ln.nd; maxt = remaining;
     }
     float u = pcg_f32(ln.rng);                                        // :194 / :422
@@ -285,7 +291,7 @@ __device__ __forceinline__ void sf_collide(const SceneK &S, const GRID &G, float
             }
             ln.tr_old = ln.tr_old * trm_o;
             ln.tr_new = ln.tr_new * trm_n;
-            if (!(ln.tr_new != 0.f || ln.tr_old != 0.f)) { ln.flags |= SF_POST_NEE; ln.ev = EV_SLOW; return; }
+            if (!(ln.tr_new != 0.f || ln.tr_old != 0.f)) { ln.flags |= SF_POST_NEE; ln.ev = EV_NEE; return; }
             ln.total += m.t;
             return;
         }
@@ -315,7 +321,7 @@ __device__ __forceinline__ void sf_collide(const SceneK &S, const GRID &G, float
     }
     // the segment left the medium: the surface part of this iteration follows, with the si found above
     ln.flags |= nee ? SF_NEE_ESC : SF_ESC;
-    ln.ev = EV_SLOW;
+    ln.ev = nee ? EV_NEE : EV_SLOW;
 }
 
 // ---------------------------------------------------------------------------
@@ -384,8 +390,8 @@ __device__ __forceinline__ void sf_scatter(const SceneK &S, const GridK &G, SfLa
 // EV_SLOW pieces
 // ---------------------------------------------------------------------------
 // BSDF sampling and the end of the iteration (:346-380) at the surface point (sp, sn, shape), incident direction d
-template <int MODE, bool ADJ>
-__device__ __forceinline__ void sf_bsdf(const SceneK &S, SfLane &ln, SfSink &sk) {
+__device__ __forceinline__ void sf_bsdf(const SceneK &S, SfLane &ln) {
+    ln.flags &= ~SF_BSDF;
     (void) pcg_f32(ln.rng);                                           // :347
     float b2x = pcg_f32(ln.rng), b2y = pcg_f32(ln.rng);               // :348
     if (ln.vshape < 0) {
@@ -402,7 +408,7 @@ __device__ __forceinline__ void sf_bsdf(const SceneK &S, SfLane &ln, SfSink &sk)
     float ci = -dot3(n, ln.d);
     V3 wl = cosine_hemisphere(b2x, b2y);
     float pdf = RCV_INV_PI * wl.z;
-    if (!((ci > 0.f) && (pdf > 0.f))) { sf_finish<MODE, ADJ>(S, ln, sk); return; }   // :349 bs.pdf == 0: the lane ends (:380)
+    if (!((ci > 0.f) && (pdf > 0.f))) { ln.flags |= SF_FIN; ln.ev = EV_SLOW; return; }   // :349 bs.pdf == 0: the lane ends (:380)
     V3 val_old = (refl * RCV_INV_PI) * wl.z;                          // :351 eval_old(bs.wo)
     ln.thr_old = ln.thr_old * mk3(val_old.x / pdf, val_old.y / pdf, val_old.z / pdf);   // :354-355
     ln.thr_new = ln.thr_new * refl;                                   // :357
@@ -420,13 +426,13 @@ __device__ __forceinline__ void sf_bsdf(const SceneK &S, SfLane &ln, SfSink &sk)
 
 // the surface block of a main-path iteration (:283-344); entered at the start of an iteration outside the medium, or
 // with SF_ESC right after the medium part of the iteration
-template <int MODE, bool ADJ>
-__device__ __forceinline__ void sf_surface(const SceneK &S, SfLane &ln, SfSink &sk) {
+template <bool ADJ>
+__device__ __forceinline__ void sf_surface(const SceneK &S, SfLane &ln) {
     bool last = false;
     if (ln.flags & SF_ESC) {
         ln.flags &= ~SF_ESC;
     } else {
-        if (!sf_loop_head(S, ln)) { sf_finish<MODE, ADJ>(S, ln, sk); return; }
+        if (!sf_loop_head(S, ln)) { ln.flags |= SF_FIN; return; }
         last = !(ln.depth < S.max_depth);                             // :253 switches the lane off, the block below still runs
         sf_store_hit(ln, scene_hit_all(S, ln.o, ln.d, ln.id, RCV_LARGEST));   // :285-286
     }
@@ -449,7 +455,7 @@ __device__ __forceinline__ void sf_surface(const SceneK &S, SfLane &ln, SfSink &
             sf_add<ADJ>(ln, (ln.thr_old * mis_bsdf) * emitted, (ln.thr_new * mis_bsdf) * emitted);
         }
     }
-    if (!si_valid || last) { sf_finish<MODE, ADJ>(S, ln, sk); return; }   // :310, :380
+    if (!si_valid || last) { ln.flags |= SF_FIN; return; }            // :310, :380
     ln.o = ln.sp; ln.vn = ln.sn; ln.vshape = ln.shape;                // the surface vertex
     // ---- emitter sampling at a diffuse surface (:315-344)
     if (S.use_nee && ln.vshape >= 0 && (ln.depth + 1 < S.max_depth)) {
@@ -463,7 +469,7 @@ __device__ __forceinline__ void sf_surface(const SceneK &S, SfLane &ln, SfSink &
             return;
         }
     }
-    sf_bsdf<MODE, ADJ>(S, ln, sk);
+    ln.flags |= SF_BSDF;
 }
 
 // the surface part of a shadow-ray iteration (:455-477) — at the start of an iteration outside the medium, or with
@@ -491,8 +497,8 @@ __device__ __forceinline__ void sf_nee_iter(const SceneK &S, SfLane &ln) {
 
 // the shadow ray ended: its contribution (:336-344); in the adjoint's second walk, walk it again with gradients; then the
 // iteration continues (:346-380)
-template <int MODE, bool ADJ>
-__device__ __forceinline__ void sf_nee_done(const SceneK &S, SfLane &ln, SfSink &sk) {
+template <bool ADJ>
+__device__ __forceinline__ void sf_nee_done(const SceneK &S, SfLane &ln) {
     ln.flags &= ~SF_POST_NEE;
     if (!(ADJ && (ln.flags & SF_REPLAY))) {
         V3 emitter_val;
@@ -522,22 +528,26 @@ __device__ __forceinline__ void sf_nee_done(const SceneK &S, SfLane &ln, SfSink 
         }
     }
     ln.flags &= ~(SF_REPLAY | SF_IN_NEE | SF_NEE_MEDIUM);
-    if (ln.flags & SF_NEE_SURF) { sf_bsdf<MODE, ADJ>(S, ln, sk); return; }
+    if (ln.flags & SF_NEE_SURF) { ln.flags |= SF_BSDF; ln.ev = EV_SLOW; return; }
     ln.thr_old = ln.thr_old * ln.ratio;                               // :360-361
     ln.flags |= SF_NEEDS_ISECT;
     ln.id = rcp3(ln.d);
     ln.ev = EV_COLL;
 }
 
+// EV_SLOW: the main path outside the medium
 template <int MODE, bool ADJ>
 __device__ __forceinline__ void sf_slow(const SceneK &S, SfLane &ln, SfSink &sk) {
-    if (ln.flags & SF_FIN) { sf_finish<MODE, ADJ>(S, ln, sk); return; }
-    if (ln.flags & SF_IN_NEE) {
-        if (!(ln.flags & SF_POST_NEE)) sf_nee_iter(S, ln);
-        if (ln.flags & SF_POST_NEE) sf_nee_done<MODE, ADJ>(S, ln, sk);
-        return;
-    }
-    sf_surface<MODE, ADJ>(S, ln, sk);
+    // one copy of each piece: a surface block flows into its BSDF sampling and, where the path ends, into the finish
+    if (!(ln.flags & (SF_FIN | SF_BSDF))) sf_surface<ADJ>(S, ln);
+    if (ln.flags & SF_BSDF) sf_bsdf(S, ln);
+    if (ln.flags & SF_FIN) sf_finish<MODE, ADJ>(S, ln, sk);
+}
+// EV_NEE: the shadow ray outside the medium
+template <bool ADJ>
+__device__ __forceinline__ void sf_nee(const SceneK &S, SfLane &ln) {
+    if (!(ln.flags & SF_POST_NEE)) sf_nee_iter(S, ln);
+    if (ln.flags & SF_POST_NEE) sf_nee_done<ADJ>(S, ln);
 }
 
 }  // namespace rcv

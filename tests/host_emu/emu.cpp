@@ -271,6 +271,7 @@ void run_surface(const SceneK &S, const GRID &G, SfSink &sk) {
         while (ln.ev != EV_INIT) {
             if (ln.ev == EV_COLL) sf_collide<MODE, ADJ>(S, G, mu, inv_mu, ln, sk);
             else if (ln.ev == EV_SCAT) sf_scatter<MODE, ADJ>(S, G, ln, sk);
+            else if (ln.ev == EV_NEE) sf_nee<ADJ>(S, ln);
             else sf_slow<MODE, ADJ>(S, ln, sk);
         }
     }
