@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(kBlock) k_vps_raygen(const __grid_constant__ S
     uint64_t j = (uint64_t) blockIdx.x * kBlock + threadIdx.x;
     VpLane ln; ln.ev = EV_INIT; ln.flags = 0;
     VpSink sk; sk.accum = accum; sk.D.gsig = nullptr; sk.D.galb = nullptr; sk.grad_img = nullptr; sk.film_w = nullptr;
-    sk.arena = nullptr; sk.vcap = 0;
+    sk.arena = nullptr; sk.vcap = 0; sk.flat = 0; sk.drt_mis = 0;
     sk.seed = seed; sk.spp = spp; sk.alt_seed = 0;
     sk.cnt.coll = sk.cnt.scat = sk.cnt.g_sig = sk.cnt.g_alb = 0; sk.n_paths = 0;
     if (j < n_local) vp_raygen<BACKWARD>(S, ln, sk, global_lane(j, spp, spp_begin, ns));
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(kWfBlock, RCV_VP_MINBLOCKS) k_vps_wavefront(co
     ln.ev = EV_INIT; ln.flags = 0;
     VpSink sk;
     sk.accum = accum; sk.D = D; sk.grad_img = grad_img; sk.film_w = film_w; sk.arena = arena; sk.vcap = vcap;
-    sk.seed = seed; sk.spp = spp; sk.alt_seed = alt_seed;
+    sk.seed = seed; sk.spp = spp; sk.alt_seed = alt_seed; sk.flat = 0; sk.drt_mis = 0;
     sk.cnt.coll = sk.cnt.scat = sk.cnt.g_sig = sk.cnt.g_alb = 0; sk.n_paths = 0;
     ChunkCursor cc; cc.next = 0; cc.end = 0; cc.more = true;
     while (true) {
@@ -340,7 +340,7 @@ static constexpr int kPoolBlock = RCV_POOL_BLOCK;          // two-state kernels
 static constexpr int kVpPoolBlock = RCV_VP_POOL_BLOCK;     // volpathsimple kernels
 
 template <int WORDS>
-__host__ __device__ constexpr size_t pool_warp_floats() { return (size_t) WORDS * kPoolSlots + 2 * kPoolSlots / 4; }
+__host__ __device__ constexpr size_t pool_warp_floats() { return (size_t) WORDS * kPoolSlots + 2 * kPoolSlots / 4 + (kPoolSlots + 8) / 2; }   // + cls, list (bytes), prefix sums of the flattened pass-2 rounds (16 bit)
 
 // the class of every slot of the warp's pool as ballot masks (slots 32 j .. 32 j + 31 in word j)
 struct PoolMasks {
@@ -473,6 +473,9 @@ __global__ void __launch_bounds__(kVpPoolBlock, RCV_POOL_MINBLOCKS) k_vps_pool(c
     sk.seed = seed; sk.spp = spp; sk.alt_seed = alt_seed;
     sk.cnt.coll = sk.cnt.scat = sk.cnt.g_sig = sk.cnt.g_alb = 0; sk.n_paths = 0;
     sk.jobs = jobs; sk.drt_mis = drt_mis;
+    constexpr bool kFlat = RCV_FLAT_PASS2 && BACKWARD && DRT == 0;
+    sk.flat = kFlat ? 1 : 0;
+    unsigned short *pre = (unsigned short *) (list + kPoolSlots);      // kPoolSlots + 1 exclusive prefix sums (flattened pass 2)
     const uint32_t slot0 = (blockIdx.x * (kVpPoolBlock / 32) + (threadIdx.x >> 5)) * kPoolSlots;   // first arena slot of this warp's pool
     ChunkCursor cc; cc.next = 0; cc.end = 0; cc.more = true;
 #pragma unroll
@@ -481,7 +484,56 @@ __global__ void __launch_bounds__(kVpPoolBlock, RCV_POOL_MINBLOCKS) k_vps_pool(c
     while (true) {
         PoolMasks M;
         pool_masks(cls, cc.more, M);
-        if (M.n_coll == 0 && M.n_scat == 0 && M.n_slow == 0) break;
+        if (kFlat) {
+            // Flattened pass 2: the vertices of the lanes that finished pass 1 (class EV_P2) are independent of each other
+            // once the running result and the secondary sampler's position are rebuilt per vertex (vp_vertex2_flat), so a
+            // round gives each thread ONE vertex of whichever waiting lane — 32 at a time, all in the same code — instead of
+            // walking each lane's list with the few lanes that happen to wait for a vertex step.
+            static_assert(kPoolMaskWords == 2, "two slots per thread");
+            int c[2], tot[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int sl = (int) lane + 32 * j;
+                c[j] = (cls[sl] == EV_P2) ? (int) pu_f(pw[48 * kPoolSlots + sl]) - (int) pu_f(pw[49 * kPoolSlots + sl]) : 0;   // nvert - vk
+                int x = c[j];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if ((int) lane >= o) x += y; }
+                tot[j] = __shfl_sync(0xffffffffu, x, 31);
+                c[j] = x - c[j];                                       // exclusive prefix within this half
+            }
+            const int total = tot[0] + tot[1];
+            const bool idle = (M.n_coll == 0 && M.n_scat == 0 && M.n_slow == 0);
+            if (total == 0 && idle) break;
+            if (total >= 32 || (total > 0 && idle)) {
+                pre[lane] = (unsigned short) c[0]; pre[lane + 32] = (unsigned short) (tot[0] + c[1]);
+                if (lane == 0) pre[kPoolSlots] = (unsigned short) total;
+                __syncwarp();
+                const int nb = min(total, 32), g = (int) lane;
+                int s = -1, k0 = 0, k = 0;
+                V3 res = mk3(0, 0, 0);
+                if (g < nb) {
+                    int lo = 0, hi = kPoolSlots;                       // the slot with pre[s] <= g < pre[s + 1]
+                    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if ((int) pre[mid] <= g) lo = mid; else hi = mid; }
+                    s = lo;
+                    k0 = (int) pu_f(pw[49 * kPoolSlots + s]);
+                    k = k0 + (g - (int) pre[s]);
+                    const V3 res0 = mk3(pw[28 * kPoolSlots + s], pw[29 * kPoolSlots + s], pw[30 * kPoolSlots + s]);
+                    const V3 dL = mk3(pw[31 * kPoolSlots + s], pw[32 * kPoolSlots + s], pw[33 * kPoolSlots + s]);
+                    const uint32_t idx = pu_f(pw[2 * kPoolSlots + s]);
+                    res = vp_vertex2_flat(S, G, sk, (slot0 + (uint32_t) s) * (vcap + kNeeCap / 4), k0, k, res0, dL, idx);
+                }
+                __syncwarp();
+                // the thread that took the last vertex of a slot in this round writes the lane's progress back
+                if (g < nb && (g == nb - 1 || g + 1 == (int) pre[s + 1])) {
+                    const int nvert = (int) pu_f(pw[48 * kPoolSlots + s]);
+                    pw[28 * kPoolSlots + s] = res.x; pw[29 * kPoolSlots + s] = res.y; pw[30 * kPoolSlots + s] = res.z;
+                    pw[49 * kPoolSlots + s] = pf_u((uint32_t) (k + 1));
+                    if (k + 1 == nvert) { cls[s] = EV_INIT; sk.n_paths++; }
+                }
+                __syncwarp();
+                continue;
+            }
+        } else if (M.n_coll == 0 && M.n_scat == 0 && M.n_slow == 0) break;
         const int sel = pool_pick(M.n_coll, M.n_scat, M.n_slow);
         VpLane ln;
         if (sel == EV_COLL) {

@@ -65,8 +65,18 @@ enum : uint32_t {
     // work parked for the batched EV_SLOW step
     VF_POSTNEE = 512u,    // the shadow ray (or its replay) ended
     VF_END = 1024u,       // the pass ended at a loop head (:132-133)
-    VF_JOB = 2048u        // DRT: the lane is complete and its job (DRT = 1) / its gradient (DRT = 2) is to be written
+    VF_JOB = 2048u,       // DRT: the lane is complete and its job (DRT = 1) / its gradient (DRT = 2) is to be written
+    VF_ANY_OVF = 4096u    // pass 1: some shadow ray of this path overflowed its record buffer (pass 2 must replay it)
 };
+// a fourth scheduling class of the pool kernel (RCV_FLAT_PASS2): pass 1 is complete and the lane's vertices wait for a
+// flattened pass-2 round, in which every thread of the warp takes ONE vertex of whichever waiting lane (vp_vertex2_flat)
+enum : int { EV_P2 = 4 };
+// r2p (profiles/README.md): 15.37 ms against 15.52 ms for the list walk at C2 — within run-to-run noise, +6 registers and a
+// 16-byte spill: the adjoint's second pass is bound by the read-modify-write traffic of its gradient scatters, not by the
+// SIMD efficiency of its vertex rounds.  Off by default; the per-vertex function is covered by the host-emulation tests.
+#ifndef RCV_FLAT_PASS2
+#define RCV_FLAT_PASS2 0
+#endif
 
 // vertex record flags
 enum : uint32_t { VR_SCATTER = 1u, VR_NEE = 2u, VR_NEE_DONE = 4u /* its transmittance gradients were scattered in pass 1 */,
@@ -111,6 +121,7 @@ struct VpSink {
     VpsCounts cnt;
     unsigned n_paths;
     int drt_mis;            // use_drt_mis (DRT != 0)
+    int flat;               // the scheduler runs pass 2 vertex-parallel (EV_P2 / vp_vertex2_flat); else the lane walks its list
     PathQueue jobs;         // DRT = 1: job records written at the end of pass 2; DRT = 2: r0/r1 = where and what to scatter
 };
 
@@ -121,6 +132,18 @@ __device__ __forceinline__ float4 *vp_nee_record(const VpSink &sk, const VpLane 
     return sk.arena + ((size_t) ln.vbase + (size_t) sk.vcap) * 4 + i;
 }
 
+// RCV_PREFETCH_VERTEX = 1: pass 2 asks for the NEXT vertex record (L1) when it leaves a vertex — the record is an L2
+// hit whose latency the vertex step otherwise waits out at its first use (10 % of the adjoint's stall samples, r2a)
+#ifndef RCV_PREFETCH_VERTEX
+#define RCV_PREFETCH_VERTEX 0
+#endif
+__device__ __forceinline__ void prefetch_l1(const void *p) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void) p;
+#endif
+}
 // end of pass 2 (or of a render-only path)
 template <int DRT = 0>
 __device__ __forceinline__ void vp_finish(VpLane &ln, VpSink &sk) {
@@ -154,6 +177,14 @@ __device__ __forceinline__ void vp_end_pass(const SceneK &S, VpLane &ln, VpSink 
     sk.n_paths++;                                   // pass 1 complete
     // ln.dL = d(develop o put)/dL * grad_in of this sample came with the path record (computed by ray generation)
     // pass 2 starts from state_in = the pass-1 result (:68) with the secondary sampler (:119-120)
+    if (DRT == 0 && sk.flat && !(ln.flags & VF_ANY_OVF)) {
+        // pass 2 of this lane runs vertex-parallel: result = the pass-1 radiance, vk = 0 vertices done so far
+        ln.flags = VF_ADJ;
+        ln.vk = 0;
+        if (ln.nvert > 0) ln.ev = EV_P2;
+        else vp_finish<DRT>(ln, sk);
+        return;
+    }
     sampler_seed(ln.alt, sk.alt_seed, ln.idx);
     ln.flags = VF_ADJ;
     ln.vk = 0;
@@ -165,8 +196,12 @@ __device__ __forceinline__ void vp_end_pass(const SceneK &S, VpLane &ln, VpSink 
         ln.last_pdf = 0.f;
         ln.saved = 0;
     }
-    if (ln.nvert > 0) ln.ev = EV_SCAT;
-    else vp_finish<DRT>(ln, sk);
+    if (ln.nvert > 0) {
+        ln.ev = EV_SCAT;
+#if RCV_PREFETCH_VERTEX
+        prefetch_l1(vp_record(sk, ln, 0));
+#endif
+    } else vp_finish<DRT>(ln, sk);
 }
 
 // Start of a path up to the first loop iteration: camera ray, dummy channel
@@ -331,8 +366,12 @@ __device__ __forceinline__ void vp_nee_done(const SceneK &S, const GridK &G, VpL
 template <int DRT = 0>
 __device__ __forceinline__ void vp_next_vertex(VpLane &ln, VpSink &sk) {
     ln.vk += 1;
-    if (ln.vk < ln.nvert) ln.ev = EV_SCAT;
-    else vp_finish<DRT>(ln, sk);
+    if (ln.vk < ln.nvert) {
+        ln.ev = EV_SCAT;
+#if RCV_PREFETCH_VERTEX
+        prefetch_l1(vp_record(sk, ln, ln.vk));
+#endif
+    } else vp_finish<DRT>(ln, sk);
 }
 template <int DRT = 0>
 __device__ __forceinline__ void vp_replay_done(VpLane &ln, VpSink &sk) {
@@ -393,7 +432,7 @@ __device__ __forceinline__ void vp_collide_post(const SceneK &S, const GRID &G, 
             // instead of replaying the ray in pass 2.  running_t is idle during a shadow ray: it counts the records.
             int n = __float_as_int(ln.running_t);
             if (n < kNeeCap) *vp_nee_record(sk, ln, n) = make_float4(m.p.x, m.p.y, m.p.z, (tr > 0.f) ? ((-inv_mu) / tr) : 0.f);
-            else ln.flags |= VF_NEE_OVF;
+            else ln.flags |= VF_NEE_OVF | VF_ANY_OVF;
             ln.running_t = __int_as_float(n + 1);
         }
         if (BW && (ln.flags & VF_REPLAY)) {                           // :496-505
@@ -627,6 +666,93 @@ __device__ __forceinline__ void vp_vertex2(const SceneK &S, const GridK &G, VpLa
         return;
     }
     vp_next_vertex<DRT>(ln, sk);
+}
+
+// PCG32 skip-ahead (O'Neill's pcg_advance_lcg_64): the state after `delta` draws
+__host__ __device__ __forceinline__ void pcg_advance(Pcg &r, uint64_t delta) {
+    uint64_t cur_mult = 0x5851f42d4c957f2dULL, cur_plus = r.inc, acc_mult = 1u, acc_plus = 0u;
+    while (delta > 0) {
+        if (delta & 1u) { acc_mult *= cur_mult; acc_plus = acc_plus * cur_mult + cur_plus; }
+        cur_plus = (cur_mult + 1u) * cur_plus;
+        cur_mult *= cur_mult;
+        delta >>= 1;
+    }
+    r.state = acc_mult * r.state + acc_plus;
+}
+
+// Pass 2 of ONE vertex, outside the lane machine (RCV_FLAT_PASS2, use_drt = False): vertex k of the lane whose records
+// start at record `vbase`, global lane index idx, with res0 = the lane's running result before vertex k0 <= k.  Exactly
+// what vp_vertex2 computes when the lane reaches vertex k: the running result is rebuilt by subtracting the shadow-ray
+// contributions of vertices k0 .. k-1 in order (:227), the secondary sampler is skipped ahead to its 4 k-th draw (four
+// draws per vertex, :608).  Returns the running result AFTER vertex k.  Every shadow ray of such a lane had its
+// gradients scattered in pass 1 (VR_NEE_DONE): lanes with an overflowed ray walk their list in the machine instead.
+__device__ __forceinline__ V3 vp_vertex2_flat(const SceneK &S, const GridK &G, VpSink &sk, uint32_t vbase, int k0, int k, V3 res0,
+                                              V3 dL, uint32_t idx) {
+    V3 result = res0;
+    for (int j = k0; j < k; ++j) {
+        const float4 *rj = sk.arena + ((size_t) vbase + (size_t) j) * 4;
+        if (__float_as_uint(rj[1].w) & VR_NEE) {
+            float4 a = rj[2], b = rj[3];
+            result = result - mk3(a.z, a.w, b.x);
+        }
+    }
+    Pcg alt;
+    sampler_seed(alt, sk.alt_seed, idx);
+    pcg_advance(alt, 4u * (uint64_t) k);
+    const float4 *r = sk.arena + ((size_t) vbase + (size_t) k) * 4;
+    float4 r0 = r[0], r1 = r[1];
+    const V3 o = mk3(r0.x, r0.y, r0.z), d = mk3(r1.x, r1.y, r1.z);
+    const float interval = r0.w;
+    const uint32_t vf = __float_as_uint(r1.w);
+    if (vf & VR_SCATTER) {
+        V3 mei_p = ray_at(o, d, interval);                            // :384
+        Tri T = tri_setup(S, G, mei_p);
+        float st = lookup_sigma1(S, G, T);                            // :386-388
+#if RCV_VERTEX_ALBEDO
+        V3 albedo;
+        if (vf & VR_ALBEDO) { float4 r3 = r[3]; albedo = mk3(r3.y, r3.z, r3.w); }
+        else albedo = lookup_albedo(G, T, 1);
+#else
+        V3 albedo = lookup_albedo(G, T, 1);                           // :154
+#endif
+        sk.cnt.scat++;
+        V3 inv_pdf = splat3(1.f / st);                                // scattering term (:165-185)
+        V3 Li = result / vmax3(splat3(1e-8f), albedo);
+        V3 c = (dL * Li) * inv_pdf;
+        float g_st = (c.x * albedo.x + c.y * albedo.y) + c.z * albedo.z;
+        V3 g_al = c * splat3(st);
+        if (T.inside) {
+            float sg = S.scale * g_st;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float w = tri_weight(T, q);
+                uint32_t v = tri_voxel(G, T, q);
+#if !RCV_GRAD_BRICKS
+                red_add_f32(sk.D.gsig + v, w * sg);
+#endif
+                red_add_v4(sk.D.galb + v, w * g_al.x, w * g_al.y, w * g_al.z, 0.f);
+            }
+#if RCV_GRAD_BRICKS
+            red_sigma_site(G, sk.D, T, sg);
+#endif
+            sk.cnt.g_sig++; sk.cnt.g_alb++;
+        }
+    }
+    {                                                                 // transmittance term (:194-202, :597-620)
+        V3 aw = dL * result;                                          // :198
+        float inv_pdf = interval / 4.f;                               // :617
+        float g = -((aw.x * inv_pdf) + (aw.y * inv_pdf) + (aw.z * inv_pdf));
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+            float t = pcg_f32(alt) * interval;                        // :608
+            scatter_sigma_t(S, G, sk.D, ray_at(o, d, t), g, sk.cnt);
+        }
+    }
+    if (vf & VR_NEE) {                                                // :227 (its gradients were scattered in pass 1)
+        float4 r2 = r[2], r3 = r[3];
+        result = result - mk3(r2.z, r2.w, r3.x);
+    }
+    return result;
 }
 
 template <bool BW, int DRT = 0>

@@ -23,6 +23,8 @@ using namespace rcv;
 
 namespace {
 
+int g_flat = 0;      // emu_set_flat: run pass 2 of the volpathsimple adjoint through vp_vertex2_flat (as the pool kernel does)
+
 // SceneK of a description, with the `envmap` tables (host memory) when the scene has one
 struct HostScene {
     SceneK S;
@@ -178,7 +180,17 @@ void run_vps(const SceneK &S, const GRID &G, VpSink &sk) {
         VpLane ln; ln.flags = 0;
         vp_load(ln, sk, hq.Q, pos, 0u);
         while (ln.ev != EV_INIT) {
-            if (ln.ev == EV_COLL) {
+            if (ln.ev == EV_P2) {
+                // the flattened pass 2: every vertex on its own, from the lane's pass-1 result (k0 = 0) or from the running
+                // result a previous round left (k0 = k): both must give what the list walk gives
+                V3 run = ln.result;
+                for (int k = 0; k < ln.nvert; ++k)
+                    run = (k & 1) ? vp_vertex2_flat(S, G, sk, ln.vbase, k, k, run, ln.dL, ln.idx)
+                                  : vp_vertex2_flat(S, G, sk, ln.vbase, 0, k, ln.result, ln.dL, ln.idx);
+                (void) run;
+                sk.n_paths++;
+                ln.ev = EV_INIT;
+            } else if (ln.ev == EV_COLL) {
                 EMU_VP_COLLIDE<BW>(S, G, mu, inv_mu, ln, sk);
             } else if (ln.ev == EV_SCAT) {
                 vp_vertex<BW>(S, G, ln, sk);
@@ -279,6 +291,8 @@ void run_surface(const SceneK &S, const GRID &G, SfSink &sk) {
 
 extern "C" {
 
+void emu_set_flat(int on) { g_flat = on; }
+
 // scenes with rectangles: the two-state / single-state primal (adj == 0; mode as emu_twostates) or the inherited
 // prbvolpath adjoint of state `new` (adj == 1)
 int emu_surface(const rcv_scene_desc *d, const float *so, const float *ao, const float *sn, const float *an, int nz, int ny, int nx,
@@ -314,7 +328,7 @@ int emu_vps_drt_stages(const rcv_scene_desc *d, const float *sn, const float *an
     Packed P; pack(*d, sn, an, sn, an, nz, ny, nx, P, factor);
     for (int i = 0; i < 8; ++i) counters[i] = 0;
     VpSink sk; sk.accum = nullptr; sk.D.gsig = gsig; sk.D.galb = (float4 *) galb4; sk.grad_img = grad_img; sk.film_w = film_w;
-    sk.seed = seed; sk.spp = spp; sk.alt_seed = alt_seed; sk.drt_mis = use_mis;
+    sk.seed = seed; sk.spp = spp; sk.alt_seed = alt_seed; sk.drt_mis = use_mis; sk.flat = 0;
     sk.cnt.coll = sk.cnt.scat = sk.cnt.g_sig = sk.cnt.g_alb = 0; sk.n_paths = 0;
     HostBricks hb(nx, ny, nz, sk.D);
     if (factor > 0) run_vps_drt(S, P.G, sk);
@@ -359,7 +373,7 @@ int emu_vps_sg(const rcv_scene_desc *d, const float *sn, const float *an, int nz
     Packed P; pack(*d, sn, an, sn, an, nz, ny, nx, P, factor);
     for (int i = 0; i < 8; ++i) counters[i] = 0;
     VpSink sk; sk.accum = (float4 *) accum; sk.D.gsig = gsig; sk.D.galb = (float4 *) galb4; sk.grad_img = grad_img; sk.film_w = film_w;
-    sk.seed = seed; sk.spp = spp; sk.alt_seed = alt_seed; sk.drt_mis = 0;
+    sk.seed = seed; sk.spp = spp; sk.alt_seed = alt_seed; sk.drt_mis = 0; sk.flat = g_flat;
     sk.cnt.coll = sk.cnt.scat = sk.cnt.g_sig = sk.cnt.g_alb = 0; sk.n_paths = 0;
     HostBricks hb(nx, ny, nz, sk.D);
     if (factor > 0) {

@@ -32,6 +32,7 @@ def _load_emu(name):
                                C.c_void_p, C.c_void_p, f32, f32, f32, u64, C.c_int]
     lib.emu_vps_backward_lane.argtypes = [C.c_void_p, f32, f32, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32,
                                           C.c_void_p, C.c_void_p, f32, f32, u64, C.c_int, C.c_int]
+    lib.emu_set_flat.argtypes = [C.c_int]
     lib.emu_vps_drt_stages.argtypes = [C.c_void_p, f32, f32, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32,
                                        C.c_void_p, C.c_void_p, f32, f32, u64, C.c_int, C.c_int]
     return lib
@@ -486,3 +487,28 @@ def test_randomised_scenes_lane_for_lane(oracle, emu, case):
                            d1, d4, cnt, factor, 1)
     ds, da = oracle.vps_backward(d, mn, 7, 2, gimg, threads=1, film_w=film_w, use_drt=True)
     assert tol(d1, ds) and tol(d4[..., 0:3], da)
+
+
+def test_flattened_pass2_equals_the_list_walk(oracle, emu):
+    """RCV_FLAT_PASS2 (off by default in the library): pass 2 of the volpathsimple adjoint taken vertex by vertex outside the
+    lane machine — running result rebuilt from the records, secondary sampler skipped ahead with pcg_advance — scatters
+    exactly what the list walk scatters (same sites, same values, same order on the host)."""
+    d = small_scene(40, 36, max_depth=12, rr_depth=4).to_desc()
+    _, (sn, an) = media(20)
+    H, W = d.film_height, d.film_width
+    grad_img = (np.random.default_rng(3).standard_normal((H, W, 3)) / (H * W * 3)).astype(np.float32)
+    seed_grad, spp = 0xC09848F2, 3
+    film_w = oracle.film_weights(d, seed_grad, spp)
+    out = []
+    try:
+        for flat in (0, 1):
+            emu.emu_set_flat(flat)
+            acc = np.zeros((H, W, 4), np.float32); g1 = np.zeros((*sn.shape[:3], 1), np.float32); g4 = np.zeros((*sn.shape[:3], 4), np.float32)
+            cnt = np.zeros(8, np.uint64)
+            emu.emu_vps(C.addressof(d), sn, an, *sn.shape[:3], seed_grad, spp, 1, oracle.alt_seed(seed_grad), grad_img.ctypes.data,
+                        film_w.ctypes.data, acc, g1, g4, cnt)
+            out.append((g1, g4, cnt))
+    finally:
+        emu.emu_set_flat(0)
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
+    assert np.abs(out[1][0]).max() > 0
