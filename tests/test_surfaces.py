@@ -347,3 +347,48 @@ def test_gpu_boxed_scene_through_the_plugins(oracle):
     img.sum().backward()
     gs, ga = oracle.prb_backward(d, m, 2, 4, np.ones((20, 24, 3), np.float32))
     assert rel_l2(opt[ks].grad.cpu().numpy(), gs) < 1e-4 and rel_l2(opt[ka].grad.cpu().numpy(), ga) < 1e-4
+
+
+# ---- committed golden vectors of the round-2 features (tests/golden/oracle_r2.npz) ---------------------------------------
+def _golden_r2():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_r2.npz"))
+
+
+def test_golden_r2_oracle(oracle):
+    from golden.make_golden_r2 import compute
+    ref = _golden_r2()
+    out, _ = compute(oracle)
+    assert set(out) == set(ref.files)
+    for k, v in out.items():
+        if "grad" in k:
+            assert rel_l2(v, ref[k]) < 1e-6, k          # accumulated in float64, rounded once
+        else:
+            assert np.array_equal(v, ref[k]), k
+
+
+@pytest.mark.gpu
+def test_golden_r2_on_gpu(gpu_ctx):
+    """The CUDA path reproduces the committed vectors (no oracle in the loop)."""
+    from golden.make_golden_r2 import configs
+    from helpers import gpu_set_states, to_cuda
+    from recursive_control_variates_b200 import _abi
+    ref = _golden_r2()
+    env, box, old, new = configs()
+    gimg = (np.arange(16 * 12 * 3, dtype=np.float32).reshape(12, 16, 3) % 7 - 3) / (16 * 12 * 3)
+    gpu_ctx.set_majorant_factor(0); gpu_ctx.set_drt(False)
+    gpu_ctx.set_scene(env.to_desc())
+    gpu_set_states(gpu_ctx, old, new)
+    go, gn = gpu_ctx.render_twostates_accum(seed=7, spp=1)
+    assert np.array_equal(go.cpu().numpy(), ref["env_acc_old"]) and np.array_equal(gn.cpu().numpy(), ref["env_acc_new"])
+    assert np.array_equal(gpu_ctx.render_adjoint_primal_accum(seed=8, spp=1).cpu().numpy(), ref["env_vps_acc"])
+    gpu_ctx.grad_zero(); gpu_ctx.render_backward(0x5D8714D7, 2, to_cuda(gimg))
+    gs, ga = gpu_ctx.grad_read()
+    assert rel_l2(gs.cpu().numpy(), ref["env_grad_sigma_t"]) < 1e-4 and rel_l2(ga.cpu().numpy(), ref["env_grad_albedo"]) < 1e-4
+    gpu_ctx.set_scene(box.to_desc())
+    gpu_set_states(gpu_ctx, old, new)
+    go, gn = gpu_ctx.render_twostates_accum(seed=7, spp=1)
+    assert np.array_equal(go.cpu().numpy(), ref["box_acc_old"]) and np.array_equal(gn.cpu().numpy(), ref["box_acc_new"])
+    gpu_ctx.grad_zero(); gpu_ctx.render_backward(0x5D8714D7, 2, to_cuda(gimg), adjoint=_abi.RCV_ADJOINT_PRBVOLPATH)
+    gs, ga = gpu_ctx.grad_read()
+    assert rel_l2(gs.cpu().numpy(), ref["box_grad_sigma_t"]) < 1e-4 and rel_l2(ga.cpu().numpy(), ref["box_grad_albedo"]) < 1e-4
