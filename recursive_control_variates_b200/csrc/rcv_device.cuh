@@ -846,6 +846,23 @@ __device__ __forceinline__ void film_position(const SceneK &S, uint32_t seed, ui
 // Box: the pixel that contains it, weight 1.  Gaussian (hdrfilm default): radius 4 stddev, separable weights
 // max(0, exp(a x^2) - exp(a r^2)) at the pixel centres within the radius (at most 4 x 4).
 // ----------------------------------------------------------------------------
+// the gaussian filter's separable weights of a sample at film position (fx, fy): wx[i] / wy[j] for pixel columns lox + i /
+// rows loy + j, i, j < count (0 beyond)
+__device__ __forceinline__ void film_gauss_weights(const SceneK &S, float fx, float fy, int &lox, int &loy, int &count, float (&wx)[4],
+                                                   float (&wy)[4]) {
+    const float sd = S.rf_stddev, r = 4.f * sd;
+    const float alpha = -1.f / ((2.f * sd) * sd);
+    const float bias = spec_exp(alpha * (r * r));
+    count = 2 * (int) ceilf(r);
+    const float px = fx - 0.5f, py = fy - 0.5f;
+    lox = (int) ceilf(px - r); loy = (int) ceilf(py - r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float dx = (float) (lox + i) - px, dy = (float) (loy + i) - py;
+        wx[i] = (i < count) ? fmax_(0.f, spec_exp(alpha * (dx * dx)) - bias) : 0.f;
+        wy[i] = (i < count) ? fmax_(0.f, spec_exp(alpha * (dy * dy)) - bias) : 0.f;
+    }
+}
 template <class F>
 __device__ __forceinline__ void film_for_each(const SceneK &S, float fx, float fy, F f) {
     const int W = (int) S.W, H = (int) S.H;
@@ -854,19 +871,9 @@ __device__ __forceinline__ void film_for_each(const SceneK &S, float fx, float f
         if (ix >= 0 && ix < W && iy >= 0 && iy < H) f(iy * W + ix, 1.f);
         return;
     }
-    const float sd = S.rf_stddev, r = 4.f * sd;
-    const float alpha = -1.f / ((2.f * sd) * sd);
-    const float bias = spec_exp(alpha * (r * r));
-    const int count = 2 * (int) ceilf(r);
-    const float px = fx - 0.5f, py = fy - 0.5f;
-    const int lox = (int) ceilf(px - r), loy = (int) ceilf(py - r);
+    int lox, loy, count;
     float wx[4], wy[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        float dx = (float) (lox + i) - px, dy = (float) (loy + i) - py;
-        wx[i] = (i < count) ? fmax_(0.f, spec_exp(alpha * (dx * dx)) - bias) : 0.f;
-        wy[i] = (i < count) ? fmax_(0.f, spec_exp(alpha * (dy * dy)) - bias) : 0.f;
-    }
+    film_gauss_weights(S, fx, fy, lox, loy, count, wx, wy);
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll

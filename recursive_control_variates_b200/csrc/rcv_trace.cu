@@ -190,18 +190,114 @@ __global__ void __launch_bounds__(kDrtBlock, RCV_DRT_MINBLOCKS) k_vps_drt(const 
 static constexpr int kWfBlock = RCV_WF_BLOCK;
 static constexpr int kWfMinBlocks = RCV_WF_MINBLOCKS;
 
+
+// ---------------------------------------------------------------------------
+// Warp-aggregated film splats.  Lane indices are pixel-major (idx = pixel * spp + k), so when the number of samples a
+// launch takes per pixel is a multiple of 32 a warp of the one-thread-per-lane kernels holds 32 samples of ONE pixel: their
+// reconstruction-filter footprints (the pixel itself for the box filter, up to 4 x 4 pixels for the gaussian) fall into
+// the 5 x 5 tile centred on that pixel, and the warp adds ONE value per tile cell instead of one per lane and footprint
+// pixel (gaussian film weights: 25 reductions per warp instead of 512).
+// ---------------------------------------------------------------------------
+// v[k], k < 32, on every lane -> the sum over the warp of v[lane], on lane `lane` (31 shuffles)
+__device__ __forceinline__ float warp_reduce_scatter32(float (&v)[32]) {
+    const unsigned lane = threadIdx.x & 31;
+#pragma unroll
+    for (int h = 16; h >= 1; h >>= 1) {
+        const bool up = (lane & h) != 0;
+#pragma unroll
+        for (int i = 0; i < h; ++i) {
+            const float send = up ? v[i] : v[i + h];
+            const float keep = up ? v[i + h] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+        }
+    }
+    return v[0];
+}
+// this lane's filter weights on the 5 x 5 tile whose corner pixel is (tx, ty): w[5 * j + i] for pixel (tx + i, ty + j),
+// the same products wy * wx film_for_each hands out.  false: the footprint does not fit the tile (never for samples of the
+// tile's centre pixel; the caller then falls back to per-lane splats)
+__device__ __forceinline__ bool film_tile_weights(const SceneK &S, float fx, float fy, int tx, int ty, float (&w)[32]) {
+    float cx[5], cy[5];
+    bool ok;
+    if (S.rfilter != 1) {
+        const int dx = (int) floorf(fx) - tx, dy = (int) floorf(fy) - ty;
+        ok = dx >= 0 && dx < 5 && dy >= 0 && dy < 5;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) { cx[i] = (i == dx) ? 1.f : 0.f; cy[i] = (i == dy) ? 1.f : 0.f; }
+    } else {
+        int lox, loy, count;
+        float wx[4], wy[4];
+        film_gauss_weights(S, fx, fy, lox, loy, count, wx, wy);
+        const int dx = lox - tx, dy = loy - ty;
+        ok = (dx == 0 || dx == 1) && (dy == 0 || dy == 1);
+        cx[0] = dx == 0 ? wx[0] : 0.f; cy[0] = dy == 0 ? wy[0] : 0.f;
+#pragma unroll
+        for (int i = 1; i < 4; ++i) { cx[i] = dx == 0 ? wx[i] : wx[i - 1]; cy[i] = dy == 0 ? wy[i] : wy[i - 1]; }
+        cx[4] = dx == 0 ? 0.f : wx[3]; cy[4] = dy == 0 ? 0.f : wy[3];
+    }
+#pragma unroll
+    for (int c = 0; c < 32; ++c) w[c] = (c < 25) ? cy[c / 5] * cx[c % 5] : 0.f;
+    return ok;
+}
+// true when the whole warp is live and its lanes are samples of one pixel (then *pixel is that pixel)
+__device__ __forceinline__ bool warp_one_pixel(bool live, uint64_t j, uint32_t ns, uint32_t *pixel) {
+    const uint32_t pix = (uint32_t) (j / ns);
+    const uint32_t p0 = __shfl_sync(0xffffffffu, pix, 0);
+    *pixel = p0;
+    return __all_sync(0xffffffffu, live && pix == p0);
+}
+
 // --- ray generation: one thread per lane, no divergence to speak of -----------
 template <int MODE>
 __global__ void __launch_bounds__(kBlock) k_twostates_raygen(const __grid_constant__ SceneK S, uint32_t seed, uint32_t spp,
                                                              uint32_t spp_begin, uint32_t ns, uint64_t n_local, float4 *acc_old,
                                                              float4 *acc_new, PathQueue Q, Counters *C) {
     uint64_t j = (uint64_t) blockIdx.x * kBlock + threadIdx.x;
-    TsLane ln; ln.ev = EV_INIT;
+    const bool live = j < n_local;
+    TsLane ln; ln.ev = EV_INIT; ln.fx = 0.f; ln.fy = 0.f; ln.pix = -1;
+    ln.L_old = mk3(0, 0, 0); ln.L_new = mk3(0, 0, 0);
     TsSink sk; sk.acc_old = acc_old; sk.acc_new = acc_new; sk.n_coll = sk.n_scat = sk.n_paths = 0;
-    if (j < n_local) ts_raygen<MODE>(S, ln, sk, seed, spp, global_lane(j, spp, spp_begin, ns));
-    bool enter = (j < n_local) && ln.ev == EV_COLL;
+    sk.defer = true;                                      // paths that end here (they missed the medium) are splatted below
+    if (live) ts_raygen<MODE>(S, ln, sk, seed, spp, global_lane(j, spp, spp_begin, ns));
+    bool enter = live && ln.ev == EV_COLL;
     unsigned long long pos = queue_slot(Q.count, enter);
     if (enter) ts_store(ln, Q, pos);
+    // film splats of the finished paths: one value per pixel of the 5 x 5 tile and warp when the warp's lanes are samples of
+    // one pixel (see warp_one_pixel), else per lane.  Old and new radiance of such a path are the same number (unit
+    // throughputs): one reduction serves both accumulators.
+    const bool fin = live && ln.ev == EV_INIT;
+    const V3 L = (MODE == 1) ? ln.L_old : ln.L_new;
+    uint32_t pixel;
+    bool one = (S.rfilter == 1) && warp_one_pixel(live, j, ns, &pixel);   // box filter: one splat per lane is cheaper than the tile
+    const int py = (int) (pixel / S.W), px = (int) (pixel - (uint32_t) py * S.W);
+    float w[32];
+    if (one) one = __all_sync(0xffffffffu, film_tile_weights(S, ln.fx, ln.fy, px - 2, py - 2, w));
+    if (one) {
+        float v[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) v[c] = fin ? w[c] * L.x : 0.f;
+        const float sx = warp_reduce_scatter32(v);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) v[c] = fin ? w[c] * L.y : 0.f;
+        const float sy = warp_reduce_scatter32(v);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) v[c] = fin ? w[c] * L.z : 0.f;
+        const float sz = warp_reduce_scatter32(v);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) v[c] = fin ? w[c] : 0.f;
+        const float sw = warp_reduce_scatter32(v);
+        const int c = (int) (threadIdx.x & 31), x = px - 2 + c % 5, y = py - 2 + c / 5;
+        if (c < 25 && sw != 0.f && x >= 0 && x < (int) S.W && y >= 0 && y < (int) S.H) {
+            const int p = y * (int) S.W + x;
+            if (MODE != 2) red_add_v4(acc_old + p, sx, sy, sz, sw);
+            if (MODE != 1) red_add_v4(acc_new + p, sx, sy, sz, sw);
+        }
+    } else if (fin) {
+        film_for_each(S, ln.fx, ln.fy, [&](int p, float wt) {
+            if (MODE != 2) red_add_v4(acc_old + p, ln.L_old.x * wt, ln.L_old.y * wt, ln.L_old.z * wt, wt);
+            if (MODE != 1) red_add_v4(acc_new + p, ln.L_new.x * wt, ln.L_new.y * wt, ln.L_new.z * wt, wt);
+        });
+    }
     counter_flush(C, 6, sk.n_paths);
 }
 
@@ -818,11 +914,21 @@ cudaError_t launch_vps_backward(const LaunchCfg &cfg, const SceneK &S, const Gri
 __global__ void __launch_bounds__(kBlock) k_film_weights(const __grid_constant__ SceneK S, uint32_t seed, uint32_t spp,
                                                          uint32_t spp_begin, uint32_t ns, uint64_t n_local, float *film_w) {
     uint64_t j = (uint64_t) blockIdx.x * kBlock + threadIdx.x;
-    if (j >= n_local) return;
-    const uint64_t idx = global_lane(j, spp, spp_begin, ns);
-    float fx, fy;
-    film_position(S, seed, spp, (uint32_t) idx, fx, fy);
-    film_for_each(S, fx, fy, [&](int p, float w) { red_add_f32(film_w + p, w); });
+    const bool live = j < n_local;
+    float fx = 0.f, fy = 0.f;
+    if (live) film_position(S, seed, spp, (uint32_t) global_lane(j, spp, spp_begin, ns), fx, fy);
+    uint32_t pixel;
+    bool one = warp_one_pixel(live, j, ns, &pixel);
+    const int py = (int) (pixel / S.W), px = (int) (pixel - (uint32_t) py * S.W);
+    float w[32];
+    if (one) one = __all_sync(0xffffffffu, film_tile_weights(S, fx, fy, px - 2, py - 2, w));
+    if (one) {
+        const float sum = warp_reduce_scatter32(w);
+        const int c = (int) (threadIdx.x & 31), x = px - 2 + c % 5, y = py - 2 + c / 5;
+        if (c < 25 && sum != 0.f && x >= 0 && x < (int) S.W && y >= 0 && y < (int) S.H) red_add_f32(film_w + y * (int) S.W + x, sum);
+        return;
+    }
+    if (live) film_for_each(S, fx, fy, [&](int p, float w) { red_add_f32(film_w + p, w); });
 }
 
 // adds the film weights of samples [spp_begin, spp_end) of every pixel to film_w (zeroed first when `zero`)

@@ -57,10 +57,12 @@ struct TsLane {
 struct TsSink {
     float4 *acc_old, *acc_new;
     unsigned n_coll, n_scat, n_paths;
+    bool defer = false;     // ray generation: leave the film splat of a finished path to the kernel (warp-aggregated there)
 };
 
 template <int MODE>
 __device__ __forceinline__ void ts_finish(const SceneK &S, TsLane &ln, TsSink &sk) {
+    if (sk.defer) { sk.n_paths++; ln.ev = EV_INIT; return; }
     if (S.rfilter == 0) {                               // box filter: the pixel that contains the sample, weight 1
         if (ln.pix >= 0) {
             if (MODE != 2) red_add_v4(sk.acc_old + ln.pix, ln.L_old.x, ln.L_old.y, ln.L_old.z, 1.f);
