@@ -86,6 +86,10 @@ __global__ void k_majorant_final(const float *block_max, int n_blocks, float sca
         majorants[1] = scale * mx;
     }
 }
+__device__ __forceinline__ void st_global_v8(float4 *p, float a, float b, float c, float d, float e, float f, float g, float h) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "f"(e), "f"(f), "f"(g), "f"(h)
+                 : "memory");
+}
 // gather bricks: the 8 corner values of every interpolation cell, contiguous (rcv_device.cuh, GridK)
 __global__ void __launch_bounds__(kBlock) k_build_bricks(const float2 *__restrict__ sig2, int nx, int ny, int nz,
                                                          float4 *__restrict__ blk2, float4 *__restrict__ blk1) {
@@ -98,10 +102,10 @@ __global__ void __launch_bounds__(kBlock) k_build_bricks(const float2 *__restric
         float2 v[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) v[k] = __ldg(sig2 + cell_corner(nx, ny, nz, cx, cy, cz, k));
-#pragma unroll
-        for (int j = 0; j < 4; ++j) blk2[4 * c + j] = make_float4(v[2 * j].x, v[2 * j].y, v[2 * j + 1].x, v[2 * j + 1].y);
-        blk1[2 * c] = make_float4(v[0].y, v[1].y, v[2].y, v[3].y);
-        blk1[2 * c + 1] = make_float4(v[4].y, v[5].y, v[6].y, v[7].y);
+        // 256-bit stores (sm_100 STG.256): every store writes whole 32-byte sectors — three per cell instead of six halves
+        st_global_v8(blk2 + 4 * c, v[0].x, v[0].y, v[1].x, v[1].y, v[2].x, v[2].y, v[3].x, v[3].y);
+        st_global_v8(blk2 + 4 * c + 2, v[4].x, v[4].y, v[5].x, v[5].y, v[6].x, v[6].y, v[7].x, v[7].y);
+        st_global_v8(blk1 + 2 * c, v[0].y, v[1].y, v[2].y, v[3].y, v[4].y, v[5].y, v[6].y, v[7].y);
     }
 }
 
