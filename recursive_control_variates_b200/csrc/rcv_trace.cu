@@ -432,6 +432,15 @@ __global__ void __launch_bounds__(kWfBlock, RCV_VP_MINBLOCKS) k_vps_wavefront(co
 #ifndef RCV_VP_POOL_BLOCK
 #define RCV_VP_POOL_BLOCK RCV_POOL_BLOCK
 #endif
+// r2x (profiles/README.md): C1 2.98 ms against 3.12 ms, C2 unchanged — the cost of a tail step is the dependent chain
+// inside the collision handler, not the pool's scheduling.  Off.
+#ifndef RCV_STICKY_ROUNDS
+#define RCV_STICKY_ROUNDS 0
+#endif
+#ifndef RCV_STICKY_MAX
+#define RCV_STICKY_MAX 8
+#endif
+static constexpr int kStickyMax = RCV_STICKY_MAX;          // collision steps a sticky round takes at most before it reschedules
 static constexpr int kPoolBlock = RCV_POOL_BLOCK;          // two-state kernels
 static constexpr int kVpPoolBlock = RCV_VP_POOL_BLOCK;     // volpathsimple kernels
 
@@ -483,11 +492,21 @@ __global__ void __launch_bounds__(kPoolBlock, RCV_TS_POOL_MINBLOCKS) k_twostates
         if (sel == EV_COLL) {
             const int n = min(pool_list(M.coll, list), 32);
             const int s = pool_slot(list, n, 0);
+            // Sticky round: when nothing else in this pool could run (no vertex, no slow step, no record to take) the same
+            // lanes go straight into their next tentative collision from registers, for as long as all of them still want
+            // one — the scheduling and the shared-memory round trip of a round are skipped.  This is the regime a warp
+            // spends most of a small launch in (C1: one long lane per warp after the first 0.1 ms).
+            const bool sticky = RCV_STICKY_ROUNDS && M.n_scat == 0 && M.n_slow == 0 && M.n_coll <= 32;
+            TsLane ln;
+            ln.ev = EV_INIT;
+            if (s >= 0) { ts_pool_load_hot(pw, s, ln); ln.ev = EV_COLL; }
+            int left = kStickyMax;
+            bool again;
+            do {
+                if (s >= 0) ts_collide<MODE>(S, G, mu, inv_mu, ln, sk);
+                again = sticky && (--left > 0) && __all_sync(0xffffffffu, s < 0 || ln.ev == EV_COLL);
+            } while (again);
             if (s >= 0) {
-                TsLane ln;
-                ts_pool_load_hot(pw, s, ln);
-                ln.ev = EV_COLL;
-                ts_collide<MODE>(S, G, mu, inv_mu, ln, sk);
                 ts_pool_store_coll(pw, s, ln);
                 cls[s] = (unsigned char) ln.ev;
             }
@@ -635,15 +654,26 @@ __global__ void __launch_bounds__(kVpPoolBlock, RCV_POOL_MINBLOCKS) k_vps_pool(c
         if (sel == EV_COLL) {
             const int n = min(pool_list(M.coll, list), 32);
             const int s = pool_slot(list, n, 0);
+            const bool sticky = RCV_STICKY_ROUNDS && M.n_scat == 0 && M.n_slow == 0 && M.n_coll <= 32;   // see k_twostates_pool
+            ln.ev = EV_INIT;
             if (s >= 0) {
                 vp_pool_load_hot(pw, s, ln);
                 ln.ev = EV_COLL;
                 ln.vbase = (slot0 + (uint32_t) s) * (vcap + kNeeCap / 4);    // a cold word; the collision records live behind it
+            }
+            int left = kStickyMax;
+            bool again;
+            do {
+                if (s >= 0) {
 #if RCV_SPEC_COLLIDE > 1
-                vp_collide_spec<BACKWARD>(S, G, mu, inv_mu, ln, sk);
+                    vp_collide_spec<BACKWARD>(S, G, mu, inv_mu, ln, sk);
 #else
-                vp_collide<BACKWARD>(S, G, mu, inv_mu, ln, sk);
+                    vp_collide<BACKWARD>(S, G, mu, inv_mu, ln, sk);
 #endif
+                }
+                again = sticky && (--left > 0) && __all_sync(0xffffffffu, s < 0 || ln.ev == EV_COLL);
+            } while (again);
+            if (s >= 0) {
                 vp_pool_store_coll(pw, s, ln);
                 cls[s] = (unsigned char) ln.ev;
             }
