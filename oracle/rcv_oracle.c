@@ -250,7 +250,7 @@ float orc_atan2f(float y, float x) {
 /* and rounded once (the library builds the same tables independently).        */
 /* ------------------------------------------------------------------------- */
 typedef struct {
-    const float *key; int w, h; float scale;
+    const float *key; int w, h; float scale; uint64_t checksum;
     float *data;      /* (h, w + 1, 3) scaled texels, column w = column 0 */
     float *cdf_m;     /* h: cdf over the h - 1 cell rows */
     float *cdf_c;     /* (h - 1, w + 1) */
@@ -262,7 +262,16 @@ static void quads_build(const rcv_scene_desc *S);
 static void env_build(const rcv_scene_desc *S) {
     quads_build(S);
     if (S->emitter_type != RCV_EMITTER_ENVMAP) return;
-    if (g_env.key == S->envmap_rgb && g_env.w == S->env_width && g_env.h == S->env_height && g_env.scale == S->env_scale) return;
+    /* the tables are cached across calls; the key includes a checksum of the texels (a freed bitmap's address may be reused) */
+    uint64_t sum = 1469598103934665603ULL;
+    {
+        const uint32_t *tx = (const uint32_t *) S->envmap_rgb;
+        size_t n = (size_t) 3 * S->env_width * S->env_height;
+        for (size_t i = 0; i < n; ++i) sum = (sum ^ tx[i]) * 1099511628211ULL;
+    }
+    if (g_env.key == S->envmap_rgb && g_env.w == S->env_width && g_env.h == S->env_height && g_env.scale == S->env_scale &&
+        g_env.checksum == sum) return;
+    g_env.checksum = sum;
     free(g_env.data); free(g_env.cdf_m); free(g_env.cdf_c); free(g_env.pdf);
     int w = S->env_width, h = S->env_height;
     g_env.key = S->envmap_rgb; g_env.w = w; g_env.h = h; g_env.scale = S->env_scale;

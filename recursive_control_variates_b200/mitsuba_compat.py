@@ -251,7 +251,10 @@ class Scene:
                     tex = np.asarray(v["bitmap"], dtype=np.float32)
                 else:
                     from .exrio import read_exr
-                    tex = np.asarray(read_exr(v["filename"]), dtype=np.float32)[..., :3]
+                    img, names = read_exr(v["filename"])          # channels in file order (EXR sorts them: B, G, R)
+                    if not all(c in names for c in "RGB"):
+                        raise ValueError(f"{v['filename']}: an RGB image is expected")
+                    tex = np.stack([img[..., names.index(c)] for c in "RGB"], axis=-1).astype(np.float32)
                 self.envmap = np.ascontiguousarray(tex)
                 self.env_scale = float(v.get("scale", 1.0))
                 tw = np.asarray(v.get("to_world", np.eye(4)), dtype=np.float64)

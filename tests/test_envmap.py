@@ -179,3 +179,30 @@ def test_gpu_envmap_parity(oracle, gpu_ctx, env_setup, tracer):
     finally:
         gpu_ctx.set_drt(False)
         gpu_ctx.set_tracer(3)
+
+
+def test_load_dict_envmap_from_exr(tmp_path):
+    """experiments.py:81-85: {'type': 'envmap', 'filename': ..., 'scale': 0.5} — the bitmap is read with exrio, reaches the
+    C-ABI description as the emitter, and a scene with a second emitter is refused."""
+    import torch
+    from recursive_control_variates_b200 import _abi
+    from recursive_control_variates_b200 import mitsuba_compat as mi
+    from recursive_control_variates_b200 import plugins  # noqa: F401
+    from recursive_control_variates_b200.exrio import write_exr
+    tex = sky(10, 16)
+    path = str(tmp_path / "sky.exr")
+    write_exr(path, tex)
+    _, new = media(6)
+    medium = {"type": "heterogeneous", "sigma_t": {"type": "gridvolume", "data": torch.from_numpy(new[0])},
+              "albedo": {"type": "gridvolume", "data": torch.from_numpy(new[1])}, "scale": 20.0}
+    sd = {"type": "scene", "object": {"type": "obj", "bsdf": {"type": "null"}, "interior": medium},
+          "envmap": {"type": "envmap", "filename": path, "scale": 0.5},
+          "sensor": {"type": "perspective", "film": {"type": "hdrfilm", "width": 16, "height": 12}}}
+    scene = mi.load_dict(sd)
+    d = scene.scene_config(8, 8).to_desc()
+    assert d.emitter_type == _abi.RCV_EMITTER_ENVMAP and (d.env_height, d.env_width) == (10, 16) and abs(d.env_scale - 0.5) < 1e-7
+    got = np.ctypeslib.as_array((C.c_float * (10 * 16 * 3)).from_address(d.envmap_rgb)).reshape(10, 16, 3)
+    assert np.allclose(got, tex, rtol=1e-6)
+    sd["extra"] = {"type": "constant", "radiance": 1.0}
+    with pytest.raises(ValueError):
+        mi.load_dict(sd)

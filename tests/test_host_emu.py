@@ -18,7 +18,7 @@ EMU_DIR = os.path.join(HERE, "host_emu")
 
 
 def _load_emu(name):
-    subprocess.run(["make", "-C", EMU_DIR, "all"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+    subprocess.run(["make", "-j4", "-C", EMU_DIR, "all"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
     lib = C.CDLL(os.path.join(EMU_DIR, name))
     f32 = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
     u64 = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")

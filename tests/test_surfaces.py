@@ -124,7 +124,7 @@ def test_prb_adjoint_agrees_with_volpathsimple_under_the_environment(oracle):
 def emu():
     import subprocess, os
     here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_emu")
-    subprocess.run(["make", "-C", here, "all"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+    subprocess.run(["make", "-j4", "-C", here, "all"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
     lib = C.CDLL(os.path.join(here, "librcv_emu.so"))
     f32 = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
     u64 = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
