@@ -71,3 +71,44 @@ def test_product_does_not_import_oracle():
                 text = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", text, flags=re.M), f
                 assert "rcv_oracle" not in text, f
+
+
+def test_scene_validation_without_a_gpu(lib):
+    """rcv_scene_set validates the description before it touches the device: bad rectangles, a missing area light and an
+    envmap without texels are argument errors (no compute call, runs without a GPU)."""
+    import numpy as np
+    from recursive_control_variates_b200 import _abi
+    from recursive_control_variates_b200.scene import SceneConfig
+    from recursive_control_variates_b200.synthetic import boxed_quads
+
+    def status(desc):
+        h = C.c_void_p()
+        rc = lib.rcv_ctx_create(0, None, C.byref(h))
+        if rc != 0:                  # no device (the CPU suite): only the host-side checks below run
+            return None
+        try:
+            return lib.rcv_scene_set(h, C.byref(desc))
+        finally:
+            lib.rcv_ctx_destroy(h)
+
+    good = SceneConfig(width=8, height=8, quads=boxed_quads()).to_desc()
+    assert good.n_quads == 7 and good.area_quad == 6 and good.emitter_type == _abi.RCV_EMITTER_AREA
+    # host-side construction errors (scene.py) need no library at all
+    with pytest.raises(ValueError):
+        SceneConfig(width=8, height=8, quads=boxed_quads() * 2).to_desc()                     # more than RCV_MAX_QUADS
+    with pytest.raises(ValueError):
+        SceneConfig(width=8, height=8, quads=boxed_quads(), envmap=np.ones((4, 8, 3), np.float32)).to_desc()   # two emitters
+    with pytest.raises(ValueError):
+        SceneConfig(width=8, height=8, envmap=np.ones((1, 8, 3), np.float32)).to_desc()       # a single row of texels
+    if status(good) is None:
+        return
+    assert status(good) == 0
+    bad = SceneConfig(width=8, height=8, quads=boxed_quads()).to_desc()
+    bad.quads[0].ev[:] = list(bad.quads[0].eu)                                                # edges not perpendicular
+    assert status(bad) == 1 and b"perpendicular" in lib.rcv_last_error()
+    bad = SceneConfig(width=8, height=8, quads=boxed_quads()).to_desc()
+    bad.area_quad = 9
+    assert status(bad) == 1 and b"area_quad" in lib.rcv_last_error()
+    bad = SceneConfig(width=8, height=8).to_desc()
+    bad.emitter_type = _abi.RCV_EMITTER_ENVMAP
+    assert status(bad) == 1 and b"envmap" in lib.rcv_last_error()
