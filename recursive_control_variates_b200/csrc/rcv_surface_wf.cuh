@@ -33,6 +33,12 @@ namespace rcv {
 // a fourth event class: the shadow ray's work outside the medium (its surface iterations, its end).  Kept apart from
 // EV_SLOW so that a warp runs the main path's surface blocks and the shadow rays' each with their own lanes.
 enum : int { EV_NEE = 4 };
+// consecutive pieces of outside-the-medium work one handler call chains (1 = one piece per scheduling round).  r2aa, c1box:
+// two-state / adjoint 18.0 / 58.7 ms with 1, 20.5 / 59.2 with 2, 20.4 / 57.6 with 4 — lanes that run ahead of their
+// warp only desynchronise it further.
+#ifndef RCV_SF_CHAIN
+#define RCV_SF_CHAIN 1
+#endif
 
 enum : uint32_t {
     SF_NEEDS_ISECT = 1u, SF_SPECULAR = 2u, SF_IN_NEE = 4u, SF_SI_VALID = 8u,
@@ -538,16 +544,25 @@ __device__ __forceinline__ void sf_nee_done(const SceneK &S, SfLane &ln) {
 // EV_SLOW: the main path outside the medium
 template <int MODE, bool ADJ>
 __device__ __forceinline__ void sf_slow(const SceneK &S, SfLane &ln, SfSink &sk) {
-    // one copy of each piece: a surface block flows into its BSDF sampling and, where the path ends, into the finish
-    if (!(ln.flags & (SF_FIN | SF_BSDF))) sf_surface<ADJ>(S, ln);
-    if (ln.flags & SF_BSDF) sf_bsdf(S, ln);
+    // one copy of each piece: a surface block flows into its BSDF sampling and, where the path ends, into the finish; a lane
+    // that stays outside the medium goes on into the surface block of its next iteration in the same round
+#pragma unroll 1
+    for (int pass = 0; pass < RCV_SF_CHAIN; ++pass) {
+        if (!(ln.flags & (SF_FIN | SF_BSDF))) sf_surface<ADJ>(S, ln);
+        if (ln.flags & SF_BSDF) sf_bsdf(S, ln);
+        if ((ln.flags & SF_FIN) || ln.ev != EV_SLOW) break;
+    }
     if (ln.flags & SF_FIN) sf_finish<MODE, ADJ>(S, ln, sk);
 }
 // EV_NEE: the shadow ray outside the medium
 template <bool ADJ>
 __device__ __forceinline__ void sf_nee(const SceneK &S, SfLane &ln) {
-    if (!(ln.flags & SF_POST_NEE)) sf_nee_iter(S, ln);
-    if (ln.flags & SF_POST_NEE) sf_nee_done<ADJ>(S, ln);
+#pragma unroll 1
+    for (int pass = 0; pass < RCV_SF_CHAIN; ++pass) {
+        if (!(ln.flags & SF_POST_NEE)) sf_nee_iter(S, ln);
+        if (ln.flags & SF_POST_NEE) { sf_nee_done<ADJ>(S, ln); break; }
+        if (ln.ev != EV_NEE) break;
+    }
 }
 
 }  // namespace rcv
