@@ -206,3 +206,37 @@ def test_load_dict_envmap_from_exr(tmp_path):
     sd["extra"] = {"type": "constant", "radiance": 1.0}
     with pytest.raises(ValueError):
         mi.load_dict(sd)
+
+
+@pytest.mark.gpu
+def test_gpu_envmap_through_the_plugins(oracle):
+    """The reference's scene layout with an `envmap` emitter (experiments.py:81-85) through load_dict / `cv` / mi.render and
+    backward with volpathsimple as adjoint_integrator: F and the gradients against the oracle."""
+    import torch
+    from recursive_control_variates_b200 import mitsuba_compat as mi
+    from recursive_control_variates_b200 import plugins  # noqa: F401
+    _, new = media(10)
+    medium = {"type": "heterogeneous", "sigma_t": {"type": "gridvolume", "data": torch.from_numpy(new[0])},
+              "albedo": {"type": "gridvolume", "data": torch.from_numpy(new[1])}, "scale": 20.0}
+    sd = {"type": "scene",
+          "object": {"type": "obj", "bsdf": {"type": "null"},
+                     "interior": {"type": "twostatemedium", "old": medium, "new": medium, "incoming": medium}},
+          "envmap": {"type": "envmap", "bitmap": sky(10, 16), "scale": 0.5},
+          "sensor": {"type": "perspective", "film": {"type": "hdrfilm", "width": 24, "height": 20, "rfilter": {"type": "box"}}}}
+    scene = mi.load_dict(sd)
+    integ = mi.load_dict({"type": "cv", "integrator": {"type": "twostateprbvolpath", "max_depth": 8, "rr_depth": 8},
+                          "adjoint_integrator": {"type": "volpathsimple", "max_depth": 8, "rr_depth": 8, "use_drt": False}})
+    opt = mi.Adam(lr=5e-3)
+    sp = mi.traverse(scene)
+    ks, ka = "object.interior_medium.sigma_t.data", "object.interior_medium.albedo.data"
+    for _ in range(2):
+        opt[ks] = torch.from_numpy(new[0]); opt[ka] = torch.from_numpy(new[1])
+        sp.update(opt)
+    img = mi.render(scene, sp, integrator=integ, seed=1, spp=4, seed_grad=2, spp_grad=4)
+    d = integ.integrator._ctx(scene).desc
+    m = oracle.OracleMedium(d, *new)
+    _, F = oracle.render_twostates(d, m, m, 1, 4)
+    assert rel_l2(integ.F.cpu().numpy(), F) < 1e-6 and F.max() > 0
+    img.sum().backward()
+    gs, ga = oracle.vps_backward(d, m, 2, 4, np.ones((20, 24, 3), np.float32))
+    assert rel_l2(opt[ks].grad.cpu().numpy(), gs) < 1e-4 and rel_l2(opt[ka].grad.cpu().numpy(), ga) < 1e-4
