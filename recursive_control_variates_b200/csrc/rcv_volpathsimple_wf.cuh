@@ -80,12 +80,23 @@ enum : int { EV_P2 = 4 };
 
 // vertex record flags
 enum : uint32_t { VR_SCATTER = 1u, VR_NEE = 2u, VR_NEE_DONE = 4u /* its transmittance gradients were scattered in pass 1 */,
-                  VR_ALBEDO = 8u /* the record carries the vertex's albedo (RCV_VERTEX_ALBEDO) */ };
+                  VR_ALBEDO = 8u /* the record carries the vertex's albedo (RCV_VERTEX_ALBEDO) */,
+                  VR_SIGMA = 16u /* ... and its sigma_t, in r[2].x (RCV_VERTEX_SIGMA) */ };
+// RCV_VERTEX_SIGMA = 1: pass 1 also fetches sigma_t at the vertex (same interpolation set-up as its albedo gather, the
+// loads go out together) and leaves it in the record: pass 2 then needs no grid gather at all — vertex records (L2 hits)
+// in, gradient reductions out.  Same value, same arithmetic as the lookup pass 2 would make.
+#ifndef RCV_VERTEX_SIGMA
+#define RCV_VERTEX_SIGMA 1
+#endif
 // RCV_VERTEX_ALBEDO = 1: pass 1 leaves the albedo it gathered at a scattering vertex in the vertex record (in the words
 // that hold the shadow-ray direction, which only the replay fall-back needs), so pass 2 does not gather its eight
 // corners again.  Same value, same arithmetic.  r2a (profiles/README.md): adjoint 17.8 -> 16.9 ms at C2; on by default.
 #ifndef RCV_VERTEX_ALBEDO
 #define RCV_VERTEX_ALBEDO 1
+#endif
+#if !RCV_VERTEX_ALBEDO           // the record words are laid out for both or neither
+#undef RCV_VERTEX_SIGMA
+#define RCV_VERTEX_SIGMA 0
 #endif
 // records (position, -1 / (majorant * tr)) of the tentative collisions of one shadow ray, kept per arena slot behind the
 // vertex records; 16 vertex-record equivalents
@@ -328,7 +339,12 @@ __device__ __forceinline__ void vp_nee_done(const SceneK &S, const GridK &G, VpL
     if (BW) {
         float4 *r = vp_record(sk, ln, ln.nvert - 1);
         const bool ovf = (ln.flags & VF_NEE_OVF) != 0;
+#if RCV_VERTEX_SIGMA
+        if (ovf) r[2] = make_float4(__uint_as_float((uint32_t) ln.saved), __uint_as_float((uint32_t) (ln.saved >> 32)), ln.nee.x, ln.nee.y);
+        else { r[2].z = ln.nee.x; r[2].w = ln.nee.y; }               // .x keeps sigma_t; the sampler state is needed by the replay only
+#else
         r[2] = make_float4(__uint_as_float((uint32_t) ln.saved), __uint_as_float((uint32_t) (ln.saved >> 32)), ln.nee.x, ln.nee.y);
+#endif
 #if RCV_VERTEX_ALBEDO
         if (ovf) r[3] = make_float4(ln.nee.z, ln.nd.x, ln.nd.y, ln.nd.z);      // the replay needs the direction: the albedo gives way
         else r[3].x = ln.nee.z;
@@ -338,7 +354,8 @@ __device__ __forceinline__ void vp_nee_done(const SceneK &S, const GridK &G, VpL
         // a vertex that cast a shadow ray is a scattering vertex with VR_NEE set (vp_vertex1): its flag word is written
         // whole, no read-modify-write of the record
         r[1].w = __uint_as_float(VR_SCATTER | VR_NEE | (ovf ? 0u : (uint32_t) VR_NEE_DONE) |
-                                 ((RCV_VERTEX_ALBEDO && !ovf) ? (uint32_t) VR_ALBEDO : 0u));
+                                 ((RCV_VERTEX_ALBEDO && !ovf) ? (uint32_t) VR_ALBEDO : 0u) |
+                                 ((RCV_VERTEX_SIGMA && !ovf) ? (uint32_t) VR_SIGMA : 0u));
         if (!ovf) {
             // transmittance gradients of the shadow ray (:406-414, :496-505) from the recorded collisions: the same
             // values the replay in pass 2 would compute, scattered now.  The records are read three ahead of their use
@@ -526,10 +543,14 @@ __device__ __forceinline__ void vp_vertex1(const SceneK &S, const GridK &G, VpLa
     const bool did_scatter = (ln.flags & VF_DID_SCATTER) != 0;
     if (did_scatter) ln.flags |= VF_HAS_SCAT;                         // :150
     V3 albedo = mk3(1, 1, 1);
+    float st_vertex = 0.f;
     if (did_scatter) {
         V3 mei_p = ray_at(ln.o, ln.d, ln.mei_t);                      // :384
         Tri T = tri_setup(S, G, mei_p);
         albedo = lookup_albedo(G, T, 1);                              // :154
+#if RCV_VERTEX_SIGMA
+        if (BW) st_vertex = lookup_sigma1(S, G, T);                   // :386-388, for pass 2
+#endif
         sk.cnt.scat++;
     }
     ln.thr = ln.thr * albedo;                                         // :206
@@ -541,8 +562,12 @@ __device__ __forceinline__ void vp_vertex1(const SceneK &S, const GridK &G, VpLa
         r[0] = make_float4(ln.o.x, ln.o.y, ln.o.z, did_scatter ? ln.mei_t : ln.ray_maxt);   // interval of :601
 #if RCV_VERTEX_ALBEDO
         r[1] = make_float4(ln.d.x, ln.d.y, ln.d.z,
-                           __uint_as_float((did_scatter ? (VR_SCATTER | VR_ALBEDO) : 0u) | (do_nee ? VR_NEE : 0u)));
+                           __uint_as_float((did_scatter ? (VR_SCATTER | VR_ALBEDO | (RCV_VERTEX_SIGMA ? (uint32_t) VR_SIGMA : 0u)) : 0u) |
+                                           (do_nee ? VR_NEE : 0u)));
         if (did_scatter) r[3] = make_float4(0.f, albedo.x, albedo.y, albedo.z);
+#if RCV_VERTEX_SIGMA
+        if (did_scatter) r[2] = make_float4(st_vertex, 0.f, 0.f, 0.f);
+#endif
 #else
         r[1] = make_float4(ln.d.x, ln.d.y, ln.d.z, __uint_as_float((did_scatter ? VR_SCATTER : 0u) | (do_nee ? VR_NEE : 0u)));
 #endif
@@ -598,7 +623,11 @@ __device__ __forceinline__ void vp_vertex2(const SceneK &S, const GridK &G, VpLa
     if (did_scatter) {
         V3 mei_p = ray_at(ln.o, ln.d, interval);                      // :384
         Tri T = tri_setup(S, G, mei_p);
+#if RCV_VERTEX_SIGMA
+        float st = (vf & VR_SIGMA) ? r[2].x : lookup_sigma1(S, G, T);   // :386-388
+#else
         float st = lookup_sigma1(S, G, T);                            // :386-388
+#endif
 #if RCV_VERTEX_ALBEDO
         V3 albedo;
         if (vf & VR_ALBEDO) { float4 r3 = r[3]; albedo = mk3(r3.y, r3.z, r3.w); }
@@ -707,7 +736,11 @@ __device__ __forceinline__ V3 vp_vertex2_flat(const SceneK &S, const GridK &G, V
     if (vf & VR_SCATTER) {
         V3 mei_p = ray_at(o, d, interval);                            // :384
         Tri T = tri_setup(S, G, mei_p);
+#if RCV_VERTEX_SIGMA
+        float st = (vf & VR_SIGMA) ? r[2].x : lookup_sigma1(S, G, T);   // :386-388
+#else
         float st = lookup_sigma1(S, G, T);                            // :386-388
+#endif
 #if RCV_VERTEX_ALBEDO
         V3 albedo;
         if (vf & VR_ALBEDO) { float4 r3 = r[3]; albedo = mk3(r3.y, r3.z, r3.w); }

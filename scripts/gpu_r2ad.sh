@@ -1,0 +1,12 @@
+# round 2, call ad: sigma_t in the vertex record (pass 2 without any grid gather): parity, then A/B against RCV_VERTEX_SIGMA=0
+TAG=${1:-r2ad}
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_c1.py -q -m gpu -x > gpurun_out/${TAG}_pytest.log 2>&1; tail -1 gpurun_out/${TAG}_pytest.log
+B="python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-e2e --no-drt --supergrid --no-baseline-method"
+for v in default nosig default nosig; do
+  if [ "$v" = "default" ]; then unset RCV_B200_LIB; else export RCV_B200_LIB=$PWD/build/variants/librcv_$v.so; fi
+  (timeout 100 $B 2>&1 | tail -1) > gpurun_out/${TAG}_$v.json
+  python -c "
+import json
+d=json.load(open('gpurun_out/${TAG}_$v.json')); print('$v', round(d['ms_per_step'],2), 'adjoint', round(d['phases_ms_rank0']['adjoint'],2), round(d['kernels']['volpathsimple_adjoint']['ms'],2))"
+done
