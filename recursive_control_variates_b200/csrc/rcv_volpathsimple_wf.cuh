@@ -88,6 +88,11 @@ enum : uint32_t { VR_SCATTER = 1u, VR_NEE = 2u, VR_NEE_DONE = 4u /* its transmit
 #ifndef RCV_VERTEX_SIGMA
 #define RCV_VERTEX_SIGMA 1
 #endif
+// unroll factor of the four transmittance-term sites of a pass-2 vertex (:607-613)
+#ifndef RCV_TRANS_UNROLL
+#define RCV_TRANS_UNROLL 1
+#endif
+static constexpr int kTransUnroll = RCV_TRANS_UNROLL;
 // RCV_VERTEX_ALBEDO = 1: pass 1 leaves the albedo it gathered at a scattering vertex in the vertex record (in the words
 // that hold the shadow-ray direction, which only the replay fall-back needs), so pass 2 does not gather its eight
 // corners again.  Same value, same arithmetic.  r2a (profiles/README.md): adjoint 17.8 -> 16.9 ms at C2; on by default.
@@ -669,7 +674,7 @@ __device__ __forceinline__ void vp_vertex2(const SceneK &S, const GridK &G, VpLa
         V3 aw = ln.dL * ln.result;                                    // :198
         float inv_pdf = interval / 4.f;                               // :617
         float g = -((aw.x * inv_pdf) + (aw.y * inv_pdf) + (aw.z * inv_pdf));
-#pragma unroll 1
+#pragma unroll kTransUnroll
         for (int j = 0; j < 4; ++j) {
             float t = pcg_f32(ln.alt) * interval;                     // :608
             scatter_sigma_t(S, G, sk.D, ray_at(ln.o, ln.d, t), g, sk.cnt);
