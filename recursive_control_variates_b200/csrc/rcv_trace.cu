@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(kBlock) k_vps_raygen(const __grid_constant__ S
     uint64_t j = (uint64_t) blockIdx.x * kBlock + threadIdx.x;
     VpLane ln; ln.ev = EV_INIT; ln.flags = 0;
     VpSink sk; sk.accum = accum; sk.D.gsig = nullptr; sk.D.galb = nullptr; sk.grad_img = nullptr; sk.film_w = nullptr;
-    sk.arena = nullptr; sk.vcap = 0; sk.flat = 0; sk.drt_mis = 0;
+    sk.arena = nullptr; sk.vcap = 0; sk.flat = 0; sk.drt_mis = 0; sk.coop = 0; sk.coop_n = 0;
     sk.seed = seed; sk.spp = spp; sk.alt_seed = 0;
     sk.cnt.coll = sk.cnt.scat = sk.cnt.g_sig = sk.cnt.g_alb = 0; sk.n_paths = 0;
     if (j < n_local) vp_raygen<BACKWARD>(S, ln, sk, global_lane(j, spp, spp_begin, ns));
@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(kWfBlock, RCV_VP_MINBLOCKS) k_vps_wavefront(co
     ln.ev = EV_INIT; ln.flags = 0;
     VpSink sk;
     sk.accum = accum; sk.D = D; sk.grad_img = grad_img; sk.film_w = film_w; sk.arena = arena; sk.vcap = vcap;
-    sk.seed = seed; sk.spp = spp; sk.alt_seed = alt_seed; sk.flat = 0; sk.drt_mis = 0;
+    sk.seed = seed; sk.spp = spp; sk.alt_seed = alt_seed; sk.flat = 0; sk.drt_mis = 0; sk.coop = 0; sk.coop_n = 0;
     sk.cnt.coll = sk.cnt.scat = sk.cnt.g_sig = sk.cnt.g_alb = 0; sk.n_paths = 0;
     ChunkCursor cc; cc.next = 0; cc.end = 0; cc.more = true;
     while (true) {
@@ -568,6 +568,43 @@ __device__ __forceinline__ void pool_drt_complete(const SceneK &S, const GRID &G
     if (done) ln.flags = 0;
 }
 
+// RCV_COOP_NEE_RECORDS = 1: the recorded collisions of the shadow rays that ended in this slow step are scattered by
+// the whole warp.  A lane walking its own list kept 7.6 of 32 threads busy over a fifth of the adjoint's warp
+// instructions (r2w: the lists differ in length, and a slow step holds 15 lanes on average); here the lists of the
+// step are laid end to end and every thread takes each 32nd record, whoever's it is.  Same values per record; only
+// the order of the (unordered anyway) reductions into the gradient bricks changes.
+#ifndef RCV_COOP_NEE_RECORDS
+#define RCV_COOP_NEE_RECORDS 1
+#endif
+__device__ __forceinline__ void vp_nee_records_warp(const SceneK &S, const GridK &G, VpSink &sk) {
+    const unsigned full = 0xffffffffu;
+    const int lane = (int) (threadIdx.x & 31);
+    const int n = sk.coop_n;
+    sk.coop_n = 0;
+    if (!__any_sync(full, n > 0)) return;
+    int x = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(full, x, o); if (lane >= o) x += y; }
+    const int total = __shfl_sync(full, x, 31);
+    const int excl = x - n;
+    const unsigned long long rec_bits = (unsigned long long) sk.coop_rec;
+    for (int base = 0; base < total; base += 32) {
+        const int j = base + lane;
+        int own = 0;                                                   // the last thread whose list starts at or before j
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+            const int cand = own + step;
+            const int e = __shfl_sync(full, excl, cand & 31);
+            if (cand < 32 && e <= j) own = cand;
+        }
+        const int first = __shfl_sync(full, excl, own);
+        const float4 *rec = (const float4 *) __shfl_sync(full, rec_bits, own);
+        const V3 adj = mk3(__shfl_sync(full, sk.coop_adj.x, own), __shfl_sync(full, sk.coop_adj.y, own),
+                           __shfl_sync(full, sk.coop_adj.z, own));
+        if (j < total) vp_nee_record_scatter(S, G, sk, adj, rec[j - first]);
+    }
+}
+
 template <bool BACKWARD, class GRID, int DRT = 0>
 __global__ void __launch_bounds__(kVpPoolBlock, RCV_POOL_MINBLOCKS) k_vps_pool(const __grid_constant__ SceneK S,
                                                                              const __grid_constant__ GRID G, GradK D, uint32_t seed,
@@ -590,6 +627,8 @@ __global__ void __launch_bounds__(kVpPoolBlock, RCV_POOL_MINBLOCKS) k_vps_pool(c
     sk.jobs = jobs; sk.drt_mis = drt_mis;
     constexpr bool kFlat = RCV_FLAT_PASS2 && BACKWARD && DRT == 0;
     sk.flat = kFlat ? 1 : 0;
+    constexpr bool kCoop = RCV_COOP_NEE_RECORDS && BACKWARD;
+    sk.coop = kCoop ? 1 : 0; sk.coop_n = 0; sk.coop_rec = nullptr; sk.coop_adj = mk3(0, 0, 0);
     unsigned short *pre = (unsigned short *) (list + kPoolSlots);      // kPoolSlots + 1 exclusive prefix sums (flattened pass 2)
     const uint32_t slot0 = (blockIdx.x * (kVpPoolBlock / 32) + (threadIdx.x >> 5)) * kPoolSlots;   // first arena slot of this warp's pool
     ChunkCursor cc; cc.next = 0; cc.end = 0; cc.more = true;
@@ -708,6 +747,7 @@ __global__ void __launch_bounds__(kVpPoolBlock, RCV_POOL_MINBLOCKS) k_vps_pool(c
                 if (loaded && ln.ev != EV_INIT) vp_pool_store_all(pw, s, ln);
                 cls[s] = (unsigned char) ln.ev;
             }
+            if (kCoop) vp_nee_records_warp(S, G, sk);
         }
         __syncwarp();
     }

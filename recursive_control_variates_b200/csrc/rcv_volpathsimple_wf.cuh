@@ -139,6 +139,11 @@ struct VpSink {
     int drt_mis;            // use_drt_mis (DRT != 0)
     int flat;               // the scheduler runs pass 2 vertex-parallel (EV_P2 / vp_vertex2_flat); else the lane walks its list
     PathQueue jobs;         // DRT = 1: job records written at the end of pass 2; DRT = 2: r0/r1 = where and what to scatter
+    // coop != 0: a finished shadow ray leaves its recorded collisions to the scheduler (vp_nee_records_warp) instead of
+    // walking them itself: how many, where, and the adjoint they are weighted with
+    int coop, coop_n;
+    const float4 *coop_rec;
+    V3 coop_adj;
 };
 
 __device__ __forceinline__ float4 *vp_record(const VpSink &sk, const VpLane &ln, int k) {
@@ -332,6 +337,13 @@ __device__ __forceinline__ void vp_post_vertex(const SceneK &S, VpLane &ln, VpSi
     ln.ev = EV_COLL;
 }
 
+// one recorded collision of a shadow ray: adjoint * d log(tr) / d sigma_t at its position (:496-505)
+__device__ __forceinline__ void vp_nee_record_scatter(const SceneK &S, const GridK &G, VpSink &sk, V3 adjoint, float4 c) {
+    float g = 0.f;
+    g += adjoint.x * c.w; g += adjoint.y * c.w; g += adjoint.z * c.w;
+    scatter_sigma_t(S, G, sk.D, mk3(c.x, c.y, c.z), g, sk.cnt);
+}
+
 // pass 1: the shadow ray ended — its contribution (:401-404, :225), the vertex record, then the path continues
 template <bool BW, int DRT = 0>
 __device__ __forceinline__ void vp_nee_done(const SceneK &S, const GridK &G, VpLane &ln, VpSink &sk) {
@@ -368,14 +380,15 @@ __device__ __forceinline__ void vp_nee_done(const SceneK &S, const GridK &G, VpL
             const V3 adjoint = ln.dL * ln.nee;                        // :412
             const int n = __float_as_int(ln.running_t);
             const float4 *rec = vp_nee_record(sk, ln, 0);
-            const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 c0 = (0 < n) ? rec[0] : zero, c1 = (1 < n) ? rec[1] : zero, c2 = (2 < n) ? rec[2] : zero;
-            for (int i = 0; i < n; ++i) {
-                const float4 c3 = (i + 3 < n) ? rec[i + 3] : zero;
-                float g = 0.f;
-                g += adjoint.x * c0.w; g += adjoint.y * c0.w; g += adjoint.z * c0.w;
-                scatter_sigma_t(S, G, sk.D, mk3(c0.x, c0.y, c0.z), g, sk.cnt);
-                c0 = c1; c1 = c2; c2 = c3;
+            if (sk.coop) { sk.coop_n = n; sk.coop_rec = rec; sk.coop_adj = adjoint; }
+            else {
+                const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 c0 = (0 < n) ? rec[0] : zero, c1 = (1 < n) ? rec[1] : zero, c2 = (2 < n) ? rec[2] : zero;
+                for (int i = 0; i < n; ++i) {
+                    const float4 c3 = (i + 3 < n) ? rec[i + 3] : zero;
+                    vp_nee_record_scatter(S, G, sk, adjoint, c0);
+                    c0 = c1; c1 = c2; c2 = c3;
+                }
             }
         }
         ln.flags &= ~VF_NEE_OVF;

@@ -328,7 +328,7 @@ int emu_vps_drt_stages(const rcv_scene_desc *d, const float *sn, const float *an
     Packed P; pack(*d, sn, an, sn, an, nz, ny, nx, P, factor);
     for (int i = 0; i < 8; ++i) counters[i] = 0;
     VpSink sk; sk.accum = nullptr; sk.D.gsig = gsig; sk.D.galb = (float4 *) galb4; sk.grad_img = grad_img; sk.film_w = film_w;
-    sk.seed = seed; sk.spp = spp; sk.alt_seed = alt_seed; sk.drt_mis = use_mis; sk.flat = 0;
+    sk.seed = seed; sk.spp = spp; sk.alt_seed = alt_seed; sk.drt_mis = use_mis; sk.flat = 0; sk.coop = 0; sk.coop_n = 0;
     sk.cnt.coll = sk.cnt.scat = sk.cnt.g_sig = sk.cnt.g_alb = 0; sk.n_paths = 0;
     HostBricks hb(nx, ny, nz, sk.D);
     if (factor > 0) run_vps_drt(S, P.G, sk);
@@ -373,7 +373,7 @@ int emu_vps_sg(const rcv_scene_desc *d, const float *sn, const float *an, int nz
     Packed P; pack(*d, sn, an, sn, an, nz, ny, nx, P, factor);
     for (int i = 0; i < 8; ++i) counters[i] = 0;
     VpSink sk; sk.accum = (float4 *) accum; sk.D.gsig = gsig; sk.D.galb = (float4 *) galb4; sk.grad_img = grad_img; sk.film_w = film_w;
-    sk.seed = seed; sk.spp = spp; sk.alt_seed = alt_seed; sk.drt_mis = 0; sk.flat = g_flat;
+    sk.seed = seed; sk.spp = spp; sk.alt_seed = alt_seed; sk.drt_mis = 0; sk.flat = g_flat; sk.coop = 0; sk.coop_n = 0;
     sk.cnt.coll = sk.cnt.scat = sk.cnt.g_sig = sk.cnt.g_alb = 0; sk.n_paths = 0;
     HostBricks hb(nx, ny, nz, sk.D);
     if (factor > 0) {
