@@ -727,32 +727,67 @@ __device__ __forceinline__ void dda_axis(float o, float d, float id, float bmin,
 // Sampled free-flight distance (or inf) for optical depth `tau` along o + t d, t in [mint, maxt], and the majorant of the
 // cell the sample fell into.  Incremental traversal: the supercell index is carried and advanced by +-1 on the axis
 // whose boundary is crossed (the numerical specification of DESIGN.md §2; id = 1 / d).
+//
+// RCV_DDA_AHEAD = K > 1 (build option, measured slower, profiles/README.md r2ag): which supercells the ray visits is
+// geometry — only where the walk STOPS depends on the majorants read — so the walk can be taken K cells at a time: the
+// crossing distances of the next K cells are computed and their majorants requested together, then the optical depth is
+// accumulated over them in order with the tests of the plain loop.  Same operations on the same values in the same
+// order; the majorants of cells beyond the stopping point are read and dropped.  The walk turned out to be bound by
+// its instructions, not by the majorant loads (rays of a warp walk neighbouring supercells: L1 hits), so the default
+// stays K = 1, the plain loop.
+#ifndef RCV_DDA_AHEAD
+#define RCV_DDA_AHEAD 1
+#endif
 template <int SEL>
 __device__ __forceinline__ float dda_sample(const SceneK &S, const GridKS &G, V3 o, V3 d, V3 id, float mint, float maxt, float tau,
                                             float &maj_out) {
+    constexpr int K = RCV_DDA_AHEAD;
     float tx, ty, tz, dx, dy, dz;
     int cx, cy, cz, sx, sy, sz;
     dda_axis(o.x, d.x, id.x, S.bmin[0], S.bmax[0], S.inv_ext[0], G.mx, G.vox[0], mint, cx, sx, tx, dx);
     dda_axis(o.y, d.y, id.y, S.bmin[1], S.bmax[1], S.inv_ext[1], G.my, G.vox[1], mint, cy, sy, ty, dy);
     dda_axis(o.z, d.z, id.z, S.bmin[2], S.bmax[2], S.inv_ext[2], G.mz, G.vox[2], mint, cz, sz, tz, dz);
     float dda_t = mint, tau_acc = 0.f, majorant = 0.f;
-    bool reached = false;
-    while (true) {
-        float t_next = fmin_(fmin_(tx, ty), tz);
-        int axis = (tx == t_next) ? 0 : ((ty == t_next) ? 1 : 2);
-        float2 m = __ldg(G.mgrid + ((size_t) cz * G.my + cy) * G.mx + cx);
-        majorant = (SEL == 1) ? m.x : ((SEL == 2) ? m.y : fmax_(m.x, m.y));
-        float tau_next = tau_acc + (majorant * (t_next - dda_t));
-        if ((majorant > 0.f) && (tau_next >= tau)) {                  // the division only where its result can be used
-            float t_precise = dda_t + ((tau - tau_acc) / majorant);
-            if (t_precise < maxt) { dda_t = t_precise; reached = true; break; }
+    bool reached = false, done = false;
+    while (!done) {
+        float tn[K], mj[K];
+        bool last[K];
+        bool open = true;                                             // the walk has not left the grid / the interval yet
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            tn[k] = inf_(); mj[k] = 0.f; last[k] = true;
+            if (open) {
+                float t_next = fmin_(fmin_(tx, ty), tz);
+                int axis = (tx == t_next) ? 0 : ((ty == t_next) ? 1 : 2);
+                float2 m = __ldg(G.mgrid + ((size_t) cz * G.my + cy) * G.mx + cx);
+                mj[k] = (SEL == 1) ? m.x : ((SEL == 2) ? m.y : fmax_(m.x, m.y));
+                tn[k] = t_next;
+                bool end = !(t_next < maxt);
+                if (!end) {
+                    if (axis == 0) { cx += sx; if (cx < 0 || cx >= G.mx) end = true; else tx = tx + dx; }
+                    else if (axis == 1) { cy += sy; if (cy < 0 || cy >= G.my) end = true; else ty = ty + dy; }
+                    else { cz += sz; if (cz < 0 || cz >= G.mz) end = true; else tz = tz + dz; }
+                }
+                last[k] = end;
+                open = !end;
+            }
         }
-        dda_t = t_next;
-        if (!(t_next < maxt)) break;
-        if (axis == 0) { cx += sx; if (cx < 0 || cx >= G.mx) break; tx = tx + dx; }
-        else if (axis == 1) { cy += sy; if (cy < 0 || cy >= G.my) break; ty = ty + dy; }
-        else { cz += sz; if (cz < 0 || cz >= G.mz) break; tz = tz + dz; }
-        tau_acc = tau_next;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (!done) {
+                majorant = mj[k];
+                float tau_next = tau_acc + (majorant * (tn[k] - dda_t));
+                if ((majorant > 0.f) && (tau_next >= tau)) {          // the division only where its result can be used
+                    float t_precise = dda_t + ((tau - tau_acc) / majorant);
+                    if (t_precise < maxt) { dda_t = t_precise; reached = true; done = true; }
+                }
+                if (!done) {
+                    dda_t = tn[k];
+                    if (last[k]) done = true;
+                    else tau_acc = tau_next;
+                }
+            }
+        }
     }
     maj_out = majorant;
     return reached ? dda_t : inf_();
