@@ -738,6 +738,60 @@ __device__ __forceinline__ void dda_axis(float o, float d, float id, float bmin,
 #ifndef RCV_DDA_AHEAD
 #define RCV_DDA_AHEAD 1
 #endif
+// RCV_DDA_LIN_TWOSTATE / RCV_DDA_LIN_VPS: which machines walk with dda_sample_lin (r2ah: the two-state render gains
+// 22 % at factor 8, the adjoint — at its register limit — does not).
+#ifndef RCV_DDA_LIN_TWOSTATE
+#define RCV_DDA_LIN_TWOSTATE 1
+#endif
+#ifndef RCV_DDA_LIN_VPS
+#define RCV_DDA_LIN_VPS 0
+#endif
+// The same walk, leaner.  What the loop carries is chosen for the instruction count of one cell (a warp's collision round lasts
+// as long as its longest walk — 31 cells for a mean of 9 at 256^3 / factor 8 — so the cell is the unit that matters): the
+// supercell is a running LINEAR index with one signed stride per axis, the grid bounds are the number of steps left on
+// each axis, and the step is taken with selects (every lane of the warp steps a different axis; three divergent
+// branches cost three times the instructions).  Same values as stepping (cx, cy, cz): the cell sequence, the crossing
+// distances and the stopping rule are those of the specification.
+template <int SEL>
+__device__ __forceinline__ float dda_sample_lin(const SceneK &S, const GridKS &G, V3 o, V3 d, V3 id, float mint, float maxt, float tau,
+                                                float &maj_out) {
+    float tx, ty, tz, dx, dy, dz;
+    int cx, cy, cz, sx, sy, sz;
+    dda_axis(o.x, d.x, id.x, S.bmin[0], S.bmax[0], S.inv_ext[0], G.mx, G.vox[0], mint, cx, sx, tx, dx);
+    dda_axis(o.y, d.y, id.y, S.bmin[1], S.bmax[1], S.inv_ext[1], G.my, G.vox[1], mint, cy, sy, ty, dy);
+    dda_axis(o.z, d.z, id.z, S.bmin[2], S.bmax[2], S.inv_ext[2], G.mz, G.vox[2], mint, cz, sz, tz, dz);
+    int ci = (cz * G.my + cy) * G.mx + cx;
+    const int stx = sx, sty = sy * G.mx, stz = sz * (G.mx * G.my);
+    int rx = (sx > 0) ? (G.mx - 1 - cx) : cx;                         // steps left before the walk leaves the grid
+    int ry = (sy > 0) ? (G.my - 1 - cy) : cy;
+    int rz = (sz > 0) ? (G.mz - 1 - cz) : cz;
+    float dda_t = mint, tau_acc = 0.f, majorant = 0.f;
+    bool reached = false;
+    while (true) {
+        const float2 m = __ldg(G.mgrid + ci);
+        const float t_next = fmin_(fmin_(tx, ty), tz);
+        const bool a0 = (tx == t_next), a1 = !a0 && (ty == t_next);  // the axis whose boundary is crossed (else z)
+        majorant = (SEL == 1) ? m.x : ((SEL == 2) ? m.y : fmax_(m.x, m.y));
+        const float tau_next = tau_acc + (majorant * (t_next - dda_t));
+        if ((majorant > 0.f) && (tau_next >= tau)) {                  // the division only where its result can be used
+            float t_precise = dda_t + ((tau - tau_acc) / majorant);
+            if (t_precise < maxt) { dda_t = t_precise; reached = true; break; }
+        }
+        dda_t = t_next;
+        if (!(t_next < maxt)) break;
+        const int left = a0 ? rx : (a1 ? ry : rz);
+        if (left == 0) break;
+        const bool a2 = !a0 && !a1;
+        rx -= a0 ? 1 : 0; ry -= a1 ? 1 : 0; rz -= a2 ? 1 : 0;
+        tx = a0 ? (tx + dx) : tx; ty = a1 ? (ty + dy) : ty; tz = a2 ? (tz + dz) : tz;
+        ci += a0 ? stx : (a1 ? sty : stz);
+        tau_acc = tau_next;
+    }
+    maj_out = majorant;
+    return reached ? dda_t : inf_();
+}
+
+// the walk of the specification as written (K = 1), or K cells at a time
 template <int SEL>
 __device__ __forceinline__ float dda_sample(const SceneK &S, const GridKS &G, V3 o, V3 d, V3 id, float mint, float maxt, float tau,
                                             float &maj_out) {

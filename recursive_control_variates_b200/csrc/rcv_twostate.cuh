@@ -48,7 +48,7 @@ __device__ __forceinline__ void sample_interaction2(const SceneK &S, const GRID 
     float tau = -spec_log(1.f - u);                                   // :24
     float t;
     float m_cell = 0.f;
-    if constexpr (GRID::kSupergrid) t = active ? dda_sample<MODE>(S, G, o, d, id, mint, maxt, tau, m_cell) : inf_();   // :25-70
+    if constexpr (GRID::kSupergrid) t = active ? ((RCV_DDA_LIN_TWOSTATE) ? dda_sample_lin<MODE>(S, G, o, d, id, mint, maxt, tau, m_cell) : dda_sample<MODE>(S, G, o, d, id, mint, maxt, tau, m_cell)) : inf_();   // :25-70
     else t = mint + (tau * inv_mu);                                   // :78
     bool valid = active && (t <= maxt);                               // :80
     m.t = valid ? t : inf_();                                         // :88

@@ -37,7 +37,7 @@ __device__ __forceinline__ void sample_interaction1(const SceneK &S, const GRID 
     float tau = -spec_log(1.f - u);
     float t;
     float m_cell = 0.f;
-    if constexpr (GRID::kSupergrid) t = active ? dda_sample<2>(S, G, o, d, id, mint, maxt, tau, m_cell) : inf_();
+    if constexpr (GRID::kSupergrid) t = active ? ((RCV_DDA_LIN_VPS) ? dda_sample_lin<2>(S, G, o, d, id, mint, maxt, tau, m_cell) : dda_sample<2>(S, G, o, d, id, mint, maxt, tau, m_cell)) : inf_();
     else t = mint + (tau * inv_mu);
     m.valid = active && (t <= maxt);
     m.t = m.valid ? t : inf_();
@@ -61,7 +61,7 @@ __device__ __forceinline__ void sample_interaction1_issue(const SceneK &S, const
     float tau = -spec_log(1.f - u);
     float t;
     float m_cell = 0.f;
-    if constexpr (GRID::kSupergrid) t = active ? dda_sample<2>(S, G, o, d, id, mint, maxt, tau, m_cell) : inf_();
+    if constexpr (GRID::kSupergrid) t = active ? ((RCV_DDA_LIN_VPS) ? dda_sample_lin<2>(S, G, o, d, id, mint, maxt, tau, m_cell) : dda_sample<2>(S, G, o, d, id, mint, maxt, tau, m_cell)) : inf_();
     else t = mint + (tau * inv_mu);
     m.valid = active && (t <= maxt);
     m.t = m.valid ? t : inf_();
