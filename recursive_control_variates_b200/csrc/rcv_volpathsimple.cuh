@@ -386,6 +386,17 @@ __device__ __forceinline__ void vps_trace(const SceneK &S, const GRID &G, const 
 // algorithm.  Tentative collisions t_i are sampled with the volume's majorant; w_i = prod_{j<i} (1 - sigma_t(t_j) / mu)
 // estimates the transmittance up to t_i; one t_i is kept with probability proportional to w_i and the estimate carries
 // (sum_i w_i) / mu.  Two secondary-sampler draws per tentative collision (distance, selection).
+//
+// RCV_DRT_AHEAD = K > 1 (build option; no measurable difference on the reference-default line, profiles/README.md r2al,
+// so the default is the plain loop): where the tentative collisions fall depends on the secondary sampler alone (one majorant for
+// the volume), not on the densities read there, so the walk is taken K collisions at a time — K positions and selection
+// draws from a copy of the sampler, K bricks requested together — and the weights are then accumulated in order with
+// the plain loop's tests.  When the walk stops inside a group the sampler is set to where the plain loop would have
+// left it (two draws per completed collision, one for the distance that overshoots).  Same values, same order; the
+// interpolation set-up is computed again when a brick is consumed rather than kept in registers.
+#ifndef RCV_DRT_AHEAD
+#define RCV_DRT_AHEAD 1
+#endif
 template <class GRID>
 __device__ __forceinline__ float sample_interaction_drt(const SceneK &S, const GRID &G, float mu, float inv_mu, Pcg &alt, V3 o, V3 d,
                                                         V3 id, float ray_maxt, bool active, float &sel_t, VpsCounts &cnt) {
@@ -393,6 +404,53 @@ __device__ __forceinline__ float sample_interaction_drt(const SceneK &S, const G
     active = medium_interval(S, o, d, id, ray_maxt, mint, maxt) && active;
     sel_t = inf_();
     float wsum = 0.f, w = 1.f, t = mint;
+#if RCV_DRT_AHEAD > 1
+    constexpr int K = RCV_DRT_AHEAD;
+    while (active) {
+        Pcg r = alt;
+        float tk[K], xik[K];
+        Brick1 bk[K];
+        int n = 0;                                                    // collisions of this group inside the interval
+        bool over = false;                                            // the group ends with a distance beyond maxt
+        float tt = t;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            tk[k] = 0.f; xik[k] = 0.f;
+            if (!over) {
+                float u = pcg_f32(r);
+                tt = tt + ((-spec_log(1.f - u)) * inv_mu);
+                if (!(tt <= maxt)) over = true;
+                else {
+                    xik[k] = pcg_f32(r);
+                    tk[k] = tt;
+                    Tri T = tri_setup(S, G, ray_at(o, d, tt));
+                    sigma1_issue(G, T, bk[k]);
+                    n = k + 1;
+                }
+            }
+        }
+        int used = 0;                                                 // collisions consumed before the walk stopped
+        bool dead = false;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (k < n && !dead) {
+                t = tk[k];
+                wsum = wsum + w;
+                if (xik[k] * wsum <= w) sel_t = t;
+                Tri T = tri_setup(S, G, ray_at(o, d, t));
+                float st = sigma1_finish(S, T, bk[k]);
+                cnt.coll++;
+                w = w * ((mu - st) * inv_mu);
+                used = k + 1;
+                if (!(w > 0.f)) dead = true;
+            }
+        }
+        // the sampler after `used` collisions, plus the overshooting distance draw if the walk got that far
+        const int draws = 2 * used + ((!dead && over) ? 1 : 0);
+        for (int q = 0; q < draws; ++q) (void) pcg_f32(alt);
+        if (dead || over) break;
+    }
+#else
     while (active) {
         float u = pcg_f32(alt);
         t = t + ((-spec_log(1.f - u)) * inv_mu);
@@ -406,6 +464,7 @@ __device__ __forceinline__ float sample_interaction_drt(const SceneK &S, const G
         w = w * ((mu - st) * inv_mu);
         if (!(w > 0.f)) break;
     }
+#endif
     return wsum * inv_mu;
 }
 
