@@ -320,12 +320,9 @@ def emu_spec():
     return _load_emu("librcv_emu_spec.so")
 
 
-@pytest.mark.parametrize("factor", [0, 4])
-def test_speculative_collisions_change_nothing(oracle, emu, emu_spec, factor):
-    """RCV_SPEC_COLLIDE: the second tentative collision of a call is sampled on a copy of the lane's stream as if the
-    first were a null collision, and dropped otherwise.  Film accumulators, gradients and every counter are
-    bit-identical with and without it — main path and shadow rays, Russian roulette active (rr_depth 2: no
-    speculation on the two-state main path then), with and without the majorant supergrid."""
+def _every_output(lib, oracle, factor):
+    """Two-state accumulators (modes 0 and 2), adjoint gradients and DRT-stage gradients with all counters, of one build
+    of the machines on a fixed small scene (Russian roulette active, dense enough for long shadow rays)."""
     from recursive_control_variates_b200.scene import SceneConfig
     from recursive_control_variates_b200.synthetic import make_medium
     d = SceneConfig(width=24, height=20, max_depth=16, rr_depth=2, sigma_t_scale=30.0).to_desc()
@@ -334,30 +331,57 @@ def test_speculative_collisions_change_nothing(oracle, emu, emu_spec, factor):
     H, W = d.film_height, d.film_width
     grad_img = (np.random.default_rng(3).standard_normal((H, W, 3)) / (H * W * 3)).astype(np.float32)
     film_w = oracle.film_weights(d, 77, 3)
-    res = []
-    for lib in (emu, emu_spec):
-        out = []
-        for mode in (0, 2):
-            a_old = np.zeros((H, W, 4), np.float32); a_new = np.zeros_like(a_old); cnt = np.zeros(8, np.uint64)
-            if factor:
-                lib.emu_twostates_sg(C.addressof(d), so, ao, sn, an, *sn.shape[:3], 5, 3, mode, factor, a_old, a_new, cnt)
-            else:
-                lib.emu_twostates(C.addressof(d), so, ao, sn, an, *sn.shape[:3], 5, 3, mode, a_old, a_new, cnt)
-            out += [a_old, a_new, cnt]
-        acc = np.zeros((H, W, 4), np.float32)
-        g1 = np.zeros((*sn.shape[:3], 1), np.float32); g4 = np.zeros((*sn.shape[:3], 4), np.float32); cnt = np.zeros(8, np.uint64)
-        args = (C.addressof(d), sn, an, *sn.shape[:3], 77, 3, 1, oracle.alt_seed(77), grad_img.ctypes.data, film_w.ctypes.data,
-                acc, g1, g4, cnt)
+    out = []
+    for mode in (0, 2):
+        a_old = np.zeros((H, W, 4), np.float32); a_new = np.zeros_like(a_old); cnt = np.zeros(8, np.uint64)
         if factor:
-            lib.emu_vps_sg(*args, factor)
+            lib.emu_twostates_sg(C.addressof(d), so, ao, sn, an, *sn.shape[:3], 5, 3, mode, factor, a_old, a_new, cnt)
         else:
-            lib.emu_vps(*args)
-        out += [g1, g4, cnt]
-        d1 = np.zeros_like(g1); d4 = np.zeros_like(g4); dcnt = np.zeros(8, np.uint64)
-        lib.emu_vps_drt_stages(C.addressof(d), sn, an, *sn.shape[:3], 77, 3, oracle.alt_seed(77), grad_img.ctypes.data,
-                               film_w.ctypes.data, d1, d4, dcnt, factor, 1)
-        out += [d1, d4, dcnt]
-        res.append(out)
+            lib.emu_twostates(C.addressof(d), so, ao, sn, an, *sn.shape[:3], 5, 3, mode, a_old, a_new, cnt)
+        out += [a_old, a_new, cnt]
+    acc = np.zeros((H, W, 4), np.float32)
+    g1 = np.zeros((*sn.shape[:3], 1), np.float32); g4 = np.zeros((*sn.shape[:3], 4), np.float32); cnt = np.zeros(8, np.uint64)
+    args = (C.addressof(d), sn, an, *sn.shape[:3], 77, 3, 1, oracle.alt_seed(77), grad_img.ctypes.data, film_w.ctypes.data,
+            acc, g1, g4, cnt)
+    if factor:
+        lib.emu_vps_sg(*args, factor)
+    else:
+        lib.emu_vps(*args)
+    out += [g1, g4, cnt]
+    d1 = np.zeros_like(g1); d4 = np.zeros_like(g4); dcnt = np.zeros(8, np.uint64)
+    lib.emu_vps_drt_stages(C.addressof(d), sn, an, *sn.shape[:3], 77, 3, oracle.alt_seed(77), grad_img.ctypes.data,
+                           film_w.ctypes.data, d1, d4, dcnt, factor, 1)
+    out += [d1, d4, dcnt]
+    return out
+
+
+@pytest.mark.parametrize("factor", [0, 4])
+def test_speculative_collisions_change_nothing(oracle, emu, emu_spec, factor):
+    """RCV_SPEC_COLLIDE: the second tentative collision of a call is sampled on a copy of the lane's stream as if the
+    first were a null collision, and dropped otherwise.  Film accumulators, gradients and every counter are
+    bit-identical with and without it — main path and shadow rays, Russian roulette active (rr_depth 2: no
+    speculation on the two-state main path then), with and without the majorant supergrid."""
+    res = [_every_output(lib, oracle, factor) for lib in (emu, emu_spec)]
+    for a, b in zip(*res):
+        assert np.array_equal(a, b)
+    assert res[0][0].any() and res[0][6].any() and res[0][9].any()
+
+
+@pytest.fixture(scope="module")
+def emu_walks():
+    """The same machines with the non-default walks: RCV_DDA_LIN_TWOSTATE=0, RCV_DDA_LIN_VPS=1, RCV_DDA_AHEAD=3,
+    RCV_DRT_AHEAD=3."""
+    return _load_emu("librcv_emu_walks.so")
+
+
+@pytest.mark.parametrize("factor", [2, 4, 0])
+def test_walk_variants_change_nothing(oracle, emu, emu_walks, factor):
+    """The supergrid walk exists in three spellings — the loop of the specification (dda_sample, K = 1), K cells at a
+    time with their majorants in flight together (RCV_DDA_AHEAD), and with a linear cell index, steps-left counters and
+    select-based stepping (dda_sample_lin) — and the DRT walk in two (RCV_DRT_AHEAD).  Which machine uses which is a
+    build option; every spelling gives the same accumulators, gradients and counters bit for bit (factor 0: only the
+    DRT walk differs)."""
+    res = [_every_output(lib, oracle, factor) for lib in (emu, emu_walks)]
     for a, b in zip(*res):
         assert np.array_equal(a, b)
     assert res[0][0].any() and res[0][6].any() and res[0][9].any()
