@@ -590,13 +590,7 @@ __device__ __forceinline__ void vp_nee_records_warp(const SceneK &S, const GridK
     const unsigned long long rec_bits = (unsigned long long) sk.coop_rec;
     for (int base = 0; base < total; base += 32) {
         const int j = base + lane;
-        int own = 0;                                                   // the last thread whose list starts at or before j
-#pragma unroll
-        for (int step = 16; step >= 1; step >>= 1) {
-            const int cand = own + step;
-            const int e = __shfl_sync(full, excl, cand & 31);
-            if (cand < 32 && e <= j) own = cand;
-        }
+        const int own = concat_owner(j, [&](int t) { return __shfl_sync(full, excl, t); });   // every thread takes part
         const int first = __shfl_sync(full, excl, own);
         const float4 *rec = (const float4 *) __shfl_sync(full, rec_bits, own);
         const V3 adj = mk3(__shfl_sync(full, sk.coop_adj.x, own), __shfl_sync(full, sk.coop_adj.y, own),

@@ -337,6 +337,22 @@ __device__ __forceinline__ void vp_post_vertex(const SceneK &S, VpLane &ln, VpSi
     ln.ev = EV_COLL;
 }
 
+// Lists of n[0], ..., n[31] items laid end to end (vp_nee_records_warp in rcv_trace.cu: thread t holds the exclusive
+// prefix sum excl[t]): the owner of item j is the LAST t with excl[t] <= j — empty lists share their start with the
+// next one, so the last one is the list that holds j.  Five-step search; `excl_of(t)` reads thread t's prefix sum (a
+// shuffle on the device, an array on the host where the tests run it).  j beyond the total gives 31.
+template <class F>
+__device__ __forceinline__ int concat_owner(int j, F excl_of) {
+    int own = 0;
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+        const int cand = own + step;
+        const int e = excl_of(cand & 31);
+        if (cand < 32 && e <= j) own = cand;
+    }
+    return own;
+}
+
 // one recorded collision of a shadow ray: adjoint * d log(tr) / d sigma_t at its position (:496-505)
 __device__ __forceinline__ void vp_nee_record_scatter(const SceneK &S, const GridK &G, VpSink &sk, V3 adjoint, float4 c) {
     float g = 0.f;

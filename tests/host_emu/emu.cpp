@@ -292,6 +292,8 @@ void run_surface(const SceneK &S, const GRID &G, SfSink &sk) {
 extern "C" {
 
 void emu_set_flat(int on) { g_flat = on; }
+// concat_owner (rcv_volpathsimple_wf.cuh) over an array of 32 exclusive prefix sums
+int emu_concat_owner(const int *excl, int j) { return concat_owner(j, [&](int t) { return excl[t]; }); }
 
 // scenes with rectangles: the two-state / single-state primal (adj == 0; mode as emu_twostates) or the inherited
 // prbvolpath adjoint of state `new` (adj == 1)

@@ -33,6 +33,8 @@ def _load_emu(name):
     lib.emu_vps_backward_lane.argtypes = [C.c_void_p, f32, f32, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32,
                                           C.c_void_p, C.c_void_p, f32, f32, u64, C.c_int, C.c_int]
     lib.emu_set_flat.argtypes = [C.c_int]
+    lib.emu_concat_owner.argtypes = [np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS"), C.c_int]
+    lib.emu_concat_owner.restype = C.c_int
     lib.emu_vps_drt_stages.argtypes = [C.c_void_p, f32, f32, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32,
                                        C.c_void_p, C.c_void_p, f32, f32, u64, C.c_int, C.c_int]
     return lib
@@ -385,6 +387,24 @@ def test_walk_variants_change_nothing(oracle, emu, emu_walks, factor):
     for a, b in zip(*res):
         assert np.array_equal(a, b)
     assert res[0][0].any() and res[0][6].any() and res[0][9].any()
+
+
+def test_owner_search_of_the_warp_wide_record_scatter(emu):
+    """vp_nee_records_warp (rcv_trace.cu) lays the shadow-ray record lists of a slow step end to end and gives every
+    thread each 32nd record; concat_owner finds whose list a position falls into from the 32 exclusive prefix sums —
+    the same function runs here over an array instead of shuffles.  Empty lists, one long list, all lists full."""
+    rng = np.random.default_rng(11)
+    cases = [rng.integers(0, 65, 32) * (rng.random(32) < p) for p in (0.1, 0.5, 1.0) for _ in range(20)]
+    cases += [np.zeros(32, int), np.full(32, 64), np.eye(32, dtype=int)[0] * 64, np.eye(32, dtype=int)[31] * 7]
+    for n in cases:
+        n = np.asarray(n, np.int64)
+        excl = np.ascontiguousarray(np.concatenate([[0], np.cumsum(n)[:-1]]).astype(np.int32))
+        total = int(n.sum())
+        owner_of = np.repeat(np.arange(32), n)
+        for j in range(total):
+            assert emu.emu_concat_owner(excl, j) == owner_of[j]
+        if total:
+            assert emu.emu_concat_owner(excl, total + 5) == 31         # past the end: any valid thread (its record is not read)
 
 
 def test_gradient_bricks_and_voxel_reductions_agree(oracle, emu, emu_voxelreds, setup):
